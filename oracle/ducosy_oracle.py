@@ -1,0 +1,381 @@
+"""CPU oracle for the DuCoSy-GAN hot path  --  TEST INFRASTRUCTURE ONLY.
+
+This file is a CPU restatement (plain torch fp32 functional ops + numpy) of the
+reference algorithm for the dual-HU synthesis path.  It exists so that the CUDA
+product in ``ducosy_gan_b200/`` can be checked; it is never part of the product
+path.  Only ``tests/``, ``__graft_entry__.smoke()`` and ``bench.py``'s
+``cpu_baseline`` / ``--impl reference`` legs may import it.
+
+Parity status
+-------------
+* generator / discriminator / windowing / de-windowing / composite / HU
+  threshold candidates: PINNED against the reference itself.  ``oracle/make_golden.py``
+  imports ``/root/reference/modules/{model,preprocess}.py`` (and executes the
+  composite statements of ``generate.py:140-145,218-237``) in the authoring
+  container and commits small input/output vectors under ``tests/golden/``;
+  ``tests/test_oracle_golden.py`` replays them against this file.
+* SSIM (``ssim``): "parity unpinned" -- the reference delegates to the third
+  party ``pytorch_msssim`` package (unpinned in ``requirements.txt:28``, not
+  vendored, not installed here).  The restatement follows the package's
+  published algorithm (gaussian 11/1.5, valid conv, C1/C2 from data_range).
+
+Every function cites the reference ``file:line`` it follows.
+"""
+from __future__ import annotations
+
+import math
+import zlib
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+# HU ranges of the two CycleGANs (modules/argmanager.py:121-152).
+SOFT_HU = (-150.0, 250.0)
+LUNG_HU = (-1000.0, -150.0)
+
+
+# --------------------------------------------------------------------------------------
+# deterministic, RNG-library-independent weights (no shipped checkpoints: SURVEY 8c)
+# --------------------------------------------------------------------------------------
+def _param_rng(seed: int, name: str) -> np.random.Generator:
+    return np.random.Generator(np.random.PCG64([seed, zlib.crc32(name.encode())]))
+
+
+def generator_param_shapes(input_channels=1, num_residual_blocks=9, use_cbam=True):
+    """state_dict key -> shape, in the reference's order (modules/model.py:92-113)."""
+    shapes = {}
+    shapes["model.1.weight"] = (64, input_channels, 7, 7)
+    shapes["model.1.bias"] = (64,)
+    shapes["model.4.weight"] = (128, 64, 3, 3)
+    shapes["model.4.bias"] = (128,)
+    shapes["model.7.weight"] = (256, 128, 3, 3)
+    shapes["model.7.bias"] = (256,)
+    idx = 10
+    for _ in range(num_residual_blocks):
+        for j in (1, 5):
+            shapes[f"model.{idx}.block.{j}.weight"] = (256, 256, 3, 3)
+            shapes[f"model.{idx}.block.{j}.bias"] = (256,)
+        if use_cbam:
+            shapes[f"model.{idx}.cbam.channel_attention.fc.0.weight"] = (16, 256, 1, 1)
+            shapes[f"model.{idx}.cbam.channel_attention.fc.2.weight"] = (256, 16, 1, 1)
+            shapes[f"model.{idx}.cbam.spatial_attention.conv.weight"] = (1, 2, 7, 7)
+        idx += 1
+    shapes[f"model.{idx + 1}.weight"] = (128, 256, 3, 3)
+    shapes[f"model.{idx + 1}.bias"] = (128,)
+    shapes[f"model.{idx + 5}.weight"] = (64, 128, 3, 3)
+    shapes[f"model.{idx + 5}.bias"] = (64,)
+    shapes[f"model.{idx + 9}.weight"] = (1, 64, 7, 7)
+    shapes[f"model.{idx + 9}.bias"] = (1,)
+    return shapes
+
+
+def discriminator_param_shapes(input_channels=1):
+    """modules/model.py:120-129."""
+    chans = [(64, input_channels), (128, 64), (256, 128), (512, 256), (1, 512)]
+    shapes = {}
+    for key, (co, ci) in zip((0, 2, 5, 8, 12), chans):
+        shapes[f"model.{key}.weight"] = (co, ci, 4, 4)
+        shapes[f"model.{key}.bias"] = (co,)
+    return shapes
+
+
+def make_state_dict(shapes: dict, seed: int, weight_std: float = 0.02, attn_std: float | None = None):
+    """Weights ~ N(0, weight_std) as weights_init_normal does (modules/model.py:134-140); biases
+    uniform in +-0.05.  Drawn with numpy PCG64 keyed by (seed, key) so the same tensors can be
+    rebuilt anywhere without shipping a checkpoint.  ``attn_std`` optionally gives the CBAM convs a
+    larger spread so the attention maps are not all ~0.5 (exercises the sigmoid properly)."""
+    sd = {}
+    for name, shape in shapes.items():
+        rng = _param_rng(seed, name)
+        if name.endswith("bias"):
+            a = rng.uniform(-0.05, 0.05, size=shape)
+        else:
+            std = weight_std
+            if attn_std is not None and "cbam" in name:
+                std = attn_std
+            a = rng.standard_normal(size=shape) * std
+        sd[name] = torch.from_numpy(a.astype(np.float32))
+    return sd
+
+
+# --------------------------------------------------------------------------------------
+# model restatement (modules/model.py)
+# --------------------------------------------------------------------------------------
+def instance_norm(x: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
+    """nn.InstanceNorm2d defaults: biased variance, eps 1e-5, no affine, no running stats
+    (modules/model.py:61,75,79,94,97,110)."""
+    mean = x.mean(dim=(2, 3), keepdim=True)
+    var = x.var(dim=(2, 3), unbiased=False, keepdim=True)
+    return (x - mean) / torch.sqrt(var + eps)
+
+
+def channel_attention(x, w_fc0, w_fc2):
+    """modules/model.py:20-24."""
+    avg = x.mean(dim=(2, 3), keepdim=True)
+    mx = x.amax(dim=(2, 3), keepdim=True)
+
+    def fc(v):
+        return F.conv2d(F.relu(F.conv2d(v, w_fc0)), w_fc2)
+
+    return x * torch.sigmoid(fc(avg) + fc(mx))
+
+
+def spatial_attention(x, w_conv):
+    """modules/model.py:34-39."""
+    avg = x.mean(dim=1, keepdim=True)
+    mx = x.amax(dim=1, keepdim=True)
+    att = torch.sigmoid(F.conv2d(torch.cat([avg, mx], dim=1), w_conv, padding=w_conv.shape[-1] // 2))
+    return x * att
+
+
+def residual_block(x, sd, prefix, use_cbam=True):
+    """modules/model.py:56-65 (plain) and 68-87 (CBAM)."""
+    h = F.pad(x, (1, 1, 1, 1), mode="reflect")
+    h = F.conv2d(h, sd[f"{prefix}.block.1.weight"], sd[f"{prefix}.block.1.bias"])
+    h = F.relu(instance_norm(h))
+    h = F.pad(h, (1, 1, 1, 1), mode="reflect")
+    h = F.conv2d(h, sd[f"{prefix}.block.5.weight"], sd[f"{prefix}.block.5.bias"])
+    h = instance_norm(h)
+    if use_cbam:
+        h = channel_attention(h, sd[f"{prefix}.cbam.channel_attention.fc.0.weight"],
+                              sd[f"{prefix}.cbam.channel_attention.fc.2.weight"])
+        h = spatial_attention(h, sd[f"{prefix}.cbam.spatial_attention.conv.weight"])
+    return x + h
+
+
+def generator_forward(sd, x, num_residual_blocks=9, use_cbam=True, return_intermediates=False):
+    """Generator.forward (modules/model.py:92-115).  x: [B,Cin,H,W] fp32."""
+    inter = {}
+    h = F.pad(x, (3, 3, 3, 3), mode="reflect")
+    h = F.conv2d(h, sd["model.1.weight"], sd["model.1.bias"])
+    h = F.relu(instance_norm(h))
+    inter["stem"] = h
+    h = F.relu(instance_norm(F.conv2d(h, sd["model.4.weight"], sd["model.4.bias"], stride=2, padding=1)))
+    inter["down1"] = h
+    h = F.relu(instance_norm(F.conv2d(h, sd["model.7.weight"], sd["model.7.bias"], stride=2, padding=1)))
+    inter["down2"] = h
+    idx = 10
+    for _ in range(num_residual_blocks):
+        h = residual_block(h, sd, f"model.{idx}", use_cbam)
+        inter[f"block{idx}"] = h
+        idx += 1
+    for _ in range(2):
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+        h = F.conv2d(h, sd[f"model.{idx + 1}.weight"], sd[f"model.{idx + 1}.bias"], padding=1)
+        h = F.relu(instance_norm(h))
+        inter[f"up{idx}"] = h
+        idx += 4
+    h = F.pad(h, (3, 3, 3, 3), mode="reflect")
+    h = torch.tanh(F.conv2d(h, sd[f"model.{idx + 1}.weight"], sd[f"model.{idx + 1}.bias"]))
+    if return_intermediates:
+        return h, inter
+    return h
+
+
+def discriminator_forward(sd, x):
+    """Discriminator.forward (modules/model.py:120-131)."""
+    h = F.leaky_relu(F.conv2d(x, sd["model.0.weight"], sd["model.0.bias"], stride=2, padding=1), 0.2)
+    for key in (2, 5, 8):
+        h = F.conv2d(h, sd[f"model.{key}.weight"], sd[f"model.{key}.bias"], stride=2, padding=1)
+        h = F.leaky_relu(instance_norm(h), 0.2)
+    h = F.pad(h, (1, 0, 1, 0))
+    return F.conv2d(h, sd["model.12.weight"], sd["model.12.bias"], padding=1)
+
+
+# --------------------------------------------------------------------------------------
+# HU windowing / de-windowing / composite / threshold candidates (numpy, float32 like the reference)
+# --------------------------------------------------------------------------------------
+def stored_to_hu(px: np.ndarray, slope: float, intercept: float) -> np.ndarray:
+    """modules/preprocess.py:72-75 and generate.py:140-145: float32 px * slope + intercept."""
+    image = px.astype(np.float32)
+    return image * float(slope) + float(intercept)
+
+
+def hu_window(px, slope, intercept, hu_min, hu_max) -> np.ndarray:
+    """Linear inference windowing, modules/preprocess.py:72-84:  clip then 2*(x-lo)/(hi-lo)-1."""
+    image = stored_to_hu(px, slope, intercept)
+    image = np.clip(image, hu_min, hu_max)
+    return 2 * (image - hu_min) / (hu_max - hu_min) - 1
+
+
+def soft_squeeze_window(px, slope, intercept, hu_min, hu_max, sigma=50):
+    """Training-side windowing, modules/preprocess.py:6-40,43-55 (apply_hu_transform with soft squeezing)."""
+    image = stored_to_hu(px, slope, intercept)
+    image = np.clip(image, hu_min, hu_max)
+    normalized = (image - hu_min) / (hu_max - hu_min)
+    threshold = 0.9
+    k = 10.0 / sigma
+    soft_mask = 1.0 / (1.0 + np.exp(-k * (normalized - threshold)))
+    result = np.where(normalized < threshold, normalized, threshold + (1.0 - threshold) * soft_mask)
+    return 2.0 * result - 1.0
+
+
+def dewindow_to_stored(y: np.ndarray, slope, intercept, hu_min, hu_max, dtype=np.int16) -> np.ndarray:
+    """postprocess_tensor, modules/preprocess.py:96-111: (y+1)/2*(hi-lo)+lo -> (hu-b)/m -> astype (truncation)."""
+    y = np.asarray(y, dtype=np.float32)
+    denorm = (y + 1.0) / 2.0 * (hu_max - hu_min) + hu_min
+    new_px = (denorm - float(intercept)) / float(slope)
+    return new_px.astype(dtype)
+
+
+def composite(raw_px, soft_px, lung_px, slope, intercept, soft_hu=SOFT_HU, lung_hu=LUNG_HU):
+    """generate.py:213-237: start from the NCCT stored values, overwrite the soft-tissue HU range
+    with the soft-tissue generator's pixels, then the lung range with the lung generator's
+    (so lung wins where the ranges touch, HU == -150).  Returns (merged, soft_mask, lung_mask)."""
+    merged = raw_px.copy()
+    hu = stored_to_hu(raw_px, slope, intercept)
+    soft_mask = np.logical_and(hu >= soft_hu[0], hu <= soft_hu[1])
+    lung_mask = np.logical_and(hu >= lung_hu[0], hu <= lung_hu[1])
+    merged[soft_mask] = soft_px[soft_mask]
+    merged[lung_mask] = lung_px[lung_mask]
+    return merged, soft_mask, lung_mask
+
+
+def threshold_candidates(hu: np.ndarray):
+    """HU threshold candidates of the anatomical mask generator:
+    body hu>-1000, lung -1000<=hu<=-300 & body (mask_generator.py:14-20), bone hu>=200 & body
+    (mask_generator.py:179-183).  Returns uint8 (body, lung, bone)."""
+    body = (hu > -1000).astype(np.uint8)
+    lung = np.logical_and(np.logical_and(hu >= -1000, hu <= -300).astype(np.uint8), body).astype(np.uint8)
+    bone = np.logical_and((hu >= 200).astype(np.uint8), body).astype(np.uint8)
+    return body, lung, bone
+
+
+def dual_hu_synthesize(raw_px, slope, intercept, sd_soft, sd_lung, num_residual_blocks=9, use_cbam=True,
+                       return_parts=False):
+    """The whole north-star path for a volume [S,H,W] of stored values:
+    generate.py:89-102 (window -> 2 generators -> de-window) then generate.py:213-237 (composite)."""
+    S = raw_px.shape[0]
+    merged = np.empty_like(raw_px)
+    ys, yl = [], []
+    with torch.no_grad():
+        for i in range(S):
+            xs = torch.from_numpy(hu_window(raw_px[i], slope, intercept, *SOFT_HU).astype(np.float32))[None, None]
+            xl = torch.from_numpy(hu_window(raw_px[i], slope, intercept, *LUNG_HU).astype(np.float32))[None, None]
+            y_soft = generator_forward(sd_soft, xs, num_residual_blocks, use_cbam)[0, 0].numpy()
+            y_lung = generator_forward(sd_lung, xl, num_residual_blocks, use_cbam)[0, 0].numpy()
+            soft_px = dewindow_to_stored(y_soft, slope, intercept, *SOFT_HU, dtype=raw_px.dtype)
+            lung_px = dewindow_to_stored(y_lung, slope, intercept, *LUNG_HU, dtype=raw_px.dtype)
+            merged[i] = composite(raw_px[i], soft_px, lung_px, slope, intercept)[0]
+            ys.append(y_soft)
+            yl.append(y_lung)
+    if return_parts:
+        return merged, np.stack(ys), np.stack(yl)
+    return merged
+
+
+# --------------------------------------------------------------------------------------
+# synthetic inputs
+# --------------------------------------------------------------------------------------
+def synthetic_volume(S: int, H: int = 512, W: int = 512, seed: int = 0) -> np.ndarray:
+    """Stored pixels uniform in [0,2500) (slope 1, intercept -1024 => HU in [-1024,1475])."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    return rng.integers(0, 2500, size=(S, H, W), dtype=np.int16)
+
+
+def phantom_volume(S: int, H: int = 512, W: int = 512, seed: int = 0) -> np.ndarray:
+    """Structured chest phantom: air, two lung ellipses, body ellipse, spine disc (stored values, intercept -1024)."""
+    rng = np.random.Generator(np.random.PCG64(seed + 77))
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cy, cx = H / 2, W / 2
+    vol = np.empty((S, H, W), np.float32)
+    for s in range(S):
+        hu = np.full((H, W), -1000.0, np.float32)
+        body = ((yy - cy) / (0.36 * H)) ** 2 + ((xx - cx) / (0.44 * W)) ** 2 <= 1
+        hu[body] = 40 + 30 * rng.standard_normal(int(body.sum())).astype(np.float32)
+        for sgn in (-1, 1):
+            lung = ((yy - cy) / (0.22 * H)) ** 2 + ((xx - (cx + sgn * 0.2 * W)) / (0.14 * W)) ** 2 <= 1
+            hu[lung] = -800 + 60 * rng.standard_normal(int(lung.sum())).astype(np.float32)
+        spine = (yy - (cy + 0.22 * H)) ** 2 + (xx - cx) ** 2 <= (0.05 * H) ** 2
+        hu[spine] = 400 + 100 * rng.standard_normal(int(spine.sum())).astype(np.float32)
+        vol[s] = hu
+    return np.clip(np.rint(vol + 1024.0), 0, 4095).astype(np.int16)
+
+
+# --------------------------------------------------------------------------------------
+# losses (modules/trainer.py:22-184) -- restated for the training-step rows
+# --------------------------------------------------------------------------------------
+def gradient_loss(pred, target):
+    """GradientLoss, modules/trainer.py:29-40."""
+    pdy = torch.abs(pred[:, :, 1:, :] - pred[:, :, :-1, :])
+    pdx = torch.abs(pred[:, :, :, 1:] - pred[:, :, :, :-1])
+    tdy = torch.abs(target[:, :, 1:, :] - target[:, :, :-1, :])
+    tdx = torch.abs(target[:, :, :, 1:] - target[:, :, :, :-1])
+    return torch.mean(torch.abs(pdy - tdy)) + torch.mean(torch.abs(pdx - tdx))
+
+
+def _gauss_window(size=11, sigma=1.5):
+    coords = torch.arange(size, dtype=torch.float32) - size // 2
+    g = torch.exp(-(coords ** 2) / (2 * sigma ** 2))
+    return g / g.sum()
+
+
+def ssim(x, y, data_range=1.0, size=11, sigma=1.5):
+    """pytorch_msssim.SSIM(data_range=1.0,size_average=True,channel=1) as called at
+    modules/trainer.py:351,485.  PARITY UNPINNED (third-party package absent): separable valid
+    gaussian filtering, C1=(0.01L)^2, C2=(0.03L)^2, mean over the map then over batch."""
+    win = _gauss_window(size, sigma)
+    C = x.shape[1]
+
+    def filt(t):
+        t = F.conv2d(t, win.view(1, 1, -1, 1).repeat(C, 1, 1, 1), groups=C)
+        return F.conv2d(t, win.view(1, 1, 1, -1).repeat(C, 1, 1, 1), groups=C)
+
+    c1, c2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    mu1, mu2 = filt(x), filt(y)
+    s11 = filt(x * x) - mu1 * mu1
+    s22 = filt(y * y) - mu2 * mu2
+    s12 = filt(x * y) - mu1 * mu2
+    cs = (2 * s12 + c2) / (s11 + s22 + c2)
+    ssim_map = ((2 * mu1 * mu2 + c1) / (mu1 * mu1 + mu2 * mu2 + c1)) * cs
+    return ssim_map.flatten(2).mean(-1).mean(1).mean()
+
+
+def contrast_attention_loss(pred, target, source, sigma=0.15, min_w=1.0, max_w=3.0, k=7):
+    """ContrastAttentionLoss, modules/trainer.py:62-86."""
+    blur = lambda t: F.avg_pool2d(t, k, 1, k // 2)
+    pb, tb, sb = blur(pred), blur(target), blur(source)
+    diff = torch.abs(tb - sb)
+    w = min_w + (max_w - min_w) * (1.0 - torch.exp(-diff / sigma))
+    return torch.mean(w * torch.abs(pb - tb))
+
+
+def mse_gan_loss(d_out, is_real: bool):
+    """nn.MSELoss against ones/zeros, modules/trainer.py:347,459-460,470."""
+    tgt = torch.ones_like(d_out) if is_real else torch.zeros_like(d_out)
+    return F.mse_loss(d_out, tgt)
+
+
+def hu_error(y_test, y_ref, hu_min, hu_max):
+    """max-abs error of a tanh-unit output expressed in HU after de-windowing (SURVEY 8d parity gate)."""
+    return float(np.max(np.abs(np.asarray(y_test, np.float64) - np.asarray(y_ref, np.float64)))) * (hu_max - hu_min) / 2.0
+
+
+def contrast_region_loss(pred, target, source, threshold=0.15, weight=1.5):
+    """ContrastRegionLoss, modules/trainer.py:104-130 (ctor values from trainer.py:357)."""
+    pool = lambda t: F.avg_pool2d(t, 8, 8)
+    pp, tp, sp = pool(pred), pool(target), pool(source)
+    mask = torch.sigmoid(5 * ((tp - sp) - threshold))
+    region = torch.mean(mask * torch.abs(pp - tp))
+    dist = torch.abs(pred.mean() - target.mean()) + torch.abs(pred.std() - target.std())
+    return weight * (region + 0.5 * dist)
+
+
+def sobel_edges(img):
+    """ContrastEdgeLoss.get_edges, modules/trainer.py:150-155."""
+    sx = torch.tensor([[-1, 0, 1], [-2, 0, 2], [-1, 0, 1]], dtype=torch.float32).view(1, 1, 3, 3)
+    sy = torch.tensor([[-1, -2, -1], [0, 0, 0], [1, 2, 1]], dtype=torch.float32).view(1, 1, 3, 3)
+    ex = F.conv2d(img, sx, padding=1)
+    ey = F.conv2d(img, sy, padding=1)
+    return torch.sqrt(ex ** 2 + ey ** 2 + 1e-6)
+
+
+def contrast_edge_loss(pred, target, source=None):
+    """ContrastEdgeLoss.forward, modules/trainer.py:157-184: |d mean| + |d std| + |d top-10% mean| of Sobel magnitudes."""
+    pe, te = sobel_edges(pred), sobel_edges(target)
+    stats = torch.abs(pe.mean() - te.mean()) + torch.abs(pe.std() - te.std())
+    k = 0.1
+    ptop = torch.topk(pe.flatten(), int(pe.numel() * k)).values.mean()
+    ttop = torch.topk(te.flatten(), int(te.numel() * k)).values.mean()
+    return stats + torch.abs(ptop - ttop)

@@ -1,0 +1,124 @@
+"""Pins oracle/ducosy_oracle.py against vectors produced by the reference itself
+(oracle/make_golden.py, run in the authoring container against /root/reference)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ducosy_oracle as orc
+
+
+def _load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name), allow_pickle=False)
+
+
+def _x(seed, shape):
+    return torch.from_numpy(np.random.Generator(np.random.PCG64(seed)).uniform(-1, 1, size=shape).astype(np.float32))
+
+
+@pytest.mark.parametrize("name", ["gen_c1_b2_cbam_64", "gen_c3_b1_plain_32", "gen_c2_b1_cbam_128"])
+def test_generator_matches_reference(golden_dir, name):
+    g = _load(golden_dir, name + ".npz")
+    cin, nb, cbam = int(g["cin"]), int(g["blocks"]), bool(g["cbam"])
+    astd = float(g["attn_std"])
+    shapes = orc.generator_param_shapes(cin, nb, cbam)
+    # state_dict layout is the reference's (keys recorded from the reference module)
+    assert list(shapes.keys()) == [str(k) for k in g["keys"]]
+    sd = orc.make_state_dict(shapes, int(g["wseed"]), attn_std=None if astd < 0 else astd)
+    x = _x(int(g["xseed"]), (int(g["B"]), cin, int(g["H"]), int(g["W"])))
+    with torch.no_grad():
+        y = orc.generator_forward(sd, x, nb, cbam).numpy()
+    # same fp32 ops, different composition order of instance-norm => tiny fp32 noise only
+    np.testing.assert_allclose(y, g["y"], rtol=0, atol=2e-5)
+
+
+def test_generator_full_size_matches_reference(golden_dir):
+    g = _load(golden_dir, "gen_full_512.npz")
+    sd = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), int(g["wseed"]), attn_std=float(g["attn_std"]))
+    px = orc.synthetic_volume(1, 512, 512, seed=int(g["vseed"]))[0]
+    x = torch.from_numpy(orc.hu_window(px, 1.0, -1024.0, *orc.SOFT_HU).astype(np.float32))[None, None]
+    with torch.no_grad():
+        y = orc.generator_forward(sd, x)[0, 0].numpy()
+    np.testing.assert_allclose(y[::8, ::8], g["y_sub"], rtol=0, atol=5e-5)
+    assert abs(float(np.abs(y).astype(np.float64).sum()) - float(g["y_abs_sum"])) < 1.0
+
+
+def test_discriminator_matches_reference(golden_dir):
+    g = _load(golden_dir, "disc_64.npz")
+    shapes = orc.discriminator_param_shapes(1)
+    assert list(shapes.keys()) == [str(k) for k in g["keys"]]
+    assert int(g["n_conv_g"]) == 51 and int(g["n_conv_d"]) == 5
+    sd = orc.make_state_dict(shapes, int(g["wseed"]))
+    with torch.no_grad():
+        y = orc.discriminator_forward(sd, _x(int(g["xseed"]), (2, 1, 64, 64))).numpy()
+    np.testing.assert_allclose(y, g["y"], rtol=0, atol=2e-5)
+
+
+def test_hu_window_and_dewindow_bit_exact(golden_dir):
+    g = _load(golden_dir, "hu_window.npz")
+    px = g["px"]
+    for ci in range(3):
+        slope, intercept = float(g[f"slope_{ci}"]), float(g[f"intercept_{ci}"])
+        ws = orc.hu_window(px, slope, intercept, -150, 250)
+        wl = orc.hu_window(px, slope, intercept, -1000, -150)
+        assert ws.dtype == g[f"win_soft_{ci}"].dtype
+        assert np.array_equal(ws, g[f"win_soft_{ci}"])
+        assert np.array_equal(wl, g[f"win_lung_{ci}"])
+        assert np.array_equal(orc.soft_squeeze_window(px, slope, intercept, -150, 250), g[f"sq_soft_{ci}"])
+        assert np.array_equal(orc.soft_squeeze_window(px, slope, intercept, -1000, -150), g[f"sq_lung_{ci}"])
+        assert np.array_equal(ws, g[f"lin_soft_{ci}"])
+        y = g[f"y_{ci}"][0, 0]
+        ps = orc.dewindow_to_stored(y, slope, intercept, -150, 250, np.int16)
+        pl = orc.dewindow_to_stored(y, slope, intercept, -1000, -150, np.int16)
+        assert np.array_equal(ps, g[f"post_soft_{ci}"])
+        assert np.array_equal(pl, g[f"post_lung_{ci}"])
+
+
+def test_composite_bit_exact(golden_dir):
+    g = _load(golden_dir, "composite.npz")
+    for ci in range(3):
+        merged, sm, lm = orc.composite(g[f"raw_{ci}"], g[f"soft_px_{ci}"], g[f"lung_px_{ci}"],
+                                       float(g[f"slope_{ci}"]), float(g[f"intercept_{ci}"]))
+        assert np.array_equal(merged, g[f"merged_{ci}"])
+        assert np.array_equal(sm, g[f"soft_mask_{ci}"])
+        assert np.array_equal(lm, g[f"lung_mask_{ci}"])
+    assert np.array_equal(orc.stored_to_hu(g["edge_px"], 1, 0), g["hu_notags"])
+
+
+def test_composite_edge_table():
+    # px 874/873/24/23/1274/1275 @ slope 1, intercept -1024 => HU -150/-151/-1000/-1001/250/251
+    px = np.array([[874, 873, 24, 23, 1274, 1275]], np.int16)
+    soft = np.full_like(px, 111)
+    lung = np.full_like(px, 222)
+    merged, sm, lm = orc.composite(px, soft, lung, 1.0, -1024.0)
+    assert sm.tolist() == [[True, False, False, False, True, False]]
+    assert lm.tolist() == [[True, True, True, False, False, False]]
+    assert merged.tolist() == [[222, 222, 222, 23, 111, 1275]]   # lung wins at -150; outside both keeps raw
+    assert orc.dewindow_to_stored(np.array([0.0]), 1.0, -1024.0, -150, 250).tolist() == [1074]
+    assert np.array([873.575, -0.7], np.float32).astype(np.int16).tolist() == [873, 0]
+
+
+def test_threshold_candidates_bit_exact(golden_dir):
+    g = _load(golden_dir, "thresholds.npz")
+    body, lung, bone = orc.threshold_candidates(g["hu"])
+    assert np.array_equal(body, g["body"])
+    assert np.array_equal(lung, g["lung"])
+    assert np.array_equal(bone, g["bone"])
+
+
+def test_losses_match_reference(golden_dir):
+    g = _load(golden_dir, "losses.npz")
+    p, t, s = (_x(int(k), (2, 1, 64, 64)) for k in g["seeds"])
+    assert abs(orc.gradient_loss(p, t).item() - float(g["grad"])) < 1e-6
+    assert abs(orc.contrast_attention_loss(p, t, s).item() - float(g["att"])) < 1e-6
+    assert abs(orc.contrast_region_loss(p, t, s).item() - float(g["region"])) < 1e-6
+    assert abs(orc.contrast_edge_loss(p, t, s).item() - float(g["edge"])) < 1e-6
+
+
+def test_ssim_unpinned_restatement_sanity():
+    # PARITY UNPINNED (pytorch_msssim absent): only self-consistency is checked.
+    x = _x(1, (2, 1, 32, 32))
+    assert abs(orc.ssim(x, x).item() - 1.0) < 1e-6
+    assert orc.ssim(x, -x).item() < 0.5
+    assert orc.ssim(x, 0.5 * x).item() < 1.0
