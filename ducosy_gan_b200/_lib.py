@@ -1,0 +1,111 @@
+"""ctypes binding of libducosy_sm100.so (the C ABI declared in include/ducosy.h).
+
+There is no CPU or PyTorch fallback: if the library is missing or a call fails this module raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libducosy_sm100.so")
+
+F16, BF16 = 0, 1
+PAD_ZERO, PAD_REFLECT = 0, 1
+ACT_NONE, ACT_RELU, ACT_LRELU02 = 0, 1, 2
+
+
+class GenConfig(C.Structure):
+    _fields_ = [("input_channels", C.c_int), ("num_residual_blocks", C.c_int), ("use_cbam", C.c_int),
+                ("dtype", C.c_int)]
+
+
+_p, _i, _f, _ll, _sz = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t
+
+# name -> (restype, argtypes); mirrors include/ducosy.h one to one (tests check every symbol resolves)
+SIGNATURES = {
+    "ducosy_version": (_i, []),
+    "ducosy_last_error": (C.c_char_p, []),
+    "ducosy_check_device": (_i, []),
+    "ducosy_hu_window": (_i, [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p]),
+    "ducosy_hu_thresholds": (_i, [_p, _p, _p, _p, _ll, _f, _f, _p]),
+    "ducosy_dewindow_composite": (_i, [_p, _p, _p, _p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p]),
+    "ducosy_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_pack_stem_weight": (_i, [_p, _p, _i, _i, _p]),
+    "ducosy_conv2d_nhwc": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_upconv2x_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_stem_im2col": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_stem_im2col_hu": (_i, [_p, _p, _i, _i, _i, _f, _f, _f, _f, _i, _p]),
+    "ducosy_in_finalize": (_i, [_p, _i, _i, _p, _p, _p, _p, _i, _i, _p]),
+    "ducosy_in_apply_pad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_cbam_pool": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_cbam_spatial_conv": (_i, [_p, _p, _p, _i, _i, _i, _p]),
+    "ducosy_residual_apply_pad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_out_weight": (_i, [_p, _p, _i, _p]),
+    "ducosy_out_conv7x7_tanh": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_generator_num_params": (_i, [C.POINTER(GenConfig)]),
+    "ducosy_generator_packed_bytes": (_sz, [C.POINTER(GenConfig)]),
+    "ducosy_generator_workspace_bytes": (_sz, [C.POINTER(GenConfig), _i, _i, _i]),
+    "ducosy_generator_pack": (_i, [C.POINTER(GenConfig), C.POINTER(_p), _i, _p, _p]),
+    "ducosy_generator_forward": (_i, [C.POINTER(GenConfig), _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "ducosy_generator_forward_hu": (_i, [C.POINTER(GenConfig), _p, _p, _f, _f, _f, _f, _p, _i, _i, _i, _p, _sz, _p]),
+    "ducosy_generator_num_launches": (_i, [C.POINTER(GenConfig)]),
+}
+
+_lib = None
+
+
+def load():
+    """Load the shared library (built by ducosy_gan_b200/build.py).  Raises if absent: no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python -m ducosy_gan_b200.build` "
+                "(ducosy_gan_b200 has no CPU / PyTorch fallback path)")
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+class DucosyError(RuntimeError):
+    pass
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().ducosy_last_error().decode(errors="replace")
+        raise DucosyError(f"{what or 'libducosy'} failed ({rc}): {msg}")
+
+
+def ptr(t):
+    """Raw device pointer of a tensor (None -> NULL)."""
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream_ptr(stream=None):
+    s = torch.cuda.current_stream() if stream is None else stream
+    return C.c_void_p(s.cuda_stream)
+
+
+def dtype_code(dtype) -> int:
+    if dtype in (torch.float16, "fp16", "f16", F16):
+        return F16
+    if dtype in (torch.bfloat16, "bf16", BF16):
+        return BF16
+    raise ValueError(f"unsupported operand dtype {dtype!r} (fp16 or bf16)")
+
+
+def torch_dtype(code: int):
+    return torch.float16 if code == F16 else torch.bfloat16
+
+
+def call(name: str, *args):
+    check(getattr(load(), name)(*args), name)

@@ -1,0 +1,107 @@
+// Shared host/device declarations for libducosy_sm100.so
+#pragma once
+#include <cstdarg>
+#include <cstdint>
+#include <cstdio>
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/ducosy.h"
+
+namespace ducosy {
+
+// ---- error plumbing: every extern "C" entry returns 0 or a negative code; message is thread-local ----
+void set_error(const char* fmt, ...);
+int fail(int code, const char* fmt, ...);
+int check_launch(const char* what);  // cudaGetLastError -> code
+
+#define DUCOSY_CHECK(cond, code, ...) \
+  do {                                \
+    if (!(cond)) return ::ducosy::fail((code), __VA_ARGS__); \
+  } while (0)
+
+#define DUCOSY_TRY(expr)        \
+  do {                          \
+    int _rc = (expr);           \
+    if (_rc != 0) return _rc;   \
+  } while (0)
+
+int num_sms();
+
+constexpr int kMaxTaps = 16;
+constexpr int kMaxPhases = 4;
+
+// Arguments of the implicit-GEMM convolution kernel (see conv_gemm.cu for the meaning).
+struct ConvGemmArgs {
+  int num_phases, num_taps, kc_per_tap, n_blocks;
+  int B, TY, TX;           // tiles per sample along the GEMM grid rows / cols
+  int R, Wt, log2Wt;       // a tile is R rows x Wt cols of the GEMM grid (R*Wt == 128)
+  int rows_per_sample;     // units of the outermost TMA dimension per sample
+  int Cout;                // total output channels (= n_blocks * kN)
+  int8_t tap_xp[kMaxPhases][kMaxTaps], tap_dx[kMaxPhases][kMaxTaps];
+  int8_t tap_yp[kMaxPhases][kMaxTaps], tap_dy[kMaxPhases][kMaxTaps];
+  void* out;               // raw conv output, NHWC [B, Ho, Wo, Cout]
+  long long out_bs;        // elements per sample
+  int out_rs, out_ps;      // elements per output row / pixel
+  int oy_mul, ox_mul;      // GEMM-grid (y,x) -> output (y*oy_mul+oy_off, x*ox_mul+ox_off)
+  int8_t oy_off[kMaxPhases], ox_off[kMaxPhases];
+  float* partials;         // [B][tiles_per_sample][3][Cout] (sum, sum of squares, max) or nullptr
+  const float* bias;       // optional per-channel bias (epilogue mode 1)
+  int epi_mode;            // 0: raw output + statistics, 1: bias + LeakyReLU(0.2), no statistics
+};
+
+// Host-side description of one convolution as an implicit GEMM.
+struct ConvPlan {
+  const void* in;          // NHWC activation buffer (already padded as the conv needs)
+  int B, Hp, Wp, Cin;      // its shape
+  int stride;              // 1 or 2 (2: Hp and Wp must be even)
+  const void* w;           // packed weights [num_phases*Cout][num_taps*Cin], K-major
+  int Cout, num_phases, num_taps;
+  int8_t tap_dy[kMaxPhases][kMaxTaps], tap_dx[kMaxPhases][kMaxTaps];  // offsets in padded input pixels
+  int Hg, Wg;              // GEMM grid per sample
+  void* out;
+  int Ho, Wo;              // output image
+  int oy_mul, ox_mul;
+  int8_t oy_off[kMaxPhases], ox_off[kMaxPhases];
+  float* partials;
+  const float* bias;
+  int epi_mode;
+  int dtype;
+};
+
+int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream);
+inline int conv_tiles_per_sample(int num_phases, int Hg, int Wg) { return num_phases * (Hg * Wg / 128); }
+
+template <typename T> struct Cvt;
+template <> struct Cvt<__half> {
+  static __device__ __forceinline__ float to_f(__half v) { return __half2float(v); }
+  static __device__ __forceinline__ __half from_f(float v) { return __float2half_rn(v); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __half22float2(*reinterpret_cast<__half2*>(&u));
+  }
+};
+template <> struct Cvt<__nv_bfloat16> {
+  static __device__ __forceinline__ float to_f(__nv_bfloat16 v) { return __bfloat162float(v); }
+  static __device__ __forceinline__ __nv_bfloat16 from_f(float v) { return __float2bfloat16_rn(v); }
+  static __device__ __forceinline__ uint32_t pack2(float a, float b) {
+    __nv_bfloat162 h = __floats2bfloat162_rn(a, b);
+    return *reinterpret_cast<uint32_t*>(&h);
+  }
+  static __device__ __forceinline__ float2 unpack2(uint32_t u) {
+    return __bfloat1622float2(*reinterpret_cast<__nv_bfloat162*>(&u));
+  }
+};
+
+#define DUCOSY_DISPATCH_DTYPE(dtype, T, ...)                         \
+  do {                                                               \
+    if ((dtype) == DUCOSY_F16) { using T = __half; __VA_ARGS__; }    \
+    else { using T = __nv_bfloat16; __VA_ARGS__; }                   \
+  } while (0)
+
+}  // namespace ducosy

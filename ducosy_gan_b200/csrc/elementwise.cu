@@ -1,0 +1,461 @@
+// Bandwidth-bound kernels around the tensor-core convolutions: weight packing, stem im2col (optionally fused
+// with the HU window), InstanceNorm finalize/apply (+ReLU, + padding writer), CBAM channel MLP, CBAM spatial
+// pooling / 7x7 attention conv, and the residual add.  NHWC 16-bit activations, 128-bit accesses.
+#include "common.cuh"
+
+namespace ducosy {
+namespace {
+
+int ew_grid(long long work_items, int threads) {
+  const int sms = num_sms();
+  long long blocks = (work_items + threads - 1) / threads;
+  const long long cap = (long long)(sms > 0 ? sms : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat)
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// ------------------------------------------------------------------ weight packing
+template <typename T>
+__global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int kh,
+                                        int kw) {
+  const long long total = (long long)Cout * Cin * kh * kw;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    long long r = i / Cin;
+    const int tap = int(r % (kh * kw));
+    const int o = int(r / (kh * kw));
+    out[i] = Cvt<T>::from_f(w[((long long)o * Cin + c) * kh * kw + tap]);
+  }
+}
+
+// Upsample(x2 nearest) + 3x3/pad1  ==  four 2x2 convs on the source grid:
+// rows: phase 0 -> [w0, w1+w2], phase 1 -> [w0+w1, w2]; same for columns.  Sums are formed in fp32.
+template <typename T>
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin) {
+  const long long total = 4LL * Cout * 4 * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    long long r = i / Cin;
+    const int tap = int(r % 4);
+    r /= 4;
+    const int o = int(r % Cout);
+    const int phase = int(r / Cout);
+    const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+    // source-row tap a of output-row phase py gathers original rows [r0, r1]
+    const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+    const int r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+    const int s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* wk = w + ((long long)o * Cin + c) * 9;
+    float acc = 0.f;
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int ss = s0; ss <= s1; ++ss) acc += wk[rr * 3 + ss];
+    out[i] = Cvt<T>::from_f(acc);
+  }
+}
+
+template <typename T>
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cin, int Kpad) {
+  const int total = 64 * Kpad;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int k = i % Kpad, o = i / Kpad;
+    out[i] = Cvt<T>::from_f(k < 49 * Cin ? w[o * 49 * Cin + k] : 0.f);
+  }
+}
+
+// ------------------------------------------------------------------ stem im2col
+// A[(b,y,x)][k], k = c*49 + r*7 + s  <-  in[b][c][reflect(y+r-3)][reflect(x+s-3)], zero for k >= 49*Cin.
+// One thread builds 8 consecutive k (one 16-byte store); consecutive threads -> consecutive chunks of a row.
+struct InF32 {
+  const float* x;
+  __device__ __forceinline__ float at(int b, int c, int y, int x_, int Cin, int H, int W) const {
+    return x[(((long long)b * Cin + c) * H + y) * W + x_];
+  }
+};
+struct InHU {
+  const int16_t* px;
+  float slope, intercept, lo, hi, span;
+  __device__ __forceinline__ float at(int b, int, int y, int x_, int, int H, int W) const {
+    const float hu = __fadd_rn(__fmul_rn(float(px[((long long)b * H + y) * W + x_]), slope), intercept);
+    const float c = fminf(fmaxf(hu, lo), hi);
+    return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(c, lo)), span), 1.0f);  // preprocess.py:79-84
+  }
+};
+template <typename T, typename In>
+__global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int H, int W, int Kpad) {
+  const int chunks = Kpad / 8;
+  const long long total = (long long)B * H * W * chunks;
+  const int K = 49 * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int ck = int(i % chunks);
+    long long pix = i / chunks;
+    const int x = int(pix % W);
+    pix /= W;
+    const int y = int(pix % H);
+    const int b = int(pix / H);
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = ck * 8 + j;
+      if (k < K) {
+        const int c = k / 49, rs = k - c * 49, r = rs / 7, s = rs - r * 7;
+        v[j] = in.at(b, c, reflect_idx(y + r - 3, H), reflect_idx(x + s - 3, W), Cin, H, W);
+      } else {
+        v[j] = 0.f;
+      }
+    }
+    uint4 o;
+    o.x = Cvt<T>::pack2(v[0], v[1]);
+    o.y = Cvt<T>::pack2(v[2], v[3]);
+    o.z = Cvt<T>::pack2(v[4], v[5]);
+    o.w = Cvt<T>::pack2(v[6], v[7]);
+    reinterpret_cast<uint4*>(A)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm finalize (+ CBAM channel MLP)
+// One CTA per sample.  Tile partials are reduced in double; var is the biased variance, eps = 1e-5.
+__global__ void in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, float* __restrict__ scale,
+                                   float* __restrict__ shift, const float* __restrict__ fc0,
+                                   const float* __restrict__ fc2, int C) {
+  extern __shared__ float sm[];  // [C] normalised max, [C/16] hidden
+  float* smax = sm;
+  float* hidden = sm + C;
+  const int b = blockIdx.x;
+  const float* p = partials + (long long)b * tiles * 3 * C;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    double s1 = 0.0, s2 = 0.0;
+    float mx = -INFINITY;
+    for (int t = 0; t < tiles; ++t) {
+      s1 += double(p[(t * 3 + 0) * C + c]);
+      s2 += double(p[(t * 3 + 1) * C + c]);
+      mx = fmaxf(mx, p[(t * 3 + 2) * C + c]);
+    }
+    const double mean = s1 / npix;
+    double var = s2 / npix - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = float(1.0 / sqrt(var + 1e-5));
+    const float fmean = float(mean);
+    scale[b * C + c] = rstd;
+    shift[b * C + c] = -fmean * rstd;
+    smax[c] = (mx - fmean) * rstd;  // max over H*W of the normalised map (rstd > 0)
+  }
+  if (fc0 == nullptr) return;
+  __syncthreads();
+  // modules/model.py:20-24.  The avg-pool branch sees the mean of a non-affine InstanceNorm output, which is
+  // exactly zero here (statistics are taken from the stored values), and fc has no bias: fc(0) = 0.
+  const int Hd = C / 16;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Hd; j += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc += fc0[j * C + c] * smax[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) hidden[j] = fmaxf(acc, 0.f);
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < Hd; ++j) acc += fc2[c * Hd + j] * hidden[j];
+    const float s = 1.f / (1.f + __expf(-acc));
+    scale[b * C + c] *= s;
+    shift[b * C + c] *= s;
+  }
+}
+
+// ------------------------------------------------------------------ IN apply (+act) + padding writer
+template <typename T>
+__device__ __forceinline__ uint4 affine8(uint4 raw, const float* sc, const float* sh, int act) {
+  uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 f = Cvt<T>::unpack2(w[i]);
+    f.x = fmaf(f.x, sc[2 * i], sh[2 * i]);
+    f.y = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
+    if (act == DUCOSY_ACT_RELU) {
+      f.x = fmaxf(f.x, 0.f);
+      f.y = fmaxf(f.y, 0.f);
+    } else if (act == DUCOSY_ACT_LRELU02) {
+      f.x = f.x > 0.f ? f.x : 0.2f * f.x;
+      f.y = f.y > 0.f ? f.y : 0.2f * f.y;
+    }
+    w[i] = Cvt<T>::pack2(f.x, f.y);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+template <typename T>
+__global__ void in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                    const float* __restrict__ shift, T* __restrict__ out, int B, int H, int W, int C,
+                                    int pad, int pad_mode, int act) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
+  const long long total = (long long)B * Hp * Wp * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % cv);
+    long long r = i / cv;
+    const int px = int(r % Wp);
+    r /= Wp;
+    const int py = int(r % Hp);
+    const int b = int(r / Hp);
+    int sy = py - pad, sx = px - pad;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
+    if (inside || pad_mode == DUCOSY_PAD_REFLECT) {
+      sy = reflect_idx(sy, H);
+      sx = reflect_idx(sx, W);
+      const uint4 raw = reinterpret_cast<const uint4*>(y)[(((long long)b * H + sy) * W + sx) * cv + c8];
+      const float4* sc = reinterpret_cast<const float4*>(scale + b * C + c8 * 8);
+      const float4* sh = reinterpret_cast<const float4*>(shift + b * C + c8 * 8);
+      const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+      const float s8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float h8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      o = affine8<T>(raw, s8, h8, act);
+    }
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------ CBAM spatial pooling: one warp per pixel, C = 256
+template <typename T>
+__global__ void cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                 const float* __restrict__ shift, float2* __restrict__ pooled, int B, int HW) {
+  constexpr int C = 256;
+  const int lane = threadIdx.x & 31;
+  const int warps_per_block = blockDim.x >> 5;
+  const long long total = (long long)B * HW;
+  const long long wstride = (long long)gridDim.x * warps_per_block;
+  int cur_b = -1;
+  float sc[8], sh[8];
+  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < total; pix += wstride) {
+    const int b = int(pix / HW);
+    if (b != cur_b) {
+      cur_b = b;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[j] = scale[b * C + lane * 8 + j];
+        sh[j] = shift[b * C + lane * 8 + j];
+      }
+    }
+    const uint4 raw = reinterpret_cast<const uint4*>(y)[pix * (C / 8) + lane];
+    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+    float s = 0.f, m = -INFINITY;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float2 f = Cvt<T>::unpack2(w[i]);
+      const float v0 = fmaf(f.x, sc[2 * i], sh[2 * i]), v1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
+      s += v0 + v1;
+      m = fmaxf(m, fmaxf(v0, v1));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      s += __shfl_xor_sync(0xffffffffu, s, o);
+      m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    }
+    if (lane == 0) pooled[pix] = make_float2(s * (1.f / C), m);
+  }
+}
+
+// sa[b][y][x] = sigmoid( sum_{ch,r,s} w[ch][r][s] * pooled[b][y+r-3][x+s-3][ch] ), zero padding
+__global__ void cbam_spatial_conv_kernel(const float2* __restrict__ pooled, const float* __restrict__ w,
+                                         float* __restrict__ sa, int B, int H, int W) {
+  __shared__ float sw[98];
+  for (int i = threadIdx.x; i < 98; i += blockDim.x) sw[i] = w[i];
+  __syncthreads();
+  const long long total = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int x = int(i % W);
+    long long r = i / W;
+    const int yy = int(r % H);
+    const int b = int(r / H);
+    float acc = 0.f;
+#pragma unroll
+    for (int dr = 0; dr < 7; ++dr) {
+      const int sy = yy + dr - 3;
+      if (sy < 0 || sy >= H) continue;
+#pragma unroll
+      for (int ds = 0; ds < 7; ++ds) {
+        const int sx = x + ds - 3;
+        if (sx < 0 || sx >= W) continue;
+        const float2 p = __ldg(&pooled[((long long)b * H + sy) * W + sx]);
+        acc = fmaf(sw[dr * 7 + ds], p.x, acc);
+        acc = fmaf(sw[49 + dr * 7 + ds], p.y, acc);
+      }
+    }
+    sa[i] = 1.f / (1.f + __expf(-acc));
+  }
+}
+
+// out_pad = residual + (y*scale+shift) * sa ; borders by reflection / zero.  res_pad has padding res_pw.
+template <typename T>
+__global__ void residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale,
+                                          const float* __restrict__ shift, const float* __restrict__ sa,
+                                          const T* __restrict__ res_pad, int res_pw, T* __restrict__ out, int B, int H,
+                                          int W, int C, int pad, int pad_mode) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
+  const int Wr = W + 2 * res_pw, Hr = H + 2 * res_pw;
+  const long long total = (long long)B * Hp * Wp * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % cv);
+    long long r = i / cv;
+    const int px = int(r % Wp);
+    r /= Wp;
+    const int py = int(r % Hp);
+    const int b = int(r / Hp);
+    int sy = py - pad, sx = px - pad;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
+    if (inside || pad_mode == DUCOSY_PAD_REFLECT) {
+      sy = reflect_idx(sy, H);
+      sx = reflect_idx(sx, W);
+      const long long spix = ((long long)b * H + sy) * W + sx;
+      const uint4 raw = reinterpret_cast<const uint4*>(y)[spix * cv + c8];
+      const uint4 res =
+          reinterpret_cast<const uint4*>(res_pad)[(((long long)b * Hr + sy + res_pw) * Wr + sx + res_pw) * cv + c8];
+      const float att = sa != nullptr ? __ldg(sa + spix) : 1.f;
+      const float4* sc = reinterpret_cast<const float4*>(scale + b * C + c8 * 8);
+      const float4* sh = reinterpret_cast<const float4*>(shift + b * C + c8 * 8);
+      const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
+      const float s8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float h8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      const uint32_t yw[4] = {raw.x, raw.y, raw.z, raw.w};
+      const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = Cvt<T>::unpack2(yw[k]);
+        const float2 g = Cvt<T>::unpack2(rw[k]);
+        const float v0 = fmaf(f.x, s8[2 * k], h8[2 * k]), v1 = fmaf(f.y, s8[2 * k + 1], h8[2 * k + 1]);
+        ow[k] = Cvt<T>::pack2(fmaf(v0, att, g.x), fmaf(v1, att, g.y));
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    reinterpret_cast<uint4*>(out)[i] = o;
+  }
+}
+
+bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+}  // namespace
+}  // namespace ducosy
+
+using namespace ducosy;
+
+extern "C" int ducosy_pack_conv_weight(const float* w, void* packed, int Cout, int Cin, int kh, int kw, int dtype,
+                                       ducosy_stream_t stream) {
+  DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, DUCOSY_ERR_ARG, "pack_conv_weight: bad argument");
+  const long long total = (long long)Cout * Cin * kh * kw;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_conv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      w, static_cast<T*>(packed), Cout, Cin, kh, kw)));
+  return check_launch("pack_conv_weight_kernel");
+}
+
+extern "C" int ducosy_pack_upconv_weight(const float* w, void* packed, int Cout, int Cin, int dtype,
+                                         ducosy_stream_t stream) {
+  DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_weight: bad argument");
+  const long long total = 16LL * Cout * Cin;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      w, static_cast<T*>(packed), Cout, Cin)));
+  return check_launch("pack_upconv_weight_kernel");
+}
+
+extern "C" int ducosy_pack_stem_weight(const float* w, void* packed, int Cin, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(w && packed && Cin > 0, DUCOSY_ERR_ARG, "pack_stem_weight: bad argument");
+  const int Kpad = (49 * Cin + 63) / 64 * 64;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_stem_weight_kernel<T><<<ew_grid(64 * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      w, static_cast<T*>(packed), Cin, Kpad)));
+  return check_launch("pack_stem_weight_kernel");
+}
+
+extern "C" int ducosy_stem_im2col(const float* x, void* a_mat, int B, int Cin, int H, int W, int dtype,
+                                  ducosy_stream_t stream) {
+  DUCOSY_CHECK(x && a_mat && B > 0 && Cin > 0, DUCOSY_ERR_ARG, "stem_im2col: bad argument");
+  DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col: reflect pad 3 needs H,W >= 4");
+  const int Kpad = (49 * Cin + 63) / 64 * 64;
+  const long long total = (long long)B * H * W * (Kpad / 8);
+  InF32 in{x};
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (stem_im2col_kernel<T, InF32><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      in, static_cast<T*>(a_mat), B, Cin, H, W, Kpad)));
+  return check_launch("stem_im2col_kernel");
+}
+
+extern "C" int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, float slope, float intercept,
+                                     float lo, float hi, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(px && a_mat && B > 0, DUCOSY_ERR_ARG, "stem_im2col_hu: bad argument");
+  DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col_hu: reflect pad 3 needs H,W >= 4");
+  const long long total = (long long)B * H * W * 8;
+  InHU in{px, slope, intercept, lo, hi, float(double(hi) - double(lo))};
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (stem_im2col_kernel<T, InHU><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      in, static_cast<T*>(a_mat), B, 1, H, W, 64)));
+  return check_launch("stem_im2col_kernel(hu)");
+}
+
+extern "C" int ducosy_in_finalize(const float* partials, int tiles_per_sample, int npix_per_sample, float* scale,
+                                  float* shift, const float* fc0, const float* fc2, int B, int C,
+                                  ducosy_stream_t stream) {
+  DUCOSY_CHECK(partials && scale && shift && B > 0 && C > 0 && tiles_per_sample > 0 && npix_per_sample > 0,
+               DUCOSY_ERR_ARG, "in_finalize: bad argument");
+  DUCOSY_CHECK((fc0 == nullptr) == (fc2 == nullptr), DUCOSY_ERR_ARG, "in_finalize: fc0 and fc2 go together");
+  DUCOSY_CHECK(fc0 == nullptr || C % 16 == 0, DUCOSY_ERR_SHAPE, "in_finalize: CBAM needs C %% 16 == 0");
+  const int threads = C >= 256 ? 256 : 128;
+  const size_t smem = sizeof(float) * (C + C / 16 + 1);
+  in_finalize_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample, scale,
+                                                                 shift, fc0, fc2, C);
+  return check_launch("in_finalize_kernel");
+}
+
+extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const float* shift, void* out_pad, int B, int H,
+                                   int W, int C, int pad, int pad_mode, int act, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(y && scale && shift && out_pad && B > 0, DUCOSY_ERR_ARG, "in_apply_pad: bad argument");
+  DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_SHAPE, "in_apply_pad: C %% 8 != 0 or pad too large");
+  DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
+  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
+                                      pad_mode, act)));
+  return check_launch("in_apply_pad_kernel");
+}
+
+extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* shift, float* pooled, int B, int H, int W,
+                                int C, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(y && scale && shift && pooled && B > 0, DUCOSY_ERR_ARG, "cbam_pool: bad argument");
+  DUCOSY_CHECK(C == 256, DUCOSY_ERR_SHAPE, "cbam_pool: C must be 256 (got %d)", C);
+  const long long pixels = (long long)B * H * W;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T><<<ew_grid(pixels * 32 / 4, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), B, H * W)));
+  return check_launch("cbam_pool_kernel");
+}
+
+extern "C" int ducosy_cbam_spatial_conv(const float* pooled, const float* w_sa, float* sa, int B, int H, int W,
+                                        ducosy_stream_t stream) {
+  DUCOSY_CHECK(pooled && w_sa && sa && B > 0, DUCOSY_ERR_ARG, "cbam_spatial_conv: bad argument");
+  cbam_spatial_conv_kernel<<<ew_grid((long long)B * H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+      reinterpret_cast<const float2*>(pooled), w_sa, sa, B, H, W);
+  return check_launch("cbam_spatial_conv_kernel");
+}
+
+extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, const float* shift, const float* sa,
+                                         const void* res_pad, int res_pad_width, void* out_pad, int B, int H, int W,
+                                         int C, int pad, int pad_mode, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(y && scale && shift && res_pad && out_pad && B > 0, DUCOSY_ERR_ARG, "residual_apply_pad: bad argument");
+  DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W && res_pad_width >= 0, DUCOSY_ERR_SHAPE,
+               "residual_apply_pad: bad shape");
+  DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
+  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y), scale, shift, sa, static_cast<const T*>(res_pad),
+                                      res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
+  return check_launch("residual_apply_pad_kernel");
+}

@@ -1,0 +1,136 @@
+// Output layer of the generator (modules/model.py:112): ReflectionPad2d(3) + Conv2d(64, 1, 7) + Tanh.
+// One output channel makes this a GEMV-like, HBM/L2-bound layer (reads the 64-channel map once), so it does
+// not go through the tcgen05 implicit-GEMM kernel.  It is evaluated as
+//     P[y][xp][s] = sum_{r,c} in[y+r][xp][c] * w[c][r][s]           (warp-level m16n8k16 MMAs, N = 7 taps -> 8)
+//     out[y][x]   = tanh(bias + sum_s P[y][x+s][s])                 (shift-sum through shared memory)
+// A CTA produces 8 output rows x 128 columns so that every input row it loads is reused by up to 7 output rows.
+#include "common.cuh"
+
+namespace ducosy {
+namespace {
+
+constexpr int kRowsOut = 8;
+constexpr int kColsOut = 128;
+constexpr int kPos = 144;            // 9 warps x 16 padded columns (>= 128 + 6)
+constexpr int kOutThreads = 288;
+
+template <typename T>
+__device__ __forceinline__ void mma16816(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1);
+template <>
+__device__ __forceinline__ void mma16816<__half>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                                 uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+template <>
+__device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2,
+                                                        uint32_t a3, uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// packed weight layout: [r = 7][s = 8 (s == 7 is zero)][c = 64]
+template <typename T>
+__global__ void pack_out_weight_kernel(const float* __restrict__ w, T* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 7 * 8 * 64; i += gridDim.x * blockDim.x) {
+    const int c = i & 63, s = (i >> 6) & 7, r = i >> 9;
+    out[i] = Cvt<T>::from_f(s < 7 ? w[c * 49 + r * 7 + s] : 0.f);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kOutThreads)
+out_conv7x7_tanh_kernel(const T* __restrict__ in_pad, const T* __restrict__ wp, const float* __restrict__ bias,
+                        float* __restrict__ out, int B, int H, int W) {
+  __shared__ float P[kRowsOut][kPos][9];  // 9-float rows: the diagonal reads below are bank-conflict free
+  const int tiles_x = W / kColsOut, tiles_y = H / kRowsOut;
+  const int tx = blockIdx.x % tiles_x;
+  const int ty = (blockIdx.x / tiles_x) % tiles_y;
+  const int b = blockIdx.x / (tiles_x * tiles_y);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane >> 2, t = lane & 3;
+  const int Wp = W + 6, Hp = H + 6;
+
+  // B fragments for all 7 filter rows stay in registers: thread (g,t) holds w[r][s=g][cb*32 + 8t .. +7]
+  uint4 wr[7][2];
+#pragma unroll
+  for (int r = 0; r < 7; ++r)
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+      wr[r][cb] = __ldg(reinterpret_cast<const uint4*>(wp + ((r * 8 + g) * 64 + cb * 32 + 8 * t)));
+
+  float acc[kRowsOut][4];
+#pragma unroll
+  for (int i = 0; i < kRowsOut; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int xp0 = tx * kColsOut + 16 * warp + g;
+  const int xpA = min(xp0, Wp - 1), xpB = min(xp0 + 8, Wp - 1);  // columns past the row end feed unused outputs
+  const T* base = in_pad + (size_t(b) * Hp + size_t(ty) * kRowsOut) * Wp * 64 + 8 * t;
+
+#pragma unroll
+  for (int i = 0; i < kRowsOut + 6; ++i) {
+    const T* rowp = base + size_t(i) * Wp * 64;
+    uint4 A[2][2];
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb) {
+      A[cb][0] = *reinterpret_cast<const uint4*>(rowp + size_t(xpA) * 64 + cb * 32);
+      A[cb][1] = *reinterpret_cast<const uint4*>(rowp + size_t(xpB) * 64 + cb * 32);
+    }
+#pragma unroll
+    for (int yo = 0; yo < kRowsOut; ++yo) {
+      const int r = i - yo;
+      if (r < 0 || r > 6) continue;
+#pragma unroll
+      for (int cb = 0; cb < 2; ++cb) {
+        mma16816<T>(acc[yo], A[cb][0].x, A[cb][1].x, A[cb][0].y, A[cb][1].y, wr[r][cb].x, wr[r][cb].y);
+        mma16816<T>(acc[yo], A[cb][0].z, A[cb][1].z, A[cb][0].w, A[cb][1].w, wr[r][cb].z, wr[r][cb].w);
+      }
+    }
+  }
+#pragma unroll
+  for (int yo = 0; yo < kRowsOut; ++yo) {
+    P[yo][16 * warp + g][2 * t] = acc[yo][0];
+    P[yo][16 * warp + g][2 * t + 1] = acc[yo][1];
+    P[yo][16 * warp + g + 8][2 * t] = acc[yo][2];
+    P[yo][16 * warp + g + 8][2 * t + 1] = acc[yo][3];
+  }
+  __syncthreads();
+  const float bv = __ldg(bias);
+  for (int idx = threadIdx.x; idx < kRowsOut * kColsOut; idx += kOutThreads) {
+    const int yo = idx / kColsOut, x = idx % kColsOut;
+    float v = bv;
+#pragma unroll
+    for (int s = 0; s < 7; ++s) v += P[yo][x + s][s];
+    out[(size_t(b) * H + ty * kRowsOut + yo) * W + tx * kColsOut + x] = tanhf(v);
+  }
+}
+
+}  // namespace
+}  // namespace ducosy
+
+using namespace ducosy;
+
+extern "C" int ducosy_pack_out_weight(const float* w, void* packed, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(w && packed, DUCOSY_ERR_ARG, "pack_out_weight: null pointer");
+  DUCOSY_DISPATCH_DTYPE(dtype, T,
+                        (pack_out_weight_kernel<T><<<14, 256, 0, (cudaStream_t)stream>>>(w, static_cast<T*>(packed))));
+  return check_launch("pack_out_weight_kernel");
+}
+
+extern "C" int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed, const float* bias, float* out, int B,
+                                       int H, int W, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(in_pad && w_packed && bias && out && B > 0, DUCOSY_ERR_ARG, "out_conv7x7_tanh: bad argument");
+  DUCOSY_CHECK(H % kRowsOut == 0 && W % kColsOut == 0, DUCOSY_ERR_SHAPE,
+               "out_conv7x7_tanh: H must be a multiple of 8 and W of 128 (got %dx%d)", H, W);
+  DUCOSY_CHECK((reinterpret_cast<uintptr_t>(in_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+               DUCOSY_ERR_ALIGN, "out_conv7x7_tanh: 16-byte alignment");
+  const int grid = B * (H / kRowsOut) * (W / kColsOut);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(in_pad), static_cast<const T*>(w_packed), bias, out, B, H, W)));
+  return check_launch("out_conv7x7_tanh_kernel");
+}

@@ -1,0 +1,253 @@
+"""Drop-in for the reference's ``modules/model.py`` (reference file:line in each docstring).
+
+Same constructors, same ``forward`` signatures, same parameter tree -- so ``state_dict()`` keys/shapes are
+identical, existing ``.pth`` checkpoints load with ``strict=True`` and ``.apply(weights_init_normal)`` finds
+the same 51 (generator) / 5 (discriminator) ``Conv2d`` modules.  The torch layers below are parameter
+holders only: ``Generator.forward`` hands the whole network to ``libducosy_sm100.so``
+(tcgen05 implicit-GEMM convolutions + fused InstanceNorm/CBAM/residual kernels, see ../csrc).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+import torch.nn as nn
+
+from .. import _lib
+
+_NO_TRAIN_MSG = ("ducosy_gan_b200: the autograd (training) path of {} is not built yet -- this round ships the "
+                 "inference forward only; call it under torch.no_grad(). There is deliberately no PyTorch fallback.")
+
+
+def default_operand_dtype() -> int:
+    """16-bit operand type of the tensor-core convolutions: fp16 (default; TF32-class 10-bit mantissa, the
+    reference's own GPU precision) or bf16 via DUCOSY_PRECISION=bf16."""
+    return _lib.dtype_code(os.environ.get("DUCOSY_PRECISION", "fp16").lower())
+
+
+class ChannelAttention(nn.Module):
+    """reference modules/model.py:6-24 (parameters: fc.0.weight [C/r,C,1,1], fc.2.weight [C,C/r,1,1])."""
+
+    def __init__(self, channels, reduction=16):
+        super().__init__()
+        self.avg_pool = nn.AdaptiveAvgPool2d(1)
+        self.max_pool = nn.AdaptiveMaxPool2d(1)
+        self.fc = nn.Sequential(nn.Conv2d(channels, channels // reduction, 1, bias=False), nn.ReLU(inplace=True),
+                                nn.Conv2d(channels // reduction, channels, 1, bias=False))
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x):
+        raise NotImplementedError("ChannelAttention runs fused inside Generator.forward / ResidualBlockWithCBAM")
+
+
+class SpatialAttention(nn.Module):
+    """reference modules/model.py:27-39 (parameter: conv.weight [1,2,k,k])."""
+
+    def __init__(self, kernel_size=7):
+        super().__init__()
+        self.conv = nn.Conv2d(2, 1, kernel_size, padding=kernel_size // 2, bias=False)
+        self.sigmoid = nn.Sigmoid()
+
+    def forward(self, x):
+        raise NotImplementedError("SpatialAttention runs fused inside Generator.forward / ResidualBlockWithCBAM")
+
+
+class CBAM(nn.Module):
+    """reference modules/model.py:42-52."""
+
+    def __init__(self, channels, reduction=16, kernel_size=7):
+        super().__init__()
+        self.channel_attention = ChannelAttention(channels, reduction)
+        self.spatial_attention = SpatialAttention(kernel_size)
+
+    def forward(self, x):
+        raise NotImplementedError("CBAM runs fused inside Generator.forward / ResidualBlockWithCBAM")
+
+
+def _res_layers(c):
+    return nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(c, c, 3), nn.InstanceNorm2d(c), nn.ReLU(inplace=True),
+                         nn.ReflectionPad2d(1), nn.Conv2d(c, c, 3), nn.InstanceNorm2d(c))
+
+
+class ResidualBlock(nn.Module):
+    """reference modules/model.py:56-65: x + IN(conv(refpad(ReLU(IN(conv(refpad(x)))))))."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.block = _res_layers(in_features)
+
+    def forward(self, x):
+        raise NotImplementedError("ResidualBlock runs fused inside Generator.forward")
+
+
+class ResidualBlockWithCBAM(nn.Module):
+    """reference modules/model.py:68-87: x + CBAM(block(x))."""
+
+    def __init__(self, in_features):
+        super().__init__()
+        self.block = _res_layers(in_features)
+        self.cbam = CBAM(in_features)
+
+    def forward(self, x):
+        raise NotImplementedError("ResidualBlockWithCBAM runs fused inside Generator.forward")
+
+
+class Generator(nn.Module):
+    """reference modules/model.py:90-115.  ``forward(x[B,Cin,H,W] fp32 cuda) -> [B,1,H,W] fp32``.
+
+    H must be a multiple of 32 and W of 128 with W/4 in {32, 64, 128k} (512x512 is what generate.py and
+    train.py use).  Only sm_100 devices are accepted.
+    """
+
+    def __init__(self, input_channels=1, num_residual_blocks=9, use_cbam=True):
+        super().__init__()
+        layers = [nn.ReflectionPad2d(3), nn.Conv2d(input_channels, 64, 7), nn.InstanceNorm2d(64), nn.ReLU(inplace=True)]
+        ch = 64
+        for _ in range(2):
+            layers += [nn.Conv2d(ch, ch * 2, 3, stride=2, padding=1), nn.InstanceNorm2d(ch * 2), nn.ReLU(inplace=True)]
+            ch *= 2
+        block_cls = ResidualBlockWithCBAM if use_cbam else ResidualBlock
+        layers += [block_cls(ch) for _ in range(num_residual_blocks)]
+        for _ in range(2):
+            layers += [nn.Upsample(scale_factor=2), nn.Conv2d(ch, ch // 2, 3, stride=1, padding=1),
+                       nn.InstanceNorm2d(ch // 2), nn.ReLU(inplace=True)]
+            ch //= 2
+        layers += [nn.ReflectionPad2d(3), nn.Conv2d(ch, 1, 7), nn.Tanh()]
+        self.model = nn.Sequential(*layers)
+        self._cfg_tuple = (int(input_channels), int(num_residual_blocks), bool(use_cbam))
+        self._engines = {}  # device index -> _GeneratorEngine (derived caches; never part of state_dict)
+
+    # -- engine ------------------------------------------------------------------------------------------
+    def _engine(self, device) -> "_GeneratorEngine":
+        key = (device.index if device.index is not None else torch.cuda.current_device(), default_operand_dtype())
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = _GeneratorEngine(self._cfg_tuple, key[1], torch.device("cuda", key[0]))
+            self._engines[key] = eng
+        return eng
+
+    def _ordered_params(self):
+        return [p for _, p in self.named_parameters()]
+
+    def forward(self, x):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(_NO_TRAIN_MSG.format("Generator"))
+        if not x.is_cuda:
+            raise RuntimeError("ducosy_gan_b200.Generator needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
+        eng = self._engine(x.device)
+        eng.sync_weights(self._ordered_params())
+        return eng.forward(x)
+
+    def forward_hu(self, px, slope, intercept, hu_min, hu_max):
+        """Fused preprocess_dicom windowing (reference modules/preprocess.py:72-84) + forward:
+        ``px`` int16 [B,H,W] stored values on the GPU -> [B,1,H,W] fp32.  Needs input_channels == 1."""
+        eng = self._engine(px.device)
+        eng.sync_weights(self._ordered_params())
+        return eng.forward_hu(px, slope, intercept, hu_min, hu_max)
+
+
+class _GeneratorEngine:
+    """Per-device derived state of a Generator: packed 16-bit weights and the activation workspace."""
+
+    def __init__(self, cfg_tuple, dtype_code, device):
+        self.device = device
+        self.cfg = _lib.GenConfig(cfg_tuple[0], cfg_tuple[1], int(cfg_tuple[2]), dtype_code)
+        self.lib = _lib.load()
+        self.num_params = self.lib.ducosy_generator_num_params(C.byref(self.cfg))
+        with torch.cuda.device(device):
+            self.packed = torch.empty(self.lib.ducosy_generator_packed_bytes(C.byref(self.cfg)) + 256,
+                                      dtype=torch.uint8, device=device)
+        self._versions = None
+        self._ws = {}
+
+    def _packed_ptr(self):
+        return (self.packed.data_ptr() + 255) // 256 * 256
+
+    def sync_weights(self, params):
+        """Re-pack when any fp32 master parameter changed (load_state_dict, optimizer step, .to())."""
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if sig == self._versions:
+            return
+        if len(params) != self.num_params:
+            raise RuntimeError(f"expected {self.num_params} parameter tensors, found {len(params)}")
+        keep = []
+        for p in params:
+            t = p.detach()
+            if t.device != self.device or t.dtype != torch.float32 or not t.is_contiguous():
+                t = t.to(device=self.device, dtype=torch.float32).contiguous()
+            keep.append(t)
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        with torch.cuda.device(self.device):
+            _lib.call("ducosy_generator_pack", C.byref(self.cfg), arr, len(keep), C.c_void_p(self._packed_ptr()),
+                      _lib.stream_ptr())
+        self._keepalive = keep
+        self._versions = sig
+
+    def workspace(self, B, H, W):
+        key = (B, H, W)
+        ws = self._ws.get(key)
+        if ws is None:
+            need = self.lib.ducosy_generator_workspace_bytes(C.byref(self.cfg), B, H, W)
+            if need == 0:
+                raise _lib.DucosyError(f"unsupported generator input shape B={B} H={H} W={W}: "
+                                       "H must be a multiple of 32, W of 128, W/4 in {32,64,128k}")
+            self._ws.clear()  # one live workspace per engine
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            self._ws[key] = ws
+        return ws, (ws.data_ptr() + 1023) // 1024 * 1024, ws.numel() - 1024
+
+    def forward(self, x):
+        if x.dim() != 4 or x.shape[1] != self.cfg.input_channels:
+            raise RuntimeError(f"expected input [B,{self.cfg.input_channels},H,W], got {tuple(x.shape)}")
+        x = x.to(dtype=torch.float32).contiguous()
+        B, _, H, W = x.shape
+        with torch.cuda.device(self.device):
+            _, wptr, wbytes = self.workspace(B, H, W)
+            out = torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
+            _lib.call("ducosy_generator_forward", C.byref(self.cfg), C.c_void_p(self._packed_ptr()), _lib.ptr(x),
+                      _lib.ptr(out), B, H, W, C.c_void_p(wptr), wbytes, _lib.stream_ptr())
+        return out
+
+    def forward_hu(self, px, slope, intercept, lo, hi, out=None):
+        if px.dtype != torch.int16 or px.dim() != 3 or not px.is_contiguous():
+            raise RuntimeError("forward_hu expects a contiguous int16 [B,H,W] tensor of stored pixel values")
+        B, H, W = px.shape
+        with torch.cuda.device(self.device):
+            _, wptr, wbytes = self.workspace(B, H, W)
+            if out is None:
+                out = torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
+            _lib.call("ducosy_generator_forward_hu", C.byref(self.cfg), C.c_void_p(self._packed_ptr()), _lib.ptr(px),
+                      float(slope), float(intercept), float(lo), float(hi), _lib.ptr(out), B, H, W, C.c_void_p(wptr),
+                      wbytes, _lib.stream_ptr())
+        return out
+
+
+class Discriminator(nn.Module):
+    """reference modules/model.py:118-131 (PatchGAN).  Parameter tree only in this round: the forward/backward
+    kernels belong to the training-step rows that follow the inference path."""
+
+    def __init__(self, input_channels=1):
+        super().__init__()
+        layers, ch_in = [], input_channels
+        for i, ch_out in enumerate((64, 128, 256, 512)):
+            layers.append(nn.Conv2d(ch_in, ch_out, 4, stride=2, padding=1))
+            if i > 0:
+                layers.append(nn.InstanceNorm2d(ch_out))
+            layers.append(nn.LeakyReLU(0.2, inplace=True))
+            ch_in = ch_out
+        layers += [nn.ZeroPad2d((1, 0, 1, 0)), nn.Conv2d(512, 1, 4, padding=1)]
+        self.model = nn.Sequential(*layers)
+
+    def forward(self, img):
+        raise NotImplementedError(_NO_TRAIN_MSG.format("Discriminator"))
+
+
+def weights_init_normal(m):
+    """reference modules/model.py:134-140: Conv* weights ~ N(0, 0.02); BatchNorm2d weights ~ N(1, 0.02), bias 0."""
+    name = type(m).__name__
+    if "Conv" in name:
+        nn.init.normal_(m.weight.data, 0.0, 0.02)
+    elif "BatchNorm2d" in name:
+        nn.init.normal_(m.weight.data, 1.0, 0.02)
+        nn.init.constant_(m.bias.data, 0.0)

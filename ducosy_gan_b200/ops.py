@@ -1,0 +1,201 @@
+"""Tensor-level wrappers over the layer entry points of libducosy_sm100.so.
+
+Activations are NHWC 16-bit torch tensors (fp16 or bf16), statistics fp32.  These wrappers only allocate
+outputs and pass raw pointers; every FLOP happens in the CUDA library.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LRELU02, ACT_NONE, ACT_RELU, PAD_REFLECT, PAD_ZERO, call, dtype_code, ptr, stream_ptr  # noqa: F401
+
+
+def _dev(t):
+    return torch.cuda.device(t.device)
+
+
+# ------------------------------------------------------------------ HU kernels
+def hu_window(px: torch.Tensor, slope, intercept, soft=(-150.0, 250.0), lung=(-1000.0, -150.0)):
+    """int16 stored values -> (soft-window, lung-window) fp32 in [-1,1]   (reference preprocess.py:72-84)."""
+    assert px.dtype == torch.int16 and px.is_cuda and px.is_contiguous()
+    with _dev(px):
+        o_s = torch.empty(px.shape, dtype=torch.float32, device=px.device)
+        o_l = torch.empty(px.shape, dtype=torch.float32, device=px.device)
+        call("ducosy_hu_window", ptr(px), ptr(o_s), ptr(o_l), px.numel(), float(slope), float(intercept),
+             float(soft[0]), float(soft[1]), float(lung[0]), float(lung[1]), stream_ptr())
+    return o_s, o_l
+
+
+def hu_thresholds(px: torch.Tensor, slope, intercept):
+    """(body, lung, bone) uint8 candidates   (reference mask_generator.py:14-20,179-183)."""
+    assert px.dtype == torch.int16 and px.is_cuda and px.is_contiguous()
+    with _dev(px):
+        outs = [torch.empty(px.shape, dtype=torch.uint8, device=px.device) for _ in range(3)]
+        call("ducosy_hu_thresholds", ptr(px), ptr(outs[0]), ptr(outs[1]), ptr(outs[2]), px.numel(), float(slope),
+             float(intercept), stream_ptr())
+    return tuple(outs)
+
+
+def dewindow_composite(raw_px, y_soft, y_lung, slope, intercept, soft=(-150.0, 250.0), lung=(-1000.0, -150.0),
+                       want_parts=False, out=None):
+    """De-window both generator outputs and merge by HU range of the raw NCCT (reference preprocess.py:96-111,
+    generate.py:218-237).  Returns merged int16 (and soft_px, lung_px, masks when want_parts)."""
+    assert raw_px.dtype == torch.int16 and raw_px.is_contiguous()
+    assert y_soft.dtype == torch.float32 and y_lung.dtype == torch.float32
+    assert y_soft.numel() == raw_px.numel() == y_lung.numel()
+    y_soft, y_lung = y_soft.contiguous(), y_lung.contiguous()
+    with _dev(raw_px):
+        merged = torch.empty_like(raw_px) if out is None else out
+        sp = torch.empty_like(raw_px) if want_parts else None
+        lp = torch.empty_like(raw_px) if want_parts else None
+        mk = torch.empty(raw_px.shape, dtype=torch.uint8, device=raw_px.device) if want_parts else None
+        call("ducosy_dewindow_composite", ptr(raw_px), ptr(y_soft), ptr(y_lung), ptr(merged), ptr(sp), ptr(lp), ptr(mk),
+             raw_px.numel(), float(slope), float(intercept), float(soft[0]), float(soft[1]), float(lung[0]),
+             float(lung[1]), stream_ptr())
+    return (merged, sp, lp, mk) if want_parts else merged
+
+
+# ------------------------------------------------------------------ weight packing
+def pack_conv_weight(w: torch.Tensor, dtype=torch.float16):
+    Cout, Cin, kh, kw = w.shape
+    w = w.detach().to(torch.float32).contiguous()
+    with _dev(w):
+        out = torch.empty((Cout, kh * kw * Cin), dtype=dtype, device=w.device)
+        call("ducosy_pack_conv_weight", ptr(w), ptr(out), Cout, Cin, kh, kw, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def pack_upconv_weight(w: torch.Tensor, dtype=torch.float16):
+    Cout, Cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    w = w.detach().to(torch.float32).contiguous()
+    with _dev(w):
+        out = torch.empty((4 * Cout, 4 * Cin), dtype=dtype, device=w.device)
+        call("ducosy_pack_upconv_weight", ptr(w), ptr(out), Cout, Cin, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def pack_stem_weight(w: torch.Tensor, dtype=torch.float16):
+    Cout, Cin, kh, kw = w.shape
+    assert Cout == 64 and kh == 7 and kw == 7
+    w = w.detach().to(torch.float32).contiguous()
+    kpad = (49 * Cin + 63) // 64 * 64
+    with _dev(w):
+        out = torch.empty((64, kpad), dtype=dtype, device=w.device)
+        call("ducosy_pack_stem_weight", ptr(w), ptr(out), Cin, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def pack_out_weight(w: torch.Tensor, dtype=torch.float16):
+    assert tuple(w.shape) == (1, 64, 7, 7)
+    w = w.detach().to(torch.float32).contiguous()
+    with _dev(w):
+        out = torch.empty((7, 8, 64), dtype=dtype, device=w.device)
+        call("ducosy_pack_out_weight", ptr(w), ptr(out), dtype_code(dtype), stream_ptr())
+    return out
+
+
+# ------------------------------------------------------------------ convolutions
+def conv2d_nhwc(x_pad: torch.Tensor, w_packed: torch.Tensor, kh, kw, stride, want_stats=True, bias=None, act=ACT_NONE):
+    """x_pad [B,Hp,Wp,Cin] 16-bit (already padded) -> raw y [B,Ho,Wo,Cout], partials [B,Ho*Wo/128,3,Cout] | None."""
+    B, Hp, Wp, Cin = x_pad.shape
+    Cout = w_packed.shape[0]
+    assert x_pad.is_contiguous() and w_packed.is_contiguous() and w_packed.dtype == x_pad.dtype
+    Ho, Wo = (Hp - kh) // stride + 1, (Wp - kw) // stride + 1
+    with _dev(x_pad):
+        y = torch.empty((B, Ho, Wo, Cout), dtype=x_pad.dtype, device=x_pad.device)
+        partials = torch.empty((B, Ho * Wo // 128, 3, Cout), dtype=torch.float32, device=x_pad.device) if want_stats else None
+        call("ducosy_conv2d_nhwc", ptr(x_pad), ptr(w_packed), ptr(y), ptr(partials), ptr(bias), int(act), B, Hp, Wp, Cin,
+             Cout, kh, kw, stride, dtype_code(x_pad.dtype), stream_ptr())
+    return y, partials
+
+
+def upconv2x_nhwc(x_pad: torch.Tensor, w_packed4: torch.Tensor):
+    """Upsample(x2 nearest)+Conv3x3(pad 1) from the zero-padded source [B,Hs+2,Ws+2,Cin] -> raw y [B,2Hs,2Ws,Cout]."""
+    B, Hp, Wp, Cin = x_pad.shape
+    Hs, Ws = Hp - 2, Wp - 2
+    Cout = w_packed4.shape[0] // 4
+    with _dev(x_pad):
+        y = torch.empty((B, 2 * Hs, 2 * Ws, Cout), dtype=x_pad.dtype, device=x_pad.device)
+        partials = torch.empty((B, 4 * Hs * Ws // 128, 3, Cout), dtype=torch.float32, device=x_pad.device)
+        call("ducosy_upconv2x_nhwc", ptr(x_pad), ptr(w_packed4), ptr(y), ptr(partials), B, Hs, Ws, Cin, Cout,
+             dtype_code(x_pad.dtype), stream_ptr())
+    return y, partials
+
+
+def stem_im2col(x: torch.Tensor, dtype=torch.float16):
+    B, Cin, H, W = x.shape
+    x = x.to(torch.float32).contiguous()
+    kpad = (49 * Cin + 63) // 64 * 64
+    with _dev(x):
+        a = torch.empty((B, H, W, kpad), dtype=dtype, device=x.device)
+        call("ducosy_stem_im2col", ptr(x), ptr(a), B, Cin, H, W, dtype_code(dtype), stream_ptr())
+    return a
+
+
+def stem_im2col_hu(px: torch.Tensor, slope, intercept, lo, hi, dtype=torch.float16):
+    B, H, W = px.shape
+    with _dev(px):
+        a = torch.empty((B, H, W, 64), dtype=dtype, device=px.device)
+        call("ducosy_stem_im2col_hu", ptr(px), ptr(a), B, H, W, float(slope), float(intercept), float(lo), float(hi),
+             dtype_code(dtype), stream_ptr())
+    return a
+
+
+# ------------------------------------------------------------------ normalisation / attention
+def in_finalize(partials: torch.Tensor, npix: int, fc0=None, fc2=None):
+    B, tiles, _, Cn = partials.shape
+    with _dev(partials):
+        scale = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
+        shift = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
+        call("ducosy_in_finalize", ptr(partials), tiles, int(npix), ptr(scale), ptr(shift), ptr(fc0), ptr(fc2), B, Cn,
+             stream_ptr())
+    return scale, shift
+
+
+def in_apply_pad(y, scale, shift, pad, pad_mode, act):
+    B, H, W, Cn = y.shape
+    with _dev(y):
+        out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), dtype=y.dtype, device=y.device)
+        call("ducosy_in_apply_pad", ptr(y), ptr(scale), ptr(shift), ptr(out), B, H, W, Cn, pad, pad_mode, act,
+             dtype_code(y.dtype), stream_ptr())
+    return out
+
+
+def cbam_pool(y, scale, shift):
+    B, H, W, Cn = y.shape
+    with _dev(y):
+        pooled = torch.empty((B, H, W, 2), dtype=torch.float32, device=y.device)
+        call("ducosy_cbam_pool", ptr(y), ptr(scale), ptr(shift), ptr(pooled), B, H, W, Cn, dtype_code(y.dtype), stream_ptr())
+    return pooled
+
+
+def cbam_spatial_conv(pooled, w_sa):
+    B, H, W, _ = pooled.shape
+    w_sa = w_sa.detach().to(torch.float32).contiguous()
+    with _dev(pooled):
+        sa = torch.empty((B, H, W), dtype=torch.float32, device=pooled.device)
+        call("ducosy_cbam_spatial_conv", ptr(pooled), ptr(w_sa), ptr(sa), B, H, W, stream_ptr())
+    return sa
+
+
+def residual_apply_pad(y, scale, shift, sa, res_pad, res_pad_width, pad, pad_mode):
+    B, H, W, Cn = y.shape
+    with _dev(y):
+        out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), dtype=y.dtype, device=y.device)
+        call("ducosy_residual_apply_pad", ptr(y), ptr(scale), ptr(shift), ptr(sa), ptr(res_pad), res_pad_width, ptr(out),
+             B, H, W, Cn, pad, pad_mode, dtype_code(y.dtype), stream_ptr())
+    return out
+
+
+def out_conv7x7_tanh(x_pad, w_packed, bias):
+    B, Hp, Wp, Cn = x_pad.shape
+    assert Cn == 64
+    H, W = Hp - 6, Wp - 6
+    bias = bias.detach().to(torch.float32).contiguous()
+    with _dev(x_pad):
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=x_pad.device)
+        call("ducosy_out_conv7x7_tanh", ptr(x_pad), ptr(w_packed), ptr(bias), ptr(out), B, H, W,
+             dtype_code(x_pad.dtype), stream_ptr())
+    return out

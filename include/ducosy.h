@@ -1,0 +1,161 @@
+/* libducosy_sm100.so -- C ABI of the B200-native DuCoSy-GAN hot path.
+ *
+ * The reference (qqaazz0222/DuCoSy-GAN) is pure Python/PyTorch and has no FFI of its own; each entry point
+ * below names the reference code (file:line under /root/reference) whose arithmetic it replaces.  The Python
+ * host (ducosy_gan_b200/modules/model.py, ducosy_gan_b200/synthesis.py) binds these with ctypes and presents
+ * the reference's modules/model.py API on top.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in _host; the caller owns all memory, the library
+ *     never allocates or frees device memory and keeps no pointer after returning;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), makes no host sync and is
+ *     CUDA-graph capturable;
+ *   - return value: 0 on success, a negative DUCOSY_ERR_* code otherwise; ducosy_last_error() gives the
+ *     thread-local message.  Nothing aborts or throws across the ABI;
+ *   - activations are NHWC 16-bit (DUCOSY_F16 or DUCOSY_BF16), statistics / final output fp32;
+ *   - only sm_100 (B200) devices are accepted: there is no fallback path.
+ */
+#ifndef DUCOSY_H_
+#define DUCOSY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DUCOSY_VERSION 100
+
+enum { DUCOSY_F16 = 0, DUCOSY_BF16 = 1 };
+enum {
+  DUCOSY_OK = 0,
+  DUCOSY_ERR_SHAPE = -1,     /* unsupported shape / channel count */
+  DUCOSY_ERR_ALIGN = -2,     /* pointer alignment */
+  DUCOSY_ERR_WORKSPACE = -3, /* workspace too small */
+  DUCOSY_ERR_CUDA = -4,      /* CUDA runtime / driver error (launch failure, no device) */
+  DUCOSY_ERR_ARCH = -5,      /* device is not sm_100 */
+  DUCOSY_ERR_ARG = -6        /* null pointer / bad enum */
+};
+enum { DUCOSY_PAD_ZERO = 0, DUCOSY_PAD_REFLECT = 1 };
+enum { DUCOSY_ACT_NONE = 0, DUCOSY_ACT_RELU = 1, DUCOSY_ACT_LRELU02 = 2 };
+
+typedef void* ducosy_stream_t; /* cudaStream_t */
+
+int ducosy_version(void);
+const char* ducosy_last_error(void);
+/* 0 if the current device is sm_100, DUCOSY_ERR_ARCH / DUCOSY_ERR_CUDA otherwise. */
+int ducosy_check_device(void);
+
+/* ---------------------------------------------------------------- HU windowing / composite (bandwidth kernels) */
+
+/* preprocess_dicom, modules/preprocess.py:72-84: hu = float(px)*slope + intercept; for each of the two windows
+ * clip(hu, lo, hi) then 2*(x-lo)/(hi-lo)-1, every step rounded to fp32 exactly like numpy.  n stored values ->
+ * out_soft[n], out_lung[n] (fp32).  Either output may be NULL. */
+int ducosy_hu_window(const int16_t* px, float* out_soft, float* out_lung, long long n, float slope, float intercept,
+                     float soft_lo, float soft_hi, float lung_lo, float lung_hi, ducosy_stream_t stream);
+
+/* HU threshold candidates of the anatomical mask generator (modules/mask_generator.py:14-20,179-183):
+ * body = hu > -1000, lung = -1000 <= hu <= -300 & body, bone = hu >= 200 & body, uint8 {0,1}. NULL outputs are skipped. */
+int ducosy_hu_thresholds(const int16_t* px, uint8_t* body, uint8_t* lung, uint8_t* bone, long long n, float slope,
+                         float intercept, ducosy_stream_t stream);
+
+/* postprocess_tensor (modules/preprocess.py:96-111) for both generators followed by the complementary composite
+ * (generate.py:140-145,218-237) in ONE pass: y_soft / y_lung are the tanh outputs (fp32), raw_px the NCCT stored
+ * values.  merged[i] = lung_px if lung range, else soft_px if soft range, else raw (lung wins at HU == lung_hi).
+ * Optional outputs (may be NULL): soft_px / lung_px (the de-windowed stored values, truncation toward zero) and
+ * masks (bit0 = soft range, bit1 = lung range).  Bit-exact with the numpy reference for the same y. */
+int ducosy_dewindow_composite(const int16_t* raw_px, const float* y_soft, const float* y_lung, int16_t* merged,
+                              int16_t* soft_px, int16_t* lung_px, uint8_t* masks, long long n, float slope,
+                              float intercept, float soft_lo, float soft_hi, float lung_lo, float lung_hi,
+                              ducosy_stream_t stream);
+
+/* ---------------------------------------------------------------- layer kernels (exported for tests and reuse) */
+
+/* Pack an OIHW fp32 conv weight into the K-major 16-bit GEMM operand [Cout][kh*kw*Cin] (k = (r*kw+s)*Cin + c). */
+int ducosy_pack_conv_weight(const float* w_oihw, void* packed, int Cout, int Cin, int kh, int kw, int dtype,
+                            ducosy_stream_t stream);
+/* Pack the 3x3 weight of "Upsample(x2, nearest) + Conv2d(3x3, pad 1)" (modules/model.py:108) into four
+ * phase-specific 2x2 kernels on the source grid: [4*Cout][4*Cin], phase = py*2+px, tap = a*2+b. */
+int ducosy_pack_upconv_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
+/* Pack the 7x7 stem weight [64][Cin][7][7] into [64][Kpad], Kpad = roundup(49*Cin, 64), k = c*49 + r*7 + s. */
+int ducosy_pack_stem_weight(const float* w_oihw, void* packed, int Cin, int dtype, ducosy_stream_t stream);
+
+/* Convolution as implicit GEMM on tcgen05 tensor cores.
+ *   in      : NHWC 16-bit, already padded: [B][Hp][Wp][Cin], Cin % 64 == 0
+ *   w       : packed by ducosy_pack_conv_weight
+ *   out     : raw (pre-normalisation) output NHWC [B][Ho][Wo][Cout]
+ *   partials: fp32 [B][Ho*Wo/128][3][Cout] per-tile per-channel (sum, sum of squares, max), or NULL
+ *   kh,kw,stride: 3,3,1 (input padded by 1) | 3,3,2 (zero-padded by 1) | 4,4,2 (zero-padded by 1) | 1,1,1
+ *   bias/act: NULL/0 for convs followed by InstanceNorm; bias + LeakyReLU(0.2) when act == DUCOSY_ACT_LRELU02. */
+int ducosy_conv2d_nhwc(const void* in, const void* w, void* out, float* partials, const float* bias, int act, int B,
+                       int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, int dtype, ducosy_stream_t stream);
+/* Upsample(x2)+Conv3x3 (modules/model.py:108-109) from the zero-padded source [B][Hs+2][Ws+2][Cin];
+ * out [B][2Hs][2Ws][Cout]; partials [B][4*Hs*Ws/128][3][Cout]. */
+int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, void* out, float* partials, int B, int Hs, int Ws,
+                         int Cin, int Cout, int dtype, ducosy_stream_t stream);
+
+/* im2col for the 7x7 reflect-padded stem (modules/model.py:94): x fp32 NCHW [B][Cin][H][W] -> A [B*H*W][Kpad]. */
+int ducosy_stem_im2col(const float* x_nchw, void* a_mat, int B, int Cin, int H, int W, int dtype, ducosy_stream_t stream);
+/* Same, fused with the HU windowing of modules/preprocess.py:72-84 (Cin = 1): stored px int16 [B][H][W] in. */
+int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, float slope, float intercept, float lo,
+                          float hi, int dtype, ducosy_stream_t stream);
+
+/* InstanceNorm statistics (modules/model.py InstanceNorm2d: biased var, eps 1e-5) from the conv partials:
+ * scale[b][c] = rstd, shift[b][c] = -mean*rstd.  When fc0/fc2 are given (CBAM channel attention,
+ * modules/model.py:13-24: fc0 [C/16][C], fc2 [C][C/16], fp32) the channel attention
+ * s = sigmoid(fc(avgpool) + fc(maxpool)) of the NORMALISED map is folded in: scale *= s, shift *= s. */
+int ducosy_in_finalize(const float* partials, int tiles_per_sample, int npix_per_sample, float* scale, float* shift,
+                       const float* fc0, const float* fc2, int B, int C, ducosy_stream_t stream);
+
+/* out_pad[b][y+p][x+p][c] = act(y*scale + shift), borders filled by reflection or zeros. */
+int ducosy_in_apply_pad(const void* y, const float* scale, const float* shift, void* out_pad, int B, int H, int W, int C,
+                        int pad, int pad_mode, int act, int dtype, ducosy_stream_t stream);
+
+/* CBAM spatial attention (modules/model.py:34-39), C == 256:
+ *   pool : pooled[b][y][x] = (mean_c v, max_c v), v = y*scale + shift
+ *   conv : sa = sigmoid(conv7x7_{2->1, zero pad 3}(pooled)), w_sa = spatial_attention.conv.weight [1][2][7][7] fp32
+ *   apply: out_pad = res_pad(interior) + v * sa   (sa == NULL: plain ResidualBlock, modules/model.py:65) */
+int ducosy_cbam_pool(const void* y, const float* scale, const float* shift, float* pooled, int B, int H, int W, int C,
+                     int dtype, ducosy_stream_t stream);
+int ducosy_cbam_spatial_conv(const float* pooled, const float* w_sa, float* sa, int B, int H, int W, ducosy_stream_t stream);
+int ducosy_residual_apply_pad(const void* y, const float* scale, const float* shift, const float* sa,
+                              const void* res_pad, int res_pad_width, void* out_pad, int B, int H, int W, int C, int pad,
+                              int pad_mode, int dtype, ducosy_stream_t stream);
+
+/* Output conv (modules/model.py:112): reflect-padded input [B][H+6][W+6][64] 16-bit, weight [1][64][7][7] fp32,
+ * bias[1] fp32 -> out fp32 [B][H][W] = tanh(conv + bias).  w_packed from ducosy_pack_out_weight. */
+int ducosy_pack_out_weight(const float* w_oihw, void* packed, int dtype, ducosy_stream_t stream);
+int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed, const float* bias, float* out, int B, int H, int W,
+                            int dtype, ducosy_stream_t stream);
+
+/* ---------------------------------------------------------------- whole-generator entry points */
+
+typedef struct {
+  int input_channels;      /* Generator(input_channels=...) modules/model.py:92 */
+  int num_residual_blocks; /* default 9 */
+  int use_cbam;            /* default 1 */
+  int dtype;               /* DUCOSY_F16 | DUCOSY_BF16 (16-bit operand type of the tensor-core convs) */
+} ducosy_gen_config;
+
+/* Number of parameter tensors in state_dict order (modules/model.py:92-113) and packed-cache size in bytes. */
+int ducosy_generator_num_params(const ducosy_gen_config* cfg);
+size_t ducosy_generator_packed_bytes(const ducosy_gen_config* cfg);
+size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg, int B, int H, int W);
+/* params_host: host array of DEVICE pointers to the fp32 parameters in state_dict order. */
+int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params_host, int num_params, void* packed,
+                          ducosy_stream_t stream);
+/* Generator.forward (modules/model.py:114): x fp32 NCHW [B][Cin][H][W] -> out fp32 [B][1][H][W]. */
+int ducosy_generator_forward(const ducosy_gen_config* cfg, const void* packed, const float* x_nchw, float* out, int B,
+                             int H, int W, void* workspace, size_t workspace_bytes, ducosy_stream_t stream);
+/* Same with the input taken straight from stored pixel values through the HU window (generate.py:91-96), Cin = 1. */
+int ducosy_generator_forward_hu(const ducosy_gen_config* cfg, const void* packed, const int16_t* px, float slope,
+                                float intercept, float hu_lo, float hu_hi, float* out, int B, int H, int W,
+                                void* workspace, size_t workspace_bytes, ducosy_stream_t stream);
+/* Number of kernels one forward launches (for bench accounting). */
+int ducosy_generator_num_launches(const ducosy_gen_config* cfg);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DUCOSY_H_ */

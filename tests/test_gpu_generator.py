@@ -1,0 +1,93 @@
+"""Generator / dual-HU path parity on the B200 (pytest -m gpu): CUDA product through the drop-in
+modules/model.py API and the C ABI, checked against the oracle and the committed golden vectors."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ducosy_oracle as orc  # noqa: E402
+
+# Stated tolerance (tanh units) of the 16-bit-operand / fp32-accumulate path against the fp32 oracle.
+# 1 HU = 0.005 (soft-tissue window, 400 HU span) or 0.00235 (lung window, 850 HU span).
+TOL_TANH = {"fp16": 6e-3, "bf16": 5e-2}
+
+
+def _x(seed, shape):
+    return torch.from_numpy(np.random.Generator(np.random.PCG64(seed)).uniform(-1, 1, size=shape).astype(np.float32))
+
+
+def _gen(cin, nb, cbam, sd):
+    from ducosy_gan_b200.modules.model import Generator
+    G = Generator(cin, nb, cbam)
+    G.load_state_dict(sd, strict=True)
+    return G.cuda().eval()
+
+
+@pytest.mark.parametrize("precision", ["fp16", "bf16"])
+def test_generator_matches_golden_128(golden_dir, precision, monkeypatch):
+    monkeypatch.setenv("DUCOSY_PRECISION", precision)
+    g = np.load(os.path.join(golden_dir, "gen_c2_b1_cbam_128.npz"))
+    sd = orc.make_state_dict(orc.generator_param_shapes(2, 1, True), int(g["wseed"]), attn_std=float(g["attn_std"]))
+    G = _gen(2, 1, True, sd)
+    with torch.no_grad():
+        y = G(_x(int(g["xseed"]), (1, 2, 128, 128)).cuda()).cpu().numpy()
+    err = np.abs(y - g["y"]).max()
+    print(f"gen 128 golden [{precision}]: max abs err {err:.3e}")
+    assert err < TOL_TANH[precision]
+
+
+@pytest.mark.parametrize("cin,nb,cbam,B,H,W", [(1, 2, True, 2, 128, 128), (3, 1, False, 1, 128, 256), (1, 0, True, 1, 256, 128)])
+def test_generator_matches_oracle_small(cin, nb, cbam, B, H, W):
+    sd = orc.make_state_dict(orc.generator_param_shapes(cin, nb, cbam), 77, attn_std=0.2)
+    G = _gen(cin, nb, cbam, sd)
+    x = _x(5, (B, cin, H, W))
+    with torch.no_grad():
+        y = G(x.cuda()).cpu()
+        ref = orc.generator_forward(sd, x, nb, cbam)
+    err = (y - ref).abs().max().item()
+    print(f"gen cin={cin} nb={nb} cbam={cbam} {H}x{W}: max abs err {err:.3e}")
+    assert err < TOL_TANH["fp16"]
+
+
+def test_generator_full_size_vs_oracle_and_golden(golden_dir):
+    g = np.load(os.path.join(golden_dir, "gen_full_512.npz"))
+    sd = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), int(g["wseed"]), attn_std=float(g["attn_std"]))
+    G = _gen(1, 9, True, sd)
+    px = orc.synthetic_volume(1, 512, 512, seed=int(g["vseed"]))
+    x = torch.from_numpy(orc.hu_window(px[0], 1.0, -1024.0, *orc.SOFT_HU).astype(np.float32))[None, None]
+    with torch.no_grad():
+        y = G(x.cuda())
+        y_hu = G.forward_hu(torch.from_numpy(px).cuda(), 1.0, -1024.0, *orc.SOFT_HU)
+        ref = orc.generator_forward(sd, x)
+    assert torch.equal(y, y_hu)                       # fused-window entry == windowed tensor entry
+    y = y.cpu()
+    err = (y - ref).abs().max().item()
+    err_hu = orc.hu_error(y.numpy(), ref.numpy(), *orc.SOFT_HU)
+    print(f"gen 512 full: max abs err {err:.3e} tanh = {err_hu:.2f} HU (soft window); mean abs {float((y - ref).abs().mean()):.2e}")
+    assert np.abs(y[0, 0].numpy()[::8, ::8] - g["y_sub"]).max() < TOL_TANH["fp16"]
+    assert err < TOL_TANH["fp16"]
+
+
+def test_generator_is_deterministic_and_batch_invariant():
+    sd = orc.make_state_dict(orc.generator_param_shapes(1, 2, True), 5, attn_std=0.2)
+    G = _gen(1, 2, True, sd)
+    x = _x(9, (3, 1, 128, 128)).cuda()
+    with torch.no_grad():
+        a, b = G(x), G(x)
+        single = G(x[1:2].contiguous())
+    assert torch.equal(a, b)
+    assert torch.equal(a[1:2], single)               # InstanceNorm is per sample: no cross-sample coupling
+
+
+def test_load_state_dict_invalidates_packed_weights():
+    shapes = orc.generator_param_shapes(1, 1, True)
+    G = _gen(1, 1, True, orc.make_state_dict(shapes, 1))
+    x = _x(3, (1, 1, 128, 128)).cuda()
+    with torch.no_grad():
+        y1 = G(x)
+        G.load_state_dict(orc.make_state_dict(shapes, 2))
+        y2 = G(x)
+    assert not torch.equal(y1, y2)
