@@ -164,7 +164,8 @@ using namespace ducosy;
 extern "C" int ducosy_hu_window(const int16_t* px, float* out_soft, float* out_lung, long long n, float slope,
                                 float intercept, float soft_lo, float soft_hi, float lung_lo, float lung_hi,
                                 ducosy_stream_t stream) {
-  DUCOSY_CHECK(px != nullptr && n >= 0, DUCOSY_ERR_ARG, "hu_window: null input");
+  if (n == 0) return 0;
+  DUCOSY_CHECK(px != nullptr && n > 0, DUCOSY_ERR_ARG, "hu_window: null input");
   DUCOSY_CHECK(aligned16(px) && aligned16(out_soft) && aligned16(out_lung), DUCOSY_ERR_ALIGN,
                "hu_window: buffers must be 16-byte aligned");
   if (n == 0) return 0;
@@ -176,7 +177,8 @@ extern "C" int ducosy_hu_window(const int16_t* px, float* out_soft, float* out_l
 
 extern "C" int ducosy_hu_thresholds(const int16_t* px, uint8_t* body, uint8_t* lung, uint8_t* bone, long long n,
                                     float slope, float intercept, ducosy_stream_t stream) {
-  DUCOSY_CHECK(px != nullptr && n >= 0, DUCOSY_ERR_ARG, "hu_thresholds: null input");
+  if (n == 0) return 0;
+  DUCOSY_CHECK(px != nullptr && n > 0, DUCOSY_ERR_ARG, "hu_thresholds: null input");
   DUCOSY_CHECK(aligned16(px) && aligned16(body) && aligned16(lung) && aligned16(bone), DUCOSY_ERR_ALIGN,
                "hu_thresholds: buffers must be 16-byte aligned");
   if (n == 0) return 0;
@@ -189,7 +191,8 @@ extern "C" int ducosy_dewindow_composite(const int16_t* raw_px, const float* y_s
                                          int16_t* merged, int16_t* soft_px, int16_t* lung_px, uint8_t* masks,
                                          long long n, float slope, float intercept, float soft_lo, float soft_hi,
                                          float lung_lo, float lung_hi, ducosy_stream_t stream) {
-  DUCOSY_CHECK(raw_px && y_soft && y_lung && merged && n >= 0, DUCOSY_ERR_ARG, "dewindow_composite: null pointer");
+  if (n == 0) return 0;
+  DUCOSY_CHECK(raw_px && y_soft && y_lung && merged && n > 0, DUCOSY_ERR_ARG, "dewindow_composite: null pointer");
   DUCOSY_CHECK(slope != 0.0f, DUCOSY_ERR_ARG, "dewindow_composite: RescaleSlope is 0");
   DUCOSY_CHECK(aligned16(raw_px) && aligned16(y_soft) && aligned16(y_lung) && aligned16(merged) && aligned16(soft_px) &&
                    aligned16(lung_px) && aligned16(masks),

@@ -1,0 +1,132 @@
+"""Volume-level dual-HU synthesis: the arithmetic of the reference's ``generate()`` + ``synthesis()``
+(generate.py:89-102 and generate.py:213-237) without the per-slice DICOM round trip.
+
+    raw stored values [S,H,W] int16
+        -> HU window (soft-tissue, lung)         preprocess.py:72-84      (fused into the stem im2col kernel)
+        -> soft-tissue Generator, lung Generator  model.py:92-115          (two CUDA streams, batched slices)
+        -> de-window + complementary composite    preprocess.py:96-111, generate.py:218-237   (one kernel)
+        -> merged stored values [S,H,W] int16
+
+Slices are independent, so a volume shards across ranks by contiguous slice ranges with no collective
+(``shard_range``).  DICOM I/O stays with the caller (out of scope).
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+
+from . import ops
+from .modules.model import Generator
+
+SOFT_HU = (-150.0, 250.0)   # modules/argmanager.py:121-136
+LUNG_HU = (-1000.0, -150.0)  # modules/argmanager.py:138-152
+
+
+def shard_range(num_slices: int, rank: int, world_size: int):
+    """Contiguous slice range [lo, hi) of ``rank``; ranges are disjoint, ordered and cover [0, S)."""
+    if not (0 <= rank < world_size):
+        raise ValueError("rank out of range")
+    return num_slices * rank // world_size, num_slices * (rank + 1) // world_size
+
+
+class DualHUSynthesizer:
+    """Both A2B generators + composite for whole volumes on one GPU.
+
+    soft_model / lung_model: ``ducosy_gan_b200.modules.model.Generator(input_channels=1)`` instances holding the
+    checkpoints (as generate.py:29-49 builds them).  ``batch_slices`` slices go through each generator at once.
+    """
+
+    def __init__(self, soft_model: Generator, lung_model: Generator, soft_hu=SOFT_HU, lung_hu=LUNG_HU,
+                 batch_slices: int = 8, device=None):
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.soft_model, self.lung_model = soft_model, lung_model
+        self.soft_hu, self.lung_hu = tuple(map(float, soft_hu)), tuple(map(float, lung_hu))
+        self.batch_slices = int(batch_slices)
+        self._streams = None
+        self._bufs = {}
+
+    # ------------------------------------------------------------------ helpers
+    def _engines(self):
+        es = self.soft_model._engine(self.device)
+        el = self.lung_model._engine(self.device)
+        es.sync_weights(self.soft_model._ordered_params())
+        el.sync_weights(self.lung_model._ordered_params())
+        return es, el
+
+    def _buffers(self, B, H, W):
+        key = (B, H, W)
+        if key not in self._bufs:
+            self._bufs.clear()
+            mk = lambda: torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
+            self._bufs[key] = (mk(), mk())
+        return self._bufs[key]
+
+    def launches_per_chunk(self):
+        import ctypes as C
+        es, el = self._engines()
+        return (es.lib.ducosy_generator_num_launches(C.byref(es.cfg)) +
+                el.lib.ducosy_generator_num_launches(C.byref(el.cfg)) + 1)
+
+    # ------------------------------------------------------------------ device-resident volume
+    def synthesize_device(self, raw_px: torch.Tensor, slope=1.0, intercept=-1024.0, out: torch.Tensor | None = None):
+        """raw_px: int16 [S,H,W] on this GPU -> merged int16 [S,H,W] (same device).  Asynchronous."""
+        if raw_px.dtype != torch.int16 or raw_px.dim() != 3 or not raw_px.is_cuda:
+            raise RuntimeError("synthesize_device expects an int16 [S,H,W] CUDA tensor of stored pixel values")
+        raw_px = raw_px.contiguous()
+        S, H, W = raw_px.shape
+        if out is None:
+            out = torch.empty_like(raw_px)
+        es, el = self._engines()
+        with torch.cuda.device(self.device):
+            if self._streams is None:
+                self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            s_soft, s_lung = self._streams
+            cur = torch.cuda.current_stream()
+            B = min(self.batch_slices, S)
+            ys, yl = self._buffers(B, H, W)
+            # make sure both engine workspaces exist before the side streams use them
+            es.workspace(B, H, W)
+            el.workspace(B, H, W)
+            for lo in range(0, S, B):
+                n = min(B, S - lo)
+                chunk = raw_px[lo:lo + n]
+                if n != B:  # ragged tail: run it as its own (smaller) batch after the pipeline drains
+                    cur.wait_stream(s_soft)
+                    cur.wait_stream(s_lung)
+                    ys_t = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
+                    yl_t = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
+                    es._ws.clear()
+                    el._ws.clear()
+                    es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys_t)
+                    el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl_t)
+                    ops.dewindow_composite(chunk, ys_t, yl_t, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+                    continue
+                s_soft.wait_stream(cur)
+                s_lung.wait_stream(cur)
+                with torch.cuda.stream(s_soft):
+                    es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys)
+                with torch.cuda.stream(s_lung):
+                    el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl)
+                cur.wait_stream(s_soft)
+                cur.wait_stream(s_lung)
+                ops.dewindow_composite(chunk, ys, yl, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+        return out
+
+    # ------------------------------------------------------------------ host volume (the end-to-end call)
+    def synthesize_volume(self, raw_px, slope=1.0, intercept=-1024.0, out_host: torch.Tensor | None = None):
+        """raw_px: int16 [S,H,W] numpy array or (ideally pinned) CPU tensor -> merged int16 CPU tensor.
+        Host->device and device->host copies are part of this call (the reference's .to(device)/.cpu())."""
+        if isinstance(raw_px, np.ndarray):
+            raw_px = torch.from_numpy(np.ascontiguousarray(raw_px))
+        if raw_px.is_cuda:
+            return self.synthesize_device(raw_px, slope, intercept)
+        if raw_px.dtype != torch.int16 or raw_px.dim() != 3:
+            raise RuntimeError("synthesize_volume expects int16 [S,H,W] stored pixel values")
+        with torch.cuda.device(self.device):
+            dev_in = raw_px.to(self.device, non_blocking=True)
+            dev_out = self.synthesize_device(dev_in, slope, intercept)
+            if out_host is None:
+                out_host = torch.empty(raw_px.shape, dtype=torch.int16, pin_memory=True)
+            out_host.copy_(dev_out, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return out_host
