@@ -1,0 +1,258 @@
+#!/usr/bin/env python
+"""bench.py -- dual-HU synthesis throughput (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload (BASELINE.json configs[1]): soft-tissue + lung A2B generators (input_channels=1, 9 CBAM residual
+blocks, seeded random weights) + de-window + complementary composite over a synthetic 300-slice 512x512
+NCCT volume.  One step = one pass over the volume.  With N ranks every rank synthesizes its own 300-slice
+volume (independent slices, no data-path collective) => weak scaling; value = all slices / max-over-ranks time.
+
+One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+S, H, W = 300, 512, 512
+SLOPE, INTERCEPT = 1.0, -1024.0
+GFLOP_PER_SLICE = 2 * 447.82            # two generators, Cin = 1, nominal conv FLOPs
+METRIC = "dual_hu_synth_slices_per_sec"
+UNIT = "slices/s"
+WORKLOAD = "dual-HU generate: soft-tissue + lung Generator(Cin=1, 9 CBAM blocks) + composite, 300x512x512 int16 volume per GPU"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return {"hbm_gbs": p["hbm_gbs"], "tf_burst": p["bf16_tflops"], "tf_sustained": p["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons every 200 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.proc = index, [], None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+        self.join(timeout=2)
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 7 for n, v in zip(names, r[3:7]) if v.lower().startswith("active")})
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(sm)}
+
+
+def make_models(device, seed=1234):
+    """Seeded random-init generators (no shipped checkpoints: reference .gitignore:220-221)."""
+    from ducosy_gan_b200.modules.model import Generator, weights_init_normal
+    torch.manual_seed(seed)
+    soft = Generator(input_channels=1, num_residual_blocks=9)      # generate.py:29-30
+    lung = Generator(input_channels=1, num_residual_blocks=9)
+    soft.apply(weights_init_normal)
+    lung.apply(weights_init_normal)
+    return soft.to(device).eval(), lung.to(device).eval()
+
+
+def synthetic_volume(seed):
+    g = np.random.Generator(np.random.PCG64(seed))
+    return g.integers(0, 2500, size=(S, H, W), dtype=np.int16)     # HU in [-1024, 1475] at slope 1 / intercept -1024
+
+
+def time_dominant_kernel(device, batch, iters=20):
+    """CUDA-event timing of the dominant kernel alone: the 3x3 256->256 residual-block convolution
+    (tcgen05 implicit GEMM) at the batch the synthesizer uses.  Returns (avg seconds, FLOPs per launch)."""
+    from ducosy_gan_b200 import ops
+    dt = torch.float16 if os.environ.get("DUCOSY_PRECISION", "fp16") == "fp16" else torch.bfloat16
+    x = torch.randn((batch, 130, 130, 256), device=device).to(dt)
+    w = ops.pack_conv_weight(torch.randn((256, 256, 3, 3), device=device) * 0.02, dt)
+    for _ in range(3):
+        ops.conv2d_nhwc(x, w, 3, 3, 1)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        ops.conv2d_nhwc(x, w, 3, 3, 1)
+    e1.record()
+    torch.cuda.synchronize()
+    flops = 2.0 * batch * 128 * 128 * 256 * 256 * 9
+    return e0.elapsed_time(e1) / 1e3 / iters, flops
+
+
+def cpu_baseline_sample(n_slices=3):
+    """Oracle (CPU restatement of the reference path) timed on the host cores on a bounded sample."""
+    from oracle import ducosy_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_s = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1234)
+    sd_l = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1235)
+    vol = synthetic_volume(0)[: n_slices + 1]
+    orc.dual_hu_synthesize(vol[:1], SLOPE, INTERCEPT, sd_s, sd_l)          # warm-up slice
+    t0 = time.perf_counter()
+    orc.dual_hu_synthesize(vol[1:], SLOPE, INTERCEPT, sd_s, sd_l)
+    dt = time.perf_counter() - t0
+    return {"value": n_slices / dt, "unit": UNIT, "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n_slices} of the {S} slices (512x512), fp32 torch-CPU oracle of the same path, after 1 warm-up slice"}
+
+
+def run_reference(args, rank):
+    """--impl reference: the reference's CPU path (oracle port; the reference itself cannot travel to the box)."""
+    if rank != 0:
+        return
+    from oracle import ducosy_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    sd_s = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1234)
+    sd_l = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1235)
+    n = 2                                                                    # slices per step (bounded sample)
+    vol = synthetic_volume(0)[:n]
+    for _ in range(min(args.warmup, 1)):
+        orc.dual_hu_synthesize(vol[:1], SLOPE, INTERCEPT, sd_s, sd_l)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        orc.dual_hu_synthesize(vol, SLOPE, INTERCEPT, sd_s, sd_l)
+    dt = time.perf_counter() - t0
+    val = n * args.steps / dt
+    cores = torch.get_num_threads()
+    sample = f"{n} slices (512x512) per step of the {S}-slice volume; fp32 torch-CPU oracle port of the reference path"
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch-slices", type=int, default=int(os.environ.get("DUCOSY_BATCH_SLICES", "10")))
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU fallback (use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    from ducosy_gan_b200.synthesis import DualHUSynthesizer
+    soft, lung = make_models(device)
+    synth = DualHUSynthesizer(soft, lung, batch_slices=args.batch_slices, device=device)
+    host_vol = torch.from_numpy(synthetic_volume(rank)).pin_memory()
+    host_out = torch.empty_like(host_vol).pin_memory()
+    dev_vol = host_vol.to(device)
+    dev_out = torch.empty_like(dev_vol)
+
+    def barrier():
+        if world > 1:
+            dist.barrier(device_ids=[local_rank])
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        sec = torch.tensor([e0.elapsed_time(e1) / 1e3], device=device)
+        if world > 1:
+            dist.all_reduce(sec, op=dist.ReduceOp.MAX)
+        return float(sec.item())
+
+    dev_step = lambda: synth.synthesize_device(dev_vol, SLOPE, INTERCEPT, out=dev_out)
+    e2e_step = lambda: synth.synthesize_volume(host_vol, SLOPE, INTERCEPT, out_host=host_out)
+
+    for _ in range(args.warmup):
+        dev_step()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    sec = timed(dev_step, args.steps)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_step()
+    sec_e2e = timed(e2e_step, args.steps)
+
+    value = world * S * args.steps / sec
+    e2e_value = world * S * args.steps / sec_e2e
+    chunks = (S + args.batch_slices - 1) // args.batch_slices
+    launches = synth.launches_per_chunk() * chunks * args.steps
+
+    if rank == 0:
+        pk = peaks()
+        ksec, kflops = time_dominant_kernel(device, args.batch_slices)
+        achieved = kflops / ksec / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": os.environ.get("DUCOSY_PRECISION", "fp16") + " operands, fp32 accumulate",
+            "data": "synthetic",
+            "config": {"workload": WORKLOAD, "slices_per_gpu": S, "batch_slices": args.batch_slices,
+                       "weights": "random init (weights_init_normal, seed 1234)",
+                       "l2": "inputs larger than L2 (157 MB volume, >2 GB of activations per batch)",
+                       "parallelism": f"slice-sharded x{world}, no collective"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": S * H * W * 2, "d2h_bytes_per_step": S * H * W * 2},
+            "gpu_launches": launches,
+            "clocks": clocks,
+            "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<256> (3x3 256->256 residual-block conv)",
+                         "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
+                         "traffic": None, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
+                         "path_frac_of_sustained": value / world * GFLOP_PER_SLICE / 1e3 / pk["tf_sustained"]},
+        }
+        if world == 1 and not args.skip_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_sample()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

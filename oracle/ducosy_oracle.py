@@ -379,3 +379,33 @@ def contrast_edge_loss(pred, target, source=None):
     ptop = torch.topk(pe.flatten(), int(pe.numel() * k)).values.mean()
     ttop = torch.topk(te.flatten(), int(te.numel() * k)).values.mean()
     return stats + torch.abs(ptop - ttop)
+
+
+def generator_forward_rounded(sd, x, nb=9, cbam=True, dt=torch.float16):
+    """generator_forward with activations / conv weights rounded to the 16-bit operand type ``dt`` at the points
+    where the CUDA path stores them (fp32 arithmetic otherwise).  Its distance to ``generator_forward`` is the
+    quantisation noise a 16-bit-operand implementation must show; used to tell that noise from real defects."""
+    r = lambda t: t.to(dt).float()
+    inorm = instance_norm
+    h = F.conv2d(r(F.pad(x, (3, 3, 3, 3), mode="reflect")), r(sd["model.1.weight"]))
+    h = r(F.relu(inorm(r(h))))
+    h = r(F.relu(inorm(r(F.conv2d(h, r(sd["model.4.weight"]), stride=2, padding=1)))))
+    h = r(F.relu(inorm(r(F.conv2d(h, r(sd["model.7.weight"]), stride=2, padding=1)))))
+    idx = 10
+    for _ in range(nb):
+        p = f"model.{idx}"
+        t = r(F.conv2d(F.pad(h, (1, 1, 1, 1), mode="reflect"), r(sd[p + ".block.1.weight"])))
+        t = r(F.relu(inorm(t)))
+        t = r(F.conv2d(F.pad(t, (1, 1, 1, 1), mode="reflect"), r(sd[p + ".block.5.weight"])))
+        t = inorm(t)
+        if cbam:
+            t = channel_attention(t, sd[p + ".cbam.channel_attention.fc.0.weight"], sd[p + ".cbam.channel_attention.fc.2.weight"])
+            t = spatial_attention(t, sd[p + ".cbam.spatial_attention.conv.weight"])
+        h = r(h + t)
+        idx += 1
+    for _ in range(2):
+        h = F.interpolate(h, scale_factor=2, mode="nearest")
+        h = r(F.relu(inorm(r(F.conv2d(h, r(sd[f"model.{idx + 1}.weight"]), padding=1)))))
+        idx += 4
+    h = F.conv2d(F.pad(h, (3, 3, 3, 3), mode="reflect"), r(sd[f"model.{idx + 1}.weight"]), sd[f"model.{idx + 1}.bias"])
+    return torch.tanh(h)
