@@ -109,7 +109,7 @@ GenLayout make_layout(const ducosy_gen_config& c) {
 }
 
 struct GenWorkspace {
-  size_t a_stem, y0, p0, y1, p1, y2a, y2b, pa, pb, pc, p_out, partials, scale, shift, pooled, sa, total;
+  size_t a_stem, y0, p0, y1, p1, y2a, y2b, pa, pb, pc, p_out, partials, scale, shift, chmax, pooled, sa, total;
 };
 
 GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
@@ -138,6 +138,7 @@ GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
   w.partials = take(size_t(B) * (HW / 128) * 3 * 64 * 4);
   w.scale = take(size_t(B) * 256 * 4);
   w.shift = take(size_t(B) * 256 * 4);
+  w.chmax = take(size_t(B) * 256 * 4);
   w.pooled = take(size_t(B) * H4 * W4 * 2 * 4);
   w.sa = take(size_t(B) * H4 * W4 * 4);
   w.total = off;
@@ -158,11 +159,11 @@ int check_gen_shape(const ducosy_gen_config& c, int B, int H, int W) {
   return 0;
 }
 
-int run_conv_in(ConvPlan& p, float* scale, float* shift, const float* fc0, const float* fc2, int C, int npix,
-                cudaStream_t st) {
+int run_conv_in(ConvPlan& p, float* scale, float* shift, const float* fc0, const float* fc2, float* chmax, int C,
+                int npix, cudaStream_t st) {
   DUCOSY_TRY(launch_conv_gemm(p, st));
   return ducosy_in_finalize(p.partials, conv_tiles_per_sample(p.num_phases, p.Hg, p.Wg), npix, scale, shift, fc0, fc2,
-                            p.B, C, st);
+                            chmax, p.B, C, st);
 }
 
 int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const float* x, const int16_t* px,
@@ -182,6 +183,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   float* partials = reinterpret_cast<float*>(base + w.partials);
   float* scale = reinterpret_cast<float*>(base + w.scale);
   float* shift = reinterpret_cast<float*>(base + w.shift);
+  float* chmax = reinterpret_cast<float*>(base + w.chmax);
   float* pooled = reinterpret_cast<float*>(base + w.pooled);
   float* sa = reinterpret_cast<float*>(base + w.sa);
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
@@ -201,7 +203,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.stem; p.Cout = 64; p.num_phases = 1; p.num_taps = 1;
     p.Hg = H; p.Wg = W; p.out = P(w.y0); p.Ho = H; p.Wo = W; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, 64, H * W, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 64, H * W, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p0), B, H, W, 64, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   }
   // ---- down 1: 3x3 s2 p1 64 -> 128, IN, ReLU   modules/model.py:96-98
@@ -211,7 +213,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.d1; p.Cout = 128; fill_taps_3x3(p);
     p.Hg = H2; p.Wg = W2; p.out = P(w.y1); p.Ho = H2; p.Wo = W2; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, 128, H2 * W2, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 128, H2 * W2, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y1), scale, shift, P(w.p1), B, H2, W2, 128, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   }
   // ---- down 2: 3x3 s2 p1 128 -> 256, IN, ReLU
@@ -222,7 +224,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.d2; p.Cout = 256; fill_taps_3x3(p);
     p.Hg = H4; p.Wg = W4; p.out = P(w.y2a); p.Ho = H4; p.Wo = W4; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, 256, H4 * W4, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 256, H4 * W4, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y2a), scale, shift, P(cur), B, H4, W4, 256, 1,
                                    nb > 0 ? DUCOSY_PAD_REFLECT : DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   }
@@ -233,12 +235,12 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.c1[i]; p.Cout = 256; fill_taps_3x3(p);
     p.Hg = H4; p.Wg = W4; p.out = P(w.y2a); p.Ho = H4; p.Wo = W4; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, 256, H4 * W4, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 256, H4 * W4, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y2a), scale, shift, P(w.pc), B, H4, W4, 256, 1, DUCOSY_PAD_REFLECT, DUCOSY_ACT_RELU, dt, st));
     p.in = P(w.pc); p.w = pk + L.c2[i]; p.out = P(w.y2b);
     const float* fc0 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc0[i]) : nullptr;
     const float* fc2 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc2[i]) : nullptr;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, 256, H4 * W4, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, chmax, 256, H4 * W4, st));
     const float* sa_ptr = nullptr;
     if (c.use_cbam) {
       DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
@@ -251,11 +253,11 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   }
   // ---- up 1: nearest x2 + 3x3 p1 256 -> 128, IN, ReLU   modules/model.py:107-111
   DUCOSY_TRY(ducosy_upconv2x_nhwc(P(cur), pk + L.up1, P(w.y1), partials, B, H4, W4, 256, 128, dt, st));
-  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H4, W4), H2 * W2, scale, shift, nullptr, nullptr, B, 128, st));
+  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H4, W4), H2 * W2, scale, shift, nullptr, nullptr, nullptr, B, 128, st));
   DUCOSY_TRY(ducosy_in_apply_pad(P(w.y1), scale, shift, P(w.p1), B, H2, W2, 128, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   // ---- up 2: nearest x2 + 3x3 p1 128 -> 64, IN, ReLU
   DUCOSY_TRY(ducosy_upconv2x_nhwc(P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt, st));
-  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H2, W2), H * W, scale, shift, nullptr, nullptr, B, 64, st));
+  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H2, W2), H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
   DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p_out), B, H, W, 64, 3, DUCOSY_PAD_REFLECT, DUCOSY_ACT_RELU, dt, st));
   // ---- output: reflect-pad 3 + 7x7 conv 64 -> 1 + tanh   modules/model.py:112
   return ducosy_out_conv7x7_tanh(P(w.p_out), pk + L.outw, reinterpret_cast<const float*>(pk + L.outb), out, B, H, W, dt, st);
@@ -330,7 +332,7 @@ extern "C" size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg,
 }
 extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
-  return 17 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 2 : 0));
+  return 17 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 3 : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,

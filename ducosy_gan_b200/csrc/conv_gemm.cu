@@ -13,8 +13,8 @@
 //   A tile for (tap, 64-channel chunk) is ONE TMA box of the padded NHWC input, described by a 5-D
 //   tensor map (c, x-parity, x, y-parity, y*batch) so that stride-2 convs are plain boxes too.
 //
-// Warp roles (256 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> 16-bit NHWC store, plus the
+// Warp roles (384 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> 16-bit NHWC store, plus the
 // InstanceNorm / CBAM-pool statistics: per-tile per-channel sum, sum of squares and max).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include "common.cuh"
@@ -27,8 +27,8 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
-constexpr int kThreads = 256;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 384;                   // 4 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 
 template <int kN>
 struct Cfg {
@@ -193,6 +193,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may read
+    const int half = (warp - 4) >> 2;   // two warps share a quarter: each takes half of the kN columns
     const int m = q * 32 + lane;        // accumulator row = pixel inside the tile
     const int ry = m >> a.log2Wt, rx = m & (a.Wt - 1);
     const int et = threadIdx.x - (kThreads - kEpiThreads);
@@ -207,7 +208,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
 #pragma unroll 1
-      for (int ch = 0; ch < kN / 32; ++ch) {
+      for (int ch = half * (kN / 64); ch < (half + 1) * (kN / 64); ++ch) {
         uint32_t v[32];
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * kN + ch * 32), v);
         tmem_ld_wait();

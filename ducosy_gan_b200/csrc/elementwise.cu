@@ -123,23 +123,83 @@ __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int
   }
 }
 
+// Row-staged variant for small Cin: a CTA owns one image row, stages the 7 reflected input rows (already converted
+// to T) in shared memory, then every thread assembles whole 128-byte K-rows with compile-time (r, s) offsets.
+template <typename T, typename In, int CIN>
+__global__ void __launch_bounds__(256)
+stem_im2col_rows_kernel(In in, T* __restrict__ A, int H, int W) {
+  constexpr int KPAD = (49 * CIN + 63) / 64 * 64;
+  extern __shared__ __align__(16) uint8_t im2col_smem[];
+  T* tile = reinterpret_cast<T*>(im2col_smem);  // [CIN][7][W + 6]
+  const int y = blockIdx.x, b = blockIdx.y, Wp = W + 6;
+  for (int i = threadIdx.x; i < CIN * 7 * Wp; i += blockDim.x) {
+    const int xp = i % Wp, r = (i / Wp) % 7, c = i / (7 * Wp);
+    tile[i] = Cvt<T>::from_f(in.at(b, c, reflect_idx(y + r - 3, H), reflect_idx(xp - 3, W), CIN, H, W));
+  }
+  __syncthreads();
+  const unsigned short* t16 = reinterpret_cast<const unsigned short*>(tile);
+  for (int x = threadIdx.x; x < W; x += blockDim.x) {
+    uint4* dst = reinterpret_cast<uint4*>(A + (((long long)b * H + y) * W + x) * KPAD);
+#pragma unroll
+    for (int ck = 0; ck < KPAD / 8; ++ck) {
+      uint32_t w[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        uint32_t lo = 0, hi = 0;
+        const int k0 = ck * 8 + 2 * j, k1 = k0 + 1;
+        if (k0 < 49 * CIN) lo = t16[((k0 / 49) * 7 + (k0 % 49) / 7) * Wp + x + (k0 % 7)];
+        if (k1 < 49 * CIN) hi = t16[((k1 / 49) * 7 + (k1 % 49) / 7) * Wp + x + (k1 % 7)];
+        w[j] = lo | (hi << 16);
+      }
+      dst[ck] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+  }
+}
+
+template <typename T, typename In>
+int launch_im2col(In in, T* A, int B, int Cin, int H, int W, cudaStream_t st) {
+  const size_t smem = size_t(Cin) * 7 * (W + 6) * sizeof(T);
+  const dim3 grid(H, B);
+  if (Cin <= 3 && smem <= 48 * 1024) {
+    if (Cin == 1) stem_im2col_rows_kernel<T, In, 1><<<grid, 256, smem, st>>>(in, A, H, W);
+    else if (Cin == 2) stem_im2col_rows_kernel<T, In, 2><<<grid, 256, smem, st>>>(in, A, H, W);
+    else stem_im2col_rows_kernel<T, In, 3><<<grid, 256, smem, st>>>(in, A, H, W);
+  } else {
+    const int Kpad = (49 * Cin + 63) / 64 * 64;
+    const long long total = (long long)B * H * W * (Kpad / 8);
+    stem_im2col_kernel<T, In><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
+  }
+  return check_launch("stem_im2col_kernel");
+}
+
 // ------------------------------------------------------------------ InstanceNorm finalize (+ CBAM channel MLP)
-// One CTA per sample.  Tile partials are reduced in double; var is the biased variance, eps = 1e-5.
-__global__ void in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, float* __restrict__ scale,
-                                   float* __restrict__ shift, const float* __restrict__ fc0,
-                                   const float* __restrict__ fc2, int C) {
-  extern __shared__ float sm[];  // [C] normalised max, [C/16] hidden
-  float* smax = sm;
-  float* hidden = sm + C;
-  const int b = blockIdx.x;
-  const float* p = partials + (long long)b * tiles * 3 * C;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) {
-    double s1 = 0.0, s2 = 0.0;
-    float mx = -INFINITY;
-    for (int t = 0; t < tiles; ++t) {
-      s1 += double(p[(t * 3 + 0) * C + c]);
-      s2 += double(p[(t * 3 + 1) * C + c]);
-      mx = fmaxf(mx, p[(t * 3 + 2) * C + c]);
+// grid (C/32, B), 8 warps: warp w reduces tiles w, w+8, ... for 32 consecutive channels (coalesced 128-byte rows),
+// partial sums in double, combined through shared memory.  var is the biased variance, eps = 1e-5.
+__global__ void __launch_bounds__(256)
+in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, float* __restrict__ scale,
+                   float* __restrict__ shift, float* __restrict__ chmax, int C) {
+  __shared__ double s1s[8][32], s2s[8][32];
+  __shared__ float mxs[8][32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
+  const float* p = partials + (long long)b * tiles * 3 * C + c;
+  double s1 = 0.0, s2 = 0.0;
+  float mx = -INFINITY;
+  for (int t = warp; t < tiles; t += 8) {
+    s1 += double(p[(long long)(t * 3 + 0) * C]);
+    s2 += double(p[(long long)(t * 3 + 1) * C]);
+    mx = fmaxf(mx, p[(long long)(t * 3 + 2) * C]);
+  }
+  s1s[warp][lane] = s1;
+  s2s[warp][lane] = s2;
+  mxs[warp][lane] = mx;
+  __syncthreads();
+  if (warp == 0) {
+#pragma unroll
+    for (int w = 1; w < 8; ++w) {
+      s1 += s1s[w][lane];
+      s2 += s2s[w][lane];
+      mx = fmaxf(mx, mxs[w][lane]);
     }
     const double mean = s1 / npix;
     double var = s2 / npix - mean * mean;
@@ -148,12 +208,22 @@ __global__ void in_finalize_kernel(const float* __restrict__ partials, int tiles
     const float fmean = float(mean);
     scale[b * C + c] = rstd;
     shift[b * C + c] = -fmean * rstd;
-    smax[c] = (mx - fmean) * rstd;  // max over H*W of the normalised map (rstd > 0)
+    if (chmax != nullptr) chmax[b * C + c] = (mx - fmean) * rstd;  // max over H*W of the normalised map (rstd > 0)
   }
-  if (fc0 == nullptr) return;
+}
+
+// CBAM channel attention (modules/model.py:20-24), one CTA per sample: s = sigmoid(fc(avgpool) + fc(maxpool)) folded
+// into the InstanceNorm affine.  The avg-pool branch sees the mean of a non-affine InstanceNorm output, which is
+// exactly zero here (statistics are taken from the stored values), and fc has no bias: fc(0) = 0.
+__global__ void __launch_bounds__(256)
+cbam_channel_mlp_kernel(const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
+                        float* __restrict__ scale, float* __restrict__ shift, int C) {
+  extern __shared__ float sm[];  // [C] normalised max, [C/16] hidden
+  float* smax = sm;
+  float* hidden = sm + C;
+  const int b = blockIdx.x;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) smax[c] = chmax[b * C + c];
   __syncthreads();
-  // modules/model.py:20-24.  The avg-pool branch sees the mean of a non-affine InstanceNorm output, which is
-  // exactly zero here (statistics are taken from the stored values), and fc has no bias: fc(0) = 0.
   const int Hd = C / 16;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int j = warp; j < Hd; j += nwarps) {
@@ -226,43 +296,49 @@ __global__ void in_apply_pad_kernel(const T* __restrict__ y, const float* __rest
   }
 }
 
-// ------------------------------------------------------------------ CBAM spatial pooling: one warp per pixel, C = 256
+// ------------------------------------------------------------------ CBAM spatial pooling, C = 256
+// 8 lanes per pixel, each lane owns 4 x 8 channels (four independent 128-bit loads, every load instruction of a
+// pixel's 8 lanes covers one full 128-byte line), local reduction then 3 shuffle steps.  grid (x, B).
 template <typename T>
-__global__ void cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                                 const float* __restrict__ shift, float2* __restrict__ pooled, int B, int HW) {
+__global__ void __launch_bounds__(256)
+cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                 float2* __restrict__ pooled, int HW) {
   constexpr int C = 256;
-  const int lane = threadIdx.x & 31;
-  const int warps_per_block = blockDim.x >> 5;
-  const long long total = (long long)B * HW;
-  const long long wstride = (long long)gridDim.x * warps_per_block;
-  int cur_b = -1;
-  float sc[8], sh[8];
-  for (long long pix = (long long)blockIdx.x * warps_per_block + (threadIdx.x >> 5); pix < total; pix += wstride) {
-    const int b = int(pix / HW);
-    if (b != cur_b) {
-      cur_b = b;
+  const int lane = threadIdx.x & 31, seg = lane & 7, sub = lane >> 3;
+  const int b = blockIdx.y;
+  float sc[4][8], sh[4][8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        sc[j] = scale[b * C + lane * 8 + j];
-        sh[j] = shift[b * C + lane * 8 + j];
-      }
+  for (int j = 0; j < 4; ++j)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      sc[j][i] = scale[b * C + j * 64 + seg * 8 + i];
+      sh[j][i] = shift[b * C + j * 64 + seg * 8 + i];
     }
-    const uint4 raw = reinterpret_cast<const uint4*>(y)[pix * (C / 8) + lane];
-    const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+  const int warps = (blockDim.x >> 5) * gridDim.x;
+  const uint4* base = reinterpret_cast<const uint4*>(y) + (long long)b * HW * (C / 8);
+  for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g * 4 < HW; g += warps) {
+    const int pix = g * 4 + sub;
+    uint4 raw[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) raw[j] = base[(long long)pix * (C / 8) + j * 8 + seg];
     float s = 0.f, m = -INFINITY;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float2 f = Cvt<T>::unpack2(w[i]);
-      const float v0 = fmaf(f.x, sc[2 * i], sh[2 * i]), v1 = fmaf(f.y, sc[2 * i + 1], sh[2 * i + 1]);
-      s += v0 + v1;
-      m = fmaxf(m, fmaxf(v0, v1));
+    for (int j = 0; j < 4; ++j) {
+      const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const float2 f = Cvt<T>::unpack2(w[i]);
+        const float v0 = fmaf(f.x, sc[j][2 * i], sh[j][2 * i]), v1 = fmaf(f.y, sc[j][2 * i + 1], sh[j][2 * i + 1]);
+        s += v0 + v1;
+        m = fmaxf(m, fmaxf(v0, v1));
+      }
     }
 #pragma unroll
-    for (int o = 16; o; o >>= 1) {
+    for (int o = 4; o; o >>= 1) {
       s += __shfl_xor_sync(0xffffffffu, s, o);
       m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
     }
-    if (lane == 0) pooled[pix] = make_float2(s * (1.f / C), m);
+    if (seg == 0) pooled[(long long)b * HW + pix] = make_float2(s * (1.f / C), m);
   }
 }
 
@@ -383,37 +459,35 @@ extern "C" int ducosy_stem_im2col(const float* x, void* a_mat, int B, int Cin, i
                                   ducosy_stream_t stream) {
   DUCOSY_CHECK(x && a_mat && B > 0 && Cin > 0, DUCOSY_ERR_ARG, "stem_im2col: bad argument");
   DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col: reflect pad 3 needs H,W >= 4");
-  const int Kpad = (49 * Cin + 63) / 64 * 64;
-  const long long total = (long long)B * H * W * (Kpad / 8);
   InF32 in{x};
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (stem_im2col_kernel<T, InF32><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      in, static_cast<T*>(a_mat), B, Cin, H, W, Kpad)));
-  return check_launch("stem_im2col_kernel");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InF32>(in, static_cast<T*>(a_mat), B, Cin, H, W, (cudaStream_t)stream)));
 }
 
 extern "C" int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, float slope, float intercept,
                                      float lo, float hi, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(px && a_mat && B > 0, DUCOSY_ERR_ARG, "stem_im2col_hu: bad argument");
   DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col_hu: reflect pad 3 needs H,W >= 4");
-  const long long total = (long long)B * H * W * 8;
   InHU in{px, slope, intercept, lo, hi, float(double(hi) - double(lo))};
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (stem_im2col_kernel<T, InHU><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      in, static_cast<T*>(a_mat), B, 1, H, W, 64)));
-  return check_launch("stem_im2col_kernel(hu)");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InHU>(in, static_cast<T*>(a_mat), B, 1, H, W, (cudaStream_t)stream)));
 }
 
 extern "C" int ducosy_in_finalize(const float* partials, int tiles_per_sample, int npix_per_sample, float* scale,
-                                  float* shift, const float* fc0, const float* fc2, int B, int C,
+                                  float* shift, const float* fc0, const float* fc2, float* chmax, int B, int C,
                                   ducosy_stream_t stream) {
   DUCOSY_CHECK(partials && scale && shift && B > 0 && C > 0 && tiles_per_sample > 0 && npix_per_sample > 0,
                DUCOSY_ERR_ARG, "in_finalize: bad argument");
   DUCOSY_CHECK((fc0 == nullptr) == (fc2 == nullptr), DUCOSY_ERR_ARG, "in_finalize: fc0 and fc2 go together");
-  DUCOSY_CHECK(fc0 == nullptr || C % 16 == 0, DUCOSY_ERR_SHAPE, "in_finalize: CBAM needs C %% 16 == 0");
-  const int threads = C >= 256 ? 256 : 128;
-  const size_t smem = sizeof(float) * (C + C / 16 + 1);
-  in_finalize_kernel<<<B, threads, smem, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample, scale,
-                                                                 shift, fc0, fc2, C);
-  return check_launch("in_finalize_kernel");
+  DUCOSY_CHECK(fc0 == nullptr || chmax != nullptr, DUCOSY_ERR_ARG, "in_finalize: CBAM needs the chmax scratch [B][C]");
+  DUCOSY_CHECK(C % 32 == 0, DUCOSY_ERR_SHAPE, "in_finalize: C %% 32 != 0");
+  in_finalize_kernel<<<dim3(C / 32, B), 256, 0, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample,
+                                                                        scale, shift, chmax, C);
+  DUCOSY_TRY(check_launch("in_finalize_kernel"));
+  if (fc0 != nullptr) {
+    const size_t smem = sizeof(float) * (C + C / 16 + 1);
+    cbam_channel_mlp_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(chmax, fc0, fc2, scale, shift, C);
+    return check_launch("cbam_channel_mlp_kernel");
+  }
+  return 0;
 }
 
 extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const float* shift, void* out_pad, int B, int H,
@@ -432,9 +506,13 @@ extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* 
                                 int C, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(y && scale && shift && pooled && B > 0, DUCOSY_ERR_ARG, "cbam_pool: bad argument");
   DUCOSY_CHECK(C == 256, DUCOSY_ERR_SHAPE, "cbam_pool: C must be 256 (got %d)", C);
-  const long long pixels = (long long)B * H * W;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T><<<ew_grid(pixels * 32 / 4, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), B, H * W)));
+  DUCOSY_CHECK((H * W) % 4 == 0, DUCOSY_ERR_SHAPE, "cbam_pool: H*W must be a multiple of 4");
+  const int groups = H * W / 4;
+  int gx = (groups + 7) / 8;                     // 8 warps per CTA
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 8 / (B > 0 ? B : 1) + 1;
+  if (gx > cap) gx = cap;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), H * W)));
   return check_launch("cbam_pool_kernel");
 }
 

@@ -149,8 +149,9 @@ def in_finalize(partials: torch.Tensor, npix: int, fc0=None, fc2=None):
     with _dev(partials):
         scale = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
         shift = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
-        call("ducosy_in_finalize", ptr(partials), tiles, int(npix), ptr(scale), ptr(shift), ptr(fc0), ptr(fc2), B, Cn,
-             stream_ptr())
+        chmax = torch.empty((B, Cn), dtype=torch.float32, device=partials.device) if fc0 is not None else None
+        call("ducosy_in_finalize", ptr(partials), tiles, int(npix), ptr(scale), ptr(shift), ptr(fc0), ptr(fc2), ptr(chmax),
+             B, Cn, stream_ptr())
     return scale, shift
 
 

@@ -104,9 +104,10 @@ int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, f
 /* InstanceNorm statistics (modules/model.py InstanceNorm2d: biased var, eps 1e-5) from the conv partials:
  * scale[b][c] = rstd, shift[b][c] = -mean*rstd.  When fc0/fc2 are given (CBAM channel attention,
  * modules/model.py:13-24: fc0 [C/16][C], fc2 [C][C/16], fp32) the channel attention
- * s = sigmoid(fc(avgpool) + fc(maxpool)) of the NORMALISED map is folded in: scale *= s, shift *= s. */
+ * s = sigmoid(fc(avgpool) + fc(maxpool)) of the NORMALISED map is folded in: scale *= s, shift *= s;
+ * chmax_scratch [B][C] fp32 then receives the per-channel max of the normalised map (required with fc0/fc2). */
 int ducosy_in_finalize(const float* partials, int tiles_per_sample, int npix_per_sample, float* scale, float* shift,
-                       const float* fc0, const float* fc2, int B, int C, ducosy_stream_t stream);
+                       const float* fc0, const float* fc2, float* chmax_scratch, int B, int C, ducosy_stream_t stream);
 
 /* out_pad[b][y+p][x+p][c] = act(y*scale + shift), borders filled by reflection or zeros. */
 int ducosy_in_apply_pad(const void* y, const float* scale, const float* shift, void* out_pad, int B, int H, int W, int C,
