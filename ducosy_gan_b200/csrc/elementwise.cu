@@ -173,22 +173,36 @@ int launch_im2col(In in, T* A, int B, int Cin, int H, int W, cudaStream_t st) {
 }
 
 // ------------------------------------------------------------------ InstanceNorm finalize (+ CBAM channel MLP)
-// grid (C/32, B), 8 warps: warp w reduces tiles w, w+8, ... for 32 consecutive channels (coalesced 128-byte rows),
-// partial sums in double, combined through shared memory.  var is the biased variance, eps = 1e-5.
-__global__ void __launch_bounds__(256)
+// grid (C/32, B), 32 warps: warp w reduces tiles w, w+32, ... for 32 consecutive channels (coalesced 128-byte rows,
+// 4 tiles = 12 loads in flight), partial sums in double, combined through shared memory in a fixed order
+// (deterministic).  var is the biased variance, eps = 1e-5.
+constexpr int kFinWarps = 32;
+__global__ void __launch_bounds__(kFinWarps * 32)
 in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, float* __restrict__ scale,
                    float* __restrict__ shift, float* __restrict__ chmax, int C) {
-  __shared__ double s1s[8][32], s2s[8][32];
-  __shared__ float mxs[8][32];
+  __shared__ double s1s[kFinWarps][32], s2s[kFinWarps][32];
+  __shared__ float mxs[kFinWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + lane, b = blockIdx.y;
   const float* p = partials + (long long)b * tiles * 3 * C + c;
   double s1 = 0.0, s2 = 0.0;
   float mx = -INFINITY;
-  for (int t = warp; t < tiles; t += 8) {
-    s1 += double(p[(long long)(t * 3 + 0) * C]);
-    s2 += double(p[(long long)(t * 3 + 1) * C]);
-    mx = fmaxf(mx, p[(long long)(t * 3 + 2) * C]);
+  for (int t0 = warp; t0 < tiles; t0 += kFinWarps * 4) {
+    float a[4], q[4], m[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int t = t0 + u * kFinWarps;
+      const bool ok = t < tiles;
+      a[u] = ok ? p[(long long)(t * 3 + 0) * C] : 0.f;
+      q[u] = ok ? p[(long long)(t * 3 + 1) * C] : 0.f;
+      m[u] = ok ? p[(long long)(t * 3 + 2) * C] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s1 += double(a[u]);
+      s2 += double(q[u]);
+      mx = fmaxf(mx, m[u]);
+    }
   }
   s1s[warp][lane] = s1;
   s2s[warp][lane] = s2;
@@ -196,7 +210,7 @@ in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, floa
   __syncthreads();
   if (warp == 0) {
 #pragma unroll
-    for (int w = 1; w < 8; ++w) {
+    for (int w = 1; w < kFinWarps; ++w) {
       s1 += s1s[w][lane];
       s2 += s2s[w][lane];
       mx = fmaxf(mx, mxs[w][lane]);
@@ -264,35 +278,54 @@ __device__ __forceinline__ uint4 affine8(uint4 raw, const float* sc, const float
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+// Row-persistent layout shared by the two padding writers below: a CTA walks padded output rows (b, py); inside a
+// row thread t handles 16-byte chunks t, t+256, ...  Because 256 is a multiple of C/8, a thread always sees the same
+// 8 channels, so its scale/shift live in registers; four chunks are in flight per thread (ILP) and the grid is
+// 4 CTAs per SM so that a tensor-core conv CTA of the other generator's stream can share the SM.
+constexpr int kRowILP = 4;
+
 template <typename T>
-__global__ void in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                                    const float* __restrict__ shift, T* __restrict__ out, int B, int H, int W, int C,
-                                    int pad, int pad_mode, int act) {
+__global__ void __launch_bounds__(256)
+in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                    T* __restrict__ out, int B, int H, int W, int C, int pad, int pad_mode, int act) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
-  const long long total = (long long)B * Hp * Wp * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = int(i % cv);
-    long long r = i / cv;
-    const int px = int(r % Wp);
-    r /= Wp;
-    const int py = int(r % Hp);
-    const int b = int(r / Hp);
-    int sy = py - pad, sx = px - pad;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
-    if (inside || pad_mode == DUCOSY_PAD_REFLECT) {
-      sy = reflect_idx(sy, H);
-      sx = reflect_idx(sx, W);
-      const uint4 raw = reinterpret_cast<const uint4*>(y)[(((long long)b * H + sy) * W + sx) * cv + c8];
+  const int c8 = threadIdx.x % cv, row_chunks = Wp * cv;
+  const int px0 = threadIdx.x / cv, px_step = 256 / cv;
+  int cur_b = -1;
+  float s8[8], h8[8];
+  for (int row = blockIdx.x; row < B * Hp; row += gridDim.x) {
+    const int b = row / Hp, py = row - b * Hp;
+    if (b != cur_b) {
+      cur_b = b;
       const float4* sc = reinterpret_cast<const float4*>(scale + b * C + c8 * 8);
       const float4* sh = reinterpret_cast<const float4*>(shift + b * C + c8 * 8);
       const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
-      const float s8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float h8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      o = affine8<T>(raw, s8, h8, act);
+      s8[0] = a0.x; s8[1] = a0.y; s8[2] = a0.z; s8[3] = a0.w; s8[4] = a1.x; s8[5] = a1.y; s8[6] = a1.z; s8[7] = a1.w;
+      h8[0] = b0.x; h8[1] = b0.y; h8[2] = b0.z; h8[3] = b0.w; h8[4] = b1.x; h8[5] = b1.y; h8[6] = b1.z; h8[7] = b1.w;
     }
-    reinterpret_cast<uint4*>(out)[i] = o;
+    int sy = py - pad;
+    const bool row_inside = sy >= 0 && sy < H;
+    sy = reflect_idx(sy, H);
+    const uint4* src_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cv + c8;
+    uint4* dst_row = reinterpret_cast<uint4*>(out) + (long long)row * row_chunks + c8;
+    for (int px = px0; px < Wp; px += px_step * kRowILP) {
+      uint4 raw[kRowILP];
+      bool live[kRowILP];
+#pragma unroll
+      for (int u = 0; u < kRowILP; ++u) {
+        const int p = px + u * px_step;
+        int sx = p - pad;
+        const bool inside = row_inside && sx >= 0 && sx < W;
+        live[u] = p < Wp && (inside || pad_mode == DUCOSY_PAD_REFLECT);
+        sx = reflect_idx(sx, W);
+        if (live[u]) raw[u] = src_row[(long long)sx * cv];
+      }
+#pragma unroll
+      for (int u = 0; u < kRowILP; ++u) {
+        const int p = px + u * px_step;
+        if (p < Wp) dst_row[(long long)p * cv] = live[u] ? affine8<T>(raw[u], s8, h8, act) : make_uint4(0, 0, 0, 0);
+      }
+    }
   }
 }
 
@@ -375,51 +408,77 @@ __global__ void cbam_spatial_conv_kernel(const float2* __restrict__ pooled, cons
 
 // out_pad = residual + (y*scale+shift) * sa ; borders by reflection / zero.  res_pad has padding res_pw.
 template <typename T>
-__global__ void residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale,
-                                          const float* __restrict__ shift, const float* __restrict__ sa,
-                                          const T* __restrict__ res_pad, int res_pw, T* __restrict__ out, int B, int H,
-                                          int W, int C, int pad, int pad_mode) {
+__global__ void __launch_bounds__(256)
+residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
+                          const float* __restrict__ sa, const T* __restrict__ res_pad, int res_pw, T* __restrict__ out,
+                          int B, int H, int W, int C, int pad, int pad_mode) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
   const int Wr = W + 2 * res_pw, Hr = H + 2 * res_pw;
-  const long long total = (long long)B * Hp * Wp * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = int(i % cv);
-    long long r = i / cv;
-    const int px = int(r % Wp);
-    r /= Wp;
-    const int py = int(r % Hp);
-    const int b = int(r / Hp);
-    int sy = py - pad, sx = px - pad;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    const bool inside = sy >= 0 && sy < H && sx >= 0 && sx < W;
-    if (inside || pad_mode == DUCOSY_PAD_REFLECT) {
-      sy = reflect_idx(sy, H);
-      sx = reflect_idx(sx, W);
-      const long long spix = ((long long)b * H + sy) * W + sx;
-      const uint4 raw = reinterpret_cast<const uint4*>(y)[spix * cv + c8];
-      const uint4 res =
-          reinterpret_cast<const uint4*>(res_pad)[(((long long)b * Hr + sy + res_pw) * Wr + sx + res_pw) * cv + c8];
-      const float att = sa != nullptr ? __ldg(sa + spix) : 1.f;
+  const int c8 = threadIdx.x % cv, row_chunks = Wp * cv;
+  const int px0 = threadIdx.x / cv, px_step = 256 / cv;
+  int cur_b = -1;
+  float s8[8], h8[8];
+  for (int row = blockIdx.x; row < B * Hp; row += gridDim.x) {
+    const int b = row / Hp, py = row - b * Hp;
+    if (b != cur_b) {
+      cur_b = b;
       const float4* sc = reinterpret_cast<const float4*>(scale + b * C + c8 * 8);
       const float4* sh = reinterpret_cast<const float4*>(shift + b * C + c8 * 8);
       const float4 a0 = __ldg(sc), a1 = __ldg(sc + 1), b0 = __ldg(sh), b1 = __ldg(sh + 1);
-      const float s8[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-      const float h8[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-      const uint32_t yw[4] = {raw.x, raw.y, raw.z, raw.w};
-      const uint32_t rw[4] = {res.x, res.y, res.z, res.w};
-      uint32_t ow[4];
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 f = Cvt<T>::unpack2(yw[k]);
-        const float2 g = Cvt<T>::unpack2(rw[k]);
-        const float v0 = fmaf(f.x, s8[2 * k], h8[2 * k]), v1 = fmaf(f.y, s8[2 * k + 1], h8[2 * k + 1]);
-        ow[k] = Cvt<T>::pack2(fmaf(v0, att, g.x), fmaf(v1, att, g.y));
-      }
-      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+      s8[0] = a0.x; s8[1] = a0.y; s8[2] = a0.z; s8[3] = a0.w; s8[4] = a1.x; s8[5] = a1.y; s8[6] = a1.z; s8[7] = a1.w;
+      h8[0] = b0.x; h8[1] = b0.y; h8[2] = b0.z; h8[3] = b0.w; h8[4] = b1.x; h8[5] = b1.y; h8[6] = b1.z; h8[7] = b1.w;
     }
-    reinterpret_cast<uint4*>(out)[i] = o;
+    int sy = py - pad;
+    const bool row_inside = sy >= 0 && sy < H;
+    sy = reflect_idx(sy, H);
+    const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cv + c8;
+    const uint4* r_row = reinterpret_cast<const uint4*>(res_pad) + (((long long)b * Hr + sy + res_pw) * Wr + res_pw) * cv + c8;
+    const float* sa_row = sa != nullptr ? sa + ((long long)b * H + sy) * W : nullptr;
+    uint4* dst_row = reinterpret_cast<uint4*>(out) + (long long)row * row_chunks + c8;
+    for (int px = px0; px < Wp; px += px_step * kRowILP) {
+      uint4 raw[kRowILP], res[kRowILP];
+      float att[kRowILP];
+      bool live[kRowILP];
+#pragma unroll
+      for (int u = 0; u < kRowILP; ++u) {
+        const int p = px + u * px_step;
+        int sx = p - pad;
+        const bool inside = row_inside && sx >= 0 && sx < W;
+        live[u] = p < Wp && (inside || pad_mode == DUCOSY_PAD_REFLECT);
+        sx = reflect_idx(sx, W);
+        if (live[u]) {
+          raw[u] = y_row[(long long)sx * cv];
+          res[u] = r_row[(long long)sx * cv];
+          att[u] = sa_row != nullptr ? __ldg(sa_row + sx) : 1.f;
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < kRowILP; ++u) {
+        const int p = px + u * px_step;
+        if (p >= Wp) continue;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (live[u]) {
+          const uint32_t yw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
+          const uint32_t rw[4] = {res[u].x, res[u].y, res[u].z, res[u].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 f = Cvt<T>::unpack2(yw[k]);
+            const float2 g = Cvt<T>::unpack2(rw[k]);
+            const float v0 = fmaf(f.x, s8[2 * k], h8[2 * k]), v1 = fmaf(f.y, s8[2 * k + 1], h8[2 * k + 1]);
+            ow[k] = Cvt<T>::pack2(fmaf(v0, att[u], g.x), fmaf(v1, att[u], g.y));
+          }
+          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        dst_row[(long long)p * cv] = o;
+      }
+    }
   }
+}
+
+int row_grid(int rows) {
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 4;
+  return rows < cap ? (rows > 0 ? rows : 1) : cap;
 }
 
 bool al16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -479,7 +538,7 @@ extern "C" int ducosy_in_finalize(const float* partials, int tiles_per_sample, i
   DUCOSY_CHECK((fc0 == nullptr) == (fc2 == nullptr), DUCOSY_ERR_ARG, "in_finalize: fc0 and fc2 go together");
   DUCOSY_CHECK(fc0 == nullptr || chmax != nullptr, DUCOSY_ERR_ARG, "in_finalize: CBAM needs the chmax scratch [B][C]");
   DUCOSY_CHECK(C % 32 == 0, DUCOSY_ERR_SHAPE, "in_finalize: C %% 32 != 0");
-  in_finalize_kernel<<<dim3(C / 32, B), 256, 0, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample,
+  in_finalize_kernel<<<dim3(C / 32, B), kFinWarps * 32, 0, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample,
                                                                         scale, shift, chmax, C);
   DUCOSY_TRY(check_launch("in_finalize_kernel"));
   if (fc0 != nullptr) {
@@ -495,8 +554,8 @@ extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const floa
   DUCOSY_CHECK(y && scale && shift && out_pad && B > 0, DUCOSY_ERR_ARG, "in_apply_pad: bad argument");
   DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_SHAPE, "in_apply_pad: C %% 8 != 0 or pad too large");
   DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
-  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "in_apply_pad: C must be one of 8..2048 with C/8 dividing 256");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
                                       pad_mode, act)));
   return check_launch("in_apply_pad_kernel");
@@ -531,8 +590,8 @@ extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, cons
   DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W && res_pad_width >= 0, DUCOSY_ERR_SHAPE,
                "residual_apply_pad: bad shape");
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
-  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_apply_pad: C/8 must divide 256");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(y), scale, shift, sa, static_cast<const T*>(res_pad),
                                       res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");

@@ -12,6 +12,8 @@ Slices are independent, so a volume shards across ranks by contiguous slice rang
 """
 from __future__ import annotations
 
+import os
+
 import numpy as np
 import torch
 
@@ -78,10 +80,11 @@ class DualHUSynthesizer:
             out = torch.empty_like(raw_px)
         es, el = self._engines()
         with torch.cuda.device(self.device):
-            if self._streams is None:
-                self._streams = (torch.cuda.Stream(), torch.cuda.Stream())
-            s_soft, s_lung = self._streams
             cur = torch.cuda.current_stream()
+            if self._streams is None:
+                one = os.environ.get("DUCOSY_SINGLE_STREAM", "0") == "1"   # experiment switch: serialise the two generators
+                self._streams = (cur, cur) if one else (torch.cuda.Stream(), torch.cuda.Stream())
+            s_soft, s_lung = self._streams
             B = min(self.batch_slices, S)
             ys, yl = self._buffers(B, H, W)
             # make sure both engine workspaces exist before the side streams use them
