@@ -17,6 +17,9 @@
 // warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> 16-bit NHWC store, plus the
 // InstanceNorm / CBAM-pool statistics: per-tile per-channel sum, sum of squares and max).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
+#include <cstdlib>
+#include <type_traits>
+
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -30,11 +33,16 @@ constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
 constexpr int kThreads = 384;                   // 4 control warps + 8 epilogue warps
 constexpr int kEpiThreads = 256;
 
-template <int kN>
+// kCG = 1: one CTA per 128 x kN tile.  kCG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x kN
+// tile; each CTA stages its own 128 A rows and HALF of the B rows, so L2->SMEM traffic per FLOP drops by a third
+// and the same shared memory holds 6 instead of 4 pipeline stages.
+template <int kN, int kCG>
 struct Cfg {
-  static constexpr int kBBytes = kN * kBlockK * 2;
+  static constexpr int kBRows = kN / kCG;
+  static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = kN == 256 ? 4 : (kN == 128 ? 6 : 8);
+  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * kN;        // two accumulator stages (power of two >= 32)
   static constexpr int kStatFloats = 4 * 3 * kN;  // per epilogue warp: sum / sumsq / max
   static constexpr size_t kSmemBytes = 1024 + size_t(kStages) * kStageBytes + kStatFloats * 4 + 256;
@@ -84,11 +92,11 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmArgs& a
   return t;
 }
 
-template <int kN, typename T>
+template <int kN, typename T, int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const ConvGemmArgs a) {
-  using C = Cfg<kN>;
+  using C = Cfg<kN, kCG>;
   constexpr int kStages = C::kStages;
   constexpr int kFmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 
@@ -106,7 +114,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int kiters = a.num_taps * a.kc_per_tap;
   const int tiles_m_per_sample = a.num_phases * a.TY * a.TX;
-  const int total_tiles = a.B * tiles_m_per_sample * a.n_blocks;
+  // work unit = (group of kCG consecutive m-tiles) x (n-block); this CTA owns m-tile  unit_m * kCG + rank
+  const int total_units = (a.B * tiles_m_per_sample / kCG) * a.n_blocks;
+  const uint32_t rank = kCG == 2 ? cluster_ctarank() : 0u;
+  const int unit0 = blockIdx.x / kCG, unit_step = gridDim.x / kCG;
+  auto unit_tile = [&](int unit) { return ((unit / a.n_blocks) * kCG + int(rank)) * a.n_blocks + unit % a.n_blocks; };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -119,16 +131,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], kEpiThreads);
+      mbar_init(&tempty[i], kEpiThreads * kCG);  // in a pair both CTAs' epilogues release the leader's MMA warp
     }
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, C::kTmemCols);
-    tmem_relinquish();
+    if (kCG == 2) {
+      tmem_alloc_cg2(tmem_slot, C::kTmemCols);
+      tmem_relinquish_cg2();
+    } else {
+      tmem_alloc(tmem_slot, C::kTmemCols);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -137,20 +154,27 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (lane == 0) {
       int s = 0;
       uint32_t ph = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const TileCoord tc = decode_tile(tile, a);
+      for (int unit = unit0; unit < total_units; unit += unit_step) {
+        const TileCoord tc = decode_tile(unit_tile(unit), a);
         const int x0 = tc.tx * a.Wt;
         const int row0 = tc.b * a.rows_per_sample + tc.ty * a.R;
-        const int n0 = tc.phase * a.Cout + tc.nb * kN;
+        const int n0 = tc.phase * a.Cout + tc.nb * kN + int(rank) * C::kBRows;
         for (int t = 0; t < a.num_taps; ++t) {
           const int xp = a.tap_xp[tc.phase][t], dx = a.tap_dx[tc.phase][t];
           const int yp = a.tap_yp[tc.phase][t], dy = a.tap_dy[tc.phase][t];
           for (int kc = 0; kc < a.kc_per_tap; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa = smem + size_t(s) * C::kStageBytes;
-            mbar_arrive_expect_tx(&full[s], C::kStageBytes);
-            tma_load_5d(sa, &tmA, &full[s], kc * kBlockK, xp, x0 + dx, yp, row0 + dy);
-            tma_load_2d(sa + kABytes, &tmB, &full[s], (t * a.kc_per_tap + kc) * kBlockK, n0);
+            if (kCG == 2) {
+              // both CTAs' loads complete on the leader's barrier, which expects the bytes of the whole pair
+              if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::kStageBytes);
+              tma_load_5d_cg2(sa, &tmA, &full[s], kc * kBlockK, xp, x0 + dx, yp, row0 + dy);
+              tma_load_2d_cg2(sa + kABytes, &tmB, &full[s], (t * a.kc_per_tap + kc) * kBlockK, n0);
+            } else {
+              mbar_arrive_expect_tx(&full[s], C::kStageBytes);
+              tma_load_5d(sa, &tmA, &full[s], kc * kBlockK, xp, x0 + dx, yp, row0 + dy);
+              tma_load_2d(sa + kABytes, &tmB, &full[s], (t * a.kc_per_tap + kc) * kBlockK, n0);
+            }
             if (++s == kStages) {
               s = 0;
               ph ^= 1;
@@ -159,12 +183,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    constexpr uint32_t idesc = umma_idesc_f16(kFmt, kTileM, kN);
+  } else if (warp == 1 && rank == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only in a pair)
+    constexpr uint32_t idesc = umma_idesc_f16(kFmt, kTileM * kCG, kN);
     int s = 0, as = 0;
     uint32_t ph = 0, aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
       mbar_wait(&tempty[as], aph ^ 1);  // epilogue has drained this accumulator stage
       tc_fence_after();
       const uint32_t d_tmem = tmem_base + uint32_t(as * kN);
@@ -176,10 +200,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint64_t da = umma_desc_k_sw128(sa);
           const uint64_t db = umma_desc_k_sw128(sa + kABytes);
 #pragma unroll
-          for (int j = 0; j < kBlockK / 16; ++j)  // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
-            umma_f16(d_tmem, da + uint64_t(j * 2), db + uint64_t(j * 2), idesc, (k | j) != 0 ? 1u : 0u);
-          umma_commit(&empty[s]);                 // frees the smem stage once these MMAs retire
-          if (k == kiters - 1) umma_commit(&tfull[as]);
+          for (int j = 0; j < kBlockK / 16; ++j) {  // +32 bytes (2 x 16 B) per K=16 step inside the swizzle row
+            if (kCG == 2) umma_f16_cg2(d_tmem, da + uint64_t(j * 2), db + uint64_t(j * 2), idesc, (k | j) != 0 ? 1u : 0u);
+            else umma_f16(d_tmem, da + uint64_t(j * 2), db + uint64_t(j * 2), idesc, (k | j) != 0 ? 1u : 0u);
+          }
+          if (kCG == 2) {
+            umma_commit_mc(&empty[s], 3);           // frees the stage in BOTH CTAs once these MMAs retire
+            if (k == kiters - 1) umma_commit_mc(&tfull[as], 3);
+          } else {
+            umma_commit(&empty[s]);                 // frees the smem stage once these MMAs retire
+            if (k == kiters - 1) umma_commit(&tfull[as]);
+          }
         }
         __syncwarp();
         if (++s == kStages) {
@@ -199,8 +230,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - (kThreads - kEpiThreads);
     int as = 0;
     uint32_t aph = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-      const TileCoord tc = decode_tile(tile, a);
+    for (int unit = unit0; unit < total_units; unit += unit_step) {
+      const TileCoord tc = decode_tile(unit_tile(unit), a);
       const int gy = tc.ty * a.R + ry, gx = tc.tx * a.Wt + rx;
       T* orow = reinterpret_cast<T*>(a.out) + size_t(tc.b) * a.out_bs +
                 size_t(gy * a.oy_mul + a.oy_off[tc.phase]) * a.out_rs +
@@ -251,7 +282,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
       tc_fence_before();
-      mbar_arrive(&tempty[as]);  // accumulator stage may be overwritten by the next-but-one tile
+      if (kCG == 2 && rank != 0) mbar_arrive_remote(&tempty[as], 0);  // the leader's MMA warp owns the TMEM pipeline
+      else mbar_arrive(&tempty[as]);  // accumulator stage may be overwritten by the next-but-one tile
       if (a.partials != nullptr) {
         named_bar_sync(1, kEpiThreads);
         float* pdst = a.partials + (size_t(tc.b) * tiles_m_per_sample + tc.tile_m) * 3 * a.Cout + tc.nb * kN;
@@ -269,10 +301,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (kCG == 2) cluster_sync_all(); else __syncthreads();  // pair: the peer may still signal barriers in this CTA
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::kTmemCols);
+    if (kCG == 2) tmem_dealloc_cg2(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
 }
 
@@ -293,18 +325,35 @@ EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
-template <int kN, typename T>
+template <int kN, typename T, int kCG>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& args, int grid,
                 cudaStream_t stream) {
-  using C = Cfg<kN>;
+  using C = Cfg<kN, kCG>;
   static bool configured = false;
-  auto kern = conv_gemm_kernel<kN, T>;
+  auto kern = conv_gemm_kernel<kN, T, kCG>;
   if (!configured) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes));
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
     configured = true;
   }
-  kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+  if (kCG == 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args);
+    if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaLaunchKernelEx(conv_gemm pair): %s", cudaGetErrorString(e));
+  } else {
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+  }
   return check_launch("conv_gemm_kernel");
 }
 
@@ -369,6 +418,10 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.bias = p.bias;
   a.epi_mode = p.epi_mode;
 
+  // CTA pairs whenever the m-tiles of one (sample, phase) pair up; DUCOSY_CONV_CTA_GROUP=1 forces single CTAs.
+  static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();
+  const int cg = (cg_env == 2 && (a.TY * a.TX) % 2 == 0) ? 2 : 1;
+
   EncodeTiledFn encode = get_encode_fn();
   DUCOSY_CHECK(encode != nullptr, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   const CUtensorMapDataType dt = p.dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
@@ -394,7 +447,7 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
     const cuuint64_t Ktot = cuuint64_t(p.num_taps) * p.Cin;
     const cuuint64_t gdim[2] = {Ktot, cuuint64_t(p.num_phases) * p.Cout};
     const cuuint64_t gstr[1] = {Ktot * 2};
-    const cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(kN)};
+    const cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(kN / cg)};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = encode(&tmB, dt, 2, const_cast<void*>(p.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
                         CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -405,12 +458,18 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   const int total_tiles = a.B * a.num_phases * a.TY * a.TX * a.n_blocks;
   const int sms = num_sms();
   DUCOSY_CHECK(sms > 0, DUCOSY_ERR_CUDA, "conv_gemm: no CUDA device");
-  const int grid = total_tiles < sms ? total_tiles : sms;
+  int grid = total_tiles < sms ? total_tiles : sms;
   if (grid == 0) return 0;
+  if (cg == 2) grid &= ~1;  // whole pairs (total_tiles is even here)
 
-#define DUCOSY_LAUNCH_N(N)                                                            \
-  if (p.dtype == DUCOSY_F16) return launch_impl<N, __half>(tmA, tmB, a, grid, stream); \
-  else return launch_impl<N, __nv_bfloat16>(tmA, tmB, a, grid, stream);
+#define DUCOSY_LAUNCH_N(N)                                                                             \
+  if (cg == 2) {                                                                                       \
+    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 2>(tmA, tmB, a, grid, stream);             \
+    else return launch_impl<N, __nv_bfloat16, 2>(tmA, tmB, a, grid, stream);                            \
+  } else {                                                                                             \
+    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 1>(tmA, tmB, a, grid, stream);             \
+    else return launch_impl<N, __nv_bfloat16, 1>(tmA, tmB, a, grid, stream);                            \
+  }
   if (kN == 256) { DUCOSY_LAUNCH_N(256) }
   if (kN == 128) { DUCOSY_LAUNCH_N(128) }
   DUCOSY_LAUNCH_N(64)
