@@ -13,9 +13,12 @@
 //   A tile for (tap, 64-channel chunk) is ONE TMA box of the padded NHWC input, described by a 5-D
 //   tensor map (c, x-parity, x, y-parity, y*batch) so that stride-2 convs are plain boxes too.
 //
-// Warp roles (384 threads, 1 CTA/SM): warp 0 = TMA producer, warp 1 = MMA issuer (one lane),
-// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> 16-bit NHWC store, plus the
-// InstanceNorm / CBAM-pool statistics: per-tile per-channel sum, sum of squares and max).
+// Warp roles (384 threads, 1 CTA/SM): warps 0-7 = epilogue, warp 8 = TMA producer, warp 9 = MMA issuer (one lane),
+// warp 10 = TMEM allocator.  Epilogue: TMEM -> registers -> 16-bit tile staged in shared memory (TMA swizzle) ->
+// one TMA store per 64-channel slab, and the InstanceNorm / CBAM-pool statistics (per-tile per-channel sum, sum of
+// squares, max) as a conflict-free column pass over the staged tile.  The first version stored straight from
+// registers and reduced with warp shuffles: 4096 uncoalesced store wavefronts + ~3000 shuffles per tile on the
+// LSU / shared-memory crossbar cost the UMMA operand fetch 17-22 % (measured, tools/conv_bench.py).
 // Two TMEM accumulator stages let the epilogue of tile i overlap the MMAs of tile i+1.
 #include <cstdlib>
 #include <type_traits>
@@ -30,7 +33,8 @@ namespace {
 constexpr int kTileM = 128;
 constexpr int kBlockK = 64;                       // 64 x 16-bit = one 128-byte swizzle row
 constexpr int kABytes = kTileM * kBlockK * 2;     // 16 KiB
-constexpr int kThreads = 384;                   // 4 control warps + 8 epilogue warps
+constexpr int kThreads = 384;                   // 8 epilogue warps + 4 control warps
+constexpr int kWarpTma = 8, kWarpMma = 9, kWarpAlloc = 10;
 constexpr int kEpiThreads = 256;
 
 // kCG = 1: one CTA per 128 x kN tile.  kCG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x kN
@@ -41,38 +45,21 @@ struct Cfg {
   static constexpr int kBRows = kN / kCG;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStagesRaw = (200 * 1024) / kStageBytes;
-  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
   static constexpr int kTmemCols = 2 * kN;        // two accumulator stages (power of two >= 32)
-  static constexpr int kStatFloats = 4 * 3 * kN;  // per epilogue warp: sum / sumsq / max
-  static constexpr size_t kSmemBytes = 1024 + size_t(kStages) * kStageBytes + kStatFloats * 4 + 256;
+  // epilogue staging: the 16-bit output tile as kSlabs x [128 rows][64 channels] in the TMA 128-byte-swizzle layout
+  static constexpr int kSlabs = kN / 64;
+  static constexpr int kSlabBytes = kTileM * 128;
+  static constexpr int kOutBytes = kSlabs * kSlabBytes;
+  static constexpr int kParts = 8 / kSlabs;       // row parts per slab in the column pass (8 epilogue warps)
+  static constexpr int kStatFloats = kParts * 3 * kN;
+  static constexpr int kFixedBytes = 1024 + kOutBytes + kStatFloats * 4 + 256;
+  static constexpr int kStagesRaw = (227 * 1024 - kFixedBytes) / kStageBytes;
+  static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+  static constexpr size_t kSmemBytes = size_t(kFixedBytes) + size_t(kStages) * kStageBytes;
 };
 
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
-}
-
-// Transposing butterfly: on entry lane L holds x[0..31] (32 columns of its row); on exit x[0] of
-// lane L is the reduction of column L over the 32 lanes.  31 shuffles instead of 160.
-template <bool kMax, int H>
-__device__ __forceinline__ void butterfly_step(float (&x)[32], int lane) {
-  const bool up = (lane & H) != 0;
-#pragma unroll
-  for (int i = 0; i < H; ++i) {
-    const float send = up ? x[i] : x[i + H];
-    const float keep = up ? x[i + H] : x[i];
-    const float recv = __shfl_xor_sync(0xffffffffu, send, H);
-    x[i] = kMax ? fmaxf(keep, recv) : keep + recv;
-  }
-}
-template <bool kMax>
-__device__ __forceinline__ float butterfly_reduce(float (&x)[32], int lane) {
-  butterfly_step<kMax, 16>(x, lane);
-  butterfly_step<kMax, 8>(x, lane);
-  butterfly_step<kMax, 4>(x, lane);
-  butterfly_step<kMax, 2>(x, lane);
-  butterfly_step<kMax, 1>(x, lane);
-  return x[0];
 }
 
 struct TileCoord {
@@ -95,7 +82,7 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmArgs& a
 template <int kN, typename T, int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const ConvGemmArgs a) {
+                 const __grid_constant__ CUtensorMap tmO, const ConvGemmArgs a) {
   using C = Cfg<kN, kCG>;
   constexpr int kStages = C::kStages;
   constexpr int kFmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
@@ -103,7 +90,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   const uint32_t raw_addr = smem_u32(smem_raw);
   uint8_t* smem = smem_raw + ((1024u - (raw_addr & 1023u)) & 1023u);  // SWIZZLE_128B wants 1024-B alignment
-  float* stat = reinterpret_cast<float*>(smem + size_t(kStages) * C::kStageBytes);
+  uint8_t* otile = smem + size_t(kStages) * C::kStageBytes;  // 1024-byte aligned (stage sizes are multiples of 1 KiB)
+  float* stat = reinterpret_cast<float*>(otile + C::kOutBytes);
   uint64_t* full = reinterpret_cast<uint64_t*>(stat + C::kStatFloats);
   uint64_t* empty = full + kStages;
   uint64_t* tfull = empty + kStages;
@@ -120,11 +108,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int unit0 = blockIdx.x / kCG, unit_step = gridDim.x / kCG;
   auto unit_tile = [&](int unit) { return ((unit / a.n_blocks) * kCG + int(rank)) * a.n_blocks + unit % a.n_blocks; };
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    tma_prefetch_desc(&tmO);
   }
-  if (warp == 1 && lane == 0) {
+  if (warp == kWarpMma && lane == 0) {
     for (int i = 0; i < kStages; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
@@ -135,7 +124,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     fence_barrier_init();
   }
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     if (kCG == 2) {
       tmem_alloc_cg2(tmem_slot, C::kTmemCols);
       tmem_relinquish_cg2();
@@ -149,7 +138,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  if (warp == 0) {
+  if (warp == kWarpTma) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       int s = 0;
@@ -183,7 +172,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         }
       }
     }
-  } else if (warp == 1 && rank == 0) {
+  } else if (warp == kWarpMma && rank == 0) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only in a pair)
     constexpr uint32_t idesc = umma_idesc_f16(kFmt, kTileM * kCG, kN);
     int s = 0, as = 0;
@@ -221,21 +210,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
-  } else if (warp >= 4) {
+  } else if (warp < 8) {
     // ------------------------------------------------------------------ epilogue
     const int q = warp & 3;             // TMEM lane quarter this warp may read
-    const int half = (warp - 4) >> 2;   // two warps share a quarter: each takes half of the kN columns
+    const int half = warp >> 2;         // two warps share a quarter: each takes half of the kN columns
     const int m = q * 32 + lane;        // accumulator row = pixel inside the tile
-    const int ry = m >> a.log2Wt, rx = m & (a.Wt - 1);
-    const int et = threadIdx.x - (kThreads - kEpiThreads);
+    const int et = threadIdx.x;
+    // column pass role: this warp reduces rows [cp_part*kRows, +kRows) of slab cp_slab; lane owns 2 adjacent columns
+    constexpr int kRows = kTileM / C::kParts;
+    const int cp_slab = warp / C::kParts, cp_part = warp % C::kParts;
     int as = 0;
     uint32_t aph = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const TileCoord tc = decode_tile(unit_tile(unit), a);
-      const int gy = tc.ty * a.R + ry, gx = tc.tx * a.Wt + rx;
-      T* orow = reinterpret_cast<T*>(a.out) + size_t(tc.b) * a.out_bs +
-                size_t(gy * a.oy_mul + a.oy_off[tc.phase]) * a.out_rs +
-                size_t(gx * a.ox_mul + a.ox_off[tc.phase]) * a.out_ps + tc.nb * kN;
       mbar_wait(&tfull[as], aph);
       tc_fence_after();
 #pragma unroll 1
@@ -244,7 +231,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(as * kN + ch * 32), v);
         tmem_ld_wait();
         float r[32];
-        if (a.epi_mode == 1) {
+        if ((a.epi_mode & 3) == 1) {
 #pragma unroll
           for (int i = 0; i < 32; ++i) {
             float f = __uint_as_float(v[i]) + __ldg(a.bias + tc.nb * kN + ch * 32 + i);
@@ -254,47 +241,61 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll
           for (int i = 0; i < 32; ++i) r[i] = __uint_as_float(v[i]);
         }
-        uint32_t pk[16];
+        // stage the rounded values: row m of slab ch/2, 16-byte chunk c at (c ^ (m & 7)) -- conflict-free STS.128
+        uint8_t* rowp = otile + (ch >> 1) * C::kSlabBytes + m * 128;
 #pragma unroll
-        for (int i = 0; i < 16; ++i) pk[i] = Cvt<T>::pack2(r[2 * i], r[2 * i + 1]);
-        uint4* dst = reinterpret_cast<uint4*>(orow + ch * 32);
-#pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
-        if (a.partials != nullptr) {
-          // statistics of the values as stored (rounded to T), so that (y - mean) is exactly centred
-#pragma unroll
-          for (int i = 0; i < 16; ++i) {
-            const float2 f2 = Cvt<T>::unpack2(pk[i]);
-            r[2 * i] = f2.x;
-            r[2 * i + 1] = f2.y;
-          }
-          float t[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = r[i];
-          const float s1 = butterfly_reduce<false>(t, lane);
-#pragma unroll
-          for (int i = 0; i < 32; ++i) t[i] = r[i] * r[i];
-          const float s2 = butterfly_reduce<false>(t, lane);
-          const float mx = butterfly_reduce<true>(r, lane);
-          stat[(q * 3 + 0) * kN + ch * 32 + lane] = s1;
-          stat[(q * 3 + 1) * kN + ch * 32 + lane] = s2;
-          stat[(q * 3 + 2) * kN + ch * 32 + lane] = mx;
+        for (int i = 0; i < 4; ++i) {
+          const uint4 pk = make_uint4(Cvt<T>::pack2(r[8 * i], r[8 * i + 1]), Cvt<T>::pack2(r[8 * i + 2], r[8 * i + 3]),
+                                      Cvt<T>::pack2(r[8 * i + 4], r[8 * i + 5]), Cvt<T>::pack2(r[8 * i + 6], r[8 * i + 7]));
+          *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (m & 7)) << 4)) = pk;
         }
       }
       tc_fence_before();
       if (kCG == 2 && rank != 0) mbar_arrive_remote(&tempty[as], 0);  // the leader's MMA warp owns the TMEM pipeline
       else mbar_arrive(&tempty[as]);  // accumulator stage may be overwritten by the next-but-one tile
+      fence_proxy_async_smem();        // generic-proxy writes above -> visible to the TMA (async proxy) store below
+      named_bar_sync(1, kEpiThreads);
+      if (et == 0 && !(a.epi_mode & 4)) {  // bit 2: timing experiment only (DUCOSY_DEBUG_SKIP_STORE)
+#pragma unroll
+        for (int sb = 0; sb < C::kSlabs; ++sb)
+          tma_store_5d(&tmO, otile + sb * C::kSlabBytes, tc.nb * kN + sb * 64, a.ox_off[tc.phase], tc.tx * a.Wt,
+                       a.oy_off[tc.phase], (tc.b * a.TY + tc.ty) * a.R);
+        tma_store_commit();
+      }
       if (a.partials != nullptr) {
+        // statistics of the values as stored (rounded to T), so that (y - mean) is exactly centred
+        const uint8_t* sl = otile + cp_slab * C::kSlabBytes + (lane & 3) * 4;
+        float s1a = 0.f, s1b = 0.f, s2a = 0.f, s2b = 0.f, mxa = -INFINITY, mxb = -INFINITY;
+#pragma unroll 8
+        for (int rr = 0; rr < kRows; ++rr) {
+          const int mr = cp_part * kRows + rr;
+          const float2 f = Cvt<T>::unpack2(*reinterpret_cast<const uint32_t*>(sl + mr * 128 + (((lane >> 2) ^ (mr & 7)) << 4)));
+          s1a += f.x;
+          s1b += f.y;
+          s2a = fmaf(f.x, f.x, s2a);
+          s2b = fmaf(f.y, f.y, s2b);
+          mxa = fmaxf(mxa, f.x);
+          mxb = fmaxf(mxb, f.y);
+        }
+        const int col = cp_slab * 64 + lane * 2;
+        *reinterpret_cast<float2*>(&stat[(cp_part * 3 + 0) * kN + col]) = make_float2(s1a, s1b);
+        *reinterpret_cast<float2*>(&stat[(cp_part * 3 + 1) * kN + col]) = make_float2(s2a, s2b);
+        *reinterpret_cast<float2*>(&stat[(cp_part * 3 + 2) * kN + col]) = make_float2(mxa, mxb);
         named_bar_sync(1, kEpiThreads);
         float* pdst = a.partials + (size_t(tc.b) * tiles_m_per_sample + tc.tile_m) * 3 * a.Cout + tc.nb * kN;
         for (int idx = et; idx < 3 * kN; idx += kEpiThreads) {
-          const int which = idx / kN, col = idx - which * kN;
-          const float v0 = stat[(0 * 3 + which) * kN + col], v1 = stat[(1 * 3 + which) * kN + col];
-          const float v2 = stat[(2 * 3 + which) * kN + col], v3 = stat[(3 * 3 + which) * kN + col];
-          pdst[which * a.Cout + col] = which == 2 ? fmaxf(fmaxf(v0, v1), fmaxf(v2, v3)) : (v0 + v1) + (v2 + v3);
+          const int which = idx / kN, col2 = idx - which * kN;
+          float acc = stat[which * kN + col2];
+#pragma unroll
+          for (int pp = 1; pp < C::kParts; ++pp) {
+            const float o = stat[(pp * 3 + which) * kN + col2];
+            acc = which == 2 ? fmaxf(acc, o) : acc + o;
+          }
+          pdst[which * a.Cout + col2] = acc;
         }
-        named_bar_sync(1, kEpiThreads);
       }
+      if (et == 0) tma_store_wait_read();  // the staged tile may be overwritten once the TMA engine has read it
+      named_bar_sync(1, kEpiThreads);
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -302,7 +303,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
   tc_fence_before();
   if (kCG == 2) cluster_sync_all(); else __syncthreads();  // pair: the peer may still signal barriers in this CTA
-  if (warp == 2) {
+  if (warp == kWarpAlloc) {
     tc_fence_after();
     if (kCG == 2) tmem_dealloc_cg2(tmem_base, C::kTmemCols); else tmem_dealloc(tmem_base, C::kTmemCols);
   }
@@ -326,8 +327,8 @@ EncodeTiledFn get_encode_fn() {
 }
 
 template <int kN, typename T, int kCG>
-int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmArgs& args, int grid,
-                cudaStream_t stream) {
+int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmArgs& args,
+                int grid, cudaStream_t stream) {
   using C = Cfg<kN, kCG>;
   static bool configured = false;
   auto kern = conv_gemm_kernel<kN, T, kCG>;
@@ -349,10 +350,10 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const ConvGemmAr
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
-    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, args);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, args);
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaLaunchKernelEx(conv_gemm pair): %s", cudaGetErrorString(e));
   } else {
-    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, args);
+    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, args);
   }
   return check_launch("conv_gemm_kernel");
 }
@@ -417,6 +418,8 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.partials = p.partials;
   a.bias = p.bias;
   a.epi_mode = p.epi_mode;
+  static const bool skip_store = getenv("DUCOSY_DEBUG_SKIP_STORE") != nullptr;
+  if (skip_store) a.epi_mode |= 4;
 
   // CTA pairs whenever the m-tiles of one (sample, phase) pair up; DUCOSY_CONV_CTA_GROUP=1 forces single CTAs.
   static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();
@@ -425,7 +428,26 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   EncodeTiledFn encode = get_encode_fn();
   DUCOSY_CHECK(encode != nullptr, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   const CUtensorMapDataType dt = p.dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmO;
+  {
+    // output tile store: (c, x-phase, x, y-phase, y*batch) so that the sub-pixel (x2 upsampling) phases are boxes too
+    const cuuint64_t C2 = cuuint64_t(p.Cout) * 2, W = cuuint64_t(p.Wo), H = cuuint64_t(p.Ho);
+    cuuint64_t gdim[5], gstr[4];
+    DUCOSY_CHECK(p.oy_mul == p.ox_mul && (p.oy_mul == 1 || (p.oy_mul == 2 && p.Ho % 2 == 0 && p.Wo % 2 == 0)),
+                 DUCOSY_ERR_SHAPE, "conv_gemm: output stride must be 1 or 2");
+    if (p.oy_mul == 1) {
+      gdim[0] = p.Cout; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
+      gstr[0] = C2; gstr[1] = C2; gstr[2] = W * C2; gstr[3] = W * C2;
+    } else {
+      gdim[0] = p.Cout; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
+      gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
+    }
+    const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
+    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUresult r = encode(&tmO, dt, 5, p.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled(out) failed with %d", int(r));
+  }
   {
     const cuuint64_t C2 = cuuint64_t(p.Cin) * 2, W = cuuint64_t(p.Wp), H = cuuint64_t(p.Hp);
     cuuint64_t gdim[5], gstr[4];
@@ -464,11 +486,11 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
 
 #define DUCOSY_LAUNCH_N(N)                                                                             \
   if (cg == 2) {                                                                                       \
-    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 2>(tmA, tmB, a, grid, stream);             \
-    else return launch_impl<N, __nv_bfloat16, 2>(tmA, tmB, a, grid, stream);                            \
+    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 2>(tmA, tmB, tmO, a, grid, stream);             \
+    else return launch_impl<N, __nv_bfloat16, 2>(tmA, tmB, tmO, a, grid, stream);                            \
   } else {                                                                                             \
-    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 1>(tmA, tmB, a, grid, stream);             \
-    else return launch_impl<N, __nv_bfloat16, 1>(tmA, tmB, a, grid, stream);                            \
+    if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 1>(tmA, tmB, tmO, a, grid, stream);             \
+    else return launch_impl<N, __nv_bfloat16, 1>(tmA, tmB, tmO, a, grid, stream);                            \
   }
   if (kN == 256) { DUCOSY_LAUNCH_N(256) }
   if (kN == 128) { DUCOSY_LAUNCH_N(128) }
