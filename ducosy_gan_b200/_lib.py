@@ -34,6 +34,8 @@ SIGNATURES = {
     "ducosy_dewindow_composite": (_i, [_p, _p, _p, _p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p]),
     "ducosy_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_upconv_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_pack_upconv_merged_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_upconv2x_merged_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_stem_weight": (_i, [_p, _p, _i, _i, _p]),
     "ducosy_conv2d_nhwc": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_upconv2x_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),

@@ -101,7 +101,7 @@ GenLayout make_layout(const ducosy_gen_config& c) {
     }
   }
   L.up1 = take(size_t(4) * 128 * 4 * 256 * 2);
-  L.up2 = take(size_t(4) * 64 * 4 * 128 * 2);
+  L.up2 = take(size_t(4) * 64 * 9 * 128 * 2);  // merged-phase packing (N = 256, nine source offsets)
   L.outw = take(7 * 8 * 64 * 2);
   L.outb = take(4);
   L.total = off;
@@ -256,8 +256,8 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H4, W4), H2 * W2, scale, shift, nullptr, nullptr, nullptr, B, 128, st));
   DUCOSY_TRY(ducosy_in_apply_pad(P(w.y1), scale, shift, P(w.p1), B, H2, W2, 128, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   // ---- up 2: nearest x2 + 3x3 p1 128 -> 64, IN, ReLU
-  DUCOSY_TRY(ducosy_upconv2x_nhwc(P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt, st));
-  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H2, W2), H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
+  DUCOSY_TRY(ducosy_upconv2x_merged_nhwc(P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt, st));
+  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(1, H2, W2), H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
   DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p_out), B, H, W, 64, 3, DUCOSY_PAD_REFLECT, DUCOSY_ACT_RELU, dt, st));
   // ---- output: reflect-pad 3 + 7x7 conv 64 -> 1 + tanh   modules/model.py:112
   return ducosy_out_conv7x7_tanh(P(w.p_out), pk + L.outw, reinterpret_cast<const float*>(pk + L.outb), out, B, H, W, dt, st);
@@ -319,6 +319,20 @@ extern "C" int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, v
   return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
 }
 
+extern "C" int ducosy_upconv2x_merged_nhwc(const void* in_pad, const void* w_merged, void* out, float* partials, int B,
+                                           int Hs, int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(in_pad && w_merged && out && B > 0, DUCOSY_ERR_ARG, "upconv2x_merged_nhwc: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_merged_nhwc: bad dtype");
+  DUCOSY_CHECK(Cout == 64, DUCOSY_ERR_SHAPE, "upconv2x_merged_nhwc: Cout must be 64 (N = 4*Cout = 256)");
+  DUCOSY_TRY(check_device_cached());
+  ConvPlan p{};
+  p.in = in_pad; p.B = B; p.Hp = Hs + 2; p.Wp = Ws + 2; p.Cin = Cin; p.stride = 1;
+  p.w = w_merged; p.Cout = 4 * Cout; p.fold = 4; fill_taps_3x3(p);
+  p.Hg = Hs; p.Wg = Ws; p.out = out; p.Ho = 2 * Hs; p.Wo = 2 * Ws; p.oy_mul = p.ox_mul = 2;
+  p.partials = partials; p.dtype = dtype;
+  return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ducosy_generator_num_params(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_params: null config");
   return 6 + cfg->num_residual_blocks * (4 + (cfg->use_cbam ? 3 : 0)) + 6;
@@ -362,7 +376,7 @@ extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* 
     }
   }
   DUCOSY_TRY(ducosy_pack_upconv_weight(params[k], pk + L.up1, 128, 256, c.dtype, stream)); k += 2;
-  DUCOSY_TRY(ducosy_pack_upconv_weight(params[k], pk + L.up2, 64, 128, c.dtype, stream)); k += 2;
+  DUCOSY_TRY(ducosy_pack_upconv_merged_weight(params[k], pk + L.up2, 64, 128, c.dtype, stream)); k += 2;
   DUCOSY_TRY(ducosy_pack_out_weight(params[k++], pk + L.outw, c.dtype, stream));
   cudaMemcpyAsync(pk + L.outb, params[k++], 4, cudaMemcpyDeviceToDevice, st);
   return check_launch("generator_pack");

@@ -39,7 +39,9 @@ struct ConvGemmArgs {
   int B, TY, TX;           // tiles per sample along the GEMM grid rows / cols
   int R, Wt, log2Wt;       // a tile is R rows x Wt cols of the GEMM grid (R*Wt == 128)
   int rows_per_sample;     // units of the outermost TMA dimension per sample
-  int Cout;                // total output channels (= n_blocks * kN)
+  int Cout;                // GEMM N total (= n_blocks * kN) = fold * Cstore
+  int Cstore;              // channels of the output tensor
+  int fold;                // 1, or 4: the four x2-upsampling phases are column blocks of ONE tile (merged phases)
   int8_t tap_xp[kMaxPhases][kMaxTaps], tap_dx[kMaxPhases][kMaxTaps];
   int8_t tap_yp[kMaxPhases][kMaxTaps], tap_dy[kMaxPhases][kMaxTaps];
   void* out;               // raw conv output, NHWC [B, Ho, Wo, Cout]
@@ -59,6 +61,7 @@ struct ConvPlan {
   int stride;              // 1 or 2 (2: Hp and Wp must be even)
   const void* w;           // packed weights [num_phases*Cout][num_taps*Cin], K-major
   int Cout, num_phases, num_taps;
+  int fold;                // 0/1 normal; 4: Cout = 4 * (output channels), column block f = output phase (f>>1, f&1)
   int8_t tap_dy[kMaxPhases][kMaxTaps], tap_dx[kMaxPhases][kMaxTaps];  // offsets in padded input pixels
   int Hg, Wg;              // GEMM grid per sample
   void* out;

@@ -257,9 +257,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       named_bar_sync(1, kEpiThreads);
       if (et == 0 && !(a.epi_mode & 4)) {  // bit 2: timing experiment only (DUCOSY_DEBUG_SKIP_STORE)
 #pragma unroll
-        for (int sb = 0; sb < C::kSlabs; ++sb)
-          tma_store_5d(&tmO, otile + sb * C::kSlabBytes, tc.nb * kN + sb * 64, a.ox_off[tc.phase], tc.tx * a.Wt,
-                       a.oy_off[tc.phase], (tc.b * a.TY + tc.ty) * a.R);
+        for (int sb = 0; sb < C::kSlabs; ++sb) {
+          const int n = tc.nb * kN + sb * 64;
+          const int f = n / a.Cstore;  // merged phases: column block -> output phase; otherwise 0
+          tma_store_5d(&tmO, otile + sb * C::kSlabBytes, n - f * a.Cstore, a.fold > 1 ? (f & 1) : a.ox_off[tc.phase],
+                       tc.tx * a.Wt, a.fold > 1 ? (f >> 1) : a.oy_off[tc.phase], (tc.b * a.TY + tc.ty) * a.R);
+        }
         tma_store_commit();
       }
       if (a.partials != nullptr) {
@@ -282,16 +285,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         *reinterpret_cast<float2*>(&stat[(cp_part * 3 + 1) * kN + col]) = make_float2(s2a, s2b);
         *reinterpret_cast<float2*>(&stat[(cp_part * 3 + 2) * kN + col]) = make_float2(mxa, mxb);
         named_bar_sync(1, kEpiThreads);
-        float* pdst = a.partials + (size_t(tc.b) * tiles_m_per_sample + tc.tile_m) * 3 * a.Cout + tc.nb * kN;
-        for (int idx = et; idx < 3 * kN; idx += kEpiThreads) {
-          const int which = idx / kN, col2 = idx - which * kN;
-          float acc = stat[which * kN + col2];
+        // per-tile partial row [3][Cstore]; merged phases fold their `fold` column blocks into the same channels
+        const int ncols = kN / a.fold;
+        float* pdst = a.partials + (size_t(tc.b) * tiles_m_per_sample + tc.tile_m) * 3 * a.Cstore + (tc.nb * kN) % a.Cstore;
+        for (int idx = et; idx < 3 * ncols; idx += kEpiThreads) {
+          const int which = idx / ncols, col2 = idx - which * ncols;
+          float acc = which == 2 ? -INFINITY : 0.f;
+          for (int f = 0; f < a.fold; ++f)
 #pragma unroll
-          for (int pp = 1; pp < C::kParts; ++pp) {
-            const float o = stat[(pp * 3 + which) * kN + col2];
-            acc = which == 2 ? fmaxf(acc, o) : acc + o;
-          }
-          pdst[which * a.Cout + col2] = acc;
+            for (int pp = 0; pp < C::kParts; ++pp) {
+              const float o = stat[(pp * 3 + which) * kN + f * ncols + col2];
+              acc = which == 2 ? fmaxf(acc, o) : acc + o;
+            }
+          pdst[which * a.Cstore + col2] = acc;
         }
       }
       if (et == 0) tma_store_wait_read();  // the staged tile may be overwritten once the TMA engine has read it
@@ -394,6 +400,10 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.TX = p.Wg / Wt;
   a.rows_per_sample = p.stride == 1 ? p.Hp : p.Hp / 2;
   a.Cout = p.Cout;
+  a.fold = p.fold > 1 ? p.fold : 1;
+  a.Cstore = p.Cout / a.fold;
+  DUCOSY_CHECK(a.fold == 1 || (a.fold == 4 && p.num_phases == 1 && p.Cout == kN && a.Cstore % 64 == 0 && p.oy_mul == 2),
+               DUCOSY_ERR_SHAPE, "conv_gemm: merged phases need fold 4, one n-block, 64-channel slabs");
   for (int ph = 0; ph < p.num_phases; ++ph) {
     for (int t = 0; t < p.num_taps; ++t) {
       const int dy = p.tap_dy[ph][t], dx = p.tap_dx[ph][t];
@@ -410,9 +420,9 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
     a.ox_off[ph] = p.ox_off[ph];
   }
   a.out = p.out;
-  a.out_bs = (long long)p.Ho * p.Wo * p.Cout;
-  a.out_rs = p.Wo * p.Cout;
-  a.out_ps = p.Cout;
+  a.out_bs = (long long)p.Ho * p.Wo * a.Cstore;
+  a.out_rs = p.Wo * a.Cstore;
+  a.out_ps = a.Cstore;
   a.oy_mul = p.oy_mul;
   a.ox_mul = p.ox_mul;
   a.partials = p.partials;
@@ -431,15 +441,15 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   CUtensorMap tmA, tmB, tmO;
   {
     // output tile store: (c, x-phase, x, y-phase, y*batch) so that the sub-pixel (x2 upsampling) phases are boxes too
-    const cuuint64_t C2 = cuuint64_t(p.Cout) * 2, W = cuuint64_t(p.Wo), H = cuuint64_t(p.Ho);
+    const cuuint64_t C2 = cuuint64_t(a.Cstore) * 2, W = cuuint64_t(p.Wo), H = cuuint64_t(p.Ho);
     cuuint64_t gdim[5], gstr[4];
     DUCOSY_CHECK(p.oy_mul == p.ox_mul && (p.oy_mul == 1 || (p.oy_mul == 2 && p.Ho % 2 == 0 && p.Wo % 2 == 0)),
                  DUCOSY_ERR_SHAPE, "conv_gemm: output stride must be 1 or 2");
     if (p.oy_mul == 1) {
-      gdim[0] = p.Cout; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
+      gdim[0] = a.Cstore; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
       gstr[0] = C2; gstr[1] = C2; gstr[2] = W * C2; gstr[3] = W * C2;
     } else {
-      gdim[0] = p.Cout; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
+      gdim[0] = a.Cstore; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
       gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
     }
     const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};

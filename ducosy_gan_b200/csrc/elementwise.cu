@@ -63,6 +63,35 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __rest
   }
 }
 
+// Merged-phase variant for Cout = 64: ONE GEMM with N = 4*Cout columns (column block f = output phase) over the nine
+// source offsets (dy, dx) in {0,1,2}^2; entries of offsets a phase does not touch are zero.  2.25x the MACs of the
+// four 2x2 convs, but A tiles are loaded once for all phases and the tile is N = 256 wide.
+template <typename T>
+__global__ void pack_upconv_merged_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin) {
+  const long long total = 4LL * Cout * 9 * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    long long r = i / Cin;
+    const int tap = int(r % 9);
+    r /= 9;
+    const int o = int(r % Cout);
+    const int f = int(r / Cout);
+    const int py = f >> 1, px = f & 1, a = tap / 3 - py, b = tap % 3 - px;
+    float acc = 0.f;
+    if (a >= 0 && a <= 1 && b >= 0 && b <= 1) {
+      const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2);
+      const int r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+      const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2);
+      const int s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+      const float* wk = w + ((long long)o * Cin + c) * 9;
+      for (int rr = r0; rr <= r1; ++rr)
+        for (int ss = s0; ss <= s1; ++ss) acc += wk[rr * 3 + ss];
+    }
+    out[i] = Cvt<T>::from_f(acc);
+  }
+}
+
 template <typename T>
 __global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cin, int Kpad) {
   const int total = 64 * Kpad;
@@ -504,6 +533,15 @@ extern "C" int ducosy_pack_upconv_weight(const float* w, void* packed, int Cout,
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
                                       w, static_cast<T*>(packed), Cout, Cin)));
   return check_launch("pack_upconv_weight_kernel");
+}
+
+extern "C" int ducosy_pack_upconv_merged_weight(const float* w, void* packed, int Cout, int Cin, int dtype,
+                                                ducosy_stream_t stream) {
+  DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_merged_weight: bad argument");
+  const long long total = 36LL * Cout * Cin;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_merged_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      w, static_cast<T*>(packed), Cout, Cin)));
+  return check_launch("pack_upconv_merged_weight_kernel");
 }
 
 extern "C" int ducosy_pack_stem_weight(const float* w, void* packed, int Cin, int dtype, ducosy_stream_t stream) {

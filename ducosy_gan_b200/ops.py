@@ -124,6 +124,29 @@ def upconv2x_nhwc(x_pad: torch.Tensor, w_packed4: torch.Tensor):
     return y, partials
 
 
+def pack_upconv_merged_weight(w: torch.Tensor, dtype=torch.float16):
+    Cout, Cin, kh, kw = w.shape
+    assert kh == 3 and kw == 3
+    w = w.detach().to(torch.float32).contiguous()
+    with _dev(w):
+        out = torch.empty((4 * Cout, 9 * Cin), dtype=dtype, device=w.device)
+        call("ducosy_pack_upconv_merged_weight", ptr(w), ptr(out), Cout, Cin, dtype_code(dtype), stream_ptr())
+    return out
+
+
+def upconv2x_merged_nhwc(x_pad: torch.Tensor, w_merged: torch.Tensor):
+    """Merged-phase Upsample(x2)+Conv3x3 (Cout = 64): raw y [B,2Hs,2Ws,Cout], partials [B,Hs*Ws/128,3,Cout]."""
+    B, Hp, Wp, Cin = x_pad.shape
+    Hs, Ws = Hp - 2, Wp - 2
+    Cout = w_merged.shape[0] // 4
+    with _dev(x_pad):
+        y = torch.empty((B, 2 * Hs, 2 * Ws, Cout), dtype=x_pad.dtype, device=x_pad.device)
+        partials = torch.empty((B, Hs * Ws // 128, 3, Cout), dtype=torch.float32, device=x_pad.device)
+        call("ducosy_upconv2x_merged_nhwc", ptr(x_pad), ptr(w_merged), ptr(y), ptr(partials), B, Hs, Ws, Cin, Cout,
+             dtype_code(x_pad.dtype), stream_ptr())
+    return y, partials
+
+
 def stem_im2col(x: torch.Tensor, dtype=torch.float16):
     B, Cin, H, W = x.shape
     x = x.to(torch.float32).contiguous()

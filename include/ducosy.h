@@ -78,6 +78,10 @@ int ducosy_pack_conv_weight(const float* w_oihw, void* packed, int Cout, int Cin
 /* Pack the 3x3 weight of "Upsample(x2, nearest) + Conv2d(3x3, pad 1)" (modules/model.py:108) into four
  * phase-specific 2x2 kernels on the source grid: [4*Cout][4*Cin], phase = py*2+px, tap = a*2+b. */
 int ducosy_pack_upconv_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
+/* Merged-phase packing of the same layer for Cout = 64: [4*Cout][9*Cin], row = phase*Cout + o, k = (dy*3+dx)*Cin + c
+ * over the nine source offsets; zero where a phase does not use an offset (one N = 256 GEMM instead of four N = 64). */
+int ducosy_pack_upconv_merged_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype,
+                                     ducosy_stream_t stream);
 /* Pack the 7x7 stem weight [64][Cin][7][7] into [64][Kpad], Kpad = roundup(49*Cin, 64), k = c*49 + r*7 + s. */
 int ducosy_pack_stem_weight(const float* w_oihw, void* packed, int Cin, int dtype, ducosy_stream_t stream);
 
@@ -94,6 +98,10 @@ int ducosy_conv2d_nhwc(const void* in, const void* w, void* out, float* partials
  * out [B][2Hs][2Ws][Cout]; partials [B][4*Hs*Ws/128][3][Cout]. */
 int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, void* out, float* partials, int B, int Hs, int Ws,
                          int Cin, int Cout, int dtype, ducosy_stream_t stream);
+
+/* Same layer through the merged-phase packing (Cout = 64): partials [B][Hs*Ws/128][3][Cout]. */
+int ducosy_upconv2x_merged_nhwc(const void* in_pad, const void* w_merged, void* out, float* partials, int B, int Hs,
+                                int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream);
 
 /* im2col for the 7x7 reflect-padded stem (modules/model.py:94): x fp32 NCHW [B][Cin][H][W] -> A [B*H*W][Kpad]. */
 int ducosy_stem_im2col(const float* x_nchw, void* a_mat, int B, int Cin, int H, int W, int dtype, ducosy_stream_t stream);

@@ -152,6 +152,25 @@ def test_upconv2x_matches_upsample_conv(ops, dtype, shape):
     assert torch.equal(partials[:, :, 2, :].amax(1), yf.amax((1, 2)))
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_upconv2x_merged_phases(ops, dtype):
+    B, Hs, Ws, Cin, Cout = 2, 16, 32, 128, 64
+    x = _rand((B, Cin, Hs, Ws), 23).to(dtype)
+    w = _rand((Cout, Cin, 3, 3), 24, 0.05)
+    xp = F.pad(x.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    y, partials = ops.upconv2x_merged_nhwc(xp, ops.pack_upconv_merged_weight(w.cuda(), dtype))
+    y4, _ = ops.upconv2x_nhwc(xp, ops.pack_upconv_weight(w.cuda(), dtype))
+    assert torch.equal(y, y4)                      # same operands, same k order per phase: bit-identical to the 4-phase path
+    ref = F.conv2d(F.interpolate(x.float().cuda(), scale_factor=2, mode="nearest"), w.cuda(), padding=1)
+    eps = 2.0 ** -9 if dtype == torch.float16 else 2.0 ** -6
+    assert (y.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= eps * ref.abs().max().item() + 1e-3
+    yf = y.float()
+    assert partials.shape == (B, Hs * Ws // 128, 3, Cout)
+    assert torch.allclose(partials[:, :, 0, :].sum(1), yf.sum((1, 2)), rtol=1e-3, atol=0.05)
+    assert torch.allclose(partials[:, :, 1, :].sum(1), (yf * yf).sum((1, 2)), rtol=1e-3, atol=0.05)
+    assert torch.equal(partials[:, :, 2, :].amax(1), yf.amax((1, 2)))
+
+
 # ------------------------------------------------------------------ stem im2col
 def test_stem_im2col_and_hu_variant(ops):
     x = _rand((2, 3, 16, 24), 31)
