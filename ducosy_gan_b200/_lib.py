@@ -41,6 +41,8 @@ SIGNATURES = {
     "ducosy_upconv2x_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_stem_im2col": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_stem_im2col_hu": (_i, [_p, _p, _i, _i, _i, _f, _f, _f, _f, _i, _p]),
+    "ducosy_stem_prepare": (_i, [_p, _p, _f, _f, _f, _f, _p, _i, _i, _i, _i, _p]),
+    "ducosy_stem_fused": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_in_finalize": (_i, [_p, _i, _i, _p, _p, _p, _p, _p, _i, _i, _p]),
     "ducosy_in_apply_pad": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_cbam_pool": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),

@@ -172,6 +172,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   DUCOSY_CHECK(packed && out && ws && (x || px), DUCOSY_ERR_ARG, "generator_forward: null pointer");
   DUCOSY_TRY(check_device_cached());
   DUCOSY_TRY(check_gen_shape(c, B, H, W));
+  DUCOSY_CHECK(px == nullptr || c.input_channels == 1, DUCOSY_ERR_SHAPE, "generator_forward_hu: needs input_channels == 1");
   DUCOSY_CHECK((reinterpret_cast<uintptr_t>(ws) & 1023) == 0 && (reinterpret_cast<uintptr_t>(packed) & 255) == 0,
                DUCOSY_ERR_ALIGN, "generator_forward: workspace must be 1024-byte and packed weights 256-byte aligned");
   const GenLayout L = make_layout(c);
@@ -190,21 +191,29 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   const int nb = c.num_residual_blocks;
   const int dt = c.dtype;
 
-  // ---- stem: reflect-pad 3 + 7x7 conv as (im2col) x (weights), IN, ReLU   modules/model.py:94
-  if (px != nullptr) {
-    DUCOSY_CHECK(c.input_channels == 1, DUCOSY_ERR_SHAPE, "generator_forward_hu: needs input_channels == 1");
-    DUCOSY_TRY(ducosy_stem_im2col_hu(px, P(w.a_stem), B, H, W, slope, intercept, lo, hi, dt, st));
+  // ---- stem: reflect-pad 3 + 7x7 conv, IN, ReLU   modules/model.py:94
+  if (c.input_channels == 1) {
+    // fused two-pass stem (stem.cu): statistics pass, then conv + normalise + ReLU written once, zero-padded
+    DUCOSY_TRY(ducosy_stem_prepare(x, px, slope, intercept, lo, hi, P(w.a_stem), B, H, W, dt, st));
+    DUCOSY_TRY(ducosy_stem_fused(P(w.a_stem), pk + L.stem, partials, nullptr, nullptr, nullptr, B, H, W, 0, dt, st));
+    DUCOSY_TRY(ducosy_in_finalize(partials, H, H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
+    DUCOSY_TRY(ducosy_stem_fused(P(w.a_stem), pk + L.stem, nullptr, scale, shift, P(w.p0), B, H, W, 1, dt, st));
   } else {
-    DUCOSY_TRY(ducosy_stem_im2col(x, P(w.a_stem), B, c.input_channels, H, W, dt, st));
-  }
-  {
-    ConvPlan p{};
-    p.in = P(w.a_stem); p.B = B; p.Hp = H; p.Wp = W; p.Cin = L.Kpad; p.stride = 1;
-    p.w = pk + L.stem; p.Cout = 64; p.num_phases = 1; p.num_taps = 1;
-    p.Hg = H; p.Wg = W; p.out = P(w.y0); p.Ho = H; p.Wo = W; p.oy_mul = p.ox_mul = 1;
-    p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 64, H * W, st));
-    DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p0), B, H, W, 64, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
+    // general input_channels: (im2col) x (weights) on the tensor-core GEMM
+    if (px != nullptr) {
+        DUCOSY_TRY(ducosy_stem_im2col_hu(px, P(w.a_stem), B, H, W, slope, intercept, lo, hi, dt, st));
+    } else {
+      DUCOSY_TRY(ducosy_stem_im2col(x, P(w.a_stem), B, c.input_channels, H, W, dt, st));
+    }
+    {
+      ConvPlan p{};
+      p.in = P(w.a_stem); p.B = B; p.Hp = H; p.Wp = W; p.Cin = L.Kpad; p.stride = 1;
+      p.w = pk + L.stem; p.Cout = 64; p.num_phases = 1; p.num_taps = 1;
+      p.Hg = H; p.Wg = W; p.out = P(w.y0); p.Ho = H; p.Wo = W; p.oy_mul = p.ox_mul = 1;
+      p.partials = partials; p.dtype = dt;
+      DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 64, H * W, st));
+      DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p0), B, H, W, 64, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
+    }
   }
   // ---- down 1: 3x3 s2 p1 64 -> 128, IN, ReLU   modules/model.py:96-98
   {

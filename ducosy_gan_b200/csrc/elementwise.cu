@@ -2,6 +2,7 @@
 // with the HU window), InstanceNorm finalize/apply (+ReLU, + padding writer), CBAM channel MLP, CBAM spatial
 // pooling / 7x7 attention conv, and the residual add.  NHWC 16-bit activations, 128-bit accesses.
 #include "common.cuh"
+#include "input_fn.cuh"
 
 namespace ducosy {
 namespace {
@@ -13,12 +14,6 @@ int ew_grid(long long work_items, int threads) {
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   return int(blocks);
-}
-
-__device__ __forceinline__ int reflect_idx(int i, int n) {  // ReflectionPad2d semantics (no edge repeat)
-  if (i < 0) i = -i;
-  if (i >= n) i = 2 * n - 2 - i;
-  return i;
 }
 
 // ------------------------------------------------------------------ weight packing
@@ -104,21 +99,6 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restri
 // ------------------------------------------------------------------ stem im2col
 // A[(b,y,x)][k], k = c*49 + r*7 + s  <-  in[b][c][reflect(y+r-3)][reflect(x+s-3)], zero for k >= 49*Cin.
 // One thread builds 8 consecutive k (one 16-byte store); consecutive threads -> consecutive chunks of a row.
-struct InF32 {
-  const float* x;
-  __device__ __forceinline__ float at(int b, int c, int y, int x_, int Cin, int H, int W) const {
-    return x[(((long long)b * Cin + c) * H + y) * W + x_];
-  }
-};
-struct InHU {
-  const int16_t* px;
-  float slope, intercept, lo, hi, span;
-  __device__ __forceinline__ float at(int b, int, int y, int x_, int, int H, int W) const {
-    const float hu = __fadd_rn(__fmul_rn(float(px[((long long)b * H + y) * W + x_]), slope), intercept);
-    const float c = fminf(fmaxf(hu, lo), hi);
-    return __fsub_rn(__fdiv_rn(__fmul_rn(2.0f, __fsub_rn(c, lo)), span), 1.0f);  // preprocess.py:79-84
-  }
-};
 template <typename T, typename In>
 __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int H, int W, int Kpad) {
   const int chunks = Kpad / 8;

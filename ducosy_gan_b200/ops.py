@@ -223,3 +223,23 @@ def out_conv7x7_tanh(x_pad, w_packed, bias):
         call("ducosy_out_conv7x7_tanh", ptr(x_pad), ptr(w_packed), ptr(bias), ptr(out), B, H, W,
              dtype_code(x_pad.dtype), stream_ptr())
     return out
+
+
+def stem_fused(w_packed, x=None, px=None, window=None):
+    """Fused stem for Cin = 1: (x fp32 [B,1,H,W] | px int16 [B,H,W] + window=(slope, intercept, lo, hi)) ->
+    zero-padded ReLU(IN(conv7x7)) [B,H+2,W+2,64] 16-bit."""
+    src = x if x is not None else px
+    B, H, W = (x.shape[0], x.shape[2], x.shape[3]) if x is not None else px.shape
+    slope, intercept, lo, hi = window if window is not None else (0.0, 0.0, 0.0, 0.0)
+    dt = w_packed.dtype
+    with _dev(src):
+        xw = torch.empty((B, H, W), dtype=dt, device=src.device)
+        partials = torch.empty((B, H, 3, 64), dtype=torch.float32, device=src.device)
+        out = torch.empty((B, H + 2, W + 2, 64), dtype=dt, device=src.device)
+        xin = x.to(torch.float32).contiguous() if x is not None else None
+        call("ducosy_stem_prepare", ptr(xin), ptr(px) if px is not None else None, float(slope), float(intercept),
+             float(lo), float(hi), ptr(xw), B, H, W, dtype_code(dt), stream_ptr())
+        call("ducosy_stem_fused", ptr(xw), ptr(w_packed), ptr(partials), None, None, None, B, H, W, 0, dtype_code(dt), stream_ptr())
+        scale, shift = in_finalize(partials, H * W)
+        call("ducosy_stem_fused", ptr(xw), ptr(w_packed), None, ptr(scale), ptr(shift), ptr(out), B, H, W, 1, dtype_code(dt), stream_ptr())
+    return out

@@ -109,6 +109,17 @@ int ducosy_stem_im2col(const float* x_nchw, void* a_mat, int B, int Cin, int H, 
 int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, float slope, float intercept, float lo,
                           float hi, int dtype, ducosy_stream_t stream);
 
+/* Fused stem for input_channels == 1 (modules/preprocess.py:72-84 + modules/model.py:94).
+ * ducosy_stem_prepare: network input -- either x_nchw (fp32 [B][1][H][W]) or px (stored int16 [B][H][W] through the
+ *   slope/intercept/lo/hi window) -- -> 16-bit xw [B][H][W].
+ * ducosy_stem_fused(xw, w_packed from ducosy_pack_stem_weight, ...):
+ *   apply == 0: statistics pass -> partials [B][H][3][64] (then ducosy_in_finalize(partials, H, H*W, ...));
+ *   apply == 1: conv again, (y*scale+shift), ReLU -> out_pad [B][H+2][W+2][64] 16-bit with a zero border. */
+int ducosy_stem_prepare(const float* x_nchw, const int16_t* px, float slope, float intercept, float lo, float hi, void* xw,
+                        int B, int H, int W, int dtype, ducosy_stream_t stream);
+int ducosy_stem_fused(const void* xw, const void* w_packed, float* partials, const float* scale, const float* shift,
+                      void* out_pad, int B, int H, int W, int apply, int dtype, ducosy_stream_t stream);
+
 /* InstanceNorm statistics (modules/model.py InstanceNorm2d: biased var, eps 1e-5) from the conv partials:
  * scale[b][c] = rstd, shift[b][c] = -mean*rstd.  When fc0/fc2 are given (CBAM channel attention,
  * modules/model.py:13-24: fc0 [C/16][C], fc2 [C][C/16], fp32) the channel attention

@@ -186,6 +186,25 @@ def test_stem_im2col_and_hu_variant(ops):
     assert torch.equal(ah[..., :49].cpu(), refh)
 
 
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_stem_fused_two_pass(ops, dtype):
+    # conv7x7(reflect pad 3) -> IN -> ReLU -> zero pad 1, from a fp32 tensor and from stored pixels through the HU window
+    w = _rand((64, 1, 7, 7), 33, 0.1)
+    wp = ops.pack_stem_weight(w.cuda(), dtype)
+    w_r = wp.float()[:, :49].reshape(64, 1, 7, 7)
+    tol = 6e-3 if dtype == torch.float16 else 4e-2
+    x = _rand((2, 1, 32, 128), 34).to(dtype).float()        # representable in the operand type
+    out = ops.stem_fused(wp, x=x.cuda())
+    ref = F.pad(F.relu(F.instance_norm(F.conv2d(F.pad(x.cuda(), (3, 3, 3, 3), mode="reflect"), w_r))), (1, 1, 1, 1))
+    assert (out.float().permute(0, 3, 1, 2) - ref).abs().max().item() < tol
+    assert torch.count_nonzero(out[:, 0]).item() == 0 and torch.count_nonzero(out[:, :, -1]).item() == 0
+    px = orc.synthetic_volume(2, 16, 128, seed=35)
+    outh = ops.stem_fused(wp, px=torch.from_numpy(px).cuda(), window=(1.0, -1024.0, -150.0, 250.0))
+    xw = torch.from_numpy(orc.hu_window(px, 1.0, -1024.0, -150, 250).astype(np.float32))[:, None].to(dtype).float().cuda()
+    refh = F.pad(F.relu(F.instance_norm(F.conv2d(F.pad(xw, (3, 3, 3, 3), mode="reflect"), w_r))), (1, 1, 1, 1))
+    assert (outh.float().permute(0, 3, 1, 2) - refh).abs().max().item() < tol
+
+
 # ------------------------------------------------------------------ InstanceNorm / CBAM / residual kernels
 def _fake_partials(y):
     """Build [B, tiles, 3, C] partials from an NHWC tensor exactly as the conv epilogue would (128-pixel tiles)."""
