@@ -224,8 +224,9 @@ class _GeneratorEngine:
 
 
 class Discriminator(nn.Module):
-    """reference modules/model.py:118-131 (PatchGAN).  Parameter tree only in this round: the forward/backward
-    kernels belong to the training-step rows that follow the inference path."""
+    """reference modules/model.py:118-131 (PatchGAN).  ``forward(img[B,1,H,W] fp32 cuda) -> [B,1,H/16,W/16] fp32``;
+    H and W multiples of 256.  Inference / validation forward only in this round (reference
+    modules/trainer.py:243 evaluates it under no_grad); the backward belongs to the training-step rows."""
 
     def __init__(self, input_channels=1):
         super().__init__()
@@ -238,9 +239,65 @@ class Discriminator(nn.Module):
             ch_in = ch_out
         layers += [nn.ZeroPad2d((1, 0, 1, 0)), nn.Conv2d(512, 1, 4, padding=1)]
         self.model = nn.Sequential(*layers)
+        self._input_channels = int(input_channels)
+        self._engines = {}
 
     def forward(self, img):
-        raise NotImplementedError(_NO_TRAIN_MSG.format("Discriminator"))
+        if torch.is_grad_enabled() and (img.requires_grad or any(p.requires_grad for p in self.parameters())):
+            raise NotImplementedError(_NO_TRAIN_MSG.format("Discriminator"))
+        if self._input_channels != 1:
+            raise NotImplementedError("ducosy_gan_b200.Discriminator supports input_channels == 1 (what the reference trains)")
+        if not img.is_cuda:
+            raise RuntimeError("ducosy_gan_b200.Discriminator needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
+        dev = img.device
+        key = (dev.index if dev.index is not None else torch.cuda.current_device(), default_operand_dtype())
+        eng = self._engines.get(key)
+        if eng is None:
+            eng = self._engines[key] = _DiscriminatorEngine(key[1], torch.device("cuda", key[0]))
+        eng.sync_weights([p for _, p in self.named_parameters()])
+        return eng.forward(img)
+
+
+class _DiscriminatorEngine:
+    """Per-device packed weights + workspace of a Discriminator."""
+
+    def __init__(self, dtype_code, device):
+        self.device, self.dtype_code, self.lib = device, dtype_code, _lib.load()
+        with torch.cuda.device(device):
+            self.packed = torch.empty(self.lib.ducosy_discriminator_packed_bytes() + 256, dtype=torch.uint8, device=device)
+        self._versions, self._ws = None, {}
+
+    def _packed_ptr(self):
+        return (self.packed.data_ptr() + 255) // 256 * 256
+
+    def sync_weights(self, params):
+        sig = tuple((p.data_ptr(), p._version) for p in params)
+        if sig == self._versions:
+            return
+        keep = [p.detach().to(device=self.device, dtype=torch.float32).contiguous() for p in params]
+        arr = (C.c_void_p * len(keep))(*[t.data_ptr() for t in keep])
+        with torch.cuda.device(self.device):
+            _lib.call("ducosy_discriminator_pack", arr, len(keep), C.c_void_p(self._packed_ptr()), self.dtype_code,
+                      _lib.stream_ptr())
+        self._keepalive, self._versions = keep, sig
+
+    def forward(self, img):
+        if img.dim() != 4 or img.shape[1] != 1:
+            raise RuntimeError(f"expected input [B,1,H,W], got {tuple(img.shape)}")
+        img = img.to(dtype=torch.float32).contiguous()
+        B, _, H, W = img.shape
+        with torch.cuda.device(self.device):
+            ws = self._ws.get((B, H, W))
+            if ws is None:
+                need = self.lib.ducosy_discriminator_workspace_bytes(B, H, W)
+                if need == 0:
+                    raise _lib.DucosyError(f"unsupported discriminator input shape {tuple(img.shape)}: H, W multiples of 256")
+                self._ws.clear()
+                ws = self._ws[(B, H, W)] = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            out = torch.empty((B, 1, H // 16, W // 16), dtype=torch.float32, device=self.device)
+            _lib.call("ducosy_discriminator_forward", C.c_void_p(self._packed_ptr()), _lib.ptr(img), _lib.ptr(out), B, H, W,
+                      C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024), ws.numel() - 1024, self.dtype_code, _lib.stream_ptr())
+        return out
 
 
 def weights_init_normal(m):

@@ -175,6 +175,17 @@ int ducosy_generator_forward_hu(const ducosy_gen_config* cfg, const void* packed
 /* Number of kernels one forward launches (for bench accounting). */
 int ducosy_generator_num_launches(const ducosy_gen_config* cfg);
 
+/* ---------------------------------------------------------------- PatchGAN discriminator forward (modules/model.py:118-131) */
+
+size_t ducosy_discriminator_packed_bytes(void);
+size_t ducosy_discriminator_workspace_bytes(int B, int H, int W);
+/* params_host: host array of the 10 DEVICE fp32 tensors model.{0,2,5,8,12}.{weight,bias} in state_dict order. */
+int ducosy_discriminator_pack(const float* const* params_host, int num_params, void* packed, int dtype,
+                              ducosy_stream_t stream);
+/* Discriminator.forward: x fp32 [B][1][H][W] (H, W multiples of 256) -> out fp32 [B][1][H/16][W/16]. */
+int ducosy_discriminator_forward(const void* packed, const float* x, float* out, int B, int H, int W, void* workspace,
+                                 size_t workspace_bytes, int dtype, ducosy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

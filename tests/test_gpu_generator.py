@@ -105,3 +105,23 @@ def test_load_state_dict_invalidates_packed_weights():
         G.load_state_dict(orc.make_state_dict(shapes, 2))
         y2 = G(x)
     assert not torch.equal(y1, y2)
+
+
+@pytest.mark.parametrize("B,H,W", [(2, 256, 256), (1, 512, 512), (1, 256, 512)])
+def test_discriminator_forward_matches_oracle(B, H, W):
+    from ducosy_gan_b200.modules.model import Discriminator
+    sd = orc.make_state_dict(orc.discriminator_param_shapes(1), 21)
+    D = Discriminator(1)
+    D.load_state_dict(sd, strict=True)
+    D = D.cuda().eval()
+    x = _x(31, (B, 1, H, W))
+    with torch.no_grad():
+        y = D(x.cuda()).cpu()
+        ref = orc.discriminator_forward(sd, x)
+    assert y.shape == ref.shape == (B, 1, H // 16, W // 16)
+    err = (y - ref).abs().max().item()
+    print(f"disc {B}x{H}x{W}: max abs err {err:.3e} (ref abs max {ref.abs().max().item():.3f})")
+    assert err < 1.5e-2 * max(1.0, ref.abs().max().item())
+    # MSE-GAN validation loss (reference modules/trainer.py:243,347) from the patch map
+    mse = ((y - 1) ** 2).mean().item()
+    assert abs(mse - orc.mse_gan_loss(ref, True).item()) < 2e-2
