@@ -50,6 +50,7 @@ SIGNATURES = {
     "ducosy_residual_apply_pad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_out_weight": (_i, [_p, _p, _i, _p]),
     "ducosy_out_conv7x7_tanh": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_out_conv7x7_tanh_fused": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ducosy_generator_num_params": (_i, [C.POINTER(GenConfig)]),
     "ducosy_generator_packed_bytes": (_sz, [C.POINTER(GenConfig)]),
     "ducosy_generator_workspace_bytes": (_sz, [C.POINTER(GenConfig), _i, _i, _i]),

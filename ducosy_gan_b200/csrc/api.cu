@@ -267,9 +267,9 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   // ---- up 2: nearest x2 + 3x3 p1 128 -> 64, IN, ReLU
   DUCOSY_TRY(ducosy_upconv2x_merged_nhwc(P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt, st));
   DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(1, H2, W2), H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
-  DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p_out), B, H, W, 64, 3, DUCOSY_PAD_REFLECT, DUCOSY_ACT_RELU, dt, st));
-  // ---- output: reflect-pad 3 + 7x7 conv 64 -> 1 + tanh   modules/model.py:112
-  return ducosy_out_conv7x7_tanh(P(w.p_out), pk + L.outw, reinterpret_cast<const float*>(pk + L.outb), out, B, H, W, dt, st);
+  // ---- output: IN apply + ReLU + reflect-pad 3 folded into the loader of the 7x7 conv 64 -> 1 + tanh   modules/model.py:110-112
+  return ducosy_out_conv7x7_tanh_fused(P(w.y0), scale, shift, pk + L.outw, reinterpret_cast<const float*>(pk + L.outb), out, B,
+                                       H, W, dt, st);
 }
 
 }  // namespace
@@ -355,7 +355,7 @@ extern "C" size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg,
 }
 extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
-  return 17 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 3 : 0));
+  return 16 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 3 : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,

@@ -41,10 +41,20 @@ __global__ void pack_out_weight_kernel(const float* __restrict__ w, T* __restric
   }
 }
 
-template <typename T>
+__device__ __forceinline__ int reflect_px(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+// kFused == false: `in` is the reflect-padded, already normalised map [B][H+6][W+6][64].
+// kFused == true : `in` is the RAW conv output [B][H][W][64]; InstanceNorm apply + ReLU (scale/shift [B][64]) and the
+//                  reflection padding are done on the fly while loading the A fragments (saves a full read+write pass).
+template <typename T, bool kFused>
 __global__ void __launch_bounds__(kOutThreads)
-out_conv7x7_tanh_kernel(const T* __restrict__ in_pad, const T* __restrict__ wp, const float* __restrict__ bias,
-                        float* __restrict__ out, int B, int H, int W) {
+out_conv7x7_tanh_kernel(const T* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
+                        const T* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ out, int B, int H,
+                        int W) {
   __shared__ float P[kRowsOut][kPos][9];  // 9-float rows: the diagonal reads below are bank-conflict free
   const int tiles_x = W / kColsOut, tiles_y = H / kRowsOut;
   const int tx = blockIdx.x % tiles_x;
@@ -69,17 +79,45 @@ out_conv7x7_tanh_kernel(const T* __restrict__ in_pad, const T* __restrict__ wp, 
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
   const int xp0 = tx * kColsOut + 16 * warp + g;
-  const int xpA = min(xp0, Wp - 1), xpB = min(xp0 + 8, Wp - 1);  // columns past the row end feed unused outputs
-  const T* base = in_pad + (size_t(b) * Hp + size_t(ty) * kRowsOut) * Wp * 64 + 8 * t;
+  int xpA = min(xp0, Wp - 1), xpB = min(xp0 + 8, Wp - 1);  // columns past the row end feed unused outputs
+  float sc[2][8], sh[2][8];
+  if (kFused) {
+    xpA = reflect_px(xpA - 3, W);
+    xpB = reflect_px(xpB - 3, W);
+#pragma unroll
+    for (int cb = 0; cb < 2; ++cb)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        sc[cb][j] = scale[b * 64 + cb * 32 + 8 * t + j];
+        sh[cb][j] = shift[b * 64 + cb * 32 + 8 * t + j];
+      }
+  }
+  const T* base = kFused ? in + size_t(b) * H * W * 64 + 8 * t
+                         : in + (size_t(b) * Hp + size_t(ty) * kRowsOut) * Wp * 64 + 8 * t;
+  const int rowlen = kFused ? W : Wp;
 
 #pragma unroll
   for (int i = 0; i < kRowsOut + 6; ++i) {
-    const T* rowp = base + size_t(i) * Wp * 64;
+    const T* rowp = base + size_t(kFused ? reflect_px(ty * kRowsOut + i - 3, H) : i) * rowlen * 64;
     uint4 A[2][2];
 #pragma unroll
     for (int cb = 0; cb < 2; ++cb) {
       A[cb][0] = *reinterpret_cast<const uint4*>(rowp + size_t(xpA) * 64 + cb * 32);
       A[cb][1] = *reinterpret_cast<const uint4*>(rowp + size_t(xpB) * 64 + cb * 32);
+      if (kFused) {  // relu(y*scale + shift) in fp32, rounded back to T exactly like the stand-alone apply kernel
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t w4[4] = {A[cb][h].x, A[cb][h].y, A[cb][h].z, A[cb][h].w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            float2 f = Cvt<T>::unpack2(w4[j]);
+            f.x = fmaxf(fmaf(f.x, sc[cb][2 * j], sh[cb][2 * j]), 0.f);
+            f.y = fmaxf(fmaf(f.y, sc[cb][2 * j + 1], sh[cb][2 * j + 1]), 0.f);
+            w4[j] = Cvt<T>::pack2(f.x, f.y);
+          }
+          A[cb][h] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+        }
+      }
     }
 #pragma unroll
     for (int yo = 0; yo < kRowsOut; ++yo) {
@@ -130,7 +168,23 @@ extern "C" int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed,
   DUCOSY_CHECK((reinterpret_cast<uintptr_t>(in_pad) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
                DUCOSY_ERR_ALIGN, "out_conv7x7_tanh: 16-byte alignment");
   const int grid = B * (H / kRowsOut) * (W / kColsOut);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(in_pad), static_cast<const T*>(w_packed), bias, out, B, H, W)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T, false><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(in_pad), nullptr, nullptr, static_cast<const T*>(w_packed), bias,
+                                      out, B, H, W)));
   return check_launch("out_conv7x7_tanh_kernel");
+}
+
+extern "C" int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* scale, const float* shift, const void* w_packed,
+                                             const float* bias, float* out, int B, int H, int W, int dtype,
+                                             ducosy_stream_t stream) {
+  DUCOSY_CHECK(y_raw && scale && shift && w_packed && bias && out && B > 0, DUCOSY_ERR_ARG, "out_conv7x7_tanh_fused: bad argument");
+  DUCOSY_CHECK(H % kRowsOut == 0 && W % kColsOut == 0 && H >= 4, DUCOSY_ERR_SHAPE,
+               "out_conv7x7_tanh_fused: H must be a multiple of 8 and W of 128 (got %dx%d)", H, W);
+  DUCOSY_CHECK((reinterpret_cast<uintptr_t>(y_raw) & 15) == 0 && (reinterpret_cast<uintptr_t>(w_packed) & 15) == 0,
+               DUCOSY_ERR_ALIGN, "out_conv7x7_tanh_fused: 16-byte alignment");
+  const int grid = B * (H / kRowsOut) * (W / kColsOut);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T, true><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y_raw), scale, shift, static_cast<const T*>(w_packed), bias, out,
+                                      B, H, W)));
+  return check_launch("out_conv7x7_tanh_kernel(fused)");
 }

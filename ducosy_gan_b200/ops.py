@@ -243,3 +243,15 @@ def stem_fused(w_packed, x=None, px=None, window=None):
         scale, shift = in_finalize(partials, H * W)
         call("ducosy_stem_fused", ptr(xw), ptr(w_packed), None, ptr(scale), ptr(shift), ptr(out), B, H, W, 1, dtype_code(dt), stream_ptr())
     return out
+
+
+def out_conv7x7_tanh_fused(y_raw, scale, shift, w_packed, bias):
+    """IN apply + ReLU + reflect pad 3 + conv7x7(64->1) + tanh from the raw NHWC map [B,H,W,64]."""
+    B, H, W, Cn = y_raw.shape
+    assert Cn == 64
+    bias = bias.detach().to(torch.float32).contiguous()
+    with _dev(y_raw):
+        out = torch.empty((B, 1, H, W), dtype=torch.float32, device=y_raw.device)
+        call("ducosy_out_conv7x7_tanh_fused", ptr(y_raw), ptr(scale), ptr(shift), ptr(w_packed), ptr(bias), ptr(out), B, H, W,
+             dtype_code(y_raw.dtype), stream_ptr())
+    return out

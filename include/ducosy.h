@@ -148,6 +148,10 @@ int ducosy_residual_apply_pad(const void* y, const float* scale, const float* sh
 int ducosy_pack_out_weight(const float* w_oihw, void* packed, int dtype, ducosy_stream_t stream);
 int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed, const float* bias, float* out, int B, int H, int W,
                             int dtype, ducosy_stream_t stream);
+/* Same from the RAW previous conv output y_raw [B][H][W][64]: InstanceNorm apply (scale/shift [B][64]) + ReLU + the
+ * reflection padding are folded into the loader (modules/model.py:110-112 in one kernel). */
+int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* scale, const float* shift, const void* w_packed,
+                                  const float* bias, float* out, int B, int H, int W, int dtype, ducosy_stream_t stream);
 
 /* ---------------------------------------------------------------- whole-generator entry points */
 

@@ -267,3 +267,16 @@ def test_out_conv7x7_tanh(ops, dtype):
     w_r = wp.float().view(7, 8, 64)[:, :7, :].permute(2, 0, 1).reshape(1, 64, 7, 7)
     ref = torch.tanh(F.conv2d(F.pad(x.float().cuda(), (3, 3, 3, 3), mode="reflect"), w_r, bias.cuda()))
     assert (out - ref).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("dtype", DTYPES)
+def test_out_conv_fused_equals_apply_then_conv(ops, dtype):
+    B, H, W = 2, 16, 128
+    y = (_rand((B, H, W, 64), 71) * 2 + 0.5).to(dtype).cuda()
+    scale, shift = ops.in_finalize(_fake_partials(y), H * W)
+    w = _rand((1, 64, 7, 7), 72, 0.02)
+    bias = torch.tensor([-0.03]).cuda()
+    wp = ops.pack_out_weight(w.cuda(), dtype)
+    ref = ops.out_conv7x7_tanh(ops.in_apply_pad(y, scale, shift, 3, ops.PAD_REFLECT, ops.ACT_RELU), wp, bias)
+    got = ops.out_conv7x7_tanh_fused(y, scale, shift, wp, bias)
+    assert torch.equal(got, ref)
