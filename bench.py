@@ -162,7 +162,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch-slices", type=int, default=int(os.environ.get("DUCOSY_BATCH_SLICES", "15")))
+    ap.add_argument("--batch-slices", type=int, default=int(os.environ.get("DUCOSY_BATCH_SLICES", "30")))
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
