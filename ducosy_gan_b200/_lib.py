@@ -58,6 +58,8 @@ SIGNATURES = {
     "ducosy_generator_forward": (_i, [C.POINTER(GenConfig), _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_generator_forward_hu": (_i, [C.POINTER(GenConfig), _p, _p, _f, _f, _f, _f, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_generator_num_launches": (_i, [C.POINTER(GenConfig)]),
+    "ducosy_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
+    "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_discriminator_packed_bytes": (_sz, []),
     "ducosy_discriminator_workspace_bytes": (_sz, [_i, _i, _i]),
     "ducosy_discriminator_pack": (_i, [C.POINTER(_p), _i, _p, _i, _p]),

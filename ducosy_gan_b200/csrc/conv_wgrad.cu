@@ -1,0 +1,290 @@
+// Weight gradient of the NHWC convolutions on tcgen05 (building block of the training-step rows):
+//   dW[o][tap][c] = sum_{pixels p} dY[p][o] * Xpad[p + offset(tap)][c]
+// Per tap this is a GEMM with M = Cout, N = Cin and K = pixels.  Both operands are "MN-major" for the tensor core
+// (the M / N index is the contiguous NHWC channel, K = pixel strides by the channel count): the TMA boxes
+// (64 channels x 64 pixels, 128-byte swizzle) land exactly in the canonical MN-major UMMA layout -- 128-byte rows of
+// 64 channels per pixel, 8-pixel swizzle atoms 1 KiB apart (SBO), 64-channel slabs 8 KiB apart (LBO).
+// Work unit = (tap, 128-row block of Cout, K split); each CTA accumulates one unit in TMEM (fp32) and writes its
+// partial tile; a second kernel reduces the K splits in fixed order (deterministic).
+#include <type_traits>
+
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace ducosy {
+namespace {
+
+constexpr int kWgThreads = 256;
+constexpr int kKChunk = 64;                 // pixels per pipeline stage
+constexpr int kSlab = kKChunk * 128;        // bytes: 64 pixel rows x 64 channels x 16 bit
+constexpr int kWgStages = 4;
+
+struct WgradArgs {
+  int num_taps, B, TY, TX, R, Wt, log2Wt;   // pixel chunks: R rows x Wt cols of the dY grid (R*Wt == 64)
+  int rows_per_sample;                      // outermost TMA dim units of the input map per sample
+  int Cin, Cout, m_blocks, n_slabs;         // n_slabs = Cin / 64 (<= 4)
+  int splits, chunks_per_split;
+  int8_t tap_xp[kMaxTaps], tap_dx[kMaxTaps], tap_yp[kMaxTaps], tap_dy[kMaxTaps];
+  float* partial;                           // [splits][taps][Cout][Cin] fp32
+};
+
+// MN-major, 128-byte swizzle operand descriptor: LBO = distance between 64-element slabs, SBO = 8-row atom pitch.
+__device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint32_t lbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr >> 4) & 0x3FFF);
+  d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(2) << 61;
+  return d;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(kWgThreads, 1)
+conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs a) {
+  constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
+  extern __shared__ uint8_t wg_raw[];
+  const uint32_t raw_addr = smem_u32(wg_raw);
+  uint8_t* smem = wg_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
+  const int stage_bytes = (2 + a.n_slabs) * kSlab;          // A: 2 slabs (128 output channels), B: n_slabs
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * 6 * kSlab);
+  uint64_t* empty = full + kWgStages;
+  uint64_t* done = empty + kWgStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // unit decode: blockIdx.x = ((split * taps + tap) * m_blocks + mb)
+  const int mb = blockIdx.x % a.m_blocks;
+  const int tap = (blockIdx.x / a.m_blocks) % a.num_taps;
+  const int split = blockIdx.x / (a.m_blocks * a.num_taps);
+  const int chunks_total = a.B * a.TY * a.TX;
+  const int c_begin = split * a.chunks_per_split;
+  const int c_end = min(c_begin + a.chunks_per_split, chunks_total);
+  const int N = a.n_slabs * 64;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDY);
+    tma_prefetch_desc(&tmX);
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < kWgStages; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    mbar_init(done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, 256);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int ch = c_begin; ch < c_end; ++ch) {
+        const int tx = ch % a.TX;
+        int r = ch / a.TX;
+        const int ty = r % a.TY;
+        const int b = r / a.TY;
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = smem + size_t(s) * stage_bytes;
+        mbar_arrive_expect_tx(&full[s], stage_bytes);
+        // A: dY chunk, two 64-channel slabs of this 128-row block of Cout; dY is unpadded [B][Ho][Wo][Cout]
+        for (int h = 0; h < 2; ++h)
+          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mb * 128 + h * 64, 0, tx * a.Wt, 0, (b * a.TY + ty) * a.R);
+        // B: the input pixels this tap multiplies, all Cin channels
+        for (int sl = 0; sl < a.n_slabs; ++sl)
+          tma_load_5d(st + (2 + sl) * kSlab, &tmX, &full[s], sl * 64, a.tap_xp[tap], tx * a.Wt + a.tap_dx[tap],
+                      a.tap_yp[tap], b * a.rows_per_sample + ty * a.R + a.tap_dy[tap]);
+        if (++s == kWgStages) {
+          s = 0;
+          ph ^= 1;
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // instruction descriptor: fp32 accumulate, A and B both MN-major (bits 15 / 16), M = 128, N = Cin
+    const uint32_t idesc = umma_idesc_f16(kFmt, 128, N) | (1u << 15) | (1u << 16);
+    int s = 0;
+    uint32_t ph = 0;
+    for (int ch = c_begin; ch < c_end; ++ch) {
+      mbar_wait(&full[s], ph);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + size_t(s) * stage_bytes);
+#pragma unroll
+        for (int j = 0; j < kKChunk / 16; ++j) {  // 16 pixels = two 8-row swizzle atoms = 2 KiB per K step
+          const uint64_t da = umma_desc_mn_sw128(sa + j * 2048, kSlab);
+          const uint64_t db = umma_desc_mn_sw128(sa + 2 * kSlab + j * 2048, kSlab);
+          umma_f16(tmem_base, da, db, idesc, (ch > c_begin || j > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);
+        if (ch == c_end - 1) umma_commit(done);
+      }
+      __syncwarp();
+      if (++s == kWgStages) {
+        s = 0;
+        ph ^= 1;
+      }
+    }
+  } else if (warp >= 4) {
+    const int q = warp & 3;
+    const int o = mb * 128 + q * 32 + lane;
+    mbar_wait(done, 0);
+    tc_fence_after();
+    float* dst = a.partial + ((size_t(split) * a.num_taps + tap) * a.Cout + o) * a.Cin;
+    for (int chn = 0; chn < N / 32; ++chn) {
+      uint32_t v[32];
+      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chn * 32), v);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        reinterpret_cast<uint4*>(dst + chn * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 256);
+  }
+}
+
+// dw[o][tap*Cin + c] = sum over splits, fixed order
+__global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
+                                    int Cout, int Cin) {
+  const long long per_split = (long long)taps * Cout * Cin;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_split; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Cin);
+    long long r = i / Cin;
+    const int o = int(r % Cout);
+    const int tap = int(r / Cout);
+    float acc = 0.f;
+    for (int s = 0; s < splits; ++s) acc += partial[s * per_split + i];
+    dw[((long long)o * taps + tap) * Cin + c] = acc;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn wg_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn == nullptr) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  }
+  return fn;
+}
+
+int encode_nhwc_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int B, int Hp, int Wp, int C, int stride,
+                    int Wt, int R) {
+  EncodeTiledFn encode = wg_encode_fn();
+  DUCOSY_CHECK(encode != nullptr, DUCOSY_ERR_CUDA, "conv_wgrad: cuTensorMapEncodeTiled is not available");
+  const cuuint64_t C2 = cuuint64_t(C) * 2, W = cuuint64_t(Wp), H = cuuint64_t(Hp);
+  cuuint64_t gdim[5], gstr[4];
+  if (stride == 1) {
+    gdim[0] = C; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(B) * H;
+    gstr[0] = C2; gstr[1] = C2; gstr[2] = W * C2; gstr[3] = W * C2;
+  } else {
+    gdim[0] = C; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(B) * H / 2;
+    gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
+  }
+  const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
+  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+  CUresult r = encode(tm, dt, 5, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_wgrad: cuTensorMapEncodeTiled failed with %d", int(r));
+  return 0;
+}
+
+}  // namespace
+}  // namespace ducosy
+
+using namespace ducosy;
+
+extern "C" size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw) {
+  if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
+  const int chunks = B * Ho * Wo / kKChunk;
+  const int units = kh * kw * ((Cout + 127) / 128);
+  int splits = (2 * 148 + units - 1) / units;
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  return size_t(splits) * kh * kw * Cout * Cin * 4;
+}
+
+// x_pad: the padded NHWC input the forward conv read ([B][Hp][Wp][Cin]); dy: NHWC output gradient [B][Ho][Wo][Cout],
+// 16-bit both; dw: fp32 [Cout][kh*kw*Cin] in the packed forward layout (k = (r*kw+s)*Cin + c).
+extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float* dw, int B, int Hp, int Wp, int Cin,
+                                        int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes,
+                                        int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(x_pad && dy && dw && workspace && B > 0, DUCOSY_ERR_ARG, "conv2d_wgrad: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_wgrad: bad dtype");
+  DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
+               "conv2d_wgrad: kernel %dx%d stride %d unsupported", kh, kw, stride);
+  DUCOSY_CHECK(Cin % 64 == 0 && Cin <= 256 && Cout % 128 == 0, DUCOSY_ERR_SHAPE,
+               "conv2d_wgrad: needs Cin in {64,128,192,256} and Cout a multiple of 128 (got %d -> %d)", Cin, Cout);
+  DUCOSY_CHECK(stride == 1 || (Hp % 2 == 0 && Wp % 2 == 0), DUCOSY_ERR_SHAPE, "conv2d_wgrad: stride 2 needs even padded extents");
+  DUCOSY_TRY(ducosy_check_device());
+  const int Ho = (Hp - kh) / stride + 1, Wo = (Wp - kw) / stride + 1;
+  const int Wt = Wo < kKChunk ? Wo : kKChunk;
+  DUCOSY_CHECK(Wt >= 8 && (Wt & (Wt - 1)) == 0 && Wo % Wt == 0 && Ho % (kKChunk / Wt) == 0, DUCOSY_ERR_SHAPE,
+               "conv2d_wgrad: output grid %dx%d unsupported", Ho, Wo);
+  const int R = kKChunk / Wt;
+  WgradArgs a{};
+  a.num_taps = kh * kw;
+  a.B = B; a.R = R; a.Wt = Wt;
+  a.TY = Ho / R; a.TX = Wo / Wt;
+  a.rows_per_sample = stride == 1 ? Hp : Hp / 2;
+  a.Cin = Cin; a.Cout = Cout; a.m_blocks = Cout / 128; a.n_slabs = Cin / 64;
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s) {
+      const int t = r * kw + s;
+      if (stride == 1) { a.tap_xp[t] = 0; a.tap_dx[t] = int8_t(s); a.tap_yp[t] = 0; a.tap_dy[t] = int8_t(r); }
+      else { a.tap_xp[t] = int8_t(s & 1); a.tap_dx[t] = int8_t(s >> 1); a.tap_yp[t] = int8_t(r & 1); a.tap_dy[t] = int8_t(r >> 1); }
+    }
+  const int chunks = B * a.TY * a.TX;
+  const int units = a.num_taps * a.m_blocks;
+  int splits = (2 * 148 + units - 1) / units;
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  a.chunks_per_split = (chunks + splits - 1) / splits;
+  splits = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;   // no empty split
+  a.splits = splits;
+  const size_t need = size_t(splits) * a.num_taps * Cout * Cin * 4;
+  DUCOSY_CHECK(workspace_bytes >= need, DUCOSY_ERR_WORKSPACE, "conv2d_wgrad: workspace %zu < required %zu bytes", workspace_bytes, need);
+  a.partial = static_cast<float*>(workspace);
+
+  const CUtensorMapDataType dt = dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmDY, tmX;
+  DUCOSY_TRY(encode_nhwc_map(&tmDY, dt, dy, B, Ho, Wo, Cout, 1, Wt, R));
+  DUCOSY_TRY(encode_nhwc_map(&tmX, dt, x_pad, B, Hp, Wp, Cin, stride, Wt, R));
+
+  const size_t smem = 1024 + size_t(kWgStages) * 6 * kSlab + 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = splits * units;
+  if (dtype == DUCOSY_F16) {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; }
+    conv_wgrad_kernel<__half><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);
+  } else {
+    static bool cfg = false;
+    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; }
+    conv_wgrad_kernel<__nv_bfloat16><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);
+  }
+  DUCOSY_TRY(check_launch("conv_wgrad_kernel"));
+  const long long per_split = (long long)a.num_taps * Cout * Cin;
+  long long blocks = (per_split + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dw, splits, a.num_taps, Cout, Cin);
+  return check_launch("wgrad_reduce_kernel");
+}

@@ -255,3 +255,18 @@ def out_conv7x7_tanh_fused(y_raw, scale, shift, w_packed, bias):
         call("ducosy_out_conv7x7_tanh_fused", ptr(y_raw), ptr(scale), ptr(shift), ptr(w_packed), ptr(bias), ptr(out), B, H, W,
              dtype_code(y_raw.dtype), stream_ptr())
     return out
+
+
+def conv2d_wgrad_nhwc(x_pad, dy, kh, kw, stride):
+    """Weight gradient dW fp32 [Cout, kh*kw*Cin] (packed forward layout) from the padded input and the output gradient."""
+    B, Hp, Wp, Cin = x_pad.shape
+    _, Ho, Wo, Cout = dy.shape
+    assert x_pad.is_contiguous() and dy.is_contiguous() and x_pad.dtype == dy.dtype
+    lib = _lib.load()
+    with _dev(x_pad):
+        need = lib.ducosy_conv2d_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, kh, kw)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=x_pad.device)
+        dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=x_pad.device)
+        call("ducosy_conv2d_wgrad_nhwc", ptr(x_pad), ptr(dy), ptr(dw), B, Hp, Wp, Cin, Cout, kh, kw, stride, ptr(ws),
+             ws.numel(), dtype_code(x_pad.dtype), stream_ptr())
+    return dw

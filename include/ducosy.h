@@ -179,6 +179,17 @@ int ducosy_generator_forward_hu(const ducosy_gen_config* cfg, const void* packed
 /* Number of kernels one forward launches (for bench accounting). */
 int ducosy_generator_num_launches(const ducosy_gen_config* cfg);
 
+/* ---------------------------------------------------------------- backward building blocks (training-step rows, in progress)
+ *
+ * Weight gradient of the NHWC convolutions on the tensor cores: dW[o][(r*kw+s)*Cin + c] = sum_pixels dy[p][o] *
+ * x_pad[p*stride + (r,s)][c] (what autograd computes for modules/trainer.py:513,519,524).  x_pad is the padded input
+ * the forward conv read, dy the output gradient [B][Ho][Wo][Cout], both 16-bit NHWC; dw fp32 in the packed forward
+ * layout.  Cin in {64,128,192,256}, Cout % 128 == 0.  Deterministic (fixed-order reduction of the K splits). */
+size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
+int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float* dw, int B, int Hp, int Wp, int Cin, int Cout, int kh,
+                             int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
+                             ducosy_stream_t stream);
+
 /* ---------------------------------------------------------------- PatchGAN discriminator forward (modules/model.py:118-131) */
 
 size_t ducosy_discriminator_packed_bytes(void);

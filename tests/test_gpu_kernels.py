@@ -280,3 +280,22 @@ def test_out_conv_fused_equals_apply_then_conv(ops, dtype):
     ref = ops.out_conv7x7_tanh(ops.in_apply_pad(y, scale, shift, 3, ops.PAD_REFLECT, ops.ACT_RELU), wp, bias)
     got = ops.out_conv7x7_tanh_fused(y, scale, shift, wp, bias)
     assert torch.equal(got, ref)
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 256, 256, 3, 1), (1, 64, 64, 64, 128, 3, 2), (2, 32, 64, 128, 256, 4, 2),
+                                  (1, 16, 128, 192, 128, 1, 1)])
+def test_conv2d_wgrad_matches_autograd(ops, case):
+    B, H, W, Cin, Cout, k, stride = case
+    dtype = torch.float16
+    pad = 0 if k == 1 else 1
+    x = _rand((B, Cin, H, W), 81).to(dtype)
+    Ho, Wo = (H + 2 * pad - k) // stride + 1, (W + 2 * pad - k) // stride + 1
+    dy = _rand((B, Cout, Ho, Wo), 82).to(dtype)
+    xp = F.pad(x.float(), (pad,) * 4).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dyn = dy.float().permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dw = ops.conv2d_wgrad_nhwc(xp, dyn, k, k, stride)                      # [Cout][k*k*Cin]
+    w0 = torch.zeros((Cout, Cin, k, k), device="cuda", requires_grad=True)
+    F.conv2d(x.float().cuda(), w0, stride=stride, padding=pad).backward(dy.float().cuda())
+    ref = w0.grad.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)            # packed layout: (r*kw+s)*Cin + c
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
