@@ -59,7 +59,18 @@ SIGNATURES = {
     "ducosy_generator_forward_hu": (_i, [C.POINTER(GenConfig), _p, _p, _f, _f, _f, _f, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_generator_num_launches": (_i, [C.POINTER(GenConfig)]),
     "ducosy_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
-    "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
+    "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
+    "ducosy_in_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
+    "ducosy_in_backward_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_dgrad_s2_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_conv4x4s2_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_grad_scale": (_i, [_p, _ll, _p, _p]),
+    "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
+    "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_disc_first_backward_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_disc_first_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_discriminator_backward_workspace_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_discriminator_backward": (_i, [_p, _p, _p, _p, C.POINTER(_p), _p, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_discriminator_packed_bytes": (_sz, []),
     "ducosy_discriminator_workspace_bytes": (_sz, [_i, _i, _i]),
     "ducosy_discriminator_pack": (_i, [C.POINTER(_p), _i, _p, _i, _p]),

@@ -22,6 +22,7 @@ constexpr int kWgStages = 4;
 struct WgradArgs {
   int num_taps, B, TY, TX, R, Wt, log2Wt;   // pixel chunks: R rows x Wt cols of the dY grid (R*Wt == 64)
   int rows_per_sample;                      // outermost TMA dim units of the input map per sample
+  int dy_pad, dy_rows_per_sample;           // dY may live inside a zero-padded buffer (border width dy_pad)
   int Cin, Cout, m_blocks, n_slabs;         // n_slabs = Cin / 64 (<= 4)
   int splits, chunks_per_split;
   int8_t tap_xp[kMaxTaps], tap_dx[kMaxTaps], tap_yp[kMaxTaps], tap_dy[kMaxTaps];
@@ -97,7 +98,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         // A: dY chunk, two 64-channel slabs of this 128-row block of Cout; dY is unpadded [B][Ho][Wo][Cout]
         for (int h = 0; h < 2; ++h)
-          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mb * 128 + h * 64, 0, tx * a.Wt, 0, (b * a.TY + ty) * a.R);
+          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mb * 128 + h * 64, 0, tx * a.Wt + a.dy_pad, 0,
+                      b * a.dy_rows_per_sample + ty * a.R + a.dy_pad);
         // B: the input pixels this tap multiplies, all Cin channels
         for (int sl = 0; sl < a.n_slabs; ++sl)
           tma_load_5d(st + (2 + sl) * kSlab, &tmX, &full[s], sl * 64, a.tap_xp[tap], tx * a.Wt + a.tap_dx[tap],
@@ -222,11 +224,11 @@ extern "C" size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int
   return size_t(splits) * kh * kw * Cout * Cin * 4;
 }
 
-// x_pad: the padded NHWC input the forward conv read ([B][Hp][Wp][Cin]); dy: NHWC output gradient [B][Ho][Wo][Cout],
-// 16-bit both; dw: fp32 [Cout][kh*kw*Cin] in the packed forward layout (k = (r*kw+s)*Cin + c).
-extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float* dw, int B, int Hp, int Wp, int Cin,
-                                        int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes,
-                                        int dtype, ducosy_stream_t stream) {
+// x_pad: the padded NHWC input the forward conv read ([B][Hp][Wp][Cin]); dy: NHWC output gradient
+// [B][Ho+2*dy_pad][Wo+2*dy_pad][Cout] (interior used), 16-bit both; dw: fp32 [Cout][kh*kw*Cin] in the packed forward layout (k = (r*kw+s)*Cin + c).
+extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp,
+                                        int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                                        size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(x_pad && dy && dw && workspace && B > 0, DUCOSY_ERR_ARG, "conv2d_wgrad: null pointer");
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_wgrad: bad dtype");
   DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
@@ -245,6 +247,8 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float
   a.B = B; a.R = R; a.Wt = Wt;
   a.TY = Ho / R; a.TX = Wo / Wt;
   a.rows_per_sample = stride == 1 ? Hp : Hp / 2;
+  a.dy_pad = dy_pad;
+  a.dy_rows_per_sample = Ho + 2 * dy_pad;
   a.Cin = Cin; a.Cout = Cout; a.m_blocks = Cout / 128; a.n_slabs = Cin / 64;
   for (int r = 0; r < kh; ++r)
     for (int s = 0; s < kw; ++s) {
@@ -266,7 +270,8 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float
 
   const CUtensorMapDataType dt = dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmDY, tmX;
-  DUCOSY_TRY(encode_nhwc_map(&tmDY, dt, dy, B, Ho, Wo, Cout, 1, Wt, R));
+  DUCOSY_CHECK(dy_pad >= 0 && dy_pad <= 4, DUCOSY_ERR_ARG, "conv2d_wgrad: dy_pad out of range");
+  DUCOSY_TRY(encode_nhwc_map(&tmDY, dt, dy, B, Ho + 2 * dy_pad, Wo + 2 * dy_pad, Cout, 1, Wt, R));
   DUCOSY_TRY(encode_nhwc_map(&tmX, dt, x_pad, B, Hp, Wp, Cin, stride, Wt, R));
 
   const size_t smem = 1024 + size_t(kWgStages) * 6 * kSlab + 256;

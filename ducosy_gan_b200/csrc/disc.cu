@@ -4,6 +4,8 @@
 // The three middle convolutions (K = 1024 / 2048 / 4096) run on the tcgen05 implicit-GEMM kernel (conv_gemm.cu); the
 // first layer (Cin = 1, 16 MACs per output) and the last (Cout = 1, a 8192-long dot product per patch) are
 // bandwidth-bound and get their own small kernels.  Conv biases in front of the non-affine InstanceNorm cancel.
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ducosy {
@@ -103,7 +105,7 @@ __global__ void pack_disc_last_weight_kernel(const float* __restrict__ w /*[1][5
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 struct DiscLayout {
-  size_t w1, b1, w2, w3, w4, w5, b5, total;
+  size_t w1, b1, w2, w3, w4, w5, b5, wd2, wd3, wd4, total;   // wd*: transposed packings for the input gradients
 };
 DiscLayout make_disc_layout() {
   DiscLayout L{};
@@ -116,11 +118,14 @@ DiscLayout make_disc_layout() {
   L.w4 = take(size_t(512) * 16 * 256 * 2);
   L.w5 = take(16 * 512 * 2);
   L.b5 = take(4);
+  L.wd2 = take(size_t(16) * 128 * 64 * 2);
+  L.wd3 = take(size_t(16) * 256 * 128 * 2);
+  L.wd4 = take(size_t(16) * 512 * 256 * 2);
   L.total = off;
   return L;
 }
 struct DiscWorkspace {
-  size_t p1, y2, p2, y3, p3, y4, p4, partials, scale, shift, total;
+  size_t p1, y2, p2, y3, p3, y4, p4, partials, scale[3], shift[3], total;   // nothing aliased: backward reads it all
 };
 DiscWorkspace make_disc_workspace(int B, int H, int W) {
   DiscWorkspace w{};
@@ -135,8 +140,10 @@ DiscWorkspace make_disc_workspace(int B, int H, int W) {
   w.y4 = take(size_t(B) * H4 * W4 * 512 * 2);
   w.p4 = take(size_t(B) * (H4 + 4) * (W4 + 4) * 512 * 2);
   w.partials = take(size_t(B) * (size_t(H2) * W2 / 128) * 3 * 128 * 4);
-  w.scale = take(size_t(B) * 512 * 4);
-  w.shift = take(size_t(B) * 512 * 4);
+  for (int l = 0; l < 3; ++l) {
+    w.scale[l] = take(size_t(B) * 512 * 4);
+    w.shift[l] = take(size_t(B) * 512 * 4);
+  }
   w.total = off;
   return w;
 }
@@ -172,6 +179,9 @@ extern "C" int ducosy_discriminator_pack(const float* const* params, int num_par
   DUCOSY_TRY(ducosy_pack_conv_weight(params[6], pk + L.w4, 512, 256, 4, 4, dtype, stream));
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_disc_last_weight_kernel<T><<<32, 256, 0, st>>>(params[8], reinterpret_cast<T*>(pk + L.w5))));
   cudaMemcpyAsync(pk + L.b5, params[9], 4, cudaMemcpyDeviceToDevice, st);
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[2], pk + L.wd2, 128, 64, dtype, stream));
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[4], pk + L.wd3, 256, 128, dtype, stream));
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[6], pk + L.wd4, 512, 256, dtype, stream));
   return check_launch("discriminator_pack");
 }
 
@@ -192,8 +202,6 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
   const uint8_t* pk = static_cast<const uint8_t*>(packed);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   float* partials = reinterpret_cast<float*>(base + w.partials);
-  float* scale = reinterpret_cast<float*>(base + w.scale);
-  float* shift = reinterpret_cast<float*>(base + w.shift);
   const int H1 = H / 2, W1 = W / 2;
   {
     const long long total = (long long)B * (H1 + 2) * (W1 + 2) * 8;
@@ -211,6 +219,8 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
   int Hi = H1, Wi = W1, Ci = 64;
   for (int l = 0; l < 3; ++l) {
     const int Ho = Hi / 2, Wo = Wi / 2, Co = Ci * 2;
+    float* scale = reinterpret_cast<float*>(base + w.scale[l]);
+    float* shift = reinterpret_cast<float*>(base + w.shift[l]);
     DUCOSY_TRY(ducosy_conv2d_nhwc(base + in_off[l], pk + w_off[l], base + y_off[l], partials, nullptr, DUCOSY_ACT_NONE, B,
                                   Hi + 2, Wi + 2, Ci, Co, 4, 4, 2, dtype, stream));
     DUCOSY_TRY(ducosy_in_finalize(partials, Ho * Wo / 128, Ho * Wo, scale, shift, nullptr, nullptr, nullptr, B, Co, stream));
@@ -228,4 +238,89 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
                                         reinterpret_cast<const float*>(pk + L.b5), out, B, Hi, Wi)));
   }
   return check_launch("disc_last_conv_kernel");
+}
+
+// ---------------------------------------------------------------- backward
+namespace ducosy {
+namespace {
+struct DiscBwdWorkspace {
+  size_t da[4], dyp[3], in_scratch, wg_ws, dwp, first_scratch, gs, total;   // da[l]: grad wrt the activation after layer l+1
+};
+DiscBwdWorkspace make_disc_bwd_workspace(int B, int H, int W) {
+  DiscBwdWorkspace w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) { const size_t o = off; off = align_up(off + bytes, 1024); return o; };
+  int Hl = H / 2, Wl = W / 2, Cl = 64;
+  size_t in_max = 0, wg_max = 0;
+  for (int l = 0; l < 4; ++l) {
+    w.da[l] = take(size_t(B) * Hl * Wl * Cl * 2);
+    if (l > 0) {
+      w.dyp[l - 1] = take(size_t(B) * (Hl + 2) * (Wl + 2) * Cl * 2);
+      in_max = std::max(in_max, ducosy_in_backward_scratch_bytes(B, Hl, Wl, Cl));
+      wg_max = std::max(wg_max, ducosy_conv2d_wgrad_workspace_bytes(B, Hl, Wl, Cl / 2, Cl, 4, 4));
+    }
+    Hl /= 2; Wl /= 2; Cl *= 2;
+  }
+  w.in_scratch = take(in_max);
+  w.wg_ws = take(wg_max);
+  w.dwp = take(size_t(512) * 16 * 256 * 4);
+  w.first_scratch = take(ducosy_disc_first_backward_scratch_bytes(B, H, W));
+  w.gs = take(16);
+  w.total = off;
+  return w;
+}
+}  // namespace
+}  // namespace ducosy
+
+extern "C" size_t ducosy_discriminator_backward_workspace_bytes(int B, int H, int W) {
+  return check_disc_shape(B, H, W) == 0 ? make_disc_bwd_workspace(B, H, W).total : 0;
+}
+
+// Backward of ducosy_discriminator_forward.  fwd_workspace must be the (untouched) workspace of that forward call.
+// grads_host: host array of 10 DEVICE fp32 buffers shaped like model.{0,2,5,8,12}.{weight,bias} (written, not accumulated);
+// dx: optional gradient w.r.t. the input image [B][1][H][W] (NULL to skip).
+extern "C" int ducosy_discriminator_backward(const void* packed, const float* x, const float* dout, const void* fwd_workspace,
+                                             float* const* grads_host, float* dx, int B, int H, int W, void* workspace,
+                                             size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(packed && x && dout && fwd_workspace && grads_host && workspace, DUCOSY_ERR_ARG, "discriminator_backward: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "discriminator_backward: bad dtype");
+  DUCOSY_TRY(check_disc_shape(B, H, W));
+  for (int i = 0; i < 10; ++i) DUCOSY_CHECK(grads_host[i] != nullptr, DUCOSY_ERR_ARG, "discriminator_backward: gradient buffer %d is null", i);
+  const DiscLayout L = make_disc_layout();
+  const DiscWorkspace fw = make_disc_workspace(B, H, W);
+  const DiscBwdWorkspace bw = make_disc_bwd_workspace(B, H, W);
+  DUCOSY_CHECK(workspace_bytes >= bw.total, DUCOSY_ERR_WORKSPACE, "discriminator_backward: workspace %zu < required %zu bytes",
+               workspace_bytes, bw.total);
+  const uint8_t* pk = static_cast<const uint8_t*>(packed);
+  const uint8_t* fb = static_cast<const uint8_t*>(fwd_workspace);
+  uint8_t* bb = static_cast<uint8_t*>(workspace);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int H4 = H / 16, W4 = W / 16;
+
+  // power-of-two scale that lifts the (tiny) loss gradient out of the fp16 subnormal range; undone in fp32 at the end
+  float* gs = reinterpret_cast<float*>(bb + bw.gs);
+  DUCOSY_TRY(ducosy_grad_scale(dout, (long long)B * H4 * W4, gs, stream));
+  // last layer: grad wrt a4 (the LeakyReLU(IN(.)) map) + its weight / bias gradients
+  DUCOSY_TRY(ducosy_disc_last_backward(dout, pk + L.w5, fb + fw.p4, bb + bw.da[3], grads_host[8], grads_host[9], gs, B, H4, W4, dtype, stream));
+
+  const size_t y_off[3] = {fw.y2, fw.y3, fw.y4}, pin_off[3] = {fw.p1, fw.p2, fw.p3}, wd_off[3] = {L.wd2, L.wd3, L.wd4};
+  int Hl = H4, Wl = W4, Cl = 512;
+  for (int l = 2; l >= 0; --l) {   // layers 4, 3, 2 of the reference (index l: conv l+2)
+    const float* scale = reinterpret_cast<const float*>(fb + fw.scale[l]);
+    const float* shift = reinterpret_cast<const float*>(fb + fw.shift[l]);
+    // InstanceNorm + LeakyReLU backward -> gradient of the raw conv output, zero-padded for the phase convs below
+    DUCOSY_TRY(ducosy_in_backward_pad(bb + bw.da[l + 1], fb + y_off[l], scale, shift, bb + bw.dyp[l],
+                                      reinterpret_cast<float*>(bb + bw.in_scratch), B, Hl, Wl, Cl, 1, DUCOSY_ACT_LRELU02, dtype, stream));
+    // weight gradient (tensor cores) -> OIHW; the conv bias in front of a non-affine InstanceNorm has zero gradient
+    DUCOSY_TRY(ducosy_conv2d_wgrad_nhwc(fb + pin_off[l], bb + bw.dyp[l], 1, reinterpret_cast<float*>(bb + bw.dwp), B, 2 * Hl + 2,
+                                        2 * Wl + 2, Cl / 2, Cl, 4, 4, 2, bb + bw.wg_ws, bw.dwp - bw.wg_ws, dtype, stream));
+    DUCOSY_TRY(ducosy_unpack_wgrad(reinterpret_cast<const float*>(bb + bw.dwp), grads_host[2 + 2 * l], Cl, Cl / 2, 16, gs, stream));
+    cudaMemsetAsync(grads_host[3 + 2 * l], 0, size_t(Cl) * 4, st);
+    // input gradient (tensor cores): grad wrt the previous activation map
+    DUCOSY_TRY(ducosy_conv4x4s2_dgrad_nhwc(bb + bw.dyp[l], pk + wd_off[l], bb + bw.da[l], B, Hl, Wl, Cl / 2, Cl, dtype, stream));
+    Hl *= 2; Wl *= 2; Cl /= 2;
+  }
+  // first layer
+  return ducosy_disc_first_backward(bb + bw.da[0], fb + fw.p1, x, reinterpret_cast<const float*>(pk + L.w1), grads_host[0],
+                                    grads_host[1], dx, reinterpret_cast<float*>(bb + bw.first_scratch), gs, B, H, W, dtype, stream);
 }

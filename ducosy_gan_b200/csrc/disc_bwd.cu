@@ -1,0 +1,417 @@
+// PatchGAN discriminator backward (what autograd computes for modules/trainer.py:518-524 through modules/model.py:118-131).
+// Tensor-core work reuses the forward machinery:
+//   * input gradient of the 4x4 stride-2 convs = four phase-specific 2x2 convs over the zero-padded output gradient
+//     (the adjoint of a stride-2 conv is "fractionally strided"): exactly the sub-pixel launch of conv_gemm.cu with a
+//     transposed weight packing;
+//   * weight gradients = conv_wgrad.cu (MN-major tcgen05 GEMM over the pixels).
+// InstanceNorm + LeakyReLU backward, the first (Cin = 1) and last (Cout = 1) layers are bandwidth-bound kernels here.
+// All reductions run in a fixed order (deterministic gradients).
+#include "common.cuh"
+
+namespace ducosy {
+namespace {
+
+__device__ __forceinline__ float act_grad(float n, int act) {  // derivative of the activation at pre-activation n
+  if (act == DUCOSY_ACT_RELU) return n > 0.f ? 1.f : 0.f;
+  if (act == DUCOSY_ACT_LRELU02) return n > 0.f ? 1.f : 0.2f;
+  return 1.f;
+}
+
+// ------------------------------------------------------------------ gradient scaling for the 16-bit backward maps
+// Loss gradients are tiny (mean-reduced losses divide by the element count) and would sit in the fp16 subnormal range.
+// The incoming gradient is multiplied by a power of two that brings its max magnitude into [1, 2); the backward is
+// linear, so the final fp32 parameter / input gradients are simply multiplied by the inverse.  gs[0] = scale, gs[1] = 1/scale.
+__global__ void __launch_bounds__(1024)
+grad_scale_kernel(const float* __restrict__ g, long long n, float* __restrict__ gs) {
+  __shared__ float red[32];
+  float m = 0.f;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+#pragma unroll
+  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    m = red[threadIdx.x];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    if (threadIdx.x == 0) {
+      int e = 0;
+      if (m > 0.f && isfinite(m)) {
+        frexpf(m, &e);             // m = f * 2^e, f in [0.5, 1)
+        e = 1 - e;                 // m * 2^e in [1, 2)
+        e = max(-60, min(60, e));
+      }
+      gs[0] = ldexpf(1.f, e);
+      gs[1] = ldexpf(1.f, -e);
+    }
+  }
+}
+
+// ------------------------------------------------------------------ InstanceNorm(+activation) backward
+// forward: n = y*rstd + shift, a = act(n).  Given da: g = da * act'(n);
+//   dy = rstd * (g - mean(g) - n * mean(g*n))          (per sample and channel, means over H*W)
+// pass 1: per-block partial sums [B][blocks][2][C];  pass 2 (in_bwd_finalize): fixed-order sum -> [B][2][C];
+// pass 3: dy written 16-bit into a zero-padded buffer.
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+                     const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block) {
+  extern __shared__ float red[];  // [rows][2][C] with rows = 256 / (C/8)
+  const int cv = C / 8, c8 = threadIdx.x % cv, prow = threadIdx.x / cv, rows = 256 / cv;
+  const int b = blockIdx.y;
+  const int p0 = blockIdx.x * pix_per_block, p1 = min(p0 + pix_per_block, HW);
+  float sc[8], sh[8], s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    sc[j] = scale[b * C + c8 * 8 + j];
+    sh[j] = shift[b * C + c8 * 8 + j];
+    s1[j] = 0.f;
+    s2[j] = 0.f;
+  }
+  const uint4* dav = reinterpret_cast<const uint4*>(da) + (size_t(b) * HW) * cv + c8;
+  const uint4* yv = reinterpret_cast<const uint4*>(y) + (size_t(b) * HW) * cv + c8;
+  for (int p = p0 + prow; p < p1; p += rows) {
+    const uint4 a = dav[size_t(p) * cv], v = yv[size_t(p) * cv];
+    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, vw[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+      const float n0 = fmaf(fy.x, sc[2 * k], sh[2 * k]), n1 = fmaf(fy.y, sc[2 * k + 1], sh[2 * k + 1]);
+      const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);
+      s1[2 * k] += g0;
+      s1[2 * k + 1] += g1;
+      s2[2 * k] = fmaf(g0, n0, s2[2 * k]);
+      s2[2 * k + 1] = fmaf(g1, n1, s2[2 * k + 1]);
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    red[(prow * 2 + 0) * C + c8 * 8 + j] = s1[j];
+    red[(prow * 2 + 1) * C + c8 * 8 + j] = s2[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 2 * C; i += 256) {
+    float acc = 0.f;
+    for (int r = 0; r < rows; ++r) acc += red[r * 2 * C + i];
+    partial[(size_t(b) * gridDim.x + blockIdx.x) * 2 * C + i] = acc;
+  }
+}
+
+__global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int blocks, int C, float inv_hw) {
+  const int b = blockIdx.y;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * C; i += gridDim.x * blockDim.x) {
+    double acc = 0.0;
+    for (int k = 0; k < blocks; ++k) acc += double(partial[(size_t(b) * blocks + k) * 2 * C + i]);
+    sums[size_t(b) * 2 * C + i] = float(acc * inv_hw);   // means
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+                        const float* __restrict__ shift, const float* __restrict__ means, T* __restrict__ dy_pad, int B,
+                        int H, int W, int C, int pad, int act) {
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
+  const long long total = (long long)B * Hp * Wp * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % cv);
+    long long r = i / cv;
+    const int px = int(r % Wp);
+    r /= Wp;
+    const int py = int(r % Hp);
+    const int b = int(r / Hp);
+    const int sy = py - pad, sx = px - pad;
+    uint4 o = make_uint4(0, 0, 0, 0);
+    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
+      const size_t src = ((size_t(b) * H + sy) * W + sx) * cv + c8;
+      const uint4 a = reinterpret_cast<const uint4*>(da)[src], v = reinterpret_cast<const uint4*>(y)[src];
+      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, vw[4] = {v.x, v.y, v.z, v.w};
+      uint32_t ow[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+        float res[2];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          const int c = c8 * 8 + 2 * k + e;
+          const float rstd = scale[b * C + c];
+          const float n = fmaf(e ? fy.y : fy.x, rstd, shift[b * C + c]);
+          const float g = (e ? fa.y : fa.x) * act_grad(n, act);
+          res[e] = rstd * (g - means[size_t(b) * 2 * C + c] - n * means[size_t(b) * 2 * C + C + c]);
+        }
+        ow[k] = Cvt<T>::pack2(res[0], res[1]);
+      }
+      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+    }
+    reinterpret_cast<uint4*>(dy_pad)[i] = o;
+  }
+}
+
+// ------------------------------------------------------------------ dgrad weight packing for the 4x4 stride-2 convs
+// Wd[phase*Ci + c][(a*2+b)*Co + o] = W[o][c][r(py,a)][s(px,b)],  r(0,.) = {3,1}, r(1,.) = {2,0}
+template <typename T>
+__global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+  const long long total = 16LL * Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = int(i % Co);
+    long long r = i / Co;
+    const int tap = int(r % 4);
+    r /= 4;
+    const int c = int(r % Ci);
+    const int phase = int(r / Ci);
+    const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
+    const int rr = py == 0 ? (a == 0 ? 3 : 1) : (a == 0 ? 2 : 0);
+    const int ss = px == 0 ? (b == 0 ? 3 : 1) : (b == 0 ? 2 : 0);
+    out[i] = Cvt<T>::from_f(w[(((long long)o * Ci + c) * 4 + rr) * 4 + ss]);
+  }
+}
+
+// packed fp32 weight gradient [Co][taps*Ci + c] -> OIHW [Co][Ci][taps]
+__global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps,
+                                    const float* __restrict__ gs) {
+  const float inv = gs != nullptr ? gs[1] : 1.f;
+  const long long total = (long long)Co * Ci * taps;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = int(i % taps);
+    long long r = i / taps;
+    const int c = int(r % Ci);
+    const int o = int(r / Ci);
+    g[i] = packed[((long long)o * taps + tap) * Ci + c] * inv;
+  }
+}
+
+// ------------------------------------------------------------------ last layer (512 -> 1) backward
+// forward: out[yo][xo] = b + sum_{r,s,c} p4[yo+r][xo+s][c] w[c][r][s], p4 = a4 zero-padded by 2.
+// da4[y][x][c] = sum_{r,s} dout[y+2-r][x+2-s] w[c][r][s]
+template <typename T>
+__global__ void disc_last_dgrad_kernel(const float* __restrict__ dout, const T* __restrict__ wp /*[16][512]*/,
+                                       T* __restrict__ da, int B, int Hs, int Ws, const float* __restrict__ gs) {
+  const float gscale = gs != nullptr ? gs[0] : 1.f;
+  const long long total = (long long)B * Hs * Ws * 64;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i & 63);
+    long long r = i >> 6;
+    const int x = int(r % Ws);
+    r /= Ws;
+    const int y = int(r % Hs);
+    const int b = int(r / Hs);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int tap = 0; tap < 16; ++tap) {
+      const int yo = y + 2 - (tap >> 2), xo = x + 2 - (tap & 3);
+      if (yo < 0 || yo >= Hs || xo < 0 || xo >= Ws) continue;
+      const float d = dout[((long long)b * Hs + yo) * Ws + xo] * gscale;
+      const uint4 wv = *reinterpret_cast<const uint4*>(wp + tap * 512 + c8 * 8);
+      const uint32_t ww[4] = {wv.x, wv.y, wv.z, wv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = Cvt<T>::unpack2(ww[k]);
+        acc[2 * k] = fmaf(d, f.x, acc[2 * k]);
+        acc[2 * k + 1] = fmaf(d, f.y, acc[2 * k + 1]);
+      }
+    }
+    reinterpret_cast<uint4*>(da)[i] = make_uint4(Cvt<T>::pack2(acc[0], acc[1]), Cvt<T>::pack2(acc[2], acc[3]),
+                                                 Cvt<T>::pack2(acc[4], acc[5]), Cvt<T>::pack2(acc[6], acc[7]));
+  }
+}
+// dw[c][tap] = sum_{b,yo,xo} dout * p4[b][yo+r][xo+s][c];  db = sum dout.  One block per tap, one thread per channel.
+template <typename T>
+__global__ void __launch_bounds__(512)
+disc_last_wgrad_kernel(const float* __restrict__ dout, const T* __restrict__ p4, float* __restrict__ dw,
+                       float* __restrict__ db, int B, int Hs, int Ws) {
+  const int tap = blockIdx.x, c = threadIdx.x, r = tap >> 2, s = tap & 3;
+  const int Hp = Hs + 4, Wp = Ws + 4;
+  float acc = 0.f, dsum = 0.f;
+  for (int b = 0; b < B; ++b)
+    for (int yo = 0; yo < Hs; ++yo)
+      for (int xo = 0; xo < Ws; ++xo) {
+        const float d = dout[((long long)b * Hs + yo) * Ws + xo];
+        acc = fmaf(d, Cvt<T>::to_f(p4[(((long long)b * Hp + yo + r) * Wp + xo + s) * 512 + c]), acc);
+        dsum += d;
+      }
+  dw[c * 16 + tap] = acc;
+  if (tap == 0 && c == 0) *db = dsum;
+}
+
+// ------------------------------------------------------------------ first layer (1 -> 64) backward
+// dpre = da1 * lrelu'(a1); dw1[o][tap] = sum dpre[pix][o] * x[2y+r-1][2x+s-1]; db1[o] = sum dpre[pix][o].
+// thread = (channel o, tap group of 4); each block reduces a pixel range into partial[block][64][17].
+template <typename T>
+__global__ void __launch_bounds__(256)
+disc_first_wgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, const float* __restrict__ x,
+                        float* __restrict__ partial, int B, int H, int W, int pix_per_block) {
+  const int Ho = H / 2, Wo = W / 2;
+  const int o = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  const long long P = (long long)B * Ho * Wo;
+  const long long q0 = (long long)blockIdx.x * pix_per_block, q1 = min(q0 + (long long)pix_per_block, P);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
+  for (long long q = q0; q < q1; ++q) {
+    const int xo = int(q % Wo);
+    long long r = q / Wo;
+    const int yo = int(r % Ho);
+    const int b = int(r / Ho);
+    const float a1 = Cvt<T>::to_f(p1[(((long long)b * (Ho + 2) + yo + 1) * (Wo + 2) + xo + 1) * 64 + o]);
+    const float d = Cvt<T>::to_f(da1[q * 64 + o]) * (a1 > 0.f ? 1.f : 0.2f);
+    bsum += d;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int tap = tg * 4 + k, iy = 2 * yo + (tap >> 2) - 1, ix = 2 * xo + (tap & 3) - 1;
+      const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((long long)b * H + iy) * W + ix) : 0.f;
+      acc[k] = fmaf(d, xv, acc[k]);
+    }
+  }
+  float* dst = partial + (size_t(blockIdx.x) * 64 + o) * 17;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) dst[tg * 4 + k] = acc[k];
+  if (tg == 0) dst[16] = bsum;
+}
+__global__ void disc_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
+                                               int blocks, const float* __restrict__ gs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 64 * 17
+  if (i >= 64 * 17) return;
+  double acc = 0.0;
+  for (int k = 0; k < blocks; ++k) acc += double(partial[size_t(k) * 64 * 17 + i]);
+  const int o = i / 17, t = i % 17;
+  if (gs != nullptr) acc *= double(gs[1]);
+  if (t < 16) dw[o * 16 + t] = float(acc);
+  else db[o] = float(acc);
+}
+// input gradient of the first layer: dx[iy][ix] = sum_{o, (r,s) with matching parity} dpre[(iy+1-r)/2][(ix+1-s)/2][o] w1[o][r][s]
+template <typename T>
+__global__ void disc_first_dgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, const float* __restrict__ w1,
+                                        float* __restrict__ dx, int B, int H, int W, const float* __restrict__ gs) {
+  const float inv = gs != nullptr ? gs[1] : 1.f;
+  __shared__ float sw[64 * 16];
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[i] = w1[i];
+  __syncthreads();
+  const int Ho = H / 2, Wo = W / 2;
+  const long long total = (long long)B * H * W;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int ix = int(i % W);
+    long long r = i / W;
+    const int iy = int(r % H);
+    const int b = int(r / H);
+    float acc = 0.f;
+    for (int rr = (iy + 1) & 1; rr < 4; rr += 2) {
+      const int yo = (iy + 1 - rr) / 2;
+      if (iy + 1 - rr < 0 || yo >= Ho) continue;
+      for (int ss = (ix + 1) & 1; ss < 4; ss += 2) {
+        const int xo = (ix + 1 - ss) / 2;
+        if (ix + 1 - ss < 0 || xo >= Wo) continue;
+        const T* d = da1 + (((long long)b * Ho + yo) * Wo + xo) * 64;
+        const T* a = p1 + (((long long)b * (Ho + 2) + yo + 1) * (Wo + 2) + xo + 1) * 64;
+        for (int o = 0; o < 64; ++o) {
+          const float av = Cvt<T>::to_f(a[o]);
+          acc = fmaf(Cvt<T>::to_f(d[o]) * (av > 0.f ? 1.f : 0.2f), sw[o * 16 + rr * 4 + ss], acc);
+        }
+      }
+    }
+    dx[i] = acc * inv;
+  }
+}
+
+int grid_for_items(long long items, int threads) {
+  long long blocks = (items + threads - 1) / threads;
+  const long long cap = (long long)(num_sms() > 0 ? num_sms() : 148) * 8;
+  if (blocks > cap) blocks = cap;
+  if (blocks < 1) blocks = 1;
+  return int(blocks);
+}
+
+}  // namespace
+}  // namespace ducosy
+
+using namespace ducosy;
+
+// Generic InstanceNorm(+activation) backward on NHWC 16-bit maps (also the generator's building block):
+//   da, y [B][H][W][C]; scale/shift from ducosy_in_finalize of the forward; scratch: fp32 [B*(blocks+1)*2*C] with
+//   blocks = ceil(H*W / 2048); dy_pad [B][H+2p][W+2p][C] (zero border).
+extern "C" size_t ducosy_in_backward_scratch_bytes(int B, int H, int W, int C) {
+  const int blocks = (H * W + 2047) / 2048;
+  return size_t(B) * (blocks + 1) * 2 * C * 4;
+}
+extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad,
+                                      float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
+                                      ducosy_stream_t stream) {
+  DUCOSY_CHECK(da && y && scale && shift && dy_pad && scratch && B > 0, DUCOSY_ERR_ARG, "in_backward_pad: null pointer");
+  DUCOSY_CHECK(C % 8 == 0 && 256 % (C / 8) == 0 && pad >= 0, DUCOSY_ERR_SHAPE, "in_backward_pad: C/8 must divide 256");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int HW = H * W, ppb = 2048, blocks = (HW + ppb - 1) / ppb;
+  float* partial = scratch;
+  float* means = scratch + size_t(B) * blocks * 2 * C;
+  const size_t smem = size_t(256 / (C / 8)) * 2 * C * 4;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T><<<dim3(blocks, B), 256, smem, st>>>(
+                                      static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb)));
+  DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
+  in_bwd_finalize_kernel<<<dim3((2 * C + 255) / 256, B), 256, 0, st>>>(partial, means, blocks, C, 1.0f / float(HW));
+  DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
+  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_pad_kernel<T><<<grid_for_items(total, 256), 256, 0, st>>>(
+                                      static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
+                                      static_cast<T*>(dy_pad), B, H, W, C, pad, act)));
+  return check_launch("in_bwd_apply_pad_kernel");
+}
+
+extern "C" int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype,
+                                           ducosy_stream_t stream) {
+  DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_dgrad_s2_weight: bad argument");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_dgrad_s2_weight_kernel<T><<<grid_for_items(16LL * Cout * Cin, 256), 256, 0,
+                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+  return check_launch("pack_dgrad_s2_weight_kernel");
+}
+
+// Input gradient of Conv2d(Cin, Cout, 4, stride 2, padding 1): dy_pad [B][Ho+2][Wo+2][Cout] (zero border) -> dx [B][2Ho][2Wo][Cin].
+extern "C" int ducosy_conv4x4s2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin,
+                                           int Cout, int dtype, ducosy_stream_t stream) {
+  // four 2x2 phase convs over the padded gradient: same launch as the x2 up-conv with (Cin, Cout) swapped
+  return ducosy_upconv2x_nhwc(dy_pad, w_dgrad, dx, nullptr, B, Ho, Wo, Cout, Cin, dtype, stream);
+}
+
+extern "C" int ducosy_grad_scale(const float* g, long long n, float* gs, ducosy_stream_t stream) {
+  DUCOSY_CHECK(g && gs && n > 0, DUCOSY_ERR_ARG, "grad_scale: bad argument");
+  grad_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, n, gs);
+  return check_launch("grad_scale_kernel");
+}
+
+extern "C" int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
+                                   ducosy_stream_t stream) {
+  DUCOSY_CHECK(packed && g_oihw, DUCOSY_ERR_ARG, "unpack_wgrad: null pointer");
+  unpack_wgrad_kernel<<<grid_for_items((long long)Cout * Cin * taps, 256), 256, 0, (cudaStream_t)stream>>>(packed, g_oihw, Cout, Cin, taps, gs);
+  return check_launch("unpack_wgrad_kernel");
+}
+
+extern "C" int ducosy_disc_last_backward(const float* dout, const void* w5_packed, const void* p4, void* da4, float* dw5,
+                                         float* db5, const float* gs, int B, int Hs, int Ws, int dtype,
+                                         ducosy_stream_t stream) {
+  DUCOSY_CHECK(dout && w5_packed && p4 && da4 && dw5 && db5, DUCOSY_ERR_ARG, "disc_last_backward: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_dgrad_kernel<T><<<grid_for_items((long long)B * Hs * Ws * 64, 256), 256, 0, st>>>(
+                                      dout, static_cast<const T*>(w5_packed), static_cast<T*>(da4), B, Hs, Ws, gs)));
+  DUCOSY_TRY(check_launch("disc_last_dgrad_kernel"));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_wgrad_kernel<T><<<16, 512, 0, st>>>(dout, static_cast<const T*>(p4), dw5, db5, B, Hs, Ws)));
+  return check_launch("disc_last_wgrad_kernel");
+}
+
+extern "C" size_t ducosy_disc_first_backward_scratch_bytes(int B, int H, int W) {
+  const long long P = (long long)B * (H / 2) * (W / 2);
+  return size_t((P + 1023) / 1024) * 64 * 17 * 4;
+}
+extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const float* x, const float* w1, float* dw1,
+                                          float* db1, float* dx, float* scratch, const float* gs, int B, int H, int W,
+                                          int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(da1 && p1 && x && w1 && dw1 && db1 && scratch, DUCOSY_ERR_ARG, "disc_first_backward: null pointer");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long P = (long long)B * (H / 2) * (W / 2);
+  const int blocks = int((P + 1023) / 1024);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_wgrad_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(da1), static_cast<const T*>(p1),
+                                                                                     x, scratch, B, H, W, 1024)));
+  DUCOSY_TRY(check_launch("disc_first_wgrad_kernel"));
+  disc_first_wgrad_reduce_kernel<<<(64 * 17 + 255) / 256, 256, 0, st>>>(scratch, dw1, db1, blocks, gs);
+  DUCOSY_TRY(check_launch("disc_first_wgrad_reduce_kernel"));
+  if (dx != nullptr) {
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_dgrad_kernel<T><<<grid_for_items((long long)B * H * W, 256), 256, 0, st>>>(
+                                        static_cast<const T*>(da1), static_cast<const T*>(p1), w1, dx, B, H, W, gs)));
+    return check_launch("disc_first_dgrad_kernel");
+  }
+  return 0;
+}

@@ -225,8 +225,9 @@ class _GeneratorEngine:
 
 class Discriminator(nn.Module):
     """reference modules/model.py:118-131 (PatchGAN).  ``forward(img[B,1,H,W] fp32 cuda) -> [B,1,H/16,W/16] fp32``;
-    H and W multiples of 256.  Inference / validation forward only in this round (reference
-    modules/trainer.py:243 evaluates it under no_grad); the backward belongs to the training-step rows."""
+    H and W multiples of 256.  Differentiable w.r.t. its parameters and the input image: under autograd the forward and
+    the backward both run in libducosy_sm100.so (BASELINE config 3: forward/backward with the MSE adversarial loss of
+    reference modules/trainer.py:347,518-524)."""
 
     def __init__(self, input_channels=1):
         super().__init__()
@@ -243,8 +244,6 @@ class Discriminator(nn.Module):
         self._engines = {}
 
     def forward(self, img):
-        if torch.is_grad_enabled() and (img.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(_NO_TRAIN_MSG.format("Discriminator"))
         if self._input_channels != 1:
             raise NotImplementedError("ducosy_gan_b200.Discriminator supports input_channels == 1 (what the reference trains)")
         if not img.is_cuda:
@@ -254,8 +253,29 @@ class Discriminator(nn.Module):
         eng = self._engines.get(key)
         if eng is None:
             eng = self._engines[key] = _DiscriminatorEngine(key[1], torch.device("cuda", key[0]))
-        eng.sync_weights([p for _, p in self.named_parameters()])
+        params = [p for _, p in self.named_parameters()]
+        eng.sync_weights(params)
+        if torch.is_grad_enabled() and (img.requires_grad or any(p.requires_grad for p in params)):
+            return _DiscriminatorFunction.apply(eng, img, *params)
         return eng.forward(img)
+
+
+class _DiscriminatorFunction(torch.autograd.Function):
+    """autograd bridge: forward keeps the activation workspace, backward calls ducosy_discriminator_backward."""
+
+    @staticmethod
+    def forward(ctx, eng, img, *params):
+        img = img.detach().to(dtype=torch.float32).contiguous()
+        out, ws = eng.forward(img, keep_workspace=True)
+        ctx.eng, ctx.ws, ctx.img = eng, ws, img
+        ctx.shapes = [tuple(p.shape) for p in params]
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        grads, dx = ctx.eng.backward(ctx.img, dout, ctx.ws, ctx.shapes, ctx.needs_input_grad[1])
+        ctx.ws = None
+        return (None, dx, *grads)
 
 
 class _DiscriminatorEngine:
@@ -281,23 +301,46 @@ class _DiscriminatorEngine:
                       _lib.stream_ptr())
         self._keepalive, self._versions = keep, sig
 
-    def forward(self, img):
+    @staticmethod
+    def _aligned(t):
+        return (t.data_ptr() + 1023) // 1024 * 1024
+
+    def forward(self, img, keep_workspace=False):
         if img.dim() != 4 or img.shape[1] != 1:
             raise RuntimeError(f"expected input [B,1,H,W], got {tuple(img.shape)}")
         img = img.to(dtype=torch.float32).contiguous()
         B, _, H, W = img.shape
         with torch.cuda.device(self.device):
-            ws = self._ws.get((B, H, W))
+            ws = None if keep_workspace else self._ws.get((B, H, W))
             if ws is None:
                 need = self.lib.ducosy_discriminator_workspace_bytes(B, H, W)
                 if need == 0:
                     raise _lib.DucosyError(f"unsupported discriminator input shape {tuple(img.shape)}: H, W multiples of 256")
-                self._ws.clear()
-                ws = self._ws[(B, H, W)] = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+                ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+                if not keep_workspace:   # inference: one cached workspace; training: one per call, owned by autograd
+                    self._ws.clear()
+                    self._ws[(B, H, W)] = ws
             out = torch.empty((B, 1, H // 16, W // 16), dtype=torch.float32, device=self.device)
             _lib.call("ducosy_discriminator_forward", C.c_void_p(self._packed_ptr()), _lib.ptr(img), _lib.ptr(out), B, H, W,
-                      C.c_void_p((ws.data_ptr() + 1023) // 1024 * 1024), ws.numel() - 1024, self.dtype_code, _lib.stream_ptr())
-        return out
+                      C.c_void_p(self._aligned(ws)), ws.numel() - 1024, self.dtype_code, _lib.stream_ptr())
+        return (out, ws) if keep_workspace else out
+
+    def backward(self, img, dout, fwd_ws, shapes, need_dx):
+        B, _, H, W = img.shape
+        dout = dout.detach().to(dtype=torch.float32).contiguous()
+        with torch.cuda.device(self.device):
+            need = self.lib.ducosy_discriminator_backward_workspace_bytes(B, H, W)
+            bws = self._bws.get((B, H, W)) if hasattr(self, "_bws") else None
+            if bws is None:
+                self._bws = {(B, H, W): torch.empty(need + 1024, dtype=torch.uint8, device=self.device)}
+                bws = self._bws[(B, H, W)]
+            grads = [torch.empty(s, dtype=torch.float32, device=self.device) for s in shapes]
+            dx = torch.empty_like(img) if need_dx else None
+            arr = (C.c_void_p * len(grads))(*[g.data_ptr() for g in grads])
+            _lib.call("ducosy_discriminator_backward", C.c_void_p(self._packed_ptr()), _lib.ptr(img), _lib.ptr(dout),
+                      C.c_void_p(self._aligned(fwd_ws)), arr, _lib.ptr(dx), B, H, W, C.c_void_p(self._aligned(bws)),
+                      bws.numel() - 1024, self.dtype_code, _lib.stream_ptr())
+        return grads, dx
 
 
 def weights_init_normal(m):

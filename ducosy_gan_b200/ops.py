@@ -257,16 +257,44 @@ def out_conv7x7_tanh_fused(y_raw, scale, shift, w_packed, bias):
     return out
 
 
-def conv2d_wgrad_nhwc(x_pad, dy, kh, kw, stride):
-    """Weight gradient dW fp32 [Cout, kh*kw*Cin] (packed forward layout) from the padded input and the output gradient."""
+def conv2d_wgrad_nhwc(x_pad, dy, kh, kw, stride, dy_pad=0):
+    """Weight gradient dW fp32 [Cout, kh*kw*Cin] (packed forward layout) from the padded input and the output gradient
+    (dy may be stored inside a buffer with a border of dy_pad pixels)."""
     B, Hp, Wp, Cin = x_pad.shape
     _, Ho, Wo, Cout = dy.shape
+    Ho, Wo = Ho - 2 * dy_pad, Wo - 2 * dy_pad
     assert x_pad.is_contiguous() and dy.is_contiguous() and x_pad.dtype == dy.dtype
     lib = _lib.load()
     with _dev(x_pad):
         need = lib.ducosy_conv2d_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, kh, kw)
         ws = torch.empty(max(need, 16), dtype=torch.uint8, device=x_pad.device)
         dw = torch.empty((Cout, kh * kw * Cin), dtype=torch.float32, device=x_pad.device)
-        call("ducosy_conv2d_wgrad_nhwc", ptr(x_pad), ptr(dy), ptr(dw), B, Hp, Wp, Cin, Cout, kh, kw, stride, ptr(ws),
+        call("ducosy_conv2d_wgrad_nhwc", ptr(x_pad), ptr(dy), int(dy_pad), ptr(dw), B, Hp, Wp, Cin, Cout, kh, kw, stride, ptr(ws),
              ws.numel(), dtype_code(x_pad.dtype), stream_ptr())
     return dw
+
+
+def in_backward_pad(da, y, scale, shift, pad, act):
+    """InstanceNorm(+activation) backward: da, y NHWC 16-bit -> dy zero-padded [B,H+2p,W+2p,C]."""
+    B, H, W, Cn = y.shape
+    lib = _lib.load()
+    with _dev(y):
+        scratch = torch.empty(max(lib.ducosy_in_backward_scratch_bytes(B, H, W, Cn) // 4, 4), dtype=torch.float32, device=y.device)
+        out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), dtype=y.dtype, device=y.device)
+        call("ducosy_in_backward_pad", ptr(da), ptr(y), ptr(scale), ptr(shift), ptr(out), ptr(scratch), B, H, W, Cn, pad, act,
+             dtype_code(y.dtype), stream_ptr())
+    return out
+
+
+def conv4x4s2_dgrad_nhwc(dy_pad, w_oihw):
+    """Input gradient of Conv2d(Cin,Cout,4,stride 2,padding 1): dy_pad [B,Ho+2,Wo+2,Cout] -> dx [B,2Ho,2Wo,Cin]."""
+    Cout, Cin = w_oihw.shape[:2]
+    B, Hp, Wp, _ = dy_pad.shape
+    w = w_oihw.detach().to(torch.float32).contiguous()
+    with _dev(dy_pad):
+        wd = torch.empty((4 * Cin, 4 * Cout), dtype=dy_pad.dtype, device=dy_pad.device)
+        call("ducosy_pack_dgrad_s2_weight", ptr(w), ptr(wd), Cout, Cin, dtype_code(dy_pad.dtype), stream_ptr())
+        dx = torch.empty((B, 2 * (Hp - 2), 2 * (Wp - 2), Cin), dtype=dy_pad.dtype, device=dy_pad.device)
+        call("ducosy_conv4x4s2_dgrad_nhwc", ptr(dy_pad), ptr(wd), ptr(dx), B, Hp - 2, Wp - 2, Cin, Cout, dtype_code(dy_pad.dtype),
+             stream_ptr())
+    return dx

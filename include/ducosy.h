@@ -183,14 +183,40 @@ int ducosy_generator_num_launches(const ducosy_gen_config* cfg);
  *
  * Weight gradient of the NHWC convolutions on the tensor cores: dW[o][(r*kw+s)*Cin + c] = sum_pixels dy[p][o] *
  * x_pad[p*stride + (r,s)][c] (what autograd computes for modules/trainer.py:513,519,524).  x_pad is the padded input
- * the forward conv read, dy the output gradient [B][Ho][Wo][Cout], both 16-bit NHWC; dw fp32 in the packed forward
+ * the forward conv read, dy the output gradient [B][Ho+2*dy_pad][Wo+2*dy_pad][Cout] (interior), both 16-bit NHWC; dw fp32 in the packed forward
  * layout.  Cin in {64,128,192,256}, Cout % 128 == 0.  Deterministic (fixed-order reduction of the K splits). */
 size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
-int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, float* dw, int B, int Hp, int Wp, int Cin, int Cout, int kh,
-                             int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
+int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp, int Cin,
+                             int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
                              ducosy_stream_t stream);
 
-/* ---------------------------------------------------------------- PatchGAN discriminator forward (modules/model.py:118-131) */
+/* InstanceNorm(+activation) backward on NHWC 16-bit maps: forward n = y*scale + shift, a = act(n); given da returns
+ * dy = rstd*(g - mean(g) - n*mean(g*n)), g = da*act'(n), written with a zero border of `pad` pixels (ready for the
+ * phase / dgrad convolutions).  scratch: ducosy_in_backward_scratch_bytes. */
+size_t ducosy_in_backward_scratch_bytes(int B, int H, int W, int C);
+int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad, float* scratch,
+                           int B, int H, int W, int C, int pad, int act, int dtype, ducosy_stream_t stream);
+/* Input gradient of Conv2d(Cin, Cout, 4, stride 2, padding 1) as four 2x2 phase convolutions over the zero-padded output
+ * gradient dy_pad [B][Ho+2][Wo+2][Cout] -> dx [B][2Ho][2Wo][Cin]; w_dgrad from ducosy_pack_dgrad_s2_weight ([4*Cin][4*Cout]). */
+int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
+int ducosy_conv4x4s2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin, int Cout,
+                                int dtype, ducosy_stream_t stream);
+/* Power-of-two scaling of a loss gradient for the 16-bit backward maps: gs[0] = 2^e with max|g|*2^e in [1,2), gs[1] = 2^-e.
+ * The functions below take `gs` (device pointer, NULL = no scaling): dgrad entry points multiply by gs[0], the fp32
+ * parameter / input gradients are multiplied by gs[1]. */
+int ducosy_grad_scale(const float* g, long long n, float* gs, ducosy_stream_t stream);
+/* packed fp32 weight gradient [Cout][taps*Cin] -> OIHW [Cout][Cin][taps] (times gs[1]). */
+int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
+                        ducosy_stream_t stream);
+/* First (1->64) and last (512->1) discriminator layers, backward (modules/model.py:122,128). */
+int ducosy_disc_last_backward(const float* dout, const void* w5_packed, const void* p4, void* da4, float* dw5, float* db5,
+                              const float* gs, int B, int Hs, int Ws, int dtype, ducosy_stream_t stream);
+size_t ducosy_disc_first_backward_scratch_bytes(int B, int H, int W);
+int ducosy_disc_first_backward(const void* da1, const void* p1, const float* x, const float* w1, float* dw1, float* db1,
+                               float* dx, float* scratch, const float* gs, int B, int H, int W, int dtype,
+                               ducosy_stream_t stream);
+
+/* ---------------------------------------------------------------- PatchGAN discriminator forward / backward (modules/model.py:118-131) */
 
 size_t ducosy_discriminator_packed_bytes(void);
 size_t ducosy_discriminator_workspace_bytes(int B, int H, int W);
@@ -200,6 +226,12 @@ int ducosy_discriminator_pack(const float* const* params_host, int num_params, v
 /* Discriminator.forward: x fp32 [B][1][H][W] (H, W multiples of 256) -> out fp32 [B][1][H/16][W/16]. */
 int ducosy_discriminator_forward(const void* packed, const float* x, float* out, int B, int H, int W, void* workspace,
                                  size_t workspace_bytes, int dtype, ducosy_stream_t stream);
+/* Backward of that forward (loss.backward() of modules/trainer.py:518-524): fwd_workspace is the untouched workspace of the
+ * forward call; grads_host = host array of 10 DEVICE fp32 buffers shaped like the parameters (overwritten); dx optional. */
+size_t ducosy_discriminator_backward_workspace_bytes(int B, int H, int W);
+int ducosy_discriminator_backward(const void* packed, const float* x, const float* dout, const void* fwd_workspace,
+                                  float* const* grads_host, float* dx, int B, int H, int W, void* workspace,
+                                  size_t workspace_bytes, int dtype, ducosy_stream_t stream);
 
 #ifdef __cplusplus
 }

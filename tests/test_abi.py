@@ -67,9 +67,9 @@ def test_discriminator_state_dict_layout_matches_reference():
     assert sum(p.numel() for p in D.parameters()) == 2762689
 
 
-def test_discriminator_training_forward_is_loud():
+def test_discriminator_cpu_input_is_loud():
     from ducosy_gan_b200.modules.model import Discriminator
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
         Discriminator(1)(torch.zeros(1, 1, 256, 256))
 
 

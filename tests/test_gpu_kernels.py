@@ -299,3 +299,48 @@ def test_conv2d_wgrad_matches_autograd(ops, case):
     ref = w0.grad.permute(0, 2, 3, 1).reshape(Cout, k * k * Cin)            # packed layout: (r*kw+s)*Cin + c
     err = (dw - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
+
+
+def test_in_backward_matches_autograd(ops):
+    dtype = torch.float16
+    B, H, W, Cn = 2, 16, 32, 128
+    y = (_rand((B, H, W, Cn), 91) * 1.5 + 0.8).to(dtype).cuda()
+    da = _rand((B, H, W, Cn), 92).to(dtype).cuda()
+    scale, shift = ops.in_finalize(_fake_partials(y), H * W)
+    for act, fn in ((ops.ACT_LRELU02, lambda t: F.leaky_relu(t, 0.2)), (ops.ACT_RELU, F.relu), (ops.ACT_NONE, lambda t: t)):
+        got = ops.in_backward_pad(da, y, scale, shift, 1, act)
+        yr = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+        fn(F.instance_norm(yr)).backward(da.float().permute(0, 3, 1, 2))
+        ref = F.pad(yr.grad, (1, 1, 1, 1))
+        err = (got.float().permute(0, 3, 1, 2) - ref).abs().max().item()
+        assert err < 4e-3 * max(1.0, ref.abs().max().item()), (act, err, ref.abs().max().item())
+
+
+@pytest.mark.parametrize("case", [(2, 16, 16, 256, 512), (1, 32, 64, 64, 128)])
+def test_conv4x4s2_dgrad_matches_autograd(ops, case):
+    B, Ho, Wo, Cin, Cout = case
+    dtype = torch.float16
+    dy = _rand((B, Cout, Ho, Wo), 93).to(dtype)
+    w = (_rand((Cout, Cin, 4, 4), 94, 0.05)).to(dtype).float()
+    dyp = F.pad(dy.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dx = ops.conv4x4s2_dgrad_nhwc(dyp, w.cuda())
+    x0 = torch.zeros((B, Cin, 2 * Ho, 2 * Wo), device="cuda", requires_grad=True)
+    F.conv2d(x0, w.cuda(), stride=2, padding=1).backward(dy.float().cuda())
+    ref = x0.grad
+    err = (dx.float().permute(0, 3, 1, 2) - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
+
+
+def test_conv2d_wgrad_with_padded_dy(ops):
+    dtype = torch.float16
+    B, H, W, Cin, Cout = 2, 32, 32, 256, 512
+    x = _rand((B, Cin, H, W), 95).to(dtype)
+    dy = _rand((B, Cout, H // 2, W // 2), 96).to(dtype)
+    xp = F.pad(x.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dyp = F.pad(dy.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dw = ops.conv2d_wgrad_nhwc(xp, dyp, 4, 4, 2, dy_pad=1)
+    w0 = torch.zeros((Cout, Cin, 4, 4), device="cuda", requires_grad=True)
+    F.conv2d(x.float().cuda(), w0, stride=2, padding=1).backward(dy.float().cuda())
+    ref = w0.grad.permute(0, 2, 3, 1).reshape(Cout, 16 * Cin)
+    err = (dw - ref).abs().max().item()
+    assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
