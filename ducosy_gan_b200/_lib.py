@@ -30,6 +30,8 @@ SIGNATURES = {
     "ducosy_last_error": (C.c_char_p, []),
     "ducosy_check_device": (_i, []),
     "ducosy_hu_window": (_i, [_p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p]),
+    "ducosy_hu_window_soft": (_i, [_p, _p, _ll, _f, _f, _f, _f, _f, _p]),
+    "ducosy_apply_windowing": (_i, [_p, _p, _ll, _f, _f, _f, _f, _p]),
     "ducosy_hu_thresholds": (_i, [_p, _p, _p, _p, _ll, _f, _f, _p]),
     "ducosy_dewindow_composite": (_i, [_p, _p, _p, _p, _p, _p, _p, _ll, _f, _f, _f, _f, _f, _f, _p]),
     "ducosy_pack_conv_weight": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
@@ -58,6 +60,21 @@ SIGNATURES = {
     "ducosy_generator_forward": (_i, [C.POINTER(GenConfig), _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_generator_forward_hu": (_i, [C.POINTER(GenConfig), _p, _p, _f, _f, _f, _f, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_generator_num_launches": (_i, [C.POINTER(GenConfig)]),
+    "ducosy_loss_scratch_bytes": (_sz, []),
+    "ducosy_loss_l1_forward": (_i, [_p, _p, _ll, _p, _p, _p]),
+    "ducosy_loss_l1_backward": (_i, [_p, _p, _ll, _p, _p, _p]),
+    "ducosy_loss_mse_const_forward": (_i, [_p, _f, _ll, _p, _p, _p]),
+    "ducosy_loss_mse_const_backward": (_i, [_p, _f, _ll, _p, _p, _p]),
+    "ducosy_loss_gradient_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "ducosy_loss_gradient_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p]),
+    "ducosy_loss_contrast_attention_forward": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _f, _p, _p, _p, _p]),
+    "ducosy_loss_contrast_attention_backward": (_i, [_p, _i, _i, _i, _p, _p, _p]),
+    "ducosy_loss_contrast_region_forward": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
+    "ducosy_loss_contrast_region_backward": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _p, _p, _p]),
+    "ducosy_loss_contrast_edge_forward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p, _p, _p]),
+    "ducosy_loss_contrast_edge_backward": (_i, [_p, _p, _i, _i, _i, _p, _p, _p, _p]),
+    "ducosy_loss_ssim_forward": (_i, [_p, _p, _i, _i, _i, _f, _p, _p, _p, _p, _p]),
+    "ducosy_loss_ssim_backward": (_i, [_p, _p, _p, _i, _i, _i, _p, _p, _p, _p]),
     "ducosy_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_in_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),

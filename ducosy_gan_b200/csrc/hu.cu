@@ -146,6 +146,29 @@ __global__ void dewindow_composite_kernel(const int16_t* __restrict__ raw, const
   }
 }
 
+// training-side windowing with soft squeezing (modules/preprocess.py:6-40,43-55; dataset.py:118-120)
+__global__ void hu_window_soft_kernel(const int16_t* __restrict__ px, float* __restrict__ out, long long n, float slope,
+                                      float intercept, float lo, float hi, float span, float k) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float hu = stored_to_hu(px[i], slope, intercept);
+    const float c = fminf(fmaxf(hu, lo), hi);
+    const float nrm = __fdiv_rn(__fsub_rn(c, lo), span);                                   // preprocess.py:20
+    const float sm = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(__fmul_rn(-k, __fsub_rn(nrm, 0.9f)))));  // preprocess.py:28
+    const float r = nrm < 0.9f ? nrm : __fadd_rn(0.9f, __fmul_rn(0.1f, sm));               // preprocess.py:31-35
+    out[i] = __fsub_rn(__fmul_rn(2.0f, r), 1.0f);                                          // preprocess.py:38
+  }
+}
+// display windowing of a tanh-range tensor (modules/preprocess.py:58-65)
+__global__ void apply_windowing_kernel(const float* __restrict__ y, float* __restrict__ out, long long n, float lo, float span,
+                                       float wlo, float whi, float ww) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const float hu = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(y[i], 1.0f), 2.0f), span), lo);
+    out[i] = __fdiv_rn(__fsub_rn(fminf(fmaxf(hu, wlo), whi), wlo), ww);
+  }
+}
+
 int grid_for(long long work_items, int threads) {
   const int sms = num_sms();
   long long blocks = (work_items + threads - 1) / threads;
@@ -203,4 +226,24 @@ extern "C" int ducosy_dewindow_composite(const int16_t* raw_px, const float* y_s
       raw_px, y_soft, y_lung, merged, soft_px, lung_px, masks, n, slope, intercept, soft_lo, soft_hi, sspan, lung_lo,
       lung_hi, lspan);
   return check_launch("dewindow_composite_kernel");
+}
+
+extern "C" int ducosy_hu_window_soft(const int16_t* px, float* out, long long n, float slope, float intercept, float hu_lo,
+                                     float hu_hi, float sigma, ducosy_stream_t stream) {
+  if (n == 0) return 0;
+  DUCOSY_CHECK(px && out && n > 0 && sigma > 0.f, DUCOSY_ERR_ARG, "hu_window_soft: bad argument");
+  hu_window_soft_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      px, out, n, slope, intercept, hu_lo, hu_hi, float(double(hu_hi) - double(hu_lo)), float(10.0 / double(sigma)));
+  return check_launch("hu_window_soft_kernel");
+}
+
+extern "C" int ducosy_apply_windowing(const float* y, float* out, long long n, float hu_lo, float hu_hi, float window_center,
+                                      float window_width, ducosy_stream_t stream) {
+  if (n == 0) return 0;
+  DUCOSY_CHECK(y && out && n > 0 && window_width != 0.f, DUCOSY_ERR_ARG, "apply_windowing: bad argument");
+  const double half = double(window_width) / 2.0;
+  apply_windowing_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      y, out, n, hu_lo, float(double(hu_hi) - double(hu_lo)), float(double(window_center) - half),
+      float(double(window_center) + half), window_width);
+  return check_launch("apply_windowing_kernel");
 }

@@ -298,3 +298,23 @@ def conv4x4s2_dgrad_nhwc(dy_pad, w_oihw):
         call("ducosy_conv4x4s2_dgrad_nhwc", ptr(dy_pad), ptr(wd), ptr(dx), B, Hp - 2, Wp - 2, Cin, Cout, dtype_code(dy_pad.dtype),
              stream_ptr())
     return dx
+
+
+def hu_window_soft(px, slope, intercept, hu_lo, hu_hi, sigma=50.0):
+    """Soft-squeezed training windowing (reference preprocess.py:6-55): int16 stored values -> fp32 in [-1,1]."""
+    assert px.dtype == torch.int16 and px.is_cuda and px.is_contiguous()
+    with _dev(px):
+        out = torch.empty(px.shape, dtype=torch.float32, device=px.device)
+        call("ducosy_hu_window_soft", ptr(px), ptr(out), px.numel(), float(slope), float(intercept), float(hu_lo), float(hu_hi),
+             float(sigma), stream_ptr())
+    return out
+
+
+def apply_windowing(y, hu_lo, hu_hi, window_center, window_width):
+    """Display windowing of a tanh-range tensor (reference preprocess.py:58-65)."""
+    y = y.to(torch.float32).contiguous()
+    with _dev(y):
+        out = torch.empty_like(y)
+        call("ducosy_apply_windowing", ptr(y), ptr(out), y.numel(), float(hu_lo), float(hu_hi), float(window_center),
+             float(window_width), stream_ptr())
+    return out

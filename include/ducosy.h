@@ -55,6 +55,15 @@ int ducosy_check_device(void);
 int ducosy_hu_window(const int16_t* px, float* out_soft, float* out_lung, long long n, float slope, float intercept,
                      float soft_lo, float soft_hi, float lung_lo, float lung_hi, ducosy_stream_t stream);
 
+/* Training-side windowing with soft squeezing, apply_hu_transform + apply_soft_squeezing (modules/preprocess.py:6-55,
+ * modules/dataset.py:118-120): n stored values -> out[n] fp32 in [-1, 1]; sigma = 50 in the reference.  Same float32 steps
+ * as numpy; only exp() may differ by an ulp. */
+int ducosy_hu_window_soft(const int16_t* px, float* out, long long n, float slope, float intercept, float hu_lo, float hu_hi,
+                          float sigma, ducosy_stream_t stream);
+/* apply_windowing (modules/preprocess.py:58-65): tanh-range tensor -> display intensity in [0,1] for a (center, width) window. */
+int ducosy_apply_windowing(const float* y, float* out, long long n, float hu_lo, float hu_hi, float window_center,
+                           float window_width, ducosy_stream_t stream);
+
 /* HU threshold candidates of the anatomical mask generator (modules/mask_generator.py:14-20,179-183):
  * body = hu > -1000, lung = -1000 <= hu <= -300 & body, bone = hu >= 200 & body, uint8 {0,1}. NULL outputs are skipped. */
 int ducosy_hu_thresholds(const int16_t* px, uint8_t* body, uint8_t* lung, uint8_t* bone, long long n, float slope,
@@ -178,6 +187,47 @@ int ducosy_generator_forward_hu(const ducosy_gen_config* cfg, const void* packed
                                 void* workspace, size_t workspace_bytes, ducosy_stream_t stream);
 /* Number of kernels one forward launches (for bench accounting). */
 int ducosy_generator_num_launches(const ducosy_gen_config* cfg);
+
+/* ---------------------------------------------------------------- loss terms of the CycleGAN step, forward + backward
+ * (modules/trainer.py:22-184,347-358,469-512).  Images are fp32 [B][1][H][W]; loss_out / gout are DEVICE scalars (no host
+ * sync); reductions are fixed-order (deterministic).  scratch: ducosy_loss_scratch_bytes() bytes, 16-byte aligned.
+ * Backward functions return the gradient w.r.t. the first argument (the generated image), scaled by gout[0]. */
+size_t ducosy_loss_scratch_bytes(void);
+/* nn.L1Loss (cycle / identity, trainer.py:348-349) and nn.MSELoss against a constant patch target (trainer.py:347,459-460) */
+int ducosy_loss_l1_forward(const float* a, const float* b, long long n, float* loss_out, float* scratch, ducosy_stream_t stream);
+int ducosy_loss_l1_backward(const float* a, const float* b, long long n, const float* gout, float* da, ducosy_stream_t stream);
+int ducosy_loss_mse_const_forward(const float* a, float target, long long n, float* loss_out, float* scratch, ducosy_stream_t stream);
+int ducosy_loss_mse_const_backward(const float* a, float target, long long n, const float* gout, float* da, ducosy_stream_t stream);
+/* GradientLoss (trainer.py:22-40) */
+int ducosy_loss_gradient_forward(const float* pred, const float* target, int B, int H, int W, float* loss_out, float* scratch,
+                                 ducosy_stream_t stream);
+int ducosy_loss_gradient_backward(const float* pred, const float* target, int B, int H, int W, const float* gout, float* dpred,
+                                  ducosy_stream_t stream);
+/* ContrastAttentionLoss (trainer.py:43-86), blur kernel 7; umap [B*H*W] (may be NULL in forward-only use) feeds the backward */
+int ducosy_loss_contrast_attention_forward(const float* pred, const float* target, const float* source, int B, int H, int W,
+                                           float sigma, float min_w, float max_w, float* loss_out, float* umap, float* scratch,
+                                           ducosy_stream_t stream);
+int ducosy_loss_contrast_attention_backward(const float* umap, int B, int H, int W, const float* gout, float* dpred,
+                                            ducosy_stream_t stream);
+/* ContrastRegionLoss (trainer.py:89-130); state: 4 floats */
+int ducosy_loss_contrast_region_forward(const float* pred, const float* target, const float* source, int B, int H, int W,
+                                        float threshold, float weight, float* loss_out, float* state, float* scratch,
+                                        ducosy_stream_t stream);
+int ducosy_loss_contrast_region_backward(const float* pred, const float* target, const float* source, int B, int H, int W,
+                                         float threshold, float weight, const float* state, const float* gout, float* dpred,
+                                         ducosy_stream_t stream);
+/* ContrastEdgeLoss (trainer.py:133-184): Sobel magnitude mean/std + exact top-10 % mean by radix selection instead of
+ * torch.topk; ep/et: edge maps [B*H*W]; state: 8 floats */
+int ducosy_loss_contrast_edge_forward(const float* pred, const float* target, int B, int H, int W, float* loss_out, float* ep,
+                                      float* et, float* state, float* scratch, ducosy_stream_t stream);
+int ducosy_loss_contrast_edge_backward(const float* pred, const float* ep, int B, int H, int W, const float* state,
+                                       const float* gout, float* dpred, ducosy_stream_t stream);
+/* mean SSIM (pytorch_msssim.SSIM(data_range, size_average=True, channel=1) as called at trainer.py:351,485 -- PARITY
+ * UNPINNED, the package is absent from the reference tree): tmp 5*B*H*(W-10) floats, dmaps 3*B*(H-10)*(W-10) floats */
+int ducosy_loss_ssim_forward(const float* x, const float* y, int B, int H, int W, float data_range, float* ssim_out, float* tmp,
+                             float* dmaps, float* scratch, ducosy_stream_t stream);
+int ducosy_loss_ssim_backward(const float* x, const float* y, const float* dmaps, int B, int H, int W, const float* gout, float* tmp,
+                              float* dx, ducosy_stream_t stream);
 
 /* ---------------------------------------------------------------- backward building blocks (training-step rows, in progress)
  *

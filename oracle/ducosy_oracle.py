@@ -219,6 +219,15 @@ def dewindow_to_stored(y: np.ndarray, slope, intercept, hu_min, hu_max, dtype=np
     return new_px.astype(dtype)
 
 
+def apply_windowing(y, hu_min, hu_max, window_center, window_width):
+    """apply_windowing, modules/preprocess.py:58-65 (display windowing of a tanh-range tensor, used for the validation
+    JPEGs at modules/trainer.py:276-278): de-window, clamp to [wc - ww/2, wc + ww/2], scale to [0, 1]."""
+    t = torch.as_tensor(y, dtype=torch.float32)
+    hu = (t + 1.0) / 2.0 * (hu_max - hu_min) + hu_min
+    lo, hi = window_center - window_width / 2.0, window_center + window_width / 2.0
+    return ((torch.clamp(hu, lo, hi) - lo) / window_width).numpy()
+
+
 def composite(raw_px, soft_px, lung_px, slope, intercept, soft_hu=SOFT_HU, lung_hu=LUNG_HU):
     """generate.py:213-237: start from the NCCT stored values, overwrite the soft-tissue HU range
     with the soft-tissue generator's pixels, then the lung range with the lung generator's

@@ -145,6 +145,9 @@ def main():
         hu_out[f"y_{ci}"] = yt.numpy()
         hu_out[f"post_soft_{ci}"] = ref_pre.postprocess_tensor(yt, dcm, -150, 250)
         hu_out[f"post_lung_{ci}"] = ref_pre.postprocess_tensor(yt, dcm, -1000, -150)
+        # apply_windowing (display windowing, reference argmanager.py:126-127,143-144 window settings)
+        hu_out[f"disp_soft_{ci}"] = ref_pre.apply_windowing(yt, types.SimpleNamespace(hu_min=-150, hu_max=250, window_center=40, window_width=400)).numpy()
+        hu_out[f"disp_lung_{ci}"] = ref_pre.apply_windowing(yt, types.SimpleNamespace(hu_min=-1000, hu_max=-150, window_center=-600, window_width=1500)).numpy()
         hu_out[f"slope_{ci}"] = slope
         hu_out[f"intercept_{ci}"] = intercept
     np.savez_compressed(os.path.join(OUT, "hu_window.npz"), **hu_out)

@@ -344,3 +344,18 @@ def test_conv2d_wgrad_with_padded_dy(ops):
     ref = w0.grad.permute(0, 2, 3, 1).reshape(Cout, 16 * Cin)
     err = (dw - ref).abs().max().item()
     assert err <= 2e-3 * ref.abs().max().item() + 1e-2, (err, ref.abs().max().item())
+
+
+def test_soft_squeeze_window_and_display_windowing(ops):
+    px = orc.synthetic_volume(2, 64, 96, seed=101)
+    d = torch.from_numpy(px).cuda()
+    for lo, hi in ((-150, 250), (-1000, -150)):
+        got = ops.hu_window_soft(d, 1.0, -1024.0, lo, hi).cpu().numpy()
+        ref = orc.soft_squeeze_window(px, 1.0, -1024.0, lo, hi)
+        assert np.abs(got - ref).max() <= 2.4e-7          # same fp32 steps; exp() may differ by one ulp of the result
+        below = ref < 2 * 0.9 - 1 - 1e-6                   # the linear part of the curve is bit-exact
+        assert np.array_equal(got[below], ref[below].astype(np.float32))
+    y = torch.from_numpy(np.random.Generator(np.random.PCG64(5)).uniform(-1, 1, size=(2, 1, 64, 64)).astype(np.float32))
+    for lo, hi, wc, ww in ((-150, 250, 40, 400), (-1000, -150, -600, 1500)):
+        got = ops.apply_windowing(y.cuda(), lo, hi, wc, ww).cpu().numpy()
+        assert np.array_equal(got, orc.apply_windowing(y.numpy(), lo, hi, wc, ww))

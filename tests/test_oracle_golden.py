@@ -73,6 +73,8 @@ def test_hu_window_and_dewindow_bit_exact(golden_dir):
         pl = orc.dewindow_to_stored(y, slope, intercept, -1000, -150, np.int16)
         assert np.array_equal(ps, g[f"post_soft_{ci}"])
         assert np.array_equal(pl, g[f"post_lung_{ci}"])
+        assert np.array_equal(orc.apply_windowing(g[f"y_{ci}"], -150, 250, 40, 400), g[f"disp_soft_{ci}"])
+        assert np.array_equal(orc.apply_windowing(g[f"y_{ci}"], -1000, -150, -600, 1500), g[f"disp_lung_{ci}"])
 
 
 def test_composite_bit_exact(golden_dir):
