@@ -81,6 +81,9 @@ SIGNATURES = {
     "ducosy_in_backward_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_dgrad_s2_weight": (_i, [_p, _p, _i, _i, _i, _p]),
     "ducosy_conv4x4s2_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_dgrad_s1_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_conv3x3s1_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pad_fold": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_grad_scale": (_i, [_p, _ll, _p, _p]),
     "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

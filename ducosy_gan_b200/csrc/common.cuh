@@ -49,6 +49,7 @@ struct ConvGemmArgs {
   int out_rs, out_ps;      // elements per output row / pixel
   int oy_mul, ox_mul;      // GEMM-grid (y,x) -> output (y*oy_mul+oy_off, x*ox_mul+ox_off)
   int8_t oy_off[kMaxPhases], ox_off[kMaxPhases];
+  int out_rows, out_y_off, out_x_off;   // output storage: rows per sample (in units of oy_mul rows) and tile offsets
   float* partials;         // [B][tiles_per_sample][3][Cout] (sum, sum of squares, max) or nullptr
   const float* bias;       // optional per-channel bias (epilogue mode 1)
   int epi_mode;            // 0: raw output + statistics, 1: bias + LeakyReLU(0.2), no statistics
@@ -68,6 +69,7 @@ struct ConvPlan {
   int Ho, Wo;              // output image
   int oy_mul, ox_mul;
   int8_t oy_off[kMaxPhases], ox_off[kMaxPhases];
+  int out_y_off, out_x_off;  // the GEMM grid may be written at an offset inside a larger output image (Ho x Wo)
   float* partials;
   const float* bias;
   int epi_mode;

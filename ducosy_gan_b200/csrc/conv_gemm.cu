@@ -261,7 +261,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int n = tc.nb * kN + sb * 64;
           const int f = n / a.Cstore;  // merged phases: column block -> output phase; otherwise 0
           tma_store_5d(&tmO, otile + sb * C::kSlabBytes, n - f * a.Cstore, a.fold > 1 ? (f & 1) : a.ox_off[tc.phase],
-                       tc.tx * a.Wt, a.fold > 1 ? (f >> 1) : a.oy_off[tc.phase], (tc.b * a.TY + tc.ty) * a.R);
+                       tc.tx * a.Wt + a.out_x_off, a.fold > 1 ? (f >> 1) : a.oy_off[tc.phase],
+                       tc.b * a.out_rows + tc.ty * a.R + a.out_y_off);
         }
         tma_store_commit();
       }
@@ -425,6 +426,12 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.out_ps = a.Cstore;
   a.oy_mul = p.oy_mul;
   a.ox_mul = p.ox_mul;
+  a.out_rows = p.Ho / p.oy_mul;
+  a.out_y_off = p.out_y_off;
+  a.out_x_off = p.out_x_off;
+  DUCOSY_CHECK(p.out_y_off >= 0 && p.out_x_off >= 0 && (p.Hg + p.out_y_off) * p.oy_mul <= p.Ho &&
+                   (p.Wg + p.out_x_off) * p.ox_mul <= p.Wo,
+               DUCOSY_ERR_SHAPE, "conv_gemm: GEMM grid does not fit the output image");
   a.partials = p.partials;
   a.bias = p.bias;
   a.epi_mode = p.epi_mode;

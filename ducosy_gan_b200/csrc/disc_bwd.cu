@@ -166,6 +166,90 @@ __global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __re
   }
 }
 
+// ------------------------------------------------------------------ 3x3 stride-1 input gradient
+// Wd[c][(r*3+s)*Co + o] = W[o][c][r][s]
+template <typename T>
+__global__ void pack_dgrad_s1_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+  const long long total = 9LL * Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = int(i % Co);
+    long long r = i / Co;
+    const int tap = int(r % 9);
+    const int c = int(r / 9);
+    out[i] = Cvt<T>::from_f(w[((long long)o * Ci + c) * 9 + tap]);
+  }
+}
+// the two outer columns of the padded-input gradient (v = 0 uses filter column s = 0, v = W+1 uses s = 2):
+//   dxpad[u][v][c] = sum_{r,o} dy[u-r][v-s][o] * W[o][c][r][s]     (dy_pad2 has a zero border of 2)
+template <typename T>
+__global__ void dgrad_s1_edge_cols_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H,
+                                          int W, int Ci, int Co) {
+  const long long total = (long long)B * (H + 2) * 2 * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c = int(i % Ci);
+    long long q = i / Ci;
+    const int side = int(q & 1);
+    q >>= 1;
+    const int u = int(q % (H + 2));
+    const int b = int(q / (H + 2));
+    const int v = side ? W + 1 : 0, s = side ? 2 : 0;
+    float acc = 0.f;
+    for (int r = 0; r < 3; ++r) {
+      const T* d = dy_pad2 + (((long long)b * (H + 4) + (u - r + 2)) * (W + 4) + (v - s + 2)) * Co;
+      const T* wv = wd + ((long long)c * 9 + r * 3 + s) * Co;
+      for (int o = 0; o < Co; o += 8) {
+        const uint4 dv = *reinterpret_cast<const uint4*>(d + o), kv = *reinterpret_cast<const uint4*>(wv + o);
+        const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w}, kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = Cvt<T>::unpack2(dw[k]), w2 = Cvt<T>::unpack2(kw[k]);
+          acc = fmaf(a.x, w2.x, acc);
+          acc = fmaf(a.y, w2.y, acc);
+        }
+      }
+    }
+    dxpad[(((long long)b * (H + 2) + u) * (W + 2) + v) * Ci + c] = Cvt<T>::from_f(acc);
+  }
+}
+// adjoint of the padding: gradient w.r.t. the padded map [B][H+2p][W+2p][C] -> gradient w.r.t. the un-padded map
+template <typename T>
+__global__ void pad_fold_kernel(const T* __restrict__ dxpad, T* __restrict__ dx, int B, int H, int W, int C, int pad, int mode) {
+  const int cv = C / 8, Hp = H + 2 * pad, Wp = W + 2 * pad;
+  const long long total = (long long)B * H * W * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % cv);
+    long long r = i / cv;
+    const int x = int(r % W);
+    r /= W;
+    const int y = int(r % H);
+    const int b = int(r / H);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // padded rows / cols that reflect onto (y, x): p -> |p - pad| on the low side, 2(n-1) - (p - pad) on the high side
+    int rows[3], cols[3], nr = 0, nc = 0;
+    rows[nr++] = y + pad;
+    cols[nc++] = x + pad;
+    if (mode == DUCOSY_PAD_REFLECT) {
+      if (y >= 1 && y <= pad) rows[nr++] = pad - y;
+      if (y <= H - 2 && y >= H - 1 - pad) rows[nr++] = pad + 2 * (H - 1) - y;
+      if (x >= 1 && x <= pad) cols[nc++] = pad - x;
+      if (x <= W - 2 && x >= W - 1 - pad) cols[nc++] = pad + 2 * (W - 1) - x;
+    }
+    for (int a = 0; a < nr; ++a)
+      for (int bb = 0; bb < nc; ++bb) {
+        const uint4 v = reinterpret_cast<const uint4*>(dxpad)[(((long long)b * Hp + rows[a]) * Wp + cols[bb]) * cv + c8];
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 f = Cvt<T>::unpack2(w4[k]);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
+        }
+      }
+    reinterpret_cast<uint4*>(dx)[i] = make_uint4(Cvt<T>::pack2(acc[0], acc[1]), Cvt<T>::pack2(acc[2], acc[3]),
+                                                 Cvt<T>::pack2(acc[4], acc[5]), Cvt<T>::pack2(acc[6], acc[7]));
+  }
+}
+
 // packed fp32 weight gradient [Co][taps*Ci + c] -> OIHW [Co][Ci][taps]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps,
                                     const float* __restrict__ gs) {
@@ -414,4 +498,50 @@ extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const
     return check_launch("disc_first_dgrad_kernel");
   }
   return 0;
+}
+
+extern "C" int ducosy_pack_dgrad_s1_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_dgrad_s1_weight: bad argument");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_dgrad_s1_weight_kernel<T><<<grid_for_items(9LL * Cout * Cin, 256), 256, 0,
+                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+  return check_launch("pack_dgrad_s1_weight_kernel");
+}
+
+// Gradient w.r.t. the PADDED input of a 3x3 stride-1 conv: dy_pad2 [B][H+4][W+4][Cout] (zero border 2) ->
+// dxpad [B][H+2][W+2][Cin].  Columns 1..W on the tensor cores (implicit GEMM over the H+2 rows), the two outer columns
+// on CUDA cores.  Follow with ducosy_pad_fold for the gradient of the un-padded map.
+extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* dxpad, int B, int H, int W, int Cin,
+                                           int Cout, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(dy_pad2 && w_dgrad && dxpad && B > 0, DUCOSY_ERR_ARG, "conv3x3s1_dgrad: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv3x3s1_dgrad: bad dtype");
+  DUCOSY_CHECK(Cout % 64 == 0 && Cin % 64 == 0, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: channels must be multiples of 64");
+  DUCOSY_CHECK(W % 128 == 0, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: W must be a multiple of 128 (the H+2 padded rows are tiled row by row)");
+  DUCOSY_TRY(ducosy_check_device());
+  ConvPlan p{};
+  p.in = dy_pad2; p.B = B; p.Hp = H + 4; p.Wp = W + 4; p.Cin = Cout; p.stride = 1;
+  p.w = w_dgrad; p.Cout = Cin; p.num_phases = 1; p.num_taps = 9;
+  for (int r = 0; r < 3; ++r)
+    for (int s = 0; s < 3; ++s) {
+      p.tap_dy[0][r * 3 + s] = int8_t(2 - r);   // dxpad[u][v'+1] reads dy_pad2[u + 2 - r][v' + 3 - s]
+      p.tap_dx[0][r * 3 + s] = int8_t(3 - s);
+    }
+  p.Hg = H + 2; p.Wg = W; p.out = dxpad; p.Ho = H + 2; p.Wo = W + 2; p.oy_mul = p.ox_mul = 1;
+  p.out_y_off = 0; p.out_x_off = 1;
+  p.partials = nullptr; p.dtype = dtype;
+  DUCOSY_TRY(launch_conv_gemm(p, static_cast<cudaStream_t>(stream)));
+  const long long total = (long long)B * (H + 2) * 2 * Cin;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols_kernel<T><<<grid_for_items(total, 128), 128, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,
+                                      Cin, Cout)));
+  return check_launch("dgrad_s1_edge_cols_kernel");
+}
+
+// Adjoint of ReflectionPad2d(pad) / zero padding: dxpad [B][H+2p][W+2p][C] -> dx [B][H][W][C] (16-bit NHWC).
+extern "C" int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
+                               ducosy_stream_t stream) {
+  DUCOSY_CHECK(dxpad && dx && B > 0 && C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_ARG, "pad_fold: bad argument");
+  const long long total = (long long)B * H * W * (C / 8);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pad_fold_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(dxpad), static_cast<T*>(dx), B, H, W, C, pad, pad_mode)));
+  return check_launch("pad_fold_kernel");
 }

@@ -318,3 +318,21 @@ def apply_windowing(y, hu_lo, hu_hi, window_center, window_width):
         call("ducosy_apply_windowing", ptr(y), ptr(out), y.numel(), float(hu_lo), float(hu_hi), float(window_center),
              float(window_width), stream_ptr())
     return out
+
+
+def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode):
+    """Input gradient of pad(1) + Conv2d(3x3): dy_pad2 [B,H+4,W+4,Cout] (zero border 2) -> dx [B,H,W,Cin] after folding
+    the padding adjoint (reflect or zero)."""
+    Cout, Cin = w_oihw.shape[:2]
+    B, Hp, Wp, _ = dy_pad2.shape
+    H, W = Hp - 4, Wp - 4
+    w = w_oihw.detach().to(torch.float32).contiguous()
+    dc = dtype_code(dy_pad2.dtype)
+    with _dev(dy_pad2):
+        wd = torch.empty((Cin, 9 * Cout), dtype=dy_pad2.dtype, device=dy_pad2.device)
+        call("ducosy_pack_dgrad_s1_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+        dxpad = torch.empty((B, H + 2, W + 2, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
+        call("ducosy_conv3x3s1_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dxpad), B, H, W, Cin, Cout, dc, stream_ptr())
+        dx = torch.empty((B, H, W, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
+        call("ducosy_pad_fold", ptr(dxpad), ptr(dx), B, H, W, Cin, 1, pad_mode, dc, stream_ptr())
+    return dx, dxpad

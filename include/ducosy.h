@@ -255,6 +255,14 @@ int ducosy_conv4x4s2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* d
  * The functions below take `gs` (device pointer, NULL = no scaling): dgrad entry points multiply by gs[0], the fp32
  * parameter / input gradients are multiplied by gs[1]. */
 int ducosy_grad_scale(const float* g, long long n, float* gs, ducosy_stream_t stream);
+/* Input gradient of the 3x3 stride-1 convs (modules/model.py:60-62,73-79) w.r.t. their PADDED input: dy_pad2
+ * [B][H+4][W+4][Cout] (zero border 2) -> dxpad [B][H+2][W+2][Cin]; w_dgrad [Cin][9*Cout] from ducosy_pack_dgrad_s1_weight.
+ * ducosy_pad_fold is the adjoint of ReflectionPad2d / zero padding: dxpad -> dx [B][H][W][C]. */
+int ducosy_pack_dgrad_s1_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
+int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* dxpad, int B, int H, int W, int Cin, int Cout,
+                                int dtype, ducosy_stream_t stream);
+int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
+                    ducosy_stream_t stream);
 /* packed fp32 weight gradient [Cout][taps*Cin] -> OIHW [Cout][Cin][taps] (times gs[1]). */
 int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
                         ducosy_stream_t stream);

@@ -359,3 +359,22 @@ def test_soft_squeeze_window_and_display_windowing(ops):
     for lo, hi, wc, ww in ((-150, 250, 40, 400), (-1000, -150, -600, 1500)):
         got = ops.apply_windowing(y.cuda(), lo, hi, wc, ww).cpu().numpy()
         assert np.array_equal(got, orc.apply_windowing(y.numpy(), lo, hi, wc, ww))
+
+
+@pytest.mark.parametrize("mode", ["reflect", "zero"])
+@pytest.mark.parametrize("case", [(2, 32, 128, 256, 256), (1, 16, 128, 128, 64), (1, 8, 256, 64, 128)])
+def test_conv3x3s1_dgrad_with_pad_fold(ops, case, mode):
+    B, H, W, Cin, Cout = case
+    dtype = torch.float16
+    dy = _rand((B, Cout, H, W), 111).to(dtype)
+    w = _rand((Cout, Cin, 3, 3), 112, 0.05).to(dtype).float()
+    dyp = F.pad(dy.float(), (2, 2, 2, 2)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dx, dxpad = ops.conv3x3s1_dgrad(dyp, w.cuda(), ops.PAD_REFLECT if mode == "reflect" else ops.PAD_ZERO)
+    x0 = torch.zeros((B, Cin, H, W), device="cuda", requires_grad=True)
+    xp = F.pad(x0, (1, 1, 1, 1), mode="reflect" if mode == "reflect" else "constant")
+    xp.retain_grad()
+    F.conv2d(xp, w.cuda()).backward(dy.float().cuda())
+    ref_pad, ref = xp.grad, x0.grad
+    tol = 2e-3 * ref_pad.abs().max().item() + 1e-2
+    assert (dxpad.float().permute(0, 3, 1, 2) - ref_pad).abs().max().item() <= tol       # incl. the two CUDA-core columns
+    assert (dx.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2 * tol
