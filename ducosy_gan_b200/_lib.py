@@ -79,11 +79,14 @@ SIGNATURES = {
     "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_in_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ducosy_in_backward_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
-    "ducosy_pack_dgrad_s2_weight": (_i, [_p, _p, _i, _i, _i, _p]),
-    "ducosy_conv4x4s2_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_dgrad_s2_weight": (_i, [_p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_convs2_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_dgrad_s1_weight": (_i, [_p, _p, _i, _i, _i, _p]),
     "ducosy_conv3x3s1_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pad_fold": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pack_upconv_dgrad_weight": (_i, [_p, _p, _i, _i, _i, _p]),
+    "ducosy_upconv2x_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_upsample2x_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_grad_scale": (_i, [_p, _ll, _p, _p]),
     "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -179,9 +179,9 @@ extern "C" int ducosy_discriminator_pack(const float* const* params, int num_par
   DUCOSY_TRY(ducosy_pack_conv_weight(params[6], pk + L.w4, 512, 256, 4, 4, dtype, stream));
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_disc_last_weight_kernel<T><<<32, 256, 0, st>>>(params[8], reinterpret_cast<T*>(pk + L.w5))));
   cudaMemcpyAsync(pk + L.b5, params[9], 4, cudaMemcpyDeviceToDevice, st);
-  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[2], pk + L.wd2, 128, 64, dtype, stream));
-  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[4], pk + L.wd3, 256, 128, dtype, stream));
-  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[6], pk + L.wd4, 512, 256, dtype, stream));
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[2], pk + L.wd2, 128, 64, 4, dtype, stream));
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[4], pk + L.wd3, 256, 128, 4, dtype, stream));
+  DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[6], pk + L.wd4, 512, 256, 4, dtype, stream));
   return check_launch("discriminator_pack");
 }
 
@@ -317,7 +317,7 @@ extern "C" int ducosy_discriminator_backward(const void* packed, const float* x,
     DUCOSY_TRY(ducosy_unpack_wgrad(reinterpret_cast<const float*>(bb + bw.dwp), grads_host[2 + 2 * l], Cl, Cl / 2, 16, gs, stream));
     cudaMemsetAsync(grads_host[3 + 2 * l], 0, size_t(Cl) * 4, st);
     // input gradient (tensor cores): grad wrt the previous activation map
-    DUCOSY_TRY(ducosy_conv4x4s2_dgrad_nhwc(bb + bw.dyp[l], pk + wd_off[l], bb + bw.da[l], B, Hl, Wl, Cl / 2, Cl, dtype, stream));
+    DUCOSY_TRY(ducosy_convs2_dgrad_nhwc(bb + bw.dyp[l], pk + wd_off[l], bb + bw.da[l], B, Hl, Wl, Cl / 2, Cl, dtype, stream));
     Hl *= 2; Wl *= 2; Cl /= 2;
   }
   // first layer

@@ -148,9 +148,10 @@ in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const
 }
 
 // ------------------------------------------------------------------ dgrad weight packing for the 4x4 stride-2 convs
-// Wd[phase*Ci + c][(a*2+b)*Co + o] = W[o][c][r(py,a)][s(px,b)],  r(0,.) = {3,1}, r(1,.) = {2,0}
+// Wd[phase*Ci + c][(a*2+b)*Co + o] = W[o][c][r(py,a)][s(px,b)]
+//   4x4 kernel: r(0,.) = {3,1}, r(1,.) = {2,0};  3x3 kernel (model.py:96-98): r(0,.) = {-,1}, r(1,.) = {2,0} (- = no tap: zero)
 template <typename T>
-__global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+__global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int ksz) {
   const long long total = 16LL * Co * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int o = int(i % Co);
@@ -162,7 +163,7 @@ __global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __re
     const int py = phase >> 1, px = phase & 1, a = tap >> 1, b = tap & 1;
     const int rr = py == 0 ? (a == 0 ? 3 : 1) : (a == 0 ? 2 : 0);
     const int ss = px == 0 ? (b == 0 ? 3 : 1) : (b == 0 ? 2 : 0);
-    out[i] = Cvt<T>::from_f(w[(((long long)o * Ci + c) * 4 + rr) * 4 + ss]);
+    out[i] = Cvt<T>::from_f((rr < ksz && ss < ksz) ? w[(((long long)o * Ci + c) * ksz + rr) * ksz + ss] : 0.f);
   }
 }
 
@@ -247,6 +248,48 @@ __global__ void pad_fold_kernel(const T* __restrict__ dxpad, T* __restrict__ dx,
       }
     reinterpret_cast<uint4*>(dx)[i] = make_uint4(Cvt<T>::pack2(acc[0], acc[1]), Cvt<T>::pack2(acc[2], acc[3]),
                                                  Cvt<T>::pack2(acc[4], acc[5]), Cvt<T>::pack2(acc[6], acc[7]));
+  }
+}
+
+// ------------------------------------------------------------------ Upsample(x2 nearest) + Conv3x3(pad 1) backward
+// forward (conv_gemm sub-pixel form): out[2i+py][2j+px] = sum_{a,b} Wp[ph][a][b] . srcpad[i+a+py][j+b+px]; its adjoint
+// gathers, for every source pixel, 16 (phase, tap) entries of the output gradient on the stride-2 sub-lattices:
+//   Wd[c][(ph*4 + a*2 + b)*Co + o] = Wp[ph][a][b][o][c]       (Wp = the pre-summed phase weights of pack_upconv_weight)
+template <typename T>
+__global__ void pack_upconv_dgrad_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+  const long long total = 16LL * Co * Ci;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int o = int(i % Co);
+    long long r = i / Co;
+    const int t16 = int(r % 16);
+    const int c = int(r / 16);
+    const int phase = t16 >> 2, a = (t16 >> 1) & 1, b = t16 & 1, py = phase >> 1, px = phase & 1;
+    const int r0 = py == 0 ? (a == 0 ? 0 : 1) : (a == 0 ? 0 : 2), r1 = py == 0 ? (a == 0 ? 0 : 2) : (a == 0 ? 1 : 2);
+    const int s0 = px == 0 ? (b == 0 ? 0 : 1) : (b == 0 ? 0 : 2), s1 = px == 0 ? (b == 0 ? 0 : 2) : (b == 0 ? 1 : 2);
+    const float* wk = w + ((long long)o * Ci + c) * 9;
+    float acc = 0.f;
+    for (int rr = r0; rr <= r1; ++rr)
+      for (int ss = s0; ss <= s1; ++ss) acc += wk[rr * 3 + ss];
+    out[i] = Cvt<T>::from_f(acc);
+  }
+}
+// nearest x2 upsampling of the (un-padded interior of the) zero-padded source + zero pad 1: the operand the weight
+// gradient needs; only the backward materialises it.
+template <typename T>
+__global__ void upsample2x_pad_kernel(const T* __restrict__ src_pad, T* __restrict__ up_pad, int B, int Hs, int Ws, int C) {
+  const int cv = C / 8, Hu = 2 * Hs + 2, Wu = 2 * Ws + 2;
+  const long long total = (long long)B * Hu * Wu * cv;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int c8 = int(i % cv);
+    long long r = i / cv;
+    const int x = int(r % Wu);
+    r /= Wu;
+    const int y = int(r % Hu);
+    const int b = int(r / Hu);
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (y >= 1 && y <= 2 * Hs && x >= 1 && x <= 2 * Ws)
+      v = reinterpret_cast<const uint4*>(src_pad)[(((long long)b * (Hs + 2) + (y - 1) / 2 + 1) * (Ws + 2) + (x - 1) / 2 + 1) * cv + c8];
+    reinterpret_cast<uint4*>(up_pad)[i] = v;
   }
 }
 
@@ -436,16 +479,16 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
   return check_launch("in_bwd_apply_pad_kernel");
 }
 
-extern "C" int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype,
+extern "C" int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int ksize, int dtype,
                                            ducosy_stream_t stream) {
-  DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_dgrad_s2_weight: bad argument");
+  DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0 && (ksize == 3 || ksize == 4), DUCOSY_ERR_ARG, "pack_dgrad_s2_weight: bad argument");
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_dgrad_s2_weight_kernel<T><<<grid_for_items(16LL * Cout * Cin, 256), 256, 0,
-                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin, ksize)));
   return check_launch("pack_dgrad_s2_weight_kernel");
 }
 
-// Input gradient of Conv2d(Cin, Cout, 4, stride 2, padding 1): dy_pad [B][Ho+2][Wo+2][Cout] (zero border) -> dx [B][2Ho][2Wo][Cin].
-extern "C" int ducosy_conv4x4s2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin,
+// Input gradient of Conv2d(Cin, Cout, 4 or 3, stride 2, padding 1): dy_pad [B][Ho+2][Wo+2][Cout] (zero border) -> dx [B][2Ho][2Wo][Cin].
+extern "C" int ducosy_convs2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin,
                                            int Cout, int dtype, ducosy_stream_t stream) {
   // four 2x2 phase convs over the padded gradient: same launch as the x2 up-conv with (Cin, Cout) swapped
   return ducosy_upconv2x_nhwc(dy_pad, w_dgrad, dx, nullptr, B, Ho, Wo, Cout, Cin, dtype, stream);
@@ -544,4 +587,41 @@ extern "C" int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W,
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pad_fold_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(dxpad), static_cast<T*>(dx), B, H, W, C, pad, pad_mode)));
   return check_launch("pad_fold_kernel");
+}
+
+extern "C" int ducosy_pack_upconv_dgrad_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_dgrad_weight: bad argument");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_dgrad_weight_kernel<T><<<grid_for_items(16LL * Cout * Cin, 256), 256, 0,
+                                                                       (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+  return check_launch("pack_upconv_dgrad_weight_kernel");
+}
+
+// Input gradient of Upsample(x2)+Conv3x3 (modules/model.py:108-109): dy_pad2 [B][2Hs+4][2Ws+4][Cout] (zero border 2) ->
+// dsrc [B][Hs][Ws][Cin]; one implicit GEMM over 16 (phase, tap) gathers with stride-2 TMA boxes.
+extern "C" int ducosy_upconv2x_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* dsrc, int B, int Hs, int Ws, int Cin,
+                                          int Cout, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(dy_pad2 && w_dgrad && dsrc && B > 0, DUCOSY_ERR_ARG, "upconv2x_dgrad: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_dgrad: bad dtype");
+  DUCOSY_TRY(ducosy_check_device());
+  ConvPlan p{};
+  p.in = dy_pad2; p.B = B; p.Hp = 2 * Hs + 4; p.Wp = 2 * Ws + 4; p.Cin = Cout; p.stride = 2;
+  p.w = w_dgrad; p.Cout = Cin; p.num_phases = 1; p.num_taps = 16;
+  for (int t16 = 0; t16 < 16; ++t16) {
+    const int phase = t16 >> 2, a = (t16 >> 1) & 1, b = t16 & 1, py = phase >> 1, px = phase & 1;
+    p.tap_dy[0][t16] = int8_t(2 * (2 - a - py) + py);   // padded-by-2 pixel row of dY[2(i+1-a-py)+py] relative to 2i
+    p.tap_dx[0][t16] = int8_t(2 * (2 - b - px) + px);
+  }
+  p.Hg = Hs; p.Wg = Ws; p.out = dsrc; p.Ho = Hs; p.Wo = Ws; p.oy_mul = p.ox_mul = 1;
+  p.partials = nullptr; p.dtype = dtype;
+  return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+// up_pad [B][2Hs+2][2Ws+2][C] = zero-pad-1(nearest-x2(interior of src_pad [B][Hs+2][Ws+2][C])): x operand of the weight
+// gradient of Upsample(x2)+Conv3x3 (then ducosy_conv2d_wgrad_nhwc(up_pad, dy, ..., 3, 3, 1)).
+extern "C" int ducosy_upsample2x_pad(const void* src_pad, void* up_pad, int B, int Hs, int Ws, int C, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(src_pad && up_pad && B > 0 && C % 8 == 0, DUCOSY_ERR_ARG, "upsample2x_pad: bad argument");
+  const long long total = (long long)B * (2 * Hs + 2) * (2 * Ws + 2) * (C / 8);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (upsample2x_pad_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(src_pad), static_cast<T*>(up_pad), B, Hs, Ws, C)));
+  return check_launch("upsample2x_pad_kernel");
 }

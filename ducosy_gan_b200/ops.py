@@ -286,16 +286,16 @@ def in_backward_pad(da, y, scale, shift, pad, act):
     return out
 
 
-def conv4x4s2_dgrad_nhwc(dy_pad, w_oihw):
-    """Input gradient of Conv2d(Cin,Cout,4,stride 2,padding 1): dy_pad [B,Ho+2,Wo+2,Cout] -> dx [B,2Ho,2Wo,Cin]."""
-    Cout, Cin = w_oihw.shape[:2]
+def convs2_dgrad_nhwc(dy_pad, w_oihw):
+    """Input gradient of Conv2d(Cin,Cout,k,stride 2,padding 1), k in {3,4}: dy_pad [B,Ho+2,Wo+2,Cout] -> dx [B,2Ho,2Wo,Cin]."""
+    Cout, Cin, ksz = w_oihw.shape[:3]
     B, Hp, Wp, _ = dy_pad.shape
     w = w_oihw.detach().to(torch.float32).contiguous()
     with _dev(dy_pad):
         wd = torch.empty((4 * Cin, 4 * Cout), dtype=dy_pad.dtype, device=dy_pad.device)
-        call("ducosy_pack_dgrad_s2_weight", ptr(w), ptr(wd), Cout, Cin, dtype_code(dy_pad.dtype), stream_ptr())
+        call("ducosy_pack_dgrad_s2_weight", ptr(w), ptr(wd), Cout, Cin, int(ksz), dtype_code(dy_pad.dtype), stream_ptr())
         dx = torch.empty((B, 2 * (Hp - 2), 2 * (Wp - 2), Cin), dtype=dy_pad.dtype, device=dy_pad.device)
-        call("ducosy_conv4x4s2_dgrad_nhwc", ptr(dy_pad), ptr(wd), ptr(dx), B, Hp - 2, Wp - 2, Cin, Cout, dtype_code(dy_pad.dtype),
+        call("ducosy_convs2_dgrad_nhwc", ptr(dy_pad), ptr(wd), ptr(dx), B, Hp - 2, Wp - 2, Cin, Cout, dtype_code(dy_pad.dtype),
              stream_ptr())
     return dx
 
@@ -336,3 +336,24 @@ def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode):
         dx = torch.empty((B, H, W, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
         call("ducosy_pad_fold", ptr(dxpad), ptr(dx), B, H, W, Cin, 1, pad_mode, dc, stream_ptr())
     return dx, dxpad
+
+
+def upconv2x_backward(src_pad, dy_pad2, w_oihw):
+    """Backward of Upsample(x2)+Conv3x3(pad 1): src_pad [B,Hs+2,Ws+2,Cin] (zero border), dy_pad2 [B,2Hs+4,2Ws+4,Cout]
+    (zero border 2) -> (dsrc [B,Hs,Ws,Cin], dW fp32 OIHW [Cout,Cin,3,3])."""
+    Cout, Cin = w_oihw.shape[:2]
+    B, Hp, Wp, _ = src_pad.shape
+    Hs, Ws = Hp - 2, Wp - 2
+    dt, dc = src_pad.dtype, dtype_code(src_pad.dtype)
+    w = w_oihw.detach().to(torch.float32).contiguous()
+    with _dev(src_pad):
+        wd = torch.empty((Cin, 16 * Cout), dtype=dt, device=src_pad.device)
+        call("ducosy_pack_upconv_dgrad_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+        dsrc = torch.empty((B, Hs, Ws, Cin), dtype=dt, device=src_pad.device)
+        call("ducosy_upconv2x_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dsrc), B, Hs, Ws, Cin, Cout, dc, stream_ptr())
+        up = torch.empty((B, 2 * Hs + 2, 2 * Ws + 2, Cin), dtype=dt, device=src_pad.device)
+        call("ducosy_upsample2x_pad", ptr(src_pad), ptr(up), B, Hs, Ws, Cin, dc, stream_ptr())
+        dwp = conv2d_wgrad_nhwc(up, dy_pad2, 3, 3, 1, dy_pad=2)
+        dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=src_pad.device)
+        call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, 9, None, stream_ptr())
+    return dsrc, dw

@@ -246,11 +246,13 @@ int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, floa
 size_t ducosy_in_backward_scratch_bytes(int B, int H, int W, int C);
 int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad, float* scratch,
                            int B, int H, int W, int C, int pad, int act, int dtype, ducosy_stream_t stream);
-/* Input gradient of Conv2d(Cin, Cout, 4, stride 2, padding 1) as four 2x2 phase convolutions over the zero-padded output
- * gradient dy_pad [B][Ho+2][Wo+2][Cout] -> dx [B][2Ho][2Wo][Cin]; w_dgrad from ducosy_pack_dgrad_s2_weight ([4*Cin][4*Cout]). */
-int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
-int ducosy_conv4x4s2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin, int Cout,
-                                int dtype, ducosy_stream_t stream);
+/* Input gradient of Conv2d(Cin, Cout, k, stride 2, padding 1), k = 4 (PatchGAN) or 3 (generator down convs,
+ * modules/model.py:96-98), as four 2x2 phase convolutions over the zero-padded output gradient dy_pad [B][Ho+2][Wo+2][Cout]
+ * -> dx [B][2Ho][2Wo][Cin]; w_dgrad from ducosy_pack_dgrad_s2_weight ([4*Cin][4*Cout], zero taps where k = 3 has none). */
+int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int ksize, int dtype,
+                                ducosy_stream_t stream);
+int ducosy_convs2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad, void* dx, int B, int Ho, int Wo, int Cin, int Cout,
+                             int dtype, ducosy_stream_t stream);
 /* Power-of-two scaling of a loss gradient for the 16-bit backward maps: gs[0] = 2^e with max|g|*2^e in [1,2), gs[1] = 2^-e.
  * The functions below take `gs` (device pointer, NULL = no scaling): dgrad entry points multiply by gs[0], the fp32
  * parameter / input gradients are multiplied by gs[1]. */
@@ -263,6 +265,13 @@ int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* 
                                 int dtype, ducosy_stream_t stream);
 int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
                     ducosy_stream_t stream);
+/* Backward of Upsample(x2 nearest)+Conv3x3(pad 1) (modules/model.py:108-109): input gradient dy_pad2 [B][2Hs+4][2Ws+4][Cout]
+ * (zero border 2) -> dsrc [B][Hs][Ws][Cin] with w_dgrad [Cin][16*Cout] from ducosy_pack_upconv_dgrad_weight; for the weight
+ * gradient materialise the upsampled, zero-padded source with ducosy_upsample2x_pad and call ducosy_conv2d_wgrad_nhwc (3x3, s1). */
+int ducosy_pack_upconv_dgrad_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream);
+int ducosy_upconv2x_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* dsrc, int B, int Hs, int Ws, int Cin, int Cout,
+                               int dtype, ducosy_stream_t stream);
+int ducosy_upsample2x_pad(const void* src_pad, void* up_pad, int B, int Hs, int Ws, int C, int dtype, ducosy_stream_t stream);
 /* packed fp32 weight gradient [Cout][taps*Cin] -> OIHW [Cout][Cin][taps] (times gs[1]). */
 int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
                         ducosy_stream_t stream);

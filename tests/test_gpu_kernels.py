@@ -316,14 +316,14 @@ def test_in_backward_matches_autograd(ops):
         assert err < 4e-3 * max(1.0, ref.abs().max().item()), (act, err, ref.abs().max().item())
 
 
-@pytest.mark.parametrize("case", [(2, 16, 16, 256, 512), (1, 32, 64, 64, 128)])
-def test_conv4x4s2_dgrad_matches_autograd(ops, case):
-    B, Ho, Wo, Cin, Cout = case
+@pytest.mark.parametrize("case", [(2, 16, 16, 256, 512, 4), (1, 32, 64, 64, 128, 4), (2, 32, 32, 128, 256, 3), (1, 16, 64, 64, 128, 3)])
+def test_stride2_dgrad_matches_autograd(ops, case):
+    B, Ho, Wo, Cin, Cout, ksz = case
     dtype = torch.float16
     dy = _rand((B, Cout, Ho, Wo), 93).to(dtype)
-    w = (_rand((Cout, Cin, 4, 4), 94, 0.05)).to(dtype).float()
+    w = (_rand((Cout, Cin, ksz, ksz), 94, 0.05)).to(dtype).float()
     dyp = F.pad(dy.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
-    dx = ops.conv4x4s2_dgrad_nhwc(dyp, w.cuda())
+    dx = ops.convs2_dgrad_nhwc(dyp, w.cuda())
     x0 = torch.zeros((B, Cin, 2 * Ho, 2 * Wo), device="cuda", requires_grad=True)
     F.conv2d(x0, w.cuda(), stride=2, padding=1).backward(dy.float().cuda())
     ref = x0.grad
@@ -378,3 +378,20 @@ def test_conv3x3s1_dgrad_with_pad_fold(ops, case, mode):
     tol = 2e-3 * ref_pad.abs().max().item() + 1e-2
     assert (dxpad.float().permute(0, 3, 1, 2) - ref_pad).abs().max().item() <= tol       # incl. the two CUDA-core columns
     assert (dx.float().permute(0, 3, 1, 2) - ref).abs().max().item() <= 2 * tol
+
+
+@pytest.mark.parametrize("case", [(2, 32, 32, 256, 128), (1, 16, 64, 128, 128)])
+def test_upconv2x_backward_matches_autograd(ops, case):
+    B, Hs, Ws, Cin, Cout = case
+    dtype = torch.float16
+    x = _rand((B, Cin, Hs, Ws), 121).to(dtype)
+    dy = _rand((B, Cout, 2 * Hs, 2 * Ws), 122).to(dtype)
+    w = _rand((Cout, Cin, 3, 3), 123, 0.05)
+    xp = F.pad(x.float(), (1, 1, 1, 1)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dyp = F.pad(dy.float(), (2, 2, 2, 2)).permute(0, 2, 3, 1).contiguous().to(dtype).cuda()
+    dsrc, dw = ops.upconv2x_backward(xp, dyp, w.cuda())
+    xr = x.float().cuda().requires_grad_(True)
+    wr = w.cuda().requires_grad_(True)
+    F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), wr, padding=1).backward(dy.float().cuda())
+    assert (dsrc.float().permute(0, 3, 1, 2) - xr.grad).abs().max().item() <= 4e-3 * xr.grad.abs().max().item() + 1e-2
+    assert (dw - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item() + 1e-2
