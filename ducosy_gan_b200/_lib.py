@@ -89,7 +89,8 @@ SIGNATURES = {
     "ducosy_upsample2x_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_grad_scale": (_i, [_p, _ll, _p, _p]),
     "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
-    "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_disc_last_backward_scratch_bytes": (_sz, []),
+    "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ducosy_disc_first_backward_scratch_bytes": (_sz, [_i, _i, _i]),
     "ducosy_disc_first_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ducosy_discriminator_backward_workspace_bytes": (_sz, [_i, _i, _i]),

@@ -16,9 +16,9 @@ namespace {
 template <typename T>
 __global__ void disc_first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][16]*/,
                                        const float* __restrict__ bias, T* __restrict__ out, int B, int H, int W) {
-  __shared__ float sw[64 * 16];
+  __shared__ __align__(16) float sw[16 * 64];  // [tap][channel]: a thread's 8 channels are two conflict-free float4 reads
   __shared__ float sb[64];
-  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[i] = w[i];
+  for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[(i & 15) * 64 + (i >> 4)] = w[i];
   for (int i = threadIdx.x; i < 64; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   const int Ho = H / 2, Wo = W / 2, Hp = Ho + 2, Wp = Wo + 2;
@@ -43,13 +43,16 @@ __global__ void disc_first_conv_kernel(const float* __restrict__ x, const float*
         }
       float v[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int c = c8 * 8 + j;
-        float acc = sb[c];
+      for (int j = 0; j < 8; ++j) v[j] = sb[c8 * 8 + j];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) acc = fmaf(in[k], sw[c * 16 + k], acc);
-        v[j] = acc > 0.f ? acc : 0.2f * acc;
+      for (int k = 0; k < 16; ++k) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&sw[k * 64 + c8 * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&sw[k * 64 + c8 * 8 + 4]);
+        v[0] = fmaf(in[k], w0.x, v[0]); v[1] = fmaf(in[k], w0.y, v[1]); v[2] = fmaf(in[k], w0.z, v[2]); v[3] = fmaf(in[k], w0.w, v[3]);
+        v[4] = fmaf(in[k], w1.x, v[4]); v[5] = fmaf(in[k], w1.y, v[5]); v[6] = fmaf(in[k], w1.z, v[6]); v[7] = fmaf(in[k], w1.w, v[7]);
       }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = v[j] > 0.f ? v[j] : 0.2f * v[j];
       o = make_uint4(Cvt<T>::pack2(v[0], v[1]), Cvt<T>::pack2(v[2], v[3]), Cvt<T>::pack2(v[4], v[5]), Cvt<T>::pack2(v[6], v[7]));
     }
     reinterpret_cast<uint4*>(out)[i] = o;
@@ -244,7 +247,7 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
 namespace ducosy {
 namespace {
 struct DiscBwdWorkspace {
-  size_t da[4], dyp[3], in_scratch, wg_ws, dwp, first_scratch, gs, total;   // da[l]: grad wrt the activation after layer l+1
+  size_t da[4], dyp[3], in_scratch, wg_ws, dwp, first_scratch, last_scratch, gs, total;   // da[l]: grad wrt the activation after layer l+1
 };
 DiscBwdWorkspace make_disc_bwd_workspace(int B, int H, int W) {
   DiscBwdWorkspace w{};
@@ -265,6 +268,7 @@ DiscBwdWorkspace make_disc_bwd_workspace(int B, int H, int W) {
   w.wg_ws = take(wg_max);
   w.dwp = take(size_t(512) * 16 * 256 * 4);
   w.first_scratch = take(ducosy_disc_first_backward_scratch_bytes(B, H, W));
+  w.last_scratch = take(ducosy_disc_last_backward_scratch_bytes());
   w.gs = take(16);
   w.total = off;
   return w;
@@ -301,7 +305,8 @@ extern "C" int ducosy_discriminator_backward(const void* packed, const float* x,
   float* gs = reinterpret_cast<float*>(bb + bw.gs);
   DUCOSY_TRY(ducosy_grad_scale(dout, (long long)B * H4 * W4, gs, stream));
   // last layer: grad wrt a4 (the LeakyReLU(IN(.)) map) + its weight / bias gradients
-  DUCOSY_TRY(ducosy_disc_last_backward(dout, pk + L.w5, fb + fw.p4, bb + bw.da[3], grads_host[8], grads_host[9], gs, B, H4, W4, dtype, stream));
+  DUCOSY_TRY(ducosy_disc_last_backward(dout, pk + L.w5, fb + fw.p4, bb + bw.da[3], grads_host[8], grads_host[9],
+                                       reinterpret_cast<float*>(bb + bw.last_scratch), gs, B, H4, W4, dtype, stream));
 
   const size_t y_off[3] = {fw.y2, fw.y3, fw.y4}, pin_off[3] = {fw.p1, fw.p2, fw.p3}, wd_off[3] = {L.wd2, L.wd3, L.wd4};
   int Hl = H4, Wl = W4, Cl = 512;

@@ -342,22 +342,36 @@ __global__ void disc_last_dgrad_kernel(const float* __restrict__ dout, const T* 
   }
 }
 // dw[c][tap] = sum_{b,yo,xo} dout * p4[b][yo+r][xo+s][c];  db = sum dout.  One block per tap, one thread per channel.
+constexpr int kLastSplits = 32;
+// grid (16 taps, kLastSplits): each block reduces a slice of the output rows; partial [split][8192 + 1]
 template <typename T>
 __global__ void __launch_bounds__(512)
-disc_last_wgrad_kernel(const float* __restrict__ dout, const T* __restrict__ p4, float* __restrict__ dw,
-                       float* __restrict__ db, int B, int Hs, int Ws) {
+disc_last_wgrad_kernel(const float* __restrict__ dout, const T* __restrict__ p4, float* __restrict__ partial, int B, int Hs, int Ws) {
   const int tap = blockIdx.x, c = threadIdx.x, r = tap >> 2, s = tap & 3;
   const int Hp = Hs + 4, Wp = Ws + 4;
+  const int rows = B * Hs, r0 = (rows * blockIdx.y) / kLastSplits, r1 = (rows * (blockIdx.y + 1)) / kLastSplits;
   float acc = 0.f, dsum = 0.f;
-  for (int b = 0; b < B; ++b)
-    for (int yo = 0; yo < Hs; ++yo)
-      for (int xo = 0; xo < Ws; ++xo) {
-        const float d = dout[((long long)b * Hs + yo) * Ws + xo];
-        acc = fmaf(d, Cvt<T>::to_f(p4[(((long long)b * Hp + yo + r) * Wp + xo + s) * 512 + c]), acc);
-        dsum += d;
-      }
-  dw[c * 16 + tap] = acc;
-  if (tap == 0 && c == 0) *db = dsum;
+  for (int row = r0; row < r1; ++row) {
+    const int b = row / Hs, yo = row - b * Hs;
+    const T* src = p4 + (((long long)b * Hp + yo + r) * Wp + s) * 512 + c;
+    const float* dr = dout + (long long)row * Ws;
+#pragma unroll 4
+    for (int xo = 0; xo < Ws; ++xo) {
+      const float d = dr[xo];
+      acc = fmaf(d, Cvt<T>::to_f(src[(long long)xo * 512]), acc);
+      dsum += d;
+    }
+  }
+  partial[(size_t)blockIdx.y * 8193 + c * 16 + tap] = acc;
+  if (tap == 0 && c == 0) partial[(size_t)blockIdx.y * 8193 + 8192] = dsum;
+}
+__global__ void disc_last_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i > 8192) return;
+  float acc = 0.f;
+  for (int k = 0; k < kLastSplits; ++k) acc += partial[(size_t)k * 8193 + i];
+  if (i < 8192) dw[i] = acc;
+  else *db = acc;
 }
 
 // ------------------------------------------------------------------ first layer (1 -> 64) backward
@@ -507,21 +521,25 @@ extern "C" int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout,
   return check_launch("unpack_wgrad_kernel");
 }
 
+extern "C" size_t ducosy_disc_last_backward_scratch_bytes(void) { return size_t(kLastSplits) * 8193 * 4; }
 extern "C" int ducosy_disc_last_backward(const float* dout, const void* w5_packed, const void* p4, void* da4, float* dw5,
-                                         float* db5, const float* gs, int B, int Hs, int Ws, int dtype,
+                                         float* db5, float* scratch, const float* gs, int B, int Hs, int Ws, int dtype,
                                          ducosy_stream_t stream) {
   DUCOSY_CHECK(dout && w5_packed && p4 && da4 && dw5 && db5, DUCOSY_ERR_ARG, "disc_last_backward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_dgrad_kernel<T><<<grid_for_items((long long)B * Hs * Ws * 64, 256), 256, 0, st>>>(
                                       dout, static_cast<const T*>(w5_packed), static_cast<T*>(da4), B, Hs, Ws, gs)));
   DUCOSY_TRY(check_launch("disc_last_dgrad_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_wgrad_kernel<T><<<16, 512, 0, st>>>(dout, static_cast<const T*>(p4), dw5, db5, B, Hs, Ws)));
-  return check_launch("disc_last_wgrad_kernel");
+  DUCOSY_CHECK(scratch != nullptr, DUCOSY_ERR_ARG, "disc_last_backward: scratch (ducosy_disc_last_backward_scratch_bytes) is null");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_wgrad_kernel<T><<<dim3(16, kLastSplits), 512, 0, st>>>(dout, static_cast<const T*>(p4), scratch, B, Hs, Ws)));
+  DUCOSY_TRY(check_launch("disc_last_wgrad_kernel"));
+  disc_last_wgrad_reduce_kernel<<<(8193 + 255) / 256, 256, 0, st>>>(scratch, dw5, db5);
+  return check_launch("disc_last_wgrad_reduce_kernel");
 }
 
 extern "C" size_t ducosy_disc_first_backward_scratch_bytes(int B, int H, int W) {
   const long long P = (long long)B * (H / 2) * (W / 2);
-  return size_t((P + 1023) / 1024) * 64 * 17 * 4;
+  return size_t((P + 255) / 256) * 64 * 17 * 4;
 }
 extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const float* x, const float* w1, float* dw1,
                                           float* db1, float* dx, float* scratch, const float* gs, int B, int H, int W,
@@ -529,9 +547,9 @@ extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const
   DUCOSY_CHECK(da1 && p1 && x && w1 && dw1 && db1 && scratch, DUCOSY_ERR_ARG, "disc_first_backward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long P = (long long)B * (H / 2) * (W / 2);
-  const int blocks = int((P + 1023) / 1024);
+  const int blocks = int((P + 255) / 256);
   DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_wgrad_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(da1), static_cast<const T*>(p1),
-                                                                                     x, scratch, B, H, W, 1024)));
+                                                                                     x, scratch, B, H, W, 256)));
   DUCOSY_TRY(check_launch("disc_first_wgrad_kernel"));
   disc_first_wgrad_reduce_kernel<<<(64 * 17 + 255) / 256, 256, 0, st>>>(scratch, dw1, db1, blocks, gs);
   DUCOSY_TRY(check_launch("disc_first_wgrad_reduce_kernel"));

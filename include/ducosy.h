@@ -276,8 +276,9 @@ int ducosy_upsample2x_pad(const void* src_pad, void* up_pad, int B, int Hs, int 
 int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
                         ducosy_stream_t stream);
 /* First (1->64) and last (512->1) discriminator layers, backward (modules/model.py:122,128). */
+size_t ducosy_disc_last_backward_scratch_bytes(void);
 int ducosy_disc_last_backward(const float* dout, const void* w5_packed, const void* p4, void* da4, float* dw5, float* db5,
-                              const float* gs, int B, int Hs, int Ws, int dtype, ducosy_stream_t stream);
+                              float* scratch, const float* gs, int B, int Hs, int Ws, int dtype, ducosy_stream_t stream);
 size_t ducosy_disc_first_backward_scratch_bytes(int B, int H, int W);
 int ducosy_disc_first_backward(const void* da1, const void* p1, const float* x, const float* w1, float* dw1, float* db1,
                                float* dx, float* scratch, const float* gs, int B, int H, int W, int dtype,
