@@ -88,6 +88,10 @@ SIGNATURES = {
     "ducosy_upconv2x_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_upsample2x_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_grad_scale": (_i, [_p, _ll, _p, _p]),
+    "ducosy_out_conv_backward_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_out_conv_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_stem_col2im": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
+    "ducosy_unpack_stem_wgrad": (_i, [_p, _p, _i, _i, _p, _p]),
     "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ducosy_disc_last_backward_scratch_bytes": (_sz, []),
     "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

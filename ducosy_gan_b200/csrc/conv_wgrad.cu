@@ -145,9 +145,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
       uint32_t v[32];
       tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chn * 32), v);
       tmem_ld_wait();
+      if (o < a.Cout) {   // Cout = 64: the upper 64 accumulator rows come from TMA zero fill and are not stored
 #pragma unroll
-      for (int i = 0; i < 8; ++i)
-        reinterpret_cast<uint4*>(dst + chn * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        for (int i = 0; i < 8; ++i)
+          reinterpret_cast<uint4*>(dst + chn * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      }
     }
   }
   tc_fence_before();
@@ -233,8 +235,8 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_wgrad: bad dtype");
   DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
                "conv2d_wgrad: kernel %dx%d stride %d unsupported", kh, kw, stride);
-  DUCOSY_CHECK(Cin % 64 == 0 && Cin <= 256 && Cout % 128 == 0, DUCOSY_ERR_SHAPE,
-               "conv2d_wgrad: needs Cin in {64,128,192,256} and Cout a multiple of 128 (got %d -> %d)", Cin, Cout);
+  DUCOSY_CHECK(Cin % 64 == 0 && Cin <= 256 && (Cout % 128 == 0 || Cout == 64), DUCOSY_ERR_SHAPE,
+               "conv2d_wgrad: needs Cin in {64,128,192,256} and Cout 64 or a multiple of 128 (got %d -> %d)", Cin, Cout);
   DUCOSY_CHECK(stride == 1 || (Hp % 2 == 0 && Wp % 2 == 0), DUCOSY_ERR_SHAPE, "conv2d_wgrad: stride 2 needs even padded extents");
   DUCOSY_TRY(ducosy_check_device());
   const int Ho = (Hp - kh) / stride + 1, Wo = (Wp - kw) / stride + 1;
@@ -249,7 +251,7 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   a.rows_per_sample = stride == 1 ? Hp : Hp / 2;
   a.dy_pad = dy_pad;
   a.dy_rows_per_sample = Ho + 2 * dy_pad;
-  a.Cin = Cin; a.Cout = Cout; a.m_blocks = Cout / 128; a.n_slabs = Cin / 64;
+  a.Cin = Cin; a.Cout = Cout; a.m_blocks = (Cout + 127) / 128; a.n_slabs = Cin / 64;
   for (int r = 0; r < kh; ++r)
     for (int s = 0; s < kw; ++s) {
       const int t = r * kw + s;

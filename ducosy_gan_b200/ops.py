@@ -357,3 +357,54 @@ def upconv2x_backward(src_pad, dy_pad2, w_oihw):
         dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=src_pad.device)
         call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, 9, None, stream_ptr())
     return dsrc, dw
+
+
+def grad_scale(g):
+    """Power-of-two scale for the 16-bit gradient maps: gs[0] brings max|g| into [1,2), gs[1] = 1/gs[0]."""
+    g = g.contiguous()
+    with _dev(g):
+        gs = torch.empty(2, dtype=torch.float32, device=g.device)
+        call("ducosy_grad_scale", ptr(g), g.numel(), ptr(gs), stream_ptr())
+    return gs
+
+
+def out_conv_backward(dout, out, in_pad, w, gs):
+    """Backward of ReflectionPad(3)+Conv7x7(64->1)+Tanh (reference modules/model.py:112-113): returns
+    (da 16-bit [B,H,W,64] scaled by gs[0], dw fp32 [1,64,7,7], db fp32 [1])."""
+    B, Hp, Wp, Cn = in_pad.shape
+    H, W = Hp - 6, Wp - 6
+    assert Cn == 64 and in_pad.is_contiguous()
+    dout = dout.to(torch.float32).contiguous()
+    out = out.to(torch.float32).contiguous()
+    w = w.detach().to(torch.float32).contiguous()
+    lib = _lib.load()
+    with _dev(in_pad):
+        scratch = torch.empty(lib.ducosy_out_conv_backward_scratch_bytes(B, H, W) // 4, dtype=torch.float32, device=in_pad.device)
+        da = torch.empty((B, H, W, 64), dtype=in_pad.dtype, device=in_pad.device)
+        dw = torch.empty((1, 64, 7, 7), dtype=torch.float32, device=in_pad.device)
+        db = torch.empty(1, dtype=torch.float32, device=in_pad.device)
+        call("ducosy_out_conv_backward", ptr(dout), ptr(out), ptr(in_pad), ptr(w), ptr(da), ptr(dw), ptr(db), ptr(scratch), ptr(gs),
+             B, H, W, dtype_code(in_pad.dtype), stream_ptr())
+    return da, dw, db
+
+
+def stem_backward(dy, cols, w, gs, want_dx=True):
+    """Backward of ReflectionPad(3)+Conv7x7(Cin->64) given the gradient dy [B,H,W,64] of the raw conv output and the
+    saved im2col matrix cols [B,H,W,Kpad] (reference modules/model.py:90-91): returns (dw fp32 [64,Cin,7,7] true scale,
+    dx fp32 [B,1,H,W] for image channel 0 -- the mask channels are data and get no gradient -- or None)."""
+    B, H, W, Kpad = cols.shape
+    Cin = w.shape[1]
+    dt = dy.dtype
+    with _dev(dy):
+        dwp = conv2d_wgrad_nhwc(cols, dy, 1, 1, 1)                       # [64, Kpad]
+        dw = torch.empty((64, Cin, 7, 7), dtype=torch.float32, device=dy.device)
+        call("ducosy_unpack_stem_wgrad", ptr(dwp), ptr(dw), Cin, Kpad, ptr(gs), stream_ptr())
+        dx = None
+        if want_dx:
+            # dcol[p][k] = sum_o dy[p][o] * w[o][0][k]  (k < 49): a 1x1 conv with "Cout" = 64 columns
+            w1 = torch.zeros((64, 64, 1, 1), dtype=torch.float32, device=dy.device)
+            w1[:49, :, 0, 0] = w.detach().to(torch.float32)[:, 0].reshape(64, 49).t()
+            dcol, _ = conv2d_nhwc(dy, pack_conv_weight(w1, dt), 1, 1, 1, want_stats=False)
+            dx = torch.empty((B, 1, H, W), dtype=torch.float32, device=dy.device)
+            call("ducosy_stem_col2im", ptr(dcol), ptr(dx), ptr(gs), B, H, W, dtype_code(dt), stream_ptr())
+    return dw, dx

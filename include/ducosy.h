@@ -162,6 +162,20 @@ int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed, const floa
 int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* scale, const float* shift, const void* w_packed,
                                   const float* bias, float* out, int B, int H, int W, int dtype, ducosy_stream_t stream);
 
+/* Generator backward pieces (what autograd computes through modules/model.py:90-92 and :112-113 for
+ * modules/trainer.py:497).  16-bit gradient maps carry the power-of-two scale gs[0]; fp32 results leave with the true scale.
+ *
+ * Output conv + tanh: dout, out fp32 [B][H][W]; in_pad = the reflect-padded activation the forward conv read
+ * [B][H+6][W+6][64] 16-bit; w fp32 [1][64][7][7] -> da 16-bit [B][H][W][64] (scaled by gs[0]), dw fp32 [64*49], db fp32 [1]. */
+size_t ducosy_out_conv_backward_scratch_bytes(int B, int H, int W);
+int ducosy_out_conv_backward(const float* dout, const float* out, const void* in_pad, const float* w, void* da, float* dw,
+                             float* db, float* scratch, const float* gs, int B, int H, int W, int dtype, ducosy_stream_t stream);
+/* Stem: dcol [B][H][W][64] 16-bit = gradient of the first 64 im2col columns (channel 0, k = r*7+s) -> image gradient
+ * dx fp32 [B][H][W] (true scale: multiplied by gs[1]) through the adjoint of ReflectionPad2d(3) + im2col. */
+int ducosy_stem_col2im(const void* dcol, float* dx, const float* gs, int B, int H, int W, int dtype, ducosy_stream_t stream);
+/* packed [64][Kpad] weight gradient of the stem GEMM -> OIHW [64][Cin][7][7], multiplied by gs[1]. */
+int ducosy_unpack_stem_wgrad(const float* packed, float* g_oihw, int Cin, int Kpad, const float* gs, ducosy_stream_t stream);
+
 /* ---------------------------------------------------------------- whole-generator entry points */
 
 typedef struct {
@@ -234,7 +248,7 @@ int ducosy_loss_ssim_backward(const float* x, const float* y, const float* dmaps
  * Weight gradient of the NHWC convolutions on the tensor cores: dW[o][(r*kw+s)*Cin + c] = sum_pixels dy[p][o] *
  * x_pad[p*stride + (r,s)][c] (what autograd computes for modules/trainer.py:513,519,524).  x_pad is the padded input
  * the forward conv read, dy the output gradient [B][Ho+2*dy_pad][Wo+2*dy_pad][Cout] (interior), both 16-bit NHWC; dw fp32 in the packed forward
- * layout.  Cin in {64,128,192,256}, Cout % 128 == 0.  Deterministic (fixed-order reduction of the K splits). */
+ * layout.  Cin in {64,128,192,256}, Cout = 64 or Cout % 128 == 0.  Deterministic (fixed-order reduction of the K splits). */
 size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw);
 int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp, int Cin,
                              int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,

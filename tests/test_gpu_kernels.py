@@ -283,7 +283,7 @@ def test_out_conv_fused_equals_apply_then_conv(ops, dtype):
 
 
 @pytest.mark.parametrize("case", [(2, 32, 32, 256, 256, 3, 1), (1, 64, 64, 64, 128, 3, 2), (2, 32, 64, 128, 256, 4, 2),
-                                  (1, 16, 128, 192, 128, 1, 1)])
+                                  (1, 16, 128, 192, 128, 1, 1), (2, 32, 64, 128, 64, 3, 1), (1, 16, 128, 64, 64, 1, 1)])
 def test_conv2d_wgrad_matches_autograd(ops, case):
     B, H, W, Cin, Cout, k, stride = case
     dtype = torch.float16
