@@ -196,10 +196,34 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ packed, float
   g[i] = packed[(i / K) * Kpad + (i % K)] * gs[1];
 }
 
+// a += b on 16-bit maps (the skip connection of the residual blocks carries the gradient straight through)
+template <typename T>
+__global__ void __launch_bounds__(256)
+add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, long long n8) {
+  const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (i >= n8) return;
+  const uint4 va = reinterpret_cast<const uint4*>(a)[i], vb = reinterpret_cast<const uint4*>(b)[i];
+  const uint32_t wa[4] = {va.x, va.y, va.z, va.w}, wb[4] = {vb.x, vb.y, vb.z, vb.w};
+  uint32_t o[4];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 fa = Cvt<T>::unpack2(wa[k]), fb = Cvt<T>::unpack2(wb[k]);
+    o[k] = Cvt<T>::pack2(fa.x + fb.x, fa.y + fb.y);
+  }
+  reinterpret_cast<uint4*>(a)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 }  // namespace
 }  // namespace ducosy
 
 using namespace ducosy;
+
+extern "C" int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(a && b && n > 0 && n % 8 == 0, DUCOSY_ERR_ARG, "add_inplace: needs non-null pointers and n %% 8 == 0");
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (add_inplace_kernel<T><<<grid_items(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                                      static_cast<T*>(a), static_cast<const T*>(b), n / 8)));
+  return check_launch("add_inplace_kernel");
+}
 
 namespace {
 constexpr int kTanhBlocks = 592;

@@ -131,10 +131,13 @@ class Generator(nn.Module):
         return [p for _, p in self.named_parameters()]
 
     def forward(self, x):
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
-            raise NotImplementedError(_NO_TRAIN_MSG.format("Generator"))
         if not x.is_cuda:
             raise RuntimeError("ducosy_gan_b200.Generator needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            if x.dim() != 4 or x.shape[1] != self._cfg_tuple[0]:
+                raise RuntimeError(f"expected input [B,{self._cfg_tuple[0]},H,W], got {tuple(x.shape)}")
+            _lib.check(_lib.load().ducosy_check_device(), "check_device")
+            return _GeneratorFunction.apply(self._cfg_tuple, x, *self._ordered_params())
         eng = self._engine(x.device)
         eng.sync_weights(self._ordered_params())
         return eng.forward(x)
@@ -145,6 +148,40 @@ class Generator(nn.Module):
         eng = self._engine(px.device)
         eng.sync_weights(self._ordered_params())
         return eng.forward_hu(px, slope, intercept, hu_min, hu_max)
+
+
+class _GeneratorFunction(torch.autograd.Function):
+    """autograd bridge of the training path (reference modules/trainer.py:455-500): the forward keeps the raw conv outputs
+    and InstanceNorm statistics, the backward runs ..training.generator_backward.  The image gradient flows to channel 0
+    (the CT slice); the mask channels the reference concatenates (trainer.py:430-450) are data."""
+
+    @staticmethod
+    def forward(ctx, cfg, x, *params):
+        from .. import training
+        dtype = torch.float16 if default_operand_dtype() == _lib.F16 else torch.bfloat16
+        xs = x.detach().to(dtype=torch.float32).contiguous()
+        ps = [p.detach() for p in params]
+        with torch.cuda.device(x.device):
+            out, saved = training.generator_forward_train(ps, cfg, xs, dtype)
+        saved.pop("out")
+        ctx.cfg, ctx.saved, ctx.params, ctx.in_shape = cfg, saved, ps, tuple(x.shape)
+        ctx.save_for_backward(out)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from .. import training
+        (out,) = ctx.saved_tensors
+        saved = ctx.saved
+        saved["out"] = out
+        with torch.cuda.device(out.device):
+            grads, dx = training.generator_backward(ctx.params, ctx.cfg, saved, dout, ctx.needs_input_grad[1])
+            if dx is not None and ctx.in_shape[1] > 1:
+                full = torch.zeros(ctx.in_shape, dtype=torch.float32, device=out.device)
+                full[:, :1] = dx
+                dx = full
+        ctx.saved = None
+        return (None, dx, *grads)
 
 
 class _GeneratorEngine:

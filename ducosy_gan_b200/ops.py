@@ -338,7 +338,24 @@ def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode):
     return dx, dxpad
 
 
-def upconv2x_backward(src_pad, dy_pad2, w_oihw):
+def unpack_wgrad(dwp, Cout, Cin, taps, gs=None):
+    """Packed fp32 weight gradient [Cout, taps*Cin] -> OIHW [Cout, Cin, k, k] (times gs[1] when a gradient scale is given)."""
+    k = int(round(taps ** 0.5))
+    with _dev(dwp):
+        dw = torch.empty((Cout, Cin, k, k), dtype=torch.float32, device=dwp.device)
+        call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, taps, ptr(gs), stream_ptr())
+    return dw
+
+
+def add_inplace(a, b):
+    """a += b on 16-bit maps."""
+    assert a.dtype == b.dtype and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    with _dev(a):
+        call("ducosy_add_inplace", ptr(a), ptr(b), a.numel(), dtype_code(a.dtype), stream_ptr())
+    return a
+
+
+def upconv2x_backward(src_pad, dy_pad2, w_oihw, gs=None):
     """Backward of Upsample(x2)+Conv3x3(pad 1): src_pad [B,Hs+2,Ws+2,Cin] (zero border), dy_pad2 [B,2Hs+4,2Ws+4,Cout]
     (zero border 2) -> (dsrc [B,Hs,Ws,Cin], dW fp32 OIHW [Cout,Cin,3,3])."""
     Cout, Cin = w_oihw.shape[:2]
@@ -355,7 +372,7 @@ def upconv2x_backward(src_pad, dy_pad2, w_oihw):
         call("ducosy_upsample2x_pad", ptr(src_pad), ptr(up), B, Hs, Ws, Cin, dc, stream_ptr())
         dwp = conv2d_wgrad_nhwc(up, dy_pad2, 3, 3, 1, dy_pad=2)
         dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=src_pad.device)
-        call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, 9, None, stream_ptr())
+        call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, 9, ptr(gs), stream_ptr())
     return dsrc, dw
 
 

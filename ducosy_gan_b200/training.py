@@ -1,0 +1,120 @@
+"""Generator forward-with-saved-activations and backward for the CycleGAN step (reference modules/trainer.py:455-500
+through modules/model.py:56-115).  Host orchestration only: every tensor op below is a kernel of libducosy_sm100.so
+reached through the C ABI (ops.py); nothing here computes with torch.
+
+Layout: activations are NHWC 16-bit, raw conv outputs are kept next to the InstanceNorm (scale, shift) pairs so the
+normalised values are re-derived instead of stored; 16-bit gradient maps carry the power-of-two scale gs[0]
+(ops.grad_scale), fp32 parameter / image gradients leave with the true scale.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import ops
+from .ops import ACT_NONE, ACT_RELU, PAD_REFLECT, PAD_ZERO
+
+
+def _split_params(params, num_blocks, use_cbam):
+    """named_parameters() order of modules/model.py:90-115 -> (stem, d1, d2, blocks, u1, u2, out)."""
+    it = iter(params)
+    take = lambda n: [next(it) for _ in range(n)]
+    stem, d1, d2 = take(2), take(2), take(2)
+    blocks = [take(7 if use_cbam else 4) for _ in range(num_blocks)]
+    u1, u2, out = take(2), take(2), take(2)
+    return stem, d1, d2, blocks, u1, u2, out
+
+
+def generator_forward_train(params, cfg, x, dtype):
+    """x fp32 [B,Cin,H,W] -> (out fp32 [B,1,H,W], saved activations)."""
+    _, num_blocks, use_cbam = cfg
+    stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
+    B, _, H, W = x.shape
+    if H % 32 or W % 512:
+        raise RuntimeError(f"training path needs H % 32 == 0 and W % 512 == 0 (got {H}x{W}); 512x512 is what train.py uses")
+    S = {"shape": (B, H, W)}
+    S["cols"] = ops.stem_im2col(x, dtype)
+    y0, part = ops.conv2d_nhwc(S["cols"], ops.pack_stem_weight(stem[0], dtype), 1, 1, 1)
+    S["y0"], S["n0"] = y0, ops.in_finalize(part, H * W)
+    S["p0"] = ops.in_apply_pad(y0, *S["n0"], 1, PAD_ZERO, ACT_RELU)
+    y1, part = ops.conv2d_nhwc(S["p0"], ops.pack_conv_weight(d1[0], dtype), 3, 3, 2)
+    S["y1"], S["n1"] = y1, ops.in_finalize(part, H * W // 4)
+    S["p1"] = ops.in_apply_pad(y1, *S["n1"], 1, PAD_ZERO, ACT_RELU)
+    y2, part = ops.conv2d_nhwc(S["p1"], ops.pack_conv_weight(d2[0], dtype), 3, 3, 2)
+    S["y2"], S["n2"] = y2, ops.in_finalize(part, H * W // 16)
+    r = ops.in_apply_pad(y2, *S["n2"], 1, PAD_REFLECT if num_blocks else PAD_ZERO, ACT_RELU)
+    npix = H * W // 16
+    S["blocks"] = []
+    for i, bp in enumerate(blocks):
+        last = i == num_blocks - 1
+        sv = {"r": r}
+        ya, part = ops.conv2d_nhwc(r, ops.pack_conv_weight(bp[0], dtype), 3, 3, 1)
+        sv["ya"], sv["na"] = ya, ops.in_finalize(part, npix)
+        sv["pa"] = ops.in_apply_pad(ya, *sv["na"], 1, PAD_REFLECT, ACT_RELU)
+        yb, part = ops.conv2d_nhwc(sv["pa"], ops.pack_conv_weight(bp[2], dtype), 3, 3, 1)
+        sv["yb"] = yb
+        out_mode = PAD_ZERO if last else PAD_REFLECT
+        if use_cbam:
+            r = ops.cbam_forward_train(sv, part, npix, bp[4], bp[5], bp[6], out_mode)
+        else:
+            sv["nb"] = ops.in_finalize(part, npix)
+            r = ops.residual_apply_pad(yb, *sv["nb"], None, sv["r"], 1, 1, out_mode)
+        S["blocks"].append(sv)
+    S["r_last"] = r
+    yu1, part = ops.upconv2x_nhwc(r, ops.pack_upconv_weight(u1[0], dtype))
+    S["yu1"], S["nu1"] = yu1, ops.in_finalize(part, H * W // 4)
+    S["pu1"] = ops.in_apply_pad(yu1, *S["nu1"], 1, PAD_ZERO, ACT_RELU)
+    yu2, part = ops.upconv2x_merged_nhwc(S["pu1"], ops.pack_upconv_merged_weight(u2[0], dtype))
+    S["yu2"], S["nu2"] = yu2, ops.in_finalize(part, H * W)
+    S["pout"] = ops.in_apply_pad(yu2, *S["nu2"], 3, PAD_REFLECT, ACT_RELU)
+    out = ops.out_conv7x7_tanh(S["pout"], ops.pack_out_weight(outp[0], dtype), outp[1])
+    S["out"] = out
+    return out, S
+
+
+def generator_backward(params, cfg, S, dout, want_dx=True):
+    """dout fp32 [B,1,H,W] -> (list of fp32 parameter gradients in named_parameters() order, dx fp32 [B,1,H,W] | None).
+    Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant)."""
+    _, num_blocks, use_cbam = cfg
+    stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
+    dout = dout.to(torch.float32).contiguous()
+    gs = ops.grad_scale(dout)
+    zero = lambda p: torch.zeros_like(p, dtype=torch.float32)
+
+    da, dw_out, db_out = ops.out_conv_backward(dout, S["out"], S["pout"], outp[0], gs)
+    dyu2 = ops.in_backward_pad(da, S["yu2"], *S["nu2"], 2, ACT_RELU)
+    dpu1, dw_u2 = ops.upconv2x_backward(S["pu1"], dyu2, u2[0], gs)
+    dyu1 = ops.in_backward_pad(dpu1, S["yu1"], *S["nu1"], 2, ACT_RELU)
+    dr, dw_u1 = ops.upconv2x_backward(S["r_last"], dyu1, u1[0], gs)
+
+    block_grads = []
+    for bp, sv in zip(reversed(blocks), reversed(S["blocks"])):
+        if use_cbam:
+            dn, cbam_grads = ops.cbam_backward(sv, dr, bp[4], bp[5], bp[6], gs)
+            dyb = ops.in_backward_pad(dn, sv["yb"], *sv["nb"], 2, ACT_NONE)
+        else:
+            cbam_grads = []
+            dyb = ops.in_backward_pad(dr, sv["yb"], *sv["nb"], 2, ACT_NONE)
+        C = bp[0].shape[0]
+        dw_b = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(sv["pa"], dyb, 3, 3, 1, dy_pad=2), C, C, 9, gs)
+        dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
+        dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
+        dw_a = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(sv["r"], dya, 3, 3, 1, dy_pad=2), C, C, 9, gs)
+        dskip, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT)
+        dr = ops.add_inplace(dskip, dr)
+        block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)
+    block_grads.reverse()
+
+    dy2 = ops.in_backward_pad(dr, S["y2"], *S["n2"], 1, ACT_RELU)
+    dw_d2 = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(S["p1"], dy2, 3, 3, 2, dy_pad=1), d2[0].shape[0], d2[0].shape[1], 9, gs)
+    dp1 = ops.convs2_dgrad_nhwc(dy2, d2[0])
+    dy1 = ops.in_backward_pad(dp1, S["y1"], *S["n1"], 1, ACT_RELU)
+    dw_d1 = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(S["p0"], dy1, 3, 3, 2, dy_pad=1), d1[0].shape[0], d1[0].shape[1], 9, gs)
+    dp0 = ops.convs2_dgrad_nhwc(dy1, d1[0])
+    dy0 = ops.in_backward_pad(dp0, S["y0"], *S["n0"], 0, ACT_RELU)
+    dw_stem, dx = ops.stem_backward(dy0, S["cols"], stem[0], gs, want_dx)
+
+    grads = [dw_stem, zero(stem[1]), dw_d1, zero(d1[1]), dw_d2, zero(d2[1])]
+    for g in block_grads:
+        grads += g
+    grads += [dw_u1, zero(u1[1]), dw_u2, zero(u2[1]), dw_out, db_out]
+    return grads, dx

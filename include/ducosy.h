@@ -175,6 +175,8 @@ int ducosy_out_conv_backward(const float* dout, const float* out, const void* in
 int ducosy_stem_col2im(const void* dcol, float* dx, const float* gs, int B, int H, int W, int dtype, ducosy_stream_t stream);
 /* packed [64][Kpad] weight gradient of the stem GEMM -> OIHW [64][Cin][7][7], multiplied by gs[1]. */
 int ducosy_unpack_stem_wgrad(const float* packed, float* g_oihw, int Cin, int Kpad, const float* gs, ducosy_stream_t stream);
+/* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
+int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 
 /* ---------------------------------------------------------------- whole-generator entry points */
 

@@ -73,9 +73,11 @@ def test_discriminator_cpu_input_is_loud():
         Discriminator(1)(torch.zeros(1, 1, 256, 256))
 
 
-def test_generator_training_forward_is_loud():
+def test_generator_cpu_input_is_loud():
     from ducosy_gan_b200.modules.model import Generator
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(RuntimeError):
+        Generator(1, 1)(torch.zeros(1, 1, 128, 128))
+    with torch.no_grad(), pytest.raises(RuntimeError):
         Generator(1, 1)(torch.zeros(1, 1, 128, 128))
 
 

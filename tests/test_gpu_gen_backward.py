@@ -66,3 +66,145 @@ def test_stem_backward_matches_autograd(ops, Cin):
     dw, dx = ops.stem_backward(dy.permute(0, 2, 3, 1).contiguous().cuda(), cols, w.cuda(), gs)
     assert _rel(dw, wr.grad) < 3e-3, _rel(dw, wr.grad)
     assert _rel(dx[:, 0], xr.grad[:, 0]) < 3e-3, _rel(dx[:, 0], xr.grad[:, 0])
+
+
+# ------------------------------------------------------------------ whole generator: autograd bridge vs torch autograd
+def _torch_generator(P, x, num_blocks, use_cbam, q=lambda t: t):
+    """fp32 torch restatement of reference modules/model.py:90-115 (functional, for autograd).  ``q`` rounds what the
+    kernels store in 16 bit (operands, raw conv outputs, activations) with a straight-through gradient, so that the
+    ReLU masks of the reference agree with the kernels' and only the backward arithmetic is compared."""
+    names = list(P.keys())
+    it = iter(names)
+    nxt = lambda: P[next(it)]
+    wq = lambda: q(nxt())
+    h = q(F.conv2d(F.pad(q(x), (3, 3, 3, 3), mode="reflect"), wq(), nxt()))
+    h = q(F.relu(F.instance_norm(h)))
+    for _ in range(2):
+        h = q(F.relu(F.instance_norm(q(F.conv2d(h, wq(), nxt(), stride=2, padding=1)))))
+    for _ in range(num_blocks):
+        t = q(F.relu(F.instance_norm(q(F.conv2d(F.pad(h, (1, 1, 1, 1), mode="reflect"), wq(), nxt())))))
+        t = F.instance_norm(q(F.conv2d(F.pad(t, (1, 1, 1, 1), mode="reflect"), wq(), nxt())))
+        if use_cbam:
+            fc0, fc2, wsa = nxt(), nxt(), nxt()
+            mlp = lambda v: F.conv2d(F.relu(F.conv2d(v, fc0)), fc2)
+            ca = torch.sigmoid(mlp(F.adaptive_avg_pool2d(t, 1)) + mlp(F.adaptive_max_pool2d(t, 1)))
+            t = t * ca
+            pooled = torch.cat([t.mean(dim=1, keepdim=True), t.max(dim=1, keepdim=True)[0]], dim=1)
+            t = t * torch.sigmoid(F.conv2d(pooled, wsa, padding=3))
+        h = q(h + t)
+    for _ in range(2):
+        h = F.interpolate(h, scale_factor=2)
+        h = q(F.relu(F.instance_norm(q(F.conv2d(h, wq(), nxt(), padding=1)))))
+    return torch.tanh(F.conv2d(F.pad(h, (3, 3, 3, 3), mode="reflect"), wq(), nxt()))
+
+
+def _ste_round(dtype):
+    return lambda t: t + (t.to(dtype).float() - t).detach()
+
+
+class _RoundBoth(torch.autograd.Function):
+    """Rounds the value in the forward AND the (power-of-two scaled) gradient in the backward to `dtype`: a torch model of
+    a pipeline that stores activations and gradient maps in 16 bit."""
+
+    @staticmethod
+    def forward(ctx, t, dtype, scale):
+        ctx.dtype, ctx.scale = dtype, scale
+        return t.to(dtype).float()
+
+    @staticmethod
+    def backward(ctx, g):
+        s = ctx.scale[0]
+        return (g * s).to(ctx.dtype).float() / s, None, None
+
+
+def _round_both(dtype, scale):
+    return lambda t: _RoundBoth.apply(t, dtype, scale) if t.dim() == 4 and t.shape[0] < 64 and t.requires_grad and t.grad_fn is not None else t + (t.to(dtype).float() - t).detach()
+
+
+def _noise_floor(Cin, blocks, use_cbam, B, H, W, seed, dtype):
+    """Relative L2 distance between fp32 autograd and the same torch model with 16-bit stored activations and gradient
+    maps: the error any 16-bit-storage backward has on this network, independent of the kernels."""
+    from ducosy_gan_b200.modules.model import Generator, weights_init_normal
+    torch.manual_seed(seed)
+    G = Generator(Cin, blocks, use_cbam).cuda()
+    G.apply(weights_init_normal)
+    x = (torch.rand(B, Cin, H, W, device="cuda") * 2 - 1)
+    target = torch.rand(B, 1, H, W, device="cuda") * 2 - 1
+    grads = []
+    for mode in ("fp32", "rounded"):
+        P = {n: p.detach().clone().requires_grad_(True) for n, p in G.named_parameters()}
+        xr = x.clone().requires_grad_(True)
+        scale = [1.0]
+        q = (lambda t: t) if mode == "fp32" else _round_both(dtype, scale)
+        out = _torch_generator(P, xr, blocks, use_cbam, q)
+        loss = (out - target).abs().mean() + 0.5 * ((out - 0.3) ** 2).mean()
+        if mode == "rounded":
+            (dout,) = torch.autograd.grad(loss, out, retain_graph=True)
+            import math
+            scale[0] = 2.0 ** (-math.floor(math.log2(dout.abs().max().item())))
+        loss.backward()
+        grads.append({**{n: p.grad for n, p in P.items()}, "input": xr.grad})
+    return {n: _rel(grads[1][n], grads[0][n]) for n in grads[0] if n.endswith("weight") or n == "input"}
+
+
+def _check_generator_grads(Cin, blocks, use_cbam, B, H, W, seed, rounding_aware=False):
+    import os
+    from ducosy_gan_b200.modules.model import Generator, weights_init_normal
+    dt = torch.bfloat16 if os.environ.get("DUCOSY_PRECISION", "fp16").lower() == "bf16" else torch.float16
+    q = _ste_round(dt) if rounding_aware else (lambda t: t)
+    torch.manual_seed(seed)
+    G = Generator(Cin, blocks, use_cbam).cuda()
+    G.apply(weights_init_normal)
+    x = (torch.rand(B, Cin, H, W, device="cuda") * 2 - 1).requires_grad_(True)
+    target = torch.rand(B, 1, H, W, device="cuda") * 2 - 1
+    out = G(x)
+    loss = (out - target).abs().mean() + 0.5 * ((out - 0.3) ** 2).mean()
+    loss.backward()
+    got = {n: p.grad.clone() for n, p in G.named_parameters()}
+    got_dx = x.grad.clone()
+
+    P = {n: p.detach().clone().requires_grad_(True) for n, p in G.named_parameters()}
+    xr = x.detach().clone().requires_grad_(True)
+    ref_out = _torch_generator(P, xr, blocks, use_cbam, q)
+    ref_loss = (ref_out - target).abs().mean() + 0.5 * ((ref_out - 0.3) ** 2).mean()
+    ref_loss.backward()
+    assert (out - ref_out).abs().max().item() < (2e-2 if dt == torch.float16 else 1.5e-1)
+    report = {}
+    for n, p in P.items():
+        ref = p.grad
+        if n.endswith("bias") and not n.endswith(f"{len(list(G.model)) - 2}.bias"):
+            # biases in front of an InstanceNorm: autograd yields rounding noise around zero, the kernels an exact zero
+            assert got[n].abs().max().item() == 0.0, n
+            assert ref.abs().max().item() < 1e-3 * max(pp.grad.abs().max().item() for pp in P.values()), n
+            continue
+        report[n] = _rel(got[n], ref)
+    report["input"] = _rel(got_dx[:, :1], xr.grad[:, :1])
+    if Cin > 1:
+        assert got_dx[:, 1:].abs().max().item() == 0.0
+    return report
+
+
+def _assert_at_noise_floor(Cin, blocks, use_cbam, B, H, W):
+    """The kernels store activations and gradient maps in 16 bit.  InstanceNorm's backward projects the mean and the
+    n-correlated component out of every gradient map, so the surviving gradient is a small residual and the 16-bit
+    rounding of the maps is amplified (a few % relative L2 per tensor, growing towards the input).  The bound is
+    therefore measured, not guessed: a plain torch model of the same network that rounds the stored activations and
+    gradient maps to 16 bit gives the floor; the kernels must stay within 1.5x of it (+0.5 %) for every tensor, and
+    the last layers -- where nothing is amplified yet -- within 1 %."""
+    import os
+    dt = torch.bfloat16 if os.environ.get("DUCOSY_PRECISION", "fp16").lower() == "bf16" else torch.float16
+    report = _check_generator_grads(Cin, blocks, use_cbam, B, H, W, seed=5)
+    floor = _noise_floor(Cin, blocks, use_cbam, B, H, W, 5, dt)
+    bad = {k: (v, floor.get(k)) for k, v in report.items() if k in floor and not v < 1.5 * floor[k] + 5e-3}
+    assert not bad, (bad, report, floor)
+    last = [k for k in report if k.endswith("weight")][-1]
+    assert report[last] < 1e-2, (last, report[last])
+    assert max(report.values()) < 0.15, report
+
+
+@pytest.mark.parametrize("cfg", [(1, 2, 1, 64, 512), (3, 1, 2, 32, 512)])
+def test_generator_plain_backward_matches_autograd(cfg):
+    """Plain ResidualBlock generator (use_cbam=False): every parameter gradient and the image gradient against fp32
+    autograd, through Generator.forward / loss.backward()."""
+    Cin, blocks, B, H, W = cfg
+    _assert_at_noise_floor(Cin, blocks, False, B, H, W)
