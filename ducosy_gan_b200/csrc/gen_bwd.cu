@@ -196,6 +196,282 @@ __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ packed, float
   g[i] = packed[(i / K) * Kpad + (i % K)] * gs[1];
 }
 
+
+// ------------------------------------------------------------------ CBAM backward (modules/model.py:12-53, 68-87)
+// forward (per residual block, n = InstanceNorm(conv output), C = 256):
+//   mx[c] = max_{y,x} n;  h = relu(fc0 mx);  ca = sigmoid(fc2 h)      (the avg-pool branch sees exactly 0, see elementwise.cu)
+//   v = n * ca;  pooled = [mean_c v, max_c v];  sa = sigmoid(conv7x7(pooled));  out = x + v * sa
+// The avg-pool branch contributes nothing to the backward either: its hidden activations are relu(0) = 0 (no fc2
+// gradient), relu'(0) = 0 (no fc0 gradient), and a per-channel constant added to dn is removed by the InstanceNorm
+// backward that follows.
+constexpr int kCbamC = 256;       // channels of the residual blocks (one warp = one pixel, 8 channels per lane)
+constexpr int kCbamPix = 64;      // pixels per CTA in the warp-per-pixel passes
+
+template <typename T>
+__device__ __forceinline__ void load8(const T* p, float* f) {
+  const uint4 v = *reinterpret_cast<const uint4*>(p);
+  const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+  for (int k = 0; k < 4; ++k) {
+    const float2 t = Cvt<T>::unpack2(w[k]);
+    f[2 * k] = t.x;
+    f[2 * k + 1] = t.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void store8(T* p, const float* f) {
+  uint4 o;
+  o.x = Cvt<T>::pack2(f[0], f[1]);
+  o.y = Cvt<T>::pack2(f[2], f[3]);
+  o.z = Cvt<T>::pack2(f[4], f[5]);
+  o.w = Cvt<T>::pack2(f[6], f[7]);
+  *reinterpret_cast<uint4*>(p) = o;
+}
+__device__ __forceinline__ void load8f(const float* p, float* f) {
+  const float4 a = *reinterpret_cast<const float4*>(p), b = *reinterpret_cast<const float4*>(p + 4);
+  f[0] = a.x; f[1] = a.y; f[2] = a.z; f[3] = a.w; f[4] = b.x; f[5] = b.y; f[6] = b.z; f[7] = b.w;
+}
+
+// training-mode channel attention: keeps ca, the hidden layer and the un-folded InstanceNorm affine
+__global__ void __launch_bounds__(256)
+cbam_channel_train_kernel(const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
+                          const float* __restrict__ scale_n, const float* __restrict__ shift_n, float* __restrict__ scale_v,
+                          float* __restrict__ shift_v, float* __restrict__ ca, float* __restrict__ hidden, int C) {
+  extern __shared__ float sm[];  // [C] max, [C/16] hidden
+  float* smax = sm;
+  float* hid = sm + C;
+  const int b = blockIdx.x, Hd = C / 16;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) smax[c] = chmax[b * C + c];
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int j = warp; j < Hd; j += nwarps) {
+    float acc = 0.f;
+    for (int c = lane; c < C; c += 32) acc += fc0[j * C + c] * smax[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      hid[j] = fmaxf(acc, 0.f);
+      hidden[b * Hd + j] = hid[j];
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < Hd; ++j) acc += fc2[c * Hd + j] * hid[j];
+    const float s = 1.f / (1.f + __expf(-acc));
+    ca[b * C + c] = s;
+    scale_v[b * C + c] = scale_n[b * C + c] * s;
+    shift_v[b * C + c] = shift_n[b * C + c] * s;
+  }
+}
+
+// pass A: dz = (sum_c dout * v) * sa * (1 - sa); per-CTA arg-max over the pixels of every channel of the raw conv output
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_bwd_dz_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const float* __restrict__ scale_v,
+                   const float* __restrict__ shift_v, const float* __restrict__ sa, float* __restrict__ dz,
+                   float* __restrict__ pmax_val, int* __restrict__ pmax_idx, int HW) {
+  __shared__ float sval[8][kCbamC];
+  __shared__ int sidx[8][kCbamC];
+  const int b = blockIdx.y, blk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
+  float sv[8], hv[8], best[8];
+  int bidx[8];
+  load8f(scale_v + b * kCbamC + c0, sv);
+  load8f(shift_v + b * kCbamC + c0, hv);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bidx[k] = 0; }
+  for (int i = 0; i < kCbamPix / 8; ++i) {
+    const int pix = blk * kCbamPix + warp + i * 8;
+    const long long off = ((long long)b * HW + pix) * kCbamC + c0;
+    float d[8], y[8];
+    load8<T>(dout + off, d);
+    load8<T>(yb + off, y);
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      acc += d[k] * fmaf(y[k], sv[k], hv[k]);
+      if (y[k] > best[k]) { best[k] = y[k]; bidx[k] = pix; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) {
+      const float s = sa[(long long)b * HW + pix];
+      dz[(long long)b * HW + pix] = acc * s * (1.f - s);
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { sval[warp][c0 + k] = best[k]; sidx[warp][c0 + k] = bidx[k]; }
+  __syncthreads();
+  const int c = threadIdx.x;
+  float bv = sval[0][c];
+  int bi = sidx[0][c];
+  for (int w = 1; w < 8; ++w) {
+    const float v = sval[w][c];
+    const int i = sidx[w][c];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
+  }
+  pmax_val[((long long)b * gridDim.x + blk) * kCbamC + c] = bv;
+  pmax_idx[((long long)b * gridDim.x + blk) * kCbamC + c] = bi;
+}
+
+__global__ void cbam_argmax_finalize_kernel(const float* __restrict__ pmax_val, const int* __restrict__ pmax_idx, int nblk,
+                                            int* __restrict__ amax_pix) {
+  const int c = threadIdx.x, b = blockIdx.x;
+  float bv = -INFINITY;
+  int bi = 0;
+  for (int k = 0; k < nblk; ++k) {   // CTAs cover increasing pixel ranges: strict > keeps the first occurrence
+    const float v = pmax_val[((long long)b * nblk + k) * kCbamC + c];
+    if (v > bv) { bv = v; bi = pmax_idx[((long long)b * nblk + k) * kCbamC + c]; }
+  }
+  amax_pix[b * kCbamC + c] = bi;
+}
+
+// pass B: adjoint of the 2 -> 1 7x7 spatial-attention conv: dpooled [B][H][W][2] and per-CTA partial weight gradients
+__global__ void __launch_bounds__(256)
+cbam_sa_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ pooled, const float* __restrict__ wsa,
+                   float* __restrict__ dpooled, float* __restrict__ pdw, int B, int H, int W) {
+  __shared__ float ws[98];
+  __shared__ float red[8][98];
+  if (threadIdx.x < 98) ws[threadIdx.x] = wsa[threadIdx.x];
+  __syncthreads();
+  const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;   // B*H*W is a multiple of 256
+  const int x = int(pix % W), y = int((pix / W) % H), b = int(pix / ((long long)W * H));
+  const float* dzb = dz + (long long)b * H * W;
+  const float* pb = pooled + (long long)b * H * W * 2;
+  const float g = dz[pix];
+  float d0 = 0.f, d1 = 0.f;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int r = 0; r < 7; ++r)
+    for (int s = 0; s < 7; ++s) {
+      // dpooled[y][x] += dz[y + 3 - r][x + 3 - s] * w[ch][r][s]
+      const int yy = y + 3 - r, xx = x + 3 - s;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W) {
+        const float t = dzb[(long long)yy * W + xx];
+        d0 += t * ws[r * 7 + s];
+        d1 += t * ws[49 + r * 7 + s];
+      }
+      // dw[ch][r][s] += dz[y][x] * pooled[ch][y + r - 3][x + s - 3]
+      const int py = y + r - 3, px = x + s - 3;
+      float p0 = 0.f, p1 = 0.f;
+      if (py >= 0 && py < H && px >= 0 && px < W) {
+        const float2 pv = *reinterpret_cast<const float2*>(pb + ((long long)py * W + px) * 2);
+        p0 = g * pv.x;
+        p1 = g * pv.y;
+      }
+#pragma unroll
+      for (int o = 16; o; o >>= 1) {
+        p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+        p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+      }
+      if (lane == 0) { red[warp][r * 7 + s] = p0; red[warp][49 + r * 7 + s] = p1; }
+    }
+  *reinterpret_cast<float2*>(dpooled + pix * 2) = make_float2(d0, d1);
+  __syncthreads();
+  if (threadIdx.x < 98) {
+    float a = 0.f;
+    for (int w = 0; w < 8; ++w) a += red[w][threadIdx.x];
+    pdw[(long long)blockIdx.x * 98 + threadIdx.x] = a;
+  }
+}
+
+// pass C: dv = dout*sa + dpooled0/C + [c == argmax_c v] dpooled1;  dn = dv*ca (16 bit);  per-CTA partial dca = sum dv*n
+template <typename T>
+__global__ void __launch_bounds__(256)
+cbam_bwd_dv_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const float* __restrict__ scale_n,
+                   const float* __restrict__ shift_n, const float* __restrict__ ca, const float* __restrict__ sa,
+                   const float* __restrict__ dpooled, T* __restrict__ dn, float* __restrict__ pdca, int HW) {
+  __shared__ float sacc[8][kCbamC];
+  const int b = blockIdx.y, blk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
+  float sn[8], hn[8], cav[8], accd[8];
+  load8f(scale_n + b * kCbamC + c0, sn);
+  load8f(shift_n + b * kCbamC + c0, hn);
+  load8f(ca + b * kCbamC + c0, cav);
+#pragma unroll
+  for (int k = 0; k < 8; ++k) accd[k] = 0.f;
+  for (int i = 0; i < kCbamPix / 8; ++i) {
+    const int pix = blk * kCbamPix + warp + i * 8;
+    const long long off = ((long long)b * HW + pix) * kCbamC + c0;
+    float d[8], y[8], n[8];
+    load8<T>(dout + off, d);
+    load8<T>(yb + off, y);
+    float vmax = -INFINITY;
+    int cmax = 0;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      n[k] = fmaf(y[k], sn[k], hn[k]);
+      const float v = n[k] * cav[k];
+      if (v > vmax) { vmax = v; cmax = c0 + k; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, vmax, o);
+      const int oc = __shfl_xor_sync(0xffffffffu, cmax, o);
+      if (ov > vmax || (ov == vmax && oc < cmax)) { vmax = ov; cmax = oc; }
+    }
+    const float s = sa[(long long)b * HW + pix];
+    const float2 dp = *reinterpret_cast<const float2*>(dpooled + ((long long)b * HW + pix) * 2);
+    const float dmean = dp.x * (1.f / kCbamC);
+    float o8[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const float dv = d[k] * s + dmean + ((c0 + k) == cmax ? dp.y : 0.f);
+      accd[k] += dv * n[k];
+      o8[k] = dv * cav[k];
+    }
+    store8<T>(dn + off, o8);
+  }
+#pragma unroll
+  for (int k = 0; k < 8; ++k) sacc[warp][c0 + k] = accd[k];
+  __syncthreads();
+  float a = 0.f;
+  for (int w = 0; w < 8; ++w) a += sacc[w][threadIdx.x];
+  pdca[((long long)b * gridDim.x + blk) * kCbamC + threadIdx.x] = a;
+}
+
+// pass D (one CTA per sample): channel-attention MLP backward, per-sample fc gradients, and the max-pool scatter
+template <typename T>
+__global__ void __launch_bounds__(kCbamC)
+cbam_channel_bwd_kernel(const float* __restrict__ pdca, int nblk, const float* __restrict__ ca, const float* __restrict__ hidden,
+                        const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
+                        const int* __restrict__ amax_pix, T* __restrict__ dn, float* __restrict__ pfc0,
+                        float* __restrict__ pfc2, int HW) {
+  constexpr int Hd = kCbamC / 16;
+  __shared__ float ds[kCbamC], h[Hd], dh[Hd];
+  const int b = blockIdx.x, c = threadIdx.x;
+  float dca = 0.f;
+  for (int k = 0; k < nblk; ++k) dca += pdca[((long long)b * nblk + k) * kCbamC + c];
+  const float cv = ca[b * kCbamC + c];
+  ds[c] = dca * cv * (1.f - cv);
+  if (c < Hd) h[c] = hidden[b * Hd + c];
+  __syncthreads();
+  if (c < Hd) {
+    float a = 0.f;
+    if (h[c] > 0.f)
+      for (int k = 0; k < kCbamC; ++k) a += fc2[k * Hd + c] * ds[k];
+    dh[c] = a;
+  }
+  __syncthreads();
+  float dmx = 0.f;
+  const float mxc = chmax[b * kCbamC + c];
+#pragma unroll
+  for (int j = 0; j < Hd; ++j) {
+    dmx += fc0[j * kCbamC + c] * dh[j];
+    pfc2[((long long)b * kCbamC + c) * Hd + j] = ds[c] * h[j];
+    pfc0[((long long)b * Hd + j) * kCbamC + c] = dh[j] * mxc;
+  }
+  T* cell = dn + ((long long)b * HW + amax_pix[b * kCbamC + c]) * kCbamC + c;
+  *cell = Cvt<T>::from_f(Cvt<T>::to_f(*cell) + dmx);
+}
+
+__global__ void cbam_param_reduce_kernel(const float* __restrict__ partial, int parts, int n, float* __restrict__ out,
+                                         const float* __restrict__ gs) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float a = 0.f;
+  for (int k = 0; k < parts; ++k) a += partial[(long long)k * n + i];
+  out[i] = a * gs[1];
+}
+
 // a += b on 16-bit maps (the skip connection of the residual blocks carries the gradient straight through)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -272,4 +548,68 @@ extern "C" int ducosy_unpack_stem_wgrad(const float* packed, float* g_oihw, int 
   DUCOSY_CHECK(packed && g_oihw && gs && Cin >= 1 && Kpad >= Cin * 49, DUCOSY_ERR_ARG, "unpack_stem_wgrad: bad argument");
   unpack_stem_wgrad_kernel<<<grid_items(64LL * Cin * 49, 256), 256, 0, (cudaStream_t)stream>>>(packed, g_oihw, Cin, Kpad, gs);
   return check_launch("unpack_stem_wgrad_kernel");
+}
+
+extern "C" int ducosy_cbam_channel_train(const float* chmax, const float* fc0, const float* fc2, const float* scale_n,
+                                         const float* shift_n, float* scale_v, float* shift_v, float* ca, float* hidden, int B,
+                                         int C, ducosy_stream_t stream) {
+  DUCOSY_CHECK(chmax && fc0 && fc2 && scale_n && shift_n && scale_v && shift_v && ca && hidden, DUCOSY_ERR_ARG,
+               "cbam_channel_train: null pointer");
+  DUCOSY_CHECK(B > 0 && C % 32 == 0, DUCOSY_ERR_SHAPE, "cbam_channel_train: C %% 32 != 0");
+  const size_t smem = size_t(C + C / 16) * sizeof(float);
+  cbam_channel_train_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(chmax, fc0, fc2, scale_n, shift_n, scale_v, shift_v, ca, hidden, C);
+  return check_launch("cbam_channel_train_kernel");
+}
+
+extern "C" size_t ducosy_cbam_backward_scratch_bytes(int B, int H, int W, int C) {
+  const size_t HW = size_t(H) * W, nblk = HW / kCbamPix;
+  size_t words = B * HW * 3                 /* dz, dpooled */
+                 + 3 * B * nblk * C        /* pmax_val, pmax_idx, pdca */
+                 + size_t(B) * C           /* amax_pix */
+                 + (B * HW / 256) * 98     /* spatial conv weight partials */
+                 + 2 * size_t(B) * C * (C / 16);
+  return words * 4;
+}
+
+extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n, const float* shift_n,
+                                    const float* scale_v, const float* shift_v, const float* ca, const float* hidden,
+                                    const float* chmax, const float* pooled, const float* sa, const float* fc0, const float* fc2,
+                                    const float* wsa, void* dn, float* dfc0, float* dfc2, float* dwsa, float* scratch,
+                                    const float* gs, int B, int H, int W, int C, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(dout && yb && scale_n && shift_n && scale_v && shift_v && ca && hidden && chmax && pooled && sa && fc0 && fc2 &&
+                   wsa && dn && dfc0 && dfc2 && dwsa && scratch && gs, DUCOSY_ERR_ARG, "cbam_backward: null pointer");
+  DUCOSY_CHECK(C == kCbamC, DUCOSY_ERR_SHAPE, "cbam_backward: built for the %d-channel residual blocks (got %d)", kCbamC, C);
+  DUCOSY_CHECK(B > 0 && (H * W) % 256 == 0, DUCOSY_ERR_SHAPE, "cbam_backward: H*W must be a multiple of 256");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "cbam_backward: bad dtype");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int HW = H * W, nblk = HW / kCbamPix, sablk = B * HW / 256, Hd = C / 16;
+  float* dz = scratch;
+  float* dpooled = dz + size_t(B) * HW;
+  float* pmax_val = dpooled + size_t(B) * HW * 2;
+  int* pmax_idx = reinterpret_cast<int*>(pmax_val + size_t(B) * nblk * C);
+  float* pdca = reinterpret_cast<float*>(pmax_idx + size_t(B) * nblk * C);
+  int* amax_pix = reinterpret_cast<int*>(pdca + size_t(B) * nblk * C);
+  float* pdw = reinterpret_cast<float*>(amax_pix + size_t(B) * C);
+  float* pfc0 = pdw + size_t(sablk) * 98;
+  float* pfc2 = pfc0 + size_t(B) * C * Hd;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_bwd_dz_kernel<T><<<dim3(nblk, B), 256, 0, st>>>(
+                                      static_cast<const T*>(dout), static_cast<const T*>(yb), scale_v, shift_v, sa, dz, pmax_val,
+                                      pmax_idx, HW)));
+  DUCOSY_TRY(check_launch("cbam_bwd_dz_kernel"));
+  cbam_argmax_finalize_kernel<<<B, kCbamC, 0, st>>>(pmax_val, pmax_idx, nblk, amax_pix);
+  DUCOSY_TRY(check_launch("cbam_argmax_finalize_kernel"));
+  cbam_sa_bwd_kernel<<<sablk, 256, 0, st>>>(dz, pooled, wsa, dpooled, pdw, B, H, W);
+  DUCOSY_TRY(check_launch("cbam_sa_bwd_kernel"));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_bwd_dv_kernel<T><<<dim3(nblk, B), 256, 0, st>>>(
+                                      static_cast<const T*>(dout), static_cast<const T*>(yb), scale_n, shift_n, ca, sa, dpooled,
+                                      static_cast<T*>(dn), pdca, HW)));
+  DUCOSY_TRY(check_launch("cbam_bwd_dv_kernel"));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_channel_bwd_kernel<T><<<B, kCbamC, 0, st>>>(pdca, nblk, ca, hidden, chmax, fc0, fc2, amax_pix,
+                                                                                  static_cast<T*>(dn), pfc0, pfc2, HW)));
+  DUCOSY_TRY(check_launch("cbam_channel_bwd_kernel"));
+  const int nfc = C * Hd;
+  cbam_param_reduce_kernel<<<(nfc + 255) / 256, 256, 0, st>>>(pfc0, B, nfc, dfc0, gs);
+  cbam_param_reduce_kernel<<<(nfc + 255) / 256, 256, 0, st>>>(pfc2, B, nfc, dfc2, gs);
+  cbam_param_reduce_kernel<<<1, 128, 0, st>>>(pdw, sablk, 98, dwsa, gs);
+  return check_launch("cbam_param_reduce_kernel");
 }

@@ -167,14 +167,16 @@ def stem_im2col_hu(px: torch.Tensor, slope, intercept, lo, hi, dtype=torch.float
 
 
 # ------------------------------------------------------------------ normalisation / attention
-def in_finalize(partials: torch.Tensor, npix: int, fc0=None, fc2=None):
+def in_finalize(partials: torch.Tensor, npix: int, fc0=None, fc2=None, want_chmax=False):
     B, tiles, _, Cn = partials.shape
     with _dev(partials):
         scale = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
         shift = torch.empty((B, Cn), dtype=torch.float32, device=partials.device)
-        chmax = torch.empty((B, Cn), dtype=torch.float32, device=partials.device) if fc0 is not None else None
+        chmax = torch.empty((B, Cn), dtype=torch.float32, device=partials.device) if (fc0 is not None or want_chmax) else None
         call("ducosy_in_finalize", ptr(partials), tiles, int(npix), ptr(scale), ptr(shift), ptr(fc0), ptr(fc2), ptr(chmax),
              B, Cn, stream_ptr())
+    if want_chmax:
+        return scale, shift, chmax
     return scale, shift
 
 
@@ -425,3 +427,45 @@ def stem_backward(dy, cols, w, gs, want_dx=True):
             dx = torch.empty((B, 1, H, W), dtype=torch.float32, device=dy.device)
             call("ducosy_stem_col2im", ptr(dcol), ptr(dx), ptr(gs), B, H, W, dtype_code(dt), stream_ptr())
     return dw, dx
+
+
+def _f32c(t):
+    return t.detach().to(torch.float32).contiguous()
+
+
+def cbam_forward_train(sv, partials, npix, fc0, fc2, wsa, out_mode):
+    """Training-mode tail of a ResidualBlockWithCBAM (reference modules/model.py:68-87): from the raw second conv output
+    sv["yb"] and its statistics to the padded block output, keeping what the backward needs in sv."""
+    yb = sv["yb"]
+    B, H, W, Cn = yb.shape
+    dev = yb.device
+    scale_n, shift_n, chmax = in_finalize(partials, npix, want_chmax=True)
+    with _dev(yb):
+        scale_v, shift_v, ca = (torch.empty((B, Cn), dtype=torch.float32, device=dev) for _ in range(3))
+        hidden = torch.empty((B, Cn // 16), dtype=torch.float32, device=dev)
+        call("ducosy_cbam_channel_train", ptr(chmax), ptr(_f32c(fc0)), ptr(_f32c(fc2)), ptr(scale_n), ptr(shift_n), ptr(scale_v),
+             ptr(shift_v), ptr(ca), ptr(hidden), B, Cn, stream_ptr())
+    pooled = cbam_pool(yb, scale_v, shift_v)
+    sa = cbam_spatial_conv(pooled, wsa)
+    sv.update(nb=(scale_n, shift_n), nv=(scale_v, shift_v), ca=ca, hidden=hidden, chmax=chmax, pooled=pooled, sa=sa)
+    return residual_apply_pad(yb, scale_v, shift_v, sa, sv["r"], 1, 1, out_mode)
+
+
+def cbam_backward(sv, dout, fc0, fc2, wsa, gs):
+    """CBAM backward: dout [B,H,W,C] 16-bit (gradient of the block output) -> (dn 16-bit gradient w.r.t. InstanceNorm(yb),
+    [d fc.0.weight, d fc.2.weight, d spatial conv weight] fp32 true scale)."""
+    yb = sv["yb"]
+    B, H, W, Cn = yb.shape
+    dev = yb.device
+    lib = _lib.load()
+    with _dev(yb):
+        scratch = torch.empty(lib.ducosy_cbam_backward_scratch_bytes(B, H, W, Cn) // 4, dtype=torch.float32, device=dev)
+        dn = torch.empty_like(yb)
+        dfc0 = torch.empty(tuple(fc0.shape), dtype=torch.float32, device=dev)
+        dfc2 = torch.empty(tuple(fc2.shape), dtype=torch.float32, device=dev)
+        dwsa = torch.empty(tuple(wsa.shape), dtype=torch.float32, device=dev)
+        call("ducosy_cbam_backward", ptr(dout), ptr(yb), ptr(sv["nb"][0]), ptr(sv["nb"][1]), ptr(sv["nv"][0]), ptr(sv["nv"][1]),
+             ptr(sv["ca"]), ptr(sv["hidden"]), ptr(sv["chmax"]), ptr(sv["pooled"]), ptr(sv["sa"]), ptr(_f32c(fc0)), ptr(_f32c(fc2)),
+             ptr(_f32c(wsa)), ptr(dn), ptr(dfc0), ptr(dfc2), ptr(dwsa), ptr(scratch), ptr(gs), B, H, W, Cn, dtype_code(yb.dtype),
+             stream_ptr())
+    return dn, [dfc0, dfc2, dwsa]

@@ -175,6 +175,21 @@ int ducosy_out_conv_backward(const float* dout, const float* out, const void* in
 int ducosy_stem_col2im(const void* dcol, float* dx, const float* gs, int B, int H, int W, int dtype, ducosy_stream_t stream);
 /* packed [64][Kpad] weight gradient of the stem GEMM -> OIHW [64][Cin][7][7], multiplied by gs[1]. */
 int ducosy_unpack_stem_wgrad(const float* packed, float* g_oihw, int Cin, int Kpad, const float* gs, ducosy_stream_t stream);
+/* CBAM in training mode (modules/model.py:12-53): the channel-attention MLP keeps ca [B][C], the hidden layer [B][C/16] and
+ * writes the attention-folded affine (scale_v, shift_v) next to the un-folded InstanceNorm one (scale_n, shift_n);
+ * chmax [B][C] is the normalised per-channel max ducosy_in_finalize emits. */
+int ducosy_cbam_channel_train(const float* chmax, const float* fc0, const float* fc2, const float* scale_n, const float* shift_n,
+                              float* scale_v, float* shift_v, float* ca, float* hidden, int B, int C, ducosy_stream_t stream);
+/* CBAM backward for the 256-channel residual blocks: dout = gradient of (x + CBAM(n)) w.r.t. the CBAM branch
+ * [B][H][W][C] 16-bit (scaled by gs[0]); yb = raw conv output; pooled [B][H][W][2], sa [B][H][W] from the forward.
+ * Returns dn (gradient w.r.t. n = InstanceNorm(yb), 16-bit, scaled) and the fp32 true-scale gradients of fc.0.weight
+ * [C/16][C], fc.2.weight [C][C/16] and spatial_attention.conv.weight [1][2][7][7]. */
+size_t ducosy_cbam_backward_scratch_bytes(int B, int H, int W, int C);
+int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n, const float* shift_n, const float* scale_v,
+                         const float* shift_v, const float* ca, const float* hidden, const float* chmax, const float* pooled,
+                         const float* sa, const float* fc0, const float* fc2, const float* wsa, void* dn, float* dfc0, float* dfc2,
+                         float* dwsa, float* scratch, const float* gs, int B, int H, int W, int C, int dtype,
+                         ducosy_stream_t stream);
 /* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
 int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 
