@@ -3,6 +3,9 @@
 // CBAM / residual-block element-wise adjoints.  Everything is bandwidth-bound CUDA-core work; reductions run in a
 // fixed order (deterministic gradients).  16-bit gradient maps carry the power-of-two scale gs[0] (ducosy_grad_scale);
 // fp32 parameter / image gradients leave with the true scale.
+#include <algorithm>
+#include <cmath>
+
 #include "common.cuh"
 #include "input_fn.cuh"
 
@@ -472,6 +475,21 @@ __global__ void cbam_param_reduce_kernel(const float* __restrict__ partial, int 
   out[i] = a * gs[1];
 }
 
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad; modules/trainer.py:360-362): one fused pass over
+// (param, grad, exp_avg, exp_avg_sq), all fp32.  step_size = lr / (1 - b1^t), denom = sqrt(v) / sqrt(1 - b2^t) + eps.
+__global__ void __launch_bounds__(256)
+adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                 float b1, float b2, float eps, float step_size, float inv_sqrt_bc2) {
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
 // a += b on 16-bit maps (the skip connection of the residual blocks carries the gradient straight through)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -612,4 +630,14 @@ extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const floa
   cbam_param_reduce_kernel<<<(nfc + 255) / 256, 256, 0, st>>>(pfc2, B, nfc, dfc2, gs);
   cbam_param_reduce_kernel<<<1, 128, 0, st>>>(pdw, sablk, 98, dwsa, gs);
   return check_launch("cbam_param_reduce_kernel");
+}
+
+extern "C" int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,
+                                float beta1, float beta2, float eps, int step, ducosy_stream_t stream) {
+  DUCOSY_CHECK(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, DUCOSY_ERR_ARG, "adam_step: bad argument");
+  const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
+  const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
+  adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+                                                            float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
+  return check_launch("adam_step_kernel");
 }

@@ -190,6 +190,10 @@ int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n,
                          const float* sa, const float* fc0, const float* fc2, const float* wsa, void* dn, float* dfc0, float* dfc2,
                          float* dwsa, float* scratch, const float* gs, int B, int H, int W, int C, int dtype,
                          ducosy_stream_t stream);
+/* torch.optim.Adam step (no weight decay, no amsgrad) as constructed at modules/trainer.py:360-362: fp32 param / grad /
+ * exp_avg / exp_avg_sq of n elements updated in one pass; step counts from 1. */
+int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                     float beta2, float eps, int step, ducosy_stream_t stream);
 /* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
 int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 

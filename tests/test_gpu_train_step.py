@@ -1,0 +1,87 @@
+"""CycleGAN step (reference modules/trainer.py:447-525) on the CUDA path: the fused Adam against
+torch.optim.Adam, and the step-1 loss terms against the oracle restatement evaluated on the CPU with the same weights."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from oracle import ducosy_oracle as orc  # noqa: E402
+
+
+def test_fused_adam_matches_torch_adam():
+    from ducosy_gan_b200.optim import Adam
+    torch.manual_seed(0)
+    shapes = [(256, 256, 3, 3), (64,), (1, 2, 7, 7), (1000003,)]
+    mine = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    ref = [p.detach().clone().requires_grad_(True) for p in mine]
+    o1, o2 = Adam(mine, lr=2e-4, betas=(0.5, 0.999)), torch.optim.Adam(ref, lr=2e-4, betas=(0.5, 0.999))
+    sched = torch.optim.lr_scheduler.LambdaLR(o1, lambda e: 1.0 - 0.1 * e)       # trainer.py:364-366 drives lr this way
+    sched2 = torch.optim.lr_scheduler.LambdaLR(o2, lambda e: 1.0 - 0.1 * e)
+    for it in range(4):
+        for a, b in zip(mine, ref):
+            g = torch.randn_like(a) * (10.0 ** (it - 2))
+            a.grad, b.grad = g.clone(), g.clone()
+        o1.step(); o2.step(); sched.step(); sched2.step()
+        for a, b in zip(mine, ref):
+            assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-7
+
+
+def _oracle_step_losses(sdG_A, sdG_B, sdD_A, sdD_B, real_A, real_B, masks, blocks, cbam):
+    G = lambda sd, x: orc.generator_forward(sd, x, blocks, cbam)
+    cat = (lambda t: torch.cat([t, masks], 1)) if masks is not None else (lambda t: t)
+    l1 = torch.nn.functional.l1_loss
+    fake_B, fake_A = G(sdG_A, cat(real_A)), G(sdG_B, cat(real_B))
+    id_A, id_B = G(sdG_B, cat(real_A)), G(sdG_A, cat(real_B))
+    t = {}
+    t["id"] = (l1(id_A, real_A) + l1(id_B, real_B)) / 2
+    t["GAN"] = (orc.mse_gan_loss(orc.discriminator_forward(sdD_B, fake_B), True)
+                + orc.mse_gan_loss(orc.discriminator_forward(sdD_A, fake_A), True)) / 2
+    rec_A, rec_B = G(sdG_B, cat(fake_B)), G(sdG_A, cat(fake_A))
+    t["cycle"] = (l1(rec_A, real_A) + l1(rec_B, real_B)) / 2
+    t["grad_cycle"] = (orc.gradient_loss(rec_A, real_A) + orc.gradient_loss(rec_B, real_B)) / 2
+    t["grad_id"] = (orc.gradient_loss(id_A, real_A) + orc.gradient_loss(id_B, real_B)) / 2
+    t["ssim"] = 1 - (orc.ssim(rec_A, real_A) + orc.ssim(rec_B, real_B)) / 2
+    t["contrast_attention"] = orc.contrast_attention_loss(fake_B, real_B, real_A)
+    t["contrast_region"] = orc.contrast_region_loss(fake_B, real_B, real_A)
+    t["contrast_edge"] = orc.contrast_edge_loss(fake_B, real_B, real_A)
+    t["G"] = (t["GAN"] + 10.0 * t["cycle"] + 5.0 * t["id"] + 5.0 * t["grad_cycle"] + 2.5 * t["grad_id"] + 2.0 * t["ssim"]
+              + 2.0 * t["contrast_attention"] + 1.5 * t["contrast_region"] + 1.0 * t["contrast_edge"])
+    D = orc.discriminator_forward
+    t["D_A"] = (orc.mse_gan_loss(D(sdD_A, real_A), True) + orc.mse_gan_loss(D(sdD_A, fake_A), False)) / 2
+    t["D_B"] = (orc.mse_gan_loss(D(sdD_B, real_B), True) + orc.mse_gan_loss(D(sdD_B, fake_B), False)) / 2
+    return {k: float(v) for k, v in t.items()}
+
+
+@pytest.mark.parametrize("cfg", [(2, 1, True, 1), (1, 2, False, 2)])
+def test_train_step_losses_match_oracle_and_parameters_move(cfg):
+    """Step-1 loss terms (computed before any update) against the oracle on the same weights and batch: 3 % relative
+    (16-bit activations through up to three chained networks; |.|-type losses are first-order in that noise) -- D_A / D_B
+    are evaluated after optimizer_G.step() in the reference loop, but on fakes made before it, so the oracle's values with
+    the initial discriminator weights are exact references for them too.  Then every parameter must have moved and two
+    further steps must stay finite."""
+    from ducosy_gan_b200.trainer import CycleGANStep
+    Cin, blocks, cbam, B = cfg
+    H, W = 256, 512            # the PatchGAN kernels need multiples of 256
+    step = CycleGANStep(Cin, blocks, cbam, seed=11)
+    g = torch.Generator().manual_seed(3)
+    smooth = lambda t: torch.nn.functional.avg_pool2d(t, 5, 1, 2) * 2.0
+    real_A = smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1)
+    real_B = smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1)
+    masks = (torch.rand(B, Cin - 1, H, W, generator=g) < 0.1).float() if Cin > 1 else None
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    sds = [cpu(m) for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B)]
+    before = [p.detach().clone() for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B) for p in m.parameters()]
+    with torch.no_grad():
+        ref = _oracle_step_losses(*sds, real_A, real_B, masks, blocks, cbam)
+    dev = lambda t: None if t is None else t.cuda()
+    got = {k: v.item() for k, v in step.step(dev(real_A), dev(real_B), dev(masks)).items()}
+    bad = {k: (got[k], ref[k]) for k in ref if abs(got[k] - ref[k]) > 3e-2 * abs(ref[k]) + 1e-4}
+    assert not bad, bad
+    after = [p for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B) for p in m.parameters()]
+    names = [n for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B) for n, _ in m.named_parameters()]
+    live = [(n, a, b) for n, a, b in zip(names, after, before)]
+    still = [n for n, a, b in live if torch.equal(a, b) and not (n.endswith("bias") and a.numel() > 1)]
+    assert not still, still            # dead biases (in front of an InstanceNorm) legitimately keep a zero gradient
+    for _ in range(2):
+        out = step.step(dev(real_A), dev(real_B), dev(masks))
+    assert all(torch.isfinite(v).item() for v in out.values()), out
