@@ -6,6 +6,8 @@
 //   * weight gradients = conv_wgrad.cu (MN-major tcgen05 GEMM over the pixels).
 // InstanceNorm + LeakyReLU backward, the first (Cin = 1) and last (Cout = 1) layers are bandwidth-bound kernels here.
 // All reductions run in a fixed order (deterministic gradients).
+#include <algorithm>
+
 #include "common.cuh"
 
 namespace ducosy {
@@ -70,18 +72,29 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
   }
   const uint4* dav = reinterpret_cast<const uint4*>(da) + (size_t(b) * HW) * cv + c8;
   const uint4* yv = reinterpret_cast<const uint4*>(y) + (size_t(b) * HW) * cv + c8;
-  for (int p = p0 + prow; p < p1; p += rows) {
-    const uint4 a = dav[size_t(p) * cv], v = yv[size_t(p) * cv];
-    const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, vw[4] = {v.x, v.y, v.z, v.w};
+  constexpr int kILP = 4;   // 8 independent 16-byte loads in flight per thread
+  for (int pb = p0 + prow; pb < p1; pb += rows * kILP) {
+    uint4 a[kILP], v[kILP];
 #pragma unroll
-    for (int k = 0; k < 4; ++k) {
-      const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
-      const float n0 = fmaf(fy.x, sc[2 * k], sh[2 * k]), n1 = fmaf(fy.y, sc[2 * k + 1], sh[2 * k + 1]);
-      const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);
-      s1[2 * k] += g0;
-      s1[2 * k + 1] += g1;
-      s2[2 * k] = fmaf(g0, n0, s2[2 * k]);
-      s2[2 * k + 1] = fmaf(g1, n1, s2[2 * k + 1]);
+    for (int u = 0; u < kILP; ++u) {
+      const int p = pb + u * rows;
+      const bool ok = p < p1;
+      a[u] = ok ? dav[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
+      v[u] = ok ? yv[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
+    }
+#pragma unroll
+    for (int u = 0; u < kILP; ++u) {
+      const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+        const float n0 = fmaf(fy.x, sc[2 * k], sh[2 * k]), n1 = fmaf(fy.y, sc[2 * k + 1], sh[2 * k + 1]);
+        const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);   // masked-out loads have a = 0: g = 0
+        s1[2 * k] += g0;
+        s1[2 * k + 1] += g1;
+        s2[2 * k] = fmaf(g0, n0, s2[2 * k]);
+        s2[2 * k + 1] = fmaf(g1, n1, s2[2 * k + 1]);
+      }
     }
   }
 #pragma unroll
@@ -106,44 +119,66 @@ __global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, float*
   }
 }
 
+// grid (row CTAs, B): a CTA walks padded rows py = blockIdx.x, += gridDim.x of its sample; thread t handles the 16-byte
+// chunks t, t+256, ... of a row -- 256 is a multiple of C/8, so its 8 channels (and their rstd / shift / means) stay in
+// registers; four chunks are in flight per thread.
 template <typename T>
 __global__ void __launch_bounds__(256)
 in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ means, T* __restrict__ dy_pad, int B,
                         int H, int W, int C, int pad, int act) {
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
-  const long long total = (long long)B * Hp * Wp * cv;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-    const int c8 = int(i % cv);
-    long long r = i / cv;
-    const int px = int(r % Wp);
-    r /= Wp;
-    const int py = int(r % Hp);
-    const int b = int(r / Hp);
-    const int sy = py - pad, sx = px - pad;
-    uint4 o = make_uint4(0, 0, 0, 0);
-    if (sy >= 0 && sy < H && sx >= 0 && sx < W) {
-      const size_t src = ((size_t(b) * H + sy) * W + sx) * cv + c8;
-      const uint4 a = reinterpret_cast<const uint4*>(da)[src], v = reinterpret_cast<const uint4*>(y)[src];
-      const uint32_t aw[4] = {a.x, a.y, a.z, a.w}, vw[4] = {v.x, v.y, v.z, v.w};
-      uint32_t ow[4];
+  const int b = blockIdx.y, c8 = threadIdx.x % cv, px0 = threadIdx.x / cv, px_step = 256 / cv;
+  float rs[8], sh[8], m1[8], m2[8];
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
-        float res[2];
-#pragma unroll
-        for (int e = 0; e < 2; ++e) {
-          const int c = c8 * 8 + 2 * k + e;
-          const float rstd = scale[b * C + c];
-          const float n = fmaf(e ? fy.y : fy.x, rstd, shift[b * C + c]);
-          const float g = (e ? fa.y : fa.x) * act_grad(n, act);
-          res[e] = rstd * (g - means[size_t(b) * 2 * C + c] - n * means[size_t(b) * 2 * C + C + c]);
-        }
-        ow[k] = Cvt<T>::pack2(res[0], res[1]);
-      }
-      o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+  for (int j = 0; j < 8; ++j) {
+    const int c = c8 * 8 + j;
+    rs[j] = scale[b * C + c];
+    sh[j] = shift[b * C + c];
+    m1[j] = means[size_t(b) * 2 * C + c];
+    m2[j] = means[size_t(b) * 2 * C + C + c];
+  }
+  constexpr int kILP = 4;
+  for (int py = blockIdx.x; py < Hp; py += gridDim.x) {
+    const int sy = py - pad;
+    uint4* dst_row = reinterpret_cast<uint4*>(dy_pad) + ((size_t(b) * Hp + py) * Wp) * cv + c8;
+    if (sy < 0 || sy >= H) {
+      for (int px = px0; px < Wp; px += px_step) dst_row[size_t(px) * cv] = make_uint4(0, 0, 0, 0);
+      continue;
     }
-    reinterpret_cast<uint4*>(dy_pad)[i] = o;
+    const uint4* a_row = reinterpret_cast<const uint4*>(da) + ((size_t(b) * H + sy) * W) * cv + c8;
+    const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((size_t(b) * H + sy) * W) * cv + c8;
+    for (int pb = px0; pb < Wp; pb += px_step * kILP) {
+      uint4 a[kILP], v[kILP];
+      bool inside[kILP];
+#pragma unroll
+      for (int u = 0; u < kILP; ++u) {
+        const int sx = pb + u * px_step - pad;
+        inside[u] = sx >= 0 && sx < W;
+        a[u] = inside[u] ? a_row[size_t(sx) * cv] : make_uint4(0, 0, 0, 0);
+        v[u] = inside[u] ? y_row[size_t(sx) * cv] : make_uint4(0, 0, 0, 0);
+      }
+#pragma unroll
+      for (int u = 0; u < kILP; ++u) {
+        const int px = pb + u * px_step;
+        if (px >= Wp) break;
+        uint4 o = make_uint4(0, 0, 0, 0);
+        if (inside[u]) {
+          const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+          uint32_t ow[4];
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+            const float n0 = fmaf(fy.x, rs[2 * k], sh[2 * k]), n1 = fmaf(fy.y, rs[2 * k + 1], sh[2 * k + 1]);
+            const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);
+            ow[k] = Cvt<T>::pack2(rs[2 * k] * (g0 - m1[2 * k] - n0 * m2[2 * k]),
+                                  rs[2 * k + 1] * (g1 - m1[2 * k + 1] - n1 * m2[2 * k + 1]));
+          }
+          o = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+        }
+        dst_row[size_t(px) * cv] = o;
+      }
+    }
   }
 }
 
@@ -210,6 +245,50 @@ __global__ void dgrad_s1_edge_cols_kernel(const T* __restrict__ dy_pad2, const T
       }
     }
     dxpad[(((long long)b * (H + 2) + u) * (W + 2) + v) * Ci + c] = Cvt<T>::from_f(acc);
+  }
+}
+// Co = 256 (the residual blocks): one warp per input channel c keeps its 3 x 256 filter taps in registers (8 per lane,
+// coalesced) and walks a chunk of (b, u) positions; the dy rows are 512-byte coalesced reads shared by the 8 warps.
+template <typename T>
+__global__ void __launch_bounds__(256)
+dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H, int W,
+                             int Ci, int pos_per_block) {
+  constexpr int Co = 256;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp, side = blockIdx.y;
+  const int v = side ? W + 1 : 0, s = side ? 2 : 0;
+  float wr[3][8];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const uint4 kv = *reinterpret_cast<const uint4*>(wd + ((long long)c * 9 + r * 3 + s) * Co + lane * 8);
+    const uint32_t kw[4] = {kv.x, kv.y, kv.z, kv.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 f = Cvt<T>::unpack2(kw[k]);
+      wr[r][2 * k] = f.x;
+      wr[r][2 * k + 1] = f.y;
+    }
+  }
+  const int total = B * (H + 2);
+  const int p0 = blockIdx.z * pos_per_block, p1 = min(total, p0 + pos_per_block);
+  for (int pos = p0; pos < p1; ++pos) {
+    const int b = pos / (H + 2), u = pos - b * (H + 2);
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const uint4 dv = *reinterpret_cast<const uint4*>(
+          dy_pad2 + (((long long)b * (H + 4) + (u - r + 2)) * (W + 4) + (v - s + 2)) * Co + lane * 8);
+      const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 a = Cvt<T>::unpack2(dw[k]);
+        acc = fmaf(a.x, wr[r][2 * k], acc);
+        acc = fmaf(a.y, wr[r][2 * k + 1], acc);
+      }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) dxpad[(((long long)b * (H + 2) + u) * (W + 2) + v) * Ci + c] = Cvt<T>::from_f(acc);
   }
 }
 // adjoint of the padding: gradient w.r.t. the padded map [B][H+2p][W+2p][C] -> gradient w.r.t. the un-padded map
@@ -464,11 +543,15 @@ int grid_for_items(long long items, int threads) {
 
 using namespace ducosy;
 
+namespace {
+constexpr int kInBwdPix = 512;   // pixels per CTA of the InstanceNorm-backward reduction
+}
+
 // Generic InstanceNorm(+activation) backward on NHWC 16-bit maps (also the generator's building block):
 //   da, y [B][H][W][C]; scale/shift from ducosy_in_finalize of the forward; scratch: fp32 [B*(blocks+1)*2*C] with
-//   blocks = ceil(H*W / 2048); dy_pad [B][H+2p][W+2p][C] (zero border).
+//   blocks = ceil(H*W / 512); dy_pad [B][H+2p][W+2p][C] (zero border).
 extern "C" size_t ducosy_in_backward_scratch_bytes(int B, int H, int W, int C) {
-  const int blocks = (H * W + 2047) / 2048;
+  const int blocks = (H * W + kInBwdPix - 1) / kInBwdPix;
   return size_t(B) * (blocks + 1) * 2 * C * 4;
 }
 extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad,
@@ -477,7 +560,7 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
   DUCOSY_CHECK(da && y && scale && shift && dy_pad && scratch && B > 0, DUCOSY_ERR_ARG, "in_backward_pad: null pointer");
   DUCOSY_CHECK(C % 8 == 0 && 256 % (C / 8) == 0 && pad >= 0, DUCOSY_ERR_SHAPE, "in_backward_pad: C/8 must divide 256");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  const int HW = H * W, ppb = 2048, blocks = (HW + ppb - 1) / ppb;
+  const int HW = H * W, ppb = kInBwdPix, blocks = (HW + ppb - 1) / ppb;
   float* partial = scratch;
   float* means = scratch + size_t(B) * blocks * 2 * C;
   const size_t smem = size_t(256 / (C / 8)) * 2 * C * 4;
@@ -486,8 +569,8 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
   DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
   in_bwd_finalize_kernel<<<dim3((2 * C + 255) / 256, B), 256, 0, st>>>(partial, means, blocks, C, 1.0f / float(HW));
   DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
-  const long long total = (long long)B * (H + 2 * pad) * (W + 2 * pad) * (C / 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_pad_kernel<T><<<grid_for_items(total, 256), 256, 0, st>>>(
+  const int row_ctas = std::max(1, std::min(H + 2 * pad, (num_sms() * 4 + B - 1) / B));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_pad_kernel<T><<<dim3(row_ctas, B), 256, 0, st>>>(
                                       static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
                                       static_cast<T*>(dy_pad), B, H, W, C, pad, act)));
   return check_launch("in_bwd_apply_pad_kernel");
@@ -590,6 +673,15 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
   p.out_y_off = 0; p.out_x_off = 1;
   p.partials = nullptr; p.dtype = dtype;
   DUCOSY_TRY(launch_conv_gemm(p, static_cast<cudaStream_t>(stream)));
+  if (Cout == 256 && Cin % 8 == 0) {
+    const int positions = B * (H + 2), chunks = std::max(1, std::min(positions, (148 * 16) / std::max(1, Cin / 8 * 2)));
+    const int per = (positions + chunks - 1) / chunks;
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols256_kernel<T><<<dim3(Cin / 8, 2, (positions + per - 1) / per), 256, 0,
+                                                                      (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,
+                                        Cin, per)));
+    return check_launch("dgrad_s1_edge_cols256_kernel");
+  }
   const long long total = (long long)B * (H + 2) * 2 * Cin;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols_kernel<T><<<grid_for_items(total, 128), 128, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,

@@ -62,7 +62,9 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, fl
 }
 
 // da[b][y][x][c] = gs0 * sum over the padded positions (u,v) that mirror (y,x) of sum_{r,s} dv[u-r][v-s] * w[c][r][s]
-// thread = (pixel, 8 channels); weights transposed to [tap][channel] in shared memory.
+// thread = (4 pixels along x, 8 channels); weights transposed to [tap][channel] in shared memory.  Away from the border
+// (one padded position per pixel, every tap inside the image) a row of 10 dv values feeds 7 taps x 4 pixels x 8 channels
+// of FMAs; the 2 % of threads that touch the reflection / the image edge take the general path.
 template <typename T>
 __global__ void __launch_bounds__(256)
 out_conv_dgrad_kernel(const float* __restrict__ dv, const float* __restrict__ w, T* __restrict__ da,
@@ -71,41 +73,80 @@ out_conv_dgrad_kernel(const float* __restrict__ dv, const float* __restrict__ w,
   for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i % 49][i / 49] = w[i];   // w is [c][tap]
   __syncthreads();
   const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
-  const long long total = (long long)B * H * W * 8;
+  const int Wg = W / 4;
+  const long long total = (long long)B * H * Wg * 8;
   if (item >= total) return;
   const int c8 = int(item & 7);
-  const long long pix = item >> 3;
-  const int x = int(pix % W), y = int((pix / W) % H), b = int(pix / ((long long)W * H));
+  const long long grp = item >> 3;
+  const int x0 = int(grp % Wg) * 4, y = int((grp / Wg) % H), b = int(grp / ((long long)Wg * H));
   const float* dvb = dv + (long long)b * H * W;
-  int us[3], vs[3];
-  const int nu = reflect_sources(y, H, 3, us), nv = reflect_sources(x, W, 3, vs);
-  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  for (int iu = 0; iu < nu; ++iu)
-    for (int iv = 0; iv < nv; ++iv) {
-      const int u = us[iu], v = vs[iv];
+  const float sc = gs[0];
+  T* dst = da + (((long long)b * H + y) * W + x0) * 64 + c8 * 8;
+  if (y >= 4 && y <= H - 5 && x0 >= 4 && x0 + 3 <= W - 5) {
+    float acc[4][8];
 #pragma unroll
-      for (int r = 0; r < 7; ++r) {
-        const int yo = u - r;
-        if (yo < 0 || yo >= H) continue;
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const int xo = v - s;
-          if (xo < 0 || xo >= W) continue;
-          const float g = __ldg(dvb + (long long)yo * W + xo);
-          const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 7 + s][c8 * 8]);
-          const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 7 + s][c8 * 8 + 4]);
-          acc[0] += g * w0.x; acc[1] += g * w0.y; acc[2] += g * w0.z; acc[3] += g * w0.w;
-          acc[4] += g * w1.x; acc[5] += g * w1.y; acc[6] += g * w1.z; acc[7] += g * w1.w;
+      for (int k = 0; k < 8; ++k) acc[i][k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < 7; ++r) {
+      const float* row = dvb + (long long)(y + 3 - r) * W + (x0 - 3);
+      float d[10];
+#pragma unroll
+      for (int j = 0; j < 10; ++j) d[j] = __ldg(row + j);
+#pragma unroll
+      for (int s = 0; s < 7; ++s) {
+        const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 7 + s][c8 * 8]);
+        const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 7 + s][c8 * 8 + 4]);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const float g = d[i + 6 - s];   // dv[y+3-r][x0+i+3-s]
+          acc[i][0] += g * w0.x; acc[i][1] += g * w0.y; acc[i][2] += g * w0.z; acc[i][3] += g * w0.w;
+          acc[i][4] += g * w1.x; acc[i][5] += g * w1.y; acc[i][6] += g * w1.z; acc[i][7] += g * w1.w;
         }
       }
     }
-  const float sc = gs[0];
-  uint4 o;
-  o.x = Cvt<T>::pack2(acc[0] * sc, acc[1] * sc);
-  o.y = Cvt<T>::pack2(acc[2] * sc, acc[3] * sc);
-  o.z = Cvt<T>::pack2(acc[4] * sc, acc[5] * sc);
-  o.w = Cvt<T>::pack2(acc[6] * sc, acc[7] * sc);
-  *reinterpret_cast<uint4*>(da + pix * 64 + c8 * 8) = o;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      float o8[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) o8[k] = acc[i][k] * sc;
+      uint4 o;
+      o.x = Cvt<T>::pack2(o8[0], o8[1]); o.y = Cvt<T>::pack2(o8[2], o8[3]);
+      o.z = Cvt<T>::pack2(o8[4], o8[5]); o.w = Cvt<T>::pack2(o8[6], o8[7]);
+      *reinterpret_cast<uint4*>(dst + i * 64) = o;
+    }
+    return;
+  }
+  for (int i = 0; i < 4; ++i) {
+    const int x = x0 + i;
+    int us[3], vs[3];
+    const int nu = reflect_sources(y, H, 3, us), nv = reflect_sources(x, W, 3, vs);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int iu = 0; iu < nu; ++iu)
+      for (int iv = 0; iv < nv; ++iv) {
+        const int u = us[iu], v = vs[iv];
+        for (int r = 0; r < 7; ++r) {
+          const int yo = u - r;
+          if (yo < 0 || yo >= H) continue;
+          for (int s2 = 0; s2 < 7; ++s2) {
+            const int xo = v - s2;
+            if (xo < 0 || xo >= W) continue;
+            const float g = __ldg(dvb + (long long)yo * W + xo);
+            const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 7 + s2][c8 * 8]);
+            const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 7 + s2][c8 * 8 + 4]);
+            acc[0] += g * w0.x; acc[1] += g * w0.y; acc[2] += g * w0.z; acc[3] += g * w0.w;
+            acc[4] += g * w1.x; acc[5] += g * w1.y; acc[6] += g * w1.z; acc[7] += g * w1.w;
+          }
+        }
+      }
+    uint4 o;
+    o.x = Cvt<T>::pack2(acc[0] * sc, acc[1] * sc);
+    o.y = Cvt<T>::pack2(acc[2] * sc, acc[3] * sc);
+    o.z = Cvt<T>::pack2(acc[4] * sc, acc[5] * sc);
+    o.w = Cvt<T>::pack2(acc[6] * sc, acc[7] * sc);
+    *reinterpret_cast<uint4*>(dst + i * 64) = o;
+  }
 }
 
 // dw[c][r][s] = sum over padded pixels (u,v) of in_pad[u][v][c] * dv[u-r][v-s]   (dv zero outside the image)
@@ -317,16 +358,26 @@ cbam_bwd_dz_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const f
   pmax_idx[((long long)b * gridDim.x + blk) * kCbamC + c] = bi;
 }
 
-__global__ void cbam_argmax_finalize_kernel(const float* __restrict__ pmax_val, const int* __restrict__ pmax_idx, int nblk,
-                                            int* __restrict__ amax_pix) {
-  const int c = threadIdx.x, b = blockIdx.x;
+// one warp per (sample, channel): lanes scan the CTA partials, ties resolve to the smallest pixel index (first occurrence)
+__global__ void __launch_bounds__(256)
+cbam_argmax_finalize_kernel(const float* __restrict__ pmax_val, const int* __restrict__ pmax_idx, int nblk,
+                            int* __restrict__ amax_pix) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int c = blockIdx.x * 8 + warp, b = blockIdx.y;
   float bv = -INFINITY;
-  int bi = 0;
-  for (int k = 0; k < nblk; ++k) {   // CTAs cover increasing pixel ranges: strict > keeps the first occurrence
+  int bi = 0x7fffffff;
+  for (int k = lane; k < nblk; k += 32) {
     const float v = pmax_val[((long long)b * nblk + k) * kCbamC + c];
-    if (v > bv) { bv = v; bi = pmax_idx[((long long)b * nblk + k) * kCbamC + c]; }
+    const int i = pmax_idx[((long long)b * nblk + k) * kCbamC + c];
+    if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
   }
-  amax_pix[b * kCbamC + c] = bi;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > bv || (ov == bv && oi < bi)) { bv = ov; bi = oi; }
+  }
+  if (lane == 0) amax_pix[b * kCbamC + c] = bi;
 }
 
 // pass B: adjoint of the 2 -> 1 7x7 spatial-attention conv: dpooled [B][H][W][2] and per-CTA partial weight gradients
@@ -533,6 +584,7 @@ extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, con
                                         ducosy_stream_t stream) {
   DUCOSY_CHECK(dout && out && in_pad && w && da && dw && db && scratch && gs, DUCOSY_ERR_ARG, "out_conv_backward: null pointer");
   DUCOSY_CHECK(B > 0 && H >= 8 && W >= 8, DUCOSY_ERR_SHAPE, "out_conv_backward: needs B > 0 and H, W >= 8 (got %d x %d x %d)", B, H, W);
+  DUCOSY_CHECK(W % 4 == 0, DUCOSY_ERR_SHAPE, "out_conv_backward: W must be a multiple of 4 (got %d)", W);
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "out_conv_backward: bad dtype");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * H * W;
@@ -543,7 +595,7 @@ extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, con
   DUCOSY_TRY(check_launch("out_tanh_bwd_kernel"));
   sum_partials_kernel<<<1, 256, 0, st>>>(tpart, kTanhBlocks, db);
   DUCOSY_TRY(check_launch("sum_partials_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_dgrad_kernel<T><<<grid_items(n * 8, 256), 256, 0, st>>>(dv, w, static_cast<T*>(da), gs, B, H, W)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_dgrad_kernel<T><<<grid_items(n * 2, 256), 256, 0, st>>>(dv, w, static_cast<T*>(da), gs, B, H, W)));
   DUCOSY_TRY(check_launch("out_conv_dgrad_kernel"));
   const int blocks = min(kOutWgradBlocks, B * (H + 6));
   const size_t smem = size_t(7) * (W + 12) * sizeof(float);
@@ -614,7 +666,7 @@ extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const floa
                                       static_cast<const T*>(dout), static_cast<const T*>(yb), scale_v, shift_v, sa, dz, pmax_val,
                                       pmax_idx, HW)));
   DUCOSY_TRY(check_launch("cbam_bwd_dz_kernel"));
-  cbam_argmax_finalize_kernel<<<B, kCbamC, 0, st>>>(pmax_val, pmax_idx, nblk, amax_pix);
+  cbam_argmax_finalize_kernel<<<dim3(kCbamC / 8, B), 256, 0, st>>>(pmax_val, pmax_idx, nblk, amax_pix);
   DUCOSY_TRY(check_launch("cbam_argmax_finalize_kernel"));
   cbam_sa_bwd_kernel<<<sablk, 256, 0, st>>>(dz, pooled, wsa, dpooled, pdw, B, H, W);
   DUCOSY_TRY(check_launch("cbam_sa_bwd_kernel"));
