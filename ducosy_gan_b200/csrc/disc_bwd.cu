@@ -247,16 +247,26 @@ __global__ void dgrad_s1_edge_cols_kernel(const T* __restrict__ dy_pad2, const T
     dxpad[(((long long)b * (H + 2) + u) * (W + 2) + v) * Ci + c] = Cvt<T>::from_f(acc);
   }
 }
-// Co = 256 (the residual blocks): one warp per input channel c keeps its 3 x 256 filter taps in registers (8 per lane,
-// coalesced) and walks a chunk of (b, u) positions; the dy rows are 512-byte coalesced reads shared by the 8 warps.
+// Co = 256 (the residual blocks): a CTA = 8 input channels (one per warp, its 3 x 256 filter taps in registers, 8 per
+// lane) x one chunk of rows of one sample; the dy rows the chunk meets are staged once in shared memory, so L2 sees each
+// of them once per 8 channels instead of once per channel.
 template <typename T>
 __global__ void __launch_bounds__(256)
 dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H, int W,
-                             int Ci, int pos_per_block) {
+                             int Ci, int rows_per_chunk, int chunks_per_sample) {
   constexpr int Co = 256;
+  extern __shared__ uint4 srows[];   // [rows_per_chunk + 2][32] 16-byte pieces: dy_pad2 rows u0 .. u1+1 at column v - s + 2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + warp, side = blockIdx.y;
+  const int b = blockIdx.z / chunks_per_sample, chunk = blockIdx.z % chunks_per_sample;
+  const int u0 = chunk * rows_per_chunk, u1 = min(H + 2, u0 + rows_per_chunk);
+  if (u0 >= u1) return;
   const int v = side ? W + 1 : 0, s = side ? 2 : 0;
+  const int nrows = u1 - u0 + 2;
+  for (int i = threadIdx.x; i < nrows * 32; i += 256) {
+    const int j = i >> 5, piece = i & 31;
+    srows[i] = *reinterpret_cast<const uint4*>(dy_pad2 + (((long long)b * (H + 4) + (u0 + j)) * (W + 4) + (v - s + 2)) * Co + piece * 8);
+  }
   float wr[3][8];
 #pragma unroll
   for (int r = 0; r < 3; ++r) {
@@ -269,15 +279,12 @@ dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict_
       wr[r][2 * k + 1] = f.y;
     }
   }
-  const int total = B * (H + 2);
-  const int p0 = blockIdx.z * pos_per_block, p1 = min(total, p0 + pos_per_block);
-  for (int pos = p0; pos < p1; ++pos) {
-    const int b = pos / (H + 2), u = pos - b * (H + 2);
+  __syncthreads();
+  for (int u = u0; u < u1; ++u) {
     float acc = 0.f;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-      const uint4 dv = *reinterpret_cast<const uint4*>(
-          dy_pad2 + (((long long)b * (H + 4) + (u - r + 2)) * (W + 4) + (v - s + 2)) * Co + lane * 8);
+      const uint4 dv = srows[(u - r + 2 - u0) * 32 + lane];   // dy_pad2 row u - r + 2
       const uint32_t dw[4] = {dv.x, dv.y, dv.z, dv.w};
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
@@ -674,12 +681,13 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
   p.partials = nullptr; p.dtype = dtype;
   DUCOSY_TRY(launch_conv_gemm(p, static_cast<cudaStream_t>(stream)));
   if (Cout == 256 && Cin % 8 == 0) {
-    const int positions = B * (H + 2), chunks = std::max(1, std::min(positions, (148 * 16) / std::max(1, Cin / 8 * 2)));
-    const int per = (positions + chunks - 1) / chunks;
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols256_kernel<T><<<dim3(Cin / 8, 2, (positions + per - 1) / per), 256, 0,
-                                                                      (cudaStream_t)stream>>>(
+    const int cps = std::max(1, std::min(H + 2, (148 * 16) / std::max(1, Cin / 8 * 2 * B)));
+    const int per = (H + 2 + cps - 1) / cps, chunks = (H + 2 + per - 1) / per;
+    const size_t smem = size_t(per + 2) * 512;
+    DUCOSY_CHECK(smem <= 48 * 1024, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: H too large for the edge-column kernel");
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols256_kernel<T><<<dim3(Cin / 8, 2, B * chunks), 256, smem, (cudaStream_t)stream>>>(
                                         static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,
-                                        Cin, per)));
+                                        Cin, per, chunks)));
     return check_launch("dgrad_s1_edge_cols256_kernel");
   }
   const long long total = (long long)B * (H + 2) * 2 * Cin;

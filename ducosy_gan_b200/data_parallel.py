@@ -1,0 +1,147 @@
+"""Batch-sharded (data-parallel) CycleGAN step: one process per GPU, each with full replicas of G_A2B / G_B2A / D_A / D_B
+and 1/world of the batch (BASELINE config 4).  Replaces the reference's ``nn.DataParallel`` wrapping
+(modules/trainer.py:333-338: per-forward parameter broadcast + gather to GPU 0) with the one exchange the step
+really has: a gradient all-reduce (mean) over NCCL/NVLink per optimiser, on a flat bucket the parameter ``.grad``
+tensors are views of (no flatten / unflatten copies).
+
+InstanceNorm is per sample, so activations need no synchronisation.  Two loss terms are *batch-global* in the
+reference -- ContrastRegionLoss and ContrastEdgeLoss take an unbiased std (and a top-10 % mean) over the whole batch
+tensor (trainer.py:117-127,163-181) -- so their three inputs are all-gathered (1 MB per sample each) and the terms are
+evaluated on the full batch on every rank; with the mean-all-reduce that follows, weighting them by ``world`` gives
+exactly the gradient of the single-process step.
+"""
+from __future__ import annotations
+
+import torch
+import torch.distributed as dist
+
+from .losses import l1_loss, mse_gan_loss
+from .trainer import CycleGANStep
+
+
+class GradBucket:
+    """Flat fp32 gradient buffer; every ``p.grad`` is a view into it, ``all_reduce_mean`` is one collective."""
+
+    def __init__(self, params):
+        self.params = [p for p in params if p.requires_grad]
+        total = sum(p.numel() for p in self.params)
+        dev = self.params[0].device
+        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        off = 0
+        for p in self.params:
+            p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def zero(self):
+        self.flat.zero_()
+        off = 0
+        for p in self.params:            # re-attach views an optimizer.zero_grad(set_to_none=True) may have dropped
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4:
+                p.grad = self.flat[off:off + p.numel()].view_as(p)
+            off += p.numel()
+
+    def all_reduce_mean(self, group=None, async_op=False):
+        world = dist.get_world_size(group)
+        if world == 1:
+            return None
+        if dist.get_backend(group) == "nccl":
+            return dist.all_reduce(self.flat, op=dist.ReduceOp.AVG, group=group, async_op=async_op)
+        work = dist.all_reduce(self.flat, op=dist.ReduceOp.SUM, group=group, async_op=False)   # gloo has no AVG
+        self.flat.div_(world)
+        return work
+
+
+class _AllGatherBatch(torch.autograd.Function):
+    """[b, ...] per rank -> [world*b, ...] on every rank (rank-major).  Backward hands each rank the slice of the
+    gradient that belongs to its own samples: every rank evaluates the same full-batch loss, so no reduction is due."""
+
+    @staticmethod
+    def forward(ctx, x, group):
+        ctx.group = group
+        world = dist.get_world_size(group)
+        x = x.contiguous()
+        out = torch.empty((world * x.shape[0],) + tuple(x.shape[1:]), dtype=x.dtype, device=x.device)
+        dist.all_gather_into_tensor(out, x, group=group)
+        ctx.b = x.shape[0]
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        r = dist.get_rank(ctx.group)
+        return g[r * ctx.b:(r + 1) * ctx.b].contiguous(), None
+
+
+def all_gather_batch(x, group=None):
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return x
+    return _AllGatherBatch.apply(x, group)
+
+
+def shard_batch(n, rank, world):
+    """Contiguous sample range of this rank: [n*rank//world, n*(rank+1)//world)."""
+    return n * rank // world, n * (rank + 1) // world
+
+
+class DataParallelCycleGANStep(CycleGANStep):
+    """``CycleGANStep`` over the local shard of the batch, with the gradient exchange between backward and optimiser step.
+    Every rank must construct it with the same ``seed`` (identical replicas, as DataParallel's broadcast guarantees)."""
+
+    def __init__(self, *args, group=None, **kw):
+        if kw.get("seed") is None:
+            raise ValueError("data-parallel replicas need a common seed")
+        super().__init__(*args, **kw)
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.bucket_G = GradBucket(list(self.G_A2B.parameters()) + list(self.G_B2A.parameters()))
+        self.bucket_D_A = GradBucket(list(self.D_A.parameters()))
+        self.bucket_D_B = GradBucket(list(self.D_B.parameters()))
+
+    def generator_losses(self, real_A, real_B, masks=None):
+        if self.world == 1:
+            return super().generator_losses(real_A, real_B, masks)
+        # identical to CycleGANStep.generator_losses except that the two batch-global criteria see the gathered batch
+        cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
+        real_A_input, real_B_input = cat(real_A), cat(real_B)
+        fake_B, fake_A = self.G_A2B(real_A_input), self.G_B2A(real_B_input)
+        id_A, id_B = self.G_B2A(real_A_input), self.G_A2B(real_B_input)
+        loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
+        loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
+        rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
+        loss_cycle = (l1_loss(rec_A, real_A) + l1_loss(rec_B, real_B)) / 2
+        loss_grad_cycle = (self.criterion_gradient(rec_A, real_A) + self.criterion_gradient(rec_B, real_B)) / 2
+        loss_grad_id = (self.criterion_gradient(id_A, real_A) + self.criterion_gradient(id_B, real_B)) / 2
+        loss_ssim = 1 - ((self.criterion_ssim(rec_A, real_A) + self.criterion_ssim(rec_B, real_B)) / 2)
+        loss_att = self.criterion_contrast_attention(fake_B, real_B, real_A)
+        g = self.group
+        fake_B_all, real_B_all, real_A_all = all_gather_batch(fake_B, g), all_gather_batch(real_B, g), all_gather_batch(real_A, g)
+        loss_region = self.criterion_contrast_region(fake_B_all, real_B_all, real_A_all)
+        loss_edge = self.criterion_contrast_edge(fake_B_all, real_B_all, real_A_all)
+        w = float(self.world)   # see the module docstring: full-batch terms x world, then mean-all-reduce
+        loss_G = (loss_GAN + self.lambda_cyc * loss_cycle + self.lambda_id * loss_id + 5.0 * loss_grad_cycle + 2.5 * loss_grad_id
+                  + 2.0 * loss_ssim + 2.0 * loss_att + w * (1.5 * loss_region + 1.0 * loss_edge))
+        terms = dict(GAN=loss_GAN, cycle=loss_cycle, id=loss_id, grad_cycle=loss_grad_cycle, grad_id=loss_grad_id, ssim=loss_ssim,
+                     contrast_attention=loss_att, contrast_region=loss_region, contrast_edge=loss_edge)
+        return loss_G, terms, fake_A, fake_B
+
+    def step(self, real_A, real_B, masks=None):
+        """real_A / real_B / masks are this rank's shard of the batch."""
+        self.bucket_G.zero()
+        loss_G, terms, fake_A, fake_B = self.generator_losses(real_A, real_B, masks)
+        loss_G.backward()
+        self.bucket_G.all_reduce_mean(self.group)
+        self.optimizer_G.step()
+
+        self.bucket_D_A.zero()   # also discards what loss_G.backward() left in the discriminators (trainer.py:517)
+        loss_D_A = (mse_gan_loss(self.D_A(real_A), True) + mse_gan_loss(self.D_A(fake_A.detach()), False)) / 2
+        loss_D_A.backward()
+        self.bucket_D_A.all_reduce_mean(self.group)
+        self.optimizer_D_A.step()
+
+        self.bucket_D_B.zero()
+        loss_D_B = (mse_gan_loss(self.D_B(real_B), True) + mse_gan_loss(self.D_B(fake_B.detach()), False)) / 2
+        loss_D_B.backward()
+        self.bucket_D_B.all_reduce_mean(self.group)
+        self.optimizer_D_B.step()
+        out = {k: v.detach() for k, v in terms.items()}
+        out.update(G=loss_G.detach(), D_A=loss_D_A.detach(), D_B=loss_D_B.detach())
+        return out

@@ -57,3 +57,60 @@ def _worker(rank, world, port, S, tmpdir):
 def test_two_rank_gloo_sharded_volume(tmp_path):
     port = 29500 + os.getpid() % 2000
     mp.spawn(_worker, args=(2, port, 37, str(tmp_path)), nprocs=2, join=True)
+
+
+# ------------------------------------------------------------------ training exchange step
+def _dp_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ducosy_gan_b200.data_parallel import GradBucket, all_gather_batch, shard_batch
+    torch.manual_seed(0)                                    # identical replicas on every rank
+    params = [torch.nn.Parameter(torch.randn(s)) for s in [(4, 3, 3, 3), (4,), (7, 5)]]
+    bucket = GradBucket(params)
+    full_x = torch.arange(4 * 5, dtype=torch.float32).reshape(4, 5) / 10.0
+    lo, hi = shard_batch(4, rank, world)
+    x = full_x[lo:hi]
+
+    def loss_fn(batch):                                     # a per-sample-mean loss, like the L1 / MSE terms
+        return ((batch @ params[2].t()) ** 2).mean() + params[0].sum() * batch.mean() + (params[1] ** 2).sum()
+
+    bucket.zero()
+    loss_fn(x).backward()
+    for p in params:                                        # autograd accumulated in place: still views of the bucket
+        assert p.grad.data_ptr() >= bucket.flat.data_ptr() and p.grad.data_ptr() < bucket.flat.data_ptr() + bucket.flat.numel() * 4
+    bucket.all_reduce_mean()
+    got = [p.grad.clone() for p in params]
+    ref_params = [p.detach().clone().requires_grad_(True) for p in params]
+    ((full_x @ ref_params[2].t()) ** 2).mean().add(ref_params[0].sum() * full_x.mean()).add((ref_params[1] ** 2).sum()).backward()
+    for g, r in zip(got, ref_params):
+        assert torch.allclose(g, r.grad, rtol=1e-5, atol=1e-6), (g - r.grad).abs().max()
+    # set_to_none zero_grad must not detach the views for good
+    torch.optim.SGD(params, lr=0.1).zero_grad(set_to_none=True)
+    bucket.zero()
+    assert all(p.grad is not None and p.grad.abs().sum() == 0 for p in params)
+
+    # all-gather with autograd: a batch-global statistic (unbiased std over the whole batch, trainer.py:117-127)
+    w = torch.nn.Parameter(torch.tensor([1.5, -0.5]))
+    bucket2 = GradBucket([w])
+    bucket2.zero()
+    local = x[:, :2] * w
+    gathered = all_gather_batch(local)
+    assert gathered.shape[0] == 4
+    (world * gathered.std()).backward()                     # full-batch term x world, then mean-all-reduce
+    bucket2.all_reduce_mean()
+    w_ref = w.detach().clone().requires_grad_(True)
+    (full_x[:, :2] * w_ref).std().backward()
+    assert torch.allclose(w.grad, w_ref.grad, rtol=1e-5, atol=1e-6), (w.grad, w_ref.grad)
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_gradient_exchange():
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_dp_worker, args=(2, port), nprocs=2, join=True)
+
+
+@pytest.mark.parametrize("world", [1, 2, 4, 8])
+def test_shard_batch_covers(world):
+    from ducosy_gan_b200.data_parallel import shard_batch
+    r = [shard_batch(8, k, world) for k in range(world)]
+    assert r[0][0] == 0 and r[-1][1] == 8 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
