@@ -156,6 +156,50 @@ def run_reference(args, rank):
     }), flush=True)
 
 
+def train_metric(device, rank, world, steps, warmup=2):
+    """Second half of BASELINE.json's metric: CycleGAN train steps/s (config 4: batch 8, 512x512, soft-tissue generators
+    with two mask channels, all losses, three Adam steps).  The global batch of 8 is sharded over the ranks with a NCCL
+    gradient all-reduce (strong scaling).  Every step copies its batch from pinned host memory and reads the loss back."""
+    import torch.distributed as dist
+    from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, shard_batch
+    B, cin = 8, 3
+    if world > B:
+        return None
+    lo, hi = shard_batch(B, rank, world)
+    g = torch.Generator().manual_seed(2)
+    host = [(torch.rand(B, 1, H, W, generator=g) * 2 - 1)[lo:hi].contiguous().pin_memory() for _ in range(2)]
+    host.append((torch.rand(B, cin - 1, H, W, generator=g) < 0.1).float()[lo:hi].contiguous().pin_memory())
+    step = DataParallelCycleGANStep(cin, 9, True, seed=1234, device=device)
+
+    def one():
+        a, b, m = (t.to(device, non_blocking=True) for t in host)
+        return step.step(a, b, m)["G"].item()
+
+    for _ in range(warmup):
+        one()
+    if world > 1:
+        dist.barrier(device_ids=[device.index])
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = one()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = float(ms.item())
+    tflop = (6 * B * 451.11 * 3 + 6 * B * 13.04 * 3) / 1e3      # SURVEY 8(d): nominal conv work, backward = 2x forward
+    return {"metric": "cyclegan_train_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
+            "warmup": warmup, "global_batch": B, "scaling": "strong", "loss_G": loss,
+            "config": "G_A2B/G_B2A (Cin 3, 9 CBAM blocks) + D_A/D_B, 512x512, all 9 loss terms, 3 fused Adam steps; "
+                      f"batch 8 sharded x{world}" + (", NCCL gradient all-reduce" if world > 1 else ""),
+            "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": 4,
+            "nominal_tflop_per_step": tflop, "achieved_tflops_nominal": tflop / ms * 1e3 / world,
+            "frac_of_sustained_peak_per_gpu": tflop / ms * 1e3 / world / peaks()["tf_sustained"]}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -164,6 +208,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-slices", type=int, default=int(os.environ.get("DUCOSY_BATCH_SLICES", "30")))
     ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=3, help="timed CycleGAN steps for the 'train' object (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
@@ -221,11 +266,17 @@ def main():
     e2e_step()
     sec_e2e = timed(e2e_step, args.steps)
 
-    value = world * S * args.steps / sec
-    e2e_value = world * S * args.steps / sec_e2e
     chunks = (S + args.batch_slices - 1) // args.batch_slices
     launches = synth.launches_per_chunk() * chunks * args.steps
+    train = None
+    if args.train_steps > 0:
+        del dev_out, dev_vol
+        synth = None
+        torch.cuda.empty_cache()
+        train = train_metric(device, rank, world, args.train_steps)
 
+    value = world * S * args.steps / sec
+    e2e_value = world * S * args.steps / sec_e2e
     if rank == 0:
         pk = peaks()
         ksec, kflops = time_dominant_kernel(device, args.batch_slices)
@@ -247,6 +298,8 @@ def main():
                          "traffic": None, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                          "path_frac_of_sustained": value / world * GFLOP_PER_SLICE / 1e3 / pk["tf_sustained"]},
         }
+        if train is not None:
+            line["train"] = train
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
         print(json.dumps(line), flush=True)

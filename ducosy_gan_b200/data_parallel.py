@@ -41,6 +41,8 @@ class GradBucket:
             off += p.numel()
 
     def all_reduce_mean(self, group=None, async_op=False):
+        if not dist.is_initialized():
+            return None
         world = dist.get_world_size(group)
         if world == 1:
             return None
