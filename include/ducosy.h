@@ -162,6 +162,17 @@ int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed, const floa
 int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* scale, const float* shift, const void* w_packed,
                                   const float* bias, float* out, int B, int H, int W, int dtype, ducosy_stream_t stream);
 
+/* Post-composite volume smoothing (generate.py:254-263 + modules/postprocess.py:47-60,99-109,114-160):
+ * z Gaussian (float32) -> z Gaussian (float32) -> xy unsharp mask in float64 -> clip to the range of the first result ->
+ * voxels >= hu_threshold keep the first result -> int16 (truncation).  Bit-exact with scipy's correlate1d arithmetic
+ * (symmetric-kernel order, no FMA, mode 'reflect').  merged/out: device int16 [S][H][W]; scratch: device,
+ * ducosy_postprocess_scratch_bytes; wz1/wz2/wxy: HOST arrays of 2r+1 normalised float64 weights (radius 1..4 for z,
+ * 1..8 for xy), as scipy.ndimage computes them. */
+size_t ducosy_postprocess_scratch_bytes(int S, int H, int W);
+int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, float* scratch, int S, int H, int W, const double* wz1, int rz1,
+                              const double* wz2, int rz2, const double* wxy, int rxy, double sharpen_amount, float hu_threshold,
+                              ducosy_stream_t stream);
+
 /* Generator backward pieces (what autograd computes through modules/model.py:90-92 and :112-113 for
  * modules/trainer.py:497).  16-bit gradient maps carry the power-of-two scale gs[0]; fp32 results leave with the true scale.
  *

@@ -418,3 +418,39 @@ def generator_forward_rounded(sd, x, nb=9, cbam=True, dt=torch.float16):
         idx += 4
     h = F.conv2d(F.pad(h, (3, 3, 3, 3), mode="reflect"), r(sd[f"model.{idx + 1}.weight"]), sd[f"model.{idx + 1}.bias"])
     return torch.tanh(h)
+
+
+# --------------------------------------------------------------------------------------
+# post-composite volume smoothing
+# --------------------------------------------------------------------------------------
+def postprocess_test_volume(S: int, H: int, W: int, seed: int) -> np.ndarray:
+    """Seeded int16 volume for the post-processing tests: noisy soft tissue, a flat air region (exactly constant: the
+    case where 1-ulp differences of a float64 blur would flip the int16 truncation), bone >= 750 (kept voxels), and
+    slice-to-slice jumps for the z filters."""
+    g = np.random.Generator(np.random.PCG64(seed))
+    vol = g.normal(1060.0, 40.0, size=(S, H, W))
+    vol += (np.arange(S) % 3)[:, None, None] * 25.0                     # stair-steps along z
+    vol[:, : H // 4, : W // 3] = 24.0                                    # air, flat
+    vol[:, H // 2: H // 2 + 6, W // 2: W // 2 + 9] = g.normal(1900.0, 200.0, size=(S, 6, 9))   # bone
+    vol[S // 2:, -5:, :] = 700.0 + g.integers(0, 120, size=(S - S // 2, 5, W))                 # straddles the 750 threshold
+    return np.clip(np.rint(vol), -2000, 4000).astype(np.int16)
+
+
+def postprocess_volume(merged: np.ndarray, pre_sigma_z=0.8, sigma_z=0.7, sigma_xy=0.05, sharpen_amount=1.7,
+                       sharpen_radius=1.2, hu_threshold=750) -> np.ndarray:
+    """generate.py:254-263 followed through modules/postprocess.py:45-50 (copy + mask), :58-60 (gaussian3d), :99-103
+    (unsharp call), :106 (restore), :109 (int16) and unsharp_mask :140-160, with scipy doing the filtering exactly as in
+    the reference.  merged: int16 [S,H,W] -> int16 [S,H,W]."""
+    from scipy.ndimage import gaussian_filter, gaussian_filter1d
+    vol = np.array(merged, dtype=np.float32)                                         # generate.py:255
+    vol = gaussian_filter1d(vol, sigma=pre_sigma_z, axis=0)                          # generate.py:258-259
+    original = vol.copy()                                                            # postprocess.py:47
+    high = vol >= hu_threshold                                                       # postprocess.py:50
+    pp = gaussian_filter(vol, sigma=(sigma_z, sigma_xy, sigma_xy))                   # postprocess.py:58-60
+    sm, orig = pp.astype(np.float64), original.astype(np.float64)                    # postprocess.py:140-141
+    hf = sm - gaussian_filter(sm, sigma=(0, sharpen_radius, sharpen_radius))         # postprocess.py:145-146
+    ohf = orig - gaussian_filter(orig, sigma=(0, sharpen_radius, sharpen_radius))    # postprocess.py:149-150
+    comb = (1 - sharpen_amount) * hf + sharpen_amount * ohf                          # postprocess.py:153
+    sharp = np.clip(sm + comb * sharpen_amount, orig.min(), orig.max())              # postprocess.py:156-159
+    sharp[high] = original[high]                                                     # postprocess.py:106
+    return sharp.astype(np.int16)                                                    # postprocess.py:109

@@ -124,3 +124,13 @@ def test_ssim_unpinned_restatement_sanity():
     assert abs(orc.ssim(x, x).item() - 1.0) < 1e-6
     assert orc.ssim(x, -x).item() < 0.99
     assert orc.ssim(x, 0.5 * x).item() < 1.0
+
+
+def test_postprocess_volume_matches_reference_golden(golden_dir):
+    """the oracle restatement against outputs of the reference's own generate.py:254-263 +
+    modules/postprocess.py (tests/golden/postprocess.npz, made by oracle/make_golden_postprocess.py) -- bit-exact."""
+    g = np.load(os.path.join(golden_dir, "postprocess.npz"))
+    for name in "abc":
+        S, H, W, seed = (int(v) for v in g[f"shape_{name}"])
+        vol = orc.postprocess_test_volume(S, H, W, seed)
+        assert np.array_equal(orc.postprocess_volume(vol), g[f"out_{name}"]), name
