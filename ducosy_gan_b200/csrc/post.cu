@@ -40,7 +40,7 @@ __device__ __forceinline__ double to_d(float v) { return double(v); }
 template <typename TIn, int R, bool kMinMax>
 __global__ void __launch_bounds__(256)
 zfilter_kernel(const TIn* __restrict__ in, float* __restrict__ out, float* __restrict__ pmin, float* __restrict__ pmax, int S,
-               long long HW, PostWeights pw, int which) {
+               long long HW, PostWeights pw, int which, int mm_z0, int mm_z1) {
   const double* w = which == 1 ? pw.wz1 : pw.wz2;
   const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
   float mn = INFINITY, mx = -INFINITY;
@@ -54,7 +54,7 @@ zfilter_kernel(const TIn* __restrict__ in, float* __restrict__ out, float* __res
       for (int j = -R; j < 0; ++j) tmp = __dadd_rn(tmp, __dmul_rn(__dadd_rn(win[R + j], win[R - j]), w[R + j]));
       const float o = float(tmp);
       out[(long long)z * HW + p] = o;
-      if (kMinMax) { mn = fminf(mn, o); mx = fmaxf(mx, o); }
+      if (kMinMax && z >= mm_z0 && z < mm_z1) { mn = fminf(mn, o); mx = fmaxf(mx, o); }
 #pragma unroll
       for (int j = 0; j < 2 * R; ++j) win[j] = win[j + 1];
       win[2 * R] = to_d(in[(long long)reflect_ext(z + 1 + R, S) * HW + p]);
@@ -162,9 +162,16 @@ extern "C" size_t ducosy_postprocess_scratch_bytes(int S, int H, int W) {
   return (2 * n + 2 * blocks + 2) * sizeof(float);
 }
 
+extern "C" size_t ducosy_postprocess_minmax_offset_bytes(int S, int H, int W) {
+  return ducosy_postprocess_scratch_bytes(S, H, W) - 2 * sizeof(float);
+}
+
 extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, float* scratch, int S, int H, int W,
                                          const double* wz1, int rz1, const double* wz2, int rz2, const double* wxy, int rxy,
-                                         double sharpen_amount, float hu_threshold, ducosy_stream_t stream) {
+                                         double sharpen_amount, float hu_threshold, int phases, int mm_z0, int mm_z1,
+                                         ducosy_stream_t stream) {
+  DUCOSY_CHECK(phases >= 1 && phases <= 3 && mm_z0 >= 0 && mm_z1 <= S && mm_z0 < mm_z1, DUCOSY_ERR_ARG,
+               "postprocess_volume: phases must be 1, 2 or 3 and 0 <= mm_z0 < mm_z1 <= S");
   DUCOSY_CHECK(merged && out && scratch && wz1 && wz2 && wxy, DUCOSY_ERR_ARG, "postprocess_volume: null pointer");
   DUCOSY_CHECK(S > 0 && H > 0 && W > 0, DUCOSY_ERR_SHAPE, "postprocess_volume: empty volume");
   DUCOSY_CHECK(rz1 >= 1 && rz1 <= kMaxRZ && rz2 >= 1 && rz2 <= kMaxRZ, DUCOSY_ERR_ARG,
@@ -188,7 +195,8 @@ extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, fl
   float* pmax = pmin + blocks;
   float* mm = pmax + blocks;
 #define ZF(TIn, R, MM, src, dst, which)                                                                     \
-  zfilter_kernel<TIn, R, MM><<<blocks, 256, 0, st>>>(src, dst, pmin, pmax, S, HW, pw, which)
+  zfilter_kernel<TIn, R, MM><<<blocks, 256, 0, st>>>(src, dst, pmin, pmax, S, HW, pw, which, mm_z0, mm_z1)
+  if (phases & 1) {
   switch (rz1) {
     case 1: ZF(short, 1, true, merged, v1, 1); break;
     case 2: ZF(short, 2, true, merged, v1, 1); break;
@@ -204,8 +212,10 @@ extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, fl
     case 3: ZF(float, 3, false, v1, pp, 2); break;
     default: ZF(float, 4, false, v1, pp, 2); break;
   }
-#undef ZF
   DUCOSY_TRY(check_launch("zfilter_kernel"));
+  }
+#undef ZF
+  if (!(phases & 2)) return 0;
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, S);
   short* o = reinterpret_cast<short*>(out);
   switch (rxy) {

@@ -6,6 +6,7 @@
         -> soft-tissue Generator, lung Generator  model.py:92-115          (two CUDA streams, batched slices)
         -> de-window + complementary composite    preprocess.py:96-111, generate.py:218-237   (one kernel)
         -> merged stored values [S,H,W] int16
+        -> (optional) z / unsharp volume smoothing generate.py:254-263                        (postprocess.py, on device)
 
 Slices are independent, so a volume shards across ranks by contiguous slice ranges with no collective
 (``shard_range``).  DICOM I/O stays with the caller (out of scope).
@@ -70,8 +71,11 @@ class DualHUSynthesizer:
                 el.lib.ducosy_generator_num_launches(C.byref(el.cfg)) + 1)
 
     # ------------------------------------------------------------------ device-resident volume
-    def synthesize_device(self, raw_px: torch.Tensor, slope=1.0, intercept=-1024.0, out: torch.Tensor | None = None):
-        """raw_px: int16 [S,H,W] on this GPU -> merged int16 [S,H,W] (same device).  Asynchronous."""
+    def synthesize_device(self, raw_px: torch.Tensor, slope=1.0, intercept=-1024.0, out: torch.Tensor | None = None,
+                          postprocess: bool = False, group=None):
+        """raw_px: int16 [S,H,W] on this GPU -> merged int16 [S,H,W] (same device).  Asynchronous.
+        ``postprocess=True`` appends the volume smoothing of generate.py:254-263 on the device (``postprocess.py``); when
+        the volume is sharded over the ranks of ``group`` this is where the path has its one exchange (z halo)."""
         if raw_px.dtype != torch.int16 or raw_px.dim() != 3 or not raw_px.is_cuda:
             raise RuntimeError("synthesize_device expects an int16 [S,H,W] CUDA tensor of stored pixel values")
         raw_px = raw_px.contiguous()
@@ -113,21 +117,25 @@ class DualHUSynthesizer:
                 cur.wait_stream(s_soft)
                 cur.wait_stream(s_lung)
                 ops.dewindow_composite(chunk, ys, yl, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+            if postprocess:
+                from .postprocess import postprocess_volume_sharded
+                out.copy_(postprocess_volume_sharded(out, group))
         return out
 
     # ------------------------------------------------------------------ host volume (the end-to-end call)
-    def synthesize_volume(self, raw_px, slope=1.0, intercept=-1024.0, out_host: torch.Tensor | None = None):
+    def synthesize_volume(self, raw_px, slope=1.0, intercept=-1024.0, out_host: torch.Tensor | None = None,
+                          postprocess: bool = False, group=None):
         """raw_px: int16 [S,H,W] numpy array or (ideally pinned) CPU tensor -> merged int16 CPU tensor.
         Host->device and device->host copies are part of this call (the reference's .to(device)/.cpu())."""
         if isinstance(raw_px, np.ndarray):
             raw_px = torch.from_numpy(np.ascontiguousarray(raw_px))
         if raw_px.is_cuda:
-            return self.synthesize_device(raw_px, slope, intercept)
+            return self.synthesize_device(raw_px, slope, intercept, postprocess=postprocess, group=group)
         if raw_px.dtype != torch.int16 or raw_px.dim() != 3:
             raise RuntimeError("synthesize_volume expects int16 [S,H,W] stored pixel values")
         with torch.cuda.device(self.device):
             dev_in = raw_px.to(self.device, non_blocking=True)
-            dev_out = self.synthesize_device(dev_in, slope, intercept)
+            dev_out = self.synthesize_device(dev_in, slope, intercept, postprocess=postprocess, group=group)
             if out_host is None:
                 out_host = torch.empty(raw_px.shape, dtype=torch.int16, pin_memory=True)
             out_host.copy_(dev_out, non_blocking=True)

@@ -167,11 +167,15 @@ int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* scale, const f
  * voxels >= hu_threshold keep the first result -> int16 (truncation).  Bit-exact with scipy's correlate1d arithmetic
  * (symmetric-kernel order, no FMA, mode 'reflect').  merged/out: device int16 [S][H][W]; scratch: device,
  * ducosy_postprocess_scratch_bytes; wz1/wz2/wxy: HOST arrays of 2r+1 normalised float64 weights (radius 1..4 for z,
- * 1..8 for xy), as scipy.ndimage computes them. */
+ * 1..8 for xy), as scipy.ndimage computes them.
+ * phases: 1 = the two z filters + (min, max) of the first result over slices [mm_z0, mm_z1) written to the two floats at
+ * ducosy_postprocess_minmax_offset_bytes inside scratch; 2 = the in-plane part, reading that pair; 3 = both.  A
+ * z-sharded volume runs phase 1 on its halo-extended slab, min/max-all-reduces the pair across ranks, then runs phase 2. */
 size_t ducosy_postprocess_scratch_bytes(int S, int H, int W);
+size_t ducosy_postprocess_minmax_offset_bytes(int S, int H, int W);
 int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, float* scratch, int S, int H, int W, const double* wz1, int rz1,
                               const double* wz2, int rz2, const double* wxy, int rxy, double sharpen_amount, float hu_threshold,
-                              ducosy_stream_t stream);
+                              int phases, int mm_z0, int mm_z1, ducosy_stream_t stream);
 
 /* Generator backward pieces (what autograd computes through modules/model.py:90-92 and :112-113 for
  * modules/trainer.py:497).  16-bit gradient maps carry the power-of-two scale gs[0]; fp32 results leave with the true scale.

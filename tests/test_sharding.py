@@ -114,3 +114,24 @@ def test_shard_batch_covers(world):
     from ducosy_gan_b200.data_parallel import shard_batch
     r = [shard_batch(8, k, world) for k in range(world)]
     assert r[0][0] == 0 and r[-1][1] == 8 and all(a[1] == b[0] for a, b in zip(r, r[1:]))
+
+
+# ------------------------------------------------------------------ z halo of the post-composite smoothing
+def _halo_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ducosy_gan_b200.postprocess import Z_HALO, exchange_z_halo
+    S = 29
+    vol = torch.arange(S * 4 * 5, dtype=torch.int16).reshape(S, 4, 5)
+    lo, hi = shard_range(S, rank, world)
+    slab, first = exchange_z_halo(vol[lo:hi].clone(), Z_HALO)
+    elo, ehi = max(0, lo - Z_HALO), min(S, hi + Z_HALO)
+    assert first == lo - elo
+    assert torch.equal(slab, vol[elo:ehi]), (rank, slab.shape)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_gloo_z_halo_exchange(world):
+    port = 33500 + os.getpid() % 2000 + world
+    mp.spawn(_halo_worker, args=(world, port), nprocs=world, join=True)
