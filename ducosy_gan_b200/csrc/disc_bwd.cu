@@ -23,30 +23,38 @@ __device__ __forceinline__ float act_grad(float n, int act) {  // derivative of 
 // Loss gradients are tiny (mean-reduced losses divide by the element count) and would sit in the fp16 subnormal range.
 // The incoming gradient is multiplied by a power of two that brings its max magnitude into [1, 2); the backward is
 // linear, so the final fp32 parameter / input gradients are simply multiplied by the inverse.  gs[0] = scale, gs[1] = 1/scale.
-__global__ void __launch_bounds__(1024)
-grad_scale_kernel(const float* __restrict__ g, long long n, float* __restrict__ gs) {
-  __shared__ float red[32];
+// Two kernels: the max magnitude is collected with an integer atomicMax on the bit pattern (non-negative floats order
+// like their bits; max is exact and order-independent, so the result is deterministic), then one thread derives the scale.
+__global__ void __launch_bounds__(256)
+grad_absmax_kernel(const float* __restrict__ g, long long n, int* __restrict__ slot) {
+  __shared__ float red[8];
   float m = 0.f;
-  for (long long i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, fabsf(g[i]));
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float v = fabsf(g[i]);
+    m = (v > m || v != v) ? v : m;   // NaN propagates to the "not finite" branch below
+  }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  for (int o = 16; o; o >>= 1) {
+    const float t = __shfl_xor_sync(0xffffffffu, m, o);
+    m = (t > m || t != t) ? t : m;
+  }
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    m = red[threadIdx.x];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-    if (threadIdx.x == 0) {
-      int e = 0;
-      if (m > 0.f && isfinite(m)) {
-        frexpf(m, &e);             // m = f * 2^e, f in [0.5, 1)
-        e = 1 - e;                 // m * 2^e in [1, 2)
-        e = max(-60, min(60, e));
-      }
-      gs[0] = ldexpf(1.f, e);
-      gs[1] = ldexpf(1.f, -e);
-    }
+  if (threadIdx.x == 0) {
+    for (int i = 1; i < 8; ++i) m = (red[i] > m || red[i] != red[i]) ? red[i] : m;
+    atomicMax(slot, __float_as_int(m));   // NaN bit patterns (> 0x7f800000) win the max as well
   }
+}
+__global__ void grad_scale_finalize_kernel(float* __restrict__ gs) {
+  const float m = __int_as_float(reinterpret_cast<int*>(gs)[1]);
+  int e = 0;
+  if (m > 0.f && isfinite(m)) {
+    frexpf(m, &e);             // m = f * 2^e, f in [0.5, 1)
+    e = 1 - e;                 // m * 2^e in [1, 2)
+    e = max(-60, min(60, e));
+  }
+  gs[0] = ldexpf(1.f, e);
+  gs[1] = ldexpf(1.f, -e);
 }
 
 // ------------------------------------------------------------------ InstanceNorm(+activation) backward
@@ -467,31 +475,63 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 disc_first_wgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, const float* __restrict__ x,
                         float* __restrict__ partial, int B, int H, int W, int pix_per_block) {
+  // thread = (pixel lane pl 0..7, tap group tg 0..3 = filter row, channel group cg 0..7 = 8 channels): a warp is one pixel
+  // lane, its 128-byte da1 / p1 rows are read with 16-byte loads (shared by the 4 tap groups through L1)
+  __shared__ float red[8][64 * 17];
   const int Ho = H / 2, Wo = W / 2;
-  const int o = threadIdx.x & 63, tg = threadIdx.x >> 6;
+  const int cg = threadIdx.x & 7, tg = (threadIdx.x >> 3) & 3, pl = threadIdx.x >> 5;
   const long long P = (long long)B * Ho * Wo;
   const long long q0 = (long long)blockIdx.x * pix_per_block, q1 = min(q0 + (long long)pix_per_block, P);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f}, bsum = 0.f;
-  for (long long q = q0; q < q1; ++q) {
+  float acc[8][4], bsum[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bsum[j] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[j][k] = 0.f;
+  }
+  for (long long q = q0 + pl; q < q1; q += 8) {
     const int xo = int(q % Wo);
-    long long r = q / Wo;
-    const int yo = int(r % Ho);
-    const int b = int(r / Ho);
-    const float a1 = Cvt<T>::to_f(p1[(((long long)b * (Ho + 2) + yo + 1) * (Wo + 2) + xo + 1) * 64 + o]);
-    const float d = Cvt<T>::to_f(da1[q * 64 + o]) * (a1 > 0.f ? 1.f : 0.2f);
-    bsum += d;
+    const long long r = q / Wo;
+    const int yo = int(r % Ho), b = int(r / Ho);
+    const uint4 aq = *reinterpret_cast<const uint4*>(p1 + (((long long)b * (Ho + 2) + yo + 1) * (Wo + 2) + xo + 1) * 64 + cg * 8);
+    const uint4 dq = *reinterpret_cast<const uint4*>(da1 + q * 64 + cg * 8);
+    const uint32_t aw4[4] = {aq.x, aq.y, aq.z, aq.w}, dw4[4] = {dq.x, dq.y, dq.z, dq.w};
+    float xv[4];
+    const int iy = 2 * yo + tg - 1;
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
-      const int tap = tg * 4 + k, iy = 2 * yo + (tap >> 2) - 1, ix = 2 * xo + (tap & 3) - 1;
-      const float xv = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((long long)b * H + iy) * W + ix) : 0.f;
-      acc[k] = fmaf(d, xv, acc[k]);
+      const int ix = 2 * xo + k - 1;
+      xv[k] = (iy >= 0 && iy < H && ix >= 0 && ix < W) ? __ldg(x + ((long long)b * H + iy) * W + ix) : 0.f;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float2 av = Cvt<T>::unpack2(aw4[j]), dv = Cvt<T>::unpack2(dw4[j]);
+      const float d0 = dv.x * (av.x > 0.f ? 1.f : 0.2f), d1 = dv.y * (av.y > 0.f ? 1.f : 0.2f);
+      bsum[2 * j] += d0;
+      bsum[2 * j + 1] += d1;
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        acc[2 * j][k] = fmaf(d0, xv[k], acc[2 * j][k]);
+        acc[2 * j + 1][k] = fmaf(d1, xv[k], acc[2 * j + 1][k]);
+      }
     }
   }
-  float* dst = partial + (size_t(blockIdx.x) * 64 + o) * 17;
 #pragma unroll
-  for (int k = 0; k < 4; ++k) dst[tg * 4 + k] = acc[k];
-  if (tg == 0) dst[16] = bsum;
+  for (int j = 0; j < 8; ++j) {
+    const int o = cg * 8 + j;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) red[pl][o * 17 + tg * 4 + k] = acc[j][k];
+    if (tg == 0) red[pl][o * 17 + 16] = bsum[j];
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < 64 * 17; i += 256) {
+    float a = 0.f;
+#pragma unroll
+    for (int l = 0; l < 8; ++l) a += red[l][i];          // fixed order: deterministic
+    partial[size_t(blockIdx.x) * 64 * 17 + i] = a;
+  }
 }
+
 __global__ void disc_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
                                                int blocks, const float* __restrict__ gs) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 64 * 17
@@ -527,9 +567,16 @@ __global__ void disc_first_dgrad_kernel(const T* __restrict__ da1, const T* __re
         if (ix + 1 - ss < 0 || xo >= Wo) continue;
         const T* d = da1 + (((long long)b * Ho + yo) * Wo + xo) * 64;
         const T* a = p1 + (((long long)b * (Ho + 2) + yo + 1) * (Wo + 2) + xo + 1) * 64;
-        for (int o = 0; o < 64; ++o) {
-          const float av = Cvt<T>::to_f(a[o]);
-          acc = fmaf(Cvt<T>::to_f(d[o]) * (av > 0.f ? 1.f : 0.2f), sw[o * 16 + rr * 4 + ss], acc);
+#pragma unroll 2
+        for (int o = 0; o < 64; o += 8) {
+          const uint4 dq = *reinterpret_cast<const uint4*>(d + o), aq = *reinterpret_cast<const uint4*>(a + o);
+          const uint32_t dw4[4] = {dq.x, dq.y, dq.z, dq.w}, aw4[4] = {aq.x, aq.y, aq.z, aq.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 dv = Cvt<T>::unpack2(dw4[k]), av = Cvt<T>::unpack2(aw4[k]);
+            acc = fmaf(dv.x * (av.x > 0.f ? 1.f : 0.2f), sw[(o + 2 * k) * 16 + rr * 4 + ss], acc);
+            acc = fmaf(dv.y * (av.y > 0.f ? 1.f : 0.2f), sw[(o + 2 * k + 1) * 16 + rr * 4 + ss], acc);
+          }
         }
       }
     }
@@ -600,8 +647,13 @@ extern "C" int ducosy_convs2_dgrad_nhwc(const void* dy_pad, const void* w_dgrad,
 
 extern "C" int ducosy_grad_scale(const float* g, long long n, float* gs, ducosy_stream_t stream) {
   DUCOSY_CHECK(g && gs && n > 0, DUCOSY_ERR_ARG, "grad_scale: bad argument");
-  grad_scale_kernel<<<1, 1024, 0, (cudaStream_t)stream>>>(g, n, gs);
-  return check_launch("grad_scale_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  DUCOSY_CHECK(cudaMemsetAsync(gs, 0, 2 * sizeof(float), st) == cudaSuccess, DUCOSY_ERR_CUDA, "grad_scale: memset failed");
+  const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 4));
+  grad_absmax_kernel<<<blocks, 256, 0, st>>>(g, n, reinterpret_cast<int*>(gs) + 1);
+  DUCOSY_TRY(check_launch("grad_absmax_kernel"));
+  grad_scale_finalize_kernel<<<1, 1, 0, st>>>(gs);
+  return check_launch("grad_scale_finalize_kernel");
 }
 
 extern "C" int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,

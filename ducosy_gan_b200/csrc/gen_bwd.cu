@@ -150,48 +150,47 @@ out_conv_dgrad_kernel(const float* __restrict__ dv, const float* __restrict__ w,
 }
 
 // dw[c][r][s] = sum over padded pixels (u,v) of in_pad[u][v][c] * dv[u-r][v-s]   (dv zero outside the image)
-// block = 256 threads = 64 channels x 4 tap groups; one padded row per iteration, the 7 dv rows it meets staged in
-// shared memory with zero borders.  partial: [gridDim.x][64*49].
-constexpr int kOutWgradTapsPerGroup = 13;
+// block = 448 threads = 64 channels x 7 filter rows; one padded row per iteration, the 7 dv rows it meets staged in
+// shared memory with zero borders.  A thread keeps the 7 dv values its filter row needs for the current pixel in a
+// register window that slides by one per pixel: 1 shared load + 1 global load per 7 FMAs.  partial: [gridDim.x][64*49].
+constexpr int kOutWgradThreads = 448;
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(kOutWgradThreads)
 out_conv_wgrad_kernel(const T* __restrict__ in_pad, const float* __restrict__ dv, float* __restrict__ partial, int B, int H, int W) {
   extern __shared__ float rows[];                 // [7][W + 12], rows[r][j] = dv[u - r][j - 6]
   const int Wp = W + 6, Hp = H + 6, pitch = W + 12;
-  const int c = threadIdx.x & 63, tg = threadIdx.x >> 6;
-  const int tap0 = tg * kOutWgradTapsPerGroup;
-  float acc[kOutWgradTapsPerGroup];
+  const int c = threadIdx.x & 63, r = threadIdx.x >> 6;
+  float acc[7];
 #pragma unroll
-  for (int i = 0; i < kOutWgradTapsPerGroup; ++i) acc[i] = 0.f;
-  int roff[kOutWgradTapsPerGroup];                // smem offset of tap (r,s) relative to column v: r*pitch + 6 - s
-#pragma unroll
-  for (int i = 0; i < kOutWgradTapsPerGroup; ++i) {
-    const int tap = min(tap0 + i, 48);
-    roff[i] = (tap / 7) * pitch + 6 - (tap % 7);
-  }
+  for (int i = 0; i < 7; ++i) acc[i] = 0.f;
   for (int row = blockIdx.x; row < B * Hp; row += gridDim.x) {
     const int b = row / Hp, u = row % Hp;
     __syncthreads();
-    for (int i = threadIdx.x; i < 7 * pitch; i += 256) {
-      const int r = i / pitch, j = i % pitch, yo = u - r, xo = j - 6;
+    for (int i = threadIdx.x; i < 7 * pitch; i += kOutWgradThreads) {
+      const int rr = i / pitch, j = i % pitch, yo = u - rr, xo = j - 6;
       rows[i] = (yo >= 0 && yo < H && xo >= 0 && xo < W) ? dv[((long long)b * H + yo) * W + xo] : 0.f;
     }
     __syncthreads();
     const T* src = in_pad + ((long long)row * Wp) * 64 + c;
-#pragma unroll 2
+    const float* rw = rows + r * pitch;           // tap s of pixel v reads rw[v + 6 - s]
+    float win[7];                                 // win[k] = rw[v + k], k = 0..6  (tap s uses win[6 - s])
+#pragma unroll
+    for (int k = 0; k < 6; ++k) win[k + 1] = rw[k];
+#pragma unroll 7
     for (int v = 0; v < Wp; ++v) {
+#pragma unroll
+      for (int k = 0; k < 6; ++k) win[k] = win[k + 1];
+      win[6] = rw[v + 6];
       const float a = Cvt<T>::to_f(src[(long long)v * 64]);
 #pragma unroll
-      for (int i = 0; i < kOutWgradTapsPerGroup; ++i) acc[i] += a * rows[roff[i] + v];
+      for (int s = 0; s < 7; ++s) acc[s] = fmaf(a, win[6 - s], acc[s]);
     }
   }
-  float* dst = partial + (long long)blockIdx.x * (64 * 49) + c * 49;
+  float* dst = partial + (long long)blockIdx.x * (64 * 49) + c * 49 + r * 7;
 #pragma unroll
-  for (int i = 0; i < kOutWgradTapsPerGroup; ++i)
-    if (tap0 + i < 49) dst[tap0 + i] = acc[i];
+  for (int s = 0; s < 7; ++s) dst[s] = acc[s];
 }
 
-// tap groups: 0 -> taps 0..12, 1 -> 13..25, 2 -> 26..38, 3 -> 39..48 (10 taps; the clamp above keeps its tail idle)
 __global__ void out_conv_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 49) return;
@@ -600,7 +599,7 @@ extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, con
   const int blocks = min(kOutWgradBlocks, B * (H + 6));
   const size_t smem = size_t(7) * (W + 12) * sizeof(float);
   DUCOSY_CHECK(smem <= 48 * 1024, DUCOSY_ERR_SHAPE, "out_conv_backward: W too large (%d)", W);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_wgrad_kernel<T><<<blocks, 256, smem, st>>>(static_cast<const T*>(in_pad), dv, wpart, B, H, W)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_wgrad_kernel<T><<<blocks, kOutWgradThreads, smem, st>>>(static_cast<const T*>(in_pad), dv, wpart, B, H, W)));
   DUCOSY_TRY(check_launch("out_conv_wgrad_kernel"));
   out_conv_wgrad_reduce_kernel<<<(64 * 49 + 255) / 256, 256, 0, st>>>(wpart, blocks, dw);
   return check_launch("out_conv_wgrad_reduce_kernel");

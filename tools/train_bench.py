@@ -60,6 +60,10 @@ if a.profile:
             d = agg.setdefault(n, [0, 0.0])
             d[0] += 1
             d[1] += ev.device_time
+    if os.environ.get("LIST_KERNEL"):
+        evs = sorted((ev for ev in prof.events() if ev.device_type == torch.autograd.DeviceType.CUDA
+                      and os.environ["LIST_KERNEL"] in ev.name), key=lambda e: e.time_range.start)
+        print(os.environ["LIST_KERNEL"], "durations (us), launch order:", [round(e.device_time) for e in evs][:120])
     tot = sum(v[1] for v in agg.values())
     print(f"kernel time total {tot / 1e3:.2f} ms")
     for n, (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1])[:28]:
