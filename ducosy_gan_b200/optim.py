@@ -37,4 +37,6 @@ class Adam(torch.optim.Optimizer):
                 with torch.cuda.device(p.device):
                     call("ducosy_adam_step", ptr(p), ptr(g), ptr(st["exp_avg"]), ptr(st["exp_avg_sq"]), p.numel(), float(group["lr"]),
                          float(b1), float(b2), float(group["eps"]), int(st["step"]), stream_ptr())
+                # the kernel wrote through the raw pointer: tell autograd / the packed-weight caches (keyed by _version)
+                torch.autograd.graph.increment_version(p)
         return loss

@@ -21,9 +21,28 @@ def test_fused_adam_matches_torch_adam():
         for a, b in zip(mine, ref):
             g = torch.randn_like(a) * (10.0 ** (it - 2))
             a.grad, b.grad = g.clone(), g.clone()
+        v0 = mine[0]._version
         o1.step(); o2.step(); sched.step(); sched2.step()
+        assert mine[0]._version > v0      # the packed 16-bit weight caches of the modules are keyed by _version
         for a, b in zip(mine, ref):
             assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-7
+
+
+def test_fused_adam_invalidates_packed_weight_caches():
+    """the kernel writes parameters through raw pointers: a module's next forward must see the new weights"""
+    from ducosy_gan_b200.modules.model import Discriminator, weights_init_normal
+    from ducosy_gan_b200.optim import Adam
+    torch.manual_seed(1)
+    D = Discriminator(1).cuda().apply(weights_init_normal)
+    x = torch.rand(1, 1, 256, 256, device="cuda") * 2 - 1
+    with torch.no_grad():
+        y0 = D(x).clone()
+    opt = Adam(D.parameters(), lr=1e-2, betas=(0.5, 0.999))
+    D(x).square().mean().backward()
+    opt.step()
+    with torch.no_grad():
+        y1 = D(x)
+    assert (y1 - y0).abs().max().item() > 1e-3
 
 
 def _oracle_step_losses(sdG_A, sdG_B, sdD_A, sdD_B, real_A, real_B, masks, blocks, cbam):
@@ -85,3 +104,58 @@ def test_train_step_losses_match_oracle_and_parameters_move(cfg):
     for _ in range(2):
         out = step.step(dev(real_A), dev(real_B), dev(masks))
     assert all(torch.isfinite(v).item() for v in out.values()), out
+
+
+def test_train_loss_trajectory_matches_oracle():
+    """BASELINE north_star: "training losses after N steps".  Four optimisation steps of the CUDA path against four steps of
+    the fp32 oracle (autograd through the restated networks / losses, torch.optim.Adam) from the same initial weights on
+    the same batch.  Adam's first updates are +-lr per weight, so the 16-bit gradient noise of the CUDA path only flips
+    updates of near-zero gradients and the trajectories stay together: every logged loss within 5 % at every step."""
+    from ducosy_gan_b200.trainer import CycleGANStep
+    Cin, blocks, cbam, B, H, W, N = 1, 1, True, 1, 256, 512, 4
+    step = CycleGANStep(Cin, blocks, cbam, seed=21)
+    g = torch.Generator().manual_seed(8)
+    smooth = lambda t: torch.nn.functional.avg_pool2d(t, 5, 1, 2) * 2.0
+    real_A = smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1)
+    real_B = smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1)
+    cpu = lambda m: {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    sdGA, sdGB, sdDA, sdDB = (cpu(m) for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B))
+    oG = torch.optim.Adam(list(sdGA.values()) + list(sdGB.values()), lr=2e-4, betas=(0.5, 0.999))
+    oDA = torch.optim.Adam(list(sdDA.values()), lr=2e-4, betas=(0.5, 0.999))
+    oDB = torch.optim.Adam(list(sdDB.values()), lr=2e-4, betas=(0.5, 0.999))
+    G = lambda sd, x: orc.generator_forward(sd, x, blocks, cbam)
+    D = orc.discriminator_forward
+    l1 = torch.nn.functional.l1_loss
+    ref_hist, got_hist = [], []
+    for _ in range(N):
+        # ---- oracle step (reference modules/trainer.py:462-524 on the restated modules)
+        oG.zero_grad()
+        fake_B, fake_A = G(sdGA, real_A), G(sdGB, real_B)
+        id_A, id_B = G(sdGB, real_A), G(sdGA, real_B)
+        loss_id = (l1(id_A, real_A) + l1(id_B, real_B)) / 2
+        loss_GAN = (orc.mse_gan_loss(D(sdDB, fake_B), True) + orc.mse_gan_loss(D(sdDA, fake_A), True)) / 2
+        rec_A, rec_B = G(sdGB, fake_B), G(sdGA, fake_A)
+        loss_G = (loss_GAN + 10.0 * (l1(rec_A, real_A) + l1(rec_B, real_B)) / 2 + 5.0 * loss_id
+                  + 5.0 * (orc.gradient_loss(rec_A, real_A) + orc.gradient_loss(rec_B, real_B)) / 2
+                  + 2.5 * (orc.gradient_loss(id_A, real_A) + orc.gradient_loss(id_B, real_B)) / 2
+                  + 2.0 * (1 - (orc.ssim(rec_A, real_A) + orc.ssim(rec_B, real_B)) / 2)
+                  + 2.0 * orc.contrast_attention_loss(fake_B, real_B, real_A)
+                  + 1.5 * orc.contrast_region_loss(fake_B, real_B, real_A) + 1.0 * orc.contrast_edge_loss(fake_B, real_B, real_A))
+        loss_G.backward()
+        oG.step()
+        oDA.zero_grad()
+        loss_DA = (orc.mse_gan_loss(D(sdDA, real_A), True) + orc.mse_gan_loss(D(sdDA, fake_A.detach()), False)) / 2
+        loss_DA.backward()
+        oDA.step()
+        oDB.zero_grad()
+        loss_DB = (orc.mse_gan_loss(D(sdDB, real_B), True) + orc.mse_gan_loss(D(sdDB, fake_B.detach()), False)) / 2
+        loss_DB.backward()
+        oDB.step()
+        ref_hist.append(dict(G=loss_G.item(), D_A=loss_DA.item(), D_B=loss_DB.item(), GAN=loss_GAN.item(), id=loss_id.item()))
+        # ---- CUDA step
+        out = step.step(real_A.cuda(), real_B.cuda())
+        got_hist.append({k: out[k].item() for k in ref_hist[-1]})
+    bad = [(i, k, got_hist[i][k], ref_hist[i][k]) for i in range(N) for k in ref_hist[i]
+           if abs(got_hist[i][k] - ref_hist[i][k]) > 5e-2 * abs(ref_hist[i][k]) + 1e-4]
+    assert not bad, (bad, got_hist, ref_hist)
+    assert ref_hist[-1]["G"] < ref_hist[0]["G"] and got_hist[-1]["G"] < got_hist[0]["G"]      # both actually train
