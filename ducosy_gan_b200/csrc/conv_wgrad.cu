@@ -24,6 +24,7 @@ struct WgradArgs {
   int rows_per_sample;                      // outermost TMA dim units of the input map per sample
   int dy_pad, dy_rows_per_sample;           // dY may live inside a zero-padded buffer (border width dy_pad)
   int Cin, Cout, m_blocks, n_slabs;         // n_slabs = Cin / 64 (<= 4)
+  int m_per_cta, stages;                    // 128-row blocks of Cout one CTA accumulates (they share the B tiles), pipeline depth
   int splits, chunks_per_split;
   int8_t tap_xp[kMaxTaps], tap_dx[kMaxTaps], tap_yp[kMaxTaps], tap_dy[kMaxTaps];
   float* partial;                           // [splits][taps][Cout][Cin] fp32
@@ -40,24 +41,28 @@ __device__ __forceinline__ uint64_t umma_desc_mn_sw128(uint32_t smem_addr, uint3
   return d;
 }
 
-template <typename T>
+template <typename T, int kMP>
 __global__ void __launch_bounds__(kWgThreads, 1)
 conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constant__ CUtensorMap tmX, const WgradArgs a) {
   constexpr int kFmt = std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
   extern __shared__ uint8_t wg_raw[];
   const uint32_t raw_addr = smem_u32(wg_raw);
   uint8_t* smem = wg_raw + ((1024u - (raw_addr & 1023u)) & 1023u);
-  const int stage_bytes = (2 + a.n_slabs) * kSlab;          // A: 2 slabs (128 output channels), B: n_slabs
+  constexpr int a_slabs = 2 * kMP;                           // A: 2 slabs per 128 output channels, B: n_slabs
+  const int stage_bytes = (a_slabs + a.n_slabs) * kSlab;
+  constexpr int stages = kMP == 2 ? 3 : kWgStages;
+  constexpr uint32_t tmem_cols = kMP == 2 ? 512u : 256u;
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + kWgStages * 6 * kSlab);
   uint64_t* empty = full + kWgStages;
   uint64_t* done = empty + kWgStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // unit decode: blockIdx.x = ((split * taps + tap) * m_blocks + mb)
-  const int mb = blockIdx.x % a.m_blocks;
-  const int tap = (blockIdx.x / a.m_blocks) % a.num_taps;
-  const int split = blockIdx.x / (a.m_blocks * a.num_taps);
+  // unit decode: blockIdx.x = ((split * taps + tap) * m_units + mu), m_units = m_blocks / m_per_cta
+  const int m_units = a.m_blocks / kMP;
+  const int mu = blockIdx.x % m_units;
+  const int tap = (blockIdx.x / m_units) % a.num_taps;
+  const int split = blockIdx.x / (m_units * a.num_taps);
   const int chunks_total = a.B * a.TY * a.TX;
   const int c_begin = split * a.chunks_per_split;
   const int c_end = min(c_begin + a.chunks_per_split, chunks_total);
@@ -76,7 +81,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     fence_barrier_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, 256);
+    tmem_alloc(tmem_slot, tmem_cols);
     tmem_relinquish();
   }
   tc_fence_before();
@@ -96,15 +101,15 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_wait(&empty[s], ph ^ 1);
         uint8_t* st = smem + size_t(s) * stage_bytes;
         mbar_arrive_expect_tx(&full[s], stage_bytes);
-        // A: dY chunk, two 64-channel slabs of this 128-row block of Cout; dY is unpadded [B][Ho][Wo][Cout]
-        for (int h = 0; h < 2; ++h)
-          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mb * 128 + h * 64, 0, tx * a.Wt + a.dy_pad, 0,
+        // A: dY chunk, 64-channel slabs of this CTA's 128-row block(s) of Cout
+        for (int h = 0; h < a_slabs; ++h)
+          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mu * kMP * 128 + h * 64, 0, tx * a.Wt + a.dy_pad, 0,
                       b * a.dy_rows_per_sample + ty * a.R + a.dy_pad);
         // B: the input pixels this tap multiplies, all Cin channels
         for (int sl = 0; sl < a.n_slabs; ++sl)
-          tma_load_5d(st + (2 + sl) * kSlab, &tmX, &full[s], sl * 64, a.tap_xp[tap], tx * a.Wt + a.tap_dx[tap],
+          tma_load_5d(st + (a_slabs + sl) * kSlab, &tmX, &full[s], sl * 64, a.tap_xp[tap], tx * a.Wt + a.tap_dx[tap],
                       a.tap_yp[tap], b * a.rows_per_sample + ty * a.R + a.tap_dy[tap]);
-        if (++s == kWgStages) {
+        if (++s == stages) {
           s = 0;
           ph ^= 1;
         }
@@ -122,33 +127,38 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         const uint32_t sa = smem_u32(smem + size_t(s) * stage_bytes);
 #pragma unroll
         for (int j = 0; j < kKChunk / 16; ++j) {  // 16 pixels = two 8-row swizzle atoms = 2 KiB per K step
-          const uint64_t da = umma_desc_mn_sw128(sa + j * 2048, kSlab);
-          const uint64_t db = umma_desc_mn_sw128(sa + 2 * kSlab + j * 2048, kSlab);
-          umma_f16(tmem_base, da, db, idesc, (ch > c_begin || j > 0) ? 1u : 0u);
+          const uint64_t db = umma_desc_mn_sw128(sa + a_slabs * kSlab + j * 2048, kSlab);
+#pragma unroll
+          for (int mh = 0; mh < kMP; ++mh) {
+            const uint64_t da = umma_desc_mn_sw128(sa + mh * 2 * kSlab + j * 2048, kSlab);
+            umma_f16(tmem_base + uint32_t(mh * 256), da, db, idesc, (ch > c_begin || j > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[s]);
         if (ch == c_end - 1) umma_commit(done);
       }
       __syncwarp();
-      if (++s == kWgStages) {
+      if (++s == stages) {
         s = 0;
         ph ^= 1;
       }
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
-    const int o = mb * 128 + q * 32 + lane;
     mbar_wait(done, 0);
     tc_fence_after();
-    float* dst = a.partial + ((size_t(split) * a.num_taps + tap) * a.Cout + o) * a.Cin;
-    for (int chn = 0; chn < N / 32; ++chn) {
-      uint32_t v[32];
-      tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(chn * 32), v);
-      tmem_ld_wait();
-      if (o < a.Cout) {   // Cout = 64: the upper 64 accumulator rows come from TMA zero fill and are not stored
+    for (int mh = 0; mh < kMP; ++mh) {
+      const int o = (mu * kMP + mh) * 128 + q * 32 + lane;
+      float* dst = a.partial + ((size_t(split) * a.num_taps + tap) * a.Cout + o) * a.Cin;
+      for (int chn = 0; chn < N / 32; ++chn) {
+        uint32_t v[32];
+        tmem_ld_32x32(tmem_base + (uint32_t(q * 32) << 16) + uint32_t(mh * 256 + chn * 32), v);
+        tmem_ld_wait();
+        if (o < a.Cout) {   // Cout = 64: the upper 64 accumulator rows come from TMA zero fill and are not stored
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          reinterpret_cast<uint4*>(dst + chn * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i)
+            reinterpret_cast<uint4*>(dst + chn * 32)[i] = make_uint4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        }
       }
     }
   }
@@ -156,7 +166,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 256);
+    tmem_dealloc(tmem_base, tmem_cols);
   }
 }
 
@@ -211,6 +221,16 @@ int encode_nhwc_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, i
   return 0;
 }
 
+// K splits: one CTA per SM and unit.  The grid must not spill into an extra wave (297 CTAs on 148 SMs run as long as
+// 444), so the count is rounded DOWN to whole waves: two waves of light CTAs, one wave of the double-M ones.
+int wgrad_splits(int units, int m_per_cta, int chunks) {
+  const int target = (m_per_cta == 2 ? 1 : 2) * 148;
+  int splits = target / units;
+  if (splits > chunks) splits = chunks;
+  if (splits < 1) splits = 1;
+  return splits;
+}
+
 }  // namespace
 }  // namespace ducosy
 
@@ -219,10 +239,8 @@ using namespace ducosy;
 extern "C" size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
   const int chunks = B * Ho * Wo / kKChunk;
-  const int units = kh * kw * ((Cout + 127) / 128);
-  int splits = (2 * 148 + units - 1) / units;
-  if (splits > chunks) splits = chunks;
-  if (splits < 1) splits = 1;
+  const int m_blocks = (Cout + 127) / 128, m_per_cta = (m_blocks % 2 == 0) ? 2 : 1;
+  const int splits = wgrad_splits(kh * kw * (m_blocks / m_per_cta), m_per_cta, chunks);
   return size_t(splits) * kh * kw * Cout * Cin * 4;
 }
 
@@ -259,10 +277,10 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
       else { a.tap_xp[t] = int8_t(s & 1); a.tap_dx[t] = int8_t(s >> 1); a.tap_yp[t] = int8_t(r & 1); a.tap_dy[t] = int8_t(r >> 1); }
     }
   const int chunks = B * a.TY * a.TX;
-  const int units = a.num_taps * a.m_blocks;
-  int splits = (2 * 148 + units - 1) / units;
-  if (splits > chunks) splits = chunks;
-  if (splits < 1) splits = 1;
+  a.m_per_cta = (a.m_blocks % 2 == 0) ? 2 : 1;   // two 128-row blocks of Cout share the B tiles: a third less L2 -> SMEM traffic
+  a.stages = a.m_per_cta == 2 ? 3 : kWgStages;
+  const int units = a.num_taps * (a.m_blocks / a.m_per_cta);
+  int splits = wgrad_splits(units, a.m_per_cta, chunks);
   a.chunks_per_split = (chunks + splits - 1) / splits;
   splits = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;   // no empty split
   a.splits = splits;
@@ -279,15 +297,18 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   const size_t smem = 1024 + size_t(kWgStages) * 6 * kSlab + 256;
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const int grid = splits * units;
+#define DUCOSY_WGRAD_LAUNCH(T, MP)                                                                              \
+  do {                                                                                                          \
+    static bool cfg = false;                                                                                    \
+    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; } \
+    conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
+  } while (0)
   if (dtype == DUCOSY_F16) {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; }
-    conv_wgrad_kernel<__half><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);
+    if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__half, 2); else DUCOSY_WGRAD_LAUNCH(__half, 1);
   } else {
-    static bool cfg = false;
-    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; }
-    conv_wgrad_kernel<__nv_bfloat16><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);
+    if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__nv_bfloat16, 2); else DUCOSY_WGRAD_LAUNCH(__nv_bfloat16, 1);
   }
+#undef DUCOSY_WGRAD_LAUNCH
   DUCOSY_TRY(check_launch("conv_wgrad_kernel"));
   const long long per_split = (long long)a.num_taps * Cout * Cin;
   long long blocks = (per_split + 255) / 256;
