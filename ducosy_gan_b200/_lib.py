@@ -84,6 +84,7 @@ SIGNATURES = {
     "ducosy_pack_dgrad_s1_weight": (_i, [_p, _p, _i, _i, _i, _p]),
     "ducosy_conv3x3s1_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pad_fold": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_pad_fold_add": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_upconv_dgrad_weight": (_i, [_p, _p, _i, _i, _i, _p]),
     "ducosy_upconv2x_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_upsample2x_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
@@ -93,6 +94,9 @@ SIGNATURES = {
     "ducosy_stem_col2im": (_i, [_p, _p, _p, _i, _i, _i, _i, _p]),
     "ducosy_unpack_stem_wgrad": (_i, [_p, _p, _i, _i, _p, _p]),
     "ducosy_add_inplace": (_i, [_p, _p, _ll, _i, _p]),
+    "ducosy_upconv2x_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
+    "ducosy_upconv2x_wgrad_nhwc": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
+    "ducosy_unpack_upconv_wgrad": (_i, [_p, _p, _i, _i, _p, _p]),
     "ducosy_postprocess_scratch_bytes": (_sz, [_i, _i, _i]),
     "ducosy_postprocess_minmax_offset_bytes": (_sz, [_i, _i, _i]),
     "ducosy_postprocess_volume": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _i, C.c_double, _f, _i, _i, _i, _p]),

@@ -27,6 +27,7 @@ struct WgradArgs {
   int m_per_cta, stages;                    // 128-row blocks of Cout one CTA accumulates (they share the B tiles), pipeline depth
   int splits, chunks_per_split;
   int8_t tap_xp[kMaxTaps], tap_dx[kMaxTaps], tap_yp[kMaxTaps], tap_dy[kMaxTaps];
+  int8_t dyq_xp[kMaxTaps], dyq_yp[kMaxTaps];   // parity of the dY pixels a unit reads (stride-2 dY map: sub-pixel up-conv wgrad)
   float* partial;                           // [splits][taps][Cout][Cin] fp32
 };
 
@@ -103,8 +104,8 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
         mbar_arrive_expect_tx(&full[s], stage_bytes);
         // A: dY chunk, 64-channel slabs of this CTA's 128-row block(s) of Cout
         for (int h = 0; h < a_slabs; ++h)
-          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mu * kMP * 128 + h * 64, 0, tx * a.Wt + a.dy_pad, 0,
-                      b * a.dy_rows_per_sample + ty * a.R + a.dy_pad);
+          tma_load_5d(st + h * kSlab, &tmDY, &full[s], mu * kMP * 128 + h * 64, a.dyq_xp[tap], tx * a.Wt + a.dy_pad,
+                      a.dyq_yp[tap], b * a.dy_rows_per_sample + ty * a.R + a.dy_pad);
         // B: the input pixels this tap multiplies, all Cin channels
         for (int sl = 0; sl < a.n_slabs; ++sl)
           tma_load_5d(st + (a_slabs + sl) * kSlab, &tmX, &full[s], sl * 64, a.tap_xp[tap], tx * a.Wt + a.tap_dx[tap],
@@ -315,4 +316,117 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   if (blocks > 148 * 8) blocks = 148 * 8;
   wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dw, splits, a.num_taps, Cout, Cin);
   return check_launch("wgrad_reduce_kernel");
+}
+
+// Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) without materialising the
+// up-sampled map: the forward runs as four phase-specific 2x2 convs on the source grid (pack_upconv_weight_kernel), so
+// the gradient of the 16 pre-summed (phase, tap) blocks is a wgrad over the SOURCE pixels -- 16 units x Hs*Ws pixels
+// instead of 9 x 4*Hs*Ws (4/9 of the MACs, less than half of the operand traffic) -- with dY read at stride 2 (phase =
+// pixel parity).  dwph: fp32 [Cout][16*Cin], unit index (phase*4 + a*2 + b); ducosy_unpack_upconv_wgrad folds it back
+// to the 3x3 weight (adjoint of the pre-summing).  src_pad: [B][Hs+2][Ws+2][Cin] (zero border 1); dy:
+// [B][2Hs+2*dy_pad][2Ws+2*dy_pad][Cout], dy_pad even.
+extern "C" size_t ducosy_upconv2x_wgrad_workspace_bytes(int B, int Hs, int Ws, int Cin, int Cout) {
+  if (B <= 0 || Hs <= 0 || Ws <= 0) return 0;
+  const int chunks = B * Hs * Ws / kKChunk;
+  const int m_blocks = (Cout + 127) / 128, m_per_cta = (m_blocks % 2 == 0) ? 2 : 1;
+  const int splits = wgrad_splits(16 * (m_blocks / m_per_cta), m_per_cta, chunks);
+  return size_t(splits) * 16 * Cout * Cin * 4;
+}
+
+extern "C" int ducosy_upconv2x_wgrad_nhwc(const void* src_pad, const void* dy, int dy_pad, float* dwph, int B, int Hs, int Ws,
+                                          int Cin, int Cout, void* workspace, size_t workspace_bytes, int dtype,
+                                          ducosy_stream_t stream) {
+  DUCOSY_CHECK(src_pad && dy && dwph && workspace && B > 0, DUCOSY_ERR_ARG, "upconv2x_wgrad: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_wgrad: bad dtype");
+  DUCOSY_CHECK(Cin % 64 == 0 && Cin <= 256 && (Cout % 128 == 0 || Cout == 64), DUCOSY_ERR_SHAPE,
+               "upconv2x_wgrad: needs Cin in {64,128,192,256} and Cout 64 or a multiple of 128 (got %d -> %d)", Cin, Cout);
+  DUCOSY_CHECK(dy_pad >= 0 && dy_pad <= 4 && dy_pad % 2 == 0, DUCOSY_ERR_ARG, "upconv2x_wgrad: dy_pad must be 0, 2 or 4");
+  DUCOSY_TRY(ducosy_check_device());
+  const int Wt = Ws < kKChunk ? Ws : kKChunk;
+  DUCOSY_CHECK(Wt >= 8 && (Wt & (Wt - 1)) == 0 && Ws % Wt == 0 && Hs % (kKChunk / Wt) == 0, DUCOSY_ERR_SHAPE,
+               "upconv2x_wgrad: source grid %dx%d unsupported", Hs, Ws);
+  const int R = kKChunk / Wt;
+  WgradArgs a{};
+  a.num_taps = 16;
+  a.B = B; a.R = R; a.Wt = Wt;
+  a.TY = Hs / R; a.TX = Ws / Wt;
+  a.rows_per_sample = Hs + 2;
+  a.dy_pad = dy_pad / 2;                                   // in units of the stride-2 map
+  a.dy_rows_per_sample = (2 * Hs + 2 * dy_pad) / 2;
+  a.Cin = Cin; a.Cout = Cout; a.m_blocks = (Cout + 127) / 128; a.n_slabs = Cin / 64;
+  for (int u = 0; u < 16; ++u) {
+    const int phase = u >> 2, ta = (u >> 1) & 1, tb = u & 1, py = phase >> 1, px = phase & 1;
+    a.tap_xp[u] = 0; a.tap_yp[u] = 0;
+    a.tap_dy[u] = int8_t(ta + py);                         // source row i + a + py of the padded source (api.cu: upconv2x_nhwc)
+    a.tap_dx[u] = int8_t(tb + px);
+    a.dyq_yp[u] = int8_t(py);                              // dY pixel (2i + py, 2j + px); dy_pad is even, so parity is unchanged
+    a.dyq_xp[u] = int8_t(px);
+  }
+  const int chunks = B * a.TY * a.TX;
+  a.m_per_cta = (a.m_blocks % 2 == 0) ? 2 : 1;
+  a.stages = a.m_per_cta == 2 ? 3 : kWgStages;
+  const int units = a.num_taps * (a.m_blocks / a.m_per_cta);
+  int splits = wgrad_splits(units, a.m_per_cta, chunks);
+  a.chunks_per_split = (chunks + splits - 1) / splits;
+  splits = (chunks + a.chunks_per_split - 1) / a.chunks_per_split;
+  a.splits = splits;
+  const size_t need = size_t(splits) * a.num_taps * Cout * Cin * 4;
+  DUCOSY_CHECK(workspace_bytes >= need, DUCOSY_ERR_WORKSPACE, "upconv2x_wgrad: workspace %zu < required %zu bytes", workspace_bytes, need);
+  a.partial = static_cast<float*>(workspace);
+  const CUtensorMapDataType dt = dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUtensorMap tmDY, tmX;
+  DUCOSY_TRY(encode_nhwc_map(&tmDY, dt, dy, B, 2 * Hs + 2 * dy_pad, 2 * Ws + 2 * dy_pad, Cout, 2, Wt, R));
+  DUCOSY_TRY(encode_nhwc_map(&tmX, dt, src_pad, B, Hs + 2, Ws + 2, Cin, 1, Wt, R));
+  const size_t smem = 1024 + size_t(kWgStages) * 6 * kSlab + 256;
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int grid = splits * units;
+#define DUCOSY_WGRAD_LAUNCH(T, MP)                                                                              \
+  do {                                                                                                          \
+    cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
+    conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
+  } while (0)
+  if (dtype == DUCOSY_F16) {
+    if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__half, 2); else DUCOSY_WGRAD_LAUNCH(__half, 1);
+  } else {
+    if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__nv_bfloat16, 2); else DUCOSY_WGRAD_LAUNCH(__nv_bfloat16, 1);
+  }
+#undef DUCOSY_WGRAD_LAUNCH
+  DUCOSY_TRY(check_launch("conv_wgrad_kernel"));
+  const long long per_split = (long long)a.num_taps * Cout * Cin;
+  long long blocks = (per_split + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dwph, splits, a.num_taps, Cout, Cin);
+  return check_launch("wgrad_reduce_kernel");
+}
+
+namespace ducosy {
+namespace {
+// dW[o][c][r][s] = gs1 * sum_{py,px} dWph[o][((py*2+px)*4 + a(py,r)*2 + b(px,s)) * Cin + c],  a(0,r) = (r >= 1), a(1,r) = (r >= 2)
+__global__ void unpack_upconv_wgrad_kernel(const float* __restrict__ dwph, float* __restrict__ g, int Cout, int Cin,
+                                           const float* __restrict__ gs) {
+  const float inv = gs != nullptr ? gs[1] : 1.f;
+  const long long total = (long long)Cout * Cin * 9;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const int tap = int(i % 9), r = tap / 3, s = tap % 3;
+    const long long oc = i / 9;
+    const int c = int(oc % Cin), o = int(oc / Cin);
+    float acc = 0.f;
+    for (int py = 0; py < 2; ++py)
+      for (int px = 0; px < 2; ++px) {
+        const int ta = py == 0 ? (r >= 1) : (r >= 2), tb = px == 0 ? (s >= 1) : (s >= 2);
+        acc += dwph[((long long)o * 16 + (py * 2 + px) * 4 + ta * 2 + tb) * Cin + c];
+      }
+    g[i] = acc * inv;
+  }
+}
+}  // namespace
+}  // namespace ducosy
+
+extern "C" int ducosy_unpack_upconv_wgrad(const float* dwph, float* g_oihw, int Cout, int Cin, const float* gs, ducosy_stream_t stream) {
+  DUCOSY_CHECK(dwph && g_oihw && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "unpack_upconv_wgrad: bad argument");
+  const long long total = (long long)Cout * Cin * 9;
+  long long blocks = (total + 255) / 256;
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  unpack_upconv_wgrad_kernel<<<int(blocks), 256, 0, (cudaStream_t)stream>>>(dwph, g_oihw, Cout, Cin, gs);
+  return check_launch("unpack_upconv_wgrad_kernel");
 }

@@ -308,7 +308,8 @@ dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict_
 }
 // adjoint of the padding: gradient w.r.t. the padded map [B][H+2p][W+2p][C] -> gradient w.r.t. the un-padded map
 template <typename T>
-__global__ void pad_fold_kernel(const T* __restrict__ dxpad, T* __restrict__ dx, int B, int H, int W, int C, int pad, int mode) {
+__global__ void pad_fold_kernel(const T* __restrict__ dxpad, const T* __restrict__ add, T* __restrict__ dx, int B, int H, int W, int C,
+                                int pad, int mode) {
   const int cv = C / 8, Hp = H + 2 * pad, Wp = W + 2 * pad;
   const long long total = (long long)B * H * W * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -319,6 +320,16 @@ __global__ void pad_fold_kernel(const T* __restrict__ dxpad, T* __restrict__ dx,
     const int y = int(r % H);
     const int b = int(r / H);
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (add != nullptr) {   // the skip connection's gradient joins here (saves a separate pass over the map)
+      const uint4 v = reinterpret_cast<const uint4*>(add)[i];
+      const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 f = Cvt<T>::unpack2(w4[k]);
+        acc[2 * k] = f.x;
+        acc[2 * k + 1] = f.y;
+      }
+    }
     // padded rows / cols that reflect onto (y, x): p -> |p - pad| on the low side, 2(n-1) - (p - pad) on the high side
     int rows[3], cols[3], nr = 0, nc = 0;
     rows[nr++] = y + pad;
@@ -750,13 +761,18 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
 }
 
 // Adjoint of ReflectionPad2d(pad) / zero padding: dxpad [B][H+2p][W+2p][C] -> dx [B][H][W][C] (16-bit NHWC).
-extern "C" int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
-                               ducosy_stream_t stream) {
+extern "C" int ducosy_pad_fold_add(const void* dxpad, const void* add, void* dx, int B, int H, int W, int C, int pad, int pad_mode,
+                                   int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(dxpad && dx && B > 0 && C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_ARG, "pad_fold: bad argument");
   const long long total = (long long)B * H * W * (C / 8);
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pad_fold_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(dxpad), static_cast<T*>(dx), B, H, W, C, pad, pad_mode)));
+                                      static_cast<const T*>(dxpad), static_cast<const T*>(add), static_cast<T*>(dx), B, H, W, C, pad,
+                                      pad_mode)));
   return check_launch("pad_fold_kernel");
+}
+extern "C" int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
+                               ducosy_stream_t stream) {
+  return ducosy_pad_fold_add(dxpad, nullptr, dx, B, H, W, C, pad, pad_mode, dtype, stream);
 }
 
 extern "C" int ducosy_pack_upconv_dgrad_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream) {

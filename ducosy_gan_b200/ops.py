@@ -322,9 +322,9 @@ def apply_windowing(y, hu_lo, hu_hi, window_center, window_width):
     return out
 
 
-def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode):
+def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode, add=None):
     """Input gradient of pad(1) + Conv2d(3x3): dy_pad2 [B,H+4,W+4,Cout] (zero border 2) -> dx [B,H,W,Cin] after folding
-    the padding adjoint (reflect or zero)."""
+    the padding adjoint (reflect or zero); ``add`` [B,H,W,Cin] is summed in (the skip connection's gradient)."""
     Cout, Cin = w_oihw.shape[:2]
     B, Hp, Wp, _ = dy_pad2.shape
     H, W = Hp - 4, Wp - 4
@@ -336,7 +336,7 @@ def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode):
         dxpad = torch.empty((B, H + 2, W + 2, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
         call("ducosy_conv3x3s1_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dxpad), B, H, W, Cin, Cout, dc, stream_ptr())
         dx = torch.empty((B, H, W, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
-        call("ducosy_pad_fold", ptr(dxpad), ptr(dx), B, H, W, Cin, 1, pad_mode, dc, stream_ptr())
+        call("ducosy_pad_fold_add", ptr(dxpad), ptr(add), ptr(dx), B, H, W, Cin, 1, pad_mode, dc, stream_ptr())
     return dx, dxpad
 
 
@@ -370,11 +370,13 @@ def upconv2x_backward(src_pad, dy_pad2, w_oihw, gs=None):
         call("ducosy_pack_upconv_dgrad_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
         dsrc = torch.empty((B, Hs, Ws, Cin), dtype=dt, device=src_pad.device)
         call("ducosy_upconv2x_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dsrc), B, Hs, Ws, Cin, Cout, dc, stream_ptr())
-        up = torch.empty((B, 2 * Hs + 2, 2 * Ws + 2, Cin), dtype=dt, device=src_pad.device)
-        call("ducosy_upsample2x_pad", ptr(src_pad), ptr(up), B, Hs, Ws, Cin, dc, stream_ptr())
-        dwp = conv2d_wgrad_nhwc(up, dy_pad2, 3, 3, 1, dy_pad=2)
+        lib = _lib.load()
+        ws = torch.empty(max(lib.ducosy_upconv2x_wgrad_workspace_bytes(B, Hs, Ws, Cin, Cout), 16), dtype=torch.uint8, device=src_pad.device)
+        dwph = torch.empty((Cout, 16 * Cin), dtype=torch.float32, device=src_pad.device)
+        call("ducosy_upconv2x_wgrad_nhwc", ptr(src_pad), ptr(dy_pad2), 2, ptr(dwph), B, Hs, Ws, Cin, Cout, ptr(ws), ws.numel(), dc,
+             stream_ptr())
         dw = torch.empty((Cout, Cin, 3, 3), dtype=torch.float32, device=src_pad.device)
-        call("ducosy_unpack_wgrad", ptr(dwp), ptr(dw), Cout, Cin, 9, ptr(gs), stream_ptr())
+        call("ducosy_unpack_upconv_wgrad", ptr(dwph), ptr(dw), Cout, Cin, ptr(gs), stream_ptr())
     return dsrc, dw
 
 

@@ -99,8 +99,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
         dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
         dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
         dw_a = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(sv["r"], dya, 3, 3, 1, dy_pad=2), C, C, 9, gs)
-        dskip, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT)
-        dr = ops.add_inplace(dskip, dr)
+        dr, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT, add=dr)     # conv path + skip connection
         block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)
     block_grads.reverse()
 

@@ -290,6 +290,15 @@ int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, floa
                              int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
                              ducosy_stream_t stream);
 
+/* Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) on the SOURCE grid: the gradient of
+ * the 16 pre-summed (phase, tap) blocks of ducosy_pack_upconv_weight (4/9 of the MACs of a wgrad over the up-sampled map,
+ * which is never materialised).  src_pad [B][Hs+2][Ws+2][Cin] zero border; dy [B][2Hs+2*dy_pad][2Ws+2*dy_pad][Cout], dy_pad
+ * even; dwph fp32 [Cout][16*Cin].  ducosy_unpack_upconv_wgrad folds dwph back to the OIHW 3x3 gradient (times gs[1]). */
+size_t ducosy_upconv2x_wgrad_workspace_bytes(int B, int Hs, int Ws, int Cin, int Cout);
+int ducosy_upconv2x_wgrad_nhwc(const void* src_pad, const void* dy, int dy_pad, float* dwph, int B, int Hs, int Ws, int Cin,
+                               int Cout, void* workspace, size_t workspace_bytes, int dtype, ducosy_stream_t stream);
+int ducosy_unpack_upconv_wgrad(const float* dwph, float* g_oihw, int Cout, int Cin, const float* gs, ducosy_stream_t stream);
+
 /* InstanceNorm(+activation) backward on NHWC 16-bit maps: forward n = y*scale + shift, a = act(n); given da returns
  * dy = rstd*(g - mean(g) - n*mean(g*n)), g = da*act'(n), written with a zero border of `pad` pixels (ready for the
  * phase / dgrad convolutions).  scratch: ducosy_in_backward_scratch_bytes. */
@@ -315,6 +324,9 @@ int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dgrad, void* 
                                 int dtype, ducosy_stream_t stream);
 int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W, int C, int pad, int pad_mode, int dtype,
                     ducosy_stream_t stream);
+/* same, plus an element-wise addend [B][H][W][C] (the residual skip gradient of modules/model.py:65,87); add may be NULL */
+int ducosy_pad_fold_add(const void* dxpad, const void* add, void* dx, int B, int H, int W, int C, int pad, int pad_mode,
+                        int dtype, ducosy_stream_t stream);
 /* Backward of Upsample(x2 nearest)+Conv3x3(pad 1) (modules/model.py:108-109): input gradient dy_pad2 [B][2Hs+4][2Ws+4][Cout]
  * (zero border 2) -> dsrc [B][Hs][Ws][Cin] with w_dgrad [Cin][16*Cout] from ducosy_pack_upconv_dgrad_weight; for the weight
  * gradient materialise the upsampled, zero-padded source with ducosy_upsample2x_pad and call ducosy_conv2d_wgrad_nhwc (3x3, s1). */
