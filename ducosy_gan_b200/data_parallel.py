@@ -104,8 +104,7 @@ class DataParallelCycleGANStep(CycleGANStep):
         # identical to CycleGANStep.generator_losses except that the two batch-global criteria see the gathered batch
         cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
         real_A_input, real_B_input = cat(real_A), cat(real_B)
-        fake_B, fake_A = self.G_A2B(real_A_input), self.G_B2A(real_B_input)
-        id_A, id_B = self.G_B2A(real_A_input), self.G_A2B(real_B_input)
+        fake_B, fake_A, id_A, id_B = self._translate_and_identity(real_A_input, real_B_input)
         loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
         loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
         rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
@@ -134,13 +133,13 @@ class DataParallelCycleGANStep(CycleGANStep):
         self.optimizer_G.step()
 
         self.bucket_D_A.zero()   # also discards what loss_G.backward() left in the discriminators (trainer.py:517)
-        loss_D_A = (mse_gan_loss(self.D_A(real_A), True) + mse_gan_loss(self.D_A(fake_A.detach()), False)) / 2
+        loss_D_A = self._disc_loss(self.D_A, real_A, fake_A)
         loss_D_A.backward()
         self.bucket_D_A.all_reduce_mean(self.group)
         self.optimizer_D_A.step()
 
         self.bucket_D_B.zero()
-        loss_D_B = (mse_gan_loss(self.D_B(real_B), True) + mse_gan_loss(self.D_B(fake_B.detach()), False)) / 2
+        loss_D_B = self._disc_loss(self.D_B, real_B, fake_B)
         loss_D_B.backward()
         self.bucket_D_B.all_reduce_mean(self.group)
         self.optimizer_D_B.step()

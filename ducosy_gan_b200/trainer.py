@@ -3,6 +3,9 @@ models, criteria and optimisers built at trainer.py:320-362 -- on the kernels of
 
 The only torch tensor ops left are the ones the reference's own loop body performs between modules: ``torch.cat`` of
 the mask channels (trainer.py:450-452,476-478) and the scalar arithmetic of the loss mix (trainer.py:493-512).
+One scheduling difference, with identical per-sample results: where the reference calls the same network twice on
+independent inputs (translation + identity, trainer.py:464-467; real + fake, trainer.py:518,523) the two inputs go through
+as one batch.
 """
 from __future__ import annotations
 
@@ -42,8 +45,7 @@ class CycleGANStep:
         """trainer.py:447-512: returns (loss_G, dict of the individual terms, fake_A, fake_B)."""
         cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
         real_A_input, real_B_input = cat(real_A), cat(real_B)
-        fake_B, fake_A = self.G_A2B(real_A_input), self.G_B2A(real_B_input)
-        id_A, id_B = self.G_B2A(real_A_input), self.G_A2B(real_B_input)
+        fake_B, fake_A, id_A, id_B = self._translate_and_identity(real_A_input, real_B_input)
         loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
         loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
         rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
@@ -60,6 +62,21 @@ class CycleGANStep:
                      contrast_attention=loss_att, contrast_region=loss_region, contrast_edge=loss_edge)
         return loss_G, terms, fake_A, fake_B
 
+    def _translate_and_identity(self, real_A_input, real_B_input):
+        """trainer.py:464-467: fake_B, fake_A = G_A2B(A), G_B2A(B); id_A, id_B = G_B2A(A), G_A2B(B).  Each generator sees its two
+        inputs as ONE batch of 2B samples (InstanceNorm is per sample and the kernels are batch-invariant, so every sample's
+        output and gradient are what the two separate calls give; half the launches, twice the work per launch)."""
+        B = real_A_input.shape[0]
+        ab = self.G_A2B(torch.cat([real_A_input, real_B_input], dim=0))
+        ba = self.G_B2A(torch.cat([real_B_input, real_A_input], dim=0))
+        return ab[:B], ba[:B], ba[B:], ab[B:]
+
+    def _disc_loss(self, D, real, fake):
+        """trainer.py:518 / :523: (MSE(D(real), valid) + MSE(D(fake.detach()), fake)) / 2, both images in one batch of 2B."""
+        B = real.shape[0]
+        out = D(torch.cat([real, fake.detach()], dim=0))
+        return (mse_gan_loss(out[:B], True) + mse_gan_loss(out[B:], False)) / 2
+
     def _sync(self, opt):
         if self.grad_hook is not None:
             self.grad_hook([p for g in opt.param_groups for p in g["params"]])
@@ -73,13 +90,13 @@ class CycleGANStep:
         self.optimizer_G.step()
 
         self.optimizer_D_A.zero_grad()
-        loss_D_A = (mse_gan_loss(self.D_A(real_A), True) + mse_gan_loss(self.D_A(fake_A.detach()), False)) / 2
+        loss_D_A = self._disc_loss(self.D_A, real_A, fake_A)
         loss_D_A.backward()
         self._sync(self.optimizer_D_A)
         self.optimizer_D_A.step()
 
         self.optimizer_D_B.zero_grad()
-        loss_D_B = (mse_gan_loss(self.D_B(real_B), True) + mse_gan_loss(self.D_B(fake_B.detach()), False)) / 2
+        loss_D_B = self._disc_loss(self.D_B, real_B, fake_B)
         loss_D_B.backward()
         self._sync(self.optimizer_D_B)
         self.optimizer_D_B.step()
