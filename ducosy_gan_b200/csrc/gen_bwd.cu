@@ -540,6 +540,31 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
   }
 }
 
+// Same update with the learning rate and the step count read from device memory (state = {lr, step}), so that a whole
+// optimisation step can live in a CUDA graph: nothing that changes between replays is baked into the launch.
+__global__ void adam_advance_kernel(float* __restrict__ state) { state[1] += 1.f; }
+__global__ void __launch_bounds__(256)
+adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
+                     float b1, float b2, float eps, const float* __restrict__ state) {
+  __shared__ float s_step_size, s_inv_sqrt_bc2;
+  if (threadIdx.x == 0) {
+    const double t = double(state[1]);
+    const double bc1 = 1.0 - pow(double(b1), t), bc2 = 1.0 - pow(double(b2), t);
+    s_step_size = float(double(state[0]) / bc1);
+    s_inv_sqrt_bc2 = float(1.0 / sqrt(bc2));
+  }
+  __syncthreads();
+  const float step_size = s_step_size, inv_sqrt_bc2 = s_inv_sqrt_bc2;
+  for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
+    const float gi = g[i];
+    const float mi = b1 * m[i] + (1.f - b1) * gi;
+    const float vi = b2 * v[i] + (1.f - b2) * gi * gi;
+    m[i] = mi;
+    v[i] = vi;
+    p[i] -= step_size * mi / (sqrtf(vi) * inv_sqrt_bc2 + eps);
+  }
+}
+
 // a += b on 16-bit maps (the skip connection of the residual blocks carries the gradient straight through)
 template <typename T>
 __global__ void __launch_bounds__(256)
@@ -691,4 +716,18 @@ extern "C" int ducosy_adam_step(float* param, const float* grad, float* exp_avg,
   adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
                                                             float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
   return check_launch("adam_step_kernel");
+}
+
+extern "C" int ducosy_adam_advance(float* state, ducosy_stream_t stream) {
+  DUCOSY_CHECK(state != nullptr, DUCOSY_ERR_ARG, "adam_advance: null pointer");
+  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  return check_launch("adam_advance_kernel");
+}
+
+extern "C" int ducosy_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n,
+                                    const float* state, float beta1, float beta2, float eps, ducosy_stream_t stream) {
+  DUCOSY_CHECK(param && grad && exp_avg && exp_avg_sq && state && n > 0, DUCOSY_ERR_ARG, "adam_step_dev: bad argument");
+  const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
+  adam_step_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, state);
+  return check_launch("adam_step_dev_kernel");
 }

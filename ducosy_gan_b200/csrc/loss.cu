@@ -292,6 +292,13 @@ __global__ void select_pick_kernel(unsigned* __restrict__ hist, int pass, unsign
   sel[1] = rank - acc;
   for (int i = 0; i < 256; ++i) hist[i] = 0;
 }
+// selection state for both edge maps, set from kernel arguments (a host-to-device copy of a stack array would be read
+// again -- from a dead stack frame -- every time a CUDA graph holding it is replayed)
+__global__ void select_init_kernel(unsigned* __restrict__ sel, unsigned k) {
+  const int t = threadIdx.x;
+  if (t < 4) sel[t] = (t & 1) ? k : 0u;
+  for (int i = 4 + t; i < 4 + 256; i += blockDim.x) sel[i] = 0u;
+}
 // partial sums for the top-k mean: [sum of e > tau, count of e > tau]
 __global__ void topk_sum_kernel(const float* __restrict__ e, long long n, const unsigned* __restrict__ sel, float* __restrict__ partial) {
   const float tau = __uint_as_float(sel[0]);
@@ -589,9 +596,7 @@ extern "C" int ducosy_loss_contrast_edge_forward(const float* pred, const float*
   unsigned* sel = sel_of(scratch);   // [0..1] sel_p, [2..3] sel_t, [4..259] hist
   edge_fwd_kernel<<<g, kLossThreads, 0, st>>>(pred, target, B, H, W, ep, et, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 4, sums, st));
-  const unsigned init[4] = {0u, unsigned(k), 0u, unsigned(k)};
-  cudaMemcpyAsync(sel, init, sizeof(init), cudaMemcpyHostToDevice, st);
-  cudaMemsetAsync(sel + 4, 0, 256 * 4, st);
+  select_init_kernel<<<1, 256, 0, st>>>(sel, unsigned(k));
   for (int which = 0; which < 2; ++which) {
     const float* e = which == 0 ? ep : et;
     for (int pass = 0; pass < 4; ++pass) {

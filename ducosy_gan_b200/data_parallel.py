@@ -146,3 +146,43 @@ class DataParallelCycleGANStep(CycleGANStep):
         out = {k: v.detach() for k, v in terms.items()}
         out.update(G=loss_G.detach(), D_A=loss_D_A.detach(), D_B=loss_D_B.detach())
         return out
+
+
+class GraphedCycleGANStep:
+    """One whole optimisation step -- six generator passes, the discriminators, nine losses, three gradient all-reduces and
+    three Adam updates, ~3000 kernel launches -- captured once in a CUDA graph and replayed.  At small per-rank batches
+    (global batch 8 over 8 GPUs = one sample per rank) the eager step is bound by Python launching those kernels, not by the
+    GPU; the replay is one launch.
+
+    ``step`` must be a ``DataParallelCycleGANStep(..., capturable=True)`` (gradients live in static buckets, Adam reads
+    {lr, step} from device memory).  The example batch fixes the shapes; the ``warmup`` eager steps needed before a capture
+    are real optimisation steps on that batch."""
+
+    def __init__(self, step: "DataParallelCycleGANStep", real_A, real_B, masks=None, warmup=3):
+        if not all(o.capturable for o in (step.optimizer_G, step.optimizer_D_A, step.optimizer_D_B)):
+            raise ValueError("construct the step with capturable=True")
+        self.step = step
+        self.static = [None if t is None else t.clone() for t in (real_A, real_B, masks)]
+        cur = torch.cuda.current_stream()
+        side = torch.cuda.Stream()
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(warmup):
+                step.step(*self.static)
+        cur.wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(self.graph):
+            self.out = step.step(*self.static)
+        self._params = [p for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B) for p in m.parameters()]
+
+    def __call__(self, real_A, real_B, masks=None):
+        for dst, src in zip(self.static, (real_A, real_B, masks)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        for o in (self.step.optimizer_G, self.step.optimizer_D_A, self.step.optimizer_D_B):
+            o.push_lr()
+        self.graph.replay()
+        for p in self._params:      # the replay changed the weights behind autograd's back: keep _version-keyed caches honest
+            torch.autograd.graph.increment_version(p)
+        return self.out

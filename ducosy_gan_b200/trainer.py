@@ -20,7 +20,7 @@ class CycleGANStep:
     """Holds G_A2B, G_B2A, D_A, D_B, the nine criteria and the three Adam optimisers (trainer.py:328-362)."""
 
     def __init__(self, input_channels=1, num_residual_blocks=9, use_cbam=True, lr=2e-4, lambda_cyc=10.0, lambda_id=5.0,
-                 device="cuda", seed=None):
+                 device="cuda", seed=None, capturable=False):
         if seed is not None:
             torch.manual_seed(seed)
         dev = torch.device(device)
@@ -35,9 +35,10 @@ class CycleGANStep:
         self.criterion_contrast_attention = ContrastAttentionLoss(sigma=0.15, min_weight=1.0, max_weight=3.0, blur_kernel=7)
         self.criterion_contrast_region = ContrastRegionLoss(threshold=0.15, weight=1.5)
         self.criterion_contrast_edge = ContrastEdgeLoss()
-        self.optimizer_G = Adam(list(self.G_A2B.parameters()) + list(self.G_B2A.parameters()), lr=lr, betas=(0.5, 0.999))
-        self.optimizer_D_A = Adam(self.D_A.parameters(), lr=lr, betas=(0.5, 0.999))
-        self.optimizer_D_B = Adam(self.D_B.parameters(), lr=lr, betas=(0.5, 0.999))
+        self.optimizer_G = Adam(list(self.G_A2B.parameters()) + list(self.G_B2A.parameters()), lr=lr, betas=(0.5, 0.999),
+                                capturable=capturable)
+        self.optimizer_D_A = Adam(self.D_A.parameters(), lr=lr, betas=(0.5, 0.999), capturable=capturable)
+        self.optimizer_D_B = Adam(self.D_B.parameters(), lr=lr, betas=(0.5, 0.999), capturable=capturable)
         self.lambda_cyc, self.lambda_id = lambda_cyc, lambda_id
         self.grad_hook = None   # optional callable(list of params) run before each optimizer.step (data-parallel all-reduce)
 

@@ -209,6 +209,12 @@ int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n,
  * exp_avg / exp_avg_sq of n elements updated in one pass; step counts from 1. */
 int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                      float beta2, float eps, int step, ducosy_stream_t stream);
+/* The same update with {lr, step} read from DEVICE memory (state[0] = lr, state[1] = step as a float), for CUDA-graph capture
+ * of a whole optimisation step: ducosy_adam_advance increments the step once per optimizer.step(), then one
+ * ducosy_adam_step_dev per tensor. */
+int ducosy_adam_advance(float* state, ducosy_stream_t stream);
+int ducosy_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* state,
+                         float beta1, float beta2, float eps, ducosy_stream_t stream);
 /* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
 int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 

@@ -10,7 +10,7 @@ import torch
 import torch.distributed as dist
 
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
-from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, shard_batch  # noqa: E402
+from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, GraphedCycleGANStep, shard_batch  # noqa: E402
 from ducosy_gan_b200.trainer import CycleGANStep  # noqa: E402
 
 rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
@@ -56,22 +56,28 @@ dist.barrier()
 # ---- (2) timing at global batch 8
 A, Bt, M = batch(8, 2)
 lo, hi = shard_batch(8, rank, world)
-dp = DataParallelCycleGANStep(Cin, blocks, True, seed=1234)
+use_graph = os.environ.get("DP_GRAPH", "1") == "1"
+dp = DataParallelCycleGANStep(Cin, blocks, True, seed=1234, capturable=use_graph)
+if use_graph:
+    graphed = GraphedCycleGANStep(dp, A[lo:hi].contiguous(), Bt[lo:hi].contiguous(), M[lo:hi].contiguous(), warmup=2)
+    run_step = lambda: graphed(A[lo:hi], Bt[lo:hi], M[lo:hi])
+else:
+    run_step = lambda: dp.step(A[lo:hi], Bt[lo:hi], M[lo:hi])
 for _ in range(2):
-    dp.step(A[lo:hi], Bt[lo:hi], M[lo:hi])
+    run_step()
 steps = 5
 dist.barrier()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(steps):
-    out = dp.step(A[lo:hi], Bt[lo:hi], M[lo:hi])
+    out = run_step()
 e1.record()
 torch.cuda.synchronize()
 t = torch.tensor([e0.elapsed_time(e1) / steps], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
-    res.update(global_batch=8, ms_per_step=t.item(), steps_per_s=1e3 / t.item(), samples_per_s=8e3 / t.item(),
+    res.update(global_batch=8, cuda_graph=use_graph, ms_per_step=t.item(), steps_per_s=1e3 / t.item(), samples_per_s=8e3 / t.item(),
                final_losses={k: float(v) for k, v in out.items()})
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
