@@ -190,6 +190,7 @@ def train_metric(device, rank, world, steps, warmup=2):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    graphed.close()      # the graph holds captured NCCL collectives: it must be gone before the process group is torn down
     tflop = (6 * B * 451.11 * 3 + 6 * B * 13.04 * 3) / 1e3      # nominal conv work, backward = 2x forward
     return {"metric": "cyclegan_train_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
             "warmup": max(warmup, 2) + 1, "global_batch": B, "scaling": "strong", "loss_G": loss, "cuda_graph": True,

@@ -176,6 +176,15 @@ class GraphedCycleGANStep:
             self.out = step.step(*self.static)
         self._params = [p for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B) for p in m.parameters()]
 
+    def close(self):
+        """Release the graph.  Call this before ``torch.distributed.destroy_process_group()``: tearing NCCL down while a
+        live graph still holds captured collectives blocks forever."""
+        if self.graph is not None:
+            torch.cuda.synchronize()
+            self.graph.reset()
+            self.graph = None
+            self.out = None
+
     def __call__(self, real_A, real_B, masks=None):
         for dst, src in zip(self.static, (real_A, real_B, masks)):
             if dst is not None:

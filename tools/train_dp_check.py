@@ -82,4 +82,7 @@ if rank == 0:
     print(json.dumps(res, indent=1))
     os.makedirs("gpurun_out", exist_ok=True)
     json.dump(res, open(f"gpurun_out/train_dp{world}.json", "w"), indent=1)
+if use_graph:
+    graphed.close()
+dist.barrier()
 dist.destroy_process_group()
