@@ -12,6 +12,9 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a real B200 (run with -m gpu on the GPU box)")
+    # The stated tolerances are those of the default operand type (fp16).  Tests that cover bf16 select it themselves
+    # (monkeypatch / explicit dtype arguments), so an inherited DUCOSY_PRECISION must not silently change what is tested.
+    os.environ["DUCOSY_PRECISION"] = "fp16"
 
 
 @pytest.fixture(scope="session")
