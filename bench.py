@@ -274,7 +274,10 @@ def main():
         del dev_out, dev_vol
         synth = None
         torch.cuda.empty_cache()
-        train = train_metric(device, rank, world, args.train_steps)
+        try:
+            train = train_metric(device, rank, world, args.train_steps)
+        except Exception as exc:          # the synthesis line above is the contract; a failing extra must not take it down
+            train = {"metric": "cyclegan_train_steps_per_s", "error": f"{type(exc).__name__}: {exc}"[:300]}
 
     value = world * S * args.steps / sec
     e2e_value = world * S * args.steps / sec_e2e
