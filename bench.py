@@ -299,7 +299,10 @@ def main():
             "clocks": clocks,
             "roofline": {"bound": "tensor", "kernel": "conv_gemm_kernel<256> (3x3 256->256 residual-block conv)",
                          "achieved": achieved, "peak": pk["tf_burst"], "unit": "TFLOP/s", "frac": achieved / pk["tf_burst"],
-                         "traffic": None, "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
+                         "traffic": 4.85e8 if args.batch_slices == 30 else None,
+                         "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at "
+                                         "batch 30 (profiles/r01_final_conv256_kernel.txt); algorithmic 5.13e8",
+                         "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
                          "path_frac_of_sustained": value / world * GFLOP_PER_SLICE / 1e3 / pk["tf_sustained"]},
         }
         if train is not None:
