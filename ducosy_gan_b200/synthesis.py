@@ -48,6 +48,7 @@ class DualHUSynthesizer:
         self.soft_hu, self.lung_hu = tuple(map(float, soft_hu)), tuple(map(float, lung_hu))
         self.batch_slices = int(batch_slices)
         self._streams = None
+        self._copy_streams = None
         self._bufs = {}
 
     # ------------------------------------------------------------------ helpers
@@ -74,7 +75,7 @@ class DualHUSynthesizer:
 
     # ------------------------------------------------------------------ device-resident volume
     def synthesize_device(self, raw_px: torch.Tensor, slope=1.0, intercept=-1024.0, out: torch.Tensor | None = None,
-                          postprocess: bool = False, group=None):
+                          postprocess: bool = False, group=None, before_chunk=None, after_chunk=None):
         """raw_px: int16 [S,H,W] on this GPU -> merged int16 [S,H,W] (same device).  Asynchronous.
         ``postprocess=True`` appends the volume smoothing of generate.py:254-263 on the device (``postprocess.py``); when
         the volume is sharded over the ranks of ``group`` this is where the path has its one exchange (z halo)."""
@@ -99,6 +100,8 @@ class DualHUSynthesizer:
             for lo in range(0, S, B):
                 n = min(B, S - lo)
                 chunk = raw_px[lo:lo + n]
+                if before_chunk is not None:
+                    before_chunk(lo, n)      # e.g. wait for the host->device copy of these slices (synthesize_volume)
                 if n != B:  # ragged tail: run it as its own (smaller) batch after the pipeline drains
                     cur.wait_stream(s_soft)
                     cur.wait_stream(s_lung)
@@ -109,6 +112,8 @@ class DualHUSynthesizer:
                     es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys_t)
                     el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl_t)
                     ops.dewindow_composite(chunk, ys_t, yl_t, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+                    if after_chunk is not None:
+                        after_chunk(lo, n)
                     continue
                 s_soft.wait_stream(cur)
                 s_lung.wait_stream(cur)
@@ -119,6 +124,8 @@ class DualHUSynthesizer:
                 cur.wait_stream(s_soft)
                 cur.wait_stream(s_lung)
                 ops.dewindow_composite(chunk, ys, yl, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+                if after_chunk is not None:
+                    after_chunk(lo, n)
             if postprocess:
                 from .postprocess import postprocess_volume_sharded
                 out.copy_(postprocess_volume_sharded(out, group))
@@ -135,11 +142,44 @@ class DualHUSynthesizer:
             return self.synthesize_device(raw_px, slope, intercept, postprocess=postprocess, group=group)
         if raw_px.dtype != torch.int16 or raw_px.dim() != 3:
             raise RuntimeError("synthesize_volume expects int16 [S,H,W] stored pixel values")
+        S, H, W = raw_px.shape
         with torch.cuda.device(self.device):
-            dev_in = raw_px.to(self.device, non_blocking=True)
-            dev_out = self.synthesize_device(dev_in, slope, intercept, postprocess=postprocess, group=group)
             if out_host is None:
                 out_host = torch.empty(raw_px.shape, dtype=torch.int16, pin_memory=True)
-            out_host.copy_(dev_out, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+            cur = torch.cuda.current_stream()
+            if self._copy_streams is None:
+                self._copy_streams = (torch.cuda.Stream(), torch.cuda.Stream())
+            s_in, s_out = self._copy_streams
+            dev_in = torch.empty((S, H, W), dtype=torch.int16, device=self.device)
+            dev_out = torch.empty_like(dev_in)
+            s_in.wait_stream(cur)
+            s_out.wait_stream(cur)
+            # chunk-wise pipeline: the copy engines move slices k+1 in and k-1 out while the SMs work on chunk k
+            B = max(1, min(self.batch_slices, S)) if S else 1
+            ready = {}
+            with torch.cuda.stream(s_in):
+                for lo in range(0, S, B):
+                    dev_in[lo:lo + B].copy_(raw_px[lo:lo + B], non_blocking=True)
+                    ready[lo] = torch.cuda.Event()
+                    ready[lo].record(s_in)
+
+            def before_chunk(lo, n):
+                cur.wait_event(ready[lo])
+
+            def after_chunk(lo, n):
+                if postprocess:
+                    return                     # the smoothing needs the whole volume: one copy at the end
+                done = torch.cuda.Event()
+                done.record(cur)
+                s_out.wait_event(done)
+                with torch.cuda.stream(s_out):
+                    out_host[lo:lo + n].copy_(dev_out[lo:lo + n], non_blocking=True)
+
+            if S:
+                self.synthesize_device(dev_in, slope, intercept, out=dev_out, postprocess=postprocess, group=group,
+                                       before_chunk=before_chunk, after_chunk=after_chunk)
+            if postprocess:
+                out_host.copy_(dev_out, non_blocking=True)
+            cur.wait_stream(s_out)
+            cur.synchronize()
         return out_host
