@@ -729,7 +729,8 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
   DUCOSY_CHECK(dy_pad2 && w_dgrad && dxpad && B > 0, DUCOSY_ERR_ARG, "conv3x3s1_dgrad: null pointer");
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv3x3s1_dgrad: bad dtype");
   DUCOSY_CHECK(Cout % 64 == 0 && Cin % 64 == 0, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: channels must be multiples of 64");
-  DUCOSY_CHECK(W % 128 == 0, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: W must be a multiple of 128 (the H+2 padded rows are tiled row by row)");
+  DUCOSY_CHECK(W % 128 == 0 || (W == 64 && H % 2 == 0), DUCOSY_ERR_SHAPE,
+               "conv3x3s1_dgrad: W must be a multiple of 128, or 64 with an even H (the H+2 padded rows are tiled in 128-pixel tiles)");
   DUCOSY_TRY(ducosy_check_device());
   ConvPlan p{};
   p.in = dy_pad2; p.B = B; p.Hp = H + 4; p.Wp = W + 4; p.Cin = Cout; p.stride = 1;

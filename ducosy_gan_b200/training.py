@@ -29,8 +29,8 @@ def generator_forward_train(params, cfg, x, dtype):
     _, num_blocks, use_cbam = cfg
     stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
     B, _, H, W = x.shape
-    if H % 32 or W % 512:
-        raise RuntimeError(f"training path needs H % 32 == 0 and W % 512 == 0 (got {H}x{W}); 512x512 is what train.py uses")
+    if H % 32 or (W % 512 and W != 256):
+        raise RuntimeError(f"training path needs H % 32 == 0 and W = 256 or a multiple of 512 (got {H}x{W}); 512x512 is what train.py uses")
     S = {"shape": (B, H, W)}
     S["cols"] = ops.stem_im2col(x, dtype)
     y0, part = ops.conv2d_nhwc(S["cols"], ops.pack_stem_weight(stem[0], dtype), 1, 1, 1)

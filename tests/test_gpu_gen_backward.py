@@ -210,7 +210,7 @@ def test_generator_plain_backward_matches_autograd(cfg):
     _assert_at_noise_floor(Cin, blocks, False, B, H, W)
 
 
-@pytest.mark.parametrize("cfg", [(1, 2, 1, 64, 512), (2, 1, 2, 32, 512)])
+@pytest.mark.parametrize("cfg", [(1, 2, 1, 64, 512), (2, 1, 2, 32, 512), (1, 1, 1, 256, 256)])
 def test_generator_cbam_backward_matches_autograd(cfg):
     """ResidualBlockWithCBAM generator (the shipped configuration): conv, channel-attention MLP and spatial-attention
     gradients plus the image gradient against fp32 autograd."""
