@@ -306,6 +306,74 @@ dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict_
     if (lane == 0) dxpad[(((long long)b * (H + 2) + u) * (W + 2) + v) * Ci + c] = Cvt<T>::from_f(acc);
   }
 }
+// Ci = Co = 256 (the residual blocks): the two edge columns are a [16 positions] x [768] x [256 channels] GEMM per CTA on
+// the warp-level tensor cores (mma.sync m16n8k16, fp32 accumulate): A = the dy rows the 16 positions meet (shared
+// memory, rows padded by 16 bytes against bank conflicts), B = the packed dgrad weights read straight from L2.
+template <typename T> struct EdgeMma;
+template <> struct EdgeMma<__half> {
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+template <> struct EdgeMma<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+constexpr int kEdgePitch = 256 + 8;   // elements per staged dy row
+template <typename T>
+__global__ void __launch_bounds__(256)
+dgrad_s1_edge_cols_mma_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H, int W) {
+  constexpr int C = 256;
+  __shared__ __align__(16) T rows[18 * kEdgePitch];   // rows[j][o] = dy_pad2[b][u0 + j][v - s + 2][o], j = m - r + 2
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tid = lane & 3;
+  const int u0 = blockIdx.x * 16, side = blockIdx.y, b = blockIdx.z;
+  const int v = side ? W + 1 : 0, s = side ? 2 : 0;
+  for (int i = threadIdx.x; i < 18 * 32; i += 256) {
+    const int j = i >> 5, piece = i & 31;
+    uint4 val = make_uint4(0, 0, 0, 0);
+    if (u0 + j < H + 4)
+      val = *reinterpret_cast<const uint4*>(dy_pad2 + (((long long)b * (H + 4) + (u0 + j)) * (W + 4) + (v - s + 2)) * C + piece * 8);
+    *reinterpret_cast<uint4*>(rows + j * kEdgePitch + piece * 8) = val;
+  }
+  __syncthreads();
+  float acc[4][4];
+#pragma unroll
+  for (int n = 0; n < 4; ++n)
+#pragma unroll
+    for (int k = 0; k < 4; ++k) acc[n][k] = 0.f;
+  const int c_base = warp * 32;
+#pragma unroll 1
+  for (int r = 0; r < 3; ++r) {
+    const T* ra = rows + (g - r + 2) * kEdgePitch + 2 * tid;        // position m = g
+    const T* rb = ra + 8 * kEdgePitch;                               // position m = g + 8
+    const T* wrow = wd + ((long long)(c_base + g) * 9 + r * 3 + s) * C + 2 * tid;
+#pragma unroll 4
+    for (int kk = 0; kk < 16; ++kk) {
+      const int o0 = kk * 16;
+      const uint32_t a0 = *reinterpret_cast<const uint32_t*>(ra + o0), a1 = *reinterpret_cast<const uint32_t*>(rb + o0);
+      const uint32_t a2 = *reinterpret_cast<const uint32_t*>(ra + o0 + 8), a3 = *reinterpret_cast<const uint32_t*>(rb + o0 + 8);
+#pragma unroll
+      for (int n = 0; n < 4; ++n) {
+        const T* wn = wrow + (long long)n * 8 * 9 * C + o0;          // channel c_base + n*8 + g
+        const uint32_t b0 = __ldg(reinterpret_cast<const unsigned int*>(wn));
+        const uint32_t b1 = __ldg(reinterpret_cast<const unsigned int*>(wn + 8));
+        EdgeMma<T>::mma(acc[n], a0, a1, a2, a3, b0, b1);
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < 4; ++n) {
+    const int c = c_base + n * 8 + 2 * tid;
+    const int ua = u0 + g, ub = u0 + g + 8;
+    if (ua < H + 2)
+      *reinterpret_cast<uint32_t*>(dxpad + (((long long)b * (H + 2) + ua) * (W + 2) + v) * C + c) = Cvt<T>::pack2(acc[n][0], acc[n][1]);
+    if (ub < H + 2)
+      *reinterpret_cast<uint32_t*>(dxpad + (((long long)b * (H + 2) + ub) * (W + 2) + v) * C + c) = Cvt<T>::pack2(acc[n][2], acc[n][3]);
+  }
+}
 // adjoint of the padding: gradient w.r.t. the padded map [B][H+2p][W+2p][C] -> gradient w.r.t. the un-padded map
 template <typename T>
 __global__ void pad_fold_kernel(const T* __restrict__ dxpad, const T* __restrict__ add, T* __restrict__ dx, int B, int H, int W, int C,
@@ -744,6 +812,11 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
   p.out_y_off = 0; p.out_x_off = 1;
   p.partials = nullptr; p.dtype = dtype;
   DUCOSY_TRY(launch_conv_gemm(p, static_cast<cudaStream_t>(stream)));
+  if (Cout == 256 && Cin == 256) {
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols_mma_kernel<T><<<dim3((H + 2 + 15) / 16, 2, B), 256, 0, (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W)));
+    return check_launch("dgrad_s1_edge_cols_mma_kernel");
+  }
   if (Cout == 256 && Cin % 8 == 0) {
     const int cps = std::max(1, std::min(H + 2, (148 * 16) / std::max(1, Cin / 8 * 2 * B)));
     const int per = (H + 2 + cps - 1) / cps, chunks = (H + 2 + per - 1) / per;
