@@ -362,7 +362,7 @@ def test_soft_squeeze_window_and_display_windowing(ops):
 
 
 @pytest.mark.parametrize("mode", ["reflect", "zero"])
-@pytest.mark.parametrize("case", [(2, 32, 128, 256, 256), (1, 16, 128, 128, 64), (1, 8, 256, 64, 128)])
+@pytest.mark.parametrize("case", [(2, 32, 128, 256, 256), (1, 16, 128, 128, 64), (1, 8, 256, 64, 128), (1, 16, 64, 256, 256)])
 def test_conv3x3s1_dgrad_with_pad_fold(ops, case, mode):
     B, H, W, Cin, Cout = case
     dtype = torch.float16
