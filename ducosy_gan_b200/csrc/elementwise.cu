@@ -1,8 +1,6 @@
 // Bandwidth-bound kernels around the tensor-core convolutions: weight packing, stem im2col (optionally fused
 // with the HU window), InstanceNorm finalize/apply (+ReLU, + padding writer), CBAM channel MLP, CBAM spatial
 // pooling / 7x7 attention conv, and the residual add.  NHWC 16-bit activations, 128-bit accesses.
-#include <algorithm>
-
 #include "common.cuh"
 #include "input_fn.cuh"
 
@@ -487,14 +485,8 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
   }
 }
 
-// Row-persistent kernels: exactly as many CTAs as can be resident (SMs x CTAs per SM from the occupancy calculator).  A
-// grid of 4 per SM with only 3 resident ran 1.33 waves -- the last third of the rows on a third of the machine.
-template <typename Kernel>
-int row_grid(int rows, Kernel kernel) {
-  int per_sm = 0;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, 256, 0) != cudaSuccess || per_sm < 1) per_sm = 2;
-  if (per_sm > 4) per_sm = 4;
-  const int cap = (num_sms() > 0 ? num_sms() : 148) * per_sm;
+int row_grid(int rows) {
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 4;
   return rows < cap ? (rows > 0 ? rows : 1) : cap;
 }
 
@@ -581,7 +573,7 @@ extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const floa
   DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_SHAPE, "in_apply_pad: C %% 8 != 0 or pad too large");
   DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "in_apply_pad: C must be one of 8..2048 with C/8 dividing 256");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad), in_apply_pad_kernel<T>), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
                                       pad_mode, act)));
   return check_launch("in_apply_pad_kernel");
@@ -594,9 +586,7 @@ extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* 
   DUCOSY_CHECK((H * W) % 4 == 0, DUCOSY_ERR_SHAPE, "cbam_pool: H*W must be a multiple of 4");
   const int groups = H * W / 4;
   int gx = (groups + 7) / 8;                     // 8 warps per CTA
-  int resident = 0;   // one wave of resident CTAs (see row_grid)
-  DUCOSY_DISPATCH_DTYPE(dtype, T, resident = row_grid(1 << 30, cbam_pool_kernel<T>));
-  const int cap = std::max(1, resident / B);
+  const int cap = (num_sms() > 0 ? num_sms() : 148) * 8 / (B > 0 ? B : 1) + 1;
   if (gx > cap) gx = cap;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), H * W)));
@@ -619,7 +609,7 @@ extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, cons
                "residual_apply_pad: bad shape");
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_apply_pad: C/8 must divide 256");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad), residual_apply_pad_kernel<T>), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
                                       static_cast<const T*>(y), scale, shift, sa, static_cast<const T*>(res_pad),
                                       res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");
