@@ -454,3 +454,60 @@ def postprocess_volume(merged: np.ndarray, pre_sigma_z=0.8, sigma_z=0.7, sigma_x
     sharp = np.clip(sm + comb * sharpen_amount, orig.min(), orig.max())              # postprocess.py:156-159
     sharp[high] = original[high]                                                     # postprocess.py:106
     return sharp.astype(np.int16)                                                    # postprocess.py:109
+
+
+# --------------------------------------------------------------------------------------
+# CycleGAN optimisation step
+# --------------------------------------------------------------------------------------
+def cyclegan_generator_loss(sdGA, sdGB, sdDA, sdDB, real_A, real_B, masks=None, num_residual_blocks=9, use_cbam=True,
+                            lambda_cyc=10.0, lambda_id=5.0):
+    """The generator half of the loop body, modules/trainer.py:447-512, on state dicts: returns (loss_G, dict of the nine
+    terms, fake_A, fake_B).  Loss weights: trainer.py:493-512 and argmanager.py:97-98."""
+    G = lambda sd, x: generator_forward(sd, x, num_residual_blocks, use_cbam)
+    cat = (lambda t: torch.cat([t, masks], 1)) if masks is not None else (lambda t: t)
+    l1 = F.l1_loss
+    fake_B, fake_A = G(sdGA, cat(real_A)), G(sdGB, cat(real_B))                          # trainer.py:464
+    id_A, id_B = G(sdGB, cat(real_A)), G(sdGA, cat(real_B))                              # trainer.py:467
+    t = {}
+    t["id"] = (l1(id_A, real_A) + l1(id_B, real_B)) / 2                                  # trainer.py:469
+    t["GAN"] = (mse_gan_loss(discriminator_forward(sdDB, fake_B), True)
+                + mse_gan_loss(discriminator_forward(sdDA, fake_A), True)) / 2           # trainer.py:470
+    rec_A, rec_B = G(sdGB, cat(fake_B)), G(sdGA, cat(fake_A))                            # trainer.py:474-480
+    t["cycle"] = (l1(rec_A, real_A) + l1(rec_B, real_B)) / 2                             # trainer.py:482
+    t["grad_cycle"] = (gradient_loss(rec_A, real_A) + gradient_loss(rec_B, real_B)) / 2  # trainer.py:483
+    t["grad_id"] = (gradient_loss(id_A, real_A) + gradient_loss(id_B, real_B)) / 2       # trainer.py:484
+    t["ssim"] = 1 - (ssim(rec_A, real_A) + ssim(rec_B, real_B)) / 2                      # trainer.py:485
+    t["contrast_attention"] = contrast_attention_loss(fake_B, real_B, real_A)            # trainer.py:489
+    t["contrast_region"] = contrast_region_loss(fake_B, real_B, real_A)                  # trainer.py:490
+    t["contrast_edge"] = contrast_edge_loss(fake_B, real_B, real_A)                      # trainer.py:491
+    loss_G = (t["GAN"] + lambda_cyc * t["cycle"] + lambda_id * t["id"] + 5.0 * t["grad_cycle"] + 2.5 * t["grad_id"]
+              + 2.0 * t["ssim"] + 2.0 * t["contrast_attention"] + 1.5 * t["contrast_region"] + 1.0 * t["contrast_edge"])
+    return loss_G, t, fake_A, fake_B
+
+
+def cyclegan_discriminator_loss(sdD, real, fake):
+    """modules/trainer.py:518 / :523."""
+    return (mse_gan_loss(discriminator_forward(sdD, real), True)
+            + mse_gan_loss(discriminator_forward(sdD, fake.detach()), False)) / 2
+
+
+def cyclegan_step(sds, opts, real_A, real_B, masks=None, num_residual_blocks=9, use_cbam=True):
+    """One iteration of modules/trainer.py:462-524 with torch autograd and the given optimisers (opt_G, opt_D_A, opt_D_B) over
+    the state dicts (sdGA, sdGB, sdDA, sdDB) whose tensors require grad.  Returns the logged losses as floats."""
+    sdGA, sdGB, sdDA, sdDB = sds
+    oG, oDA, oDB = opts
+    oG.zero_grad()
+    loss_G, t, fake_A, fake_B = cyclegan_generator_loss(sdGA, sdGB, sdDA, sdDB, real_A, real_B, masks, num_residual_blocks, use_cbam)
+    loss_G.backward()
+    oG.step()
+    oDA.zero_grad()
+    loss_DA = cyclegan_discriminator_loss(sdDA, real_A, fake_A)
+    loss_DA.backward()
+    oDA.step()
+    oDB.zero_grad()
+    loss_DB = cyclegan_discriminator_loss(sdDB, real_B, fake_B)
+    loss_DB.backward()
+    oDB.step()
+    out = {k: float(v.detach()) for k, v in t.items()}
+    out.update(G=float(loss_G.detach()), D_A=float(loss_DA.detach()), D_B=float(loss_DB.detach()))
+    return out

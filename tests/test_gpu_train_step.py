@@ -46,28 +46,10 @@ def test_fused_adam_invalidates_packed_weight_caches():
 
 
 def _oracle_step_losses(sdG_A, sdG_B, sdD_A, sdD_B, real_A, real_B, masks, blocks, cbam):
-    G = lambda sd, x: orc.generator_forward(sd, x, blocks, cbam)
-    cat = (lambda t: torch.cat([t, masks], 1)) if masks is not None else (lambda t: t)
-    l1 = torch.nn.functional.l1_loss
-    fake_B, fake_A = G(sdG_A, cat(real_A)), G(sdG_B, cat(real_B))
-    id_A, id_B = G(sdG_B, cat(real_A)), G(sdG_A, cat(real_B))
-    t = {}
-    t["id"] = (l1(id_A, real_A) + l1(id_B, real_B)) / 2
-    t["GAN"] = (orc.mse_gan_loss(orc.discriminator_forward(sdD_B, fake_B), True)
-                + orc.mse_gan_loss(orc.discriminator_forward(sdD_A, fake_A), True)) / 2
-    rec_A, rec_B = G(sdG_B, cat(fake_B)), G(sdG_A, cat(fake_A))
-    t["cycle"] = (l1(rec_A, real_A) + l1(rec_B, real_B)) / 2
-    t["grad_cycle"] = (orc.gradient_loss(rec_A, real_A) + orc.gradient_loss(rec_B, real_B)) / 2
-    t["grad_id"] = (orc.gradient_loss(id_A, real_A) + orc.gradient_loss(id_B, real_B)) / 2
-    t["ssim"] = 1 - (orc.ssim(rec_A, real_A) + orc.ssim(rec_B, real_B)) / 2
-    t["contrast_attention"] = orc.contrast_attention_loss(fake_B, real_B, real_A)
-    t["contrast_region"] = orc.contrast_region_loss(fake_B, real_B, real_A)
-    t["contrast_edge"] = orc.contrast_edge_loss(fake_B, real_B, real_A)
-    t["G"] = (t["GAN"] + 10.0 * t["cycle"] + 5.0 * t["id"] + 5.0 * t["grad_cycle"] + 2.5 * t["grad_id"] + 2.0 * t["ssim"]
-              + 2.0 * t["contrast_attention"] + 1.5 * t["contrast_region"] + 1.0 * t["contrast_edge"])
-    D = orc.discriminator_forward
-    t["D_A"] = (orc.mse_gan_loss(D(sdD_A, real_A), True) + orc.mse_gan_loss(D(sdD_A, fake_A), False)) / 2
-    t["D_B"] = (orc.mse_gan_loss(D(sdD_B, real_B), True) + orc.mse_gan_loss(D(sdD_B, fake_B), False)) / 2
+    """step-1 loss terms from the oracle's restatement of the loop body (oracle.cyclegan_generator_loss / _discriminator_loss)"""
+    loss_G, t, fake_A, fake_B = orc.cyclegan_generator_loss(sdG_A, sdG_B, sdD_A, sdD_B, real_A, real_B, masks, blocks, cbam)
+    t = dict(t, G=loss_G, D_A=orc.cyclegan_discriminator_loss(sdD_A, real_A, fake_A),
+             D_B=orc.cyclegan_discriminator_loss(sdD_B, real_B, fake_B))
     return {k: float(v) for k, v in t.items()}
 
 
@@ -123,35 +105,11 @@ def test_train_loss_trajectory_matches_oracle():
     oG = torch.optim.Adam(list(sdGA.values()) + list(sdGB.values()), lr=2e-4, betas=(0.5, 0.999))
     oDA = torch.optim.Adam(list(sdDA.values()), lr=2e-4, betas=(0.5, 0.999))
     oDB = torch.optim.Adam(list(sdDB.values()), lr=2e-4, betas=(0.5, 0.999))
-    G = lambda sd, x: orc.generator_forward(sd, x, blocks, cbam)
-    D = orc.discriminator_forward
-    l1 = torch.nn.functional.l1_loss
     ref_hist, got_hist = [], []
     for _ in range(N):
-        # ---- oracle step (reference modules/trainer.py:462-524 on the restated modules)
-        oG.zero_grad()
-        fake_B, fake_A = G(sdGA, real_A), G(sdGB, real_B)
-        id_A, id_B = G(sdGB, real_A), G(sdGA, real_B)
-        loss_id = (l1(id_A, real_A) + l1(id_B, real_B)) / 2
-        loss_GAN = (orc.mse_gan_loss(D(sdDB, fake_B), True) + orc.mse_gan_loss(D(sdDA, fake_A), True)) / 2
-        rec_A, rec_B = G(sdGB, fake_B), G(sdGA, fake_A)
-        loss_G = (loss_GAN + 10.0 * (l1(rec_A, real_A) + l1(rec_B, real_B)) / 2 + 5.0 * loss_id
-                  + 5.0 * (orc.gradient_loss(rec_A, real_A) + orc.gradient_loss(rec_B, real_B)) / 2
-                  + 2.5 * (orc.gradient_loss(id_A, real_A) + orc.gradient_loss(id_B, real_B)) / 2
-                  + 2.0 * (1 - (orc.ssim(rec_A, real_A) + orc.ssim(rec_B, real_B)) / 2)
-                  + 2.0 * orc.contrast_attention_loss(fake_B, real_B, real_A)
-                  + 1.5 * orc.contrast_region_loss(fake_B, real_B, real_A) + 1.0 * orc.contrast_edge_loss(fake_B, real_B, real_A))
-        loss_G.backward()
-        oG.step()
-        oDA.zero_grad()
-        loss_DA = (orc.mse_gan_loss(D(sdDA, real_A), True) + orc.mse_gan_loss(D(sdDA, fake_A.detach()), False)) / 2
-        loss_DA.backward()
-        oDA.step()
-        oDB.zero_grad()
-        loss_DB = (orc.mse_gan_loss(D(sdDB, real_B), True) + orc.mse_gan_loss(D(sdDB, fake_B.detach()), False)) / 2
-        loss_DB.backward()
-        oDB.step()
-        ref_hist.append(dict(G=loss_G.item(), D_A=loss_DA.item(), D_B=loss_DB.item(), GAN=loss_GAN.item(), id=loss_id.item()))
+        # ---- oracle step (reference modules/trainer.py:462-524 restated in oracle.cyclegan_step)
+        ref = orc.cyclegan_step((sdGA, sdGB, sdDA, sdDB), (oG, oDA, oDB), real_A, real_B, None, blocks, cbam)
+        ref_hist.append({k: ref[k] for k in ("G", "D_A", "D_B", "GAN", "id")})
         # ---- CUDA step
         out = step.step(real_A.cuda(), real_B.cuda())
         got_hist.append({k: out[k].item() for k in ref_hist[-1]})
