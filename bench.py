@@ -201,6 +201,26 @@ def train_metric(device, rank, world, steps, warmup=2):
             "frac_of_sustained_peak_per_gpu": tflop / ms * 1e3 / world / peaks()["tf_sustained"]}
 
 
+def cpu_train_baseline():
+    """The oracle's restatement of the reference loop body (pinned to modules/trainer.py:448-525 by tests/golden/train_step.npz)
+    on the host cores: one optimisation step at batch 1 (batch 8 needs ~100 GB of autograd state)."""
+    from oracle import ducosy_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    mk = lambda shapes, seed: {k: v.clone().requires_grad_(True) for k, v in orc.make_state_dict(shapes, seed).items()}
+    gsh, dsh = orc.generator_param_shapes(3, 9, True), orc.discriminator_param_shapes(1)
+    sds = (mk(gsh, 1), mk(gsh, 2), mk(dsh, 3), mk(dsh, 4))
+    adam = lambda ps: torch.optim.Adam(ps, lr=2e-4, betas=(0.5, 0.999))
+    opts = (adam(list(sds[0].values()) + list(sds[1].values())), adam(list(sds[2].values())), adam(list(sds[3].values())))
+    g = torch.Generator().manual_seed(2)
+    a, b = (torch.rand(1, 1, H, W, generator=g) * 2 - 1 for _ in range(2))
+    m = (torch.rand(1, 2, H, W, generator=g) < 0.1).float()
+    t0 = time.perf_counter()
+    orc.cyclegan_step(sds, opts, a, b, m, 9, True)
+    sec = time.perf_counter() - t0
+    return {"value": 1.0 / sec, "unit": "steps/s at batch 1", "samples_per_s": 1.0 / sec, "cores": os.cpu_count(), "kind": "port",
+            "sample": "one optimisation step at batch 1 (512x512, Cin 3, 9 CBAM blocks), fp32 torch-CPU oracle of trainer.py:448-525"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -309,6 +329,11 @@ def main():
             line["train"] = train
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
+            if train is not None and "error" not in train:
+                try:
+                    train["cpu_baseline"] = cpu_train_baseline()
+                except Exception as exc:
+                    train["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
