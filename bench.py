@@ -145,7 +145,7 @@ def run_reference(args, rank):
     val = n * args.steps / dt
     cores = torch.get_num_threads()
     sample = f"{n} slices (512x512) per step of the {S}-slice volume; fp32 torch-CPU oracle port of the reference path"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -153,7 +153,7 @@ def run_reference(args, rank):
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }), flush=True)
+    })
 
 
 def train_metric(device, rank, world, steps, warmup=2):
@@ -221,6 +221,25 @@ def cpu_train_baseline():
             "sample": "one optimisation step at batch 1 (512x512, Cin 3, 9 CBAM blocks), fp32 torch-CPU oracle of trainer.py:448-525"}
 
 
+_REAL_STDOUT_FD = None
+
+
+def _quiet_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries underneath (NCCL prints its version banner to stdout at the first
+    communicator) must not add to it: file descriptor 1 points at stderr until the result line is written."""
+    global _REAL_STDOUT_FD
+    sys.stdout.flush()
+    _REAL_STDOUT_FD = os.dup(1)
+    os.dup2(2, 1)
+
+
+def _emit(line: dict):
+    sys.stdout.flush()
+    if _REAL_STDOUT_FD is not None:
+        os.dup2(_REAL_STDOUT_FD, 1)
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -232,6 +251,7 @@ def main():
     ap.add_argument("--train-steps", type=int, default=3, help="timed CycleGAN steps for the 'train' object (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    _quiet_stdout()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -334,8 +354,9 @@ def main():
                     train["cpu_baseline"] = cpu_train_baseline()
                 except Exception as exc:
                     train["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
-        print(json.dumps(line), flush=True)
+        _emit(line)
     if world > 1:
+        os.dup2(2, 1)      # NCCL teardown chatter, if any, after the result line
         dist.destroy_process_group()
 
 
