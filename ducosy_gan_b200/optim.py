@@ -30,6 +30,29 @@ class Adam(torch.optim.Optimizer):
                 st[0:1].fill_(float(group["lr"]))
                 self._dev_lr[gi] = float(group["lr"])
 
+    # -- checkpoint / resume (reference modules/trainer.py:394-396,586-588 save and restore the optimiser state_dicts) -----
+    def state_dict(self):
+        if self.capturable:          # graph replays advance only the device-side count: bring the host copies up to date
+            for gi, group in enumerate(self.param_groups):
+                st = self._dev_state.get(gi)
+                if st is not None:
+                    step = int(round(float(st[1].item())))
+                    for p in group["params"]:
+                        if p in self.state and self.state[p]:
+                            self.state[p]["step"] = step
+        return super().state_dict()
+
+    def load_state_dict(self, state_dict):
+        super().load_state_dict(state_dict)
+        self._dev_state, self._dev_lr = {}, {}
+        if self.capturable:
+            for gi, group in enumerate(self.param_groups):
+                steps = [int(self.state[p]["step"]) for p in group["params"] if p in self.state and self.state[p]]
+                if steps:
+                    dev = group["params"][0].device
+                    self._dev_state[gi] = torch.tensor([float(group["lr"]), float(max(steps))], dtype=torch.float32, device=dev)
+                    self._dev_lr[gi] = float(group["lr"])
+
     def _state_for(self, gi, group, device):
         st = self._dev_state.get(gi)
         if st is None:

@@ -28,6 +28,46 @@ def test_fused_adam_matches_torch_adam():
             assert (a - b).abs().max().item() <= 1e-6 * b.abs().max().item() + 1e-7
 
 
+@pytest.mark.parametrize("capturable", [False, True])
+def test_fused_adam_state_dict_round_trip(capturable):
+    """checkpoint / resume as reference modules/trainer.py:394-396,586-588 does it: an optimiser restored from state_dict()
+    continues exactly like the uninterrupted one (including the device-side step count of the capturable mode), and a
+    state_dict written by torch.optim.Adam loads into the fused one."""
+    from ducosy_gan_b200.optim import Adam
+    torch.manual_seed(3)
+    w0 = torch.randn(300, 70, device="cuda")
+    grads = [torch.randn_like(w0) for _ in range(5)]
+
+    def run(opt, p, gs):
+        for g in gs:
+            p.grad = g.clone()
+            opt.step()
+
+    a = w0.clone().requires_grad_(True)
+    oa = Adam([a], lr=1e-3, betas=(0.5, 0.999), capturable=capturable)
+    run(oa, a, grads)                                             # uninterrupted
+    b = w0.clone().requires_grad_(True)
+    ob = Adam([b], lr=1e-3, betas=(0.5, 0.999), capturable=capturable)
+    run(ob, b, grads[:2])
+    import copy
+    ckpt = copy.deepcopy(ob.state_dict())
+    c = b.detach().clone().requires_grad_(True)
+    oc = Adam([c], lr=1e-3, betas=(0.5, 0.999), capturable=capturable)
+    oc.load_state_dict(ckpt)
+    run(oc, c, grads[2:])
+    assert torch.equal(a, c)
+    t = w0.clone().requires_grad_(True)                           # a checkpoint written by the reference's optimiser class
+    ot = torch.optim.Adam([t], lr=1e-3, betas=(0.5, 0.999))
+    run(ot, t, grads[:2])
+    d = t.detach().clone().requires_grad_(True)
+    od = Adam([d], lr=1e-3, betas=(0.5, 0.999), capturable=capturable)
+    import copy
+    od.load_state_dict(copy.deepcopy(ot.state_dict()))        # state_dict() hands out the live buffers, not copies
+    run(od, d, grads[2:])
+    run(ot, t, grads[2:])
+    assert (d - t).abs().max().item() <= 1e-6 * t.abs().max().item() + 1e-7
+
+
 def test_fused_adam_invalidates_packed_weight_caches():
     """the kernel writes parameters through raw pointers: a module's next forward must see the new weights"""
     from ducosy_gan_b200.modules.model import Discriminator, weights_init_normal
