@@ -1,5 +1,6 @@
 // Shared host/device declarations for libducosy_sm100.so
 #pragma once
+#include <atomic>
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
@@ -29,6 +30,18 @@ int check_launch(const char* what);  // cudaGetLastError -> code
   } while (0)
 
 int num_sms();
+
+// Per-function attributes (cudaFuncSetAttribute) live in the device context: a process that drives several GPUs
+// (nn.DataParallel replicas on Python threads) must set them once per device, not once per process.
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool first() {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    const unsigned long long bit = 1ull << dev;
+    return (mask.fetch_or(bit) & bit) == 0;
+  }
+};
 
 constexpr int kMaxTaps = 16;
 constexpr int kMaxPhases = 4;

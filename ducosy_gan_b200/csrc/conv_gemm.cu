@@ -337,12 +337,11 @@ template <int kN, typename T, int kCG>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmArgs& args,
                 int grid, cudaStream_t stream) {
   using C = Cfg<kN, kCG>;
-  static bool configured = false;
+  static PerDeviceOnce configured;
   auto kern = conv_gemm_kernel<kN, T, kCG>;
-  if (!configured) {
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes));
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
-    configured = true;
   }
   if (kCG == 2) {
     cudaLaunchConfig_t cfg{};

@@ -300,8 +300,8 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   const int grid = splits * units;
 #define DUCOSY_WGRAD_LAUNCH(T, MP)                                                                              \
   do {                                                                                                          \
-    static bool cfg = false;                                                                                    \
-    if (!cfg) { cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); cfg = true; } \
+    static PerDeviceOnce cfg;                                                                                   \
+    if (cfg.first()) cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
     conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
   } while (0)
   if (dtype == DUCOSY_F16) {

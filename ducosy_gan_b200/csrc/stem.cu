@@ -260,11 +260,10 @@ int launch_stem_pass(const void* xw, const void* wp, float* partials, const floa
   const size_t smem = 1024 + size_t(kTilesPerCta) * kATile + 64 * 128 + 64 * 8 + 4 * 2 * 64 * 4 + 32 +
                       size_t(7) * (W + 16) * 2 + 16;
   auto kern = stem_fused_kernel<T, kApply>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce configured;
+  if (configured.first()) {
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(stem_fused): %s", cudaGetErrorString(e));
-    configured = true;
   }
   DUCOSY_CHECK(smem <= 112 * 1024, DUCOSY_ERR_SHAPE, "stem_fused: image too wide (W = %d)", W);
   kern<<<dim3(H, B), kStemThreads, smem, st>>>(static_cast<const T*>(xw), static_cast<const T*>(wp), partials, scale,

@@ -20,6 +20,19 @@ _NO_TRAIN_MSG = ("ducosy_gan_b200: the autograd (training) path of {} is not bui
                  "inference forward only; call it under torch.no_grad(). There is deliberately no PyTorch fallback.")
 
 
+def _ordered_params(module):
+    """Parameters in ``named_parameters()`` order.  A replica made by ``nn.DataParallel`` (reference modules/trainer.py:335-338)
+    has no parameters of its own -- ``replicate`` stores the broadcast copies in ``_former_parameters`` of every sub-module, in
+    registration order -- so those are collected instead (they carry the grad_fn that reduces gradients back to the master)."""
+    ps = [p for _, p in module.named_parameters()]
+    if ps or not getattr(module, "_is_replica", False):
+        return ps
+    out = []
+    for m in module.modules():
+        out.extend(getattr(m, "_former_parameters", {}).values())
+    return out
+
+
 def default_operand_dtype() -> int:
     """16-bit operand type of the tensor-core convolutions: fp16 (default; TF32-class 10-bit mantissa, the
     reference's own GPU precision) or bf16 via DUCOSY_PRECISION=bf16."""
@@ -128,12 +141,12 @@ class Generator(nn.Module):
         return eng
 
     def _ordered_params(self):
-        return [p for _, p in self.named_parameters()]
+        return _ordered_params(self)
 
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("ducosy_gan_b200.Generator needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self._ordered_params())):
             if x.dim() != 4 or x.shape[1] != self._cfg_tuple[0]:
                 raise RuntimeError(f"expected input [B,{self._cfg_tuple[0]},H,W], got {tuple(x.shape)}")
             _lib.check(_lib.load().ducosy_check_device(), "check_device")
@@ -290,7 +303,7 @@ class Discriminator(nn.Module):
         eng = self._engines.get(key)
         if eng is None:
             eng = self._engines[key] = _DiscriminatorEngine(key[1], torch.device("cuda", key[0]))
-        params = [p for _, p in self.named_parameters()]
+        params = _ordered_params(self)
         eng.sync_weights(params)
         if torch.is_grad_enabled() and (img.requires_grad or any(p.requires_grad for p in params)):
             return _DiscriminatorFunction.apply(eng, img, *params)
