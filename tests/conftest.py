@@ -17,6 +17,17 @@ def pytest_configure(config):
     os.environ["DUCOSY_PRECISION"] = "fp16"
 
 
+def pytest_sessionstart(session):
+    """The library is a build artefact (git-ignored): compile it when the tree has none yet and nvcc is here, so that a fresh
+    checkout can run the suite without a separate build step.  Nothing is built when the .so exists (the GPU box gets it
+    with the snapshot) and nothing is faked when it cannot be built -- the ABI tests then fail loudly."""
+    import shutil
+    lib = os.path.join(ROOT, "ducosy_gan_b200", "lib", "libducosy_sm100.so")
+    if not os.path.exists(lib) and (shutil.which("nvcc") or os.path.exists("/usr/local/cuda/bin/nvcc")):
+        from ducosy_gan_b200 import build as _build
+        _build.build()
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN
