@@ -85,6 +85,26 @@ def test_generator_full_size_vs_oracle_and_golden(golden_dir):
     assert err < TOL_TANH["fp16"]
 
 
+def test_generator_config1_soft_tissue_with_mask_channels():
+    """BASELINE configs[0]: soft-tissue Generator A2B (input_channels = 3: slice + bone / mediastinum masks, 9 CBAM blocks),
+    batch 1, one 512x512 slice built as SURVEY 8d prescribes (windowed phantom slice, bone-candidate mask, Bernoulli(0.1)
+    mask) against the fp32 oracle: the stated fp16 tolerance, 3 HU max / 0.4 HU mean in the soft-tissue window."""
+    sd = orc.make_state_dict(orc.generator_param_shapes(3, 9, True), 1234)
+    G = _gen(3, 9, True, sd)
+    px = orc.phantom_volume(1, 512, 512, seed=0)[0]
+    hu = orc.stored_to_hu(px, 1.0, -1024.0)
+    ct = torch.from_numpy(orc.hu_window(px, 1.0, -1024.0, -150, 250).astype(np.float32))
+    bone = torch.from_numpy(((hu >= 200) & (hu > -1000)).astype(np.float32))
+    med = (torch.rand(512, 512, generator=torch.Generator().manual_seed(0)) < 0.1).float()
+    x = torch.stack([ct, bone, med])[None]
+    with torch.no_grad():
+        y = G(x.cuda()).cpu()
+        ref = orc.generator_forward(sd, x, 9, True)
+    err, mean = (y - ref).abs().max().item(), (y - ref).abs().mean().item()
+    print(f"config 1 (Cin=3, batch 1, 512x512): max {err:.3e} tanh units = {err * 200:.2f} HU, mean {mean * 200:.3f} HU")
+    assert err < TOL_TANH["fp16"] and mean < TOL_MEAN["fp16"]
+
+
 def test_generator_is_deterministic_and_batch_invariant():
     sd = orc.make_state_dict(orc.generator_param_shapes(1, 2, True), 5, attn_std=0.2)
     G = _gen(1, 2, True, sd)
