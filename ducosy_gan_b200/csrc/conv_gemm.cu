@@ -255,7 +255,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       else mbar_arrive(&tempty[as]);  // accumulator stage may be overwritten by the next-but-one tile
       fence_proxy_async_smem();        // generic-proxy writes above -> visible to the TMA (async proxy) store below
       named_bar_sync(1, kEpiThreads);
-      if (et == 0 && !(a.epi_mode & 4)) {  // bit 2: timing experiment only (DUCOSY_DEBUG_SKIP_STORE)
+      if (et == 0) {
 #pragma unroll
         for (int sb = 0; sb < C::kSlabs; ++sb) {
           const int n = tc.nb * kN + sb * 64;
@@ -434,8 +434,6 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.partials = p.partials;
   a.bias = p.bias;
   a.epi_mode = p.epi_mode;
-  static const bool skip_store = getenv("DUCOSY_DEBUG_SKIP_STORE") != nullptr;
-  if (skip_store) a.epi_mode |= 4;
 
   // CTA pairs whenever the m-tiles of one (sample, phase) pair up; DUCOSY_CONV_CTA_GROUP=1 forces single CTAs.
   static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();

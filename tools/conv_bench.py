@@ -1,5 +1,5 @@
 """Micro-benchmark of the residual-block convolution (3x3, 256->256, 128x128) through the C ABI.
-usage: python tools/conv_bench.py [B] ; env DUCOSY_CONV_CTA_GROUP=1|2, DUCOSY_DEBUG_SKIP_STORE=1"""
+usage: python tools/conv_bench.py [B] ; env DUCOSY_CONV_CTA_GROUP=1|2"""
 import os, sys, json
 import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -27,4 +27,4 @@ if __name__ == "__main__":
         for stats in (True, False):
             us, tf = run(B, stats)
             print(json.dumps({"B": B, "stats": stats, "cg": os.environ.get("DUCOSY_CONV_CTA_GROUP", "2"),
-                              "skip_store": "DUCOSY_DEBUG_SKIP_STORE" in os.environ, "us": round(us, 1), "tflops": round(tf, 1)}), flush=True)
+                              "us": round(us, 1), "tflops": round(tf, 1)}), flush=True)
