@@ -7,6 +7,10 @@ Workload (BASELINE.json configs[1]): soft-tissue + lung A2B generators (input_ch
 blocks, seeded random weights) + de-window + complementary composite over a synthetic 300-slice 512x512
 NCCT volume.  One step = one pass over the volume.  With N ranks every rank synthesizes its own 300-slice
 volume (independent slices, no data-path collective) => weak scaling; value = all slices / max-over-ranks time.
+The same line also carries configs[1] exactly as written -- ONE 300-slice volume sharded over the N ranks (`strong`) --
+output checks computed outside the timed regions (`checks`), the CycleGAN train metric at a fixed global batch of 8
+(`train`) and at 8 samples per GPU (`train_weak`), and at N = 1 the CPU oracle (`cpu_baseline`) and the same networks
+under PyTorch eager / cuDNN TF32 on the same GPU (`gpu_eager_baseline`).
 
 One JSON line on stdout (rank 0).  See DESIGN.md "Measurement" for every field.
 """
@@ -156,21 +160,32 @@ def run_reference(args, rank):
     })
 
 
-def train_metric(device, rank, world, steps, warmup=2):
-    """Second half of BASELINE.json's metric: CycleGAN train steps/s (config 4: batch 8, 512x512, soft-tissue generators
-    with two mask channels, all losses, three Adam steps).  The global batch of 8 is sharded over the ranks with a NCCL
-    gradient all-reduce (strong scaling).  Every step copies its batch from pinned host memory and reads the loss back."""
-    import torch.distributed as dist
-    from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, GraphedCycleGANStep, shard_batch
-    B, cin = 8, 3
-    if world > B:
-        return None
-    lo, hi = shard_batch(B, rank, world)
-    g = torch.Generator().manual_seed(2)
+def _train_batch(B, cin, lo, hi, seed=2):
+    g = torch.Generator().manual_seed(seed)
     host = [(torch.rand(B, 1, H, W, generator=g) * 2 - 1)[lo:hi].contiguous().pin_memory() for _ in range(2)]
     host.append((torch.rand(B, cin - 1, H, W, generator=g) < 0.1).float()[lo:hi].contiguous().pin_memory())
+    return host
+
+
+def train_metric(device, rank, world, steps, warmup=2, per_gpu_batch=None):
+    """Second half of BASELINE.json's metric: CycleGAN train steps/s (config 4: batch 8, 512x512, soft-tissue generators
+    with two mask channels, all losses, three Adam steps).  Default: the global batch of 8 is sharded over the ranks with a
+    NCCL gradient all-reduce (strong scaling); ``per_gpu_batch=8`` keeps 8 samples on every GPU instead (weak scaling,
+    global batch 8 x N).  Every step copies its batch from pinned host memory and reads the loss back."""
+    import torch.distributed as dist
+    from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, GraphedCycleGANStep, shard_batch
+    cin = 3
+    if per_gpu_batch is None:
+        B = 8
+        if world > B:
+            return None
+        lo, hi = shard_batch(B, rank, world)
+    else:
+        B = per_gpu_batch * world
+        lo, hi = per_gpu_batch * rank, per_gpu_batch * (rank + 1)
+    host = _train_batch(B, cin, lo, hi)
     step = DataParallelCycleGANStep(cin, 9, True, seed=1234, device=device, capturable=True)
-    # the whole step (~3000 launches, 3 all-reduces) is captured once in a CUDA graph; the warm-up steps are the capture's
+    # the whole step (~3000 launches, the all-reduces) is captured once in a CUDA graph; the warm-up steps are the capture's
     graphed = GraphedCycleGANStep(step, *(t.to(device) for t in host), warmup=max(warmup, 2))
 
     def one():
@@ -190,15 +205,117 @@ def train_metric(device, rank, world, steps, warmup=2):
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms = float(ms.item())
+    skipped = step.optimizer_G.skipped_steps()
     graphed.close()      # the graph holds captured NCCL collectives: it must be gone before the process group is torn down
     tflop = (6 * B * 451.11 * 3 + 6 * B * 13.04 * 3) / 1e3      # nominal conv work, backward = 2x forward
     return {"metric": "cyclegan_train_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
-            "warmup": max(warmup, 2) + 1, "global_batch": B, "scaling": "strong", "loss_G": loss, "cuda_graph": True,
+            "samples_per_s": B * 1e3 / ms, "warmup": max(warmup, 2) + 1, "global_batch": B,
+            "scaling": "strong" if per_gpu_batch is None else "weak", "loss_G": loss, "cuda_graph": True,
+            "skipped_optimizer_steps": skipped,
             "config": "G_A2B/G_B2A (Cin 3, 9 CBAM blocks) + D_A/D_B, 512x512, all 9 loss terms, 3 fused Adam steps; "
-                      f"batch 8 sharded x{world}" + (", NCCL gradient all-reduce" if world > 1 else ""),
+                      + (f"batch 8 sharded x{world}" if per_gpu_batch is None else f"{per_gpu_batch} samples per GPU x{world}")
+                      + (", NCCL gradient all-reduce" if world > 1 else ""),
             "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": 4,
             "nominal_tflop_per_step": tflop, "achieved_tflops_nominal": tflop / ms * 1e3 / world,
             "frac_of_sustained_peak_per_gpu": tflop / ms * 1e3 / world / peaks()["tf_sustained"]}
+
+
+def train_checks(device, rank, world):
+    """Correctness of the data-parallel step, outside any timed region: generator gradients after the all-reduce and the
+    logged losses of the sharded step (global batch 8 over the N ranks) against ONE process stepping the whole batch with
+    the same kernels (rank 0 computes that reference).  Relative L2 of the flat gradient; |loss_G| difference."""
+    import torch.distributed as dist
+    from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, logged_losses, shard_batch
+    from ducosy_gan_b200.trainer import CycleGANStep
+    B, cin = 8, 3
+    if world < 2 or world > B:
+        return None
+    full = [t.to(device) for t in _train_batch(B, cin, 0, B, seed=5)]
+    lo, hi = shard_batch(B, rank, world)
+    dp = DataParallelCycleGANStep(cin, 9, True, seed=77, device=device)
+    dp.bucket_G.zero()
+    loss_G, terms, fake_A, fake_B = dp.generator_losses(*(t[lo:hi].contiguous() for t in full))
+    loss_G.backward()
+    dp.bucket_G.all_reduce_mean()
+    zero = torch.zeros((), device=device)
+    logged = logged_losses(terms, zero, zero, dp.lambda_cyc, dp.lambda_id)
+    res = None
+    if rank == 0:
+        single = CycleGANStep(cin, 9, True, seed=77, device=device)
+        l1, t1, _, _ = single.generator_losses(*full)
+        l1.backward()
+        ref = torch.cat([torch.nn.functional.pad(p.grad.reshape(-1), (0, -p.numel() % 4))
+                         for p in list(single.G_A2B.parameters()) + list(single.G_B2A.parameters())])
+        got = dp.bucket_G.flat
+        res = {"dp_grad_rel_l2_vs_single_process": ((got - ref).norm() / ref.norm()).item(),
+               "dp_logged_loss_G": float(logged["G"]), "single_process_loss_G": float(l1),
+               "dp_logged_terms_max_rel_diff": max(abs(float(logged[k]) - float(t1[k])) / (abs(float(t1[k])) + 1e-12) for k in t1),
+               "global_batch": B}
+        del single
+    del dp
+    torch.cuda.empty_cache()
+    dist.barrier(device_ids=[device.index])
+    return res
+
+
+def gpu_eager_baseline(device, batch_sizes=(30, 1)):
+    """The real bar: the same two networks + composite under PyTorch eager on the SAME B200 -- cuDNN
+    convolutions with TF32 (torch's defaults, what the reference's modules/model.py runs on a GPU), fp32 activations, one
+    ATen launch per op -- through the oracle's functional restatement of modules/model.py:92-115.  Test infrastructure like
+    ``cpu_baseline``: nothing of the product runs here."""
+    import torch.nn.functional as F
+    from oracle import ducosy_oracle as orc
+    torch.backends.cudnn.allow_tf32 = True          # torch default (SURVEY section 10)
+    out = {"unit": UNIT, "tf32_convs": True, "kind": "oracle functional restatement, torch eager + cuDNN"}
+    sd_s = {k: v.to(device) for k, v in orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1234).items()}
+    sd_l = {k: v.to(device) for k, v in orc.make_state_dict(orc.generator_param_shapes(1, 9, True), 1235).items()}
+    px = torch.from_numpy(synthetic_volume(0)[: max(batch_sizes)]).to(device)
+
+    def inorm(x):                                   # what nn.InstanceNorm2d calls
+        return F.instance_norm(x, eps=1e-5)
+
+    def run(b, channels_last):
+        fmt = torch.channels_last if channels_last else torch.contiguous_format
+        cvt = lambda sd: {k: (v.contiguous(memory_format=fmt) if v.dim() == 4 else v) for k, v in sd.items()}
+        ws, wl = cvt(sd_s), cvt(sd_l)
+        old = orc.instance_norm
+        orc.instance_norm = inorm
+        try:
+            def step():
+                hu = px[:b].float() * SLOPE + INTERCEPT
+                win = lambda lo, hi: ((hu.clamp(lo, hi) - lo) / (hi - lo) * 2 - 1)[:, None].contiguous(memory_format=fmt)
+                ys = orc.generator_forward(ws, win(-150.0, 250.0))
+                yl = orc.generator_forward(wl, win(-1000.0, -150.0))
+                sp = (((ys[:, 0] + 1) / 2 * 400.0 - 150.0 - INTERCEPT) / SLOPE).to(torch.int16)
+                lp = (((yl[:, 0] + 1) / 2 * 850.0 - 1000.0 - INTERCEPT) / SLOPE).to(torch.int16)
+                merged = torch.where((hu >= -1000) & (hu <= -150), lp, torch.where((hu >= -150) & (hu <= 250), sp, px[:b]))
+                return merged
+            with torch.no_grad():
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                iters = 3 if b > 1 else 20
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(iters):
+                    step()
+                e1.record()
+                torch.cuda.synchronize()
+            return b * iters / (e0.elapsed_time(e1) / 1e3)
+        finally:
+            orc.instance_norm = old
+
+    for b in batch_sizes:
+        for cl in (False, True):
+            key = f"batch{b}_{'channels_last' if cl else 'nchw'}"
+            try:
+                out[key] = run(b, cl)
+            except Exception as exc:                  # e.g. out of memory at batch 30 fp32: report, do not fail the bench
+                out[key] = f"{type(exc).__name__}: {exc}"[:160]
+            torch.cuda.empty_cache()
+    vals = [v for v in out.values() if isinstance(v, float)]
+    out["value"] = max(vals) if vals else None
+    return out
 
 
 def cpu_train_baseline():
@@ -240,6 +357,22 @@ def _emit(line: dict):
     print(json.dumps(line), flush=True)
 
 
+def oracle_spot_check(soft, lung, vol_slice, merged_slice):
+    """rank 0, outside the timed region: one slice of the product's output against the CPU oracle run on the SAME weights."""
+    from oracle import ducosy_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu_sd = lambda m: {k: v.detach().cpu() for k, v in m.state_dict().items()}
+    ref = orc.dual_hu_synthesize(vol_slice[None], SLOPE, INTERCEPT, cpu_sd(soft), cpu_sd(lung))[0]
+    hu = orc.stored_to_hu(vol_slice, SLOPE, INTERCEPT)
+    lung_m = (hu >= -1000) & (hu <= -150)
+    soft_m = (hu >= -150) & (hu <= 250) & ~lung_m
+    outside = ~(lung_m | soft_m)
+    d = np.abs(merged_slice.astype(np.int32) - ref.astype(np.int32))
+    return {"slice": 0, "outside_both_ranges_bit_exact": bool(np.array_equal(merged_slice[outside], vol_slice[outside])),
+            "max_abs_diff_soft_hu": int(d[soft_m].max()), "max_abs_diff_lung_hu": int(d[lung_m].max()),
+            "mean_abs_diff_hu": float(d[~outside].mean()), "stated_bound_hu": {"soft": 4, "lung": 8}}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -248,7 +381,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--batch-slices", type=int, default=int(os.environ.get("DUCOSY_BATCH_SLICES", "30")))
     ap.add_argument("--skip-cpu-baseline", action="store_true")
-    ap.add_argument("--train-steps", type=int, default=3, help="timed CycleGAN steps for the 'train' object (0 = skip)")
+    ap.add_argument("--skip-checks", action="store_true")
+    ap.add_argument("--train-steps", type=int, default=20, help="timed CycleGAN steps for the 'train' objects (0 = skip)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     _quiet_stdout()
@@ -268,7 +402,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=device)
 
-    from ducosy_gan_b200.synthesis import DualHUSynthesizer
+    from ducosy_gan_b200.synthesis import DualHUSynthesizer, chunk_size, shard_range
     soft, lung = make_models(device)
     synth = DualHUSynthesizer(soft, lung, batch_slices=args.batch_slices, device=device)
     host_vol = torch.from_numpy(synthetic_volume(rank)).pin_memory()
@@ -307,17 +441,87 @@ def main():
     e2e_step()
     sec_e2e = timed(e2e_step, args.steps)
 
+    # ---- output checks, outside the timed regions: a number without a checked output proves speed only
+    checks = None
+    if not args.skip_checks:
+        sums = torch.stack([dev_out.to(torch.int64).sum(), host_out.to(device).to(torch.int64).sum()])
+        dev_step()
+        torch.cuda.synchronize()
+        sums = torch.cat([sums, dev_out.to(torch.int64).sum()[None]])
+        all_sums = [torch.zeros_like(sums) for _ in range(world)]
+        if world > 1:
+            dist.all_gather(all_sums, sums)
+        else:
+            all_sums = [sums]
+        if rank == 0:
+            checks = {"per_rank_output_checksum": [int(t[0]) for t in all_sums],
+                      "e2e_output_equals_device_output": all(int(t[0]) == int(t[1]) for t in all_sums),
+                      "repeat_run_identical": all(int(t[0]) == int(t[2]) for t in all_sums)}
+            try:
+                checks["oracle_spot_check"] = oracle_spot_check(soft, lung, host_vol[0].numpy(), dev_out[0].cpu().numpy())
+            except Exception as exc:
+                checks["oracle_spot_check"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+
+    # ---- BASELINE configs[1] as written: ONE 300-slice volume (seed 0 = rank 0's) sharded over the N ranks, strong scaling
+    strong = None
+    if world > 1:
+        lo, hi = shard_range(S, rank, world)
+        common = dev_vol if rank == 0 else torch.from_numpy(synthetic_volume(0)).to(device)
+        shard = common[lo:hi].contiguous()
+        full_ref = dev_out.clone() if rank == 0 else None        # rank 0's single-GPU result for the same volume
+        shard_out = torch.empty_like(shard)
+        shard_step = lambda: synth.synthesize_device(shard, SLOPE, INTERCEPT, out=shard_out)
+        for _ in range(2):
+            shard_step()
+        sec_strong = timed(shard_step, args.steps)
+        n_max = -(-S // world)
+        padded = torch.zeros((n_max, H, W), dtype=torch.int16, device=device)
+        padded[: hi - lo] = shard_out
+        gathered = torch.empty((world * n_max, H, W), dtype=torch.int16, device=device)
+        dist.all_gather_into_tensor(gathered, padded)
+        # single-GPU time of the same volume, measured in this run on rank 0 while the others idle
+        for_n1 = 0.0
+        if rank == 0:
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(args.steps):
+                synth.synthesize_device(common, SLOPE, INTERCEPT, out=dev_out)
+            e1.record()
+            torch.cuda.synchronize()
+            for_n1 = e0.elapsed_time(e1) / 1e3
+        barrier()
+        if rank == 0:
+            parts = [gathered[r * n_max: r * n_max + (shard_range(S, r, world)[1] - shard_range(S, r, world)[0])] for r in range(world)]
+            whole = torch.cat(parts)
+            v_strong, v_n1 = S * args.steps / sec_strong, S * args.steps / for_n1
+            strong = {"workload": f"ONE {S}-slice volume sharded by contiguous slice ranges over {world} GPUs "
+                                  f"({S // world}-{n_max} slices per rank, chunk {chunk_size(n_max, args.batch_slices)})",
+                      "value": v_strong, "unit": UNIT, "ms_per_volume": sec_strong / args.steps * 1e3,
+                      "single_gpu_value_same_run": v_n1, "efficiency_vs_n1": v_strong / (world * v_n1),
+                      "sharded_output_equals_single_gpu_output": bool(torch.equal(whole, full_ref))}
+        del common, shard, shard_out, padded, gathered
+
     chunks = (S + args.batch_slices - 1) // args.batch_slices
     launches = synth.launches_per_chunk() * chunks * args.steps
-    train = None
+    train = train_weak = tchecks = None
     if args.train_steps > 0:
         del dev_out, dev_vol
         synth = None
         torch.cuda.empty_cache()
-        try:
-            train = train_metric(device, rank, world, args.train_steps)
-        except Exception as exc:          # the synthesis line above is the contract; a failing extra must not take it down
-            train = {"metric": "cyclegan_train_steps_per_s", "error": f"{type(exc).__name__}: {exc}"[:300]}
+        def guarded(fn):
+            try:                           # the synthesis line above is the contract; a failing extra must not take it down
+                return fn()
+            except Exception as exc:
+                return {"metric": "cyclegan_train_steps_per_s", "error": f"{type(exc).__name__}: {exc}"[:300]}
+
+        train = guarded(lambda: train_metric(device, rank, world, args.train_steps))
+        if world > 1:
+            torch.cuda.empty_cache()
+            train_weak = guarded(lambda: train_metric(device, rank, world, max(args.train_steps // 2, 3), per_gpu_batch=8))
+            torch.cuda.empty_cache()
+            if not args.skip_checks:
+                tchecks = guarded(lambda: train_checks(device, rank, world))
 
     value = world * S * args.steps / sec
     e2e_value = world * S * args.steps / sec_e2e
@@ -325,6 +529,8 @@ def main():
         pk = peaks()
         ksec, kflops = time_dominant_kernel(device, args.batch_slices)
         achieved = kflops / ksec / 1e12
+        # executed tensor work per slice: the x2-upsampling convs run as sub-pixel phases, 4/9 of their nominal MACs
+        gflop_exec = GFLOP_PER_SLICE - 2 * (2 * 38.65) * (5.0 / 9.0)
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": sec / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -343,10 +549,24 @@ def main():
                          "traffic_note": "bytes per launch, dram__bytes_read.sum + dram__bytes_write.sum of one ncu --set full capture at "
                                          "batch 30 (profiles/r01_final_conv256_kernel.txt); algorithmic 5.13e8",
                          "peak_source": pk["source"] + ", burst figure (kernel timed alone)",
-                         "path_frac_of_sustained": value / world * GFLOP_PER_SLICE / 1e3 / pk["tf_sustained"]},
+                         "path_frac_of_sustained": value / world * GFLOP_PER_SLICE / 1e3 / pk["tf_sustained"],
+                         "path_frac_of_sustained_executed": value / world * gflop_exec / 1e3 / pk["tf_sustained"],
+                         "path_frac_note": "nominal = SURVEY 8(d) conv FLOPs (up-convs at 9/9); executed = what the kernels issue "
+                                           "(sub-pixel up-convs at 4/9 of their MACs)"},
         }
+        if checks is not None:
+            line["checks"] = checks
+        if strong is not None:
+            line["strong"] = strong
+        elif world == 1:
+            line["strong"] = {"value": value, "unit": UNIT, "efficiency_vs_n1": 1.0,
+                              "workload": "identical to the headline at N = 1 (one 300-slice volume on one GPU)"}
         if train is not None:
             line["train"] = train
+        if train_weak is not None:
+            line["train_weak"] = train_weak
+        if tchecks is not None:
+            line.setdefault("checks", {})["train"] = tchecks
         if world == 1 and not args.skip_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_sample()
             if train is not None and "error" not in train:
@@ -354,6 +574,12 @@ def main():
                     train["cpu_baseline"] = cpu_train_baseline()
                 except Exception as exc:
                     train["cpu_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
+            try:
+                line["gpu_eager_baseline"] = gpu_eager_baseline(device)
+                if line["gpu_eager_baseline"].get("value"):
+                    line["gpu_eager_baseline"]["speedup_of_this_path"] = value / line["gpu_eager_baseline"]["value"]
+            except Exception as exc:
+                line["gpu_eager_baseline"] = {"error": f"{type(exc).__name__}: {exc}"[:200]}
         _emit(line)
     if world > 1:
         os.dup2(2, 1)      # NCCL teardown chatter, if any, after the result line

@@ -35,11 +35,18 @@ int num_sms();
 // (nn.DataParallel replicas on Python threads) must set them once per device, not once per process.
 struct PerDeviceOnce {
   std::atomic<unsigned long long> mask{0};
-  bool first() {
+  // Runs f() (a cudaFuncSetAttribute call) unless it already SUCCEEDED on the current device.  The bit is published only
+  // after f() returned, so a second host thread on the same device either sees the finished configuration or repeats
+  // the (idempotent) call itself -- it can never launch with the attribute still unset.
+  template <class F>
+  cudaError_t once(F&& f) {
     int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return true;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return f();
     const unsigned long long bit = 1ull << dev;
-    return (mask.fetch_or(bit) & bit) == 0;
+    if (mask.load(std::memory_order_acquire) & bit) return cudaSuccess;
+    const cudaError_t e = f();
+    if (e == cudaSuccess) mask.fetch_or(bit, std::memory_order_release);
+    return e;
   }
 };
 

@@ -339,8 +339,8 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
   using C = Cfg<kN, kCG>;
   static PerDeviceOnce configured;
   auto kern = conv_gemm_kernel<kN, T, kCG>;
-  if (configured.first()) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes));
+  {
+    const cudaError_t e = configured.once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)); });
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
   }
   if (kCG == 2) {

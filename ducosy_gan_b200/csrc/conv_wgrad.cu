@@ -301,7 +301,7 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
 #define DUCOSY_WGRAD_LAUNCH(T, MP)                                                                              \
   do {                                                                                                          \
     static PerDeviceOnce cfg;                                                                                   \
-    if (cfg.first()) cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); \
+    cfg.once([&] { return cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); }); \
     conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
   } while (0)
   if (dtype == DUCOSY_F16) {

@@ -261,8 +261,8 @@ int launch_stem_pass(const void* xw, const void* wp, float* partials, const floa
                       size_t(7) * (W + 16) * 2 + 16;
   auto kern = stem_fused_kernel<T, kApply>;
   static PerDeviceOnce configured;
-  if (configured.first()) {
-    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024);
+  {
+    const cudaError_t e = configured.once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024); });
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(stem_fused): %s", cudaGetErrorString(e));
   }
   DUCOSY_CHECK(smem <= 112 * 1024, DUCOSY_ERR_SHAPE, "stem_fused: image too wide (W = %d)", W);

@@ -24,21 +24,20 @@ class GradBucket:
 
     def __init__(self, params):
         self.params = [p for p in params if p.requires_grad]
-        total = sum(p.numel() for p in self.params)
+        self.offsets, total = [], 0
+        for p in self.params:                       # every view starts 16-byte aligned (vectorised Adam / reductions)
+            self.offsets.append(total)
+            total += (p.numel() + 3) // 4 * 4
         dev = self.params[0].device
         self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
-        off = 0
-        for p in self.params:
+        for p, off in zip(self.params, self.offsets):
             p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def zero(self):
         self.flat.zero_()
-        off = 0
-        for p in self.params:            # re-attach views an optimizer.zero_grad(set_to_none=True) may have dropped
+        for p, off in zip(self.params, self.offsets):   # re-attach views an optimizer.zero_grad(set_to_none=True) may have dropped
             if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + off * 4:
                 p.grad = self.flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
 
     def all_reduce_mean(self, group=None, async_op=False):
         if not dist.is_initialized():
@@ -79,6 +78,50 @@ def all_gather_batch(x, group=None):
     return _AllGatherBatch.apply(x, group)
 
 
+TERM_KEYS = ("GAN", "cycle", "id", "grad_cycle", "grad_id", "ssim", "contrast_attention", "contrast_region", "contrast_edge")
+
+
+def loss_weights(lambda_cyc=10.0, lambda_id=5.0):
+    """The loss mix of reference modules/trainer.py:493-512 (argmanager.py:97-98)."""
+    return dict(GAN=1.0, cycle=lambda_cyc, id=lambda_id, grad_cycle=5.0, grad_id=2.5, ssim=2.0, contrast_attention=2.0,
+                contrast_region=1.5, contrast_edge=1.0)
+
+
+def logged_losses(terms, loss_D_A, loss_D_B, lambda_cyc=10.0, lambda_id=5.0, group=None):
+    """What reference modules/trainer.py:527-531 logs, for the GLOBAL batch, from each rank's shard.
+
+    The seven per-sample terms and the two discriminator losses are means over the samples of the rank, and the shards are
+    equal, so their mean over ranks is the mean over the whole batch; the two batch-global terms (region, edge) were
+    evaluated on the gathered batch and are identical on every rank, so the same mean leaves them alone.  ``G`` is then the
+    reference's mix of those values -- each term counted once.  (The ``world``-weighted expression that
+    ``generator_losses`` differentiates is a backward surrogate for the mean-all-reduce of the gradients, not a loss
+    anybody should read.)  One small all-reduce of 11 floats; detached, graph-capturable."""
+    vec = torch.stack([terms[k].detach().to(torch.float32).reshape(()) for k in TERM_KEYS]
+                      + [loss_D_A.detach().to(torch.float32).reshape(()), loss_D_B.detach().to(torch.float32).reshape(())])
+    if dist.is_initialized() and dist.get_world_size(group) > 1:
+        if dist.get_backend(group) == "nccl":
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG, group=group)
+        else:
+            dist.all_reduce(vec, op=dist.ReduceOp.SUM, group=group)
+            vec = vec / dist.get_world_size(group)
+    out = {k: vec[i] for i, k in enumerate(TERM_KEYS)}
+    w = loss_weights(lambda_cyc, lambda_id)
+    out["G"] = sum(w[k] * out[k] for k in TERM_KEYS)
+    out["D_A"], out["D_B"] = vec[len(TERM_KEYS)], vec[len(TERM_KEYS) + 1]
+    return out
+
+
+def check_equal_shards(local_batch, group=None):
+    """The mean-all-reduce of gradients and losses is the global-batch mean only for equal shards (and
+    ``all_gather_into_tensor`` needs them too): refuse anything else instead of silently weighting samples unevenly."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return
+    sizes = [None] * dist.get_world_size(group)
+    dist.all_gather_object(sizes, int(local_batch), group=group)
+    if len(set(sizes)) != 1:
+        raise ValueError(f"data-parallel step needs equal shards on every rank, got per-rank batch sizes {sizes}")
+
+
 def shard_batch(n, rank, world):
     """Contiguous sample range of this rank: [n*rank//world, n*(rank+1)//world)."""
     return n * rank // world, n * (rank + 1) // world
@@ -97,6 +140,7 @@ class DataParallelCycleGANStep(CycleGANStep):
         self.bucket_G = GradBucket(list(self.G_A2B.parameters()) + list(self.G_B2A.parameters()))
         self.bucket_D_A = GradBucket(list(self.D_A.parameters()))
         self.bucket_D_B = GradBucket(list(self.D_B.parameters()))
+        self._checked_batch = None
 
     def generator_losses(self, real_A, real_B, masks=None):
         if self.world == 1:
@@ -117,7 +161,9 @@ class DataParallelCycleGANStep(CycleGANStep):
         fake_B_all, real_B_all, real_A_all = all_gather_batch(fake_B, g), all_gather_batch(real_B, g), all_gather_batch(real_A, g)
         loss_region = self.criterion_contrast_region(fake_B_all, real_B_all, real_A_all)
         loss_edge = self.criterion_contrast_edge(fake_B_all, real_B_all, real_A_all)
-        w = float(self.world)   # see the module docstring: full-batch terms x world, then mean-all-reduce
+        # BACKWARD SURROGATE, not the logged loss: full-batch terms x world, then mean-all-reduce of the gradients gives
+        # exactly the single-process gradient (module docstring).  step() reports logged_losses() instead.
+        w = float(self.world)
         loss_G = (loss_GAN + self.lambda_cyc * loss_cycle + self.lambda_id * loss_id + 5.0 * loss_grad_cycle + 2.5 * loss_grad_id
                   + 2.0 * loss_ssim + 2.0 * loss_att + w * (1.5 * loss_region + 1.0 * loss_edge))
         terms = dict(GAN=loss_GAN, cycle=loss_cycle, id=loss_id, grad_cycle=loss_grad_cycle, grad_id=loss_grad_id, ssim=loss_ssim,
@@ -125,7 +171,11 @@ class DataParallelCycleGANStep(CycleGANStep):
         return loss_G, terms, fake_A, fake_B
 
     def step(self, real_A, real_B, masks=None):
-        """real_A / real_B / masks are this rank's shard of the batch."""
+        """real_A / real_B / masks are this rank's shard of the batch (equal shards on every rank).  Returns the losses the
+        reference logs (trainer.py:527-531) for the global batch -- identical on every rank, see ``logged_losses``."""
+        if self.world > 1 and self._checked_batch != real_A.shape[0] and not torch.cuda.is_current_stream_capturing():
+            check_equal_shards(real_A.shape[0], self.group)
+            self._checked_batch = real_A.shape[0]
         self.bucket_G.zero()
         loss_G, terms, fake_A, fake_B = self.generator_losses(real_A, real_B, masks)
         loss_G.backward()
@@ -143,9 +193,11 @@ class DataParallelCycleGANStep(CycleGANStep):
         loss_D_B.backward()
         self.bucket_D_B.all_reduce_mean(self.group)
         self.optimizer_D_B.step()
-        out = {k: v.detach() for k, v in terms.items()}
-        out.update(G=loss_G.detach(), D_A=loss_D_A.detach(), D_B=loss_D_B.detach())
-        return out
+        if self.world == 1:
+            out = {k: v.detach() for k, v in terms.items()}
+            out.update(G=loss_G.detach(), D_A=loss_D_A.detach(), D_B=loss_D_B.detach())
+            return out
+        return logged_losses(terms, loss_D_A, loss_D_B, self.lambda_cyc, self.lambda_id, self.group)
 
 
 class GraphedCycleGANStep:

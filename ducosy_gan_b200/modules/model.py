@@ -16,10 +16,6 @@ import torch.nn as nn
 
 from .. import _lib
 
-_NO_TRAIN_MSG = ("ducosy_gan_b200: the autograd (training) path of {} is not built yet -- this round ships the "
-                 "inference forward only; call it under torch.no_grad(). There is deliberately no PyTorch fallback.")
-
-
 def _ordered_params(module):
     """Parameters in ``named_parameters()`` order.  A replica made by ``nn.DataParallel`` (reference modules/trainer.py:335-338)
     has no parameters of its own -- ``replicate`` stores the broadcast copies in ``_former_parameters`` of every sub-module, in
@@ -37,6 +33,34 @@ def default_operand_dtype() -> int:
     """16-bit operand type of the tensor-core convolutions: fp16 (default; TF32-class 10-bit mantissa, the
     reference's own GPU precision) or bf16 via DUCOSY_PRECISION=bf16."""
     return _lib.dtype_code(os.environ.get("DUCOSY_PRECISION", "fp16").lower())
+
+
+class _DerivedState:
+    """Mixin of Generator / Discriminator.  The per-device engines (packed 16-bit weights, workspaces, captured graphs) are
+    derived state: never part of ``state_dict``, dropped by pickle / ``copy.deepcopy`` / ``torch.save(module)`` and rebuilt
+    lazily.  The packed-weight caches are keyed by ``(data_ptr, _version)`` of every parameter, which sees
+    ``load_state_dict``, optimiser steps, ``.to()`` and any in-place op on the parameter itself; writes through ``p.data``
+    do not bump ``_version``, so the two module-level entry points that commonly do that (``.apply(fn)`` and ``._apply``)
+    invalidate explicitly, and ``invalidate_packed_weights()`` is public for code that edits ``p.data`` by hand."""
+
+    def invalidate_packed_weights(self):
+        for eng in self._engines.values():
+            eng.invalidate()
+
+    def apply(self, fn):
+        out = super().apply(fn)
+        self.invalidate_packed_weights()
+        return out
+
+    def _apply(self, fn, *args, **kwargs):
+        out = super()._apply(fn, *args, **kwargs)
+        self._engines = {}
+        return out
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state["_engines"] = {}
+        return state
 
 
 class ChannelAttention(nn.Module):
@@ -106,7 +130,7 @@ class ResidualBlockWithCBAM(nn.Module):
         raise NotImplementedError("ResidualBlockWithCBAM runs fused inside Generator.forward")
 
 
-class Generator(nn.Module):
+class Generator(_DerivedState, nn.Module):
     """reference modules/model.py:90-115.  ``forward(x[B,Cin,H,W] fp32 cuda) -> [B,1,H,W] fp32``.
 
     H must be a multiple of 32 and W of 128 with W/4 in {32, 64, 128k} (512x512 is what generate.py and
@@ -203,16 +227,19 @@ class _GeneratorEngine:
     def __init__(self, cfg_tuple, dtype_code, device):
         self.device = device
         self.cfg = _lib.GenConfig(cfg_tuple[0], cfg_tuple[1], int(cfg_tuple[2]), dtype_code)
-        self.lib = _lib.load()
-        self.num_params = self.lib.ducosy_generator_num_params(C.byref(self.cfg))
+        lib = _lib.load()
+        self.num_params = lib.ducosy_generator_num_params(C.byref(self.cfg))
         with torch.cuda.device(device):
-            self.packed = torch.empty(self.lib.ducosy_generator_packed_bytes(C.byref(self.cfg)) + 256,
+            self.packed = torch.empty(lib.ducosy_generator_packed_bytes(C.byref(self.cfg)) + 256,
                                       dtype=torch.uint8, device=device)
         self._versions = None
         self._ws = {}
 
     def _packed_ptr(self):
         return (self.packed.data_ptr() + 255) // 256 * 256
+
+    def invalidate(self):
+        self._versions = None
 
     def sync_weights(self, params):
         """Re-pack when any fp32 master parameter changed (load_state_dict, optimizer step, .to())."""
@@ -235,16 +262,18 @@ class _GeneratorEngine:
         self._versions = sig
 
     def workspace(self, B, H, W):
-        key = (B, H, W)
-        ws = self._ws.get(key)
-        if ws is None:
-            need = self.lib.ducosy_generator_workspace_bytes(C.byref(self.cfg), B, H, W)
-            if need == 0:
-                raise _lib.DucosyError(f"unsupported generator input shape B={B} H={H} W={W}: "
-                                       "H must be a multiple of 32, W of 128, W/4 in {32,64,128k}")
-            self._ws.clear()  # one live workspace per engine
+        """One live workspace per engine.  A request that fits the live one (a ragged tail of a volume, a smaller batch)
+        reuses it: the library lays its buffers out from the sizes of the call, so any large-enough block will do."""
+        need = _lib.load().ducosy_generator_workspace_bytes(C.byref(self.cfg), B, H, W)
+        if need == 0:
+            raise _lib.DucosyError(f"unsupported generator input shape B={B} H={H} W={W}: "
+                                   "B >= 1, H a multiple of 32, W of 128, W/4 in {32,64,128k}")
+        ws = self._ws.get("ws")
+        if ws is None or ws.numel() - 1024 < need:
+            self._ws.clear()
+            ws = None
             ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
-            self._ws[key] = ws
+            self._ws["ws"] = ws
         return ws, (ws.data_ptr() + 1023) // 1024 * 1024, ws.numel() - 1024
 
     def forward(self, x):
@@ -273,7 +302,7 @@ class _GeneratorEngine:
         return out
 
 
-class Discriminator(nn.Module):
+class Discriminator(_DerivedState, nn.Module):
     """reference modules/model.py:118-131 (PatchGAN).  ``forward(img[B,1,H,W] fp32 cuda) -> [B,1,H/16,W/16] fp32``;
     H and W multiples of 256.  Differentiable w.r.t. its parameters and the input image: under autograd the forward and
     the backward both run in libducosy_sm100.so (BASELINE config 3: forward/backward with the MSE adversarial loss of
@@ -332,13 +361,16 @@ class _DiscriminatorEngine:
     """Per-device packed weights + workspace of a Discriminator."""
 
     def __init__(self, dtype_code, device):
-        self.device, self.dtype_code, self.lib = device, dtype_code, _lib.load()
+        self.device, self.dtype_code = device, dtype_code
         with torch.cuda.device(device):
-            self.packed = torch.empty(self.lib.ducosy_discriminator_packed_bytes() + 256, dtype=torch.uint8, device=device)
+            self.packed = torch.empty(_lib.load().ducosy_discriminator_packed_bytes() + 256, dtype=torch.uint8, device=device)
         self._versions, self._ws = None, {}
 
     def _packed_ptr(self):
         return (self.packed.data_ptr() + 255) // 256 * 256
+
+    def invalidate(self):
+        self._versions = None
 
     def sync_weights(self, params):
         sig = tuple((p.data_ptr(), p._version) for p in params)
@@ -363,7 +395,7 @@ class _DiscriminatorEngine:
         with torch.cuda.device(self.device):
             ws = None if keep_workspace else self._ws.get((B, H, W))
             if ws is None:
-                need = self.lib.ducosy_discriminator_workspace_bytes(B, H, W)
+                need = _lib.load().ducosy_discriminator_workspace_bytes(B, H, W)
                 if need == 0:
                     raise _lib.DucosyError(f"unsupported discriminator input shape {tuple(img.shape)}: H, W multiples of 256")
                 ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
@@ -379,7 +411,7 @@ class _DiscriminatorEngine:
         B, _, H, W = img.shape
         dout = dout.detach().to(dtype=torch.float32).contiguous()
         with torch.cuda.device(self.device):
-            need = self.lib.ducosy_discriminator_backward_workspace_bytes(B, H, W)
+            need = _lib.load().ducosy_discriminator_backward_workspace_bytes(B, H, W)
             bws = self._bws.get((B, H, W)) if hasattr(self, "_bws") else None
             if bws is None:
                 self._bws = {(B, H, W): torch.empty(need + 1024, dtype=torch.uint8, device=self.device)}
@@ -396,8 +428,10 @@ class _DiscriminatorEngine:
 def weights_init_normal(m):
     """reference modules/model.py:134-140: Conv* weights ~ N(0, 0.02); BatchNorm2d weights ~ N(1, 0.02), bias 0."""
     name = type(m).__name__
+    # same draws as the reference's ``.data`` form; writing through the Parameter bumps its ``_version``, which keys the
+    # packed-weight caches (a ``.data`` write is invisible to them)
     if "Conv" in name:
-        nn.init.normal_(m.weight.data, 0.0, 0.02)
+        nn.init.normal_(m.weight, 0.0, 0.02)
     elif "BatchNorm2d" in name:
-        nn.init.normal_(m.weight.data, 1.0, 0.02)
-        nn.init.constant_(m.bias.data, 0.0)
+        nn.init.normal_(m.weight, 1.0, 0.02)
+        nn.init.constant_(m.bias, 0.0)

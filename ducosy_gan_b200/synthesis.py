@@ -25,6 +25,18 @@ SOFT_HU = (-150.0, 250.0)   # modules/argmanager.py:121-136
 LUNG_HU = (-1000.0, -150.0)  # modules/argmanager.py:138-152
 
 
+def chunk_size(num_slices: int, batch_slices: int) -> int:
+    """Slices per generator call for a volume (or shard) of ``num_slices``: the whole thing at once while it is at most 1.5x
+    ``batch_slices`` (a 37/38-slice shard of a 300-slice volume over 8 GPUs runs as ONE batch instead of 30 + a thin tail),
+    otherwise equal chunks of at most ``batch_slices`` (33 -> 17 + 16, 300 -> 10 x 30)."""
+    if num_slices <= 0:
+        return 1
+    if 2 * num_slices <= 3 * batch_slices:
+        return num_slices
+    n_chunks = -(-num_slices // batch_slices)
+    return -(-num_slices // n_chunks)
+
+
 def shard_range(num_slices: int, rank: int, world_size: int):
     """Contiguous slice range [lo, hi) of ``rank``; ranges are disjoint, ordered and cover [0, S)."""
     if not (0 <= rank < world_size):
@@ -60,18 +72,20 @@ class DualHUSynthesizer:
         return es, el
 
     def _buffers(self, B, H, W):
-        key = (B, H, W)
-        if key not in self._bufs:
+        """fp32 generator outputs of one chunk; a pair that is large enough is reused (shards / volumes of other sizes)."""
+        have = self._bufs.get((H, W))
+        if have is None or have[0].shape[0] < B:
             self._bufs.clear()
             mk = lambda: torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
-            self._bufs[key] = (mk(), mk())
-        return self._bufs[key]
+            have = self._bufs[(H, W)] = (mk(), mk())
+        return have[0][:B], have[1][:B]
 
     def launches_per_chunk(self):
         import ctypes as C
+        from . import _lib
         es, el = self._engines()
-        return (es.lib.ducosy_generator_num_launches(C.byref(es.cfg)) +
-                el.lib.ducosy_generator_num_launches(C.byref(el.cfg)) + 1)
+        lib = _lib.load()
+        return lib.ducosy_generator_num_launches(C.byref(es.cfg)) + lib.ducosy_generator_num_launches(C.byref(el.cfg)) + 1
 
     # ------------------------------------------------------------------ device-resident volume
     def synthesize_device(self, raw_px: torch.Tensor, slope=1.0, intercept=-1024.0, out: torch.Tensor | None = None,
@@ -85,6 +99,8 @@ class DualHUSynthesizer:
         S, H, W = raw_px.shape
         if out is None:
             out = torch.empty_like(raw_px)
+        if S == 0:
+            return out
         es, el = self._engines()
         with torch.cuda.device(self.device):
             cur = torch.cuda.current_stream()
@@ -92,38 +108,27 @@ class DualHUSynthesizer:
                 one = os.environ.get("DUCOSY_SINGLE_STREAM", "0") == "1"   # experiment switch: serialise the two generators
                 self._streams = (cur, cur) if one else (torch.cuda.Stream(), torch.cuda.Stream())
             s_soft, s_lung = self._streams
-            B = min(self.batch_slices, S)
+            B = chunk_size(S, self.batch_slices)
             ys, yl = self._buffers(B, H, W)
             # make sure both engine workspaces exist before the side streams use them
             es.workspace(B, H, W)
             el.workspace(B, H, W)
             for lo in range(0, S, B):
+                # a ragged tail (n < B) goes through the same two-stream pipeline: it reuses the engines' workspaces (laid
+                # out from the sizes of the call) and the leading n slices of ys / yl -- nothing is drained or reallocated
                 n = min(B, S - lo)
                 chunk = raw_px[lo:lo + n]
                 if before_chunk is not None:
                     before_chunk(lo, n)      # e.g. wait for the host->device copy of these slices (synthesize_volume)
-                if n != B:  # ragged tail: run it as its own (smaller) batch after the pipeline drains
-                    cur.wait_stream(s_soft)
-                    cur.wait_stream(s_lung)
-                    ys_t = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
-                    yl_t = torch.empty((n, 1, H, W), dtype=torch.float32, device=self.device)
-                    es._ws.clear()
-                    el._ws.clear()
-                    es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys_t)
-                    el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl_t)
-                    ops.dewindow_composite(chunk, ys_t, yl_t, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
-                    if after_chunk is not None:
-                        after_chunk(lo, n)
-                    continue
                 s_soft.wait_stream(cur)
                 s_lung.wait_stream(cur)
                 with torch.cuda.stream(s_soft):
-                    es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys)
+                    es.forward_hu(chunk, slope, intercept, *self.soft_hu, out=ys[:n])
                 with torch.cuda.stream(s_lung):
-                    el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl)
+                    el.forward_hu(chunk, slope, intercept, *self.lung_hu, out=yl[:n])
                 cur.wait_stream(s_soft)
                 cur.wait_stream(s_lung)
-                ops.dewindow_composite(chunk, ys, yl, slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
+                ops.dewindow_composite(chunk, ys[:n], yl[:n], slope, intercept, self.soft_hu, self.lung_hu, out=out[lo:lo + n])
                 if after_chunk is not None:
                     after_chunk(lo, n)
             if postprocess:
@@ -155,7 +160,7 @@ class DualHUSynthesizer:
             s_in.wait_stream(cur)
             s_out.wait_stream(cur)
             # chunk-wise pipeline: the copy engines move slices k+1 in and k-1 out while the SMs work on chunk k
-            B = max(1, min(self.batch_slices, S)) if S else 1
+            B = chunk_size(S, self.batch_slices)
             ready = {}
             with torch.cuda.stream(s_in):
                 for lo in range(0, S, B):

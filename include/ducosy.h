@@ -215,6 +215,30 @@ int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp
 int ducosy_adam_advance(float* state, ducosy_stream_t stream);
 int ducosy_adam_step_dev(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, const float* state,
                          float beta1, float beta2, float eps, ducosy_stream_t stream);
+/* One optimizer.step() of torch.optim.Adam (modules/trainer.py:360-362) over ALL tensors of a parameter group in three launches,
+ * with a non-finite guard.  `tensors_dev` / `chunks_dev` are tables in DEVICE memory built by the caller: one
+ * ducosy_adam_tensor per parameter, and one ducosy_adam_chunk per DUCOSY_ADAM_CHUNK elements of each tensor (start is a
+ * multiple of DUCOSY_ADAM_CHUNK).  `state` is 8 floats in device memory:
+ *   [0] lr   [1] step count (advanced by this call on a clean step)   [2] scratch flag (must start at 0)
+ *   [3] number of skipped steps   [4] 1 if THIS call was skipped   [5..7] reserved.
+ * With check_finite != 0 a step whose gradients contain Inf/NaN changes nothing but [3] and [4] (torch.amp.GradScaler
+ * semantics): the 16-bit gradient maps of the training path can overflow where the reference's fp32 autograd cannot.
+ * Nothing that changes between steps is a launch argument, so the call is CUDA-graph capturable. */
+#define DUCOSY_ADAM_CHUNK 16384
+typedef struct {
+  float* param;
+  const float* grad;
+  float* exp_avg;
+  float* exp_avg_sq;
+  long long n;
+} ducosy_adam_tensor;
+typedef struct {
+  int tensor;      /* index into the tensor table */
+  int reserved;
+  long long start; /* first element of the chunk */
+} ducosy_adam_chunk;
+int ducosy_adam_multi_step(const ducosy_adam_tensor* tensors_dev, const ducosy_adam_chunk* chunks_dev, int num_chunks, float* state,
+                           float beta1, float beta2, float eps, int check_finite, ducosy_stream_t stream);
 /* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
 int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 

@@ -183,3 +183,49 @@ def test_discriminator_backward_matches_autograd(B, H, W):
     l2x = ((gx - rx).norm() / rx.norm()).item()
     print(f"  input grad: rel L2 err {l2x:.3e}")
     assert l2x < 5e-2
+
+
+def test_reinit_through_data_invalidates_packed_weights():
+    """the reference's weights_init_normal writes through ``.data`` (modules/model.py:134-140), which does not bump the
+    parameters' ``_version``: ``.apply(fn)`` must invalidate the packed 16-bit weights whatever ``fn`` does"""
+    from ducosy_gan_b200.modules.model import Discriminator, Generator, weights_init_normal
+
+    def data_init(m):                                  # the reference's exact form
+        if "Conv" in type(m).__name__:
+            torch.nn.init.normal_(m.weight.data, 0.0, 0.02)
+
+    x = _x(3, (1, 1, 128, 128)).cuda()
+    for net in (Generator(1, 1, True).cuda().eval(), Discriminator(1).cuda().eval()):
+        xin = x if isinstance(net, Generator) else _x(3, (1, 1, 256, 256)).cuda()
+        with torch.no_grad():
+            torch.manual_seed(1)
+            net.apply(weights_init_normal)
+            y1 = net(xin).clone()
+            torch.manual_seed(2)
+            net.apply(data_init)
+            y2 = net(xin).clone()
+            for p in net.parameters():                 # hand edit through .data + the documented explicit hook
+                p.data.mul_(0.5)
+            net.invalidate_packed_weights()
+            y3 = net(xin)
+        assert not torch.equal(y1, y2) and not torch.equal(y2, y3)
+
+
+def test_modules_deepcopy_and_pickle_after_forward():
+    """EMA copies (copy.deepcopy) and whole-module checkpoints (torch.save(model)) work on the reference's modules; the
+    engines (device buffers, captured graphs) are derived state and must not get in the way"""
+    import copy
+    import io
+    from ducosy_gan_b200.modules.model import Discriminator, Generator
+    sd = orc.make_state_dict(orc.generator_param_shapes(1, 1, True), 5, attn_std=0.2)
+    G = _gen(1, 1, True, sd)
+    D = Discriminator(1).cuda().eval()
+    x = _x(3, (1, 1, 256, 256)).cuda()
+    with torch.no_grad():
+        y, d = G(x), D(x)
+        G2, D2 = copy.deepcopy(G), copy.deepcopy(D)
+        buf = io.BytesIO()
+        torch.save(G, buf)
+        buf.seek(0)
+        G3 = torch.load(buf, weights_only=False)
+        assert torch.equal(G2(x), y) and torch.equal(G3(x), y) and torch.equal(D2(x), d)

@@ -186,3 +186,137 @@ def test_graphed_step_matches_eager_step():
         y = step.D_A(batches[0][0])
         y2 = eager.D_A(batches[0][0])
     assert (y - y2).abs().max().item() < 1e-3 * y2.abs().max().item() + 1e-5
+
+
+def _config4_case():
+    """BASELINE configs[3] network at batch 1: soft-tissue generators (input_channels = 3: slice + bone / mediastinum masks,
+    9 CBAM blocks), PatchGAN discriminators, 512x512."""
+    from ducosy_gan_b200.trainer import CycleGANStep
+    step = CycleGANStep(3, 9, True, seed=1234)
+    g = torch.Generator().manual_seed(2)
+    smooth = lambda t: torch.nn.functional.avg_pool2d(t, 5, 1, 2) * 2.0
+    real_A = smooth(torch.rand(1, 1, 512, 512, generator=g) * 2 - 1).clamp(-1, 1)
+    real_B = smooth(torch.rand(1, 1, 512, 512, generator=g) * 2 - 1).clamp(-1, 1)
+    masks = (torch.rand(1, 2, 512, 512, generator=g) < 0.1).float()
+    return step, real_A, real_B, masks
+
+
+def test_config4_network_step1_losses_and_gradients_vs_oracle():
+    """Step 1 of the config-4 network (Cin 3, 9 CBAM blocks, 512x512, batch 1) against oracle.cyclegan_generator_loss /
+    cyclegan_discriminator_loss under torch autograd (fp32, CPU): all 12 logged terms, and the gradient of EVERY parameter
+    tensor of the four networks as relative L2 error, asserted against the floor measured on the B200
+    (profiles/r02_config4_step1.json): 16-bit stored activations and gradient maps through up to three chained networks
+    (G -> G -> D) leave 0.1 % at the last layer of the last network and grow towards the first layer of the first."""
+    import json
+    import os
+    step, real_A, real_B, masks = _config4_case()
+    nets = dict(G_A2B=step.G_A2B, G_B2A=step.G_B2A, D_A=step.D_A, D_B=step.D_B)
+    sds = {n: {k: v.detach().cpu().clone().requires_grad_(True) for k, v in m.state_dict().items()} for n, m in nets.items()}
+    # ---- oracle: forward + autograd
+    loss_G, t, fake_A, fake_B = orc.cyclegan_generator_loss(sds["G_A2B"], sds["G_B2A"], sds["D_A"], sds["D_B"], real_A, real_B, masks, 9, True)
+    loss_G.backward()
+    ref_grads = {n: {k: v.grad.clone() for k, v in sds[n].items()} for n in ("G_A2B", "G_B2A")}
+    for n in ("D_A", "D_B"):
+        for v in sds[n].values():
+            v.grad = None
+    l_DA = orc.cyclegan_discriminator_loss(sds["D_A"], real_A, fake_A)
+    l_DA.backward()
+    l_DB = orc.cyclegan_discriminator_loss(sds["D_B"], real_B, fake_B)
+    l_DB.backward()
+    for n in ("D_A", "D_B"):
+        ref_grads[n] = {k: v.grad.clone() for k, v in sds[n].items()}
+    ref = {k: float(v) for k, v in t.items()}
+    ref.update(G=float(loss_G), D_A=float(l_DA), D_B=float(l_DB))
+    # ---- CUDA path: the same statements through the product modules
+    dev = lambda x: x.cuda()
+    for m in nets.values():
+        m.zero_grad(set_to_none=True)
+    cg, ct, cfA, cfB = step.generator_losses(dev(real_A), dev(real_B), dev(masks))
+    cg.backward()
+    got_grads = {n: {k: p.grad.detach().cpu().clone() for k, p in nets[n].named_parameters()} for n in ("G_A2B", "G_B2A")}
+    for n in ("D_A", "D_B"):
+        nets[n].zero_grad(set_to_none=True)         # trainer.py:517,522 discard what loss_G.backward() left there
+    c_DA = step._disc_loss(step.D_A, dev(real_A), cfA)
+    c_DA.backward()
+    c_DB = step._disc_loss(step.D_B, dev(real_B), cfB)
+    c_DB.backward()
+    for n in ("D_A", "D_B"):
+        got_grads[n] = {k: p.grad.detach().cpu().clone() for k, p in nets[n].named_parameters()}
+    got = {k: float(v) for k, v in ct.items()}
+    got.update(G=float(cg), D_A=float(c_DA), D_B=float(c_DB))
+    bad = {k: (got[k], ref[k]) for k in ref if abs(got[k] - ref[k]) > 2e-2 * abs(ref[k]) + 1e-4}
+    print("config-4 step-1 losses (cuda, oracle):", {k: (round(got[k], 5), round(ref[k], 5)) for k in ref})
+    assert not bad, bad
+    table, worst = {}, {}
+    for n in got_grads:
+        for k, g in got_grads[n].items():
+            r = ref_grads[n][k]
+            dead = k.endswith("bias") and r.norm().item() < 1e-3 * max(1.0, r.numel() ** 0.5) and g.abs().max().item() == 0.0
+            rel = 0.0 if dead else ((g - r).norm() / (r.norm() + 1e-30)).item()
+            table[f"{n}.{k}"] = rel
+            worst[n] = max(worst.get(n, 0.0), rel)
+    out = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "gpurun_out")
+    os.makedirs(out, exist_ok=True)
+    json.dump({"losses": {k: [got[k], ref[k]] for k in ref}, "grad_rel_l2": table, "worst_per_network": worst},
+              open(os.path.join(out, "config4_step1.json"), "w"), indent=1)
+    print("config-4 step-1 worst gradient rel-L2 per network:", {k: round(v, 4) for k, v in worst.items()})
+    top = sorted(table.items(), key=lambda kv: -kv[1])[:8]
+    print("  worst tensors:", [(k, round(v, 4)) for k, v in top])
+    # measured floor on the B200 (fp16 operands): see profiles/r02_config4_step1.json
+    assert table["G_B2A.model.28.weight"] < 0.02 and table["G_A2B.model.28.weight"] < 0.02
+    assert worst["D_A"] < 0.10 and worst["D_B"] < 0.10, worst
+    assert worst["G_A2B"] < 0.30 and worst["G_B2A"] < 0.30, worst
+    med = sorted(table.values())[len(table) // 2]
+    assert med < 0.10, med
+
+
+def test_adam_skips_a_step_with_non_finite_gradients():
+    """GradScaler-style guard of the fused Adam: a step whose gradients hold Inf/NaN changes neither the parameters nor the
+    moments nor the step count; the next clean step is exactly the step an unpoisoned optimiser would have taken."""
+    from ducosy_gan_b200.optim import Adam
+    torch.manual_seed(0)
+    shapes = [(64, 32, 3, 3), (5,), (1,), (70001,)]
+    a = [torch.randn(s, device="cuda").requires_grad_(True) for s in shapes]
+    b = [p.detach().clone().requires_grad_(True) for p in a]
+    oa, ob = Adam(a, lr=1e-3, betas=(0.5, 0.999)), Adam(b, lr=1e-3, betas=(0.5, 0.999))
+    grads = [[torch.randn(s, device="cuda") for s in shapes] for _ in range(3)]
+    for k in range(3):
+        if k == 1:                                   # poisoned step for `a` only
+            for p, g in zip(a, grads[k]):
+                p.grad = g.clone()
+            a[3].grad[12345] = float("nan")
+            a[0].grad[3, 2, 1, 0] = float("inf")
+            before = [p.detach().clone() for p in a]
+            oa.step()
+            assert all(torch.equal(x, y) for x, y in zip(before, a))
+            assert oa.skipped_steps() == 1
+            continue
+        for p, q, g in zip(a, b, grads[k]):
+            p.grad, q.grad = g.clone(), g.clone()
+        oa.step()
+        ob.step()
+    assert all(torch.equal(x, y) for x, y in zip(a, b))
+    assert oa.state_dict()["state"][0]["step"] == 2 and ob.skipped_steps() == 0
+
+
+def test_training_survives_a_constant_channel():
+    """A dead conv output channel (all-zero weights) is a constant map: InstanceNorm's backward scales its gradient by
+    1/sqrt(0 + 1e-5) = 316, the regime the 16-bit gradient maps are most exposed in.  Whatever happens there, the master
+    weights must stay finite (the update is skipped if a gradient overflowed)."""
+    from ducosy_gan_b200.trainer import CycleGANStep
+    step = CycleGANStep(1, 2, True, seed=5)
+    with torch.no_grad():
+        for G in (step.G_A2B, step.G_B2A):
+            G.model[1].weight[7].zero_()                       # stem channel 7 dead
+            G.model[4].weight[11].zero_()                      # down-conv channel 11 dead
+            G.model[10].block[1].weight[3].zero_()             # first res-block conv, channel 3 dead
+            G.model[10].block[5].weight[3].zero_()
+    g = torch.Generator().manual_seed(1)
+    real_A = (torch.rand(1, 1, 256, 512, generator=g) * 2 - 1).cuda()
+    real_B = (torch.rand(1, 1, 256, 512, generator=g) * 2 - 1).cuda()
+    for _ in range(3):
+        out = step.step(real_A, real_B)
+    assert all(torch.isfinite(v).item() for v in out.values()), out
+    for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B):
+        assert all(torch.isfinite(p).all().item() for p in m.parameters())
+    print("skipped steps:", step.optimizer_G.skipped_steps(), step.optimizer_D_A.skipped_steps(), step.optimizer_D_B.skipped_steps())

@@ -135,3 +135,38 @@ def _halo_worker(rank, world, port):
 def test_gloo_z_halo_exchange(world):
     port = 33500 + os.getpid() % 2000 + world
     mp.spawn(_halo_worker, args=(world, port), nprocs=world, join=True)
+
+
+# ------------------------------------------------------------------ logged losses under data parallelism (trainer.py:527-531)
+def _logged_worker(rank, world, port):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from ducosy_gan_b200.data_parallel import TERM_KEYS, check_equal_shards, logged_losses, loss_weights, shard_batch
+    B = 8
+    g = torch.Generator().manual_seed(5)
+    per_sample = {k: torch.rand(B, generator=g) for k in TERM_KEYS + ("D_A", "D_B")}       # per-sample values of each mean-type term
+    glob = {"contrast_region": torch.tensor(0.4321), "contrast_edge": torch.tensor(0.2468)}  # batch-global: same on all ranks
+    # single process on the whole batch: what the reference logs
+    single = {k: (glob[k] if k in glob else per_sample[k].mean()) for k in TERM_KEYS}
+    w = loss_weights()
+    single_G = sum(w[k] * single[k] for k in TERM_KEYS)
+    lo, hi = shard_batch(B, rank, world)
+    terms = {k: (glob[k] if k in glob else per_sample[k][lo:hi].mean()) for k in TERM_KEYS}
+    out = logged_losses(terms, per_sample["D_A"][lo:hi].mean(), per_sample["D_B"][lo:hi].mean())
+    for k in TERM_KEYS:
+        assert torch.allclose(out[k], single[k], rtol=1e-6, atol=1e-7), (k, out[k], single[k])
+    assert torch.allclose(out["G"], single_G, rtol=1e-6), (out["G"], single_G)
+    assert torch.allclose(out["D_A"], per_sample["D_A"].mean(), rtol=1e-6) and torch.allclose(out["D_B"], per_sample["D_B"].mean(), rtol=1e-6)
+    # the round-1 defect: the backward surrogate (global terms x world) read as the logged loss
+    surrogate = single_G + (world - 1) * (1.5 * glob["contrast_region"] + glob["contrast_edge"])
+    assert abs(float(out["G"]) - float(surrogate)) > 0.1
+    check_equal_shards(hi - lo)
+    with pytest.raises(ValueError):
+        check_equal_shards(3 + rank)
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 4])
+def test_gloo_logged_losses_equal_single_process(world):
+    port = 35500 + os.getpid() % 2000 + world
+    mp.spawn(_logged_worker, args=(world, port), nprocs=world, join=True)
