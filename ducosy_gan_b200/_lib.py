@@ -103,6 +103,12 @@ SIGNATURES = {
     "ducosy_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "ducosy_adam_advance": (_i, [_p, _p]),
     "ducosy_adam_step_dev": (_i, [_p, _p, _p, _p, _ll, _p, _f, _f, _f, _p]),
+    "ducosy_channel_attention_scratch_bytes": (_sz, [_i, _i]),
+    "ducosy_channel_attention_nchw": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_spatial_attention_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_spatial_attention_nchw": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_nchw_to_nhwc_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_adam_multi_step": (_i, [_p, _p, _i, _p, _f, _f, _f, _i, _p]),
     "ducosy_cbam_channel_train": (_i, [_p] * 9 + [_i, _i, _p]),
     "ducosy_cbam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),

@@ -25,6 +25,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace ducosy {
 
@@ -317,22 +318,6 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ host side
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-
-EncodeTiledFn get_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 template <int kN, typename T, int kCG>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmArgs& args,
                 int grid, cudaStream_t stream) {
@@ -439,8 +424,6 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();
   const int cg = (cg_env == 2 && (a.TY * a.TX) % 2 == 0) ? 2 : 1;
 
-  EncodeTiledFn encode = get_encode_fn();
-  DUCOSY_CHECK(encode != nullptr, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled is not available (no CUDA driver?)");
   const CUtensorMapDataType dt = p.dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   CUtensorMap tmA, tmB, tmO;
   {
@@ -457,10 +440,7 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
       gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
     }
     const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmO, dt, 5, p.out, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled(out) failed with %d", int(r));
+    DUCOSY_TRY(encode_tiled_cached(&tmO, dt, 5, p.out, gdim, gstr, box, "conv_gemm(out)"));
   }
   {
     const cuuint64_t C2 = cuuint64_t(p.Cin) * 2, W = cuuint64_t(p.Wp), H = cuuint64_t(p.Hp);
@@ -473,22 +453,14 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
       gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
     }
     const cuuint32_t box[5] = {cuuint32_t(kBlockK), 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
-    const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-    CUresult r = encode(&tmA, dt, 5, const_cast<void*>(p.in), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled(A) failed with %d", int(r));
+    DUCOSY_TRY(encode_tiled_cached(&tmA, dt, 5, p.in, gdim, gstr, box, "conv_gemm(A)"));
   }
   {
     const cuuint64_t Ktot = cuuint64_t(p.num_taps) * p.Cin;
     const cuuint64_t gdim[2] = {Ktot, cuuint64_t(p.num_phases) * p.Cout};
     const cuuint64_t gstr[1] = {Ktot * 2};
     const cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(kN / cg)};
-    const cuuint32_t estr[2] = {1, 1};
-    CUresult r = encode(&tmB, dt, 2, const_cast<void*>(p.w), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_gemm: cuTensorMapEncodeTiled(B) failed with %d", int(r));
+    DUCOSY_TRY(encode_tiled_cached(&tmB, dt, 2, p.w, gdim, gstr, box, "conv_gemm(B)"));
   }
 
   const int total_tiles = a.B * a.num_phases * a.TY * a.TX * a.n_blocks;

@@ -10,6 +10,7 @@
 
 #include "common.cuh"
 #include "ptx.cuh"
+#include "tmap.cuh"
 
 namespace ducosy {
 namespace {
@@ -186,25 +187,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
   }
 }
 
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
-                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
-                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-EncodeTiledFn wg_encode_fn() {
-  static EncodeTiledFn fn = nullptr;
-  if (fn == nullptr) {
-    void* p = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
-        qres == cudaDriverEntryPointSuccess)
-      fn = reinterpret_cast<EncodeTiledFn>(p);
-  }
-  return fn;
-}
-
 int encode_nhwc_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, int B, int Hp, int Wp, int C, int stride,
                     int Wt, int R) {
-  EncodeTiledFn encode = wg_encode_fn();
-  DUCOSY_CHECK(encode != nullptr, DUCOSY_ERR_CUDA, "conv_wgrad: cuTensorMapEncodeTiled is not available");
   const cuuint64_t C2 = cuuint64_t(C) * 2, W = cuuint64_t(Wp), H = cuuint64_t(Hp);
   cuuint64_t gdim[5], gstr[4];
   if (stride == 1) {
@@ -215,11 +199,7 @@ int encode_nhwc_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, i
     gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
   }
   const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
-  const cuuint32_t estr[5] = {1, 1, 1, 1, 1};
-  CUresult r = encode(tm, dt, 5, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                      CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  DUCOSY_CHECK(r == CUDA_SUCCESS, DUCOSY_ERR_CUDA, "conv_wgrad: cuTensorMapEncodeTiled failed with %d", int(r));
-  return 0;
+  return encode_tiled_cached(tm, dt, 5, base, gdim, gstr, box, "conv_wgrad");
 }
 
 // K splits: one CTA per SM and unit.  The grid must not spill into an extra wave (297 CTAs on 148 SMs run as long as

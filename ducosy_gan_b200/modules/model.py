@@ -63,8 +63,20 @@ class _DerivedState:
         return state
 
 
+def _forward_only(module, x):
+    """The stand-alone building blocks run forward-only (inside ``Generator`` the same layers are differentiable through the
+    fused training path): refuse to hand autograd a tensor without history instead of training on silent zeros."""
+    if not x.is_cuda:
+        raise RuntimeError(f"ducosy_gan_b200.{type(module).__name__} needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
+    if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in module.parameters())):
+        raise RuntimeError(f"ducosy_gan_b200.{type(module).__name__}.forward on its own is forward-only: call it under torch.no_grad() "
+                           "(training goes through Generator.forward, which differentiates these layers in its fused path)")
+    _lib.check(_lib.load().ducosy_check_device(), "check_device")
+
+
 class ChannelAttention(nn.Module):
-    """reference modules/model.py:6-24 (parameters: fc.0.weight [C/r,C,1,1], fc.2.weight [C,C/r,1,1])."""
+    """reference modules/model.py:6-24 (parameters: fc.0.weight [C/r,C,1,1], fc.2.weight [C,C/r,1,1]).
+    ``forward(x[B,C,H,W] fp32) -> x * sigmoid(fc(avgpool x) + fc(maxpool x))``, both branches (csrc/blocks.cu)."""
 
     def __init__(self, channels, reduction=16):
         super().__init__()
@@ -75,11 +87,14 @@ class ChannelAttention(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x):
-        raise NotImplementedError("ChannelAttention runs fused inside Generator.forward / ResidualBlockWithCBAM")
+        from .. import ops
+        _forward_only(self, x)
+        return ops.channel_attention_nchw(x, self.fc[0].weight.detach(), self.fc[2].weight.detach())
 
 
 class SpatialAttention(nn.Module):
-    """reference modules/model.py:27-39 (parameter: conv.weight [1,2,k,k])."""
+    """reference modules/model.py:27-39 (parameter: conv.weight [1,2,k,k]).
+    ``forward(x[B,C,H,W] fp32) -> x * sigmoid(conv_kxk(cat[mean_C x, max_C x]))`` (csrc/blocks.cu)."""
 
     def __init__(self, kernel_size=7):
         super().__init__()
@@ -87,11 +102,13 @@ class SpatialAttention(nn.Module):
         self.sigmoid = nn.Sigmoid()
 
     def forward(self, x):
-        raise NotImplementedError("SpatialAttention runs fused inside Generator.forward / ResidualBlockWithCBAM")
+        from .. import ops
+        _forward_only(self, x)
+        return ops.spatial_attention_nchw(x, self.conv.weight.detach())
 
 
 class CBAM(nn.Module):
-    """reference modules/model.py:42-52."""
+    """reference modules/model.py:42-52: channel attention, then spatial attention."""
 
     def __init__(self, channels, reduction=16, kernel_size=7):
         super().__init__()
@@ -99,12 +116,54 @@ class CBAM(nn.Module):
         self.spatial_attention = SpatialAttention(kernel_size)
 
     def forward(self, x):
-        raise NotImplementedError("CBAM runs fused inside Generator.forward / ResidualBlockWithCBAM")
+        _forward_only(self, x)
+        return self.spatial_attention(self.channel_attention(x))
 
 
 def _res_layers(c):
     return nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(c, c, 3), nn.InstanceNorm2d(c), nn.ReLU(inplace=True),
                          nn.ReflectionPad2d(1), nn.Conv2d(c, c, 3), nn.InstanceNorm2d(c))
+
+
+def _residual_block_forward(module, x, cbam):
+    """Stand-alone forward of a residual block on the generator's kernels: NCHW fp32 -> reflect-padded NHWC 16-bit ->
+    tcgen05 conv + InstanceNorm statistics -> IN/ReLU/pad -> conv -> IN (+ channel attention, spatial attention) ->
+    residual add -> NCHW fp32.  Same arithmetic as inside Generator.forward (16-bit operands, fp32 accumulate; behind the
+    non-affine InstanceNorm the avg-pool branch of the channel attention is identically zero and is not evaluated)."""
+    from .. import ops
+    _forward_only(module, x)
+    if x.dim() != 4:
+        raise RuntimeError(f"expected [B,C,H,W], got {tuple(x.shape)}")
+    B, Cn, H, W = x.shape
+    conv1, conv2 = module.block[1], module.block[5]
+    if Cn != conv1.in_channels:
+        raise RuntimeError(f"expected {conv1.in_channels} channels, got {Cn}")
+    Wt = min(W, 128)
+    if Cn % 64 or Cn not in (64, 128, 256) or W % Wt or Wt & (Wt - 1) or Wt < 8 or H % (128 // Wt) or H < 2 or W < 2:
+        raise RuntimeError(f"stand-alone residual block: channels must be 64/128/256, W one of 8/16/32/64 or a multiple of 128, H a "
+                           f"multiple of 128/min(W,128) (got C={Cn}, {H}x{W})")
+    if cbam is not None and (Cn != 256 or cbam.channel_attention.fc[0].out_channels != 16 or cbam.spatial_attention.conv.kernel_size != (7, 7)):
+        raise RuntimeError("stand-alone ResidualBlockWithCBAM: the fused CBAM kernels are built for 256 channels, reduction 16, 7x7")
+    dt = _lib.torch_dtype(default_operand_dtype())
+    cache = module.__dict__.setdefault("_packed", {})
+    sig = (conv1.weight.data_ptr(), conv1.weight._version, conv2.weight.data_ptr(), conv2.weight._version, dt)
+    if cache.get("sig") != sig:
+        cache.clear()
+        cache.update(sig=sig, w1=ops.pack_conv_weight(conv1.weight, dt), w2=ops.pack_conv_weight(conv2.weight, dt))
+    xp = ops.nchw_to_nhwc_pad(x, 1, _lib.PAD_REFLECT, dt)
+    ya, part = ops.conv2d_nhwc(xp, cache["w1"], 3, 3, 1)
+    pa = ops.in_apply_pad(ya, *ops.in_finalize(part, H * W), 1, _lib.PAD_REFLECT, _lib.ACT_RELU)
+    yb, part = ops.conv2d_nhwc(pa, cache["w2"], 3, 3, 1)
+    if cbam is None:
+        scale, shift = ops.in_finalize(part, H * W)
+        sa = None
+    else:
+        fc0 = cbam.channel_attention.fc[0].weight.detach().to(torch.float32).contiguous()
+        fc2 = cbam.channel_attention.fc[2].weight.detach().to(torch.float32).contiguous()
+        scale, shift = ops.in_finalize(part, H * W, fc0, fc2)          # InstanceNorm and channel attention as one affine map
+        sa = ops.cbam_spatial_conv(ops.cbam_pool(yb, scale, shift), cbam.spatial_attention.conv.weight)
+    out = ops.residual_apply_pad(yb, scale, shift, sa, xp, 1, 0, _lib.PAD_ZERO)
+    return ops.nhwc_to_nchw(out)
 
 
 class ResidualBlock(nn.Module):
@@ -115,7 +174,12 @@ class ResidualBlock(nn.Module):
         self.block = _res_layers(in_features)
 
     def forward(self, x):
-        raise NotImplementedError("ResidualBlock runs fused inside Generator.forward")
+        return _residual_block_forward(self, x, None)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_packed", None)
+        return state
 
 
 class ResidualBlockWithCBAM(nn.Module):
@@ -127,7 +191,12 @@ class ResidualBlockWithCBAM(nn.Module):
         self.cbam = CBAM(in_features)
 
     def forward(self, x):
-        raise NotImplementedError("ResidualBlockWithCBAM runs fused inside Generator.forward")
+        return _residual_block_forward(self, x, self.cbam)
+
+    def __getstate__(self):
+        state = self.__dict__.copy()
+        state.pop("_packed", None)
+        return state
 
 
 class Generator(_DerivedState, nn.Module):
@@ -167,6 +236,11 @@ class Generator(_DerivedState, nn.Module):
     def _ordered_params(self):
         return _ordered_params(self)
 
+    def _train_pack_cache(self):
+        """Packed operand forms of this module's weights for the training path (ops.pack_cache): per device, derived state."""
+        dev = torch.cuda.current_device()
+        return self._engines.setdefault(("train_packs", dev), _PackCache())
+
     def forward(self, x):
         if not x.is_cuda:
             raise RuntimeError("ducosy_gan_b200.Generator needs CUDA tensors on an sm_100 (B200) device; no CPU path exists")
@@ -174,9 +248,11 @@ class Generator(_DerivedState, nn.Module):
             if x.dim() != 4 or x.shape[1] != self._cfg_tuple[0]:
                 raise RuntimeError(f"expected input [B,{self._cfg_tuple[0]},H,W], got {tuple(x.shape)}")
             _lib.check(_lib.load().ducosy_check_device(), "check_device")
-            return _GeneratorFunction.apply(self._cfg_tuple, x, *self._ordered_params())
+            return _GeneratorFunction.apply((self._cfg_tuple, self._train_pack_cache()), x, *self._ordered_params())
         eng = self._engine(x.device)
         eng.sync_weights(self._ordered_params())
+        if eng.wants_graph(x, self):
+            return eng.forward_graphed(x)
         return eng.forward(x)
 
     def forward_hu(self, px, slope, intercept, hu_min, hu_max):
@@ -187,31 +263,39 @@ class Generator(_DerivedState, nn.Module):
         return eng.forward_hu(px, slope, intercept, hu_min, hu_max)
 
 
+class _PackCache(dict):
+    """ops.pack_cache store of one module on one device; ``invalidate`` makes it an engine-like entry of ``_engines``."""
+
+    def invalidate(self):
+        self.clear()
+
+
 class _GeneratorFunction(torch.autograd.Function):
     """autograd bridge of the training path (reference modules/trainer.py:455-500): the forward keeps the raw conv outputs
     and InstanceNorm statistics, the backward runs ..training.generator_backward.  The image gradient flows to channel 0
     (the CT slice); the mask channels the reference concatenates (trainer.py:430-450) are data."""
 
     @staticmethod
-    def forward(ctx, cfg, x, *params):
-        from .. import training
+    def forward(ctx, cfg_and_cache, x, *params):
+        from .. import ops, training
+        cfg, cache = cfg_and_cache
         dtype = torch.float16 if default_operand_dtype() == _lib.F16 else torch.bfloat16
         xs = x.detach().to(dtype=torch.float32).contiguous()
         ps = [p.detach() for p in params]
-        with torch.cuda.device(x.device):
+        with torch.cuda.device(x.device), ops.pack_cache(cache):
             out, saved = training.generator_forward_train(ps, cfg, xs, dtype)
         saved.pop("out")
-        ctx.cfg, ctx.saved, ctx.params, ctx.in_shape = cfg, saved, ps, tuple(x.shape)
+        ctx.cfg, ctx.saved, ctx.params, ctx.in_shape, ctx.cache = cfg, saved, ps, tuple(x.shape), cache
         ctx.save_for_backward(out)
         return out
 
     @staticmethod
     def backward(ctx, dout):
-        from .. import training
+        from .. import ops, training
         (out,) = ctx.saved_tensors
         saved = ctx.saved
         saved["out"] = out
-        with torch.cuda.device(out.device):
+        with torch.cuda.device(out.device), ops.pack_cache(ctx.cache):
             grads, dx = training.generator_backward(ctx.params, ctx.cfg, saved, dout, ctx.needs_input_grad[1])
             if dx is not None and ctx.in_shape[1] > 1:
                 full = torch.zeros(ctx.in_shape, dtype=torch.float32, device=out.device)
@@ -234,12 +318,64 @@ class _GeneratorEngine:
                                       dtype=torch.uint8, device=device)
         self._versions = None
         self._ws = {}
+        self._graphs = {}        # input shape -> (CUDAGraph, static input, static output, dedicated workspace)
 
     def _packed_ptr(self):
         return (self.packed.data_ptr() + 255) // 256 * 256
 
     def invalidate(self):
         self._versions = None
+
+    # -- small-batch calls replayed from a CUDA graph ------------------------------------------------------------------
+    GRAPH_MAX_PIXELS = 2 * 512 * 512
+
+    def wants_graph(self, x, module):
+        """generate.py:89-102 calls ``model(x)`` one slice at a time: ~100 dependent kernels of a few microseconds each, so the
+        call is bound by launch latency, not by the GPU.  Such calls (eval mode, no autograd, at most two 512x512 slices) are
+        captured once per input shape and replayed.  The graph holds only the launches: the packed weights it reads are
+        refreshed outside it whenever a parameter changes, so it never goes stale.  DUCOSY_FORWARD_GRAPH=0 disables it."""
+        return (not module.training and x.dim() == 4 and x.shape[1] == self.cfg.input_channels
+                and x.shape[0] * x.shape[2] * x.shape[3] <= self.GRAPH_MAX_PIXELS
+                and not getattr(module, "_is_replica", False)
+                and os.environ.get("DUCOSY_FORWARD_GRAPH", "1") != "0"
+                and not torch.cuda.is_current_stream_capturing())
+
+    def forward_graphed(self, x):
+        key = tuple(x.shape)
+        entry = self._graphs.get(key)
+        if entry is None:
+            entry = self._capture(x)
+        graph, xin, out, _ = entry
+        with torch.cuda.device(self.device):
+            xin.copy_(x)                      # any dtype / layout the eager call accepts
+            graph.replay()
+            return out.clone()                # the static buffer is overwritten by the next call
+
+    def _capture(self, x):
+        B, _, H, W = x.shape
+        need = _lib.load().ducosy_generator_workspace_bytes(C.byref(self.cfg), B, H, W)
+        if need == 0:
+            raise _lib.DucosyError(f"unsupported generator input shape B={B} H={H} W={W}: "
+                                   "B >= 1, H a multiple of 32, W of 128, W/4 in {32,64,128k}")
+        with torch.cuda.device(self.device):
+            ws = torch.empty(need + 1024, dtype=torch.uint8, device=self.device)
+            wptr = (ws.data_ptr() + 1023) // 1024 * 1024
+            xin = torch.empty((B, self.cfg.input_channels, H, W), dtype=torch.float32, device=self.device)
+            out = torch.empty((B, 1, H, W), dtype=torch.float32, device=self.device)
+            xin.copy_(x)
+
+            def launch():
+                _lib.call("ducosy_generator_forward", C.byref(self.cfg), C.c_void_p(self._packed_ptr()), _lib.ptr(xin),
+                          _lib.ptr(out), B, H, W, C.c_void_p(wptr), ws.numel() - 1024, _lib.stream_ptr())
+
+            launch()                          # eager once: per-device kernel attributes and TMA descriptors exist before capture
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph, capture_error_mode="thread_local"):
+                launch()
+        if len(self._graphs) >= 4:            # a handful of shapes at most; drop the oldest
+            self._graphs.pop(next(iter(self._graphs)))
+        entry = self._graphs[tuple(x.shape)] = (graph, xin, out, ws)
+        return entry
 
     def sync_weights(self, params):
         """Re-pack when any fp32 master parameter changed (load_state_dict, optimizer step, .to())."""

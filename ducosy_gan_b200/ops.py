@@ -15,6 +15,42 @@ def _dev(t):
     return torch.cuda.device(t.device)
 
 
+# Packed 16-bit operand forms of a weight (forward K-major, the three dgrad packings, ...) are functions of the fp32 master
+# weight alone.  One optimisation step uses every generator weight in several passes (translation + identity batch, cycle
+# pass, and the backward of each), so inside ``with pack_cache(d):`` the packings are kept in ``d`` -- a dict OWNED BY THE
+# MODULE whose parameters they belong to, so it dies with them and a recycled address can never alias a dead tensor -- and
+# rebuilt when the tensor's ``_version`` moved (optimiser step, load_state_dict, any in-place op).  Inside a CUDA-graph
+# capture the first use of a step records the pack kernel and the later uses record nothing, which is exactly the order a
+# replay needs.  Outside such a context every call packs afresh.
+import contextlib
+import threading
+
+_tls = threading.local()
+
+
+@contextlib.contextmanager
+def pack_cache(cache):
+    prev = getattr(_tls, "cache", None)
+    _tls.cache = cache
+    try:
+        yield
+    finally:
+        _tls.cache = prev
+
+
+def _cached_pack(kind, w, dtype, build):
+    cache = getattr(_tls, "cache", None)
+    if cache is None:
+        return build()
+    key = (kind, w.data_ptr(), dtype)
+    ent = cache.get(key)
+    if ent is not None and ent[0] == w._version and ent[2] == tuple(w.shape):
+        return ent[1]
+    out = build()
+    cache[key] = (w._version, out, tuple(w.shape))
+    return out
+
+
 # ------------------------------------------------------------------ HU kernels
 def hu_window(px: torch.Tensor, slope, intercept, soft=(-150.0, 250.0), lung=(-1000.0, -150.0)):
     """int16 stored values -> (soft-window, lung-window) fp32 in [-1,1]   (reference preprocess.py:72-84)."""
@@ -57,7 +93,7 @@ def dewindow_composite(raw_px, y_soft, y_lung, slope, intercept, soft=(-150.0, 2
 
 
 # ------------------------------------------------------------------ weight packing
-def pack_conv_weight(w: torch.Tensor, dtype=torch.float16):
+def _pack_conv_weight_build(w, dtype):
     Cout, Cin, kh, kw = w.shape
     w = w.detach().to(torch.float32).contiguous()
     with _dev(w):
@@ -66,7 +102,11 @@ def pack_conv_weight(w: torch.Tensor, dtype=torch.float16):
     return out
 
 
-def pack_upconv_weight(w: torch.Tensor, dtype=torch.float16):
+def pack_conv_weight(w: torch.Tensor, dtype=torch.float16):
+    return _cached_pack("conv", w, dtype, lambda: _pack_conv_weight_build(w, dtype))
+
+
+def _pack_upconv_weight_build(w, dtype):
     Cout, Cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     w = w.detach().to(torch.float32).contiguous()
@@ -76,7 +116,11 @@ def pack_upconv_weight(w: torch.Tensor, dtype=torch.float16):
     return out
 
 
-def pack_stem_weight(w: torch.Tensor, dtype=torch.float16):
+def pack_upconv_weight(w: torch.Tensor, dtype=torch.float16):
+    return _cached_pack("upconv", w, dtype, lambda: _pack_upconv_weight_build(w, dtype))
+
+
+def _pack_stem_weight_build(w, dtype):
     Cout, Cin, kh, kw = w.shape
     assert Cout == 64 and kh == 7 and kw == 7
     w = w.detach().to(torch.float32).contiguous()
@@ -87,13 +131,21 @@ def pack_stem_weight(w: torch.Tensor, dtype=torch.float16):
     return out
 
 
-def pack_out_weight(w: torch.Tensor, dtype=torch.float16):
+def pack_stem_weight(w: torch.Tensor, dtype=torch.float16):
+    return _cached_pack("stem", w, dtype, lambda: _pack_stem_weight_build(w, dtype))
+
+
+def _pack_out_weight_build(w, dtype):
     assert tuple(w.shape) == (1, 64, 7, 7)
     w = w.detach().to(torch.float32).contiguous()
     with _dev(w):
         out = torch.empty((7, 8, 64), dtype=dtype, device=w.device)
         call("ducosy_pack_out_weight", ptr(w), ptr(out), dtype_code(dtype), stream_ptr())
     return out
+
+
+def pack_out_weight(w: torch.Tensor, dtype=torch.float16):
+    return _cached_pack("out", w, dtype, lambda: _pack_out_weight_build(w, dtype))
 
 
 # ------------------------------------------------------------------ convolutions
@@ -124,7 +176,7 @@ def upconv2x_nhwc(x_pad: torch.Tensor, w_packed4: torch.Tensor):
     return y, partials
 
 
-def pack_upconv_merged_weight(w: torch.Tensor, dtype=torch.float16):
+def _pack_upconv_merged_weight_build(w, dtype):
     Cout, Cin, kh, kw = w.shape
     assert kh == 3 and kw == 3
     w = w.detach().to(torch.float32).contiguous()
@@ -132,6 +184,10 @@ def pack_upconv_merged_weight(w: torch.Tensor, dtype=torch.float16):
         out = torch.empty((4 * Cout, 9 * Cin), dtype=dtype, device=w.device)
         call("ducosy_pack_upconv_merged_weight", ptr(w), ptr(out), Cout, Cin, dtype_code(dtype), stream_ptr())
     return out
+
+
+def pack_upconv_merged_weight(w: torch.Tensor, dtype=torch.float16):
+    return _cached_pack("upconv_merged", w, dtype, lambda: _pack_upconv_merged_weight_build(w, dtype))
 
 
 def upconv2x_merged_nhwc(x_pad: torch.Tensor, w_merged: torch.Tensor):
@@ -294,8 +350,11 @@ def convs2_dgrad_nhwc(dy_pad, w_oihw):
     B, Hp, Wp, _ = dy_pad.shape
     w = w_oihw.detach().to(torch.float32).contiguous()
     with _dev(dy_pad):
-        wd = torch.empty((4 * Cin, 4 * Cout), dtype=dy_pad.dtype, device=dy_pad.device)
-        call("ducosy_pack_dgrad_s2_weight", ptr(w), ptr(wd), Cout, Cin, int(ksz), dtype_code(dy_pad.dtype), stream_ptr())
+        def build():
+            wd = torch.empty((4 * Cin, 4 * Cout), dtype=dy_pad.dtype, device=dy_pad.device)
+            call("ducosy_pack_dgrad_s2_weight", ptr(w), ptr(wd), Cout, Cin, int(ksz), dtype_code(dy_pad.dtype), stream_ptr())
+            return wd
+        wd = _cached_pack("dgrad_s2", w_oihw, dy_pad.dtype, build)
         dx = torch.empty((B, 2 * (Hp - 2), 2 * (Wp - 2), Cin), dtype=dy_pad.dtype, device=dy_pad.device)
         call("ducosy_convs2_dgrad_nhwc", ptr(dy_pad), ptr(wd), ptr(dx), B, Hp - 2, Wp - 2, Cin, Cout, dtype_code(dy_pad.dtype),
              stream_ptr())
@@ -331,8 +390,11 @@ def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode, add=None):
     w = w_oihw.detach().to(torch.float32).contiguous()
     dc = dtype_code(dy_pad2.dtype)
     with _dev(dy_pad2):
-        wd = torch.empty((Cin, 9 * Cout), dtype=dy_pad2.dtype, device=dy_pad2.device)
-        call("ducosy_pack_dgrad_s1_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+        def build():
+            wd = torch.empty((Cin, 9 * Cout), dtype=dy_pad2.dtype, device=dy_pad2.device)
+            call("ducosy_pack_dgrad_s1_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+            return wd
+        wd = _cached_pack("dgrad_s1", w_oihw, dy_pad2.dtype, build)
         dxpad = torch.empty((B, H + 2, W + 2, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
         call("ducosy_conv3x3s1_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dxpad), B, H, W, Cin, Cout, dc, stream_ptr())
         dx = torch.empty((B, H, W, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
@@ -366,8 +428,11 @@ def upconv2x_backward(src_pad, dy_pad2, w_oihw, gs=None):
     dt, dc = src_pad.dtype, dtype_code(src_pad.dtype)
     w = w_oihw.detach().to(torch.float32).contiguous()
     with _dev(src_pad):
-        wd = torch.empty((Cin, 16 * Cout), dtype=dt, device=src_pad.device)
-        call("ducosy_pack_upconv_dgrad_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+        def build():
+            wd = torch.empty((Cin, 16 * Cout), dtype=dt, device=src_pad.device)
+            call("ducosy_pack_upconv_dgrad_weight", ptr(w), ptr(wd), Cout, Cin, dc, stream_ptr())
+            return wd
+        wd = _cached_pack("dgrad_upconv", w_oihw, dt, build)
         dsrc = torch.empty((B, Hs, Ws, Cin), dtype=dt, device=src_pad.device)
         call("ducosy_upconv2x_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dsrc), B, Hs, Ws, Cin, Cout, dc, stream_ptr())
         lib = _lib.load()
@@ -423,9 +488,11 @@ def stem_backward(dy, cols, w, gs, want_dx=True):
         dx = None
         if want_dx:
             # dcol[p][k] = sum_o dy[p][o] * w[o][0][k]  (k < 49): a 1x1 conv with "Cout" = 64 columns
-            w1 = torch.zeros((64, 64, 1, 1), dtype=torch.float32, device=dy.device)
-            w1[:49, :, 0, 0] = w.detach().to(torch.float32)[:, 0].reshape(64, 49).t()
-            dcol, _ = conv2d_nhwc(dy, pack_conv_weight(w1, dt), 1, 1, 1, want_stats=False)
+            def build():
+                w1 = torch.zeros((64, 64, 1, 1), dtype=torch.float32, device=dy.device)
+                w1[:49, :, 0, 0] = w.detach().to(torch.float32)[:, 0].reshape(64, 49).t()
+                return _pack_conv_weight_build(w1, dt)
+            dcol, _ = conv2d_nhwc(dy, _cached_pack("stem_dgrad", w, dt, build), 1, 1, 1, want_stats=False)
             dx = torch.empty((B, 1, H, W), dtype=torch.float32, device=dy.device)
             call("ducosy_stem_col2im", ptr(dcol), ptr(dx), ptr(gs), B, H, W, dtype_code(dt), stream_ptr())
     return dw, dx
@@ -471,3 +538,50 @@ def cbam_backward(sv, dout, fc0, fc2, wsa, gs):
              ptr(_f32c(wsa)), ptr(dn), ptr(dfc0), ptr(dfc2), ptr(dwsa), ptr(scratch), ptr(gs), B, H, W, Cn, dtype_code(yb.dtype),
              stream_ptr())
     return dn, [dfc0, dfc2, dwsa]
+
+
+# ------------------------------------------------------------------ stand-alone building blocks (NCHW fp32, reference layout)
+def channel_attention_nchw(x, fc0, fc2):
+    """reference modules/model.py:20-24 on [B,C,H,W] fp32 (both pooling branches)."""
+    B, Cn, H, W = x.shape
+    hidden = fc0.shape[0]
+    x, fc0, fc2 = _f32c(x), _f32c(fc0), _f32c(fc2)
+    lib = _lib.load()
+    with _dev(x):
+        out = torch.empty_like(x)
+        scratch = torch.empty(lib.ducosy_channel_attention_scratch_bytes(B, Cn) // 4, dtype=torch.float32, device=x.device)
+        call("ducosy_channel_attention_nchw", ptr(x), ptr(fc0), ptr(fc2), ptr(out), ptr(scratch), B, Cn, hidden, H, W, stream_ptr())
+    return out
+
+
+def spatial_attention_nchw(x, w):
+    """reference modules/model.py:34-39 on [B,C,H,W] fp32; w = conv.weight [1,2,k,k]."""
+    B, Cn, H, W = x.shape
+    k = w.shape[-1]
+    x, w = _f32c(x), _f32c(w)
+    lib = _lib.load()
+    with _dev(x):
+        out = torch.empty_like(x)
+        scratch = torch.empty(lib.ducosy_spatial_attention_scratch_bytes(B, H, W) // 4, dtype=torch.float32, device=x.device)
+        call("ducosy_spatial_attention_nchw", ptr(x), ptr(w), ptr(out), ptr(scratch), B, Cn, H, W, int(k), stream_ptr())
+    return out
+
+
+def nchw_to_nhwc_pad(x, pad, pad_mode, dtype=torch.float16):
+    """fp32 [B,C,H,W] -> 16-bit [B,H+2p,W+2p,C] (reflect / zero padding)."""
+    B, Cn, H, W = x.shape
+    x = _f32c(x)
+    with _dev(x):
+        out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), dtype=dtype, device=x.device)
+        call("ducosy_nchw_to_nhwc_pad", ptr(x), ptr(out), B, Cn, H, W, int(pad), int(pad_mode), dtype_code(dtype), stream_ptr())
+    return out
+
+
+def nhwc_to_nchw(y):
+    """16-bit [B,H,W,C] -> fp32 [B,C,H,W]."""
+    B, H, W, Cn = y.shape
+    assert y.is_contiguous()
+    with _dev(y):
+        out = torch.empty((B, Cn, H, W), dtype=torch.float32, device=y.device)
+        call("ducosy_nhwc_to_nchw", ptr(y), ptr(out), B, Cn, H, W, dtype_code(y.dtype), stream_ptr())
+    return out

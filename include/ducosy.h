@@ -242,6 +242,24 @@ int ducosy_adam_multi_step(const ducosy_adam_tensor* tensors_dev, const ducosy_a
 /* a += b on 16-bit maps of n elements (n % 8 == 0): the skip connection of modules/model.py:65,87 in the backward. */
 int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream);
 
+/* ---------------------------------------------------------------- stand-alone building blocks (NCHW fp32, the reference's layout)
+ * modules/model.py:6-24  ChannelAttention.forward: out = x * sigmoid(fc(avgpool x) + fc(maxpool x)) with BOTH pooling branches;
+ * fc0 [hidden][C] and fc2 [C][hidden] are the 1x1 conv weights (no bias).  scratch: ducosy_channel_attention_scratch_bytes. */
+size_t ducosy_channel_attention_scratch_bytes(int B, int C);
+int ducosy_channel_attention_nchw(const float* x, const float* fc0, const float* fc2, float* out, float* scratch, int B, int C,
+                                  int hidden, int H, int W, ducosy_stream_t stream);
+/* modules/model.py:27-39  SpatialAttention.forward: out = x * sigmoid(conv_kxk(cat[mean_C x, max_C x])), weight [1][2][k][k],
+ * zero padding k/2, no bias, k odd.  scratch: ducosy_spatial_attention_scratch_bytes. */
+size_t ducosy_spatial_attention_scratch_bytes(int B, int H, int W);
+int ducosy_spatial_attention_nchw(const float* x, const float* w, float* out, float* scratch, int B, int C, int H, int W, int ksize,
+                                  ducosy_stream_t stream);
+/* Layout converters between the reference's NCHW fp32 tensors and the NHWC 16-bit maps of the tensor-core path (used by the
+ * stand-alone ResidualBlock / ResidualBlockWithCBAM forward, modules/model.py:56-87): fp32 [B][C][H][W] -> 16-bit
+ * [B][H+2p][W+2p][C] with reflect / zero padding, and 16-bit [B][H][W][C] -> fp32 [B][C][H][W]. */
+int ducosy_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, int H, int W, int pad, int pad_mode, int dtype,
+                            ducosy_stream_t stream);
+int ducosy_nhwc_to_nchw(const void* y, float* out, int B, int C, int H, int W, int dtype, ducosy_stream_t stream);
+
 /* ---------------------------------------------------------------- whole-generator entry points */
 
 typedef struct {

@@ -229,3 +229,78 @@ def test_modules_deepcopy_and_pickle_after_forward():
         buf.seek(0)
         G3 = torch.load(buf, weights_only=False)
         assert torch.equal(G2(x), y) and torch.equal(G3(x), y) and torch.equal(D2(x), d)
+
+
+def test_batch1_forward_replays_a_cuda_graph_bit_identical_to_eager(monkeypatch):
+    """generate.py:96-97 calls model(x) slice by slice; the eval-mode small-batch call is captured once per shape and
+    replayed.  Same kernels, same buffers layout: the bytes must equal the eager call's, for fresh inputs, after a weight
+    change (the graph reads the re-packed weights), for a second shape, and the returned tensors must not alias."""
+    shapes = orc.generator_param_shapes(1, 2, True)
+    G = _gen(1, 2, True, orc.make_state_dict(shapes, 3, attn_std=0.2))
+    xs = [_x(s, (1, 1, 256, 256)).cuda() for s in (1, 2, 3)]
+    with torch.no_grad():
+        monkeypatch.setenv("DUCOSY_FORWARD_GRAPH", "0")
+        eager = [G(x).clone() for x in xs]
+        monkeypatch.setenv("DUCOSY_FORWARD_GRAPH", "1")
+        got = [G(x) for x in xs]                      # first call captures, the others replay
+        eng = next(iter(G._engines.values()))
+        assert len(eng._graphs) == 1
+        assert all(torch.equal(a, b) for a, b in zip(eager, got))
+        assert got[0].data_ptr() != got[1].data_ptr() and not torch.equal(got[0], got[1])
+        two = torch.cat(xs[:2])
+        assert torch.equal(G(two), torch.cat(eager[:2]))          # another shape: its own graph, batch invariant
+        assert len(eng._graphs) == 2
+        G.load_state_dict(orc.make_state_dict(shapes, 4, attn_std=0.2))
+        after = G(xs[0])
+        monkeypatch.setenv("DUCOSY_FORWARD_GRAPH", "0")
+        assert torch.equal(after, G(xs[0])) and not torch.equal(after, eager[0])
+        G.train()
+        monkeypatch.setenv("DUCOSY_FORWARD_GRAPH", "1")
+        assert torch.equal(G(xs[0]), after)           # train mode: eager launches, same result (no dropout / running stats)
+
+
+# ------------------------------------------------------------------ stand-alone building blocks (reference modules/model.py:6-87)
+def test_channel_and_spatial_attention_modules_match_oracle():
+    """ChannelAttention / SpatialAttention / CBAM called on their own (NCHW fp32, both pooling branches, inputs that are NOT
+    behind an InstanceNorm so the avg branch matters): fp32 kernels, 1e-5 against the oracle."""
+    from ducosy_gan_b200.modules.model import CBAM, ChannelAttention, SpatialAttention
+    torch.manual_seed(0)
+    for C, r, k, B, H, W in [(256, 16, 7, 2, 32, 48), (64, 8, 3, 1, 17, 23), (48, 16, 7, 3, 8, 8)]:
+        x = torch.randn(B, C, H, W) * 1.5 + 0.7
+        ca, sa, cb = ChannelAttention(C, r).cuda(), SpatialAttention(k).cuda(), CBAM(C, r, k).cuda()
+        with torch.no_grad():
+            for m in (ca, sa, cb):
+                for p in m.parameters():
+                    p.normal_(0, 0.2)
+            y_ca, y_sa, y_cb = ca(x.cuda()).cpu(), sa(x.cuda()).cpu(), cb(x.cuda()).cpu()
+            cpu = lambda t: t.detach().cpu()
+            r_ca = orc.channel_attention(x, cpu(ca.fc[0].weight), cpu(ca.fc[2].weight))
+            r_sa = orc.spatial_attention(x, cpu(sa.conv.weight))
+            r_cb = orc.spatial_attention(orc.channel_attention(x, cpu(cb.channel_attention.fc[0].weight), cpu(cb.channel_attention.fc[2].weight)),
+                                         cpu(cb.spatial_attention.conv.weight))
+        for got, ref, name in ((y_ca, r_ca, "channel"), (y_sa, r_sa, "spatial"), (y_cb, r_cb, "cbam")):
+            err = (got - ref).abs().max().item() / ref.abs().max().item()
+            assert err < 1e-5, (name, C, err)
+    with pytest.raises(RuntimeError):
+        ca(x.cuda().requires_grad_(True))            # forward-only on their own: loud, not silent
+
+
+@pytest.mark.parametrize("cbam", [True, False])
+def test_residual_block_modules_match_oracle(cbam):
+    """BASELINE config 5 call: ResidualBlockWithCBAM(256)(randn(B,256,128,128)) (and the plain ResidualBlock) through the
+    tensor-core path, against oracle.residual_block: 16-bit operands, stated tolerance of the generator tests."""
+    from ducosy_gan_b200.modules.model import ResidualBlock, ResidualBlockWithCBAM
+    torch.manual_seed(3)
+    blk = (ResidualBlockWithCBAM if cbam else ResidualBlock)(256).cuda()
+    with torch.no_grad():
+        for n, p in blk.named_parameters():
+            p.normal_(0, 0.2 if "cbam" in n else 0.02)
+    sd = {f"m.{k}": v.detach().cpu() for k, v in blk.state_dict().items()}
+    for B, H, W in [(2, 128, 128), (1, 32, 64)]:
+        x = torch.randn(B, 256, H, W)
+        with torch.no_grad():
+            y = blk(x.cuda()).cpu()
+            ref = orc.residual_block(x, sd, "m", cbam)
+        err = (y - ref).abs().max().item()
+        print(f"residual block cbam={cbam} {B}x256x{H}x{W}: max abs err {err:.3e} (|ref| max {ref.abs().max().item():.2f})")
+        assert y.shape == ref.shape and err < 1.5e-2
