@@ -109,6 +109,11 @@ SIGNATURES = {
     "ducosy_spatial_attention_nchw": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_nchw_to_nhwc_pad": (_i, [_p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_nhwc_to_nchw": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
+    "ducosy_masks_scratch_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_label4": (_i, [_p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "ducosy_binary_fill_holes": (_i, [_p, _p, _i, _i, _i, _p, _sz, _p]),
+    "ducosy_detect_lung": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _sz, _p]),
+    "ducosy_detect_lung_vessels": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _sz, _p]),
     "ducosy_adam_multi_step": (_i, [_p, _p, _i, _p, _f, _f, _f, _i, _p]),
     "ducosy_cbam_channel_train": (_i, [_p] * 9 + [_i, _i, _p]),
     "ducosy_cbam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),

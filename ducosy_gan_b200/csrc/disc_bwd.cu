@@ -118,12 +118,24 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
   }
 }
 
-__global__ void in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int blocks, int C, float inv_hw) {
+// grid (ceil(2C / 32), B), 256 threads = 32 columns x 8 slices of the partial rows; fixed-order double sums (deterministic).
+// (One thread per column walking all rows serially was fine for 32 rows; with the finer reduction grid of small batches
+// -- up to 256 rows for one 128x128 sample -- it became the longest kernel of the InstanceNorm backward.)
+__global__ void __launch_bounds__(256)
+in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int blocks, int C, float inv_hw) {
+  __shared__ double part[8][33];
   const int b = blockIdx.y;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 2 * C; i += gridDim.x * blockDim.x) {
-    double acc = 0.0;
-    for (int k = 0; k < blocks; ++k) acc += double(partial[(size_t(b) * blocks + k) * 2 * C + i]);
-    sums[size_t(b) * 2 * C + i] = float(acc * inv_hw);   // means
+  const int col = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
+  double acc = 0.0;
+  if (col < 2 * C)
+    for (int k = slice; k < blocks; k += 8) acc += double(partial[(size_t(b) * blocks + k) * 2 * C + col]);
+  part[slice][threadIdx.x & 31] = acc;
+  __syncthreads();
+  if (slice == 0 && col < 2 * C) {
+    double t = 0.0;
+#pragma unroll
+    for (int s = 0; s < 8; ++s) t += part[s][threadIdx.x];
+    sums[size_t(b) * 2 * C + col] = float(t * inv_hw);   // means
   }
 }
 
@@ -711,7 +723,7 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
   DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T><<<dim3(blocks, B), 256, smem, st>>>(
                                       static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb)));
   DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
-  in_bwd_finalize_kernel<<<dim3((2 * C + 255) / 256, B), 256, 0, st>>>(partial, means, blocks, C, 1.0f / float(HW));
+  in_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, B), 256, 0, st>>>(partial, means, blocks, C, 1.0f / float(HW));
   DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
   const int row_ctas = std::max(1, std::min(H + 2 * pad, (num_sms() * 4 + B - 1) / B));
   DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_pad_kernel<T><<<dim3(row_ctas, B), 256, 0, st>>>(

@@ -142,33 +142,16 @@ class DataParallelCycleGANStep(CycleGANStep):
         self.bucket_D_B = GradBucket(list(self.D_B.parameters()))
         self._checked_batch = None
 
-    def generator_losses(self, real_A, real_B, masks=None):
+    def _batch_global_losses(self, fake_B, real_B, real_A):
+        """Region / edge terms on the all-gathered batch, identical on every rank.  Their weight in the differentiated
+        expression is ``world`` -- a BACKWARD SURROGATE, not a logged loss: full-batch terms x world, then the mean-all-reduce of
+        the gradients, gives exactly the single-process gradient (module docstring).  step() reports logged_losses()."""
         if self.world == 1:
-            return super().generator_losses(real_A, real_B, masks)
-        # identical to CycleGANStep.generator_losses except that the two batch-global criteria see the gathered batch
-        cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
-        real_A_input, real_B_input = cat(real_A), cat(real_B)
-        fake_B, fake_A, id_A, id_B = self._translate_and_identity(real_A_input, real_B_input)
-        loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
-        loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
-        rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
-        loss_cycle = (l1_loss(rec_A, real_A) + l1_loss(rec_B, real_B)) / 2
-        loss_grad_cycle = (self.criterion_gradient(rec_A, real_A) + self.criterion_gradient(rec_B, real_B)) / 2
-        loss_grad_id = (self.criterion_gradient(id_A, real_A) + self.criterion_gradient(id_B, real_B)) / 2
-        loss_ssim = 1 - ((self.criterion_ssim(rec_A, real_A) + self.criterion_ssim(rec_B, real_B)) / 2)
-        loss_att = self.criterion_contrast_attention(fake_B, real_B, real_A)
+            return super()._batch_global_losses(fake_B, real_B, real_A)
         g = self.group
         fake_B_all, real_B_all, real_A_all = all_gather_batch(fake_B, g), all_gather_batch(real_B, g), all_gather_batch(real_A, g)
-        loss_region = self.criterion_contrast_region(fake_B_all, real_B_all, real_A_all)
-        loss_edge = self.criterion_contrast_edge(fake_B_all, real_B_all, real_A_all)
-        # BACKWARD SURROGATE, not the logged loss: full-batch terms x world, then mean-all-reduce of the gradients gives
-        # exactly the single-process gradient (module docstring).  step() reports logged_losses() instead.
-        w = float(self.world)
-        loss_G = (loss_GAN + self.lambda_cyc * loss_cycle + self.lambda_id * loss_id + 5.0 * loss_grad_cycle + 2.5 * loss_grad_id
-                  + 2.0 * loss_ssim + 2.0 * loss_att + w * (1.5 * loss_region + 1.0 * loss_edge))
-        terms = dict(GAN=loss_GAN, cycle=loss_cycle, id=loss_id, grad_cycle=loss_grad_cycle, grad_id=loss_grad_id, ssim=loss_ssim,
-                     contrast_attention=loss_att, contrast_region=loss_region, contrast_edge=loss_edge)
-        return loss_G, terms, fake_A, fake_B
+        return (self.criterion_contrast_region(fake_B_all, real_B_all, real_A_all),
+                self.criterion_contrast_edge(fake_B_all, real_B_all, real_A_all), float(self.world))
 
     def step(self, real_A, real_B, masks=None):
         """real_A / real_B / masks are this rank's shard of the batch (equal shards on every rank).  Returns the losses the

@@ -40,37 +40,86 @@ class CycleGANStep:
         self.optimizer_D_A = Adam(self.D_A.parameters(), lr=lr, betas=(0.5, 0.999), capturable=capturable)
         self.optimizer_D_B = Adam(self.D_B.parameters(), lr=lr, betas=(0.5, 0.999), capturable=capturable)
         self.lambda_cyc, self.lambda_id = lambda_cyc, lambda_id
+        self._streams = {}
         self.grad_hook = None   # optional callable(list of params) run before each optimizer.step (data-parallel all-reduce)
 
+    def _side_streams(self, device):
+        """Two side streams, one per generator (DUCOSY_TRAIN_STREAMS=1 runs everything on the caller's stream).  G_A2B and
+        G_B2A are independent in the translation / identity pass and again in the cycle pass, and a generator pass alternates
+        tensor-core convolutions with bandwidth-bound normalisation / padding kernels, so two passes side by side fill each
+        other's gaps -- the more so the smaller the per-rank batch.  Autograd runs every backward node on the stream of its
+        forward, so the backward is two-stream as well; a CUDA-graph capture keeps the fork / join structure."""
+        import os
+        if os.environ.get("DUCOSY_TRAIN_STREAMS", "2") == "1" or device.type != "cuda":
+            return None
+        key = device.index if device.index is not None else torch.cuda.current_device()
+        if key not in self._streams:
+            with torch.cuda.device(key):
+                self._streams[key] = (torch.cuda.Stream(), torch.cuda.Stream())
+        return self._streams[key]
+
+    def _batch_global_losses(self, fake_B, real_B, real_A):
+        """The two criteria that take statistics over the WHOLE batch tensor (trainer.py:117-127,163-181); returns
+        (loss_region, loss_edge, weight of the pair in the expression that is differentiated).  The data-parallel step
+        overrides this (gathered batch, weight = world)."""
+        return (self.criterion_contrast_region(fake_B, real_B, real_A), self.criterion_contrast_edge(fake_B, real_B, real_A), 1.0)
+
     def generator_losses(self, real_A, real_B, masks=None):
-        """trainer.py:447-512: returns (loss_G, dict of the individual terms, fake_A, fake_B)."""
+        """trainer.py:447-512: returns (loss_G, dict of the individual terms, fake_A, fake_B).
+
+        Scheduling differences, with identical per-sample results: where the reference calls the same network twice on
+        independent inputs (translation + identity, trainer.py:464-467) the two inputs go through as one batch of 2B (the
+        kernels are batch invariant), and the two generators run on two side streams (``_side_streams``)."""
         cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
         real_A_input, real_B_input = cat(real_A), cat(real_B)
-        fake_B, fake_A, id_A, id_B = self._translate_and_identity(real_A_input, real_B_input)
+        B = real_A.shape[0]
+        streams = self._side_streams(real_A.device)
+        if streams is None:
+            ab = self.G_A2B(torch.cat([real_A_input, real_B_input], dim=0))
+            ba = self.G_B2A(torch.cat([real_B_input, real_A_input], dim=0))
+            fake_B, id_B, fake_A, id_A = ab[:B], ab[B:], ba[:B], ba[B:]
+            rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
+            join = lambda: None
+        else:
+            cur = torch.cuda.current_stream()
+            s1, s2 = streams                       # s1: every G_A2B pass, s2: every G_B2A pass
+            s1.wait_stream(cur)
+            s2.wait_stream(cur)
+            with torch.cuda.stream(s1):
+                ab = self.G_A2B(torch.cat([real_A_input, real_B_input], dim=0))
+                e1 = s1.record_event()
+            with torch.cuda.stream(s2):
+                ba = self.G_B2A(torch.cat([real_B_input, real_A_input], dim=0))
+                e2 = s2.record_event()
+            fake_B, id_B, fake_A, id_A = ab[:B], ab[B:], ba[:B], ba[B:]
+            ab.record_stream(cur), ab.record_stream(s2), ba.record_stream(cur), ba.record_stream(s1)
+            s1.wait_event(e2)                      # the cycle pass of each generator reads the other one's translation
+            s2.wait_event(e1)
+            with torch.cuda.stream(s2):
+                rec_A = self.G_B2A(cat(fake_B))
+            with torch.cuda.stream(s1):
+                rec_B = self.G_A2B(cat(fake_A))
+            rec_A.record_stream(cur), rec_B.record_stream(cur)
+            cur.wait_event(e1)                     # identity / adversarial / contrast terms overlap the cycle passes
+            cur.wait_event(e2)
+
+            def join():
+                cur.wait_stream(s1)
+                cur.wait_stream(s2)
         loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
         loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
-        rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
+        loss_grad_id = (self.criterion_gradient(id_A, real_A) + self.criterion_gradient(id_B, real_B)) / 2
+        loss_att = self.criterion_contrast_attention(fake_B, real_B, real_A)
+        loss_region, loss_edge, w_global = self._batch_global_losses(fake_B, real_B, real_A)
+        join()
         loss_cycle = (l1_loss(rec_A, real_A) + l1_loss(rec_B, real_B)) / 2
         loss_grad_cycle = (self.criterion_gradient(rec_A, real_A) + self.criterion_gradient(rec_B, real_B)) / 2
-        loss_grad_id = (self.criterion_gradient(id_A, real_A) + self.criterion_gradient(id_B, real_B)) / 2
         loss_ssim = 1 - ((self.criterion_ssim(rec_A, real_A) + self.criterion_ssim(rec_B, real_B)) / 2)
-        loss_att = self.criterion_contrast_attention(fake_B, real_B, real_A)
-        loss_region = self.criterion_contrast_region(fake_B, real_B, real_A)
-        loss_edge = self.criterion_contrast_edge(fake_B, real_B, real_A)
         loss_G = (loss_GAN + self.lambda_cyc * loss_cycle + self.lambda_id * loss_id + 5.0 * loss_grad_cycle + 2.5 * loss_grad_id
-                  + 2.0 * loss_ssim + 2.0 * loss_att + 1.5 * loss_region + 1.0 * loss_edge)
+                  + 2.0 * loss_ssim + 2.0 * loss_att + w_global * (1.5 * loss_region + 1.0 * loss_edge))
         terms = dict(GAN=loss_GAN, cycle=loss_cycle, id=loss_id, grad_cycle=loss_grad_cycle, grad_id=loss_grad_id, ssim=loss_ssim,
                      contrast_attention=loss_att, contrast_region=loss_region, contrast_edge=loss_edge)
         return loss_G, terms, fake_A, fake_B
-
-    def _translate_and_identity(self, real_A_input, real_B_input):
-        """trainer.py:464-467: fake_B, fake_A = G_A2B(A), G_B2A(B); id_A, id_B = G_B2A(A), G_A2B(B).  Each generator sees its two
-        inputs as ONE batch of 2B samples (InstanceNorm is per sample and the kernels are batch-invariant, so every sample's
-        output and gradient are what the two separate calls give; half the launches, twice the work per launch)."""
-        B = real_A_input.shape[0]
-        ab = self.G_A2B(torch.cat([real_A_input, real_B_input], dim=0))
-        ba = self.G_B2A(torch.cat([real_B_input, real_A_input], dim=0))
-        return ab[:B], ba[:B], ba[B:], ab[B:]
 
     def _disc_loss(self, D, real, fake):
         """trainer.py:518 / :523: (MSE(D(real), valid) + MSE(D(fake.detach()), fake)) / 2, both images in one batch of 2B."""

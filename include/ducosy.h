@@ -260,6 +260,30 @@ int ducosy_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, int H, int 
                             ducosy_stream_t stream);
 int ducosy_nhwc_to_nchw(const void* y, float* out, int B, int C, int H, int W, int dtype, ducosy_stream_t stream);
 
+/* ---------------------------------------------------------------- anatomical masks for training batches (first half)
+ * The scipy.ndimage pieces of modules/mask_generator.py for batches of 2-D slices [B][H][W], bit-exact with scipy.
+ * All four need `scratch` of ducosy_masks_scratch_bytes(B, H, W) bytes (256-byte aligned); B*H*W < 2^31.
+ *
+ * ducosy_label4: scipy.ndimage.label with the default structure (4-connectivity) per slice -- labels int32 [B][H][W] numbered
+ * in raster order of each component's first pixel (scipy's numbering), num_features int32 [B] (may be NULL).
+ * mask_generator.py:32,46,64,85,109,190,232. */
+size_t ducosy_masks_scratch_bytes(int B, int H, int W);
+int ducosy_label4(const uint8_t* mask, int32_t* labels, int32_t* num_features, int B, int H, int W, void* scratch,
+                  size_t scratch_bytes, ducosy_stream_t stream);
+/* scipy.ndimage.binary_fill_holes, default structure: background components (4-connectivity) that do not reach the slice
+ * border become foreground.  out uint8 {0,1}.  mask_generator.py:69,90,242,310. */
+int ducosy_binary_fill_holes(const uint8_t* mask, uint8_t* out, int B, int H, int W, void* scratch, size_t scratch_bytes,
+                             ducosy_stream_t stream);
+/* detect_lung (mask_generator.py:11-52): (lung_lower <= hu <= lung_upper) & (hu > -1000), `border_margin` rows / columns
+ * cleared on every side, components smaller than `min_size` pixels removed.  hu fp32 [B][H][W] -> uint8 {0,1}. */
+int ducosy_detect_lung(const float* hu, uint8_t* lung_mask, int B, int H, int W, float lung_lower, float lung_upper, int min_size,
+                       int border_margin, void* scratch, size_t scratch_bytes, ducosy_stream_t stream);
+/* detect_lung_vessels (mask_generator.py:55-99): on slices with >= 2 lung components, body_area > 0 and
+ * lung_area / body_area >= 0.1 (float64), (binary_fill_holes(lung) - lung) & (vessel_lower <= hu <= vessel_upper); zero on the
+ * other slices. */
+int ducosy_detect_lung_vessels(const float* hu, const uint8_t* lung_mask, uint8_t* vessel_mask, int B, int H, int W,
+                               float vessel_lower, float vessel_upper, void* scratch, size_t scratch_bytes, ducosy_stream_t stream);
+
 /* ---------------------------------------------------------------- whole-generator entry points */
 
 typedef struct {

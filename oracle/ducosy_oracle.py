@@ -511,3 +511,95 @@ def cyclegan_step(sds, opts, real_A, real_B, masks=None, num_residual_blocks=9, 
     out = {k: float(v.detach()) for k, v in t.items()}
     out.update(G=float(loss_G.detach()), D_A=float(loss_DA.detach()), D_B=float(loss_DB.detach()))
     return out
+
+
+# --------------------------------------------------------------------------------------
+# anatomical masks (first half) -- modules/mask_generator.py restated with the same scipy calls
+# PINNED: oracle/make_golden_masks.py runs the reference's own detect_lung / detect_lung_vessels (matplotlib.path stubbed: those
+# two functions never touch it) on mask_test_slices() and stores the masks in tests/golden/masks.npz.
+# --------------------------------------------------------------------------------------
+def mask_test_slices(B: int, H: int = 256, W: int = 256, seed: int = 0) -> np.ndarray:
+    """HU slices (float32, as modules/dataset.py:112-113 builds them) that exercise every branch of the mask code: a chest
+    phantom with two lungs, vessel-like discs and a few air pockets inside them (holes for binary_fill_holes), speckle
+    components below and above min_size, structures inside the border margin, one slice with a single lung (fails the
+    ">= 2 regions" test) and one empty slice."""
+    rng = np.random.Generator(np.random.PCG64(seed + 4242))
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cy, cx = H / 2, W / 2
+    out = np.empty((B, H, W), np.float32)
+    for b in range(B):
+        hu = np.full((H, W), -1000.0, np.float32)
+        if b % 5 != 4:                                                # every fifth slice stays empty air
+            body = ((yy - cy) / (0.40 * H)) ** 2 + ((xx - cx) / (0.46 * W)) ** 2 <= 1
+            hu[body] = 40 + 30 * rng.standard_normal(int(body.sum())).astype(np.float32)
+            sides = (-1, 1) if b % 5 != 3 else (1,)                   # slice 3: one lung only
+            for sgn in sides:
+                lung = ((yy - cy) / (0.24 * H)) ** 2 + ((xx - (cx + sgn * 0.21 * W)) / (0.15 * W)) ** 2 <= 1
+                hu[lung] = -800 + 60 * rng.standard_normal(int(lung.sum())).astype(np.float32)
+                for _ in range(6):                                    # vessels / nodules and air pockets inside the lung
+                    vy = cy + rng.uniform(-0.18, 0.18) * H
+                    vx = cx + sgn * 0.21 * W + rng.uniform(-0.09, 0.09) * W
+                    r = rng.uniform(1.5, 6.0)
+                    disc = (yy - vy) ** 2 + (xx - vx) ** 2 <= r * r
+                    hu[disc] = rng.choice(np.array([60.0, 300.0, 700.0, -1000.0, -250.0], np.float32))
+            for _ in range(40):                                       # lung-range speckle of 1..120 pixels anywhere (also in the margin)
+                sy, sx = int(rng.integers(0, H - 12)), int(rng.integers(0, W - 12))
+                hh, ww = int(rng.integers(1, 11)), int(rng.integers(1, 13))
+                hu[sy:sy + hh, sx:sx + ww] = -600.0
+        out[b] = hu
+    return out
+
+
+def mask_label4(mask: np.ndarray):
+    """scipy.ndimage.label with the default structure on every slice of [B,H,W] (mask_generator.py:32): (labels int32, counts)."""
+    from scipy import ndimage
+    labels = np.zeros(mask.shape, np.int32)
+    nums = np.zeros(mask.shape[0], np.int32)
+    for z in range(mask.shape[0]):
+        labels[z], nums[z] = ndimage.label(mask[z])
+    return labels, nums
+
+
+def mask_fill_holes(mask: np.ndarray) -> np.ndarray:
+    """scipy.ndimage.binary_fill_holes on every slice (mask_generator.py:69)."""
+    from scipy import ndimage
+    return np.stack([ndimage.binary_fill_holes(m).astype(np.uint8) for m in mask])
+
+
+def mask_detect_lung(hu: np.ndarray, lung_lower=-1000, lung_upper=-300, min_size=64, border_margin=32) -> np.ndarray:
+    """modules/mask_generator.py:11-52 (3-D branch: every slice on its own)."""
+    from scipy import ndimage
+    body_mask = (hu > -1000).astype(np.uint8)                                            # :14
+    lung_hu_mask = np.logical_and(hu >= lung_lower, hu <= lung_upper).astype(np.uint8)   # :17
+    lung_mask = np.logical_and(lung_hu_mask, body_mask).astype(np.uint8)                 # :20
+    _, height, width = lung_mask.shape
+    lung_mask[:, :border_margin, :] = 0                                                  # :40-43
+    lung_mask[:, height - border_margin:, :] = 0
+    lung_mask[:, :, :border_margin] = 0
+    lung_mask[:, :, width - border_margin:] = 0
+    for z in range(lung_mask.shape[0]):                                                  # :45-50
+        labeled, n = ndimage.label(lung_mask[z])
+        sizes = np.bincount(labeled.ravel(), minlength=n + 1)
+        small = np.flatnonzero(sizes < min_size)
+        small = small[small > 0]
+        lung_mask[z][np.isin(labeled, small)] = 0
+    return lung_mask
+
+
+def mask_detect_lung_vessels(hu: np.ndarray, lung_mask: np.ndarray, vessel_lower=-300, vessel_upper=600) -> np.ndarray:
+    """modules/mask_generator.py:55-99 (3-D branch)."""
+    from scipy import ndimage
+    body_mask = (hu > -1000).astype(np.uint8)
+    vessel = np.zeros_like(lung_mask, dtype=np.uint8)
+    for z in range(lung_mask.shape[0]):
+        lung_slice, body_slice = lung_mask[z], body_mask[z]
+        _, num = ndimage.label(lung_slice)                                               # :85
+        body_area, lung_area = body_slice.sum(), lung_slice.sum()
+        if num >= 2 and body_area > 0 and (lung_area / body_area) >= 0.1:                # :89
+            filled = ndimage.binary_fill_holes(lung_slice).astype(np.uint8)
+            cand = filled - lung_slice
+        else:
+            cand = np.zeros_like(lung_slice)
+        cond = np.logical_and(hu[z] >= vessel_lower, hu[z] <= vessel_upper)              # :96
+        vessel[z] = np.logical_and(cand, cond).astype(np.uint8)
+    return vessel

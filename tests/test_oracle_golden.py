@@ -164,3 +164,16 @@ def test_cyclegan_step_matches_reference_loop_body(golden_dir):
             # size, so fp32 noise on near-zero gradient entries flips a few of them (measured 3e-4 on one term): 2e-3
             tol = 1e-5 if it == 0 else 2e-3
             assert abs(out[k] - ref) <= tol * abs(ref) + 1e-6, (it, k, out[k], ref)
+
+
+def test_oracle_masks_match_reference_golden(golden_dir):
+    """SURVEY 8f N2 (first half): the oracle's restatement of modules/mask_generator.py:detect_lung / detect_lung_vessels against
+    the masks the reference's own functions produced (oracle/make_golden_masks.py)."""
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    for name in "ab":
+        B, H, W, seed = (int(v) for v in g[f"shape_{name}"])
+        hu = orc.mask_test_slices(B, H, W, seed)
+        unpack = lambda key: np.unpackbits(g[key])[: B * H * W].reshape(B, H, W)
+        lung = orc.mask_detect_lung(hu)
+        assert np.array_equal(lung, unpack(f"lung_{name}"))
+        assert np.array_equal(orc.mask_detect_lung_vessels(hu, lung), unpack(f"vessel_{name}"))
