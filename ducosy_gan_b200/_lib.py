@@ -50,6 +50,7 @@ SIGNATURES = {
     "ducosy_cbam_pool": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_cbam_spatial_conv": (_i, [_p, _p, _p, _i, _i, _i, _p]),
     "ducosy_residual_apply_pad": (_i, [_p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_residual_cbam_apply_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_out_weight": (_i, [_p, _p, _i, _p]),
     "ducosy_out_conv7x7_tanh": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _p]),
     "ducosy_out_conv7x7_tanh_fused": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

@@ -109,7 +109,7 @@ GenLayout make_layout(const ducosy_gen_config& c) {
 }
 
 struct GenWorkspace {
-  size_t a_stem, y0, p0, y1, p1, y2a, y2b, pa, pb, pc, p_out, partials, scale, shift, chmax, pooled, sa, total;
+  size_t a_stem, y0, p0, y1, p1, y2a, y2b, pa, pb, pc, p_out, partials, scale, shift, chmax, pooled, sa, tickets, total;
 };
 
 GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
@@ -141,6 +141,7 @@ GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
   w.chmax = take(size_t(B) * 256 * 4);
   w.pooled = take(size_t(B) * H4 * W4 * 2 * 4);
   w.sa = take(size_t(B) * H4 * W4 * 4);
+  w.tickets = take(size_t(B) * 4);
   w.total = off;
   return w;
 }
@@ -159,11 +160,38 @@ int check_gen_shape(const ducosy_gen_config& c, int B, int H, int W) {
   return 0;
 }
 
-int run_conv_in(ConvPlan& p, float* scale, float* shift, const float* fc0, const float* fc2, float* chmax, int C,
+// conv + InstanceNorm statistics + finalize (+ CBAM channel MLP) in ONE launch: the CTA that completes a sample's last tile
+// reduces the per-tile partials (conv_gemm.cu: finalize_sample)
+int run_conv_in(ConvPlan& p, float* scale, float* shift, const float* fc0, const float* fc2, float* chmax, int* tickets,
                 int npix, cudaStream_t st) {
-  DUCOSY_TRY(launch_conv_gemm(p, st));
-  return ducosy_in_finalize(p.partials, conv_tiles_per_sample(p.num_phases, p.Hg, p.Wg), npix, scale, shift, fc0, fc2,
-                            chmax, p.B, C, st);
+  p.fin.scale = scale; p.fin.shift = shift; p.fin.chmax = chmax; p.fin.fc0 = fc0; p.fin.fc2 = fc2;
+  p.fin.counter = tickets; p.fin.npix = npix;
+  return launch_conv_gemm(p, st);
+}
+
+void upconv_plan(ConvPlan& p, const void* in_pad, const void* w_packed4, void* out, float* partials, int B, int Hs, int Ws,
+                 int Cin, int Cout, int dtype) {
+  p.in = in_pad; p.B = B; p.Hp = Hs + 2; p.Wp = Ws + 2; p.Cin = Cin; p.stride = 1;
+  p.w = w_packed4; p.Cout = Cout; p.num_phases = 4; p.num_taps = 4;
+  for (int ph = 0; ph < 4; ++ph) {
+    const int py = ph >> 1, px = ph & 1;
+    for (int t = 0; t < 4; ++t) {
+      p.tap_dy[ph][t] = int8_t((t >> 1) + py);   // source row i + a + py - 1, +1 for the zero border
+      p.tap_dx[ph][t] = int8_t((t & 1) + px);
+    }
+    p.oy_off[ph] = int8_t(py);
+    p.ox_off[ph] = int8_t(px);
+  }
+  p.Hg = Hs; p.Wg = Ws; p.out = out; p.Ho = 2 * Hs; p.Wo = 2 * Ws; p.oy_mul = p.ox_mul = 2;
+  p.partials = partials; p.dtype = dtype;
+}
+
+void upconv_merged_plan(ConvPlan& p, const void* in_pad, const void* w_merged, void* out, float* partials, int B, int Hs,
+                        int Ws, int Cin, int Cout, int dtype) {
+  p.in = in_pad; p.B = B; p.Hp = Hs + 2; p.Wp = Ws + 2; p.Cin = Cin; p.stride = 1;
+  p.w = w_merged; p.Cout = 4 * Cout; p.fold = 4; fill_taps_3x3(p);
+  p.Hg = Hs; p.Wg = Ws; p.out = out; p.Ho = 2 * Hs; p.Wo = 2 * Ws; p.oy_mul = p.ox_mul = 2;
+  p.partials = partials; p.dtype = dtype;
 }
 
 int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const float* x, const int16_t* px,
@@ -186,7 +214,8 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   float* shift = reinterpret_cast<float*>(base + w.shift);
   float* chmax = reinterpret_cast<float*>(base + w.chmax);
   float* pooled = reinterpret_cast<float*>(base + w.pooled);
-  float* sa = reinterpret_cast<float*>(base + w.sa);
+  int* tickets = reinterpret_cast<int*>(base + w.tickets);
+  DUCOSY_CHECK(cudaMemsetAsync(tickets, 0, size_t(B) * 4, st) == cudaSuccess, DUCOSY_ERR_CUDA, "generator_forward: cudaMemsetAsync failed");
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
   const int nb = c.num_residual_blocks;
   const int dt = c.dtype;
@@ -211,7 +240,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
       p.w = pk + L.stem; p.Cout = 64; p.num_phases = 1; p.num_taps = 1;
       p.Hg = H; p.Wg = W; p.out = P(w.y0); p.Ho = H; p.Wo = W; p.oy_mul = p.ox_mul = 1;
       p.partials = partials; p.dtype = dt;
-      DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 64, H * W, st));
+      DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H * W, st));
       DUCOSY_TRY(ducosy_in_apply_pad(P(w.y0), scale, shift, P(w.p0), B, H, W, 64, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
     }
   }
@@ -222,7 +251,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.d1; p.Cout = 128; fill_taps_3x3(p);
     p.Hg = H2; p.Wg = W2; p.out = P(w.y1); p.Ho = H2; p.Wo = W2; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 128, H2 * W2, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H2 * W2, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y1), scale, shift, P(w.p1), B, H2, W2, 128, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   }
   // ---- down 2: 3x3 s2 p1 128 -> 256, IN, ReLU
@@ -233,7 +262,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.d2; p.Cout = 256; fill_taps_3x3(p);
     p.Hg = H4; p.Wg = W4; p.out = P(w.y2a); p.Ho = H4; p.Wo = W4; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 256, H4 * W4, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H4 * W4, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y2a), scale, shift, P(cur), B, H4, W4, 256, 1,
                                    nb > 0 ? DUCOSY_PAD_REFLECT : DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   }
@@ -244,29 +273,36 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     p.w = pk + L.c1[i]; p.Cout = 256; fill_taps_3x3(p);
     p.Hg = H4; p.Wg = W4; p.out = P(w.y2a); p.Ho = H4; p.Wo = W4; p.oy_mul = p.ox_mul = 1;
     p.partials = partials; p.dtype = dt;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, 256, H4 * W4, st));
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H4 * W4, st));
     DUCOSY_TRY(ducosy_in_apply_pad(P(w.y2a), scale, shift, P(w.pc), B, H4, W4, 256, 1, DUCOSY_PAD_REFLECT, DUCOSY_ACT_RELU, dt, st));
     p.in = P(w.pc); p.w = pk + L.c2[i]; p.out = P(w.y2b);
     const float* fc0 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc0[i]) : nullptr;
     const float* fc2 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc2[i]) : nullptr;
-    DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, chmax, 256, H4 * W4, st));
-    const float* sa_ptr = nullptr;
-    if (c.use_cbam) {
-      DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
-      DUCOSY_TRY(ducosy_cbam_spatial_conv(pooled, reinterpret_cast<const float*>(pk + L.saw[i]), sa, B, H4, W4, st));
-      sa_ptr = sa;
-    }
+    DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, c.use_cbam ? chmax : nullptr, tickets, H4 * W4, st));
     const int mode = i + 1 < nb ? DUCOSY_PAD_REFLECT : DUCOSY_PAD_ZERO;  // the decoder convs zero-pad
-    DUCOSY_TRY(ducosy_residual_apply_pad(P(w.y2b), scale, shift, sa_ptr, P(cur), 1, P(nxt), B, H4, W4, 256, 1, mode, dt, st));
+    if (c.use_cbam) {
+      // spatial attention: channel mean / max of the attended map, then the 7x7 conv + sigmoid inside the residual pass
+      DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
+      DUCOSY_TRY(ducosy_residual_cbam_apply_pad(P(w.y2b), scale, shift, pooled, reinterpret_cast<const float*>(pk + L.saw[i]), P(cur), 1,
+                                                P(nxt), B, H4, W4, 256, 1, mode, dt, st));
+    } else {
+      DUCOSY_TRY(ducosy_residual_apply_pad(P(w.y2b), scale, shift, nullptr, P(cur), 1, P(nxt), B, H4, W4, 256, 1, mode, dt, st));
+    }
     const size_t t = cur; cur = nxt; nxt = t;
   }
   // ---- up 1: nearest x2 + 3x3 p1 256 -> 128, IN, ReLU   modules/model.py:107-111
-  DUCOSY_TRY(ducosy_upconv2x_nhwc(P(cur), pk + L.up1, P(w.y1), partials, B, H4, W4, 256, 128, dt, st));
-  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(4, H4, W4), H2 * W2, scale, shift, nullptr, nullptr, nullptr, B, 128, st));
+  {
+    ConvPlan p{};
+    upconv_plan(p, P(cur), pk + L.up1, P(w.y1), partials, B, H4, W4, 256, 128, dt);
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H2 * W2, st));
+  }
   DUCOSY_TRY(ducosy_in_apply_pad(P(w.y1), scale, shift, P(w.p1), B, H2, W2, 128, 1, DUCOSY_PAD_ZERO, DUCOSY_ACT_RELU, dt, st));
   // ---- up 2: nearest x2 + 3x3 p1 128 -> 64, IN, ReLU
-  DUCOSY_TRY(ducosy_upconv2x_merged_nhwc(P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt, st));
-  DUCOSY_TRY(ducosy_in_finalize(partials, conv_tiles_per_sample(1, H2, W2), H * W, scale, shift, nullptr, nullptr, nullptr, B, 64, st));
+  {
+    ConvPlan p{};
+    upconv_merged_plan(p, P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt);
+    DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H * W, st));
+  }
   // ---- output: IN apply + ReLU + reflect-pad 3 folded into the loader of the 7x7 conv 64 -> 1 + tanh   modules/model.py:110-112
   return ducosy_out_conv7x7_tanh_fused(P(w.y0), scale, shift, pk + L.outw, reinterpret_cast<const float*>(pk + L.outb), out, B,
                                        H, W, dt, st);
@@ -312,19 +348,7 @@ extern "C" int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, v
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_nhwc: bad dtype");
   DUCOSY_TRY(check_device_cached());
   ConvPlan p{};
-  p.in = in_pad; p.B = B; p.Hp = Hs + 2; p.Wp = Ws + 2; p.Cin = Cin; p.stride = 1;
-  p.w = w_packed4; p.Cout = Cout; p.num_phases = 4; p.num_taps = 4;
-  for (int ph = 0; ph < 4; ++ph) {
-    const int py = ph >> 1, px = ph & 1;
-    for (int t = 0; t < 4; ++t) {
-      p.tap_dy[ph][t] = int8_t((t >> 1) + py);   // source row i + a + py - 1, +1 for the zero border
-      p.tap_dx[ph][t] = int8_t((t & 1) + px);
-    }
-    p.oy_off[ph] = int8_t(py);
-    p.ox_off[ph] = int8_t(px);
-  }
-  p.Hg = Hs; p.Wg = Ws; p.out = out; p.Ho = 2 * Hs; p.Wo = 2 * Ws; p.oy_mul = p.ox_mul = 2;
-  p.partials = partials; p.dtype = dtype;
+  upconv_plan(p, in_pad, w_packed4, out, partials, B, Hs, Ws, Cin, Cout, dtype);
   return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -335,10 +359,7 @@ extern "C" int ducosy_upconv2x_merged_nhwc(const void* in_pad, const void* w_mer
   DUCOSY_CHECK(Cout == 64, DUCOSY_ERR_SHAPE, "upconv2x_merged_nhwc: Cout must be 64 (N = 4*Cout = 256)");
   DUCOSY_TRY(check_device_cached());
   ConvPlan p{};
-  p.in = in_pad; p.B = B; p.Hp = Hs + 2; p.Wp = Ws + 2; p.Cin = Cin; p.stride = 1;
-  p.w = w_merged; p.Cout = 4 * Cout; p.fold = 4; fill_taps_3x3(p);
-  p.Hg = Hs; p.Wg = Ws; p.out = out; p.Ho = 2 * Hs; p.Wo = 2 * Ws; p.oy_mul = p.ox_mul = 2;
-  p.partials = partials; p.dtype = dtype;
+  upconv_merged_plan(p, in_pad, w_merged, out, partials, B, Hs, Ws, Cin, Cout, dtype);
   return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
 }
 
@@ -355,7 +376,9 @@ extern "C" size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg,
 }
 extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
-  return 16 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 3 : 0));
+  // stem 4 (Cin = 1), 2 x (conv + apply) down, per block conv + apply + conv + residual (+ pool), 2 up convs +
+  // 1 apply, output conv; InstanceNorm finalize and the CBAM channel MLP run inside the conv launches
+  return 12 + cfg->num_residual_blocks * (4 + (cfg->use_cbam ? 1 : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,

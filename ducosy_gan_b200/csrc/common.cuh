@@ -53,6 +53,21 @@ struct PerDeviceOnce {
 constexpr int kMaxTaps = 16;
 constexpr int kMaxPhases = 4;
 
+// InstanceNorm finalize fused into the tail of the convolution (conv_gemm.cu: finalize_sample).  The CTA whose tile is the
+// LAST one of a sample to complete (a per-sample ticket counter, self-resetting) reduces that sample's per-tile partials in
+// fixed order -- deterministic, the same arithmetic as in_finalize_kernel -- and writes scale = rstd, shift = -mean*rstd
+// (and, with fc0/fc2, folds the CBAM channel attention of modules/model.py:20-24 into them).  This removes one or two
+// dependent launches behind every convolution: ~30 % of the kernel count of a batch-1 forward.
+struct ConvFinalize {
+  float* scale;            // [B][Cstore]; nullptr = not fused (the caller launches ducosy_in_finalize)
+  float* shift;            // [B][Cstore]
+  float* chmax;            // [B][Cstore] normalised per-channel max (optional; required with fc0/fc2)
+  const float* fc0;        // [Cstore/16][Cstore] or nullptr
+  const float* fc2;        // [Cstore][Cstore/16] or nullptr
+  int* counter;            // [B] tickets, zero before the first launch (the finalizing CTA resets its sample's ticket)
+  int npix;                // pixels per sample and channel behind the statistics
+};
+
 // Arguments of the implicit-GEMM convolution kernel (see conv_gemm.cu for the meaning).
 struct ConvGemmArgs {
   int num_phases, num_taps, kc_per_tap, n_blocks;
@@ -73,6 +88,7 @@ struct ConvGemmArgs {
   float* partials;         // [B][tiles_per_sample][3][Cout] (sum, sum of squares, max) or nullptr
   const float* bias;       // optional per-channel bias (epilogue mode 1)
   int epi_mode;            // 0: raw output + statistics, 1: bias + LeakyReLU(0.2), no statistics
+  ConvFinalize fin;        // optional: InstanceNorm finalize (+ CBAM channel MLP) by the CTA that completes a sample
 };
 
 // Host-side description of one convolution as an implicit GEMM.
@@ -94,6 +110,7 @@ struct ConvPlan {
   const float* bias;
   int epi_mode;
   int dtype;
+  ConvFinalize fin;
 };
 
 int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream);

@@ -80,6 +80,98 @@ __device__ __forceinline__ TileCoord decode_tile(int tile, const ConvGemmArgs& a
   return t;
 }
 
+// InstanceNorm finalize of sample b by the 256 epilogue threads of the CTA that completed the sample's last tile (see
+// ConvFinalize in common.cuh).  `scratch` is the output staging area (free between two tiles), `tiles` the number of m-tiles
+// per sample.  Partials were written by other SMs: they are read through L2 (ld.global.cg).
+__device__ void finalize_sample(const ConvGemmArgs& a, int b, int tiles, uint8_t* scratch, int et) {
+  const int C = a.Cstore;
+  const int Cw = C < kEpiThreads ? C : kEpiThreads;    // channels handled side by side
+  const int G = kEpiThreads / Cw;                      // tile groups per channel (64 ch: 4, 128: 2, >= 256: 1)
+  const int cl = et % Cw, g = et / Cw;
+  double* sd = reinterpret_cast<double*>(scratch);                        // [G][2][Cw]
+  float* sm = reinterpret_cast<float*>(scratch + size_t(G) * 2 * Cw * 8); // [G][Cw] max, then [C] smax + [C/16] hidden
+  const float* base = a.partials + size_t(b) * tiles * 3 * C;
+  float my_scale = 0.f, my_shift = 0.f;   // C <= 256: thread (g == 0, cl) keeps its channel's pair for the MLP fold
+  for (int c0 = 0; c0 < C; c0 += Cw) {
+    const int c = c0 + cl;
+    const float* p = base + c;
+    double s1 = 0.0, s2 = 0.0;
+    float mx = -INFINITY;
+    for (int t0 = g; t0 < tiles; t0 += G * 4) {
+      float v1[4], v2[4], vm[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int t = t0 + u * G;
+        const bool ok = t < tiles;
+        v1[u] = ok ? __ldcg(p + size_t(t * 3 + 0) * C) : 0.f;
+        v2[u] = ok ? __ldcg(p + size_t(t * 3 + 1) * C) : 0.f;
+        vm[u] = ok ? __ldcg(p + size_t(t * 3 + 2) * C) : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s1 += double(v1[u]);
+        s2 += double(v2[u]);
+        mx = fmaxf(mx, vm[u]);
+      }
+    }
+    if (G > 1) {
+      sd[(g * 2 + 0) * Cw + cl] = s1;
+      sd[(g * 2 + 1) * Cw + cl] = s2;
+      sm[g * Cw + cl] = mx;
+      named_bar_sync(1, kEpiThreads);
+      if (g == 0)
+        for (int k = 1; k < G; ++k) {      // fixed order: deterministic
+          s1 += sd[(k * 2 + 0) * Cw + cl];
+          s2 += sd[(k * 2 + 1) * Cw + cl];
+          mx = fmaxf(mx, sm[k * Cw + cl]);
+        }
+    }
+    if (g == 0) {
+      const double mean = s1 / a.fin.npix;
+      double var = s2 / a.fin.npix - mean * mean;
+      if (var < 0.0) var = 0.0;
+      const float rstd = float(1.0 / sqrt(var + 1e-5));
+      const float fmean = float(mean);
+      my_scale = rstd;
+      my_shift = -fmean * rstd;
+      const float nmax = (mx - fmean) * rstd;          // max over H*W of the normalised map (rstd > 0)
+      if (a.fin.chmax != nullptr) a.fin.chmax[size_t(b) * C + c] = nmax;
+      if (a.fin.fc0 == nullptr) {
+        a.fin.scale[size_t(b) * C + c] = my_scale;
+        a.fin.shift[size_t(b) * C + c] = my_shift;
+      } else {
+        sm[c] = nmax;                                  // C == Cw == 256 here (checked on the host): G == 1, sm is free
+      }
+    }
+    if (G > 1) named_bar_sync(1, kEpiThreads);         // scratch is reused by the next channel block
+  }
+  if (a.fin.fc0 != nullptr) {
+    // CBAM channel attention behind a non-affine InstanceNorm (modules/model.py:20-24): the avg-pool branch sees a zero-mean
+    // map and contributes fc(0) = 0, so att = sigmoid(fc2 . relu(fc0 . max)); folded into (scale, shift).
+    const int Hd = C / 16;
+    float* smax = sm;
+    float* hidden = sm + C;
+    named_bar_sync(1, kEpiThreads);
+    const int warp = et >> 5, lane = et & 31;
+    for (int j = warp; j < Hd; j += kEpiThreads / 32) {
+      float acc = 0.f;
+      for (int c = lane; c < C; c += 32) acc += __ldg(a.fin.fc0 + j * C + c) * smax[c];
+#pragma unroll
+      for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+      if (lane == 0) hidden[j] = fmaxf(acc, 0.f);
+    }
+    named_bar_sync(1, kEpiThreads);
+    if (et < C) {
+      float acc = 0.f;
+      for (int j = 0; j < Hd; ++j) acc += __ldg(a.fin.fc2 + et * Hd + j) * hidden[j];
+      const float att = 1.f / (1.f + __expf(-acc));
+      a.fin.scale[size_t(b) * C + et] = my_scale * att;
+      a.fin.shift[size_t(b) * C + et] = my_shift * att;
+    }
+    named_bar_sync(1, kEpiThreads);
+  }
+}
+
 template <int kN, typename T, int kCG>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
@@ -98,6 +190,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -302,8 +395,24 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           pdst[which * a.Cstore + col2] = acc;
         }
       }
+      if (a.fin.scale != nullptr) __threadfence();   // this tile's partial row: visible device-wide before the ticket below
       if (et == 0) tma_store_wait_read();  // the staged tile may be overwritten once the TMA engine has read it
       named_bar_sync(1, kEpiThreads);
+      if (a.fin.scale != nullptr) {
+        // ticket: the CTA that completes the last (m-tile, n-block) of sample b finalizes its InstanceNorm statistics
+        if (et == 0) {
+          const int total = tiles_m_per_sample * a.n_blocks;
+          const int old = atomicAdd(a.fin.counter + tc.b, 1);
+          const int last = old == total - 1;
+          if (last) {
+            a.fin.counter[tc.b] = 0;       // self-resetting: the next launch on this workspace starts from zero again
+            __threadfence();               // acquire side: the other CTAs' partial rows are visible from here on
+          }
+          *fin_flag = last;
+        }
+        named_bar_sync(1, kEpiThreads);
+        if (*fin_flag) finalize_sample(a, tc.b, tiles_m_per_sample, otile, et);
+      }
       as ^= 1;
       if (as == 0) aph ^= 1;
     }
@@ -419,6 +528,14 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.partials = p.partials;
   a.bias = p.bias;
   a.epi_mode = p.epi_mode;
+  a.fin = p.fin;
+  if (p.fin.scale != nullptr) {
+    DUCOSY_CHECK(p.partials != nullptr && p.fin.shift != nullptr && p.fin.counter != nullptr && p.fin.npix > 0 && p.epi_mode == 0,
+                 DUCOSY_ERR_ARG, "conv_gemm: fused finalize needs partials, shift, counters and npix");
+    DUCOSY_CHECK((p.fin.fc0 == nullptr) == (p.fin.fc2 == nullptr) && (p.fin.fc0 == nullptr || (a.Cstore == 256 && p.fin.chmax != nullptr)),
+                 DUCOSY_ERR_ARG, "conv_gemm: the fused CBAM channel MLP needs fc0 + fc2 + chmax and 256 channels");
+    DUCOSY_CHECK(a.Cstore % 64 == 0 && (a.Cstore <= 256 || a.Cstore % 256 == 0), DUCOSY_ERR_SHAPE, "conv_gemm: fused finalize: bad channel count");
+  }
 
   // CTA pairs whenever the m-tiles of one (sample, phase) pair up; DUCOSY_CONV_CTA_GROUP=1 forces single CTAs.
   static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();

@@ -419,8 +419,16 @@ __global__ void cbam_spatial_conv_kernel(const float2* __restrict__ pooled, cons
 template <typename T>
 __global__ void __launch_bounds__(256)
 residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
-                          const float* __restrict__ sa, const T* __restrict__ res_pad, int res_pw, T* __restrict__ out,
+                          const float* __restrict__ sa, const float2* __restrict__ pooled, const float* __restrict__ w_sa,
+                          const T* __restrict__ res_pad, int res_pw, T* __restrict__ out,
                           int B, int H, int W, int C, int pad, int pad_mode) {
+  // pooled != nullptr: the 7x7 spatial-attention conv + sigmoid (modules/model.py:36-38) is evaluated here, one source row at
+  // a time into shared memory, instead of by a kernel of its own (98 MACs per pixel against 3 x 512 bytes moved per pixel)
+  extern __shared__ float sa_smem[];   // [98] weights, [W] attention of the current source row
+  float* sa_line = sa_smem + 98;
+  if (pooled != nullptr) {
+    for (int i = threadIdx.x; i < 98; i += 256) sa_smem[i] = w_sa[i];
+  }
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
   const int Wr = W + 2 * res_pw, Hr = H + 2 * res_pw;
   const int c8 = threadIdx.x % cv, row_chunks = Wp * cv;
@@ -443,6 +451,27 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
     const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cv + c8;
     const uint4* r_row = reinterpret_cast<const uint4*>(res_pad) + (((long long)b * Hr + sy + res_pw) * Wr + res_pw) * cv + c8;
     const float* sa_row = sa != nullptr ? sa + ((long long)b * H + sy) * W : nullptr;
+    if (pooled != nullptr) {
+      __syncthreads();                       // the previous row's readers are done with sa_line (and the weights are loaded)
+      for (int x = threadIdx.x; x < W; x += 256) {
+        float acc = 0.f;
+#pragma unroll
+        for (int dr = 0; dr < 7; ++dr) {
+          const int qy = sy + dr - 3;
+          if (qy < 0 || qy >= H) continue;
+#pragma unroll
+          for (int ds = 0; ds < 7; ++ds) {
+            const int qx = x + ds - 3;
+            if (qx < 0 || qx >= W) continue;
+            const float2 pv = __ldg(&pooled[((long long)b * H + qy) * W + qx]);
+            acc = fmaf(sa_smem[dr * 7 + ds], pv.x, acc);
+            acc = fmaf(sa_smem[49 + dr * 7 + ds], pv.y, acc);
+          }
+        }
+        sa_line[x] = 1.f / (1.f + __expf(-acc));
+      }
+      __syncthreads();
+    }
     uint4* dst_row = reinterpret_cast<uint4*>(out) + (long long)row * row_chunks + c8;
     for (int px = px0; px < Wp; px += px_step * kRowILP) {
       uint4 raw[kRowILP], res[kRowILP];
@@ -458,7 +487,7 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
         if (live[u]) {
           raw[u] = y_row[(long long)sx * cv];
           res[u] = r_row[(long long)sx * cv];
-          att[u] = sa_row != nullptr ? __ldg(sa_row + sx) : 1.f;
+          att[u] = pooled != nullptr ? sa_line[sx] : (sa_row != nullptr ? __ldg(sa_row + sx) : 1.f);
         }
       }
 #pragma unroll
@@ -610,7 +639,25 @@ extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, cons
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_apply_pad: C/8 must divide 256");
   DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, sa, static_cast<const T*>(res_pad),
+                                      static_cast<const T*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const T*>(res_pad),
                                       res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
+  return check_launch("residual_apply_pad_kernel");
+}
+
+// The same with the spatial attention evaluated inside: pooled [B][H][W][2] (channel mean, channel max of the attended map,
+// ducosy_cbam_pool) and the 7x7 conv weight w_sa [1][2][7][7] replace the precomputed sa map (and the launch of
+// ducosy_cbam_spatial_conv): modules/model.py:34-39 + :83-87 in one pass.
+extern "C" int ducosy_residual_cbam_apply_pad(const void* y, const float* scale, const float* shift, const float* pooled,
+                                              const float* w_sa, const void* res_pad, int res_pad_width, void* out_pad, int B,
+                                              int H, int W, int C, int pad, int pad_mode, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(y && scale && shift && pooled && w_sa && res_pad && out_pad && B > 0, DUCOSY_ERR_ARG, "residual_cbam_apply_pad: bad argument");
+  DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W && res_pad_width >= 0 && W <= 8192, DUCOSY_ERR_SHAPE,
+               "residual_cbam_apply_pad: bad shape");
+  DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_cbam_apply_pad: in-place is not supported");
+  DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_cbam_apply_pad: C/8 must divide 256");
+  const size_t smem = (98 + size_t(W)) * sizeof(float);
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
+                                      static_cast<const T*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
+                                      static_cast<const T*>(res_pad), res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");
 }

@@ -151,6 +151,11 @@ int ducosy_cbam_spatial_conv(const float* pooled, const float* w_sa, float* sa, 
 int ducosy_residual_apply_pad(const void* y, const float* scale, const float* shift, const float* sa,
                               const void* res_pad, int res_pad_width, void* out_pad, int B, int H, int W, int C, int pad,
                               int pad_mode, int dtype, ducosy_stream_t stream);
+/* The same pass with the spatial attention of modules/model.py:34-39 evaluated inside: `pooled` [B][H][W][2] (ducosy_cbam_pool)
+ * and the 7x7 conv weight `w_sa` [1][2][7][7] replace the precomputed attention map and the ducosy_cbam_spatial_conv launch. */
+int ducosy_residual_cbam_apply_pad(const void* y, const float* scale, const float* shift, const float* pooled, const float* w_sa,
+                                   const void* res_pad, int res_pad_width, void* out_pad, int B, int H, int W, int C, int pad,
+                                   int pad_mode, int dtype, ducosy_stream_t stream);
 
 /* Output conv (modules/model.py:112): reflect-padded input [B][H+6][W+6][64] 16-bit, weight [1][64][7][7] fp32,
  * bias[1] fp32 -> out fp32 [B][H][W] = tanh(conv + bias).  w_packed from ducosy_pack_out_weight. */
