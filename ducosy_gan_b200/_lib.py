@@ -40,6 +40,9 @@ SIGNATURES = {
     "ducosy_upconv2x_merged_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_stem_weight": (_i, [_p, _p, _i, _i, _p]),
     "ducosy_conv2d_nhwc": (_i, [_p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_conv2d_nhwc_in": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_upconv2x_nhwc_in": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_upconv2x_merged_nhwc_in": (_i, [_p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_upconv2x_nhwc": (_i, [_p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_stem_im2col": (_i, [_p, _p, _i, _i, _i, _i, _i, _p]),
     "ducosy_stem_im2col_hu": (_i, [_p, _p, _i, _i, _i, _f, _f, _f, _f, _i, _p]),

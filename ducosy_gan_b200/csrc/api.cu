@@ -1,5 +1,6 @@
 // extern "C" surface: error plumbing, convolution entry points and the whole-generator forward
 // (modules/model.py:92-115) expressed as a fixed sequence of the kernels in this directory.
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -164,6 +165,16 @@ int check_gen_shape(const ducosy_gen_config& c, int B, int H, int W) {
 // reduces the per-tile partials (conv_gemm.cu: finalize_sample)
 int run_conv_in(ConvPlan& p, float* scale, float* shift, const float* fc0, const float* fc2, float* chmax, int* tickets,
                 int npix, cudaStream_t st) {
+  // DUCOSY_FUSED_FINALIZE=1 finalizes inside the conv launch (ConvFinalize).  Measured and NOT the default: one CTA reducing a
+  // whole sample's partials (393 KB through one SM's L2 port, ~10 us) is slower than the 8-CTA finalize kernel plus its launch
+  // -- 967 -> 752 slices/s at batch 30 (the finalizing CTA pair stalls and the static tile schedule turns that into a tail),
+  // 713 -> 610 at batch 1 (profiles/r02_fusion_ab.json).
+  static const bool fused = []() { const char* e = getenv("DUCOSY_FUSED_FINALIZE"); return e != nullptr && atoi(e) != 0; }();
+  if (!fused) {
+    DUCOSY_TRY(launch_conv_gemm(p, st));
+    const int tiles = conv_tiles_per_sample(p.num_phases, p.Hg, p.Wg);
+    return ducosy_in_finalize(p.partials, tiles, npix, scale, shift, fc0, fc2, chmax, p.B, p.Cout / (p.fold > 1 ? p.fold : 1), st);
+  }
   p.fin.scale = scale; p.fin.shift = shift; p.fin.chmax = chmax; p.fin.fc0 = fc0; p.fin.fc2 = fc2;
   p.fin.counter = tickets; p.fin.npix = npix;
   return launch_conv_gemm(p, st);
@@ -280,7 +291,13 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     const float* fc2 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc2[i]) : nullptr;
     DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, c.use_cbam ? chmax : nullptr, tickets, H4 * W4, st));
     const int mode = i + 1 < nb ? DUCOSY_PAD_REFLECT : DUCOSY_PAD_ZERO;  // the decoder convs zero-pad
-    if (c.use_cbam) {
+    static const bool fused_sa = []() { const char* e = getenv("DUCOSY_FUSED_SPATIAL"); return e == nullptr || atoi(e) != 0; }();
+    if (c.use_cbam && !fused_sa) {   // experiment switch: the round-1 path with a separate spatial-attention conv launch
+      float* sa = reinterpret_cast<float*>(base + w.sa);
+      DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
+      DUCOSY_TRY(ducosy_cbam_spatial_conv(pooled, reinterpret_cast<const float*>(pk + L.saw[i]), sa, B, H4, W4, st));
+      DUCOSY_TRY(ducosy_residual_apply_pad(P(w.y2b), scale, shift, sa, P(cur), 1, P(nxt), B, H4, W4, 256, 1, mode, dt, st));
+    } else if (c.use_cbam) {
       // spatial attention: channel mean / max of the attended map, then the 7x7 conv + sigmoid inside the residual pass
       DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
       DUCOSY_TRY(ducosy_residual_cbam_apply_pad(P(w.y2b), scale, shift, pooled, reinterpret_cast<const float*>(pk + L.saw[i]), P(cur), 1,
@@ -363,6 +380,66 @@ extern "C" int ducosy_upconv2x_merged_nhwc(const void* in_pad, const void* w_mer
   return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
 }
 
+// The three convolution entry points with the InstanceNorm finalize fused into the launch (ConvFinalize, common.cuh): scale /
+// shift [B][Cout] (and chmax [B][Cout] when non-NULL) are written by the CTA that completes a sample's last tile.  `tickets`:
+// int32 [B], zero before the first use, left zero by every launch; launches that may run concurrently (different streams)
+// need different ticket arrays.
+namespace {
+void set_fin(ConvPlan& p, float* scale, float* shift, float* chmax, int* tickets, int npix) {
+  p.fin.scale = scale; p.fin.shift = shift; p.fin.chmax = chmax; p.fin.fc0 = nullptr; p.fin.fc2 = nullptr;
+  p.fin.counter = tickets; p.fin.npix = npix;
+}
+}  // namespace
+
+extern "C" int ducosy_conv2d_nhwc_in(const void* in, const void* w, void* out, float* partials, float* scale, float* shift,
+                                     float* chmax, int* tickets, int B, int Hp, int Wp, int Cin, int Cout, int kh, int kw,
+                                     int stride, int dtype, ducosy_stream_t stream) {
+  DUCOSY_CHECK(in && w && out && partials && scale && shift && tickets && B > 0, DUCOSY_ERR_ARG, "conv2d_nhwc_in: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_nhwc_in: bad dtype");
+  DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
+               "conv2d_nhwc_in: kernel %dx%d stride %d unsupported", kh, kw, stride);
+  DUCOSY_TRY(check_device_cached());
+  ConvPlan p{};
+  p.in = in; p.B = B; p.Hp = Hp; p.Wp = Wp; p.Cin = Cin; p.stride = stride;
+  p.w = w; p.Cout = Cout; p.num_phases = 1; p.num_taps = kh * kw;
+  for (int r = 0; r < kh; ++r)
+    for (int s = 0; s < kw; ++s) {
+      p.tap_dy[0][r * kw + s] = int8_t(r);
+      p.tap_dx[0][r * kw + s] = int8_t(s);
+    }
+  p.Ho = (Hp - kh) / stride + 1;
+  p.Wo = (Wp - kw) / stride + 1;
+  p.Hg = p.Ho; p.Wg = p.Wo; p.out = out; p.oy_mul = p.ox_mul = 1;
+  p.partials = partials; p.dtype = dtype;
+  set_fin(p, scale, shift, chmax, tickets, p.Ho * p.Wo);
+  return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ducosy_upconv2x_nhwc_in(const void* in_pad, const void* w_packed4, void* out, float* partials, float* scale,
+                                       float* shift, int* tickets, int B, int Hs, int Ws, int Cin, int Cout, int dtype,
+                                       ducosy_stream_t stream) {
+  DUCOSY_CHECK(in_pad && w_packed4 && out && partials && scale && shift && tickets && B > 0, DUCOSY_ERR_ARG, "upconv2x_nhwc_in: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_nhwc_in: bad dtype");
+  DUCOSY_TRY(check_device_cached());
+  ConvPlan p{};
+  upconv_plan(p, in_pad, w_packed4, out, partials, B, Hs, Ws, Cin, Cout, dtype);
+  set_fin(p, scale, shift, nullptr, tickets, 4 * Hs * Ws);
+  return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
+extern "C" int ducosy_upconv2x_merged_nhwc_in(const void* in_pad, const void* w_merged, void* out, float* partials, float* scale,
+                                              float* shift, int* tickets, int B, int Hs, int Ws, int Cin, int Cout, int dtype,
+                                              ducosy_stream_t stream) {
+  DUCOSY_CHECK(in_pad && w_merged && out && partials && scale && shift && tickets && B > 0, DUCOSY_ERR_ARG, "upconv2x_merged_nhwc_in: null pointer");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_merged_nhwc_in: bad dtype");
+  DUCOSY_CHECK(Cout == 64, DUCOSY_ERR_SHAPE, "upconv2x_merged_nhwc_in: Cout must be 64 (N = 4*Cout = 256)");
+  DUCOSY_TRY(check_device_cached());
+  ConvPlan p{};
+  upconv_merged_plan(p, in_pad, w_merged, out, partials, B, Hs, Ws, Cin, Cout, dtype);
+  set_fin(p, scale, shift, nullptr, tickets, 4 * Hs * Ws);
+  return launch_conv_gemm(p, static_cast<cudaStream_t>(stream));
+}
+
 extern "C" int ducosy_generator_num_params(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_params: null config");
   return 6 + cfg->num_residual_blocks * (4 + (cfg->use_cbam ? 3 : 0)) + 6;
@@ -376,9 +453,9 @@ extern "C" size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg,
 }
 extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
-  // stem 4 (Cin = 1), 2 x (conv + apply) down, per block conv + apply + conv + residual (+ pool), 2 up convs +
-  // 1 apply, output conv; InstanceNorm finalize and the CBAM channel MLP run inside the conv launches
-  return 12 + cfg->num_residual_blocks * (4 + (cfg->use_cbam ? 1 : 0));
+  // stem 4 (Cin = 1), 2 x (conv + finalize + apply) down, per block 2 x (conv + finalize) + apply + residual (+ channel MLP + pool;
+  // the spatial-attention conv runs inside the residual pass), 2 x (up conv + finalize) + 1 apply, output conv
+  return 18 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 2 : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,

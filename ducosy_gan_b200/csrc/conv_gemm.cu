@@ -59,6 +59,12 @@ struct Cfg {
   static constexpr size_t kSmemBytes = size_t(kFixedBytes) + size_t(kStages) * kStageBytes;
 };
 
+__device__ __forceinline__ int atom_add_acq_rel_gpu(int* p, int v) {
+  int old;
+  asm volatile("atom.add.acq_rel.gpu.global.s32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -97,10 +103,11 @@ __device__ void finalize_sample(const ConvGemmArgs& a, int b, int tiles, uint8_t
     const float* p = base + c;
     double s1 = 0.0, s2 = 0.0;
     float mx = -INFINITY;
-    for (int t0 = g; t0 < tiles; t0 += G * 4) {
-      float v1[4], v2[4], vm[4];
+    constexpr int kU = 16;      // independent L2 loads in flight per thread: one CTA reduces a whole sample, latency bound
+    for (int t0 = g; t0 < tiles; t0 += G * kU) {
+      float v1[kU], v2[kU], vm[kU];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         const int t = t0 + u * G;
         const bool ok = t < tiles;
         v1[u] = ok ? __ldcg(p + size_t(t * 3 + 0) * C) : 0.f;
@@ -108,7 +115,7 @@ __device__ void finalize_sample(const ConvGemmArgs& a, int b, int tiles, uint8_t
         vm[u] = ok ? __ldcg(p + size_t(t * 3 + 2) * C) : -INFINITY;
       }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
+      for (int u = 0; u < kU; ++u) {
         s1 += double(v1[u]);
         s2 += double(v2[u]);
         mx = fmaxf(mx, vm[u]);
@@ -190,7 +197,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull = empty + kStages;
   uint64_t* tempty = tfull + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  volatile int* fin_flag = reinterpret_cast<volatile int*>(tmem_slot + 1);
+  volatile int* fin_slot = reinterpret_cast<volatile int*>(tmem_slot + 1);   // [2] parked tickets (sample + 1, or 0)
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -314,6 +321,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     constexpr int kRows = kTileM / C::kParts;
     const int cp_slab = warp / C::kParts, cp_part = warp % C::kParts;
     int as = 0;
+    int fin_n = 0;                       // tiles this CTA has finished (parity selects the ticket slot)
     uint32_t aph = 0;
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const TileCoord tc = decode_tile(unit_tile(unit), a);
@@ -395,26 +403,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           pdst[which * a.Cstore + col2] = acc;
         }
       }
-      if (a.fin.scale != nullptr) __threadfence();   // this tile's partial row: visible device-wide before the ticket below
       if (et == 0) tma_store_wait_read();  // the staged tile may be overwritten once the TMA engine has read it
       named_bar_sync(1, kEpiThreads);
       if (a.fin.scale != nullptr) {
-        // ticket: the CTA that completes the last (m-tile, n-block) of sample b finalizes its InstanceNorm statistics
-        if (et == 0) {
+        // Ticket: the CTA that completes the last (m-tile, n-block) of a sample finalizes that sample's InstanceNorm
+        // statistics.  The barrier above orders every thread's partial-row stores before the ticket thread, whose
+        // acq_rel atomic (cumulative) publishes them device-wide; it is a thread of warp 1, not the thread that issued
+        // the TMA stores.  The answer is parked in shared memory and acted on ONE TILE LATER (after that tile's own
+        // barrier), so the round trip of the atomic never sits on the epilogue's critical path.
+        if (fin_n > 0 && fin_slot[(fin_n - 1) & 1] != 0) finalize_sample(a, fin_slot[(fin_n - 1) & 1] - 1, tiles_m_per_sample, otile, et);
+        if (et == 32) {
           const int total = tiles_m_per_sample * a.n_blocks;
-          const int old = atomicAdd(a.fin.counter + tc.b, 1);
+          const int old = atom_add_acq_rel_gpu(a.fin.counter + tc.b, 1);
           const int last = old == total - 1;
-          if (last) {
-            a.fin.counter[tc.b] = 0;       // self-resetting: the next launch on this workspace starts from zero again
-            __threadfence();               // acquire side: the other CTAs' partial rows are visible from here on
-          }
-          *fin_flag = last;
+          if (last) a.fin.counter[tc.b] = 0;   // self-resetting: the next launch on this workspace starts from zero again
+          fin_slot[fin_n & 1] = last ? tc.b + 1 : 0;
         }
-        named_bar_sync(1, kEpiThreads);
-        if (*fin_flag) finalize_sample(a, tc.b, tiles_m_per_sample, otile, et);
+        ++fin_n;
       }
       as ^= 1;
       if (as == 0) aph ^= 1;
+    }
+    if (a.fin.scale != nullptr && fin_n > 0) {   // the ticket of this CTA's last tile
+      named_bar_sync(1, kEpiThreads);
+      if (fin_slot[(fin_n - 1) & 1] != 0) finalize_sample(a, fin_slot[(fin_n - 1) & 1] - 1, tiles_m_per_sample, otile, et);
     }
   }
 

@@ -163,6 +163,68 @@ def conv2d_nhwc(x_pad: torch.Tensor, w_packed: torch.Tensor, kh, kw, stride, wan
     return y, partials
 
 
+_TICKETS = {}
+
+
+def _tickets(device, B):
+    """Zeroed int32 ticket array of the fused conv + InstanceNorm-finalize launches: one per (device, stream) -- launches on
+    different streams may overlap -- kept zero by the kernels themselves."""
+    key = (device.index, torch.cuda.current_stream(device).cuda_stream)
+    t = _TICKETS.get(key)
+    if t is None or t.numel() < B:
+        t = _TICKETS[key] = torch.zeros(max(1024, B), dtype=torch.int32, device=device)
+    return t
+
+
+def _fused_finalize():
+    """DUCOSY_FUSED_FINALIZE=1: finalize the InstanceNorm statistics inside the conv launch (ducosy_*_in entry points).  Measured
+    slower than the separate finalize kernel at every batch size (profiles/r02_fusion_ab.json), hence off by default."""
+    import os
+    return os.environ.get("DUCOSY_FUSED_FINALIZE", "0") == "1"
+
+
+def conv2d_nhwc_in(x_pad: torch.Tensor, w_packed: torch.Tensor, kh, kw, stride, want_chmax=False):
+    """conv2d_nhwc + in_finalize: raw y [B,Ho,Wo,Cout] and the InstanceNorm pair (scale, shift) [B,Cout] (+ the normalised
+    per-channel max when want_chmax).  One launch with DUCOSY_FUSED_FINALIZE=1, conv + finalize kernel otherwise."""
+    B, Hp, Wp, Cin = x_pad.shape
+    Cout = w_packed.shape[0]
+    Ho, Wo = (Hp - kh) // stride + 1, (Wp - kw) // stride + 1
+    if not _fused_finalize():
+        y, partials = conv2d_nhwc(x_pad, w_packed, kh, kw, stride)
+        return y, in_finalize(partials, Ho * Wo, want_chmax=want_chmax)
+    assert x_pad.is_contiguous() and w_packed.is_contiguous() and w_packed.dtype == x_pad.dtype
+    with _dev(x_pad):
+        dev = x_pad.device
+        y = torch.empty((B, Ho, Wo, Cout), dtype=x_pad.dtype, device=dev)
+        partials = torch.empty((B, Ho * Wo // 128, 3, Cout), dtype=torch.float32, device=dev)
+        scale = torch.empty((B, Cout), dtype=torch.float32, device=dev)
+        shift = torch.empty((B, Cout), dtype=torch.float32, device=dev)
+        chmax = torch.empty((B, Cout), dtype=torch.float32, device=dev) if want_chmax else None
+        call("ducosy_conv2d_nhwc_in", ptr(x_pad), ptr(w_packed), ptr(y), ptr(partials), ptr(scale), ptr(shift), ptr(chmax),
+             ptr(_tickets(dev, B)), B, Hp, Wp, Cin, Cout, kh, kw, stride, dtype_code(x_pad.dtype), stream_ptr())
+    return (y, (scale, shift, chmax)) if want_chmax else (y, (scale, shift))
+
+
+def upconv2x_nhwc_in(x_pad: torch.Tensor, w_packed, merged: bool):
+    """upconv2x_nhwc / upconv2x_merged_nhwc + in_finalize: raw y [B,2Hs,2Ws,Cout], (scale, shift)."""
+    B, Hp, Wp, Cin = x_pad.shape
+    Hs, Ws = Hp - 2, Wp - 2
+    Cout = w_packed.shape[0] // 4
+    if not _fused_finalize():
+        y, partials = (upconv2x_merged_nhwc if merged else upconv2x_nhwc)(x_pad, w_packed)
+        return y, in_finalize(partials, 4 * Hs * Ws)
+    with _dev(x_pad):
+        dev = x_pad.device
+        y = torch.empty((B, 2 * Hs, 2 * Ws, Cout), dtype=x_pad.dtype, device=dev)
+        tiles = (Hs * Ws // 128) if merged else (4 * Hs * Ws // 128)
+        partials = torch.empty((B, tiles, 3, Cout), dtype=torch.float32, device=dev)
+        scale = torch.empty((B, Cout), dtype=torch.float32, device=dev)
+        shift = torch.empty((B, Cout), dtype=torch.float32, device=dev)
+        call("ducosy_upconv2x_merged_nhwc_in" if merged else "ducosy_upconv2x_nhwc_in", ptr(x_pad), ptr(w_packed), ptr(y), ptr(partials),
+             ptr(scale), ptr(shift), ptr(_tickets(dev, B)), B, Hs, Ws, Cin, Cout, dtype_code(x_pad.dtype), stream_ptr())
+    return y, (scale, shift)
+
+
 def upconv2x_nhwc(x_pad: torch.Tensor, w_packed4: torch.Tensor):
     """Upsample(x2 nearest)+Conv3x3(pad 1) from the zero-padded source [B,Hs+2,Ws+2,Cin] -> raw y [B,2Hs,2Ws,Cout]."""
     B, Hp, Wp, Cin = x_pad.shape
@@ -502,13 +564,14 @@ def _f32c(t):
     return t.detach().to(torch.float32).contiguous()
 
 
-def cbam_forward_train(sv, partials, npix, fc0, fc2, wsa, out_mode):
+def cbam_forward_train(sv, stats, fc0, fc2, wsa, out_mode):
     """Training-mode tail of a ResidualBlockWithCBAM (reference modules/model.py:68-87): from the raw second conv output
-    sv["yb"] and its statistics to the padded block output, keeping what the backward needs in sv."""
+    sv["yb"] and its InstanceNorm statistics ``stats`` = (scale, shift, normalised channel max) of conv2d_nhwc_in to the padded
+    block output, keeping what the backward needs in sv."""
     yb = sv["yb"]
     B, H, W, Cn = yb.shape
     dev = yb.device
-    scale_n, shift_n, chmax = in_finalize(partials, npix, want_chmax=True)
+    scale_n, shift_n, chmax = stats
     with _dev(yb):
         scale_v, shift_v, ca = (torch.empty((B, Cn), dtype=torch.float32, device=dev) for _ in range(3))
         hidden = torch.empty((B, Cn // 16), dtype=torch.float32, device=dev)

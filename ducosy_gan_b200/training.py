@@ -32,40 +32,33 @@ def generator_forward_train(params, cfg, x, dtype):
     if H % 32 or (W % 512 and W != 256):
         raise RuntimeError(f"training path needs H % 32 == 0 and W = 256 or a multiple of 512 (got {H}x{W}); 512x512 is what train.py uses")
     S = {"shape": (B, H, W)}
+    # ops.conv2d_nhwc_in = conv + InstanceNorm finalize (one launch with DUCOSY_FUSED_FINALIZE=1, two by default)
     S["cols"] = ops.stem_im2col(x, dtype)
-    y0, part = ops.conv2d_nhwc(S["cols"], ops.pack_stem_weight(stem[0], dtype), 1, 1, 1)
-    S["y0"], S["n0"] = y0, ops.in_finalize(part, H * W)
-    S["p0"] = ops.in_apply_pad(y0, *S["n0"], 1, PAD_ZERO, ACT_RELU)
-    y1, part = ops.conv2d_nhwc(S["p0"], ops.pack_conv_weight(d1[0], dtype), 3, 3, 2)
-    S["y1"], S["n1"] = y1, ops.in_finalize(part, H * W // 4)
-    S["p1"] = ops.in_apply_pad(y1, *S["n1"], 1, PAD_ZERO, ACT_RELU)
-    y2, part = ops.conv2d_nhwc(S["p1"], ops.pack_conv_weight(d2[0], dtype), 3, 3, 2)
-    S["y2"], S["n2"] = y2, ops.in_finalize(part, H * W // 16)
-    r = ops.in_apply_pad(y2, *S["n2"], 1, PAD_REFLECT if num_blocks else PAD_ZERO, ACT_RELU)
-    npix = H * W // 16
+    S["y0"], S["n0"] = ops.conv2d_nhwc_in(S["cols"], ops.pack_stem_weight(stem[0], dtype), 1, 1, 1)
+    S["p0"] = ops.in_apply_pad(S["y0"], *S["n0"], 1, PAD_ZERO, ACT_RELU)
+    S["y1"], S["n1"] = ops.conv2d_nhwc_in(S["p0"], ops.pack_conv_weight(d1[0], dtype), 3, 3, 2)
+    S["p1"] = ops.in_apply_pad(S["y1"], *S["n1"], 1, PAD_ZERO, ACT_RELU)
+    S["y2"], S["n2"] = ops.conv2d_nhwc_in(S["p1"], ops.pack_conv_weight(d2[0], dtype), 3, 3, 2)
+    r = ops.in_apply_pad(S["y2"], *S["n2"], 1, PAD_REFLECT if num_blocks else PAD_ZERO, ACT_RELU)
     S["blocks"] = []
     for i, bp in enumerate(blocks):
         last = i == num_blocks - 1
         sv = {"r": r}
-        ya, part = ops.conv2d_nhwc(r, ops.pack_conv_weight(bp[0], dtype), 3, 3, 1)
-        sv["ya"], sv["na"] = ya, ops.in_finalize(part, npix)
-        sv["pa"] = ops.in_apply_pad(ya, *sv["na"], 1, PAD_REFLECT, ACT_RELU)
-        yb, part = ops.conv2d_nhwc(sv["pa"], ops.pack_conv_weight(bp[2], dtype), 3, 3, 1)
-        sv["yb"] = yb
+        sv["ya"], sv["na"] = ops.conv2d_nhwc_in(r, ops.pack_conv_weight(bp[0], dtype), 3, 3, 1)
+        sv["pa"] = ops.in_apply_pad(sv["ya"], *sv["na"], 1, PAD_REFLECT, ACT_RELU)
         out_mode = PAD_ZERO if last else PAD_REFLECT
         if use_cbam:
-            r = ops.cbam_forward_train(sv, part, npix, bp[4], bp[5], bp[6], out_mode)
+            sv["yb"], stats = ops.conv2d_nhwc_in(sv["pa"], ops.pack_conv_weight(bp[2], dtype), 3, 3, 1, want_chmax=True)
+            r = ops.cbam_forward_train(sv, stats, bp[4], bp[5], bp[6], out_mode)
         else:
-            sv["nb"] = ops.in_finalize(part, npix)
-            r = ops.residual_apply_pad(yb, *sv["nb"], None, sv["r"], 1, 1, out_mode)
+            sv["yb"], sv["nb"] = ops.conv2d_nhwc_in(sv["pa"], ops.pack_conv_weight(bp[2], dtype), 3, 3, 1)
+            r = ops.residual_apply_pad(sv["yb"], *sv["nb"], None, sv["r"], 1, 1, out_mode)
         S["blocks"].append(sv)
     S["r_last"] = r
-    yu1, part = ops.upconv2x_nhwc(r, ops.pack_upconv_weight(u1[0], dtype))
-    S["yu1"], S["nu1"] = yu1, ops.in_finalize(part, H * W // 4)
-    S["pu1"] = ops.in_apply_pad(yu1, *S["nu1"], 1, PAD_ZERO, ACT_RELU)
-    yu2, part = ops.upconv2x_merged_nhwc(S["pu1"], ops.pack_upconv_merged_weight(u2[0], dtype))
-    S["yu2"], S["nu2"] = yu2, ops.in_finalize(part, H * W)
-    S["pout"] = ops.in_apply_pad(yu2, *S["nu2"], 3, PAD_REFLECT, ACT_RELU)
+    S["yu1"], S["nu1"] = ops.upconv2x_nhwc_in(r, ops.pack_upconv_weight(u1[0], dtype), merged=False)
+    S["pu1"] = ops.in_apply_pad(S["yu1"], *S["nu1"], 1, PAD_ZERO, ACT_RELU)
+    S["yu2"], S["nu2"] = ops.upconv2x_nhwc_in(S["pu1"], ops.pack_upconv_merged_weight(u2[0], dtype), merged=True)
+    S["pout"] = ops.in_apply_pad(S["yu2"], *S["nu2"], 3, PAD_REFLECT, ACT_RELU)
     out = ops.out_conv7x7_tanh(S["pout"], ops.pack_out_weight(outp[0], dtype), outp[1])
     S["out"] = out
     return out, S

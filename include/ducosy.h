@@ -112,6 +112,20 @@ int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, void* out, f
 int ducosy_upconv2x_merged_nhwc(const void* in_pad, const void* w_merged, void* out, float* partials, int B, int Hs,
                                 int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream);
 
+/* The three convolution entry points above with the InstanceNorm finalize (ducosy_in_finalize without the CBAM weights) fused
+ * into the same launch: the CTA that completes the last tile of a sample reduces that sample's per-tile partials in fixed
+ * order and writes scale = 1/sqrt(var + 1e-5), shift = -mean * scale [B][Cout] (and, when chmax != NULL, the per-channel max
+ * of the normalised map).  `partials` is still required (it is the reduction's input).  `tickets`: int32 [B] in device memory,
+ * ZERO before the first use and left zero by every launch; launches that may overlap (different streams) need different
+ * ticket arrays.  Removes one dependent launch behind every convolution (modules/model.py:94-111: Conv -> InstanceNorm). */
+int ducosy_conv2d_nhwc_in(const void* in, const void* w, void* out, float* partials, float* scale, float* shift, float* chmax,
+                          int* tickets, int B, int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, int dtype,
+                          ducosy_stream_t stream);
+int ducosy_upconv2x_nhwc_in(const void* in_pad, const void* w_packed4, void* out, float* partials, float* scale, float* shift,
+                            int* tickets, int B, int Hs, int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream);
+int ducosy_upconv2x_merged_nhwc_in(const void* in_pad, const void* w_merged, void* out, float* partials, float* scale, float* shift,
+                                   int* tickets, int B, int Hs, int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream);
+
 /* im2col for the 7x7 reflect-padded stem (modules/model.py:94): x fp32 NCHW [B][Cin][H][W] -> A [B*H*W][Kpad]. */
 int ducosy_stem_im2col(const float* x_nchw, void* a_mat, int B, int Cin, int H, int W, int dtype, ducosy_stream_t stream);
 /* Same, fused with the HU windowing of modules/preprocess.py:72-84 (Cin = 1): stored px int16 [B][H][W] in. */

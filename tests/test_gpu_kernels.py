@@ -395,3 +395,25 @@ def test_upconv2x_backward_matches_autograd(ops, case):
     F.conv2d(F.interpolate(xr, scale_factor=2, mode="nearest"), wr, padding=1).backward(dy.float().cuda())
     assert (dsrc.float().permute(0, 3, 1, 2) - xr.grad).abs().max().item() <= 4e-3 * xr.grad.abs().max().item() + 1e-2
     assert (dw - wr.grad).abs().max().item() <= 2e-3 * wr.grad.abs().max().item() + 1e-2
+
+
+@pytest.mark.parametrize("B,H,W,Cin,Cout,stride", [(3, 32, 128, 256, 256, 1), (2, 64, 64, 64, 128, 2), (1, 128, 128, 128, 64, 1)])
+def test_conv_with_fused_instance_norm_finalize_matches_separate_finalize(B, H, W, Cin, Cout, stride, monkeypatch):
+    """ducosy_conv2d_nhwc_in (the InstanceNorm finalize done by the CTA that completes a sample's last tile; opt-in via
+    DUCOSY_FUSED_FINALIZE=1) against conv + ducosy_in_finalize: identical conv output, statistics equal to fp32 rounding of the
+    two summation orders, ticket array left zero (re-launchable), deterministic."""
+    from ducosy_gan_b200 import ops
+    g = torch.Generator().manual_seed(B * 1000 + Cout)
+    x = (torch.randn(B, H + 2, W + 2, Cin, generator=g)).to(torch.float16).cuda()
+    w = ops.pack_conv_weight((torch.randn(Cout, Cin, 3, 3, generator=g) * 0.05).cuda(), torch.float16)
+    monkeypatch.setenv("DUCOSY_FUSED_FINALIZE", "0")
+    y0, (s0, h0, m0) = ops.conv2d_nhwc_in(x, w, 3, 3, stride, want_chmax=True)
+    monkeypatch.setenv("DUCOSY_FUSED_FINALIZE", "1")
+    for _ in range(2):                                  # second launch: the tickets reset themselves
+        y1, (s1, h1, m1) = ops.conv2d_nhwc_in(x, w, 3, 3, stride, want_chmax=True)
+        assert torch.equal(y0, y1)
+        for a, b in ((s0, s1), (h0, h1), (m0, m1)):
+            assert (a - b).abs().max().item() <= 2e-6 * b.abs().max().item() + 1e-7
+    y2, (s2, h2, m2) = ops.conv2d_nhwc_in(x, w, 3, 3, stride, want_chmax=True)
+    assert torch.equal(s1, s2) and torch.equal(h1, h2) and torch.equal(m1, m2)
+    assert int(ops._tickets(x.device, B).abs().sum()) == 0
