@@ -478,7 +478,7 @@ def main():
         padded = torch.zeros((n_max, H, W), dtype=torch.int16, device=device)
         padded[: hi - lo] = shard_out
         gathered = torch.empty((world * n_max, H, W), dtype=torch.int16, device=device)
-        dist.all_gather_into_tensor(gathered, padded)
+        dist.all_gather_into_tensor(gathered.view(torch.uint8), padded.view(torch.uint8))     # NCCL has no int16
         # single-GPU time of the same volume, measured in this run on rank 0 while the others idle
         for_n1 = 0.0
         if rank == 0:

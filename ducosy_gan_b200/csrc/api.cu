@@ -455,7 +455,7 @@ extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
   // stem 4 (Cin = 1), 2 x (conv + finalize + apply) down, per block 2 x (conv + finalize) + apply + residual (+ channel MLP + pool;
   // the spatial-attention conv runs inside the residual pass), 2 x (up conv + finalize) + 1 apply, output conv
-  return 18 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 2 : 0));
+  return 16 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 2 : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,
