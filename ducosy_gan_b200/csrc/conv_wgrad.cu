@@ -172,10 +172,12 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   }
 }
 
-// dw[o][tap*Cin + c] = sum over splits, fixed order
+// dw = sum over splits, fixed order.  oihw == 0: packed forward layout dw[o][tap*Cin + c]; oihw != 0: the parameter's own layout
+// dw[o][c][tap] times gs[1] (the inverse gradient scale) -- reduce and unpack in one pass
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
-                                    int Cout, int Cin) {
+                                    int Cout, int Cin, int oihw, const float* __restrict__ gs) {
   const long long per_split = (long long)taps * Cout * Cin;
+  const float inv = (oihw != 0 && gs != nullptr) ? gs[1] : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_split; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % Cin);
     long long r = i / Cin;
@@ -183,7 +185,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     const int tap = int(r / Cout);
     float acc = 0.f;
     for (int s = 0; s < splits; ++s) acc += partial[s * per_split + i];
-    dw[((long long)o * taps + tap) * Cin + c] = acc;
+    if (oihw != 0) dw[((long long)o * Cin + c) * taps + tap] = acc * inv;
+    else dw[((long long)o * taps + tap) * Cin + c] = acc;
   }
 }
 
@@ -204,6 +207,11 @@ int encode_nhwc_map(CUtensorMap* tm, CUtensorMapDataType dt, const void* base, i
 
 // K splits: one CTA per SM and unit.  The grid must not spill into an extra wave (297 CTAs on 148 SMs run as long as
 // 444), so the count is rounded DOWN to whole waves: two waves of light CTAs, one wave of the double-M ones.
+// Two 128-row blocks of Cout per CTA share the B tiles (a third less L2 -> SMEM traffic), but double the fp32 partial tile
+// every CTA writes and halve the number of units; with few pixel chunks (one or two 128x128 samples) the kernel is bound by
+// that epilogue and by the split-K reduction behind it, so small problems take one block per CTA and half as many splits.
+int wgrad_m_per_cta(int m_blocks, int chunks) { return (m_blocks % 2 == 0 && chunks >= 512) ? 2 : 1; }
+
 int wgrad_splits(int units, int m_per_cta, int chunks) {
   const int target = (m_per_cta == 2 ? 1 : 2) * 148;
   int splits = target / units;
@@ -220,16 +228,17 @@ using namespace ducosy;
 extern "C" size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int Cout, int kh, int kw) {
   if (B <= 0 || Ho <= 0 || Wo <= 0) return 0;
   const int chunks = B * Ho * Wo / kKChunk;
-  const int m_blocks = (Cout + 127) / 128, m_per_cta = (m_blocks % 2 == 0) ? 2 : 1;
+  const int m_blocks = (Cout + 127) / 128, m_per_cta = wgrad_m_per_cta(m_blocks, chunks);
   const int splits = wgrad_splits(kh * kw * (m_blocks / m_per_cta), m_per_cta, chunks);
   return size_t(splits) * kh * kw * Cout * Cin * 4;
 }
 
 // x_pad: the padded NHWC input the forward conv read ([B][Hp][Wp][Cin]); dy: NHWC output gradient
 // [B][Ho+2*dy_pad][Wo+2*dy_pad][Cout] (interior used), 16-bit both; dw: fp32 [Cout][kh*kw*Cin] in the packed forward layout (k = (r*kw+s)*Cin + c).
-extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp,
-                                        int Cin, int Cout, int kh, int kw, int stride, void* workspace,
-                                        size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
+namespace {
+int conv2d_wgrad_impl(const void* x_pad, const void* dy, int dy_pad, float* dw, int oihw, const float* gs, int B, int Hp, int Wp,
+                      int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
+                      ducosy_stream_t stream) {
   DUCOSY_CHECK(x_pad && dy && dw && workspace && B > 0, DUCOSY_ERR_ARG, "conv2d_wgrad: null pointer");
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_wgrad: bad dtype");
   DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
@@ -258,7 +267,7 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
       else { a.tap_xp[t] = int8_t(s & 1); a.tap_dx[t] = int8_t(s >> 1); a.tap_yp[t] = int8_t(r & 1); a.tap_dy[t] = int8_t(r >> 1); }
     }
   const int chunks = B * a.TY * a.TX;
-  a.m_per_cta = (a.m_blocks % 2 == 0) ? 2 : 1;   // two 128-row blocks of Cout share the B tiles: a third less L2 -> SMEM traffic
+  a.m_per_cta = wgrad_m_per_cta(a.m_blocks, chunks);
   a.stages = a.m_per_cta == 2 ? 3 : kWgStages;
   const int units = a.num_taps * (a.m_blocks / a.m_per_cta);
   int splits = wgrad_splits(units, a.m_per_cta, chunks);
@@ -294,8 +303,23 @@ extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int d
   const long long per_split = (long long)a.num_taps * Cout * Cin;
   long long blocks = (per_split + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dw, splits, a.num_taps, Cout, Cin);
+  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dw, splits, a.num_taps, Cout, Cin, oihw, gs);
   return check_launch("wgrad_reduce_kernel");
+}
+}  // namespace
+
+extern "C" int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp,
+                                        int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                                        size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
+  return conv2d_wgrad_impl(x_pad, dy, dy_pad, dw, 0, nullptr, B, Hp, Wp, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, dtype, stream);
+}
+
+// The same, reduced straight into the parameter's own layout: dw_oihw fp32 [Cout][Cin][kh][kw] times gs[1] (gs = the pair of
+// ducosy_grad_scale, may be NULL) -- ducosy_conv2d_wgrad_nhwc + ducosy_unpack_wgrad in one reduction pass.
+extern "C" int ducosy_conv2d_wgrad_nhwc_oihw(const void* x_pad, const void* dy, int dy_pad, float* dw_oihw, const float* gs, int B,
+                                             int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                                             size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
+  return conv2d_wgrad_impl(x_pad, dy, dy_pad, dw_oihw, 1, gs, B, Hp, Wp, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, dtype, stream);
 }
 
 // Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) without materialising the
@@ -375,7 +399,7 @@ extern "C" int ducosy_upconv2x_wgrad_nhwc(const void* src_pad, const void* dy, i
   const long long per_split = (long long)a.num_taps * Cout * Cin;
   long long blocks = (per_split + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dwph, splits, a.num_taps, Cout, Cin);
+  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dwph, splits, a.num_taps, Cout, Cin, 0, nullptr);
   return check_launch("wgrad_reduce_kernel");
 }
 

@@ -286,6 +286,7 @@ class _GeneratorFunction(torch.autograd.Function):
             out, saved = training.generator_forward_train(ps, cfg, xs, dtype)
         saved.pop("out")
         ctx.cfg, ctx.saved, ctx.params, ctx.in_shape, ctx.cache = cfg, saved, ps, tuple(x.shape), cache
+        ctx.param_refs = params
         ctx.save_for_backward(out)
         return out
 
@@ -302,6 +303,11 @@ class _GeneratorFunction(torch.autograd.Function):
                 full[:, :1] = dx
                 dx = full
         ctx.saved = None
+        # exact-zero gradients (dead biases): a parameter that already holds a gradient tensor (flat data-parallel bucket, an
+        # earlier backward) is left alone -- adding zeros would be two launches per bias for nothing; one without gets real zeros
+        grads = [g if g is not None or (p.is_leaf and p.grad is not None) else torch.zeros_like(p, dtype=torch.float32)
+                 for g, p in zip(grads, ctx.param_refs)]
+        ctx.param_refs = None
         return (None, dx, *grads)
 
 

@@ -394,6 +394,23 @@ def conv2d_wgrad_nhwc(x_pad, dy, kh, kw, stride, dy_pad=0):
     return dw
 
 
+def conv2d_wgrad_oihw(x_pad, dy, kh, kw, stride, dy_pad=0, gs=None):
+    """Weight gradient in the parameter's own layout, fp32 [Cout,Cin,kh,kw], true scale (times gs[1]): conv2d_wgrad_nhwc and
+    unpack_wgrad in one reduction pass."""
+    B, Hp, Wp, Cin = x_pad.shape
+    _, Ho, Wo, Cout = dy.shape
+    Ho, Wo = Ho - 2 * dy_pad, Wo - 2 * dy_pad
+    assert x_pad.is_contiguous() and dy.is_contiguous() and x_pad.dtype == dy.dtype
+    lib = _lib.load()
+    with _dev(x_pad):
+        need = lib.ducosy_conv2d_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, kh, kw)
+        ws = torch.empty(max(need, 16), dtype=torch.uint8, device=x_pad.device)
+        dw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=x_pad.device)
+        call("ducosy_conv2d_wgrad_nhwc_oihw", ptr(x_pad), ptr(dy), int(dy_pad), ptr(dw), ptr(gs), B, Hp, Wp, Cin, Cout, kh, kw, stride,
+             ptr(ws), ws.numel(), dtype_code(x_pad.dtype), stream_ptr())
+    return dw
+
+
 def in_backward_pad(da, y, scale, shift, pad, act):
     """InstanceNorm(+activation) backward: da, y NHWC 16-bit -> dy zero-padded [B,H+2p,W+2p,C]."""
     B, H, W, Cn = y.shape

@@ -66,12 +66,12 @@ def generator_forward_train(params, cfg, x, dtype):
 
 def generator_backward(params, cfg, S, dout, want_dx=True):
     """dout fp32 [B,1,H,W] -> (list of fp32 parameter gradients in named_parameters() order, dx fp32 [B,1,H,W] | None).
-    Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant)."""
+    Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant), returned as None."""
     _, num_blocks, use_cbam = cfg
     stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
     dout = dout.to(torch.float32).contiguous()
     gs = ops.grad_scale(dout)
-    zero = lambda p: torch.zeros_like(p, dtype=torch.float32)
+    zero = lambda p: None      # dead bias (in front of a non-affine InstanceNorm): exact zero gradient, materialised by the caller if needed
 
     da, dw_out, db_out = ops.out_conv_backward(dout, S["out"], S["pout"], outp[0], gs)
     dyu2 = ops.in_backward_pad(da, S["yu2"], *S["nu2"], 2, ACT_RELU)
@@ -88,19 +88,19 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
             cbam_grads = []
             dyb = ops.in_backward_pad(dr, sv["yb"], *sv["nb"], 2, ACT_NONE)
         C = bp[0].shape[0]
-        dw_b = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(sv["pa"], dyb, 3, 3, 1, dy_pad=2), C, C, 9, gs)
+        dw_b = ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs)
         dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
         dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
-        dw_a = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(sv["r"], dya, 3, 3, 1, dy_pad=2), C, C, 9, gs)
+        dw_a = ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs)
         dr, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT, add=dr)     # conv path + skip connection
         block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)
     block_grads.reverse()
 
     dy2 = ops.in_backward_pad(dr, S["y2"], *S["n2"], 1, ACT_RELU)
-    dw_d2 = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(S["p1"], dy2, 3, 3, 2, dy_pad=1), d2[0].shape[0], d2[0].shape[1], 9, gs)
+    dw_d2 = ops.conv2d_wgrad_oihw(S["p1"], dy2, 3, 3, 2, dy_pad=1, gs=gs)
     dp1 = ops.convs2_dgrad_nhwc(dy2, d2[0])
     dy1 = ops.in_backward_pad(dp1, S["y1"], *S["n1"], 1, ACT_RELU)
-    dw_d1 = ops.unpack_wgrad(ops.conv2d_wgrad_nhwc(S["p0"], dy1, 3, 3, 2, dy_pad=1), d1[0].shape[0], d1[0].shape[1], 9, gs)
+    dw_d1 = ops.conv2d_wgrad_oihw(S["p0"], dy1, 3, 3, 2, dy_pad=1, gs=gs)
     dp0 = ops.convs2_dgrad_nhwc(dy1, d1[0])
     dy0 = ops.in_backward_pad(dp0, S["y0"], *S["n0"], 0, ACT_RELU)
     dw_stem, dx = ops.stem_backward(dy0, S["cols"], stem[0], gs, want_dx)

@@ -380,6 +380,11 @@ size_t ducosy_conv2d_wgrad_workspace_bytes(int B, int Ho, int Wo, int Cin, int C
 int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, float* dw, int B, int Hp, int Wp, int Cin,
                              int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes, int dtype,
                              ducosy_stream_t stream);
+/* The same, reduced straight into the parameter's own layout: dw_oihw fp32 [Cout][Cin][kh][kw], multiplied by gs[1] when gs
+ * (the pair written by ducosy_grad_scale) is non-NULL: ducosy_conv2d_wgrad_nhwc + ducosy_unpack_wgrad in one reduction pass. */
+int ducosy_conv2d_wgrad_nhwc_oihw(const void* x_pad, const void* dy, int dy_pad, float* dw_oihw, const float* gs, int B, int Hp,
+                                  int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes,
+                                  int dtype, ducosy_stream_t stream);
 
 /* Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) on the SOURCE grid: the gradient of
  * the 16 pre-summed (phase, tap) blocks of ducosy_pack_upconv_weight (4/9 of the MACs of a wgrad over the up-sampled map,

@@ -19,22 +19,33 @@ ap.add_argument("--no-cbam", action="store_true")
 ap.add_argument("--steps", type=int, default=5)
 ap.add_argument("--warmup", type=int, default=2)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--graph", action="store_true", help="replay the whole step from a CUDA graph (what bench.py times)")
 ap.add_argument("--out", default="")
 a = ap.parse_args()
 
-step = CycleGANStep(a.cin, a.blocks, not a.no_cbam, seed=1234)
+if a.graph:
+    from ducosy_gan_b200.data_parallel import DataParallelCycleGANStep, GraphedCycleGANStep  # noqa: E402
+    step = DataParallelCycleGANStep(a.cin, a.blocks, not a.no_cbam, seed=1234, capturable=True)
+else:
+    step = CycleGANStep(a.cin, a.blocks, not a.no_cbam, seed=1234)
 g = torch.Generator().manual_seed(2)
 B = a.batch
 real_A = (torch.rand(B, 1, 512, 512, generator=g) * 2 - 1).cuda()
 real_B = (torch.rand(B, 1, 512, 512, generator=g) * 2 - 1).cuda()
 masks = (torch.rand(B, a.cin - 1, 512, 512, generator=g) < 0.1).float().cuda() if a.cin > 1 else None
-for _ in range(a.warmup):
-    out = step.step(real_A, real_B, masks)
+if a.graph:
+    graphed = GraphedCycleGANStep(step, real_A, real_B, masks, warmup=max(a.warmup, 2))
+    step_fn = lambda: graphed(real_A, real_B, masks)
+    step_fn()
+else:
+    step_fn = lambda: step.step(real_A, real_B, masks)
+    for _ in range(a.warmup):
+        out = step_fn()
 torch.cuda.synchronize()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for _ in range(a.steps):
-    out = step.step(real_A, real_B, masks)
+    out = step_fn()
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / a.steps
@@ -50,7 +61,7 @@ if a.out:
 if a.profile:
     from torch.profiler import ProfilerActivity, profile
     with profile(activities=[ProfilerActivity.CUDA]) as prof:
-        step.step(real_A, real_B, masks)
+        step_fn()
         torch.cuda.synchronize()
     agg = {}
     for ev in prof.events():
