@@ -12,7 +12,7 @@ import torch
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libducosy_sm100.so")
 
-F16, BF16 = 0, 1
+F16, BF16, F16X2 = 0, 1, 2   # F16X2: split-operand (hi, lo) fp16 pairs, generator inference only (include/ducosy.h)
 PAD_ZERO, PAD_REFLECT = 0, 1
 ACT_NONE, ACT_RELU, ACT_LRELU02 = 0, 1, 2
 
@@ -181,7 +181,9 @@ def dtype_code(dtype) -> int:
         return F16
     if dtype in (torch.bfloat16, "bf16", BF16):
         return BF16
-    raise ValueError(f"unsupported operand dtype {dtype!r} (fp16 or bf16)")
+    if dtype in ("fp16x2", "f16x2", "split"):
+        return F16X2
+    raise ValueError(f"unsupported operand dtype {dtype!r} (fp16, bf16, or fp16x2 for the generator's inference path)")
 
 
 def torch_dtype(code: int):

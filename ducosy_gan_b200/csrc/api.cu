@@ -83,27 +83,28 @@ struct GenLayout {
 GenLayout make_layout(const ducosy_gen_config& c) {
   GenLayout L;
   L.Kpad = (49 * c.input_channels + 63) / 64 * 64;
+  const size_t e = c.dtype == DUCOSY_F16X2 ? 4 : 2;   // bytes per packed conv weight (split-operand mode: a hi and a lo value)
   size_t off = 0;
   auto take = [&](size_t bytes) {
     const size_t o = off;
     off = align_up(off + bytes, 256);
     return o;
   };
-  L.stem = take(size_t(64) * L.Kpad * 2);
-  L.d1 = take(size_t(128) * 9 * 64 * 2);
-  L.d2 = take(size_t(256) * 9 * 128 * 2);
+  L.stem = take(size_t(64) * L.Kpad * e);
+  L.d1 = take(size_t(128) * 9 * 64 * e);
+  L.d2 = take(size_t(256) * 9 * 128 * e);
   for (int i = 0; i < c.num_residual_blocks; ++i) {
-    L.c1.push_back(take(size_t(256) * 9 * 256 * 2));
-    L.c2.push_back(take(size_t(256) * 9 * 256 * 2));
+    L.c1.push_back(take(size_t(256) * 9 * 256 * e));
+    L.c2.push_back(take(size_t(256) * 9 * 256 * e));
     if (c.use_cbam) {
       L.fc0.push_back(take(16 * 256 * 4));
       L.fc2.push_back(take(256 * 16 * 4));
       L.saw.push_back(take(98 * 4));
     }
   }
-  L.up1 = take(size_t(4) * 128 * 4 * 256 * 2);
-  L.up2 = take(size_t(4) * 64 * 9 * 128 * 2);  // merged-phase packing (N = 256, nine source offsets)
-  L.outw = take(7 * 8 * 64 * 2);
+  L.up1 = take(size_t(4) * 128 * 4 * 256 * e);
+  L.up2 = take(size_t(4) * 64 * 9 * 128 * e);  // merged-phase packing (N = 256, nine source offsets); split mode: four 2x2 phases
+  L.outw = take(7 * 8 * 64 * e);
   L.outb = take(4);
   L.total = off;
   return L;
@@ -124,14 +125,15 @@ GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
   };
   const size_t HW = size_t(H) * W;
   const int H2 = H / 2, W2 = W / 2, H4 = H / 4, W4 = W / 4;
-  w.a_stem = take(size_t(B) * HW * L.Kpad * 2);
-  w.y0 = take(size_t(B) * HW * 64 * 2);
-  w.p0 = take(size_t(B) * (H + 2) * (W + 2) * 64 * 2);
-  w.y1 = take(size_t(B) * H2 * W2 * 128 * 2);
-  w.p1 = take(size_t(B) * (H2 + 2) * (W2 + 2) * 128 * 2);
-  w.y2a = take(size_t(B) * H4 * W4 * 256 * 2);
-  w.y2b = take(size_t(B) * H4 * W4 * 256 * 2);
-  const size_t padded = size_t(B) * (H4 + 2) * (W4 + 2) * 256 * 2;
+  const size_t e = c.dtype == DUCOSY_F16X2 ? 4 : 2;   // bytes per activation (split-operand mode: hi and lo plane per pixel)
+  w.a_stem = take(size_t(B) * HW * L.Kpad * e);
+  w.y0 = take(size_t(B) * HW * 64 * e);
+  w.p0 = take(size_t(B) * (H + 2) * (W + 2) * 64 * e);
+  w.y1 = take(size_t(B) * H2 * W2 * 128 * e);
+  w.p1 = take(size_t(B) * (H2 + 2) * (W2 + 2) * 128 * e);
+  w.y2a = take(size_t(B) * H4 * W4 * 256 * e);
+  w.y2b = take(size_t(B) * H4 * W4 * 256 * e);
+  const size_t padded = size_t(B) * (H4 + 2) * (W4 + 2) * 256 * e;
   w.pa = take(padded);
   w.pb = take(padded);
   w.pc = take(padded);
@@ -150,7 +152,8 @@ GenWorkspace make_workspace(const ducosy_gen_config& c, int B, int H, int W) {
 int check_gen_shape(const ducosy_gen_config& c, int B, int H, int W) {
   DUCOSY_CHECK(c.input_channels >= 1 && c.input_channels <= 16, DUCOSY_ERR_SHAPE, "generator: input_channels %d unsupported", c.input_channels);
   DUCOSY_CHECK(c.num_residual_blocks >= 0 && c.num_residual_blocks <= 64, DUCOSY_ERR_SHAPE, "generator: num_residual_blocks out of range");
-  DUCOSY_CHECK(c.dtype == DUCOSY_F16 || c.dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "generator: dtype must be DUCOSY_F16 or DUCOSY_BF16");
+  DUCOSY_CHECK(c.dtype == DUCOSY_F16 || c.dtype == DUCOSY_BF16 || c.dtype == DUCOSY_F16X2, DUCOSY_ERR_ARG,
+               "generator: dtype must be DUCOSY_F16, DUCOSY_BF16 or DUCOSY_F16X2");
   DUCOSY_CHECK(B >= 1, DUCOSY_ERR_SHAPE, "generator: batch must be >= 1");
   DUCOSY_CHECK(H >= 128 && W >= 128 && W % 128 == 0 && H % 32 == 0, DUCOSY_ERR_SHAPE,
                "generator: H must be a multiple of 32 and W a multiple of 128, both >= 128 (got %dx%d)", H, W);
@@ -232,7 +235,7 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   const int dt = c.dtype;
 
   // ---- stem: reflect-pad 3 + 7x7 conv, IN, ReLU   modules/model.py:94
-  if (c.input_channels == 1) {
+  if (c.input_channels == 1 && dt != DUCOSY_F16X2) {
     // fused two-pass stem (stem.cu): statistics pass, then conv + normalise + ReLU written once, zero-padded
     DUCOSY_TRY(ducosy_stem_prepare(x, px, slope, intercept, lo, hi, P(w.a_stem), B, H, W, dt, st));
     DUCOSY_TRY(ducosy_stem_fused(P(w.a_stem), pk + L.stem, partials, nullptr, nullptr, nullptr, B, H, W, 0, dt, st));
@@ -317,7 +320,8 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
   // ---- up 2: nearest x2 + 3x3 p1 128 -> 64, IN, ReLU
   {
     ConvPlan p{};
-    upconv_merged_plan(p, P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt);
+    if (dt == DUCOSY_F16X2) upconv_plan(p, P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt);
+    else upconv_merged_plan(p, P(w.p1), pk + L.up2, P(w.y0), partials, B, H2, W2, 128, 64, dt);
     DUCOSY_TRY(run_conv_in(p, scale, shift, nullptr, nullptr, nullptr, tickets, H * W, st));
   }
   // ---- output: IN apply + ReLU + reflect-pad 3 folded into the loader of the 7x7 conv 64 -> 1 + tanh   modules/model.py:110-112
@@ -338,7 +342,7 @@ extern "C" int ducosy_conv2d_nhwc(const void* in, const void* w, void* out, floa
                                   int B, int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, int dtype,
                                   ducosy_stream_t stream) {
   DUCOSY_CHECK(in && w && out && B > 0, DUCOSY_ERR_ARG, "conv2d_nhwc: null pointer");
-  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "conv2d_nhwc: bad dtype");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16 || dtype == DUCOSY_F16X2, DUCOSY_ERR_ARG, "conv2d_nhwc: bad dtype");
   DUCOSY_CHECK(kh == kw && (kh == 1 || kh == 3 || kh == 4) && (stride == 1 || stride == 2), DUCOSY_ERR_SHAPE,
                "conv2d_nhwc: kernel %dx%d stride %d unsupported", kh, kw, stride);
   DUCOSY_CHECK(act == DUCOSY_ACT_NONE || (act == DUCOSY_ACT_LRELU02 && bias != nullptr), DUCOSY_ERR_ARG,
@@ -362,7 +366,7 @@ extern "C" int ducosy_conv2d_nhwc(const void* in, const void* w, void* out, floa
 extern "C" int ducosy_upconv2x_nhwc(const void* in_pad, const void* w_packed4, void* out, float* partials, int B, int Hs,
                                     int Ws, int Cin, int Cout, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(in_pad && w_packed4 && out && B > 0, DUCOSY_ERR_ARG, "upconv2x_nhwc: null pointer");
-  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "upconv2x_nhwc: bad dtype");
+  DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16 || dtype == DUCOSY_F16X2, DUCOSY_ERR_ARG, "upconv2x_nhwc: bad dtype");
   DUCOSY_TRY(check_device_cached());
   ConvPlan p{};
   upconv_plan(p, in_pad, w_packed4, out, partials, B, Hs, Ws, Cin, Cout, dtype);
@@ -464,7 +468,7 @@ extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* 
   const ducosy_gen_config& c = *cfg;
   DUCOSY_CHECK(num_params == ducosy_generator_num_params(cfg), DUCOSY_ERR_ARG,
                "generator_pack: expected %d parameter tensors, got %d", ducosy_generator_num_params(cfg), num_params);
-  DUCOSY_CHECK(c.dtype == DUCOSY_F16 || c.dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "generator_pack: bad dtype");
+  DUCOSY_CHECK(c.dtype == DUCOSY_F16 || c.dtype == DUCOSY_BF16 || c.dtype == DUCOSY_F16X2, DUCOSY_ERR_ARG, "generator_pack: bad dtype");
   DUCOSY_CHECK((reinterpret_cast<uintptr_t>(packed) & 255) == 0, DUCOSY_ERR_ALIGN, "generator_pack: packed buffer must be 256-byte aligned");
   for (int i = 0; i < num_params; ++i) DUCOSY_CHECK(params[i] != nullptr, DUCOSY_ERR_ARG, "generator_pack: parameter %d is null", i);
   const GenLayout L = make_layout(c);
@@ -485,7 +489,9 @@ extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* 
     }
   }
   DUCOSY_TRY(ducosy_pack_upconv_weight(params[k], pk + L.up1, 128, 256, c.dtype, stream)); k += 2;
-  DUCOSY_TRY(ducosy_pack_upconv_merged_weight(params[k], pk + L.up2, 64, 128, c.dtype, stream)); k += 2;
+  if (c.dtype == DUCOSY_F16X2) { DUCOSY_TRY(ducosy_pack_upconv_weight(params[k], pk + L.up2, 64, 128, c.dtype, stream)); }
+  else { DUCOSY_TRY(ducosy_pack_upconv_merged_weight(params[k], pk + L.up2, 64, 128, c.dtype, stream)); }
+  k += 2;
   DUCOSY_TRY(ducosy_pack_out_weight(params[k++], pk + L.outw, c.dtype, stream));
   cudaMemcpyAsync(pk + L.outb, params[k++], 4, cudaMemcpyDeviceToDevice, st);
   return check_launch("generator_pack");

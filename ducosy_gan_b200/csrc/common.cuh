@@ -51,6 +51,7 @@ struct PerDeviceOnce {
 };
 
 constexpr int kMaxTaps = 16;
+constexpr int kMaxVTaps = 32;   // "virtual" taps of the split-operand mode: 3 per filter tap (A_hi*W_hi, A_lo*W_hi, A_hi*W_lo)
 constexpr int kMaxPhases = 4;
 
 // InstanceNorm finalize fused into the tail of the convolution (conv_gemm.cu: finalize_sample).  The CTA whose tile is the
@@ -77,8 +78,11 @@ struct ConvGemmArgs {
   int Cout;                // GEMM N total (= n_blocks * kN) = fold * Cstore
   int Cstore;              // channels of the output tensor
   int fold;                // 1, or 4: the four x2-upsampling phases are column blocks of ONE tile (merged phases)
-  int8_t tap_xp[kMaxPhases][kMaxTaps], tap_dx[kMaxPhases][kMaxTaps];
-  int8_t tap_yp[kMaxPhases][kMaxTaps], tap_dy[kMaxPhases][kMaxTaps];
+  int8_t tap_xp[kMaxPhases][kMaxVTaps], tap_dx[kMaxPhases][kMaxVTaps];
+  int8_t tap_yp[kMaxPhases][kMaxVTaps], tap_dy[kMaxPhases][kMaxVTaps];
+  int8_t tap_c0[kMaxPhases][kMaxVTaps];   // channel offset of the A tile in 64-channel units (split mode: 0 = hi plane, Cin/64 = lo plane)
+  int16_t tap_bk[kMaxVTaps];              // column offset of the tap's weight block in 64-column units (t * kc_per_tap when not split)
+  int split;               // 1: split-operand mode -- activations are (hi, lo) fp16 pairs stored as 2*C channels per pixel
   void* out;               // raw conv output, NHWC [B, Ho, Wo, Cout]
   long long out_bs;        // elements per sample
   int out_rs, out_ps;      // elements per output row / pixel
@@ -109,7 +113,7 @@ struct ConvPlan {
   float* partials;
   const float* bias;
   int epi_mode;
-  int dtype;
+  int dtype;               // DUCOSY_F16 / DUCOSY_BF16, or DUCOSY_F16X2: split-operand mode (see ducosy.h)
   ConvFinalize fin;
 };
 
@@ -142,8 +146,8 @@ template <> struct Cvt<__nv_bfloat16> {
 
 #define DUCOSY_DISPATCH_DTYPE(dtype, T, ...)                         \
   do {                                                               \
-    if ((dtype) == DUCOSY_F16) { using T = __half; __VA_ARGS__; }    \
-    else { using T = __nv_bfloat16; __VA_ARGS__; }                   \
+    if ((dtype) == DUCOSY_BF16) { using T = __nv_bfloat16; __VA_ARGS__; } \
+    else { using T = __half; __VA_ARGS__; }  /* DUCOSY_F16, DUCOSY_F16X2 */ \
   } while (0)
 
 }  // namespace ducosy

@@ -41,8 +41,9 @@ constexpr int kEpiThreads = 256;
 // kCG = 1: one CTA per 128 x kN tile.  kCG = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x kN
 // tile; each CTA stages its own 128 A rows and HALF of the B rows, so L2->SMEM traffic per FLOP drops by a third
 // and the same shared memory holds 6 instead of 4 pipeline stages.
-template <int kN, int kCG>
+template <int kN, int kCG, bool kSplit = false>
 struct Cfg {
+  static constexpr int kPlanes = kSplit ? 2 : 1;  // split-operand mode stages a (hi, lo) pair of 16-bit tiles
   static constexpr int kBRows = kN / kCG;
   static constexpr int kBBytes = kBRows * kBlockK * 2;
   static constexpr int kStageBytes = kABytes + kBBytes;
@@ -50,7 +51,8 @@ struct Cfg {
   // epilogue staging: the 16-bit output tile as kSlabs x [128 rows][64 channels] in the TMA 128-byte-swizzle layout
   static constexpr int kSlabs = kN / 64;
   static constexpr int kSlabBytes = kTileM * 128;
-  static constexpr int kOutBytes = kSlabs * kSlabBytes;
+  static constexpr int kPlaneBytes = kSlabs * kSlabBytes;
+  static constexpr int kOutBytes = kPlanes * kPlaneBytes;
   static constexpr int kParts = 8 / kSlabs;       // row parts per slab in the column pass (8 epilogue warps)
   static constexpr int kStatFloats = kParts * 3 * kN;
   static constexpr int kFixedBytes = 1024 + kOutBytes + kStatFloats * 4 + 256;
@@ -179,11 +181,11 @@ __device__ void finalize_sample(const ConvGemmArgs& a, int b, int tiles, uint8_t
   }
 }
 
-template <int kN, typename T, int kCG>
+template <int kN, typename T, int kCG, bool kSplit>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmO, const ConvGemmArgs a) {
-  using C = Cfg<kN, kCG>;
+  using C = Cfg<kN, kCG, kSplit>;
   constexpr int kStages = C::kStages;
   constexpr int kFmt = sizeof(T) == 2 && std::is_same<T, __nv_bfloat16>::value ? 1 : 0;
 
@@ -252,18 +254,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int t = 0; t < a.num_taps; ++t) {
           const int xp = a.tap_xp[tc.phase][t], dx = a.tap_dx[tc.phase][t];
           const int yp = a.tap_yp[tc.phase][t], dy = a.tap_dy[tc.phase][t];
+          const int ca = a.tap_c0[tc.phase][t], kb = a.tap_bk[t];   // 64-channel chunk offsets of the A plane / the B columns
           for (int kc = 0; kc < a.kc_per_tap; ++kc) {
             mbar_wait(&empty[s], ph ^ 1);
             uint8_t* sa = smem + size_t(s) * C::kStageBytes;
             if (kCG == 2) {
               // both CTAs' loads complete on the leader's barrier, which expects the bytes of the whole pair
               if (rank == 0) mbar_arrive_expect_tx(&full[s], 2 * C::kStageBytes);
-              tma_load_5d_cg2(sa, &tmA, &full[s], kc * kBlockK, xp, x0 + dx, yp, row0 + dy);
-              tma_load_2d_cg2(sa + kABytes, &tmB, &full[s], (t * a.kc_per_tap + kc) * kBlockK, n0);
+              tma_load_5d_cg2(sa, &tmA, &full[s], (ca + kc) * kBlockK, xp, x0 + dx, yp, row0 + dy);
+              tma_load_2d_cg2(sa + kABytes, &tmB, &full[s], (kb + kc) * kBlockK, n0);
             } else {
               mbar_arrive_expect_tx(&full[s], C::kStageBytes);
-              tma_load_5d(sa, &tmA, &full[s], kc * kBlockK, xp, x0 + dx, yp, row0 + dy);
-              tma_load_2d(sa + kABytes, &tmB, &full[s], (t * a.kc_per_tap + kc) * kBlockK, n0);
+              tma_load_5d(sa, &tmA, &full[s], (ca + kc) * kBlockK, xp, x0 + dx, yp, row0 + dy);
+              tma_load_2d(sa + kABytes, &tmB, &full[s], (kb + kc) * kBlockK, n0);
             }
             if (++s == kStages) {
               s = 0;
@@ -350,6 +353,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint4 pk = make_uint4(Cvt<T>::pack2(r[8 * i], r[8 * i + 1]), Cvt<T>::pack2(r[8 * i + 2], r[8 * i + 3]),
                                       Cvt<T>::pack2(r[8 * i + 4], r[8 * i + 5]), Cvt<T>::pack2(r[8 * i + 6], r[8 * i + 7]));
           *reinterpret_cast<uint4*>(rowp + ((((ch & 1) * 4 + i) ^ (m & 7)) << 4)) = pk;
+          if (kSplit) {   // lo plane: what the 16-bit rounding of the hi plane dropped (v - hi is exact in fp32)
+            uint32_t hw[4] = {pk.x, pk.y, pk.z, pk.w}, lw[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float2 h = Cvt<T>::unpack2(hw[j]);
+              lw[j] = Cvt<T>::pack2(r[8 * i + 2 * j] - h.x, r[8 * i + 2 * j + 1] - h.y);
+            }
+            *reinterpret_cast<uint4*>(rowp + C::kPlaneBytes + ((((ch & 1) * 4 + i) ^ (m & 7)) << 4)) = make_uint4(lw[0], lw[1], lw[2], lw[3]);
+          }
         }
       }
       tc_fence_before();
@@ -362,9 +374,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int sb = 0; sb < C::kSlabs; ++sb) {
           const int n = tc.nb * kN + sb * 64;
           const int f = n / a.Cstore;  // merged phases: column block -> output phase; otherwise 0
-          tma_store_5d(&tmO, otile + sb * C::kSlabBytes, n - f * a.Cstore, a.fold > 1 ? (f & 1) : a.ox_off[tc.phase],
-                       tc.tx * a.Wt + a.out_x_off, a.fold > 1 ? (f >> 1) : a.oy_off[tc.phase],
-                       tc.b * a.out_rows + tc.ty * a.R + a.out_y_off);
+#pragma unroll
+          for (int pl = 0; pl < C::kPlanes; ++pl)   // split mode: the lo plane lives Cstore channels behind the hi plane
+            tma_store_5d(&tmO, otile + pl * C::kPlaneBytes + sb * C::kSlabBytes, pl * a.Cstore + n - f * a.Cstore,
+                         a.fold > 1 ? (f & 1) : a.ox_off[tc.phase], tc.tx * a.Wt + a.out_x_off,
+                         a.fold > 1 ? (f >> 1) : a.oy_off[tc.phase], tc.b * a.out_rows + tc.ty * a.R + a.out_y_off);
         }
         tma_store_commit();
       }
@@ -375,7 +389,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 8
         for (int rr = 0; rr < kRows; ++rr) {
           const int mr = cp_part * kRows + rr;
-          const float2 f = Cvt<T>::unpack2(*reinterpret_cast<const uint32_t*>(sl + mr * 128 + (((lane >> 2) ^ (mr & 7)) << 4)));
+          float2 f = Cvt<T>::unpack2(*reinterpret_cast<const uint32_t*>(sl + mr * 128 + (((lane >> 2) ^ (mr & 7)) << 4)));
+          if (kSplit) {
+            const float2 l = Cvt<T>::unpack2(*reinterpret_cast<const uint32_t*>(sl + C::kPlaneBytes + mr * 128 + (((lane >> 2) ^ (mr & 7)) << 4)));
+            f.x += l.x;
+            f.y += l.y;
+          }
           s1a += f.x;
           s1b += f.y;
           s2a = fmaf(f.x, f.x, s2a);
@@ -439,12 +458,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 }
 
 // ------------------------------------------------------------------ host side
-template <int kN, typename T, int kCG>
+template <int kN, typename T, int kCG, bool kSplit = false>
 int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmO, const ConvGemmArgs& args,
                 int grid, cudaStream_t stream) {
-  using C = Cfg<kN, kCG>;
+  using C = Cfg<kN, kCG, kSplit>;
   static PerDeviceOnce configured;
-  auto kern = conv_gemm_kernel<kN, T, kCG>;
+  auto kern = conv_gemm_kernel<kN, T, kCG, kSplit>;
   {
     const cudaError_t e = configured.once([&] { return cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, int(C::kSmemBytes)); });
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(conv_gemm): %s", cudaGetErrorString(e));
@@ -488,13 +507,23 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
                    (reinterpret_cast<uintptr_t>(p.out) & 15) == 0,
                DUCOSY_ERR_ALIGN, "conv_gemm: input/weight buffers must be 128-byte aligned, output 16-byte");
 
-  const int kN = p.Cout >= 256 ? 256 : p.Cout;
+  // Split-operand mode (DUCOSY_F16X2, see include/ducosy.h): every activation and weight is a (hi, lo) pair of fp16 values,
+  // hi = rn(v), lo = rn(v - hi).  The input holds the lo plane Cin channels behind the hi plane (2*Cin channels per pixel), the
+  // packed weight holds [all taps hi | all taps lo] along K, and every filter tap becomes three "virtual taps"
+  // A_hi*W_hi + A_lo*W_hi + A_hi*W_lo accumulated in fp32 (the dropped A_lo*W_lo term is ~2^-22 relative).  The output is
+  // written as a (hi, lo) pair again, so the staged tile is twice as large: N is capped at 128.
+  const bool split = p.dtype == DUCOSY_F16X2;
+  const int planes = split ? 2 : 1;
+  const int kN = split ? (p.Cout >= 128 ? 128 : p.Cout) : (p.Cout >= 256 ? 256 : p.Cout);
+  DUCOSY_CHECK(!split || (p.num_taps * 3 <= kMaxVTaps && p.fold <= 1 && p.epi_mode == 0), DUCOSY_ERR_SHAPE,
+               "conv_gemm: split-operand mode supports at most %d taps, no merged phases, no bias epilogue", kMaxVTaps / 3);
   DUCOSY_CHECK(kN == 64 || kN == 128 || kN == 256, DUCOSY_ERR_SHAPE, "conv_gemm: Cout=%d unsupported", p.Cout);
   DUCOSY_CHECK(p.Cout % kN == 0, DUCOSY_ERR_SHAPE, "conv_gemm: Cout=%d unsupported", p.Cout);
 
   ConvGemmArgs a{};
   a.num_phases = p.num_phases;
-  a.num_taps = p.num_taps;
+  a.num_taps = split ? 3 * p.num_taps : p.num_taps;
+  a.split = split ? 1 : 0;
   a.kc_per_tap = p.Cin / kBlockK;
   a.n_blocks = p.Cout / kN;
   a.B = p.B;
@@ -510,17 +539,22 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   a.Cstore = p.Cout / a.fold;
   DUCOSY_CHECK(a.fold == 1 || (a.fold == 4 && p.num_phases == 1 && p.Cout == kN && a.Cstore % 64 == 0 && p.oy_mul == 2),
                DUCOSY_ERR_SHAPE, "conv_gemm: merged phases need fold 4, one n-block, 64-channel slabs");
+  DUCOSY_CHECK((p.num_taps * planes) * a.kc_per_tap < 32768 && a.kc_per_tap < 128, DUCOSY_ERR_SHAPE, "conv_gemm: K too large");
   for (int ph = 0; ph < p.num_phases; ++ph) {
-    for (int t = 0; t < p.num_taps; ++t) {
+    for (int v = 0; v < a.num_taps; ++v) {
+      // virtual tap v of filter tap t: j = 0 A_hi*W_hi, 1 A_lo*W_hi, 2 A_hi*W_lo (not split: v == t, j == 0)
+      const int t = split ? v / 3 : v, j = split ? v % 3 : 0;
       const int dy = p.tap_dy[ph][t], dx = p.tap_dx[ph][t];
       DUCOSY_CHECK(dy >= 0 && dx >= 0, DUCOSY_ERR_SHAPE, "conv_gemm: negative tap offset");
       if (p.stride == 1) {
-        a.tap_xp[ph][t] = 0; a.tap_dx[ph][t] = int8_t(dx);
-        a.tap_yp[ph][t] = 0; a.tap_dy[ph][t] = int8_t(dy);
+        a.tap_xp[ph][v] = 0; a.tap_dx[ph][v] = int8_t(dx);
+        a.tap_yp[ph][v] = 0; a.tap_dy[ph][v] = int8_t(dy);
       } else {
-        a.tap_xp[ph][t] = int8_t(dx & 1); a.tap_dx[ph][t] = int8_t(dx >> 1);
-        a.tap_yp[ph][t] = int8_t(dy & 1); a.tap_dy[ph][t] = int8_t(dy >> 1);
+        a.tap_xp[ph][v] = int8_t(dx & 1); a.tap_dx[ph][v] = int8_t(dx >> 1);
+        a.tap_yp[ph][v] = int8_t(dy & 1); a.tap_dy[ph][v] = int8_t(dy >> 1);
       }
+      a.tap_c0[ph][v] = int8_t(j == 1 ? a.kc_per_tap : 0);
+      a.tap_bk[v] = int16_t((j == 2 ? p.num_taps + t : t) * a.kc_per_tap);
     }
     a.oy_off[ph] = p.oy_off[ph];
     a.ox_off[ph] = p.ox_off[ph];
@@ -553,39 +587,39 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   static const int cg_env = []() { const char* e = getenv("DUCOSY_CONV_CTA_GROUP"); return e ? atoi(e) : 2; }();
   const int cg = (cg_env == 2 && (a.TY * a.TX) % 2 == 0) ? 2 : 1;
 
-  const CUtensorMapDataType dt = p.dtype == DUCOSY_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  const CUtensorMapDataType dt = p.dtype == DUCOSY_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16;
   CUtensorMap tmA, tmB, tmO;
   {
     // output tile store: (c, x-phase, x, y-phase, y*batch) so that the sub-pixel (x2 upsampling) phases are boxes too
-    const cuuint64_t C2 = cuuint64_t(a.Cstore) * 2, W = cuuint64_t(p.Wo), H = cuuint64_t(p.Ho);
+    const cuuint64_t Cs = cuuint64_t(a.Cstore) * planes, C2 = Cs * 2, W = cuuint64_t(p.Wo), H = cuuint64_t(p.Ho);
     cuuint64_t gdim[5], gstr[4];
     DUCOSY_CHECK(p.oy_mul == p.ox_mul && (p.oy_mul == 1 || (p.oy_mul == 2 && p.Ho % 2 == 0 && p.Wo % 2 == 0)),
                  DUCOSY_ERR_SHAPE, "conv_gemm: output stride must be 1 or 2");
     if (p.oy_mul == 1) {
-      gdim[0] = a.Cstore; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
+      gdim[0] = Cs; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
       gstr[0] = C2; gstr[1] = C2; gstr[2] = W * C2; gstr[3] = W * C2;
     } else {
-      gdim[0] = a.Cstore; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
+      gdim[0] = Cs; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
       gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
     }
     const cuuint32_t box[5] = {64, 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
     DUCOSY_TRY(encode_tiled_cached(&tmO, dt, 5, p.out, gdim, gstr, box, "conv_gemm(out)"));
   }
   {
-    const cuuint64_t C2 = cuuint64_t(p.Cin) * 2, W = cuuint64_t(p.Wp), H = cuuint64_t(p.Hp);
+    const cuuint64_t Ci = cuuint64_t(p.Cin) * planes, C2 = Ci * 2, W = cuuint64_t(p.Wp), H = cuuint64_t(p.Hp);
     cuuint64_t gdim[5], gstr[4];
     if (p.stride == 1) {
-      gdim[0] = p.Cin; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
+      gdim[0] = Ci; gdim[1] = 1; gdim[2] = W; gdim[3] = 1; gdim[4] = cuuint64_t(p.B) * H;
       gstr[0] = C2; gstr[1] = C2; gstr[2] = W * C2; gstr[3] = W * C2;
     } else {
-      gdim[0] = p.Cin; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
+      gdim[0] = Ci; gdim[1] = 2; gdim[2] = W / 2; gdim[3] = 2; gdim[4] = cuuint64_t(p.B) * H / 2;
       gstr[0] = C2; gstr[1] = 2 * C2; gstr[2] = W * C2; gstr[3] = 2 * W * C2;
     }
     const cuuint32_t box[5] = {cuuint32_t(kBlockK), 1, cuuint32_t(Wt), 1, cuuint32_t(R)};
     DUCOSY_TRY(encode_tiled_cached(&tmA, dt, 5, p.in, gdim, gstr, box, "conv_gemm(A)"));
   }
   {
-    const cuuint64_t Ktot = cuuint64_t(p.num_taps) * p.Cin;
+    const cuuint64_t Ktot = cuuint64_t(p.num_taps) * p.Cin * planes;
     const cuuint64_t gdim[2] = {Ktot, cuuint64_t(p.num_phases) * p.Cout};
     const cuuint64_t gstr[1] = {Ktot * 2};
     const cuuint32_t box[2] = {cuuint32_t(kBlockK), cuuint32_t(kN / cg)};
@@ -606,6 +640,12 @@ int launch_conv_gemm(const ConvPlan& p, cudaStream_t stream) {
   } else {                                                                                             \
     if (p.dtype == DUCOSY_F16) return launch_impl<N, __half, 1>(tmA, tmB, tmO, a, grid, stream);             \
     else return launch_impl<N, __nv_bfloat16, 1>(tmA, tmB, tmO, a, grid, stream);                            \
+  }
+  if (split) {
+    if (kN == 128) return cg == 2 ? launch_impl<128, __half, 2, true>(tmA, tmB, tmO, a, grid, stream)
+                                  : launch_impl<128, __half, 1, true>(tmA, tmB, tmO, a, grid, stream);
+    return cg == 2 ? launch_impl<64, __half, 2, true>(tmA, tmB, tmO, a, grid, stream)
+                   : launch_impl<64, __half, 1, true>(tmA, tmB, tmO, a, grid, stream);
   }
   if (kN == 256) { DUCOSY_LAUNCH_N(256) }
   if (kN == 128) { DUCOSY_LAUNCH_N(128) }

@@ -16,10 +16,59 @@ int ew_grid(long long work_items, int threads) {
   return int(blocks);
 }
 
+// ------------------------------------------------------------------ 8-channel chunks (one 128-bit access)
+template <typename T>
+__device__ __forceinline__ void unpack8(uint4 raw, float (&f)[8]) {
+  const uint32_t w[4] = {raw.x, raw.y, raw.z, raw.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float2 t = Cvt<T>::unpack2(w[i]);
+    f[2 * i] = t.x;
+    f[2 * i + 1] = t.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+  return make_uint4(Cvt<T>::pack2(f[0], f[1]), Cvt<T>::pack2(f[2], f[3]), Cvt<T>::pack2(f[4], f[5]), Cvt<T>::pack2(f[6], f[7]));
+}
+// split-operand mode: hi = rn(v), lo = rn(v - hi)
+template <typename T>
+__device__ __forceinline__ void split8(const float (&f)[8], uint4& hi, uint4& lo) {
+  hi = pack8<T>(f);
+  float h[8], r[8];
+  unpack8<T>(hi, h);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r[i] = f[i] - h[i];
+  lo = pack8<T>(r);
+}
+// value of a (hi, lo) chunk pair
+template <typename T>
+__device__ __forceinline__ void join8(uint4 hi, uint4 lo, float (&f)[8]) {
+  float l[8];
+  unpack8<T>(hi, f);
+  unpack8<T>(lo, l);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) f[i] += l[i];
+}
+
 // ------------------------------------------------------------------ weight packing
+// Element i of a packed [rows][K] matrix.  planes == 2 (split-operand mode, DUCOSY_F16X2): the row is [K hi | K lo] with
+// hi = rn(v), lo = rn(v - hi).
+template <typename T>
+__device__ __forceinline__ void store_packed(T* __restrict__ out, long long i, long long K, int planes, float v) {
+  const T hi = Cvt<T>::from_f(v);
+  if (planes == 1) {
+    out[i] = hi;
+  } else {
+    const long long row = i / K, k = i - row * K;
+    out[row * 2 * K + k] = hi;
+    out[row * 2 * K + K + k] = Cvt<T>::from_f(v - Cvt<T>::to_f(hi));
+  }
+}
+
 template <typename T>
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int kh,
-                                        int kw) {
+                                        int kw, int planes) {
   const long long total = (long long)Cout * Cin * kh * kw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -27,14 +76,14 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restri
     long long r = i / Cin;
     const int tap = int(r % (kh * kw));
     const int o = int(r / (kh * kw));
-    out[i] = Cvt<T>::from_f(w[((long long)o * Cin + c) * kh * kw + tap]);
+    store_packed(out, i, (long long)Cin * kh * kw, planes, w[((long long)o * Cin + c) * kh * kw + tap]);
   }
 }
 
 // Upsample(x2 nearest) + 3x3/pad1  ==  four 2x2 convs on the source grid:
 // rows: phase 0 -> [w0, w1+w2], phase 1 -> [w0+w1, w2]; same for columns.  Sums are formed in fp32.
 template <typename T>
-__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin) {
+__global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int planes) {
   const long long total = 4LL * Cout * 4 * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -54,7 +103,7 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __rest
     float acc = 0.f;
     for (int rr = r0; rr <= r1; ++rr)
       for (int ss = s0; ss <= s1; ++ss) acc += wk[rr * 3 + ss];
-    out[i] = Cvt<T>::from_f(acc);
+    store_packed(out, i, 4LL * Cin, planes, acc);
   }
 }
 
@@ -88,18 +137,18 @@ __global__ void pack_upconv_merged_weight_kernel(const float* __restrict__ w, T*
 }
 
 template <typename T>
-__global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cin, int Kpad) {
+__global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cin, int Kpad, int planes) {
   const int total = 64 * Kpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % Kpad, o = i / Kpad;
-    out[i] = Cvt<T>::from_f(k < 49 * Cin ? w[o * 49 * Cin + k] : 0.f);
+    store_packed(out, i, Kpad, planes, k < 49 * Cin ? w[o * 49 * Cin + k] : 0.f);
   }
 }
 
 // ------------------------------------------------------------------ stem im2col
 // A[(b,y,x)][k], k = c*49 + r*7 + s  <-  in[b][c][reflect(y+r-3)][reflect(x+s-3)], zero for k >= 49*Cin.
 // One thread builds 8 consecutive k (one 16-byte store); consecutive threads -> consecutive chunks of a row.
-template <typename T, typename In>
+template <typename T, typename In, bool kSplit>
 __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int H, int W, int Kpad) {
   const int chunks = Kpad / 8;
   const long long total = (long long)B * H * W * chunks;
@@ -123,12 +172,15 @@ __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int
         v[j] = 0.f;
       }
     }
-    uint4 o;
-    o.x = Cvt<T>::pack2(v[0], v[1]);
-    o.y = Cvt<T>::pack2(v[2], v[3]);
-    o.z = Cvt<T>::pack2(v[4], v[5]);
-    o.w = Cvt<T>::pack2(v[6], v[7]);
-    reinterpret_cast<uint4*>(A)[i] = o;
+    if (kSplit) {   // row = [Kpad hi | Kpad lo]
+      uint4 hi, lo;
+      split8<T>(v, hi, lo);
+      uint4* rowp = reinterpret_cast<uint4*>(A) + (i / chunks) * (2 * chunks);
+      rowp[ck] = hi;
+      rowp[chunks + ck] = lo;
+    } else {
+      reinterpret_cast<uint4*>(A)[i] = pack8<T>(v);
+    }
   }
 }
 
@@ -166,17 +218,21 @@ stem_im2col_rows_kernel(In in, T* __restrict__ A, int H, int W) {
 }
 
 template <typename T, typename In>
-int launch_im2col(In in, T* A, int B, int Cin, int H, int W, cudaStream_t st) {
+int launch_im2col(In in, T* A, int B, int Cin, int H, int W, bool split, cudaStream_t st) {
   const size_t smem = size_t(Cin) * 7 * (W + 6) * sizeof(T);
   const dim3 grid(H, B);
-  if (Cin <= 3 && smem <= 48 * 1024) {
+  if (split) {
+    const int Kpad = (49 * Cin + 63) / 64 * 64;
+    const long long total = (long long)B * H * W * (Kpad / 8);
+    stem_im2col_kernel<T, In, true><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
+  } else if (Cin <= 3 && smem <= 48 * 1024) {
     if (Cin == 1) stem_im2col_rows_kernel<T, In, 1><<<grid, 256, smem, st>>>(in, A, H, W);
     else if (Cin == 2) stem_im2col_rows_kernel<T, In, 2><<<grid, 256, smem, st>>>(in, A, H, W);
     else stem_im2col_rows_kernel<T, In, 3><<<grid, 256, smem, st>>>(in, A, H, W);
   } else {
     const int Kpad = (49 * Cin + 63) / 64 * 64;
     const long long total = (long long)B * H * W * (Kpad / 8);
-    stem_im2col_kernel<T, In><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
+    stem_im2col_kernel<T, In, false><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
   }
   return check_launch("stem_im2col_kernel");
 }
@@ -293,12 +349,27 @@ __device__ __forceinline__ uint4 affine8(uint4 raw, const float* sc, const float
 // 4 CTAs per SM so that a tensor-core conv CTA of the other generator's stream can share the SM.
 constexpr int kRowILP = 4;
 
+// split-operand mode: relu(v*scale + shift) of the joined (hi, lo) value, split again
 template <typename T>
+__device__ __forceinline__ void affine8_split(uint4 rh, uint4 rl, const float* sc, const float* sh, int act, uint4& oh, uint4& ol) {
+  float f[8];
+  join8<T>(rh, rl, f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    f[i] = fmaf(f[i], sc[i], sh[i]);
+    if (act == DUCOSY_ACT_RELU) f[i] = fmaxf(f[i], 0.f);
+    else if (act == DUCOSY_ACT_LRELU02) f[i] = f[i] > 0.f ? f[i] : 0.2f * f[i];
+  }
+  split8<T>(f, oh, ol);
+}
+
+// kSplit (DUCOSY_F16X2): a pixel holds 2*C channels, the lo plane C channels behind the hi plane.
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     T* __restrict__ out, int B, int H, int W, int C, int pad, int pad_mode, int act) {
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
-  const int c8 = threadIdx.x % cv, row_chunks = Wp * cv;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8, cvp = kSplit ? 2 * cv : cv;
+  const int c8 = threadIdx.x % cv, row_chunks = Wp * cvp;
   const int px0 = threadIdx.x / cv, px_step = 256 / cv;
   int cur_b = -1;
   float s8[8], h8[8];
@@ -315,10 +386,10 @@ in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
     int sy = py - pad;
     const bool row_inside = sy >= 0 && sy < H;
     sy = reflect_idx(sy, H);
-    const uint4* src_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cv + c8;
+    const uint4* src_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cvp + c8;
     uint4* dst_row = reinterpret_cast<uint4*>(out) + (long long)row * row_chunks + c8;
     for (int px = px0; px < Wp; px += px_step * kRowILP) {
-      uint4 raw[kRowILP];
+      uint4 raw[kRowILP], rawl[kSplit ? kRowILP : 1];
       bool live[kRowILP];
 #pragma unroll
       for (int u = 0; u < kRowILP; ++u) {
@@ -327,12 +398,23 @@ in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
         const bool inside = row_inside && sx >= 0 && sx < W;
         live[u] = p < Wp && (inside || pad_mode == DUCOSY_PAD_REFLECT);
         sx = reflect_idx(sx, W);
-        if (live[u]) raw[u] = src_row[(long long)sx * cv];
+        if (live[u]) {
+          raw[u] = src_row[(long long)sx * cvp];
+          if (kSplit) rawl[u] = src_row[(long long)sx * cvp + cv];
+        }
       }
 #pragma unroll
       for (int u = 0; u < kRowILP; ++u) {
         const int p = px + u * px_step;
-        if (p < Wp) dst_row[(long long)p * cv] = live[u] ? affine8<T>(raw[u], s8, h8, act) : make_uint4(0, 0, 0, 0);
+        if (p >= Wp) continue;
+        if (kSplit) {
+          uint4 oh = make_uint4(0, 0, 0, 0), ol = oh;
+          if (live[u]) affine8_split<T>(raw[u], rawl[u], s8, h8, act, oh, ol);
+          dst_row[(long long)p * cvp] = oh;
+          dst_row[(long long)p * cvp + cv] = ol;
+        } else {
+          dst_row[(long long)p * cv] = live[u] ? affine8<T>(raw[u], s8, h8, act) : make_uint4(0, 0, 0, 0);
+        }
       }
     }
   }
@@ -341,7 +423,7 @@ in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, co
 // ------------------------------------------------------------------ CBAM spatial pooling, C = 256
 // 8 lanes per pixel, each lane owns 4 x 8 channels (four independent 128-bit loads, every load instruction of a
 // pixel's 8 lanes covers one full 128-byte line), local reduction then 3 shuffle steps.  grid (x, B).
-template <typename T>
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                  float2* __restrict__ pooled, int HW) {
@@ -357,19 +439,30 @@ cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale, const
       sh[j][i] = shift[b * C + j * 64 + seg * 8 + i];
     }
   const int warps = (blockDim.x >> 5) * gridDim.x;
-  const uint4* base = reinterpret_cast<const uint4*>(y) + (long long)b * HW * (C / 8);
+  constexpr int kPix = (kSplit ? 2 : 1) * (C / 8);   // 16-byte chunks per pixel
+  const uint4* base = reinterpret_cast<const uint4*>(y) + (long long)b * HW * kPix;
   for (int g = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); g * 4 < HW; g += warps) {
     const int pix = g * 4 + sub;
-    uint4 raw[4];
+    uint4 raw[4], rawl[kSplit ? 4 : 1];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) raw[j] = base[(long long)pix * (C / 8) + j * 8 + seg];
+    for (int j = 0; j < 4; ++j) {
+      raw[j] = base[(long long)pix * kPix + j * 8 + seg];
+      if (kSplit) rawl[j] = base[(long long)pix * kPix + C / 8 + j * 8 + seg];
+    }
     float s = 0.f, m = -INFINITY;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const uint32_t w[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      uint32_t wl[4] = {0, 0, 0, 0};
+      if (kSplit) { wl[0] = rawl[j].x; wl[1] = rawl[j].y; wl[2] = rawl[j].z; wl[3] = rawl[j].w; }
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
-        const float2 f = Cvt<T>::unpack2(w[i]);
+        float2 f = Cvt<T>::unpack2(w[i]);
+        if (kSplit) {
+          const float2 l = Cvt<T>::unpack2(wl[i]);
+          f.x += l.x;
+          f.y += l.y;
+        }
         const float v0 = fmaf(f.x, sc[j][2 * i], sh[j][2 * i]), v1 = fmaf(f.y, sc[j][2 * i + 1], sh[j][2 * i + 1]);
         s += v0 + v1;
         m = fmaxf(m, fmaxf(v0, v1));
@@ -416,7 +509,7 @@ __global__ void cbam_spatial_conv_kernel(const float2* __restrict__ pooled, cons
 }
 
 // out_pad = residual + (y*scale+shift) * sa ; borders by reflection / zero.  res_pad has padding res_pw.
-template <typename T>
+template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                           const float* __restrict__ sa, const float2* __restrict__ pooled, const float* __restrict__ w_sa,
@@ -429,9 +522,9 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
   if (pooled != nullptr) {
     for (int i = threadIdx.x; i < 98; i += 256) sa_smem[i] = w_sa[i];
   }
-  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
+  const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8, cvp = kSplit ? 2 * cv : cv;
   const int Wr = W + 2 * res_pw, Hr = H + 2 * res_pw;
-  const int c8 = threadIdx.x % cv, row_chunks = Wp * cv;
+  const int c8 = threadIdx.x % cv, row_chunks = Wp * cvp;
   const int px0 = threadIdx.x / cv, px_step = 256 / cv;
   int cur_b = -1;
   float s8[8], h8[8];
@@ -448,8 +541,8 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
     int sy = py - pad;
     const bool row_inside = sy >= 0 && sy < H;
     sy = reflect_idx(sy, H);
-    const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cv + c8;
-    const uint4* r_row = reinterpret_cast<const uint4*>(res_pad) + (((long long)b * Hr + sy + res_pw) * Wr + res_pw) * cv + c8;
+    const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((long long)b * H + sy) * W * cvp + c8;
+    const uint4* r_row = reinterpret_cast<const uint4*>(res_pad) + (((long long)b * Hr + sy + res_pw) * Wr + res_pw) * cvp + c8;
     const float* sa_row = sa != nullptr ? sa + ((long long)b * H + sy) * W : nullptr;
     if (pooled != nullptr) {
       __syncthreads();                       // the previous row's readers are done with sa_line (and the weights are loaded)
@@ -474,7 +567,7 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
     }
     uint4* dst_row = reinterpret_cast<uint4*>(out) + (long long)row * row_chunks + c8;
     for (int px = px0; px < Wp; px += px_step * kRowILP) {
-      uint4 raw[kRowILP], res[kRowILP];
+      uint4 raw[kRowILP], res[kRowILP], rawl[kSplit ? kRowILP : 1], resl[kSplit ? kRowILP : 1];
       float att[kRowILP];
       bool live[kRowILP];
 #pragma unroll
@@ -485,8 +578,12 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
         live[u] = p < Wp && (inside || pad_mode == DUCOSY_PAD_REFLECT);
         sx = reflect_idx(sx, W);
         if (live[u]) {
-          raw[u] = y_row[(long long)sx * cv];
-          res[u] = r_row[(long long)sx * cv];
+          raw[u] = y_row[(long long)sx * cvp];
+          res[u] = r_row[(long long)sx * cvp];
+          if (kSplit) {
+            rawl[u] = y_row[(long long)sx * cvp + cv];
+            resl[u] = r_row[(long long)sx * cvp + cv];
+          }
           att[u] = pooled != nullptr ? sa_line[sx] : (sa_row != nullptr ? __ldg(sa_row + sx) : 1.f);
         }
       }
@@ -494,6 +591,20 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
       for (int u = 0; u < kRowILP; ++u) {
         const int p = px + u * px_step;
         if (p >= Wp) continue;
+        if (kSplit) {
+          uint4 oh = make_uint4(0, 0, 0, 0), ol = oh;
+          if (live[u]) {
+            float f[8], g[8];
+            join8<T>(raw[u], rawl[u], f);
+            join8<T>(res[u], resl[u], g);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) f[k] = fmaf(fmaf(f[k], s8[k], h8[k]), att[u], g[k]);
+            split8<T>(f, oh, ol);
+          }
+          dst_row[(long long)p * cvp] = oh;
+          dst_row[(long long)p * cvp + cv] = ol;
+          continue;
+        }
         uint4 o = make_uint4(0, 0, 0, 0);
         if (live[u]) {
           const uint32_t yw[4] = {raw[u].x, raw[u].y, raw[u].z, raw[u].w};
@@ -531,7 +642,7 @@ extern "C" int ducosy_pack_conv_weight(const float* w, void* packed, int Cout, i
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, DUCOSY_ERR_ARG, "pack_conv_weight: bad argument");
   const long long total = (long long)Cout * Cin * kh * kw;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_conv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      w, static_cast<T*>(packed), Cout, Cin, kh, kw)));
+                                      w, static_cast<T*>(packed), Cout, Cin, kh, kw, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_conv_weight_kernel");
 }
 
@@ -540,13 +651,14 @@ extern "C" int ducosy_pack_upconv_weight(const float* w, void* packed, int Cout,
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_weight: bad argument");
   const long long total = 16LL * Cout * Cin;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      w, static_cast<T*>(packed), Cout, Cin)));
+                                      w, static_cast<T*>(packed), Cout, Cin, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_upconv_weight_kernel");
 }
 
 extern "C" int ducosy_pack_upconv_merged_weight(const float* w, void* packed, int Cout, int Cin, int dtype,
                                                 ducosy_stream_t stream) {
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_merged_weight: bad argument");
+  DUCOSY_CHECK(dtype != DUCOSY_F16X2, DUCOSY_ERR_ARG, "pack_upconv_merged_weight: not available in split-operand mode");
   const long long total = 36LL * Cout * Cin;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_merged_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
                                       w, static_cast<T*>(packed), Cout, Cin)));
@@ -557,7 +669,7 @@ extern "C" int ducosy_pack_stem_weight(const float* w, void* packed, int Cin, in
   DUCOSY_CHECK(w && packed && Cin > 0, DUCOSY_ERR_ARG, "pack_stem_weight: bad argument");
   const int Kpad = (49 * Cin + 63) / 64 * 64;
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_stem_weight_kernel<T><<<ew_grid(64 * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(
-                                      w, static_cast<T*>(packed), Cin, Kpad)));
+                                      w, static_cast<T*>(packed), Cin, Kpad, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_stem_weight_kernel");
 }
 
@@ -566,7 +678,7 @@ extern "C" int ducosy_stem_im2col(const float* x, void* a_mat, int B, int Cin, i
   DUCOSY_CHECK(x && a_mat && B > 0 && Cin > 0, DUCOSY_ERR_ARG, "stem_im2col: bad argument");
   DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col: reflect pad 3 needs H,W >= 4");
   InF32 in{x};
-  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InF32>(in, static_cast<T*>(a_mat), B, Cin, H, W, (cudaStream_t)stream)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InF32>(in, static_cast<T*>(a_mat), B, Cin, H, W, dtype == DUCOSY_F16X2, (cudaStream_t)stream)));
 }
 
 extern "C" int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int H, int W, float slope, float intercept,
@@ -574,7 +686,7 @@ extern "C" int ducosy_stem_im2col_hu(const int16_t* px, void* a_mat, int B, int 
   DUCOSY_CHECK(px && a_mat && B > 0, DUCOSY_ERR_ARG, "stem_im2col_hu: bad argument");
   DUCOSY_CHECK(H >= 4 && W >= 4, DUCOSY_ERR_SHAPE, "stem_im2col_hu: reflect pad 3 needs H,W >= 4");
   InHU in{px, slope, intercept, lo, hi, float(double(hi) - double(lo))};
-  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InHU>(in, static_cast<T*>(a_mat), B, 1, H, W, (cudaStream_t)stream)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, return (launch_im2col<T, InHU>(in, static_cast<T*>(a_mat), B, 1, H, W, dtype == DUCOSY_F16X2, (cudaStream_t)stream)));
 }
 
 extern "C" int ducosy_in_finalize(const float* partials, int tiles_per_sample, int npix_per_sample, float* scale,
@@ -602,9 +714,13 @@ extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const floa
   DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_SHAPE, "in_apply_pad: C %% 8 != 0 or pad too large");
   DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "in_apply_pad: C must be one of 8..2048 with C/8 dividing 256");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
-                                      pad_mode, act)));
+  if (dtype == DUCOSY_F16X2)
+    in_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(y), scale, shift, static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode, act);
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
+                                        pad_mode, act)));
   return check_launch("in_apply_pad_kernel");
 }
 
@@ -617,8 +733,12 @@ extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* 
   int gx = (groups + 7) / 8;                     // 8 warps per CTA
   const int cap = (num_sms() > 0 ? num_sms() : 148) * 8 / (B > 0 ? B : 1) + 1;
   if (gx > cap) gx = cap;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), H * W)));
+  if (dtype == DUCOSY_F16X2)
+    cbam_pool_kernel<__half, true><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(y), scale, shift,
+                                                                                   reinterpret_cast<float2*>(pooled), H * W);
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T, false><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), H * W)));
   return check_launch("cbam_pool_kernel");
 }
 
@@ -638,9 +758,14 @@ extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, cons
                "residual_apply_pad: bad shape");
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_apply_pad: C/8 must divide 256");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const T*>(res_pad),
-                                      res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
+  if (dtype == DUCOSY_F16X2)
+    residual_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const __half*>(res_pad), res_pad_width,
+        static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode);
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const T*>(res_pad),
+                                        res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");
 }
 
@@ -656,8 +781,13 @@ extern "C" int ducosy_residual_cbam_apply_pad(const void* y, const float* scale,
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_cbam_apply_pad: in-place is not supported");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_cbam_apply_pad: C/8 must divide 256");
   const size_t smem = (98 + size_t(W)) * sizeof(float);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
-                                      static_cast<const T*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
-                                      static_cast<const T*>(res_pad), res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
+  if (dtype == DUCOSY_F16X2)
+    residual_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
+        static_cast<const __half*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
+        static_cast<const __half*>(res_pad), res_pad_width, static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode);
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
+                                        static_cast<const T*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
+                                        static_cast<const T*>(res_pad), res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");
 }

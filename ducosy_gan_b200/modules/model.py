@@ -31,8 +31,18 @@ def _ordered_params(module):
 
 def default_operand_dtype() -> int:
     """16-bit operand type of the tensor-core convolutions: fp16 (default; TF32-class 10-bit mantissa, the
-    reference's own GPU precision) or bf16 via DUCOSY_PRECISION=bf16."""
-    return _lib.dtype_code(os.environ.get("DUCOSY_PRECISION", "fp16").lower())
+    reference's own GPU precision) or bf16 via DUCOSY_PRECISION=bf16.  (DUCOSY_PRECISION=fp16x2 selects the split-operand
+    arm of the generator's inference path only -- see ``inference_operand_dtype``; everything else then runs in fp16.)"""
+    code = _lib.dtype_code(os.environ.get("DUCOSY_PRECISION", "fp16").lower())
+    return _lib.F16 if code == _lib.F16X2 else code
+
+
+def inference_operand_dtype(override=None) -> int:
+    """Operand mode of ``Generator.forward`` without autograd (generate.py:96-97).  ``fp16x2`` is the <= 1 HU precision arm:
+    every activation and weight is a (hi, lo) pair of fp16 values and each convolution tap runs three tensor-core products
+    (A_hi*W_hi + A_lo*W_hi + A_hi*W_lo, fp32 accumulate) -- fp32-class results at about a third of the fp16 throughput.
+    Selected by ``Generator.precision = "fp16x2"`` or DUCOSY_PRECISION=fp16x2."""
+    return _lib.dtype_code((override or os.environ.get("DUCOSY_PRECISION", "fp16")).lower())
 
 
 class _DerivedState:
@@ -223,10 +233,12 @@ class Generator(_DerivedState, nn.Module):
         self.model = nn.Sequential(*layers)
         self._cfg_tuple = (int(input_channels), int(num_residual_blocks), bool(use_cbam))
         self._engines = {}  # device index -> _GeneratorEngine (derived caches; never part of state_dict)
+        self.precision = None  # None: DUCOSY_PRECISION (default fp16); "fp16" | "bf16" | "fp16x2" (inference_operand_dtype)
 
     # -- engine ------------------------------------------------------------------------------------------
     def _engine(self, device) -> "_GeneratorEngine":
-        key = (device.index if device.index is not None else torch.cuda.current_device(), default_operand_dtype())
+        key = (device.index if device.index is not None else torch.cuda.current_device(),
+               inference_operand_dtype(getattr(self, "precision", None)))
         eng = self._engines.get(key)
         if eng is None:
             eng = _GeneratorEngine(self._cfg_tuple, key[1], torch.device("cuda", key[0]))

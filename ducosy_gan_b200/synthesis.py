@@ -50,13 +50,15 @@ class DualHUSynthesizer:
     soft_model / lung_model: ``ducosy_gan_b200.modules.model.Generator(input_channels=1)`` instances holding the
     checkpoints (as generate.py:29-49 builds them).  ``batch_slices`` slices go through each generator at once
     (30 is where the throughput curve flattens on a B200: 974 slices/s vs 900 at 15 and 830 at 10; about 6.4 GB of workspace
-    per generator).
+    per generator).  ``precision``: operand mode of both generators (``modules.model.inference_operand_dtype``).
     """
 
     def __init__(self, soft_model: Generator, lung_model: Generator, soft_hu=SOFT_HU, lung_hu=LUNG_HU,
-                 batch_slices: int = 30, device=None):
+                 batch_slices: int = 30, device=None, precision: str | None = None):
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.soft_model, self.lung_model = soft_model, lung_model
+        if precision is not None:          # "fp16" (default) | "bf16" | "fp16x2" (the <= 1 HU split-operand arm, ~3x slower)
+            soft_model.precision = lung_model.precision = precision
         self.soft_hu, self.lung_hu = tuple(map(float, soft_hu)), tuple(map(float, lung_hu))
         self.batch_slices = int(batch_slices)
         self._streams = None

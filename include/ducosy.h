@@ -27,7 +27,13 @@ extern "C" {
 
 #define DUCOSY_VERSION 100
 
-enum { DUCOSY_F16 = 0, DUCOSY_BF16 = 1 };
+/* Operand type of the tensor-core convolutions.  DUCOSY_F16 / DUCOSY_BF16: 16-bit activations and weights, fp32 accumulate.
+ * DUCOSY_F16X2 ("split-operand" mode, the <= 1 HU precision arm of the generator forward): every activation and packed
+ * weight is a pair of fp16 values (hi = rn(v), lo = rn(v - hi)); NHWC buffers hold 2*C 16-bit channels per pixel (hi plane,
+ * then lo plane), convolutions accumulate A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32 (3 tensor-core products per tap, ~21
+ * significant bits).  Accepted where a function's comment says so (ducosy_generator_* and the kernels it is made of);
+ * the training entry points take the 16-bit types only. */
+enum { DUCOSY_F16 = 0, DUCOSY_BF16 = 1, DUCOSY_F16X2 = 2 };
 enum {
   DUCOSY_OK = 0,
   DUCOSY_ERR_SHAPE = -1,     /* unsupported shape / channel count */

@@ -105,6 +105,55 @@ def test_generator_config1_soft_tissue_with_mask_channels():
     assert err < TOL_TANH["fp16"] and mean < TOL_MEAN["fp16"]
 
 
+# Split-operand arm (DUCOSY_F16X2, Generator.precision = "fp16x2"): (hi, lo) fp16 pairs, three tensor-core products per tap,
+# fp32 accumulate.  Stated tolerance against the fp32 oracle: max <= 2e-4 tanh units (0.04 HU soft window, 0.085 HU lung window),
+# i.e. fp32-class; after the truncating de-window cast (preprocess.py:111) that is "<= 1 HU" (a value sitting on an integer
+# boundary may fall either way).
+TOL_SPLIT = 2e-4
+
+
+@pytest.mark.parametrize("cin,nb,cbam,B,H,W", [(1, 2, True, 2, 128, 128), (3, 1, False, 1, 128, 256), (2, 1, True, 1, 256, 128)])
+def test_generator_split_operand_small(cin, nb, cbam, B, H, W):
+    sd = orc.make_state_dict(orc.generator_param_shapes(cin, nb, cbam), 77, attn_std=0.2)
+    G = _gen(cin, nb, cbam, sd)
+    G.precision = "fp16x2"
+    x = _x(5, (B, cin, H, W))
+    with torch.no_grad():
+        y = G(x.cuda()).cpu()
+        ref = orc.generator_forward(sd, x, nb, cbam)
+    err = (y - ref).abs().max().item()
+    print(f"gen fp16x2 cin={cin} nb={nb} cbam={cbam} {H}x{W}: max abs err {err:.3e}")
+    assert err < TOL_SPLIT
+
+
+def test_generator_split_operand_full_size_within_1hu(golden_dir):
+    """The <= 1 HU arm north_star asks for: 512x512, 9 CBAM blocks, both HU windows' worth of error against the fp32 oracle and
+    the reference's own golden output, then through the truncating de-window: |stored-value difference| <= 1."""
+    g = np.load(os.path.join(golden_dir, "gen_full_512.npz"))
+    sd = orc.make_state_dict(orc.generator_param_shapes(1, 9, True), int(g["wseed"]), attn_std=float(g["attn_std"]))
+    G = _gen(1, 9, True, sd)
+    G.precision = "fp16x2"
+    px = orc.synthetic_volume(1, 512, 512, seed=int(g["vseed"]))
+    x = torch.from_numpy(orc.hu_window(px[0], 1.0, -1024.0, *orc.SOFT_HU).astype(np.float32))[None, None]
+    with torch.no_grad():
+        y = G(x.cuda())
+        y_hu = G.forward_hu(torch.from_numpy(px).cuda(), 1.0, -1024.0, *orc.SOFT_HU)
+        ref = orc.generator_forward(sd, x)
+    assert torch.equal(y, y_hu)
+    y = y.cpu()
+    err = (y - ref).abs().max().item()
+    print(f"gen 512 full fp16x2: max abs err {err:.3e} tanh = {err * 200:.4f} HU (soft) / {err * 425:.4f} HU (lung); "
+          f"mean {float((y - ref).abs().mean()):.2e}")
+    assert err < TOL_SPLIT
+    assert np.abs(y[0, 0].numpy()[::8, ::8] - g["y_sub"]).max() < TOL_SPLIT
+    for lo, hi in (orc.SOFT_HU, orc.LUNG_HU):
+        a = orc.dewindow_to_stored(y[0, 0].numpy(), 1.0, -1024.0, lo, hi)
+        b = orc.dewindow_to_stored(ref[0, 0].numpy(), 1.0, -1024.0, lo, hi)
+        d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+        print(f"   de-windowed ({lo},{hi}): max |diff| {d.max()} stored units, {100.0 * (d > 0).mean():.3f} % of voxels differ")
+        assert d.max() <= 1
+
+
 def test_generator_is_deterministic_and_batch_invariant():
     sd = orc.make_state_dict(orc.generator_param_shapes(1, 2, True), 5, attn_std=0.2)
     G = _gen(1, 2, True, sd)
