@@ -99,7 +99,7 @@ def time_dominant_kernel(device, batch, iters=20):
     """CUDA-event timing of the dominant kernel alone: the 3x3 256->256 residual-block convolution
     (tcgen05 implicit GEMM) at the batch the synthesizer uses.  Returns (avg seconds, FLOPs per launch)."""
     from ducosy_gan_b200 import ops
-    dt = torch.float16 if os.environ.get("DUCOSY_PRECISION", "fp16") == "fp16" else torch.bfloat16
+    dt = torch.bfloat16 if os.environ.get("DUCOSY_PRECISION", "fp16") == "bf16" else torch.float16
     x = torch.randn((batch, 130, 130, 256), device=device).to(dt)
     w = ops.pack_conv_weight(torch.randn((256, 256, 3, 3), device=device) * 0.02, dt)
     for _ in range(3):

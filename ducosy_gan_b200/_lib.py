@@ -104,6 +104,12 @@ SIGNATURES = {
     "ducosy_unpack_upconv_wgrad": (_i, [_p, _p, _i, _i, _p, _p]),
     "ducosy_postprocess_scratch_bytes": (_sz, [_i, _i, _i]),
     "ducosy_postprocess_minmax_offset_bytes": (_sz, [_i, _i, _i]),
+    "ducosy_metrics_chunks": (_i, [_ll]),
+    "ducosy_metrics_slice_stats": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p]),
+    "ducosy_metrics_ed": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p, _p]),
+    "ducosy_metrics_normalize": (_i, [_p, _i, _p, _ll, _p, _p]),
+    "ducosy_metrics_ssim_tiles": (_i, [_i, _i]),
+    "ducosy_metrics_ssim": (_i, [_p, _p, _i, _i, _i, _i, C.c_double, _p, _p, _p]),
     "ducosy_postprocess_volume": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _i, C.c_double, _f, _i, _i, _i, _p]),
     "ducosy_adam_step": (_i, [_p, _p, _p, _p, _ll, _f, _f, _f, _f, _i, _p]),
     "ducosy_adam_advance": (_i, [_p, _p]),

@@ -7,7 +7,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_DIR = os.path.join(HERE, "lib")
 LIB_PATH = os.path.join(LIB_DIR, "libducosy_sm100.so")
-SOURCES = ["api.cu", "conv_gemm.cu", "elementwise.cu", "hu.cu", "out_conv.cu", "stem.cu", "disc.cu", "conv_wgrad.cu", "disc_bwd.cu", "loss.cu", "gen_bwd.cu", "post.cu", "optim.cu", "tmap.cu", "blocks.cu", "masks.cu"]
+SOURCES = ["api.cu", "conv_gemm.cu", "elementwise.cu", "hu.cu", "out_conv.cu", "stem.cu", "disc.cu", "conv_wgrad.cu", "disc_bwd.cu", "loss.cu", "gen_bwd.cu", "post.cu", "optim.cu", "tmap.cu", "blocks.cu", "masks.cu", "metrics.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

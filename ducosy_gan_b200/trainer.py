@@ -127,6 +127,54 @@ class CycleGANStep:
         out = D(torch.cat([real, fake.detach()], dim=0))
         return (mse_gan_loss(out[:B], True) + mse_gan_loss(out[B:], False)) / 2
 
+    # ------------------------------------------------------------------ validation (trainer.py:187-294)
+    @torch.no_grad()
+    def validation_loss(self, batches):
+        """``validate_and_save_images`` part 1 (trainer.py:205-253): mean over the batches of
+        ``loss_GAN + lambda_cyc * loss_cycle + lambda_id * loss_id`` with both generators in eval mode and no autograd.
+        ``batches``: iterable of dicts with "A", "B" (and optionally "masks") as the reference's dataloader yields them.
+        The three losses of a batch stay on the device; one host read at the end."""
+        was_training = self.G_A2B.training, self.G_B2A.training
+        self.G_A2B.eval(), self.G_B2A.eval()
+        dev = next(self.G_A2B.parameters()).device
+        total, n = None, 0
+        try:
+            for batch in batches:
+                real_A, real_B = batch["A"].to(dev), batch["B"].to(dev)
+                masks = batch["masks"].to(dev) if "masks" in batch else None
+                cat = (lambda t: torch.cat([t, masks], dim=1)) if masks is not None else (lambda t: t)
+                B = real_A.shape[0]
+                ab = self.G_A2B(torch.cat([cat(real_A), cat(real_B)], dim=0))     # fake_B | id_B   (trainer.py:228-241)
+                ba = self.G_B2A(torch.cat([cat(real_B), cat(real_A)], dim=0))     # fake_A | id_A
+                fake_B, id_B, fake_A, id_A = ab[:B], ab[B:], ba[:B], ba[B:]
+                rec_A, rec_B = self.G_B2A(cat(fake_B)), self.G_A2B(cat(fake_A))
+                loss_id = (l1_loss(id_A, real_A) + l1_loss(id_B, real_B)) / 2
+                loss_GAN = (mse_gan_loss(self.D_B(fake_B), True) + mse_gan_loss(self.D_A(fake_A), True)) / 2
+                loss_cycle = (l1_loss(rec_A, real_A) + l1_loss(rec_B, real_B)) / 2
+                loss_G = loss_GAN + self.lambda_cyc * loss_cycle + self.lambda_id * loss_id
+                total = loss_G if total is None else total + loss_G
+                n += 1
+        finally:
+            self.G_A2B.train(was_training[0]), self.G_B2A.train(was_training[1])
+        return float(total) / max(n, 1) if n else 0.0
+
+    @torch.no_grad()
+    def validation_image_grid(self, batch, hu_min, hu_max, window_center, window_width):
+        """``validate_and_save_images`` part 2 (trainer.py:257-280): real_A | fake_B | real_B, each display-windowed
+        (preprocess.py:58-65), concatenated along the width -> [B,1,H,3W] fp32 in [0,1] (what ``save_image`` receives)."""
+        from . import ops
+        dev = next(self.G_A2B.parameters()).device
+        was_training = self.G_A2B.training
+        self.G_A2B.eval()
+        try:
+            real_A, real_B = batch["A"].to(dev), batch["B"].to(dev)
+            x = torch.cat([real_A, batch["masks"].to(dev)], dim=1) if "masks" in batch else real_A
+            fake_B = self.G_A2B(x)
+        finally:
+            self.G_A2B.train(was_training)
+        win = lambda t: ops.apply_windowing(t, hu_min, hu_max, window_center, window_width)
+        return torch.cat((win(real_A), win(fake_B), win(real_B)), -1)
+
     def _sync(self, opt):
         if self.grad_hook is not None:
             self.grad_hook([p for g in opt.param_groups for p in g["params"]])

@@ -465,6 +465,30 @@ int ducosy_discriminator_backward(const void* packed, const float* x, const floa
                                   float* const* grads_host, float* dx, int B, int H, int W, void* workspace,
                                   size_t workspace_bytes, int dtype, ducosy_stream_t stream);
 
+/* ---------------------------------------------------------------- image-quality metrics over volumes
+ * calculate.py:232-271,360-381: normalize, calculate_mae, calculate_psnr, calculate_ssim (skimage structural_similarity
+ * defaults: 7x7 uniform window, sample covariance, K1 0.01, K2 0.03, valid region), calculate_cs, calculate_ed -- as two-stage
+ * fixed-order float64 reductions.  a, b: [S][n] volumes of `in_type` (n = H*W); int16 volumes reproduce numpy's int16
+ * wrap-around in (img1 - img2) and (img1 - img2)**2.
+ *   stats [S][12] = per slice: sum|a-b|, sum(a-b)^2, sum ab, sum aa, sum bb, sum a, sum b, min a, max a, min b, max b, 0
+ *   scratch: S * max(ducosy_metrics_chunks(n) * 12, ducosy_metrics_ssim_tiles(H, W)) doubles */
+enum { DUCOSY_IN_I16 = 0, DUCOSY_IN_F32 = 1, DUCOSY_IN_F64 = 2 };
+int ducosy_metrics_chunks(long long n);
+int ducosy_metrics_slice_stats(const void* a, const void* b, int in_type, int S, long long n, double* stats, double* scratch,
+                               ducosy_stream_t stream);
+/* ed_sums[S] = sum over the slice of ((a - min a)/(range a + 1e-8) - (b - min b)/(range b + 1e-8))^2 (calculate.py:373-379);
+ * `stats` from ducosy_metrics_slice_stats. */
+int ducosy_metrics_ed(const void* a, const void* b, int in_type, int S, long long n, const double* stats, double* ed_sums,
+                      double* scratch, ducosy_stream_t stream);
+/* out[i] = (in[i] - minmax[0]) / (minmax[1] - minmax[0]) in float64, zeros when the range is zero (calculate.py:232-238);
+ * minmax: 2 doubles in DEVICE memory. */
+int ducosy_metrics_normalize(const void* in, int in_type, double* out, long long total, const double* minmax,
+                             ducosy_stream_t stream);
+int ducosy_metrics_ssim_tiles(int H, int W);
+/* ssim_sums[S] = sum of the SSIM map over the valid region [3, H-3) x [3, W-3) of each slice pair; mean = / ((H-6)(W-6)). */
+int ducosy_metrics_ssim(const void* a, const void* b, int in_type, int S, int H, int W, double data_range, double* ssim_sums,
+                        double* scratch, ducosy_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -603,3 +603,95 @@ def mask_detect_lung_vessels(hu: np.ndarray, lung_mask: np.ndarray, vessel_lower
         cond = np.logical_and(hu[z] >= vessel_lower, hu[z] <= vessel_upper)              # :96
         vessel[z] = np.logical_and(cand, cond).astype(np.uint8)
     return vessel
+
+
+# --------------------------------------------------------------------------------------
+# image-quality metrics (calculate.py) -- SURVEY 8f row N4
+# --------------------------------------------------------------------------------------
+def metrics_test_volumes(S: int, H: int, W: int, seed: int):
+    """A seeded (target, prediction) pair of int16 stored-value volumes: phantom slices and a perturbed copy (noise, a contrast
+    shift inside the body, one slice left identical so the inf / zero branches of PSNR are exercised)."""
+    rng = np.random.Generator(np.random.PCG64(seed))
+    tgt = phantom_volume(S, H, W, seed=seed).astype(np.int16)
+    noise = rng.normal(0.0, 25.0, size=tgt.shape)
+    pred = tgt.astype(np.float64) + noise + 40.0 * (tgt > 900)
+    pred[:, : H // 8, : W // 8] += 300.0          # a block of large differences: (a-b)**2 leaves the int16 range
+    pred = np.clip(np.rint(pred), -2000, 4000).astype(np.int16)
+    if S > 1:
+        pred[S - 1] = tgt[S - 1]
+    return tgt, pred
+
+
+def metric_normalize(data):
+    """calculate.py:232-238."""
+    mn, mx = data.min(), data.max()
+    if mx - mn == 0:
+        return np.zeros_like(data)
+    return (data - mn) / (mx - mn)
+
+
+def metric_mae(img1, img2):
+    """calculate.py:243-245 (numpy dtype semantics kept: int16 inputs subtract in int16)."""
+    diff = np.abs(img1 - img2)
+    return np.mean(diff), [np.mean(s) for s in diff]
+
+
+def metric_psnr(img1, img2):
+    """calculate.py:247-263."""
+    mse = np.mean((img1 - img2) ** 2)
+    if mse == 0:
+        return float("inf"), [float("inf")] * len(img1)
+    rng = img1.max() - img1.min()
+    max_pixel = 1.0 if rng == 0 else rng
+    out = []
+    for s1, s2 in zip(img1, img2):
+        m = np.mean((s1 - s2) ** 2)
+        out.append(float("inf") if m == 0 else 20 * np.log10(max_pixel / np.sqrt(m)))
+    return 20 * np.log10(max_pixel / np.sqrt(mse)), out
+
+
+def skimage_structural_similarity(im1, im2, data_range):
+    """skimage.metrics.structural_similarity with its defaults as calculate.py:270 calls it (win_size 7, uniform filter,
+    use_sample_covariance=True, K1 0.01, K2 0.03, crop of (win_size-1)//2, float64 mean).  PARITY UNPINNED: scikit-image is
+    not installed here (and unpinned in requirements.txt); restated from its published implementation with the same
+    scipy.ndimage.uniform_filter it calls."""
+    from scipy.ndimage import uniform_filter
+    ft = np.float32 if im1.dtype == np.float32 else np.float64
+    im1, im2 = im1.astype(ft, copy=False), im2.astype(ft, copy=False)
+    win, NP = 7, 49
+    cov_norm = NP / (NP - 1)
+    f = lambda a: uniform_filter(a, size=win)
+    ux, uy = f(im1), f(im2)
+    uxx, uyy, uxy = f(im1 * im1), f(im2 * im2), f(im1 * im2)
+    vx, vy, vxy = cov_norm * (uxx - ux * ux), cov_norm * (uyy - uy * uy), cov_norm * (uxy - ux * uy)
+    C1, C2 = (0.01 * data_range) ** 2, (0.03 * data_range) ** 2
+    S = ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux ** 2 + uy ** 2 + C1) * (vx + vy + C2))
+    pad = (win - 1) // 2
+    return S[pad:-pad, pad:-pad].mean(dtype=np.float64)
+
+
+def metric_ssim(img1, img2):
+    """calculate.py:265-272."""
+    data_range = img2.max() - img2.min()
+    out = [skimage_structural_similarity(s1, s2, data_range) for s1, s2 in zip(img1, img2)]
+    return np.mean(out), out
+
+
+def metric_cs(img1, img2):
+    """calculate.py:360-367 (sklearn cosine_similarity: rows scaled to unit norm in float64, then the dot product)."""
+    out = []
+    for s1, s2 in zip(img1, img2):
+        v1, v2 = s1.reshape(-1).astype(np.float64), s2.reshape(-1).astype(np.float64)
+        n1, n2 = np.sqrt(v1 @ v1), np.sqrt(v2 @ v2)
+        out.append(float((v1 / (n1 if n1 else 1.0)) @ (v2 / (n2 if n2 else 1.0))))
+    return np.mean(out), out
+
+
+def metric_ed(img1, img2):
+    """calculate.py:369-381."""
+    out = []
+    for s1, s2 in zip(img1, img2):
+        a = (s1 - s1.min()) / (s1.max() - s1.min() + 1e-8)
+        b = (s2 - s2.min()) / (s2.max() - s2.min() + 1e-8)
+        out.append(np.linalg.norm(a - b) / np.prod(a.shape))
+    return np.mean(out), out

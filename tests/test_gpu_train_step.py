@@ -359,3 +359,38 @@ def test_training_survives_a_constant_channel():
     for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B):
         assert all(torch.isfinite(p).all().item() for p in m.parameters())
     print("skipped steps:", step.optimizer_G.skipped_steps(), step.optimizer_D_A.skipped_steps(), step.optimizer_D_B.skipped_steps())
+
+
+def test_validation_loss_and_image_grid_match_oracle():
+    """validate_and_save_images (reference modules/trainer.py:187-294): the validation loss
+    GAN + 10 cycle + 5 id averaged over two batches (eval mode, no autograd) against the oracle's restatement of the same
+    terms, and the display-windowed real_A | fake_B | real_B grid against oracle.apply_windowing; training mode is restored."""
+    from ducosy_gan_b200.trainer import CycleGANStep
+    Cin, blocks, cbam, B, H, W = 2, 1, True, 1, 256, 512
+    step = CycleGANStep(Cin, blocks, cbam, seed=5)
+    g = torch.Generator().manual_seed(9)
+    smooth = lambda t: torch.nn.functional.avg_pool2d(t, 5, 1, 2) * 2.0
+    batches = []
+    for _ in range(2):
+        batches.append({"A": smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1),
+                        "B": smooth(torch.rand(B, 1, H, W, generator=g) * 2 - 1).clamp(-1, 1),
+                        "masks": (torch.rand(B, Cin - 1, H, W, generator=g) < 0.1).float()})
+    cpu = lambda m: {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    sds = [cpu(m) for m in (step.G_A2B, step.G_B2A, step.D_A, step.D_B)]
+    want = 0.0
+    with torch.no_grad():
+        for b in batches:
+            _, t, _, fake_B = orc.cyclegan_generator_loss(*sds, b["A"], b["B"], b["masks"], blocks, cbam)
+            want += float(t["GAN"] + 10.0 * t["cycle"] + 5.0 * t["id"])        # trainer.py:249
+    want /= len(batches)
+    step.G_A2B.train(), step.G_B2A.train()
+    got = step.validation_loss(batches)
+    assert step.G_A2B.training and step.G_B2A.training
+    print(f"validation loss: cuda {got:.5f}  oracle {want:.5f}")
+    assert abs(got - want) <= 3e-2 * abs(want)
+    grid = step.validation_image_grid(batches[-1], -150, 250, 40, 400).cpu()
+    assert grid.shape == (B, 1, H, 3 * W)
+    win = lambda x: torch.from_numpy(orc.apply_windowing(x, -150, 250, 40, 400))
+    ref = torch.cat((win(batches[-1]["A"]), win(fake_B), win(batches[-1]["B"])), -1)
+    assert torch.equal(grid[..., :W], ref[..., :W]) and torch.equal(grid[..., 2 * W:], ref[..., 2 * W:])   # real images: same fp32 steps
+    assert (grid - ref).abs().max().item() < 1.5e-2        # fake_B: the generator's stated fp16 tolerance (window scale 400/400)

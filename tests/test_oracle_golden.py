@@ -177,3 +177,20 @@ def test_oracle_masks_match_reference_golden(golden_dir):
         lung = orc.mask_detect_lung(hu)
         assert np.array_equal(lung, unpack(f"lung_{name}"))
         assert np.array_equal(orc.mask_detect_lung_vessels(hu, lung), unpack(f"vessel_{name}"))
+
+
+def test_oracle_metrics_match_reference_golden(golden_dir):
+    """the oracle's restatements of calculate.py:232-271,360-381 against values the reference's own functions
+    produced (oracle/make_golden_metrics.py).  SSIM's core is skimage (absent): parity unpinned, see the oracle docstring."""
+    import warnings
+    g = np.load(os.path.join(golden_dir, "metrics.npz"))
+    warnings.simplefilter("ignore")
+    for name in ("a", "b"):
+        S, H, W, seed = (int(v) for v in g[f"shape_{name}"])
+        tgt, pred = orc.metrics_test_volumes(S, H, W, seed)
+        pairs = {"raw": (tgt, pred), "norm": (orc.metric_normalize(tgt), orc.metric_normalize(pred))}
+        for tag, (x, y) in pairs.items():
+            for metric in ("mae", "psnr", "ssim", "cs", "ed"):
+                m, lst = getattr(orc, f"metric_{metric}")(x, y)
+                got = np.concatenate([[float(m)], np.asarray(lst, dtype=np.float64)])
+                assert np.allclose(got, g[f"{metric}_{tag}_{name}"], rtol=1e-12, atol=0), (name, tag, metric)
