@@ -30,6 +30,10 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return 0;
 }
+bool pdl_enabled() {
+  static const bool on = []() { const char* e = getenv("DUCOSY_PDL"); return e == nullptr || atoi(e) != 0; }();
+  return on;
+}
 int num_sms() {
   static int cached[64] = {0};
   int dev = 0;

@@ -34,6 +34,7 @@ __device__ __forceinline__ float warp_max(float v) {
 // one CTA per (b, c) plane: mean and max over H*W (fixed-order tree: deterministic)
 __global__ void __launch_bounds__(256)
 ca_pool_kernel(const float* __restrict__ x, float* __restrict__ avg, float* __restrict__ mx, long long HW) {
+  pdl_prologue();
   const float* p = x + (long long)blockIdx.x * HW;
   float s = 0.f, m = -INFINITY;
   if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(p) & 15) == 0) {
@@ -73,6 +74,7 @@ ca_pool_kernel(const float* __restrict__ x, float* __restrict__ avg, float* __re
 __global__ void __launch_bounds__(256)
 ca_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx, const float* __restrict__ fc0,
               const float* __restrict__ fc2, float* __restrict__ att, int C, int Hd) {
+  pdl_prologue();
   extern __shared__ float sh[];          // hidden_avg[Hd], hidden_max[Hd]
   const int b = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -102,6 +104,7 @@ ca_mlp_kernel(const float* __restrict__ avg, const float* __restrict__ mx, const
 __global__ void __launch_bounds__(256)
 scale_planes_kernel(const float* __restrict__ x, const float* __restrict__ att, float* __restrict__ out, long long HW,
                     long long total) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256)
     out[i] = x[i] * att[i / HW];
 }
@@ -110,6 +113,7 @@ scale_planes_kernel(const float* __restrict__ x, const float* __restrict__ att, 
 // pooled[b][0][p] = mean_c x, pooled[b][1][p] = max_c x  (thread per pixel, coalesced along W for every channel plane)
 __global__ void __launch_bounds__(256)
 sa_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled, int C, long long HW, long long total) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long b = i / HW, p = i - b * HW;
     const float* src = x + b * C * HW + p;
@@ -128,6 +132,7 @@ sa_pool_kernel(const float* __restrict__ x, float* __restrict__ pooled, int C, l
 __global__ void __launch_bounds__(256)
 sa_conv_kernel(const float* __restrict__ pooled, const float* __restrict__ w, float* __restrict__ att, int H, int W, int k,
                long long total) {
+  pdl_prologue();
   extern __shared__ float wsh[];
   for (int i = threadIdx.x; i < 2 * k * k; i += 256) wsh[i] = w[i];
   __syncthreads();
@@ -157,6 +162,7 @@ sa_conv_kernel(const float* __restrict__ pooled, const float* __restrict__ w, fl
 __global__ void __launch_bounds__(256)
 scale_pixels_kernel(const float* __restrict__ x, const float* __restrict__ att, float* __restrict__ out, int C, long long HW,
                     long long total) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const long long bc = i / HW, p = i - bc * HW;
     out[i] = x[i] * att[(bc / C) * HW + p];
@@ -169,6 +175,7 @@ scale_pixels_kernel(const float* __restrict__ x, const float* __restrict__ att, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 nchw_to_nhwc_pad_kernel(const float* __restrict__ x, T* __restrict__ out, int C, int H, int W, int pad, int pad_mode) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int Hp = H + 2 * pad, Wp = W + 2 * pad;
   const int b = blockIdx.z, yp = blockIdx.y, xp0 = blockIdx.x * 32;
@@ -199,6 +206,7 @@ nchw_to_nhwc_pad_kernel(const float* __restrict__ x, T* __restrict__ out, int C,
 template <typename T>
 __global__ void __launch_bounds__(256)
 nhwc_to_nchw_kernel(const T* __restrict__ y, float* __restrict__ out, int C, int H, int W) {
+  pdl_prologue();
   __shared__ float tile[32][33];
   const int b = blockIdx.z, yy = blockIdx.y, x0 = blockIdx.x * 32;
   for (int c0 = 0; c0 < C; c0 += 32) {
@@ -235,12 +243,12 @@ extern "C" int ducosy_channel_attention_nchw(const float* x, const float* fc0, c
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long HW = (long long)H * W;
   float *avg = scratch, *mx = scratch + (size_t)B * C, *att = scratch + (size_t)2 * B * C;
-  ca_pool_kernel<<<B * C, 256, 0, st>>>(x, avg, mx, HW);
+  pdl(ca_pool_kernel, B * C, 256, 0, st)(x, avg, mx, HW);
   DUCOSY_TRY(check_launch("ca_pool_kernel"));
-  ca_mlp_kernel<<<B, 256, 2 * hidden * sizeof(float), st>>>(avg, mx, fc0, fc2, att, C, hidden);
+  pdl(ca_mlp_kernel, B, 256, 2 * hidden * sizeof(float), st)(avg, mx, fc0, fc2, att, C, hidden);
   DUCOSY_TRY(check_launch("ca_mlp_kernel"));
   const long long total = (long long)B * C * HW;
-  scale_planes_kernel<<<ew_blocks(total), 256, 0, st>>>(x, att, out, HW, total);
+  pdl(scale_planes_kernel, ew_blocks(total), 256, 0, st)(x, att, out, HW, total);
   return check_launch("scale_planes_kernel");
 }
 
@@ -254,12 +262,12 @@ extern "C" int ducosy_spatial_attention_nchw(const float* x, const float* w, flo
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long HW = (long long)H * W, npix = (long long)B * HW;
   float *pooled = scratch, *att = scratch + (size_t)2 * B * HW;
-  sa_pool_kernel<<<ew_blocks(npix), 256, 0, st>>>(x, pooled, C, HW, npix);
+  pdl(sa_pool_kernel, ew_blocks(npix), 256, 0, st)(x, pooled, C, HW, npix);
   DUCOSY_TRY(check_launch("sa_pool_kernel"));
-  sa_conv_kernel<<<ew_blocks(npix), 256, 2 * ksize * ksize * sizeof(float), st>>>(pooled, w, att, H, W, ksize, npix);
+  pdl(sa_conv_kernel, ew_blocks(npix), 256, 2 * ksize * ksize * sizeof(float), st)(pooled, w, att, H, W, ksize, npix);
   DUCOSY_TRY(check_launch("sa_conv_kernel"));
   const long long total = npix * C;
-  scale_pixels_kernel<<<ew_blocks(total), 256, 0, st>>>(x, att, out, C, HW, total);
+  pdl(scale_pixels_kernel, ew_blocks(total), 256, 0, st)(x, att, out, C, HW, total);
   return check_launch("scale_pixels_kernel");
 }
 
@@ -269,7 +277,7 @@ extern "C" int ducosy_nchw_to_nhwc_pad(const float* x, void* out, int B, int C, 
   DUCOSY_CHECK(pad >= 0 && pad < H && pad < W && B <= 65535 && H + 2 * pad <= 65535, DUCOSY_ERR_SHAPE, "nchw_to_nhwc_pad: bad shape");
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "nchw_to_nhwc_pad: bad dtype");
   const dim3 grid((W + 2 * pad + 31) / 32, H + 2 * pad, B), block(32, 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (nchw_to_nhwc_pad_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(nchw_to_nhwc_pad_kernel<T>, grid, block, 0, (cudaStream_t)stream)(
                                       x, static_cast<T*>(out), C, H, W, pad, pad_mode)));
   return check_launch("nchw_to_nhwc_pad_kernel");
 }
@@ -278,7 +286,7 @@ extern "C" int ducosy_nhwc_to_nchw(const void* y, float* out, int B, int C, int 
   DUCOSY_CHECK(y && out && B > 0 && C > 0 && H > 0 && W > 0 && B <= 65535 && H <= 65535, DUCOSY_ERR_ARG, "nhwc_to_nchw: bad argument");
   DUCOSY_CHECK(dtype == DUCOSY_F16 || dtype == DUCOSY_BF16, DUCOSY_ERR_ARG, "nhwc_to_nchw: bad dtype");
   const dim3 grid((W + 31) / 32, H, B), block(32, 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (nhwc_to_nchw_kernel<T><<<grid, block, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(nhwc_to_nchw_kernel<T>, grid, block, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(y), out, C, H, W)));
   return check_launch("nhwc_to_nchw_kernel");
 }

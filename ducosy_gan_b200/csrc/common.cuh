@@ -4,6 +4,7 @@
 #include <cstdarg>
 #include <cstdint>
 #include <cstdio>
+#include <utility>
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -49,6 +50,51 @@ struct PerDeviceOnce {
     return e;
   }
 };
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the library is launched with cudaLaunchAttributeProgrammaticStreamSerialization and starts with
+// pdl_prologue(): `griddepcontrol.launch_dependents` lets the NEXT kernel of the stream be scheduled while this one is still
+// running (its CTAs become resident, run their own prologue and stop at their wait), `griddepcontrol.wait` blocks until the
+// PREVIOUS kernel has completed and its memory operations are visible.  No global memory is touched before the wait, so the
+// data flow is exactly that of plain stream order; what disappears is the launch gap between dependent kernels -- the
+// batch-1 forward and the one-sample-per-rank training step are chains of 100 / 3000 kernels of a few microseconds each.
+// Kernels that allocate TMEM trigger only AFTER their allocation: a dependent CTA that lands on the same SM first would
+// hold TMEM columns while waiting for this very grid.  DUCOSY_PDL=0 launches without the attribute (then both
+// instructions are no-ops).
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_prologue() {
+  pdl_launch_dependents();
+  pdl_wait();
+}
+bool pdl_enabled();
+
+// kern<<<grid, block, smem, stream>>>(args...)  ==  pdl(kern, grid, block, smem, stream)(args...)
+template <typename K>
+struct PdlLaunch {
+  K kern;
+  dim3 grid, block;
+  size_t smem;
+  cudaStream_t stream;
+  template <typename... A>
+  void operator()(A&&... args) const {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 1 : 0;
+    (void)cudaLaunchKernelEx(&cfg, kern, std::forward<A>(args)...);   // errors surface through check_launch()
+  }
+};
+template <typename K>
+PdlLaunch<K> pdl(K kern, dim3 grid, dim3 block, size_t smem = 0, cudaStream_t stream = nullptr) {
+  return PdlLaunch<K>{kern, grid, block, smem, stream};
+}
 
 constexpr int kMaxTaps = 16;
 constexpr int kMaxVTaps = 32;   // "virtual" taps of the split-operand mode: 3 per filter tap (A_hi*W_hi, A_lo*W_hi, A_hi*W_lo)

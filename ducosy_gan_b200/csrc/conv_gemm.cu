@@ -240,10 +240,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (kCG == 2) cluster_sync_all(); else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch (common.cuh): TMEM is allocated, so the next kernel's CTAs may come in; the barrier /
+  // TMEM / descriptor set-up above overlapped the tail of the previous kernel, whose results are first touched below
+  pdl_launch_dependents();
 
   if (warp == kWarpTma) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
+      pdl_wait();
       int s = 0;
       uint32_t ph = 0;
       for (int unit = unit0; unit < total_units; unit += unit_step) {
@@ -326,6 +330,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int as = 0;
     int fin_n = 0;                       // tiles this CTA has finished (parity selects the ticket slot)
     uint32_t aph = 0;
+    pdl_wait();                          // before the first global store (output tile, partials, tickets)
     for (int unit = unit0; unit < total_units; unit += unit_step) {
       const TileCoord tc = decode_tile(unit_tile(unit), a);
       mbar_wait(&tfull[as], aph);
@@ -474,17 +479,19 @@ int launch_impl(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMa
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = C::kSmemBytes;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmO, args);
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaLaunchKernelEx(conv_gemm pair): %s", cudaGetErrorString(e));
   } else {
-    kern<<<grid, kThreads, C::kSmemBytes, stream>>>(tmA, tmB, tmO, args);
+    pdl(kern, grid, kThreads, C::kSmemBytes, stream)(tmA, tmB, tmO, args);
   }
   return check_launch("conv_gemm_kernel");
 }

@@ -90,9 +90,11 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // programmatic dependent launch (common.cuh): only after the TMEM allocation
 
   if (warp == 0) {
     if (lane == 0) {
+      pdl_wait();            // the operand maps come from the previous kernels
       int s = 0;
       uint32_t ph = 0;
       for (int ch = c_begin; ch < c_end; ++ch) {
@@ -147,6 +149,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
     }
   } else if (warp >= 4) {
     const int q = warp & 3;
+    pdl_wait();              // before the first global store
     mbar_wait(done, 0);
     tc_fence_after();
     for (int mh = 0; mh < kMP; ++mh) {
@@ -176,6 +179,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap tmDY, const __grid_constan
 // dw[o][c][tap] times gs[1] (the inverse gradient scale) -- reduce and unpack in one pass
 __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, int splits, int taps,
                                     int Cout, int Cin, int oihw, const float* __restrict__ gs) {
+  pdl_prologue();
   const long long per_split = (long long)taps * Cout * Cin;
   const float inv = (oihw != 0 && gs != nullptr) ? gs[1] : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < per_split; i += (long long)gridDim.x * blockDim.x) {
@@ -291,7 +295,7 @@ int conv2d_wgrad_impl(const void* x_pad, const void* dy, int dy_pad, float* dw, 
   do {                                                                                                          \
     static PerDeviceOnce cfg;                                                                                   \
     cfg.once([&] { return cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)); }); \
-    conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
+    pdl(conv_wgrad_kernel<T, MP>, grid, kWgThreads, smem, st)(tmDY, tmX, a);                                      \
   } while (0)
   if (dtype == DUCOSY_F16) {
     if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__half, 2); else DUCOSY_WGRAD_LAUNCH(__half, 1);
@@ -303,7 +307,7 @@ int conv2d_wgrad_impl(const void* x_pad, const void* dy, int dy_pad, float* dw, 
   const long long per_split = (long long)a.num_taps * Cout * Cin;
   long long blocks = (per_split + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dw, splits, a.num_taps, Cout, Cin, oihw, gs);
+  pdl(wgrad_reduce_kernel, int(blocks), 256, 0, st)(a.partial, dw, splits, a.num_taps, Cout, Cin, oihw, gs);
   return check_launch("wgrad_reduce_kernel");
 }
 }  // namespace
@@ -387,7 +391,7 @@ extern "C" int ducosy_upconv2x_wgrad_nhwc(const void* src_pad, const void* dy, i
 #define DUCOSY_WGRAD_LAUNCH(T, MP)                                                                              \
   do {                                                                                                          \
     cudaFuncSetAttribute(conv_wgrad_kernel<T, MP>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem));      \
-    conv_wgrad_kernel<T, MP><<<grid, kWgThreads, smem, st>>>(tmDY, tmX, a);                                      \
+    pdl(conv_wgrad_kernel<T, MP>, grid, kWgThreads, smem, st)(tmDY, tmX, a);                                      \
   } while (0)
   if (dtype == DUCOSY_F16) {
     if (a.m_per_cta == 2) DUCOSY_WGRAD_LAUNCH(__half, 2); else DUCOSY_WGRAD_LAUNCH(__half, 1);
@@ -399,7 +403,7 @@ extern "C" int ducosy_upconv2x_wgrad_nhwc(const void* src_pad, const void* dy, i
   const long long per_split = (long long)a.num_taps * Cout * Cin;
   long long blocks = (per_split + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  wgrad_reduce_kernel<<<int(blocks), 256, 0, st>>>(a.partial, dwph, splits, a.num_taps, Cout, Cin, 0, nullptr);
+  pdl(wgrad_reduce_kernel, int(blocks), 256, 0, st)(a.partial, dwph, splits, a.num_taps, Cout, Cin, 0, nullptr);
   return check_launch("wgrad_reduce_kernel");
 }
 
@@ -408,6 +412,7 @@ namespace {
 // dW[o][c][r][s] = gs1 * sum_{py,px} dWph[o][((py*2+px)*4 + a(py,r)*2 + b(px,s)) * Cin + c],  a(0,r) = (r >= 1), a(1,r) = (r >= 2)
 __global__ void unpack_upconv_wgrad_kernel(const float* __restrict__ dwph, float* __restrict__ g, int Cout, int Cin,
                                            const float* __restrict__ gs) {
+  pdl_prologue();
   const float inv = gs != nullptr ? gs[1] : 1.f;
   const long long total = (long long)Cout * Cin * 9;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -431,6 +436,6 @@ extern "C" int ducosy_unpack_upconv_wgrad(const float* dwph, float* g_oihw, int 
   const long long total = (long long)Cout * Cin * 9;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  unpack_upconv_wgrad_kernel<<<int(blocks), 256, 0, (cudaStream_t)stream>>>(dwph, g_oihw, Cout, Cin, gs);
+  pdl(unpack_upconv_wgrad_kernel, int(blocks), 256, 0, (cudaStream_t)stream)(dwph, g_oihw, Cout, Cin, gs);
   return check_launch("unpack_upconv_wgrad_kernel");
 }

@@ -16,6 +16,7 @@ namespace {
 template <typename T>
 __global__ void disc_first_conv_kernel(const float* __restrict__ x, const float* __restrict__ w /*[64][16]*/,
                                        const float* __restrict__ bias, T* __restrict__ out, int B, int H, int W) {
+  pdl_prologue();
   __shared__ __align__(16) float sw[16 * 64];  // [tap][channel]: a thread's 8 channels are two conflict-free float4 reads
   __shared__ float sb[64];
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[(i & 15) * 64 + (i >> 4)] = w[i];
@@ -64,6 +65,7 @@ __global__ void disc_first_conv_kernel(const float* __restrict__ x, const float*
 template <typename T>
 __global__ void disc_last_conv_kernel(const T* __restrict__ in, const T* __restrict__ wp /*[16][512]*/,
                                       const float* __restrict__ bias, float* __restrict__ out, int B, int Hs, int Ws) {
+  pdl_prologue();
   const int lane = threadIdx.x & 31;
   const int Wp = Ws + 4, Hp = Hs + 4;
   const long long total = (long long)B * Hs * Ws;
@@ -99,6 +101,7 @@ __global__ void disc_last_conv_kernel(const T* __restrict__ in, const T* __restr
 
 template <typename T>
 __global__ void pack_disc_last_weight_kernel(const float* __restrict__ w /*[1][512][4][4]*/, T* __restrict__ out) {
+  pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 16 * 512; i += gridDim.x * blockDim.x) {
     const int c = i & 511, tap = i >> 9;
     out[i] = Cvt<T>::from_f(w[c * 16 + tap]);
@@ -180,7 +183,7 @@ extern "C" int ducosy_discriminator_pack(const float* const* params, int num_par
   DUCOSY_TRY(ducosy_pack_conv_weight(params[2], pk + L.w2, 128, 64, 4, 4, dtype, stream));
   DUCOSY_TRY(ducosy_pack_conv_weight(params[4], pk + L.w3, 256, 128, 4, 4, dtype, stream));
   DUCOSY_TRY(ducosy_pack_conv_weight(params[6], pk + L.w4, 512, 256, 4, 4, dtype, stream));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_disc_last_weight_kernel<T><<<32, 256, 0, st>>>(params[8], reinterpret_cast<T*>(pk + L.w5))));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_disc_last_weight_kernel<T>, 32, 256, 0, st)(params[8], reinterpret_cast<T*>(pk + L.w5))));
   cudaMemcpyAsync(pk + L.b5, params[9], 4, cudaMemcpyDeviceToDevice, st);
   DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[2], pk + L.wd2, 128, 64, 4, dtype, stream));
   DUCOSY_TRY(ducosy_pack_dgrad_s2_weight(params[4], pk + L.wd3, 256, 128, 4, dtype, stream));
@@ -211,7 +214,7 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
     long long blocks = (total + 255) / 256;
     const long long cap = (long long)(num_sms() > 0 ? num_sms() : 148) * 8;
     if (blocks > cap) blocks = cap;
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_conv_kernel<T><<<int(blocks), 256, 0, st>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_first_conv_kernel<T>, int(blocks), 256, 0, st)(
                                         x, reinterpret_cast<const float*>(pk + L.w1), reinterpret_cast<const float*>(pk + L.b1),
                                         reinterpret_cast<T*>(base + w.p1), B, H, W)));
     DUCOSY_TRY(check_launch("disc_first_conv_kernel"));
@@ -236,7 +239,7 @@ extern "C" int ducosy_discriminator_forward(const void* packed, const float* x, 
     long long blocks = (outputs + 7) / 8;
     const long long cap = (long long)(num_sms() > 0 ? num_sms() : 148) * 8;
     if (blocks > cap) blocks = cap;
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_conv_kernel<T><<<int(blocks), 256, 0, st>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_last_conv_kernel<T>, int(blocks), 256, 0, st)(
                                         reinterpret_cast<const T*>(base + w.p4), reinterpret_cast<const T*>(pk + L.w5),
                                         reinterpret_cast<const float*>(pk + L.b5), out, B, Hi, Wi)));
   }

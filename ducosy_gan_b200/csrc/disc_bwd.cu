@@ -27,6 +27,7 @@ __device__ __forceinline__ float act_grad(float n, int act) {  // derivative of 
 // like their bits; max is exact and order-independent, so the result is deterministic), then one thread derives the scale.
 __global__ void __launch_bounds__(256)
 grad_absmax_kernel(const float* __restrict__ g, long long n, int* __restrict__ slot) {
+  pdl_prologue();
   __shared__ float red[8];
   float m = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -46,6 +47,7 @@ grad_absmax_kernel(const float* __restrict__ g, long long n, int* __restrict__ s
   }
 }
 __global__ void grad_scale_finalize_kernel(float* __restrict__ gs) {
+  pdl_prologue();
   const float m = __int_as_float(reinterpret_cast<int*>(gs)[1]);
   int e = 0;
   if (m > 0.f && isfinite(m)) {
@@ -66,6 +68,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                      const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block) {
+  pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C] with rows = 256 / (C/8)
   const int cv = C / 8, c8 = threadIdx.x % cv, prow = threadIdx.x / cv, rows = 256 / cv;
   const int b = blockIdx.y;
@@ -123,6 +126,7 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
 // -- up to 256 rows for one 128x128 sample -- it became the longest kernel of the InstanceNorm backward.)
 __global__ void __launch_bounds__(256)
 in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ sums, int blocks, int C, float inv_hw) {
+  pdl_prologue();
   __shared__ double part[8][33];
   const int b = blockIdx.y;
   const int col = blockIdx.x * 32 + (threadIdx.x & 31), slice = threadIdx.x >> 5;
@@ -147,6 +151,7 @@ __global__ void __launch_bounds__(256)
 in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ means, T* __restrict__ dy_pad, int B,
                         int H, int W, int C, int pad, int act) {
+  pdl_prologue();
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
   const int b = blockIdx.y, c8 = threadIdx.x % cv, px0 = threadIdx.x / cv, px_step = 256 / cv;
   float rs[8], sh[8], m1[8], m2[8];
@@ -207,6 +212,7 @@ in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const
 //   4x4 kernel: r(0,.) = {3,1}, r(1,.) = {2,0};  3x3 kernel (model.py:96-98): r(0,.) = {-,1}, r(1,.) = {2,0} (- = no tap: zero)
 template <typename T>
 __global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci, int ksz) {
+  pdl_prologue();
   const long long total = 16LL * Co * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int o = int(i % Co);
@@ -226,6 +232,7 @@ __global__ void pack_dgrad_s2_weight_kernel(const float* __restrict__ w, T* __re
 // Wd[c][(r*3+s)*Co + o] = W[o][c][r][s]
 template <typename T>
 __global__ void pack_dgrad_s1_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+  pdl_prologue();
   const long long total = 9LL * Co * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int o = int(i % Co);
@@ -240,6 +247,7 @@ __global__ void pack_dgrad_s1_weight_kernel(const float* __restrict__ w, T* __re
 template <typename T>
 __global__ void dgrad_s1_edge_cols_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H,
                                           int W, int Ci, int Co) {
+  pdl_prologue();
   const long long total = (long long)B * (H + 2) * 2 * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int c = int(i % Ci);
@@ -274,6 +282,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 dgrad_s1_edge_cols256_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H, int W,
                              int Ci, int rows_per_chunk, int chunks_per_sample) {
+  pdl_prologue();
   constexpr int Co = 256;
   extern __shared__ uint4 srows[];   // [rows_per_chunk + 2][32] 16-byte pieces: dy_pad2 rows u0 .. u1+1 at column v - s + 2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -338,6 +347,7 @@ constexpr int kEdgePitch = 256 + 8;   // elements per staged dy row
 template <typename T>
 __global__ void __launch_bounds__(256)
 dgrad_s1_edge_cols_mma_kernel(const T* __restrict__ dy_pad2, const T* __restrict__ wd, T* __restrict__ dxpad, int B, int H, int W) {
+  pdl_prologue();
   constexpr int C = 256;
   __shared__ __align__(16) T rows[18 * kEdgePitch];   // rows[j][o] = dy_pad2[b][u0 + j][v - s + 2][o], j = m - r + 2
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tid = lane & 3;
@@ -390,6 +400,7 @@ dgrad_s1_edge_cols_mma_kernel(const T* __restrict__ dy_pad2, const T* __restrict
 template <typename T>
 __global__ void pad_fold_kernel(const T* __restrict__ dxpad, const T* __restrict__ add, T* __restrict__ dx, int B, int H, int W, int C,
                                 int pad, int mode) {
+  pdl_prologue();
   const int cv = C / 8, Hp = H + 2 * pad, Wp = W + 2 * pad;
   const long long total = (long long)B * H * W * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -442,6 +453,7 @@ __global__ void pad_fold_kernel(const T* __restrict__ dxpad, const T* __restrict
 //   Wd[c][(ph*4 + a*2 + b)*Co + o] = Wp[ph][a][b][o][c]       (Wp = the pre-summed phase weights of pack_upconv_weight)
 template <typename T>
 __global__ void pack_upconv_dgrad_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Co, int Ci) {
+  pdl_prologue();
   const long long total = 16LL * Co * Ci;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int o = int(i % Co);
@@ -462,6 +474,7 @@ __global__ void pack_upconv_dgrad_weight_kernel(const float* __restrict__ w, T* 
 // gradient needs; only the backward materialises it.
 template <typename T>
 __global__ void upsample2x_pad_kernel(const T* __restrict__ src_pad, T* __restrict__ up_pad, int B, int Hs, int Ws, int C) {
+  pdl_prologue();
   const int cv = C / 8, Hu = 2 * Hs + 2, Wu = 2 * Ws + 2;
   const long long total = (long long)B * Hu * Wu * cv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -481,6 +494,7 @@ __global__ void upsample2x_pad_kernel(const T* __restrict__ src_pad, T* __restri
 // packed fp32 weight gradient [Co][taps*Ci + c] -> OIHW [Co][Ci][taps]
 __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Co, int Ci, int taps,
                                     const float* __restrict__ gs) {
+  pdl_prologue();
   const float inv = gs != nullptr ? gs[1] : 1.f;
   const long long total = (long long)Co * Ci * taps;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -498,6 +512,7 @@ __global__ void unpack_wgrad_kernel(const float* __restrict__ packed, float* __r
 template <typename T>
 __global__ void disc_last_dgrad_kernel(const float* __restrict__ dout, const T* __restrict__ wp /*[16][512]*/,
                                        T* __restrict__ da, int B, int Hs, int Ws, const float* __restrict__ gs) {
+  pdl_prologue();
   const float gscale = gs != nullptr ? gs[0] : 1.f;
   const long long total = (long long)B * Hs * Ws * 64;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -532,6 +547,7 @@ constexpr int kLastSplits = 32;
 template <typename T>
 __global__ void __launch_bounds__(512)
 disc_last_wgrad_kernel(const float* __restrict__ dout, const T* __restrict__ p4, float* __restrict__ partial, int B, int Hs, int Ws) {
+  pdl_prologue();
   const int tap = blockIdx.x, c = threadIdx.x, r = tap >> 2, s = tap & 3;
   const int Hp = Hs + 4, Wp = Ws + 4;
   const int rows = B * Hs, r0 = (rows * blockIdx.y) / kLastSplits, r1 = (rows * (blockIdx.y + 1)) / kLastSplits;
@@ -551,6 +567,7 @@ disc_last_wgrad_kernel(const float* __restrict__ dout, const T* __restrict__ p4,
   if (tap == 0 && c == 0) partial[(size_t)blockIdx.y * 8193 + 8192] = dsum;
 }
 __global__ void disc_last_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i > 8192) return;
   float acc = 0.f;
@@ -566,6 +583,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 disc_first_wgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, const float* __restrict__ x,
                         float* __restrict__ partial, int B, int H, int W, int pix_per_block) {
+  pdl_prologue();
   // thread = (pixel lane pl 0..7, tap group tg 0..3 = filter row, channel group cg 0..7 = 8 channels): a warp is one pixel
   // lane, its 128-byte da1 / p1 rows are read with 16-byte loads (shared by the 4 tap groups through L1)
   __shared__ float red[8][64 * 17];
@@ -625,6 +643,7 @@ disc_first_wgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, con
 
 __global__ void disc_first_wgrad_reduce_kernel(const float* __restrict__ partial, float* __restrict__ dw, float* __restrict__ db,
                                                int blocks, const float* __restrict__ gs) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;  // 64 * 17
   if (i >= 64 * 17) return;
   double acc = 0.0;
@@ -638,6 +657,7 @@ __global__ void disc_first_wgrad_reduce_kernel(const float* __restrict__ partial
 template <typename T>
 __global__ void disc_first_dgrad_kernel(const T* __restrict__ da1, const T* __restrict__ p1, const float* __restrict__ w1,
                                         float* __restrict__ dx, int B, int H, int W, const float* __restrict__ gs) {
+  pdl_prologue();
   const float inv = gs != nullptr ? gs[1] : 1.f;
   __shared__ float sw[64 * 16];
   for (int i = threadIdx.x; i < 64 * 16; i += blockDim.x) sw[i] = w1[i];
@@ -720,13 +740,13 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
   float* partial = scratch;
   float* means = scratch + size_t(B) * blocks * 2 * C;
   const size_t smem = size_t(256 / (C / 8)) * 2 * C * 4;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_reduce_kernel<T><<<dim3(blocks, B), 256, smem, st>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T>, dim3(blocks, B), 256, smem, st)(
                                       static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb)));
   DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
-  in_bwd_finalize_kernel<<<dim3((2 * C + 31) / 32, B), 256, 0, st>>>(partial, means, blocks, C, 1.0f / float(HW));
+  pdl(in_bwd_finalize_kernel, dim3((2 * C + 31) / 32, B), 256, 0, st)(partial, means, blocks, C, 1.0f / float(HW));
   DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
   const int row_ctas = std::max(1, std::min(H + 2 * pad, (num_sms() * 4 + B - 1) / B));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (in_bwd_apply_pad_kernel<T><<<dim3(row_ctas, B), 256, 0, st>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_apply_pad_kernel<T>, dim3(row_ctas, B), 256, 0, st)(
                                       static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
                                       static_cast<T*>(dy_pad), B, H, W, C, pad, act)));
   return check_launch("in_bwd_apply_pad_kernel");
@@ -735,8 +755,8 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
 extern "C" int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int ksize, int dtype,
                                            ducosy_stream_t stream) {
   DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0 && (ksize == 3 || ksize == 4), DUCOSY_ERR_ARG, "pack_dgrad_s2_weight: bad argument");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_dgrad_s2_weight_kernel<T><<<grid_for_items(16LL * Cout * Cin, 256), 256, 0,
-                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin, ksize)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_dgrad_s2_weight_kernel<T>, grid_for_items(16LL * Cout * Cin, 256), 256, 0,
+                                                                   (cudaStream_t)stream)(w_oihw, static_cast<T*>(packed), Cout, Cin, ksize)));
   return check_launch("pack_dgrad_s2_weight_kernel");
 }
 
@@ -752,16 +772,16 @@ extern "C" int ducosy_grad_scale(const float* g, long long n, float* gs, ducosy_
   cudaStream_t st = (cudaStream_t)stream;
   DUCOSY_CHECK(cudaMemsetAsync(gs, 0, 2 * sizeof(float), st) == cudaSuccess, DUCOSY_ERR_CUDA, "grad_scale: memset failed");
   const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 4));
-  grad_absmax_kernel<<<blocks, 256, 0, st>>>(g, n, reinterpret_cast<int*>(gs) + 1);
+  pdl(grad_absmax_kernel, blocks, 256, 0, st)(g, n, reinterpret_cast<int*>(gs) + 1);
   DUCOSY_TRY(check_launch("grad_absmax_kernel"));
-  grad_scale_finalize_kernel<<<1, 1, 0, st>>>(gs);
+  pdl(grad_scale_finalize_kernel, 1, 1, 0, st)(gs);
   return check_launch("grad_scale_finalize_kernel");
 }
 
 extern "C" int ducosy_unpack_wgrad(const float* packed, float* g_oihw, int Cout, int Cin, int taps, const float* gs,
                                    ducosy_stream_t stream) {
   DUCOSY_CHECK(packed && g_oihw, DUCOSY_ERR_ARG, "unpack_wgrad: null pointer");
-  unpack_wgrad_kernel<<<grid_for_items((long long)Cout * Cin * taps, 256), 256, 0, (cudaStream_t)stream>>>(packed, g_oihw, Cout, Cin, taps, gs);
+  pdl(unpack_wgrad_kernel, grid_for_items((long long)Cout * Cin * taps, 256), 256, 0, (cudaStream_t)stream)(packed, g_oihw, Cout, Cin, taps, gs);
   return check_launch("unpack_wgrad_kernel");
 }
 
@@ -771,13 +791,13 @@ extern "C" int ducosy_disc_last_backward(const float* dout, const void* w5_packe
                                          ducosy_stream_t stream) {
   DUCOSY_CHECK(dout && w5_packed && p4 && da4 && dw5 && db5, DUCOSY_ERR_ARG, "disc_last_backward: null pointer");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_dgrad_kernel<T><<<grid_for_items((long long)B * Hs * Ws * 64, 256), 256, 0, st>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_last_dgrad_kernel<T>, grid_for_items((long long)B * Hs * Ws * 64, 256), 256, 0, st)(
                                       dout, static_cast<const T*>(w5_packed), static_cast<T*>(da4), B, Hs, Ws, gs)));
   DUCOSY_TRY(check_launch("disc_last_dgrad_kernel"));
   DUCOSY_CHECK(scratch != nullptr, DUCOSY_ERR_ARG, "disc_last_backward: scratch (ducosy_disc_last_backward_scratch_bytes) is null");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_last_wgrad_kernel<T><<<dim3(16, kLastSplits), 512, 0, st>>>(dout, static_cast<const T*>(p4), scratch, B, Hs, Ws)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_last_wgrad_kernel<T>, dim3(16, kLastSplits), 512, 0, st)(dout, static_cast<const T*>(p4), scratch, B, Hs, Ws)));
   DUCOSY_TRY(check_launch("disc_last_wgrad_kernel"));
-  disc_last_wgrad_reduce_kernel<<<(8193 + 255) / 256, 256, 0, st>>>(scratch, dw5, db5);
+  pdl(disc_last_wgrad_reduce_kernel, (8193 + 255) / 256, 256, 0, st)(scratch, dw5, db5);
   return check_launch("disc_last_wgrad_reduce_kernel");
 }
 
@@ -792,13 +812,13 @@ extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long P = (long long)B * (H / 2) * (W / 2);
   const int blocks = int((P + 255) / 256);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_wgrad_kernel<T><<<blocks, 256, 0, st>>>(static_cast<const T*>(da1), static_cast<const T*>(p1),
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_first_wgrad_kernel<T>, blocks, 256, 0, st)(static_cast<const T*>(da1), static_cast<const T*>(p1),
                                                                                      x, scratch, B, H, W, 256)));
   DUCOSY_TRY(check_launch("disc_first_wgrad_kernel"));
-  disc_first_wgrad_reduce_kernel<<<(64 * 17 + 255) / 256, 256, 0, st>>>(scratch, dw1, db1, blocks, gs);
+  pdl(disc_first_wgrad_reduce_kernel, (64 * 17 + 255) / 256, 256, 0, st)(scratch, dw1, db1, blocks, gs);
   DUCOSY_TRY(check_launch("disc_first_wgrad_reduce_kernel"));
   if (dx != nullptr) {
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (disc_first_dgrad_kernel<T><<<grid_for_items((long long)B * H * W, 256), 256, 0, st>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(disc_first_dgrad_kernel<T>, grid_for_items((long long)B * H * W, 256), 256, 0, st)(
                                         static_cast<const T*>(da1), static_cast<const T*>(p1), w1, dx, B, H, W, gs)));
     return check_launch("disc_first_dgrad_kernel");
   }
@@ -807,8 +827,8 @@ extern "C" int ducosy_disc_first_backward(const void* da1, const void* p1, const
 
 extern "C" int ducosy_pack_dgrad_s1_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_dgrad_s1_weight: bad argument");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_dgrad_s1_weight_kernel<T><<<grid_for_items(9LL * Cout * Cin, 256), 256, 0,
-                                                                   (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_dgrad_s1_weight_kernel<T>, grid_for_items(9LL * Cout * Cin, 256), 256, 0,
+                                                                   (cudaStream_t)stream)(w_oihw, static_cast<T*>(packed), Cout, Cin)));
   return check_launch("pack_dgrad_s1_weight_kernel");
 }
 
@@ -836,7 +856,7 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
   p.partials = nullptr; p.dtype = dtype;
   DUCOSY_TRY(launch_conv_gemm(p, static_cast<cudaStream_t>(stream)));
   if (Cout == 256 && Cin == 256) {
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols_mma_kernel<T><<<dim3((H + 2 + 15) / 16, 2, B), 256, 0, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(dgrad_s1_edge_cols_mma_kernel<T>, dim3((H + 2 + 15) / 16, 2, B), 256, 0, (cudaStream_t)stream)(
                                         static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W)));
     return check_launch("dgrad_s1_edge_cols_mma_kernel");
   }
@@ -845,13 +865,13 @@ extern "C" int ducosy_conv3x3s1_dgrad_nhwc(const void* dy_pad2, const void* w_dg
     const int per = (H + 2 + cps - 1) / cps, chunks = (H + 2 + per - 1) / per;
     const size_t smem = size_t(per + 2) * 512;
     DUCOSY_CHECK(smem <= 48 * 1024, DUCOSY_ERR_SHAPE, "conv3x3s1_dgrad: H too large for the edge-column kernel");
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols256_kernel<T><<<dim3(Cin / 8, 2, B * chunks), 256, smem, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(dgrad_s1_edge_cols256_kernel<T>, dim3(Cin / 8, 2, B * chunks), 256, smem, (cudaStream_t)stream)(
                                         static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,
                                         Cin, per, chunks)));
     return check_launch("dgrad_s1_edge_cols256_kernel");
   }
   const long long total = (long long)B * (H + 2) * 2 * Cin;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (dgrad_s1_edge_cols_kernel<T><<<grid_for_items(total, 128), 128, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(dgrad_s1_edge_cols_kernel<T>, grid_for_items(total, 128), 128, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(dy_pad2), static_cast<const T*>(w_dgrad), static_cast<T*>(dxpad), B, H, W,
                                       Cin, Cout)));
   return check_launch("dgrad_s1_edge_cols_kernel");
@@ -862,7 +882,7 @@ extern "C" int ducosy_pad_fold_add(const void* dxpad, const void* add, void* dx,
                                    int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(dxpad && dx && B > 0 && C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_ARG, "pad_fold: bad argument");
   const long long total = (long long)B * H * W * (C / 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pad_fold_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pad_fold_kernel<T>, grid_for_items(total, 256), 256, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(dxpad), static_cast<const T*>(add), static_cast<T*>(dx), B, H, W, C, pad,
                                       pad_mode)));
   return check_launch("pad_fold_kernel");
@@ -874,8 +894,8 @@ extern "C" int ducosy_pad_fold(const void* dxpad, void* dx, int B, int H, int W,
 
 extern "C" int ducosy_pack_upconv_dgrad_weight(const float* w_oihw, void* packed, int Cout, int Cin, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(w_oihw && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_dgrad_weight: bad argument");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_dgrad_weight_kernel<T><<<grid_for_items(16LL * Cout * Cin, 256), 256, 0,
-                                                                       (cudaStream_t)stream>>>(w_oihw, static_cast<T*>(packed), Cout, Cin)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_upconv_dgrad_weight_kernel<T>, grid_for_items(16LL * Cout * Cin, 256), 256, 0,
+                                                                       (cudaStream_t)stream)(w_oihw, static_cast<T*>(packed), Cout, Cin)));
   return check_launch("pack_upconv_dgrad_weight_kernel");
 }
 
@@ -904,7 +924,7 @@ extern "C" int ducosy_upconv2x_dgrad_nhwc(const void* dy_pad2, const void* w_dgr
 extern "C" int ducosy_upsample2x_pad(const void* src_pad, void* up_pad, int B, int Hs, int Ws, int C, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(src_pad && up_pad && B > 0 && C % 8 == 0, DUCOSY_ERR_ARG, "upsample2x_pad: bad argument");
   const long long total = (long long)B * (2 * Hs + 2) * (2 * Ws + 2) * (C / 8);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (upsample2x_pad_kernel<T><<<grid_for_items(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(upsample2x_pad_kernel<T>, grid_for_items(total, 256), 256, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(src_pad), static_cast<T*>(up_pad), B, Hs, Ws, C)));
   return check_launch("upsample2x_pad_kernel");
 }

@@ -69,6 +69,7 @@ __device__ __forceinline__ void store_packed(T* __restrict__ out, long long i, l
 template <typename T>
 __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int kh,
                                         int kw, int planes) {
+  pdl_prologue();
   const long long total = (long long)Cout * Cin * kh * kw;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -84,6 +85,7 @@ __global__ void pack_conv_weight_kernel(const float* __restrict__ w, T* __restri
 // rows: phase 0 -> [w0, w1+w2], phase 1 -> [w0+w1, w2]; same for columns.  Sums are formed in fp32.
 template <typename T>
 __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin, int planes) {
+  pdl_prologue();
   const long long total = 4LL * Cout * 4 * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -112,6 +114,7 @@ __global__ void pack_upconv_weight_kernel(const float* __restrict__ w, T* __rest
 // four 2x2 convs, but A tiles are loaded once for all phases and the tile is N = 256 wide.
 template <typename T>
 __global__ void pack_upconv_merged_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cout, int Cin) {
+  pdl_prologue();
   const long long total = 4LL * Cout * 9 * Cin;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -138,6 +141,7 @@ __global__ void pack_upconv_merged_weight_kernel(const float* __restrict__ w, T*
 
 template <typename T>
 __global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int Cin, int Kpad, int planes) {
+  pdl_prologue();
   const int total = 64 * Kpad;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
     const int k = i % Kpad, o = i / Kpad;
@@ -150,6 +154,7 @@ __global__ void pack_stem_weight_kernel(const float* __restrict__ w, T* __restri
 // One thread builds 8 consecutive k (one 16-byte store); consecutive threads -> consecutive chunks of a row.
 template <typename T, typename In, bool kSplit>
 __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int H, int W, int Kpad) {
+  pdl_prologue();
   const int chunks = Kpad / 8;
   const long long total = (long long)B * H * W * chunks;
   const int K = 49 * Cin;
@@ -189,6 +194,7 @@ __global__ void stem_im2col_kernel(In in, T* __restrict__ A, int B, int Cin, int
 template <typename T, typename In, int CIN>
 __global__ void __launch_bounds__(256)
 stem_im2col_rows_kernel(In in, T* __restrict__ A, int H, int W) {
+  pdl_prologue();
   constexpr int KPAD = (49 * CIN + 63) / 64 * 64;
   extern __shared__ __align__(16) uint8_t im2col_smem[];
   T* tile = reinterpret_cast<T*>(im2col_smem);  // [CIN][7][W + 6]
@@ -224,15 +230,15 @@ int launch_im2col(In in, T* A, int B, int Cin, int H, int W, bool split, cudaStr
   if (split) {
     const int Kpad = (49 * Cin + 63) / 64 * 64;
     const long long total = (long long)B * H * W * (Kpad / 8);
-    stem_im2col_kernel<T, In, true><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
+    pdl(stem_im2col_kernel<T, In, true>, ew_grid(total, 256), 256, 0, st)(in, A, B, Cin, H, W, Kpad);
   } else if (Cin <= 3 && smem <= 48 * 1024) {
-    if (Cin == 1) stem_im2col_rows_kernel<T, In, 1><<<grid, 256, smem, st>>>(in, A, H, W);
-    else if (Cin == 2) stem_im2col_rows_kernel<T, In, 2><<<grid, 256, smem, st>>>(in, A, H, W);
-    else stem_im2col_rows_kernel<T, In, 3><<<grid, 256, smem, st>>>(in, A, H, W);
+    if (Cin == 1) pdl(stem_im2col_rows_kernel<T, In, 1>, grid, 256, smem, st)(in, A, H, W);
+    else if (Cin == 2) pdl(stem_im2col_rows_kernel<T, In, 2>, grid, 256, smem, st)(in, A, H, W);
+    else pdl(stem_im2col_rows_kernel<T, In, 3>, grid, 256, smem, st)(in, A, H, W);
   } else {
     const int Kpad = (49 * Cin + 63) / 64 * 64;
     const long long total = (long long)B * H * W * (Kpad / 8);
-    stem_im2col_kernel<T, In, false><<<ew_grid(total, 256), 256, 0, st>>>(in, A, B, Cin, H, W, Kpad);
+    pdl(stem_im2col_kernel<T, In, false>, ew_grid(total, 256), 256, 0, st)(in, A, B, Cin, H, W, Kpad);
   }
   return check_launch("stem_im2col_kernel");
 }
@@ -245,6 +251,7 @@ constexpr int kFinWarps = 32;
 __global__ void __launch_bounds__(kFinWarps * 32)
 in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, float* __restrict__ scale,
                    float* __restrict__ shift, float* __restrict__ chmax, int C) {
+  pdl_prologue();
   __shared__ double s1s[kFinWarps][32], s2s[kFinWarps][32];
   __shared__ float mxs[kFinWarps][32];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -297,6 +304,7 @@ in_finalize_kernel(const float* __restrict__ partials, int tiles, int npix, floa
 __global__ void __launch_bounds__(256)
 cbam_channel_mlp_kernel(const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
                         float* __restrict__ scale, float* __restrict__ shift, int C) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [C] normalised max, [C/16] hidden
   float* smax = sm;
   float* hidden = sm + C;
@@ -368,6 +376,7 @@ template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     T* __restrict__ out, int B, int H, int W, int C, int pad, int pad_mode, int act) {
+  pdl_prologue();
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8, cvp = kSplit ? 2 * cv : cv;
   const int c8 = threadIdx.x % cv, row_chunks = Wp * cvp;
   const int px0 = threadIdx.x / cv, px_step = 256 / cv;
@@ -427,6 +436,7 @@ template <typename T, bool kSplit>
 __global__ void __launch_bounds__(256)
 cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                  float2* __restrict__ pooled, int HW) {
+  pdl_prologue();
   constexpr int C = 256;
   const int lane = threadIdx.x & 31, seg = lane & 7, sub = lane >> 3;
   const int b = blockIdx.y;
@@ -480,6 +490,7 @@ cbam_pool_kernel(const T* __restrict__ y, const float* __restrict__ scale, const
 // sa[b][y][x] = sigmoid( sum_{ch,r,s} w[ch][r][s] * pooled[b][y+r-3][x+s-3][ch] ), zero padding
 __global__ void cbam_spatial_conv_kernel(const float2* __restrict__ pooled, const float* __restrict__ w,
                                          float* __restrict__ sa, int B, int H, int W) {
+  pdl_prologue();
   __shared__ float sw[98];
   for (int i = threadIdx.x; i < 98; i += blockDim.x) sw[i] = w[i];
   __syncthreads();
@@ -515,6 +526,7 @@ residual_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ sca
                           const float* __restrict__ sa, const float2* __restrict__ pooled, const float* __restrict__ w_sa,
                           const T* __restrict__ res_pad, int res_pw, T* __restrict__ out,
                           int B, int H, int W, int C, int pad, int pad_mode) {
+  pdl_prologue();
   // pooled != nullptr: the 7x7 spatial-attention conv + sigmoid (modules/model.py:36-38) is evaluated here, one source row at
   // a time into shared memory, instead of by a kernel of its own (98 MACs per pixel against 3 x 512 bytes moved per pixel)
   extern __shared__ float sa_smem[];   // [98] weights, [W] attention of the current source row
@@ -641,7 +653,7 @@ extern "C" int ducosy_pack_conv_weight(const float* w, void* packed, int Cout, i
                                        ducosy_stream_t stream) {
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0 && kh > 0 && kw > 0, DUCOSY_ERR_ARG, "pack_conv_weight: bad argument");
   const long long total = (long long)Cout * Cin * kh * kw;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_conv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_conv_weight_kernel<T>, ew_grid(total, 256), 256, 0, (cudaStream_t)stream)(
                                       w, static_cast<T*>(packed), Cout, Cin, kh, kw, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_conv_weight_kernel");
 }
@@ -650,7 +662,7 @@ extern "C" int ducosy_pack_upconv_weight(const float* w, void* packed, int Cout,
                                          ducosy_stream_t stream) {
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_weight: bad argument");
   const long long total = 16LL * Cout * Cin;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_upconv_weight_kernel<T>, ew_grid(total, 256), 256, 0, (cudaStream_t)stream)(
                                       w, static_cast<T*>(packed), Cout, Cin, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_upconv_weight_kernel");
 }
@@ -660,7 +672,7 @@ extern "C" int ducosy_pack_upconv_merged_weight(const float* w, void* packed, in
   DUCOSY_CHECK(w && packed && Cout > 0 && Cin > 0, DUCOSY_ERR_ARG, "pack_upconv_merged_weight: bad argument");
   DUCOSY_CHECK(dtype != DUCOSY_F16X2, DUCOSY_ERR_ARG, "pack_upconv_merged_weight: not available in split-operand mode");
   const long long total = 36LL * Cout * Cin;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_upconv_merged_weight_kernel<T><<<ew_grid(total, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_upconv_merged_weight_kernel<T>, ew_grid(total, 256), 256, 0, (cudaStream_t)stream)(
                                       w, static_cast<T*>(packed), Cout, Cin)));
   return check_launch("pack_upconv_merged_weight_kernel");
 }
@@ -668,7 +680,7 @@ extern "C" int ducosy_pack_upconv_merged_weight(const float* w, void* packed, in
 extern "C" int ducosy_pack_stem_weight(const float* w, void* packed, int Cin, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(w && packed && Cin > 0, DUCOSY_ERR_ARG, "pack_stem_weight: bad argument");
   const int Kpad = (49 * Cin + 63) / 64 * 64;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pack_stem_weight_kernel<T><<<ew_grid(64 * Kpad, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pack_stem_weight_kernel<T>, ew_grid(64 * Kpad, 256), 256, 0, (cudaStream_t)stream)(
                                       w, static_cast<T*>(packed), Cin, Kpad, dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_stem_weight_kernel");
 }
@@ -697,12 +709,12 @@ extern "C" int ducosy_in_finalize(const float* partials, int tiles_per_sample, i
   DUCOSY_CHECK((fc0 == nullptr) == (fc2 == nullptr), DUCOSY_ERR_ARG, "in_finalize: fc0 and fc2 go together");
   DUCOSY_CHECK(fc0 == nullptr || chmax != nullptr, DUCOSY_ERR_ARG, "in_finalize: CBAM needs the chmax scratch [B][C]");
   DUCOSY_CHECK(C % 32 == 0, DUCOSY_ERR_SHAPE, "in_finalize: C %% 32 != 0");
-  in_finalize_kernel<<<dim3(C / 32, B), kFinWarps * 32, 0, (cudaStream_t)stream>>>(partials, tiles_per_sample, npix_per_sample,
+  pdl(in_finalize_kernel, dim3(C / 32, B), kFinWarps * 32, 0, (cudaStream_t)stream)(partials, tiles_per_sample, npix_per_sample,
                                                                         scale, shift, chmax, C);
   DUCOSY_TRY(check_launch("in_finalize_kernel"));
   if (fc0 != nullptr) {
     const size_t smem = sizeof(float) * (C + C / 16 + 1);
-    cbam_channel_mlp_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(chmax, fc0, fc2, scale, shift, C);
+    pdl(cbam_channel_mlp_kernel, B, 256, smem, (cudaStream_t)stream)(chmax, fc0, fc2, scale, shift, C);
     return check_launch("cbam_channel_mlp_kernel");
   }
   return 0;
@@ -715,10 +727,10 @@ extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const floa
   DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "in_apply_pad: C must be one of 8..2048 with C/8 dividing 256");
   if (dtype == DUCOSY_F16X2)
-    in_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+    pdl(in_apply_pad_kernel<__half, true>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
         static_cast<const __half*>(y), scale, shift, static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode, act);
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (in_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_apply_pad_kernel<T, false>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
                                         static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
                                         pad_mode, act)));
   return check_launch("in_apply_pad_kernel");
@@ -734,10 +746,10 @@ extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* 
   const int cap = (num_sms() > 0 ? num_sms() : 148) * 8 / (B > 0 ? B : 1) + 1;
   if (gx > cap) gx = cap;
   if (dtype == DUCOSY_F16X2)
-    cbam_pool_kernel<__half, true><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(static_cast<const __half*>(y), scale, shift,
+    pdl(cbam_pool_kernel<__half, true>, dim3(gx, B), 256, 0, (cudaStream_t)stream)(static_cast<const __half*>(y), scale, shift,
                                                                                    reinterpret_cast<float2*>(pooled), H * W);
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_pool_kernel<T, false><<<dim3(gx, B), 256, 0, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(cbam_pool_kernel<T, false>, dim3(gx, B), 256, 0, (cudaStream_t)stream)(
                                         static_cast<const T*>(y), scale, shift, reinterpret_cast<float2*>(pooled), H * W)));
   return check_launch("cbam_pool_kernel");
 }
@@ -745,7 +757,7 @@ extern "C" int ducosy_cbam_pool(const void* y, const float* scale, const float* 
 extern "C" int ducosy_cbam_spatial_conv(const float* pooled, const float* w_sa, float* sa, int B, int H, int W,
                                         ducosy_stream_t stream) {
   DUCOSY_CHECK(pooled && w_sa && sa && B > 0, DUCOSY_ERR_ARG, "cbam_spatial_conv: bad argument");
-  cbam_spatial_conv_kernel<<<ew_grid((long long)B * H * W, 128), 128, 0, (cudaStream_t)stream>>>(
+  pdl(cbam_spatial_conv_kernel, ew_grid((long long)B * H * W, 128), 128, 0, (cudaStream_t)stream)(
       reinterpret_cast<const float2*>(pooled), w_sa, sa, B, H, W);
   return check_launch("cbam_spatial_conv_kernel");
 }
@@ -759,11 +771,11 @@ extern "C" int ducosy_residual_apply_pad(const void* y, const float* scale, cons
   DUCOSY_CHECK(res_pad != out_pad, DUCOSY_ERR_ARG, "residual_apply_pad: in-place is not supported");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_apply_pad: C/8 must divide 256");
   if (dtype == DUCOSY_F16X2)
-    residual_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+    pdl(residual_apply_pad_kernel<__half, true>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
         static_cast<const __half*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const __half*>(res_pad), res_pad_width,
         static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode);
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(residual_apply_pad_kernel<T, false>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
                                         static_cast<const T*>(y), scale, shift, sa, nullptr, nullptr, static_cast<const T*>(res_pad),
                                         res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");
@@ -782,11 +794,11 @@ extern "C" int ducosy_residual_cbam_apply_pad(const void* y, const float* scale,
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "residual_cbam_apply_pad: C/8 must divide 256");
   const size_t smem = (98 + size_t(W)) * sizeof(float);
   if (dtype == DUCOSY_F16X2)
-    residual_apply_pad_kernel<__half, true><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
+    pdl(residual_apply_pad_kernel<__half, true>, row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream)(
         static_cast<const __half*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
         static_cast<const __half*>(res_pad), res_pad_width, static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode);
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (residual_apply_pad_kernel<T, false><<<row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(residual_apply_pad_kernel<T, false>, row_grid(B * (H + 2 * pad)), 256, smem, (cudaStream_t)stream)(
                                         static_cast<const T*>(y), scale, shift, nullptr, reinterpret_cast<const float2*>(pooled), w_sa,
                                         static_cast<const T*>(res_pad), res_pad_width, static_cast<T*>(out_pad), B, H, W, C, pad, pad_mode)));
   return check_launch("residual_apply_pad_kernel");

@@ -28,6 +28,7 @@ __device__ __forceinline__ int reflect_sources(int i, int n, int pad, int* u) {
 __global__ void __launch_bounds__(256)
 out_tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dv,
                     float* __restrict__ partial, long long n) {
+  pdl_prologue();
   __shared__ float red[8];
   float acc = 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -47,6 +48,7 @@ out_tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ ou
 }
 
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int n, float* __restrict__ out) {
+  pdl_prologue();
   __shared__ float red[32];
   float acc = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
@@ -69,6 +71,7 @@ template <typename T>
 __global__ void __launch_bounds__(256)
 out_conv_dgrad_kernel(const float* __restrict__ dv, const float* __restrict__ w, T* __restrict__ da,
                       const float* __restrict__ gs, int B, int H, int W) {
+  pdl_prologue();
   __shared__ __align__(16) float ws[49][64];
   for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i % 49][i / 49] = w[i];   // w is [c][tap]
   __syncthreads();
@@ -157,6 +160,7 @@ constexpr int kOutWgradThreads = 448;
 template <typename T>
 __global__ void __launch_bounds__(kOutWgradThreads)
 out_conv_wgrad_kernel(const T* __restrict__ in_pad, const float* __restrict__ dv, float* __restrict__ partial, int B, int H, int W) {
+  pdl_prologue();
   extern __shared__ float rows[];                 // [7][W + 12], rows[r][j] = dv[u - r][j - 6]
   const int Wp = W + 6, Hp = H + 6, pitch = W + 12;
   const int c = threadIdx.x & 63, r = threadIdx.x >> 6;
@@ -192,6 +196,7 @@ out_conv_wgrad_kernel(const T* __restrict__ in_pad, const float* __restrict__ dv
 }
 
 __global__ void out_conv_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 49) return;
   float s = 0.f;
@@ -205,6 +210,7 @@ __global__ void out_conv_wgrad_reduce_kernel(const float* __restrict__ partial, 
 template <typename T>
 __global__ void __launch_bounds__(256)
 stem_col2im_kernel(const T* __restrict__ dcol, float* __restrict__ dx, const float* __restrict__ gs, int B, int H, int W) {
+  pdl_prologue();
   const long long pix = (long long)blockIdx.x * 256 + threadIdx.x;
   if (pix >= (long long)B * H * W) return;
   const int x = int(pix % W), y = int((pix / W) % H), b = int(pix / ((long long)W * H));
@@ -233,6 +239,7 @@ stem_col2im_kernel(const T* __restrict__ dcol, float* __restrict__ dx, const flo
 // packed stem weight gradient [64][Kpad] (k = c*49 + r*7 + s, the im2col column order) -> OIHW [64][Cin][7][7], true scale
 __global__ void unpack_stem_wgrad_kernel(const float* __restrict__ packed, float* __restrict__ g, int Cin, int Kpad,
                                          const float* __restrict__ gs) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   const int K = Cin * 49;
   if (i >= 64 * K) return;
@@ -280,6 +287,7 @@ __global__ void __launch_bounds__(256)
 cbam_channel_train_kernel(const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
                           const float* __restrict__ scale_n, const float* __restrict__ shift_n, float* __restrict__ scale_v,
                           float* __restrict__ shift_v, float* __restrict__ ca, float* __restrict__ hidden, int C) {
+  pdl_prologue();
   extern __shared__ float sm[];  // [C] max, [C/16] hidden
   float* smax = sm;
   float* hid = sm + C;
@@ -314,6 +322,7 @@ __global__ void __launch_bounds__(256)
 cbam_bwd_dz_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const float* __restrict__ scale_v,
                    const float* __restrict__ shift_v, const float* __restrict__ sa, float* __restrict__ dz,
                    float* __restrict__ pmax_val, int* __restrict__ pmax_idx, int HW) {
+  pdl_prologue();
   __shared__ float sval[8][kCbamC];
   __shared__ int sidx[8][kCbamC];
   const int b = blockIdx.y, blk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
@@ -361,6 +370,7 @@ cbam_bwd_dz_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const f
 __global__ void __launch_bounds__(256)
 cbam_argmax_finalize_kernel(const float* __restrict__ pmax_val, const int* __restrict__ pmax_idx, int nblk,
                             int* __restrict__ amax_pix) {
+  pdl_prologue();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int c = blockIdx.x * 8 + warp, b = blockIdx.y;
   float bv = -INFINITY;
@@ -383,6 +393,7 @@ cbam_argmax_finalize_kernel(const float* __restrict__ pmax_val, const int* __res
 __global__ void __launch_bounds__(256)
 cbam_sa_bwd_kernel(const float* __restrict__ dz, const float* __restrict__ pooled, const float* __restrict__ wsa,
                    float* __restrict__ dpooled, float* __restrict__ pdw, int B, int H, int W) {
+  pdl_prologue();
   __shared__ float ws[98];
   __shared__ float red[8][98];
   if (threadIdx.x < 98) ws[threadIdx.x] = wsa[threadIdx.x];
@@ -433,6 +444,7 @@ __global__ void __launch_bounds__(256)
 cbam_bwd_dv_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const float* __restrict__ scale_n,
                    const float* __restrict__ shift_n, const float* __restrict__ ca, const float* __restrict__ sa,
                    const float* __restrict__ dpooled, T* __restrict__ dn, float* __restrict__ pdca, int HW) {
+  pdl_prologue();
   __shared__ float sacc[8][kCbamC];
   const int b = blockIdx.y, blk = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c0 = lane * 8;
   float sn[8], hn[8], cav[8], accd[8];
@@ -488,6 +500,7 @@ cbam_channel_bwd_kernel(const float* __restrict__ pdca, int nblk, const float* _
                         const float* __restrict__ chmax, const float* __restrict__ fc0, const float* __restrict__ fc2,
                         const int* __restrict__ amax_pix, T* __restrict__ dn, float* __restrict__ pfc0,
                         float* __restrict__ pfc2, int HW) {
+  pdl_prologue();
   constexpr int Hd = kCbamC / 16;
   __shared__ float ds[kCbamC], h[Hd], dh[Hd];
   const int b = blockIdx.x, c = threadIdx.x;
@@ -527,6 +540,7 @@ cbam_channel_bwd_kernel(const float* __restrict__ pdca, int nblk, const float* _
 
 __global__ void cbam_param_reduce_kernel(const float* __restrict__ partial, int parts, int n, float* __restrict__ out,
                                          const float* __restrict__ gs) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   float a = 0.f;
@@ -539,6 +553,7 @@ __global__ void cbam_param_reduce_kernel(const float* __restrict__ partial, int 
 __global__ void __launch_bounds__(256)
 adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                  float b1, float b2, float eps, float step_size, float inv_sqrt_bc2) {
+  pdl_prologue();
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float gi = g[i];
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -551,10 +566,12 @@ adam_step_kernel(float* __restrict__ p, const float* __restrict__ g, float* __re
 
 // Same update with the learning rate and the step count read from device memory (state = {lr, step}), so that a whole
 // optimisation step can live in a CUDA graph: nothing that changes between replays is baked into the launch.
-__global__ void adam_advance_kernel(float* __restrict__ state) { state[1] += 1.f; }
+__global__ void adam_advance_kernel(float* __restrict__ state) {
+  pdl_prologue(); state[1] += 1.f; }
 __global__ void __launch_bounds__(256)
 adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n,
                      float b1, float b2, float eps, const float* __restrict__ state) {
+  pdl_prologue();
   __shared__ float s_step_size, s_inv_sqrt_bc2;
   if (threadIdx.x == 0) {
     const double t = double(state[1]);
@@ -578,6 +595,7 @@ adam_step_dev_kernel(float* __restrict__ p, const float* __restrict__ g, float* 
 template <typename T>
 __global__ void __launch_bounds__(256)
 add_inplace_kernel(T* __restrict__ a, const T* __restrict__ b, long long n8) {
+  pdl_prologue();
   const long long i = (long long)blockIdx.x * 256 + threadIdx.x;
   if (i >= n8) return;
   const uint4 va = reinterpret_cast<const uint4*>(a)[i], vb = reinterpret_cast<const uint4*>(b)[i];
@@ -598,7 +616,7 @@ using namespace ducosy;
 
 extern "C" int ducosy_add_inplace(void* a, const void* b, long long n, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(a && b && n > 0 && n % 8 == 0, DUCOSY_ERR_ARG, "add_inplace: needs non-null pointers and n %% 8 == 0");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (add_inplace_kernel<T><<<grid_items(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(add_inplace_kernel<T>, grid_items(n / 8, 256), 256, 0, (cudaStream_t)stream)(
                                       static_cast<T*>(a), static_cast<const T*>(b), n / 8)));
   return check_launch("add_inplace_kernel");
 }
@@ -624,32 +642,32 @@ extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, con
   float* dv = scratch;
   float* tpart = dv + n;
   float* wpart = tpart + kTanhBlocks;
-  out_tanh_bwd_kernel<<<kTanhBlocks, 256, 0, st>>>(dout, out, dv, tpart, n);
+  pdl(out_tanh_bwd_kernel, kTanhBlocks, 256, 0, st)(dout, out, dv, tpart, n);
   DUCOSY_TRY(check_launch("out_tanh_bwd_kernel"));
-  sum_partials_kernel<<<1, 256, 0, st>>>(tpart, kTanhBlocks, db);
+  pdl(sum_partials_kernel, 1, 256, 0, st)(tpart, kTanhBlocks, db);
   DUCOSY_TRY(check_launch("sum_partials_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_dgrad_kernel<T><<<grid_items(n * 2, 256), 256, 0, st>>>(dv, w, static_cast<T*>(da), gs, B, H, W)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_dgrad_kernel<T>, grid_items(n * 2, 256), 256, 0, st)(dv, w, static_cast<T*>(da), gs, B, H, W)));
   DUCOSY_TRY(check_launch("out_conv_dgrad_kernel"));
   const int blocks = min(kOutWgradBlocks, B * (H + 6));
   const size_t smem = size_t(7) * (W + 12) * sizeof(float);
   DUCOSY_CHECK(smem <= 48 * 1024, DUCOSY_ERR_SHAPE, "out_conv_backward: W too large (%d)", W);
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv_wgrad_kernel<T><<<blocks, kOutWgradThreads, smem, st>>>(static_cast<const T*>(in_pad), dv, wpart, B, H, W)));
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_wgrad_kernel<T>, blocks, kOutWgradThreads, smem, st)(static_cast<const T*>(in_pad), dv, wpart, B, H, W)));
   DUCOSY_TRY(check_launch("out_conv_wgrad_kernel"));
-  out_conv_wgrad_reduce_kernel<<<(64 * 49 + 255) / 256, 256, 0, st>>>(wpart, blocks, dw);
+  pdl(out_conv_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st)(wpart, blocks, dw);
   return check_launch("out_conv_wgrad_reduce_kernel");
 }
 
 extern "C" int ducosy_stem_col2im(const void* dcol, float* dx, const float* gs, int B, int H, int W, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(dcol && dx && gs && B > 0 && H >= 8 && W >= 8, DUCOSY_ERR_ARG, "stem_col2im: bad argument");
   const long long n = (long long)B * H * W;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (stem_col2im_kernel<T><<<grid_items(n, 256), 256, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(stem_col2im_kernel<T>, grid_items(n, 256), 256, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(dcol), dx, gs, B, H, W)));
   return check_launch("stem_col2im_kernel");
 }
 
 extern "C" int ducosy_unpack_stem_wgrad(const float* packed, float* g_oihw, int Cin, int Kpad, const float* gs, ducosy_stream_t stream) {
   DUCOSY_CHECK(packed && g_oihw && gs && Cin >= 1 && Kpad >= Cin * 49, DUCOSY_ERR_ARG, "unpack_stem_wgrad: bad argument");
-  unpack_stem_wgrad_kernel<<<grid_items(64LL * Cin * 49, 256), 256, 0, (cudaStream_t)stream>>>(packed, g_oihw, Cin, Kpad, gs);
+  pdl(unpack_stem_wgrad_kernel, grid_items(64LL * Cin * 49, 256), 256, 0, (cudaStream_t)stream)(packed, g_oihw, Cin, Kpad, gs);
   return check_launch("unpack_stem_wgrad_kernel");
 }
 
@@ -660,7 +678,7 @@ extern "C" int ducosy_cbam_channel_train(const float* chmax, const float* fc0, c
                "cbam_channel_train: null pointer");
   DUCOSY_CHECK(B > 0 && C % 32 == 0, DUCOSY_ERR_SHAPE, "cbam_channel_train: C %% 32 != 0");
   const size_t smem = size_t(C + C / 16) * sizeof(float);
-  cbam_channel_train_kernel<<<B, 256, smem, (cudaStream_t)stream>>>(chmax, fc0, fc2, scale_n, shift_n, scale_v, shift_v, ca, hidden, C);
+  pdl(cbam_channel_train_kernel, B, 256, smem, (cudaStream_t)stream)(chmax, fc0, fc2, scale_n, shift_n, scale_v, shift_v, ca, hidden, C);
   return check_launch("cbam_channel_train_kernel");
 }
 
@@ -695,25 +713,25 @@ extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const floa
   float* pdw = reinterpret_cast<float*>(amax_pix + size_t(B) * C);
   float* pfc0 = pdw + size_t(sablk) * 98;
   float* pfc2 = pfc0 + size_t(B) * C * Hd;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_bwd_dz_kernel<T><<<dim3(nblk, B), 256, 0, st>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(cbam_bwd_dz_kernel<T>, dim3(nblk, B), 256, 0, st)(
                                       static_cast<const T*>(dout), static_cast<const T*>(yb), scale_v, shift_v, sa, dz, pmax_val,
                                       pmax_idx, HW)));
   DUCOSY_TRY(check_launch("cbam_bwd_dz_kernel"));
-  cbam_argmax_finalize_kernel<<<dim3(kCbamC / 8, B), 256, 0, st>>>(pmax_val, pmax_idx, nblk, amax_pix);
+  pdl(cbam_argmax_finalize_kernel, dim3(kCbamC / 8, B), 256, 0, st)(pmax_val, pmax_idx, nblk, amax_pix);
   DUCOSY_TRY(check_launch("cbam_argmax_finalize_kernel"));
-  cbam_sa_bwd_kernel<<<sablk, 256, 0, st>>>(dz, pooled, wsa, dpooled, pdw, B, H, W);
+  pdl(cbam_sa_bwd_kernel, sablk, 256, 0, st)(dz, pooled, wsa, dpooled, pdw, B, H, W);
   DUCOSY_TRY(check_launch("cbam_sa_bwd_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_bwd_dv_kernel<T><<<dim3(nblk, B), 256, 0, st>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(cbam_bwd_dv_kernel<T>, dim3(nblk, B), 256, 0, st)(
                                       static_cast<const T*>(dout), static_cast<const T*>(yb), scale_n, shift_n, ca, sa, dpooled,
                                       static_cast<T*>(dn), pdca, HW)));
   DUCOSY_TRY(check_launch("cbam_bwd_dv_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (cbam_channel_bwd_kernel<T><<<B, kCbamC, 0, st>>>(pdca, nblk, ca, hidden, chmax, fc0, fc2, amax_pix,
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(cbam_channel_bwd_kernel<T>, B, kCbamC, 0, st)(pdca, nblk, ca, hidden, chmax, fc0, fc2, amax_pix,
                                                                                   static_cast<T*>(dn), pfc0, pfc2, HW)));
   DUCOSY_TRY(check_launch("cbam_channel_bwd_kernel"));
   const int nfc = C * Hd;
-  cbam_param_reduce_kernel<<<(nfc + 255) / 256, 256, 0, st>>>(pfc0, B, nfc, dfc0, gs);
-  cbam_param_reduce_kernel<<<(nfc + 255) / 256, 256, 0, st>>>(pfc2, B, nfc, dfc2, gs);
-  cbam_param_reduce_kernel<<<1, 128, 0, st>>>(pdw, sablk, 98, dwsa, gs);
+  pdl(cbam_param_reduce_kernel, (nfc + 255) / 256, 256, 0, st)(pfc0, B, nfc, dfc0, gs);
+  pdl(cbam_param_reduce_kernel, (nfc + 255) / 256, 256, 0, st)(pfc2, B, nfc, dfc2, gs);
+  pdl(cbam_param_reduce_kernel, 1, 128, 0, st)(pdw, sablk, 98, dwsa, gs);
   return check_launch("cbam_param_reduce_kernel");
 }
 
@@ -722,14 +740,14 @@ extern "C" int ducosy_adam_step(float* param, const float* grad, float* exp_avg,
   DUCOSY_CHECK(param && grad && exp_avg && exp_avg_sq && n > 0 && step >= 1, DUCOSY_ERR_ARG, "adam_step: bad argument");
   const double bc1 = 1.0 - pow(double(beta1), step), bc2 = 1.0 - pow(double(beta2), step);
   const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
-  adam_step_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
+  pdl(adam_step_kernel, blocks, 256, 0, (cudaStream_t)stream)(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps,
                                                             float(double(lr) / bc1), float(1.0 / sqrt(bc2)));
   return check_launch("adam_step_kernel");
 }
 
 extern "C" int ducosy_adam_advance(float* state, ducosy_stream_t stream) {
   DUCOSY_CHECK(state != nullptr, DUCOSY_ERR_ARG, "adam_advance: null pointer");
-  adam_advance_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(state);
+  pdl(adam_advance_kernel, 1, 1, 0, (cudaStream_t)stream)(state);
   return check_launch("adam_advance_kernel");
 }
 
@@ -737,6 +755,6 @@ extern "C" int ducosy_adam_step_dev(float* param, const float* grad, float* exp_
                                     const float* state, float beta1, float beta2, float eps, ducosy_stream_t stream) {
   DUCOSY_CHECK(param && grad && exp_avg && exp_avg_sq && state && n > 0, DUCOSY_ERR_ARG, "adam_step_dev: bad argument");
   const int blocks = int(std::min<long long>((n + 255) / 256, 148 * 8));
-  adam_step_dev_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, state);
+  pdl(adam_step_dev_kernel, blocks, 256, 0, (cudaStream_t)stream)(param, grad, exp_avg, exp_avg_sq, n, beta1, beta2, eps, state);
   return check_launch("adam_step_dev_kernel");
 }

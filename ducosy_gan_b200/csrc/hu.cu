@@ -29,6 +29,7 @@ struct alignas(8) U8x8 { uint8_t v[8]; };
 __global__ void hu_window_kernel(const int16_t* __restrict__ px, float* __restrict__ out_soft,
                                  float* __restrict__ out_lung, long long n, float slope, float intercept, float slo,
                                  float shi, float sspan, float llo, float lhi, float lspan) {
+  pdl_prologue();
   const long long groups = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
@@ -62,6 +63,7 @@ __global__ void hu_window_kernel(const int16_t* __restrict__ px, float* __restri
 __global__ void hu_thresholds_kernel(const int16_t* __restrict__ px, uint8_t* __restrict__ body,
                                      uint8_t* __restrict__ lung, uint8_t* __restrict__ bone, long long n, float slope,
                                      float intercept) {
+  pdl_prologue();
   const long long groups = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
@@ -114,6 +116,7 @@ __global__ void dewindow_composite_kernel(const int16_t* __restrict__ raw, const
                                           int16_t* __restrict__ soft_px, int16_t* __restrict__ lung_px,
                                           uint8_t* __restrict__ masks, long long n, float slope, float intercept,
                                           float slo, float shi, float sspan, float llo, float lhi, float lspan) {
+  pdl_prologue();
   const long long groups = n >> 3;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long g = (long long)blockIdx.x * blockDim.x + threadIdx.x; g < groups; g += stride) {
@@ -149,6 +152,7 @@ __global__ void dewindow_composite_kernel(const int16_t* __restrict__ raw, const
 // training-side windowing with soft squeezing (modules/preprocess.py:6-40,43-55; dataset.py:118-120)
 __global__ void hu_window_soft_kernel(const int16_t* __restrict__ px, float* __restrict__ out, long long n, float slope,
                                       float intercept, float lo, float hi, float span, float k) {
+  pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float hu = stored_to_hu(px[i], slope, intercept);
@@ -162,6 +166,7 @@ __global__ void hu_window_soft_kernel(const int16_t* __restrict__ px, float* __r
 // display windowing of a tanh-range tensor (modules/preprocess.py:58-65)
 __global__ void apply_windowing_kernel(const float* __restrict__ y, float* __restrict__ out, long long n, float lo, float span,
                                        float wlo, float whi, float ww) {
+  pdl_prologue();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
     const float hu = __fadd_rn(__fmul_rn(__fdiv_rn(__fadd_rn(y[i], 1.0f), 2.0f), span), lo);
@@ -193,7 +198,7 @@ extern "C" int ducosy_hu_window(const int16_t* px, float* out_soft, float* out_l
                "hu_window: buffers must be 16-byte aligned");
   if (n == 0) return 0;
   const float sspan = float(double(soft_hi) - double(soft_lo)), lspan = float(double(lung_hi) - double(lung_lo));
-  hu_window_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(hu_window_kernel, grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream))(
       px, out_soft, out_lung, n, slope, intercept, soft_lo, soft_hi, sspan, lung_lo, lung_hi, lspan);
   return check_launch("hu_window_kernel");
 }
@@ -205,7 +210,7 @@ extern "C" int ducosy_hu_thresholds(const int16_t* px, uint8_t* body, uint8_t* l
   DUCOSY_CHECK(aligned16(px) && aligned16(body) && aligned16(lung) && aligned16(bone), DUCOSY_ERR_ALIGN,
                "hu_thresholds: buffers must be 16-byte aligned");
   if (n == 0) return 0;
-  hu_thresholds_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(px, body, lung, bone,
+  pdl(hu_thresholds_kernel, grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream))(px, body, lung, bone,
                                                                                                    n, slope, intercept);
   return check_launch("hu_thresholds_kernel");
 }
@@ -222,7 +227,7 @@ extern "C" int ducosy_dewindow_composite(const int16_t* raw_px, const float* y_s
                DUCOSY_ERR_ALIGN, "dewindow_composite: buffers must be 16-byte aligned");
   if (n == 0) return 0;
   const float sspan = float(double(soft_hi) - double(soft_lo)), lspan = float(double(lung_hi) - double(lung_lo));
-  dewindow_composite_kernel<<<grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(dewindow_composite_kernel, grid_for((n + 7) / 8, 256), 256, 0, static_cast<cudaStream_t>(stream))(
       raw_px, y_soft, y_lung, merged, soft_px, lung_px, masks, n, slope, intercept, soft_lo, soft_hi, sspan, lung_lo,
       lung_hi, lspan);
   return check_launch("dewindow_composite_kernel");
@@ -232,7 +237,7 @@ extern "C" int ducosy_hu_window_soft(const int16_t* px, float* out, long long n,
                                      float hu_hi, float sigma, ducosy_stream_t stream) {
   if (n == 0) return 0;
   DUCOSY_CHECK(px && out && n > 0 && sigma > 0.f, DUCOSY_ERR_ARG, "hu_window_soft: bad argument");
-  hu_window_soft_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(hu_window_soft_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream))(
       px, out, n, slope, intercept, hu_lo, hu_hi, float(double(hu_hi) - double(hu_lo)), float(10.0 / double(sigma)));
   return check_launch("hu_window_soft_kernel");
 }
@@ -242,7 +247,7 @@ extern "C" int ducosy_apply_windowing(const float* y, float* out, long long n, f
   if (n == 0) return 0;
   DUCOSY_CHECK(y && out && n > 0 && window_width != 0.f, DUCOSY_ERR_ARG, "apply_windowing: bad argument");
   const double half = double(window_width) / 2.0;
-  apply_windowing_kernel<<<grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  pdl(apply_windowing_kernel, grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream))(
       y, out, n, hu_lo, float(double(hu_hi) - double(hu_lo)), float(double(window_center) - half),
       float(double(window_center) + half), window_width);
   return check_launch("apply_windowing_kernel");

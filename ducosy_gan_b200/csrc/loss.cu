@@ -44,6 +44,7 @@ __device__ __forceinline__ void block_partials(float (&v)[Q], float* __restrict_
 }
 // sums[q] = sum over blocks (double, fixed order); one block of 32*Q threads
 __global__ void sum_partials_kernel(const float* __restrict__ partial, int blocks, int Q, double* __restrict__ sums) {
+  pdl_prologue();
   const int q = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (q >= Q) return;
   double acc = 0.0;
@@ -55,12 +56,14 @@ __global__ void sum_partials_kernel(const float* __restrict__ partial, int block
 
 // ------------------------------------------------------------------ L1 / L2: mean |a-b|, mean (a-t)^2
 __global__ void l1_fwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, float* __restrict__ partial) {
+  pdl_prologue();
   float v[1] = {0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     v[0] += fabsf(a[i] - b[i]);
   block_partials<1>(v, partial);
 }
 __global__ void mse_const_fwd_kernel(const float* __restrict__ a, float t, long long n, float* __restrict__ partial) {
+  pdl_prologue();
   float v[1] = {0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = a[i] - t;
@@ -68,9 +71,11 @@ __global__ void mse_const_fwd_kernel(const float* __restrict__ a, float t, long 
   }
   block_partials<1>(v, partial);
 }
-__global__ void mean_finish_kernel(const double* __restrict__ sums, double inv_n, float* __restrict__ out) { out[0] = float(sums[0] * inv_n); }
+__global__ void mean_finish_kernel(const double* __restrict__ sums, double inv_n, float* __restrict__ out) {
+  pdl_prologue(); out[0] = float(sums[0] * inv_n); }
 __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restrict__ b, long long n, const float* __restrict__ gout,
                               float inv_n, float* __restrict__ da) {
+  pdl_prologue();
   const float g = gout[0] * inv_n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float d = a[i] - b[i];
@@ -79,6 +84,7 @@ __global__ void l1_bwd_kernel(const float* __restrict__ a, const float* __restri
 }
 __global__ void mse_const_bwd_kernel(const float* __restrict__ a, float t, long long n, const float* __restrict__ gout, float inv_n,
                                      float* __restrict__ da) {
+  pdl_prologue();
   const float g = 2.f * gout[0] * inv_n;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
     da[i] = g * (a[i] - t);
@@ -88,6 +94,7 @@ __global__ void mse_const_bwd_kernel(const float* __restrict__ a, float t, long 
 __device__ __forceinline__ float sgn(float x) { return x > 0.f ? 1.f : (x < 0.f ? -1.f : 0.f); }
 __global__ void gradloss_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, int B, int H, int W,
                                     float* __restrict__ partial) {
+  pdl_prologue();
   float v[2] = {0.f, 0.f};  // sum over vertical pairs, sum over horizontal pairs
   const long long n = (long long)B * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -98,12 +105,14 @@ __global__ void gradloss_fwd_kernel(const float* __restrict__ p, const float* __
   block_partials<2>(v, partial);
 }
 __global__ void gradloss_finish_kernel(const double* __restrict__ sums, double inv_ny, double inv_nx, float* __restrict__ out) {
+  pdl_prologue();
   out[0] = float(sums[1] * inv_nx + sums[0] * inv_ny);
 }
 // pair term f(dp) = | |dp| - |dt| |  ->  df/d(dp) = sgn(|dp|-|dt|) * sgn(dp); p[hi] gets +, p[lo] gets -
 __device__ __forceinline__ float pair_grad(float dp, float dt) { return sgn(fabsf(dp) - fabsf(dt)) * sgn(dp); }
 __global__ void gradloss_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, int B, int H, int W,
                                     const float* __restrict__ gout, float inv_ny, float inv_nx, float* __restrict__ dp) {
+  pdl_prologue();
   const float gy = gout[0] * inv_ny, gx = gout[0] * inv_nx;
   const long long n = (long long)B * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -135,6 +144,7 @@ __device__ __forceinline__ float box7(const float* __restrict__ img, int y, int 
 // forward: partial sums of w*|pb-tb|; also writes the per-pixel upstream map u = w*sgn(pb-tb) for the backward
 __global__ void attn_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ s, int B, int H,
                                 int W, float inv_sigma, float wmin, float wmax, float* __restrict__ umap, float* __restrict__ partial) {
+  pdl_prologue();
   float v[1] = {0.f};
   const long long n = (long long)B * H * W, hw = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -150,6 +160,7 @@ __global__ void attn_fwd_kernel(const float* __restrict__ p, const float* __rest
 // dp = gout/N * box7^T(u) ; the zero-padded 7x7 mean filter is self-adjoint
 __global__ void attn_bwd_kernel(const float* __restrict__ umap, int B, int H, int W, const float* __restrict__ gout, float inv_n,
                                 float* __restrict__ dp) {
+  pdl_prologue();
   const float g = gout[0] * inv_n;
   const long long n = (long long)B * H * W, hw = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -162,6 +173,7 @@ __global__ void attn_bwd_kernel(const float* __restrict__ umap, int B, int H, in
 // partial sums: [0] sum_patches m*|pbar-tbar|, [1] sum p, [2] sum p^2, [3] sum t, [4] sum t^2 ; thread = one 8x8 patch
 __global__ void region_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ s, int B, int H,
                                   int W, float threshold, float* __restrict__ partial) {
+  pdl_prologue();
   float v[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
   const int Hq = H / 8, Wq = W / 8;
   const long long np = (long long)B * Hq * Wq;
@@ -194,6 +206,7 @@ __global__ void region_fwd_kernel(const float* __restrict__ p, const float* __re
 // state: [0] sgn(mean p - mean t), [1] sgn(std p - std t), [2] mean p, [3] std p
 __global__ void region_finish_kernel(const double* __restrict__ sums, double npatch, double n, float weight, float* __restrict__ out,
                                      float* __restrict__ state) {
+  pdl_prologue();
   const double mp = sums[1] / n, mt = sums[3] / n;
   const double vp = fmax((sums[2] - n * mp * mp) / (n - 1.0), 0.0), vt = fmax((sums[4] - n * mt * mt) / (n - 1.0), 0.0);
   const double sp = sqrt(vp), st = sqrt(vt);
@@ -206,6 +219,7 @@ __global__ void region_finish_kernel(const double* __restrict__ sums, double npa
 __global__ void region_bwd_kernel(const float* __restrict__ p, const float* __restrict__ t, const float* __restrict__ s, int B, int H,
                                   int W, float threshold, float weight, const float* __restrict__ state,
                                   const float* __restrict__ gout, float* __restrict__ dp) {
+  pdl_prologue();
   const int Hq = H / 8, Wq = W / 8;
   const long long np = (long long)B * Hq * Wq;
   const double n = double(B) * H * W;
@@ -247,6 +261,7 @@ __device__ __forceinline__ void sobel(const float* __restrict__ img, int y, int 
 // edge maps of pred and target + partial sums [sum e_p, sum e_p^2, sum e_t, sum e_t^2]
 __global__ void edge_fwd_kernel(const float* __restrict__ p, const float* __restrict__ t, int B, int H, int W, float* __restrict__ ep,
                                 float* __restrict__ et, float* __restrict__ partial) {
+  pdl_prologue();
   float v[4] = {0.f, 0.f, 0.f, 0.f};
   const long long n = (long long)B * H * W, hw = (long long)H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -267,6 +282,7 @@ __global__ void edge_fwd_kernel(const float* __restrict__ p, const float* __rest
 // of 8 bits.  sel[0] = prefix found so far, sel[1] = remaining rank (1-based from the top) inside the prefix bucket.
 __global__ void select_hist_kernel(const float* __restrict__ e, long long n, int pass, const unsigned* __restrict__ sel,
                                    unsigned* __restrict__ hist) {
+  pdl_prologue();
   __shared__ unsigned sh[256];
   sh[threadIdx.x] = 0;  // blockDim.x == 256
   __syncthreads();
@@ -281,6 +297,7 @@ __global__ void select_hist_kernel(const float* __restrict__ e, long long n, int
   if (sh[threadIdx.x]) atomicAdd(&hist[threadIdx.x], sh[threadIdx.x]);
 }
 __global__ void select_pick_kernel(unsigned* __restrict__ hist, int pass, unsigned* __restrict__ sel) {
+  pdl_prologue();
   if (threadIdx.x != 0) return;
   unsigned rank = sel[1], acc = 0;
   int b = 255;
@@ -295,12 +312,14 @@ __global__ void select_pick_kernel(unsigned* __restrict__ hist, int pass, unsign
 // selection state for both edge maps, set from kernel arguments (a host-to-device copy of a stack array would be read
 // again -- from a dead stack frame -- every time a CUDA graph holding it is replayed)
 __global__ void select_init_kernel(unsigned* __restrict__ sel, unsigned k) {
+  pdl_prologue();
   const int t = threadIdx.x;
   if (t < 4) sel[t] = (t & 1) ? k : 0u;
   for (int i = 4 + t; i < 4 + 256; i += blockDim.x) sel[i] = 0u;
 }
 // partial sums for the top-k mean: [sum of e > tau, count of e > tau]
 __global__ void topk_sum_kernel(const float* __restrict__ e, long long n, const unsigned* __restrict__ sel, float* __restrict__ partial) {
+  pdl_prologue();
   const float tau = __uint_as_float(sel[0]);
   float v[2] = {0.f, 0.f};
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
@@ -311,6 +330,7 @@ __global__ void topk_sum_kernel(const float* __restrict__ e, long long n, const 
 __global__ void edge_finish_kernel(const double* __restrict__ s4, const double* __restrict__ tp, const double* __restrict__ tt,
                                    const unsigned* __restrict__ selp, const unsigned* __restrict__ selt, double n, double k,
                                    float* __restrict__ out, float* __restrict__ state) {
+  pdl_prologue();
   const double mp = s4[0] / n, mt = s4[2] / n;
   const double sp = sqrt(fmax((s4[1] - n * mp * mp) / (n - 1.0), 0.0)), st = sqrt(fmax((s4[3] - n * mt * mt) / (n - 1.0), 0.0));
   const double taup = double(__uint_as_float(selp[0])), taut = double(__uint_as_float(selt[0]));
@@ -334,6 +354,7 @@ __device__ __forceinline__ float edge_up(const float* __restrict__ ep, long long
 __global__ void edge_bwd_kernel(const float* __restrict__ p, const float* __restrict__ ep, int B, int H, int W,
                                 const float* __restrict__ state, const float* __restrict__ gout, float inv_n, float inv_nm1,
                                 float inv_k, float* __restrict__ dp) {
+  pdl_prologue();
   const float g = gout[0];
   const float g_mean = g * state[0] * inv_n;
   const float g_std = state[3] > 0.f ? g * state[1] * inv_nm1 / state[3] : 0.f;
@@ -370,6 +391,7 @@ __global__ void edge_bwd_kernel(const float* __restrict__ p, const float* __rest
 __constant__ float c_gauss[11];
 // horizontal valid pass over the five maps x, y, xx, yy, xy -> tmp[5][B][H][W-10]
 __global__ void ssim_hpass_kernel(const float* __restrict__ x, const float* __restrict__ y, int B, int H, int W, float* __restrict__ tmp) {
+  pdl_prologue();
   const int Wv = W - 10;
   const long long n = (long long)B * H * Wv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -390,6 +412,7 @@ __global__ void ssim_hpass_kernel(const float* __restrict__ x, const float* __re
 //   dmu1 = dS/d(mu1), dxx = dS/d(E[xx]), dxy = dS/d(E[xy])   (mu2, E[yy] belong to the target: no gradient needed)
 __global__ void ssim_vpass_kernel(const float* __restrict__ tmp, int B, int H, int W, float C1, float C2, float* __restrict__ dmaps,
                                   float* __restrict__ partial) {
+  pdl_prologue();
   const int Wv = W - 10, Hv = H - 10;
   const long long nh = (long long)B * H * Wv, n = (long long)B * Hv * Wv;
   float v[1] = {0.f};
@@ -422,6 +445,7 @@ __global__ void ssim_vpass_kernel(const float* __restrict__ tmp, int B, int H, i
 }
 // adjoint of the vertical valid pass: [B][Hv][Wv] -> [B][H][Wv] for the three derivative maps
 __global__ void ssim_vadj_kernel(const float* __restrict__ dmaps, int B, int H, int W, float* __restrict__ tmp) {
+  pdl_prologue();
   const int Wv = W - 10, Hv = H - 10;
   const long long n = (long long)B * Hv * Wv, nh = (long long)B * H * Wv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nh; i += (long long)gridDim.x * blockDim.x) {
@@ -443,6 +467,7 @@ __global__ void ssim_vadj_kernel(const float* __restrict__ dmaps, int B, int H, 
 // adjoint of the horizontal pass + chain rule: dx = g/Nmap * (Gt(dmu) + 2x*Gt(dExx) + y*Gt(dExy))
 __global__ void ssim_hadj_kernel(const float* __restrict__ tmp, const float* __restrict__ x, const float* __restrict__ y, int B, int H,
                                  int W, const float* __restrict__ gout, float scale, float* __restrict__ dx) {
+  pdl_prologue();
   const int Wv = W - 10;
   const long long n = (long long)B * H * W, nh = (long long)B * H * Wv;
   const float g = gout[0] * scale;
@@ -461,10 +486,11 @@ __global__ void ssim_hadj_kernel(const float* __restrict__ tmp, const float* __r
     dx[i] = g * (a[0] + 2.f * x[i] * a[1] + y[i] * a[2]);
   }
 }
-__global__ void ssim_finish_kernel(const double* __restrict__ sums, double inv_n, float* __restrict__ out) { out[0] = float(sums[0] * inv_n); }
+__global__ void ssim_finish_kernel(const double* __restrict__ sums, double inv_n, float* __restrict__ out) {
+  pdl_prologue(); out[0] = float(sums[0] * inv_n); }
 
 int sum_partials(const float* partial, int blocks, int Q, double* sums, cudaStream_t st) {
-  sum_partials_kernel<<<1, 32 * Q, 0, st>>>(partial, blocks, Q, sums);
+  pdl(sum_partials_kernel, 1, 32 * Q, 0, st)(partial, blocks, Q, sums);
   return check_launch("sum_partials_kernel");
 }
 int ensure_gauss() {
@@ -495,28 +521,28 @@ extern "C" int ducosy_loss_l1_forward(const float* a, const float* b, long long 
   DUCOSY_CHECK(a && b && loss_out && scratch && n > 0, DUCOSY_ERR_ARG, "loss_l1_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int g = loss_grid(n);
-  l1_fwd_kernel<<<g, kLossThreads, 0, st>>>(a, b, n, scratch);
+  pdl(l1_fwd_kernel, g, kLossThreads, 0, st)(a, b, n, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 1, sums_of(scratch), st));
-  mean_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), 1.0 / double(n), loss_out);
+  pdl(mean_finish_kernel, 1, 1, 0, st)(sums_of(scratch), 1.0 / double(n), loss_out);
   return check_launch("loss_l1_forward");
 }
 extern "C" int ducosy_loss_l1_backward(const float* a, const float* b, long long n, const float* gout, float* da, ducosy_stream_t stream) {
   DUCOSY_CHECK(a && b && gout && da && n > 0, DUCOSY_ERR_ARG, "loss_l1_backward: bad argument");
-  l1_bwd_kernel<<<loss_grid(n), kLossThreads, 0, (cudaStream_t)stream>>>(a, b, n, gout, float(1.0 / double(n)), da);
+  pdl(l1_bwd_kernel, loss_grid(n), kLossThreads, 0, (cudaStream_t)stream)(a, b, n, gout, float(1.0 / double(n)), da);
   return check_launch("loss_l1_backward");
 }
 extern "C" int ducosy_loss_mse_const_forward(const float* a, float target, long long n, float* loss_out, float* scratch, ducosy_stream_t stream) {
   DUCOSY_CHECK(a && loss_out && scratch && n > 0, DUCOSY_ERR_ARG, "loss_mse_const_forward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const int g = loss_grid(n);
-  mse_const_fwd_kernel<<<g, kLossThreads, 0, st>>>(a, target, n, scratch);
+  pdl(mse_const_fwd_kernel, g, kLossThreads, 0, st)(a, target, n, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 1, sums_of(scratch), st));
-  mean_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), 1.0 / double(n), loss_out);
+  pdl(mean_finish_kernel, 1, 1, 0, st)(sums_of(scratch), 1.0 / double(n), loss_out);
   return check_launch("loss_mse_const_forward");
 }
 extern "C" int ducosy_loss_mse_const_backward(const float* a, float target, long long n, const float* gout, float* da, ducosy_stream_t stream) {
   DUCOSY_CHECK(a && gout && da && n > 0, DUCOSY_ERR_ARG, "loss_mse_const_backward: bad argument");
-  mse_const_bwd_kernel<<<loss_grid(n), kLossThreads, 0, (cudaStream_t)stream>>>(a, target, n, gout, float(1.0 / double(n)), da);
+  pdl(mse_const_bwd_kernel, loss_grid(n), kLossThreads, 0, (cudaStream_t)stream)(a, target, n, gout, float(1.0 / double(n)), da);
   return check_launch("loss_mse_const_backward");
 }
 
@@ -526,15 +552,15 @@ extern "C" int ducosy_loss_gradient_forward(const float* pred, const float* targ
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * H * W;
   const int g = loss_grid(n);
-  gradloss_fwd_kernel<<<g, kLossThreads, 0, st>>>(pred, target, B, H, W, scratch);
+  pdl(gradloss_fwd_kernel, g, kLossThreads, 0, st)(pred, target, B, H, W, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 2, sums_of(scratch), st));
-  gradloss_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), 1.0 / (double(B) * (H - 1) * W), 1.0 / (double(B) * H * (W - 1)), loss_out);
+  pdl(gradloss_finish_kernel, 1, 1, 0, st)(sums_of(scratch), 1.0 / (double(B) * (H - 1) * W), 1.0 / (double(B) * H * (W - 1)), loss_out);
   return check_launch("loss_gradient_forward");
 }
 extern "C" int ducosy_loss_gradient_backward(const float* pred, const float* target, int B, int H, int W, const float* gout, float* dpred,
                                              ducosy_stream_t stream) {
   DUCOSY_CHECK(pred && target && gout && dpred && B > 0 && H > 1 && W > 1, DUCOSY_ERR_ARG, "loss_gradient_backward: bad argument");
-  gradloss_bwd_kernel<<<loss_grid((long long)B * H * W), kLossThreads, 0, (cudaStream_t)stream>>>(
+  pdl(gradloss_bwd_kernel, loss_grid((long long)B * H * W), kLossThreads, 0, (cudaStream_t)stream)(
       pred, target, B, H, W, gout, float(1.0 / (double(B) * (H - 1) * W)), float(1.0 / (double(B) * H * (W - 1))), dpred);
   return check_launch("loss_gradient_backward");
 }
@@ -547,16 +573,16 @@ extern "C" int ducosy_loss_contrast_attention_forward(const float* pred, const f
   cudaStream_t st = (cudaStream_t)stream;
   const long long n = (long long)B * H * W;
   const int g = loss_grid(n);
-  attn_fwd_kernel<<<g, kLossThreads, 0, st>>>(pred, target, source, B, H, W, 1.f / sigma, min_w, max_w, umap, scratch);
+  pdl(attn_fwd_kernel, g, kLossThreads, 0, st)(pred, target, source, B, H, W, 1.f / sigma, min_w, max_w, umap, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 1, sums_of(scratch), st));
-  mean_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), 1.0 / double(n), loss_out);
+  pdl(mean_finish_kernel, 1, 1, 0, st)(sums_of(scratch), 1.0 / double(n), loss_out);
   return check_launch("loss_contrast_attention_forward");
 }
 extern "C" int ducosy_loss_contrast_attention_backward(const float* umap, int B, int H, int W, const float* gout, float* dpred,
                                                        ducosy_stream_t stream) {
   DUCOSY_CHECK(umap && gout && dpred && B > 0, DUCOSY_ERR_ARG, "loss_contrast_attention_backward: bad argument");
   const long long n = (long long)B * H * W;
-  attn_bwd_kernel<<<loss_grid(n), kLossThreads, 0, (cudaStream_t)stream>>>(umap, B, H, W, gout, float(1.0 / double(n)), dpred);
+  pdl(attn_bwd_kernel, loss_grid(n), kLossThreads, 0, (cudaStream_t)stream)(umap, B, H, W, gout, float(1.0 / double(n)), dpred);
   return check_launch("loss_contrast_attention_backward");
 }
 
@@ -569,9 +595,9 @@ extern "C" int ducosy_loss_contrast_region_forward(const float* pred, const floa
   cudaStream_t st = (cudaStream_t)stream;
   const long long np = (long long)B * (H / 8) * (W / 8);
   const int g = loss_grid(np);
-  region_fwd_kernel<<<g, kLossThreads, 0, st>>>(pred, target, source, B, H, W, threshold, scratch);
+  pdl(region_fwd_kernel, g, kLossThreads, 0, st)(pred, target, source, B, H, W, threshold, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 5, sums_of(scratch), st));
-  region_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), double(np), double(B) * H * W, weight, loss_out, state);
+  pdl(region_finish_kernel, 1, 1, 0, st)(sums_of(scratch), double(np), double(B) * H * W, weight, loss_out, state);
   return check_launch("loss_contrast_region_forward");
 }
 extern "C" int ducosy_loss_contrast_region_backward(const float* pred, const float* target, const float* source, int B, int H, int W,
@@ -579,7 +605,7 @@ extern "C" int ducosy_loss_contrast_region_backward(const float* pred, const flo
                                                     float* dpred, ducosy_stream_t stream) {
   DUCOSY_CHECK(pred && target && source && state && gout && dpred && B > 0, DUCOSY_ERR_ARG, "loss_contrast_region_backward: bad argument");
   const long long np = (long long)B * (H / 8) * (W / 8);
-  region_bwd_kernel<<<loss_grid(np), kLossThreads, 0, (cudaStream_t)stream>>>(pred, target, source, B, H, W, threshold, weight, state, gout, dpred);
+  pdl(region_bwd_kernel, loss_grid(np), kLossThreads, 0, (cudaStream_t)stream)(pred, target, source, B, H, W, threshold, weight, state, gout, dpred);
   return check_launch("loss_contrast_region_backward");
 }
 
@@ -594,19 +620,19 @@ extern "C" int ducosy_loss_contrast_edge_forward(const float* pred, const float*
   const int g = loss_grid(n);
   double* sums = sums_of(scratch);
   unsigned* sel = sel_of(scratch);   // [0..1] sel_p, [2..3] sel_t, [4..259] hist
-  edge_fwd_kernel<<<g, kLossThreads, 0, st>>>(pred, target, B, H, W, ep, et, scratch);
+  pdl(edge_fwd_kernel, g, kLossThreads, 0, st)(pred, target, B, H, W, ep, et, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 4, sums, st));
-  select_init_kernel<<<1, 256, 0, st>>>(sel, unsigned(k));
+  pdl(select_init_kernel, 1, 256, 0, st)(sel, unsigned(k));
   for (int which = 0; which < 2; ++which) {
     const float* e = which == 0 ? ep : et;
     for (int pass = 0; pass < 4; ++pass) {
-      select_hist_kernel<<<g, 256, 0, st>>>(e, n, pass, sel + 2 * which, sel + 4);
-      select_pick_kernel<<<1, 32, 0, st>>>(sel + 4, pass, sel + 2 * which);
+      pdl(select_hist_kernel, g, 256, 0, st)(e, n, pass, sel + 2 * which, sel + 4);
+      pdl(select_pick_kernel, 1, 32, 0, st)(sel + 4, pass, sel + 2 * which);
     }
-    topk_sum_kernel<<<g, kLossThreads, 0, st>>>(e, n, sel + 2 * which, scratch);
+    pdl(topk_sum_kernel, g, kLossThreads, 0, st)(e, n, sel + 2 * which, scratch);
     DUCOSY_TRY(sum_partials(scratch, g, 2, sums + 8 + 4 * which, st));
   }
-  edge_finish_kernel<<<1, 1, 0, st>>>(sums, sums + 8, sums + 12, sel, sel + 2, double(n), double(k), loss_out, state);
+  pdl(edge_finish_kernel, 1, 1, 0, st)(sums, sums + 8, sums + 12, sel, sel + 2, double(n), double(k), loss_out, state);
   return check_launch("loss_contrast_edge_forward");
 }
 extern "C" int ducosy_loss_contrast_edge_backward(const float* pred, const float* ep, int B, int H, int W, const float* state,
@@ -614,7 +640,7 @@ extern "C" int ducosy_loss_contrast_edge_backward(const float* pred, const float
   DUCOSY_CHECK(pred && ep && state && gout && dpred && B > 0, DUCOSY_ERR_ARG, "loss_contrast_edge_backward: bad argument");
   const long long n = (long long)B * H * W;
   const long long k = (long long)(double(n) * 0.1);
-  edge_bwd_kernel<<<loss_grid(n), kLossThreads, 0, (cudaStream_t)stream>>>(pred, ep, B, H, W, state, gout, float(1.0 / double(n)),
+  pdl(edge_bwd_kernel, loss_grid(n), kLossThreads, 0, (cudaStream_t)stream)(pred, ep, B, H, W, state, gout, float(1.0 / double(n)),
                                                                             float(1.0 / double(n - 1)), float(1.0 / double(k)), dpred);
   return check_launch("loss_contrast_edge_backward");
 }
@@ -627,12 +653,12 @@ extern "C" int ducosy_loss_ssim_forward(const float* x, const float* y, int B, i
   DUCOSY_TRY(ensure_gauss());
   cudaStream_t st = (cudaStream_t)stream;
   const long long nv = (long long)B * (H - 10) * (W - 10);
-  ssim_hpass_kernel<<<loss_grid((long long)B * H * (W - 10)), kLossThreads, 0, st>>>(x, y, B, H, W, tmp);
+  pdl(ssim_hpass_kernel, loss_grid((long long)B * H * (W - 10)), kLossThreads, 0, st)(x, y, B, H, W, tmp);
   const int g = loss_grid(nv);
   const float C1 = (0.01f * data_range) * (0.01f * data_range), C2 = (0.03f * data_range) * (0.03f * data_range);
-  ssim_vpass_kernel<<<g, kLossThreads, 0, st>>>(tmp, B, H, W, C1, C2, dmaps, scratch);
+  pdl(ssim_vpass_kernel, g, kLossThreads, 0, st)(tmp, B, H, W, C1, C2, dmaps, scratch);
   DUCOSY_TRY(sum_partials(scratch, g, 1, sums_of(scratch), st));
-  ssim_finish_kernel<<<1, 1, 0, st>>>(sums_of(scratch), 1.0 / double(nv), ssim_out);
+  pdl(ssim_finish_kernel, 1, 1, 0, st)(sums_of(scratch), 1.0 / double(nv), ssim_out);
   return check_launch("loss_ssim_forward");
 }
 // dx = gout * d mean(SSIM) / dx  (gradient w.r.t. the first image only)
@@ -641,7 +667,7 @@ extern "C" int ducosy_loss_ssim_backward(const float* x, const float* y, const f
   DUCOSY_CHECK(x && y && dmaps && gout && tmp && dx && B > 0, DUCOSY_ERR_ARG, "loss_ssim_backward: bad argument");
   cudaStream_t st = (cudaStream_t)stream;
   const long long nv = (long long)B * (H - 10) * (W - 10);
-  ssim_vadj_kernel<<<loss_grid((long long)B * H * (W - 10)), kLossThreads, 0, st>>>(dmaps, B, H, W, tmp);
-  ssim_hadj_kernel<<<loss_grid((long long)B * H * W), kLossThreads, 0, st>>>(tmp, x, y, B, H, W, gout, float(1.0 / double(nv)), dx);
+  pdl(ssim_vadj_kernel, loss_grid((long long)B * H * (W - 10)), kLossThreads, 0, st)(dmaps, B, H, W, tmp);
+  pdl(ssim_hadj_kernel, loss_grid((long long)B * H * W), kLossThreads, 0, st)(tmp, x, y, B, H, W, gout, float(1.0 / double(nv)), dx);
   return check_launch("loss_ssim_backward");
 }

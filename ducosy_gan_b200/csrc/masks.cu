@@ -53,6 +53,7 @@ __device__ void unite(int* L, int a, int b) {
 
 // links: L[g] = g for foreground (mask != 0) pixels, -1 for background.  `invert` labels the background instead.
 __global__ void __launch_bounds__(kT) ccl_init_kernel(const uint8_t* __restrict__ mask, int* __restrict__ L, long long n, int invert) {
+  pdl_prologue();
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const bool fg = (mask[g] != 0) != (invert != 0);
     L[g] = fg ? int(g) : -1;
@@ -60,6 +61,7 @@ __global__ void __launch_bounds__(kT) ccl_init_kernel(const uint8_t* __restrict_
 }
 
 __global__ void __launch_bounds__(kT) ccl_merge_kernel(int* __restrict__ L, int H, int W, long long n) {
+  pdl_prologue();
   const int HW = H * W;
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     if (ld_link(L, int(g)) < 0) continue;
@@ -73,6 +75,7 @@ __global__ void __launch_bounds__(kT) ccl_merge_kernel(int* __restrict__ L, int 
 // border" flags per root
 __global__ void __launch_bounds__(kT) ccl_flatten_kernel(int* __restrict__ L, int* __restrict__ size, uint8_t* __restrict__ border,
                                                          int H, int W, long long n) {
+  pdl_prologue();
   const int HW = H * W;
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     if (ld_link(L, int(g)) < 0) continue;
@@ -89,6 +92,7 @@ __global__ void __launch_bounds__(kT) ccl_flatten_kernel(int* __restrict__ L, in
 // ---- scipy numbering: rank of every root among the roots of its slice, in raster order ---------------------------------
 // step 1: roots per chunk of kT pixels
 __global__ void __launch_bounds__(kT) root_count_kernel(const int* __restrict__ L, int* __restrict__ chunk_count, int HW, int chunks) {
+  pdl_prologue();
   const int b = blockIdx.y, c = blockIdx.x;
   const int p = c * kT + threadIdx.x;
   const long long g = (long long)b * HW + p;
@@ -98,6 +102,7 @@ __global__ void __launch_bounds__(kT) root_count_kernel(const int* __restrict__ 
 }
 // step 2: exclusive scan of the chunk counts of one slice (one CTA per slice), total = number of components
 __global__ void __launch_bounds__(kT) chunk_scan_kernel(int* __restrict__ chunk_count, int* __restrict__ num, int chunks) {
+  pdl_prologue();
   __shared__ int carry;
   __shared__ int warp_tot[kT / 32];
   int* cc = chunk_count + (long long)blockIdx.x * chunks;
@@ -127,6 +132,7 @@ __global__ void __launch_bounds__(kT) chunk_scan_kernel(int* __restrict__ chunk_
 // step 3: rank[g] = 1 + (number of roots before g in its slice), for roots
 __global__ void __launch_bounds__(kT) root_rank_kernel(const int* __restrict__ L, const int* __restrict__ chunk_off, int* __restrict__ rank,
                                                        int HW, int chunks) {
+  pdl_prologue();
   __shared__ int warp_tot[kT / 32];
   const int b = blockIdx.y, c = blockIdx.x;
   const int p = c * kT + threadIdx.x;
@@ -142,6 +148,7 @@ __global__ void __launch_bounds__(kT) root_rank_kernel(const int* __restrict__ L
 }
 // step 4: labels[g] = rank[root(g)] (0 for background)
 __global__ void __launch_bounds__(kT) relabel_kernel(const int* __restrict__ L, const int* __restrict__ rank, int* __restrict__ labels, long long n) {
+  pdl_prologue();
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const int r = L[g];
     labels[g] = r < 0 ? 0 : rank[r];
@@ -152,6 +159,7 @@ __global__ void __launch_bounds__(kT) relabel_kernel(const int* __restrict__ L, 
 // lung candidate: (lo <= hu <= hi) & (hu > -1000), border margin cleared   (mask_generator.py:13-29); body = hu > -1000
 __global__ void __launch_bounds__(kT) lung_candidate_kernel(const float* __restrict__ hu, uint8_t* __restrict__ cand, uint8_t* __restrict__ body,
                                                             int H, int W, long long n, float lo, float hi, int margin) {
+  pdl_prologue();
   const int HW = H * W;
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const float v = hu[g];
@@ -165,6 +173,7 @@ __global__ void __launch_bounds__(kT) lung_candidate_kernel(const float* __restr
 // keep components of at least min_size pixels   (mask_generator.py:32-36)
 __global__ void __launch_bounds__(kT) keep_large_kernel(const int* __restrict__ L, const int* __restrict__ size, uint8_t* __restrict__ out,
                                                         long long n, int min_size) {
+  pdl_prologue();
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const int r = L[g];
     out[g] = (r >= 0 && size[r] >= min_size) ? 1 : 0;
@@ -173,6 +182,7 @@ __global__ void __launch_bounds__(kT) keep_large_kernel(const int* __restrict__ 
 // filled = mask | (background component that does not touch the border)
 __global__ void __launch_bounds__(kT) fill_kernel(const uint8_t* __restrict__ mask, const int* __restrict__ L, const uint8_t* __restrict__ border,
                                                   uint8_t* __restrict__ out, long long n) {
+  pdl_prologue();
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const int r = L[g];     // links of the BACKGROUND labelling: r < 0 on foreground pixels
     out[g] = (mask[g] != 0 || (r >= 0 && border[r] == 0)) ? 1 : 0;
@@ -181,6 +191,7 @@ __global__ void __launch_bounds__(kT) fill_kernel(const uint8_t* __restrict__ ma
 // per-slice pixel counts of two uint8 masks (integer atomics)
 __global__ void __launch_bounds__(kT) area_kernel(const uint8_t* __restrict__ a, const uint8_t* __restrict__ b, int* __restrict__ area_a,
                                                   int* __restrict__ area_b, int HW) {
+  pdl_prologue();
   const int s = blockIdx.y;
   int ca = 0, cb = 0;
   for (int p = blockIdx.x * kT + threadIdx.x; p < HW; p += gridDim.x * kT) {
@@ -203,6 +214,7 @@ __global__ void __launch_bounds__(kT) vessel_kernel(const float* __restrict__ hu
                                                     const int* __restrict__ num_regions, const int* __restrict__ body_area,
                                                     const int* __restrict__ lung_area, uint8_t* __restrict__ out, int HW, long long n, float lo,
                                                     float hi) {
+  pdl_prologue();
   for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
     const int s = int(g / HW);
     const bool ok = num_regions[s] >= 2 && body_area[s] > 0 && (double(lung_area[s]) / double(body_area[s])) >= 0.1;
@@ -257,21 +269,21 @@ int run_ccl(const uint8_t* mask, int invert, int* L, int* size, uint8_t* border,
   const long long n = (long long)B * H * W;
   if (size != nullptr) cudaMemsetAsync(size, 0, size_t(n) * 4, st);
   if (border != nullptr) cudaMemsetAsync(border, 0, size_t(n), st);
-  ccl_init_kernel<<<ew_grid(n), kT, 0, st>>>(mask, L, n, invert);
-  ccl_merge_kernel<<<ew_grid(n), kT, 0, st>>>(L, H, W, n);
-  ccl_flatten_kernel<<<ew_grid(n), kT, 0, st>>>(L, size, border, H, W, n);
+  pdl(ccl_init_kernel, ew_grid(n), kT, 0, st)(mask, L, n, invert);
+  pdl(ccl_merge_kernel, ew_grid(n), kT, 0, st)(L, H, W, n);
+  pdl(ccl_flatten_kernel, ew_grid(n), kT, 0, st)(L, size, border, H, W, n);
   return check_launch("ccl kernels");
 }
 
 // number of components per slice (and optionally scipy labels) from flattened links
 int run_count(const int* L, int* chunk, int* num, int* rank, int* labels, int B, int H, int W, cudaStream_t st) {
   const int HW = H * W, chunks = (HW + kT - 1) / kT;
-  root_count_kernel<<<dim3(chunks, B), kT, 0, st>>>(L, chunk, HW, chunks);
-  chunk_scan_kernel<<<B, kT, 0, st>>>(chunk, num, chunks);
+  pdl(root_count_kernel, dim3(chunks, B), kT, 0, st)(L, chunk, HW, chunks);
+  pdl(chunk_scan_kernel, B, kT, 0, st)(chunk, num, chunks);
   if (labels != nullptr) {
     const long long n = (long long)B * HW;
-    root_rank_kernel<<<dim3(chunks, B), kT, 0, st>>>(L, chunk, rank, HW, chunks);
-    relabel_kernel<<<ew_grid(n), kT, 0, st>>>(L, rank, labels, n);
+    pdl(root_rank_kernel, dim3(chunks, B), kT, 0, st)(L, chunk, rank, HW, chunks);
+    pdl(relabel_kernel, ew_grid(n), kT, 0, st)(L, rank, labels, n);
   }
   return check_launch("component count kernels");
 }
@@ -308,7 +320,7 @@ extern "C" int ducosy_binary_fill_holes(const uint8_t* mask, uint8_t* out, int B
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * H * W;
   DUCOSY_TRY(run_ccl(mask, 1, s.L, nullptr, s.u8a, B, H, W, st));
-  fill_kernel<<<ew_grid(n), kT, 0, st>>>(mask, s.L, s.u8a, out, n);
+  pdl(fill_kernel, ew_grid(n), kT, 0, st)(mask, s.L, s.u8a, out, n);
   return check_launch("fill_kernel");
 }
 
@@ -321,10 +333,10 @@ extern "C" int ducosy_detect_lung(const float* hu, uint8_t* lung_mask, int B, in
   DUCOSY_CHECK(scratch_bytes >= s.total, DUCOSY_ERR_WORKSPACE, "detect_lung: scratch %zu < required %zu bytes", scratch_bytes, s.total);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   const long long n = (long long)B * H * W;
-  lung_candidate_kernel<<<ew_grid(n), kT, 0, st>>>(hu, s.u8a, nullptr, H, W, n, lung_lower, lung_upper, border_margin);
+  pdl(lung_candidate_kernel, ew_grid(n), kT, 0, st)(hu, s.u8a, nullptr, H, W, n, lung_lower, lung_upper, border_margin);
   DUCOSY_TRY(check_launch("lung_candidate_kernel"));
   DUCOSY_TRY(run_ccl(s.u8a, 0, s.L, s.aux, nullptr, B, H, W, st));
-  keep_large_kernel<<<ew_grid(n), kT, 0, st>>>(s.L, s.aux, lung_mask, n, min_size);
+  pdl(keep_large_kernel, ew_grid(n), kT, 0, st)(s.L, s.aux, lung_mask, n, min_size);
   return check_launch("keep_large_kernel");
 }
 
@@ -342,14 +354,14 @@ extern "C" int ducosy_detect_lung_vessels(const float* hu, const uint8_t* lung_m
   DUCOSY_TRY(run_ccl(lung_mask, 0, s.L, nullptr, nullptr, B, H, W, st));
   DUCOSY_TRY(run_count(s.L, s.chunk, s.num, nullptr, nullptr, B, H, W, st));
   // body mask and the two areas
-  lung_candidate_kernel<<<ew_grid(n), kT, 0, st>>>(hu, s.u8c, s.u8b, H, W, n, 0.f, -1.f, 0);   // only the body mask (u8b) is used
+  pdl(lung_candidate_kernel, ew_grid(n), kT, 0, st)(hu, s.u8c, s.u8b, H, W, n, 0.f, -1.f, 0);   // only the body mask (u8b) is used
   cudaMemsetAsync(s.area_a, 0, size_t(B) * 4, st);
   cudaMemsetAsync(s.area_b, 0, size_t(B) * 4, st);
-  area_kernel<<<dim3(std::min((HW + kT - 1) / kT, 64), B), kT, 0, st>>>(s.u8b, lung_mask, s.area_a, s.area_b, HW);
+  pdl(area_kernel, dim3(std::min((HW + kT - 1) / kT, 64), B), kT, 0, st)(s.u8b, lung_mask, s.area_a, s.area_b, HW);
   DUCOSY_TRY(check_launch("area_kernel"));
   // filled lung
   DUCOSY_TRY(run_ccl(lung_mask, 1, s.L, nullptr, s.u8a, B, H, W, st));
-  fill_kernel<<<ew_grid(n), kT, 0, st>>>(lung_mask, s.L, s.u8a, s.u8c, n);
-  vessel_kernel<<<ew_grid(n), kT, 0, st>>>(hu, lung_mask, s.u8c, s.num, s.area_a, s.area_b, vessel_mask, HW, n, vessel_lower, vessel_upper);
+  pdl(fill_kernel, ew_grid(n), kT, 0, st)(lung_mask, s.L, s.u8a, s.u8c, n);
+  pdl(vessel_kernel, ew_grid(n), kT, 0, st)(hu, lung_mask, s.u8c, s.num, s.area_a, s.area_b, vessel_mask, HW, n, vessel_lower, vessel_upper);
   return check_launch("vessel_kernel");
 }

@@ -39,6 +39,7 @@ template <> struct IsI16<int16_t> { static constexpr bool v = true; };
 template <typename In>
 __global__ void __launch_bounds__(kThreads)
 metrics_pair_kernel(const In* __restrict__ a, const In* __restrict__ b, long long n, int chunks, double* __restrict__ part) {
+  pdl_prologue();
   const int s = blockIdx.y, c = blockIdx.x;
   const long long per = (n + chunks - 1) / chunks;
   const long long lo = c * per, hi = lo + per < n ? lo + per : n;
@@ -84,6 +85,7 @@ metrics_pair_kernel(const In* __restrict__ a, const In* __restrict__ b, long lon
 
 // stats[s][k] = fixed-order reduction of the chunk partials
 __global__ void metrics_finalize_kernel(const double* __restrict__ part, int S, int chunks, int K, double* __restrict__ stats) {
+  pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= S * K) return;
   const int s = i / K, k = i % K;
@@ -101,6 +103,7 @@ template <typename In>
 __global__ void __launch_bounds__(kThreads)
 metrics_ed_kernel(const In* __restrict__ a, const In* __restrict__ b, long long n, int chunks, const double* __restrict__ stats,
                   double* __restrict__ part) {
+  pdl_prologue();
   const int s = blockIdx.y, c = blockIdx.x;
   const long long per = (n + chunks - 1) / chunks;
   const long long lo = c * per, hi = lo + per < n ? lo + per : n;
@@ -126,6 +129,7 @@ metrics_ed_kernel(const In* __restrict__ a, const In* __restrict__ b, long long 
 // normalize (calculate.py:232-238): (data - min) / (max - min) in float64; zeros when the range is 0.  mm = {min, max}.
 template <typename In>
 __global__ void metrics_normalize_kernel(const In* __restrict__ in, double* __restrict__ out, long long total, const double* __restrict__ mm) {
+  pdl_prologue();
   const double mn = mm[0], r = mm[1] - mm[0];
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x)
     out[i] = r == 0.0 ? 0.0 : (double(in[i]) - mn) / r;
@@ -140,6 +144,7 @@ constexpr int kSsimTile = 32, kSsimHalo = kSsimTile + 6;
 template <typename In>
 __global__ void __launch_bounds__(kThreads)
 metrics_ssim_kernel(const In* __restrict__ a, const In* __restrict__ b, int H, int W, double data_range, double* __restrict__ part) {
+  pdl_prologue();
   __shared__ double ta[kSsimHalo][kSsimHalo + 1], tb[kSsimHalo][kSsimHalo + 1];
   __shared__ double red[kThreads / 32];
   const int s = blockIdx.z;
@@ -210,10 +215,10 @@ extern "C" int ducosy_metrics_slice_stats(const void* a, const void* b, int in_t
   DUCOSY_CHECK(in_type >= DUCOSY_IN_I16 && in_type <= DUCOSY_IN_F64, DUCOSY_ERR_ARG, "metrics_slice_stats: bad input type");
   const int chunks = pick_chunks(n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DUCOSY_DISPATCH_IN(in_type, In, (metrics_pair_kernel<In><<<dim3(chunks, S), kThreads, 0, st>>>(
+  DUCOSY_DISPATCH_IN(in_type, In, (pdl(metrics_pair_kernel<In>, dim3(chunks, S), kThreads, 0, st)(
                                       static_cast<const In*>(a), static_cast<const In*>(b), n, chunks, scratch)));
   DUCOSY_TRY(check_launch("metrics_pair_kernel"));
-  metrics_finalize_kernel<<<(S * kStat + 255) / 256, 256, 0, st>>>(scratch, S, chunks, kStat, stats);
+  pdl(metrics_finalize_kernel, (S * kStat + 255) / 256, 256, 0, st)(scratch, S, chunks, kStat, stats);
   return check_launch("metrics_finalize_kernel");
 }
 
@@ -223,10 +228,10 @@ extern "C" int ducosy_metrics_ed(const void* a, const void* b, int in_type, int 
   DUCOSY_CHECK(in_type >= DUCOSY_IN_I16 && in_type <= DUCOSY_IN_F64, DUCOSY_ERR_ARG, "metrics_ed: bad input type");
   const int chunks = pick_chunks(n);
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DUCOSY_DISPATCH_IN(in_type, In, (metrics_ed_kernel<In><<<dim3(chunks, S), kThreads, 0, st>>>(
+  DUCOSY_DISPATCH_IN(in_type, In, (pdl(metrics_ed_kernel<In>, dim3(chunks, S), kThreads, 0, st)(
                                       static_cast<const In*>(a), static_cast<const In*>(b), n, chunks, stats, scratch)));
   DUCOSY_TRY(check_launch("metrics_ed_kernel"));
-  metrics_finalize_kernel<<<(S + 255) / 256, 256, 0, st>>>(scratch, S, chunks, 1, ed_sums);
+  pdl(metrics_finalize_kernel, (S + 255) / 256, 256, 0, st)(scratch, S, chunks, 1, ed_sums);
   return check_launch("metrics_finalize_kernel");
 }
 
@@ -237,7 +242,7 @@ extern "C" int ducosy_metrics_normalize(const void* in, int in_type, double* out
   const int sms = num_sms() > 0 ? num_sms() : 148;
   long long blocks = (total + 255) / 256;
   if (blocks > sms * 16LL) blocks = sms * 16LL;
-  DUCOSY_DISPATCH_IN(in_type, In, (metrics_normalize_kernel<In><<<int(blocks), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+  DUCOSY_DISPATCH_IN(in_type, In, (pdl(metrics_normalize_kernel<In>, int(blocks), 256, 0, static_cast<cudaStream_t>(stream))(
                                       static_cast<const In*>(in), out, total, minmax)));
   return check_launch("metrics_normalize_kernel");
 }
@@ -255,9 +260,9 @@ extern "C" int ducosy_metrics_ssim(const void* a, const void* b, int in_type, in
   const int gx = (W - 6 + kSsimTile - 1) / kSsimTile, gy = (H - 6 + kSsimTile - 1) / kSsimTile;
   DUCOSY_CHECK(S <= 65535, DUCOSY_ERR_SHAPE, "metrics_ssim: at most 65535 slices per call");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  DUCOSY_DISPATCH_IN(in_type, In, (metrics_ssim_kernel<In><<<dim3(gx, gy, S), kThreads, 0, st>>>(
+  DUCOSY_DISPATCH_IN(in_type, In, (pdl(metrics_ssim_kernel<In>, dim3(gx, gy, S), kThreads, 0, st)(
                                       static_cast<const In*>(a), static_cast<const In*>(b), H, W, data_range, scratch)));
   DUCOSY_TRY(check_launch("metrics_ssim_kernel"));
-  metrics_finalize_kernel<<<(S + 255) / 256, 256, 0, st>>>(scratch, S, gx * gy, 1, ssim_sums);
+  pdl(metrics_finalize_kernel, (S + 255) / 256, 256, 0, st)(scratch, S, gx * gy, 1, ssim_sums);
   return check_launch("metrics_finalize_kernel");
 }

@@ -27,6 +27,7 @@ __device__ __forceinline__ bool finite_f(float x) { return (__float_as_uint(x) &
 __global__ void __launch_bounds__(kAdamThreads)
 adam_check_kernel(const ducosy_adam_tensor* __restrict__ tensors, const ducosy_adam_chunk* __restrict__ chunks,
                   float* __restrict__ state) {
+  pdl_prologue();
   const ducosy_adam_chunk c = chunks[blockIdx.x];
   const ducosy_adam_tensor t = tensors[c.tensor];
   const long long end = c.start + DUCOSY_ADAM_CHUNK < t.n ? c.start + DUCOSY_ADAM_CHUNK : t.n;
@@ -46,6 +47,7 @@ adam_check_kernel(const ducosy_adam_tensor* __restrict__ tensors, const ducosy_a
 }
 
 __global__ void adam_advance_kernel2(float* __restrict__ state) {
+  pdl_prologue();
   const float bad = state[2];
   state[4] = bad;
   state[2] = 0.f;
@@ -55,6 +57,7 @@ __global__ void adam_advance_kernel2(float* __restrict__ state) {
 __global__ void __launch_bounds__(kAdamThreads)
 adam_multi_kernel(const ducosy_adam_tensor* __restrict__ tensors, const ducosy_adam_chunk* __restrict__ chunks,
                   const float* __restrict__ state, float b1, float b2, float eps) {
+  pdl_prologue();
   __shared__ float s_step_size, s_inv_sqrt_bc2;
   if (state[4] != 0.f) return;                     // a gradient of this step is not finite: leave everything alone
   if (threadIdx.x == 0) {
@@ -109,11 +112,11 @@ extern "C" int ducosy_adam_multi_step(const ducosy_adam_tensor* tensors_dev, con
   DUCOSY_CHECK(tensors_dev && chunks_dev && state && num_chunks > 0, DUCOSY_ERR_ARG, "adam_multi_step: bad argument");
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (check_finite) {
-    adam_check_kernel<<<num_chunks, kAdamThreads, 0, st>>>(tensors_dev, chunks_dev, state);
+    pdl(adam_check_kernel, num_chunks, kAdamThreads, 0, st)(tensors_dev, chunks_dev, state);
     DUCOSY_TRY(check_launch("adam_check_kernel"));
   }
-  adam_advance_kernel2<<<1, 1, 0, st>>>(state);
+  pdl(adam_advance_kernel2, 1, 1, 0, st)(state);
   DUCOSY_TRY(check_launch("adam_advance_kernel"));
-  adam_multi_kernel<<<num_chunks, kAdamThreads, 0, st>>>(tensors_dev, chunks_dev, state, beta1, beta2, eps);
+  pdl(adam_multi_kernel, num_chunks, kAdamThreads, 0, st)(tensors_dev, chunks_dev, state, beta1, beta2, eps);
   return check_launch("adam_multi_kernel");
 }

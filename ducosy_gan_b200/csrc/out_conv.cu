@@ -36,6 +36,7 @@ __device__ __forceinline__ void mma16816<__nv_bfloat16>(float (&c)[4], uint32_t 
 // planes == 2 (split-operand mode): a second [7][8][64] block holds lo = rn(w - hi)
 template <typename T>
 __global__ void pack_out_weight_kernel(const float* __restrict__ w, T* __restrict__ out, int planes) {
+  pdl_prologue();
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < 7 * 8 * 64; i += gridDim.x * blockDim.x) {
     const int c = i & 63, s = (i >> 6) & 7, r = i >> 9;
     const float v = s < 7 ? w[c * 49 + r * 7 + s] : 0.f;
@@ -61,6 +62,7 @@ __global__ void __launch_bounds__(kOutThreads)
 out_conv7x7_tanh_kernel(const T* __restrict__ in, const float* __restrict__ scale, const float* __restrict__ shift,
                         const T* __restrict__ wp, const float* __restrict__ bias, float* __restrict__ out, int B, int H,
                         int W) {
+  pdl_prologue();
   __shared__ float P[kRowsOut][kPos][9];  // 9-float rows: the diagonal reads below are bank-conflict free
   const int tiles_x = W / kColsOut, tiles_y = H / kRowsOut;
   const int tx = blockIdx.x % tiles_x;
@@ -190,7 +192,7 @@ using namespace ducosy;
 extern "C" int ducosy_pack_out_weight(const float* w, void* packed, int dtype, ducosy_stream_t stream) {
   DUCOSY_CHECK(w && packed, DUCOSY_ERR_ARG, "pack_out_weight: null pointer");
   DUCOSY_DISPATCH_DTYPE(dtype, T,
-                        (pack_out_weight_kernel<T><<<14, 256, 0, (cudaStream_t)stream>>>(w, static_cast<T*>(packed), dtype == DUCOSY_F16X2 ? 2 : 1)));
+                        (pdl(pack_out_weight_kernel<T>, 14, 256, 0, (cudaStream_t)stream)(w, static_cast<T*>(packed), dtype == DUCOSY_F16X2 ? 2 : 1)));
   return check_launch("pack_out_weight_kernel");
 }
 
@@ -203,7 +205,7 @@ extern "C" int ducosy_out_conv7x7_tanh(const void* in_pad, const void* w_packed,
                DUCOSY_ERR_ALIGN, "out_conv7x7_tanh: 16-byte alignment");
   const int grid = B * (H / kRowsOut) * (W / kColsOut);
   DUCOSY_CHECK(dtype != DUCOSY_F16X2, DUCOSY_ERR_ARG, "out_conv7x7_tanh: split-operand mode is available in the fused variant only");
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T, false, false><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv7x7_tanh_kernel<T, false, false>, grid, kOutThreads, 0, (cudaStream_t)stream)(
                                       static_cast<const T*>(in_pad), nullptr, nullptr, static_cast<const T*>(w_packed), bias,
                                       out, B, H, W)));
   return check_launch("out_conv7x7_tanh_kernel");
@@ -219,10 +221,10 @@ extern "C" int ducosy_out_conv7x7_tanh_fused(const void* y_raw, const float* sca
                DUCOSY_ERR_ALIGN, "out_conv7x7_tanh_fused: 16-byte alignment");
   const int grid = B * (H / kRowsOut) * (W / kColsOut);
   if (dtype == DUCOSY_F16X2)
-    out_conv7x7_tanh_kernel<__half, true, true><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+    pdl(out_conv7x7_tanh_kernel<__half, true, true>, grid, kOutThreads, 0, (cudaStream_t)stream)(
         static_cast<const __half*>(y_raw), scale, shift, static_cast<const __half*>(w_packed), bias, out, B, H, W);
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (out_conv7x7_tanh_kernel<T, true, false><<<grid, kOutThreads, 0, (cudaStream_t)stream>>>(
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv7x7_tanh_kernel<T, true, false>, grid, kOutThreads, 0, (cudaStream_t)stream)(
                                         static_cast<const T*>(y_raw), scale, shift, static_cast<const T*>(w_packed), bias, out,
                                         B, H, W)));
   return check_launch("out_conv7x7_tanh_kernel(fused)");

@@ -41,6 +41,7 @@ template <typename TIn, int R, bool kMinMax>
 __global__ void __launch_bounds__(256)
 zfilter_kernel(const TIn* __restrict__ in, float* __restrict__ out, float* __restrict__ pmin, float* __restrict__ pmax, int S,
                long long HW, PostWeights pw, int which, int mm_z0, int mm_z1) {
+  pdl_prologue();
   const double* w = which == 1 ? pw.wz1 : pw.wz2;
   const long long p = (long long)blockIdx.x * 256 + threadIdx.x;
   float mn = INFINITY, mx = -INFINITY;
@@ -78,6 +79,7 @@ zfilter_kernel(const TIn* __restrict__ in, float* __restrict__ out, float* __res
 }
 
 __global__ void minmax_finalize_kernel(const float* __restrict__ pmin, const float* __restrict__ pmax, int n, float* __restrict__ mm) {
+  pdl_prologue();
   __shared__ float smn[32], smx[32];
   float mn = INFINITY, mx = -INFINITY;
   for (int i = threadIdx.x; i < n; i += blockDim.x) { mn = fminf(mn, pmin[i]); mx = fmaxf(mx, pmax[i]); }
@@ -102,6 +104,7 @@ template <int R>
 __global__ void __launch_bounds__(256)
 unsharp_finalize_kernel(const float* __restrict__ pp, const float* __restrict__ v1, const float* __restrict__ mm,
                         short* __restrict__ out, int H, int W, PostWeights pw) {
+  pdl_prologue();
   constexpr int TW = kTile + 2 * R;
   __shared__ double tile[TW][TW];
   __shared__ double vert[kTile][TW];
@@ -195,7 +198,7 @@ extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, fl
   float* pmax = pmin + blocks;
   float* mm = pmax + blocks;
 #define ZF(TIn, R, MM, src, dst, which)                                                                     \
-  zfilter_kernel<TIn, R, MM><<<blocks, 256, 0, st>>>(src, dst, pmin, pmax, S, HW, pw, which, mm_z0, mm_z1)
+  pdl(zfilter_kernel<TIn, R, MM>, blocks, 256, 0, st)(src, dst, pmin, pmax, S, HW, pw, which, mm_z0, mm_z1)
   if (phases & 1) {
   switch (rz1) {
     case 1: ZF(short, 1, true, merged, v1, 1); break;
@@ -204,7 +207,7 @@ extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, fl
     default: ZF(short, 4, true, merged, v1, 1); break;
   }
   DUCOSY_TRY(check_launch("zfilter_kernel"));
-  minmax_finalize_kernel<<<1, 1024, 0, st>>>(pmin, pmax, blocks, mm);
+  pdl(minmax_finalize_kernel, 1, 1024, 0, st)(pmin, pmax, blocks, mm);
   DUCOSY_TRY(check_launch("minmax_finalize_kernel"));
   switch (rz2) {
     case 1: ZF(float, 1, false, v1, pp, 2); break;
@@ -219,14 +222,14 @@ extern "C" int ducosy_postprocess_volume(const int16_t* merged, int16_t* out, fl
   const dim3 grid((W + kTile - 1) / kTile, (H + kTile - 1) / kTile, S);
   short* o = reinterpret_cast<short*>(out);
   switch (rxy) {
-    case 1: unsharp_finalize_kernel<1><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 2: unsharp_finalize_kernel<2><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 3: unsharp_finalize_kernel<3><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 4: unsharp_finalize_kernel<4><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 5: unsharp_finalize_kernel<5><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 6: unsharp_finalize_kernel<6><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    case 7: unsharp_finalize_kernel<7><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
-    default: unsharp_finalize_kernel<8><<<grid, 256, 0, st>>>(pp, v1, mm, o, H, W, pw); break;
+    case 1: pdl(unsharp_finalize_kernel<1>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 2: pdl(unsharp_finalize_kernel<2>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 3: pdl(unsharp_finalize_kernel<3>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 4: pdl(unsharp_finalize_kernel<4>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 5: pdl(unsharp_finalize_kernel<5>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 6: pdl(unsharp_finalize_kernel<6>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    case 7: pdl(unsharp_finalize_kernel<7>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
+    default: pdl(unsharp_finalize_kernel<8>, grid, 256, 0, st)(pp, v1, mm, o, H, W, pw); break;
   }
   return check_launch("unsharp_finalize_kernel");
 }

@@ -47,6 +47,7 @@ __device__ __forceinline__ float bfly_sum(float (&x)[32], int lane) {
 // Input preparation (once per forward): fp32 tensor or stored pixels through the HU window -> 16-bit [B][H][W].
 template <typename T, typename In>
 __global__ void stem_input_kernel(In in, T* __restrict__ xw, int B, int H, int W) {
+  pdl_prologue();
   const long long total = (long long)B * H * W;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
     const int x = int(i % W);
@@ -77,6 +78,7 @@ stem_fused_kernel(const T* __restrict__ xw, const T* __restrict__ wp, float* __r
   const int Wp = W + 16;
   const int y = blockIdx.x, b = blockIdx.y;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_wait();   // programmatic dependent launch (common.cuh): the prepared input / statistics come from the previous kernel
 
   {
     const unsigned short* src = reinterpret_cast<const unsigned short*>(xw) + size_t(b) * H * W;
@@ -109,6 +111,7 @@ stem_fused_kernel(const T* __restrict__ xw, const T* __restrict__ wp, float* __r
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_launch_dependents();   // only after the TMEM allocation (see common.cuh)
 
   float s1[64], s2[64];  // pass 1 only: this thread's pixels, all 64 channels
   if (!kApply) {
@@ -266,7 +269,7 @@ int launch_stem_pass(const void* xw, const void* wp, float* partials, const floa
     if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "cudaFuncSetAttribute(stem_fused): %s", cudaGetErrorString(e));
   }
   DUCOSY_CHECK(smem <= 112 * 1024, DUCOSY_ERR_SHAPE, "stem_fused: image too wide (W = %d)", W);
-  kern<<<dim3(H, B), kStemThreads, smem, st>>>(static_cast<const T*>(xw), static_cast<const T*>(wp), partials, scale,
+  pdl(kern, dim3(H, B), kStemThreads, smem, st)(static_cast<const T*>(xw), static_cast<const T*>(wp), partials, scale,
                                                shift, static_cast<T*>(out_pad), H, W);
   return check_launch("stem_fused_kernel");
 }
@@ -277,7 +280,7 @@ int launch_stem_input(In in, void* xw, int B, int H, int W, cudaStream_t st) {
   long long blocks = (total + 255) / 256;
   const long long cap = (long long)(num_sms() > 0 ? num_sms() : 148) * 8;
   if (blocks > cap) blocks = cap;
-  stem_input_kernel<T, In><<<int(blocks), 256, 0, st>>>(in, static_cast<T*>(xw), B, H, W);
+  pdl(stem_input_kernel<T, In>, int(blocks), 256, 0, st)(in, static_cast<T*>(xw), B, H, W);
   return check_launch("stem_input_kernel");
 }
 

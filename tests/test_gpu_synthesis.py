@@ -119,3 +119,33 @@ def test_synthesize_edge_sizes(case):
     assert d.max() <= MAX_LUNG
     with pytest.raises(RuntimeError):
         synth.synthesize_volume(vol.astype(np.float32))
+
+
+def test_synthesize_series_dicom_folder_round_trip(tmp_path):
+    """NCCT series folder -> synthetic series folder through ``dicom_io.synthesize_series`` (one read and one
+    write per slice instead of generate.py's per-slice DICOM round trips) equals ``synthesize_volume`` (+ the device volume
+    smoothing) on the same stored values; files are named {idx:04d}.dcm in sorted-filename order (generate.py:88,285)."""
+    from test_dicom_io import _file      # tests/ is on sys.path (pytest rootdir import mode)
+    from ducosy_gan_b200 import dicom_io as dio
+    from ducosy_gan_b200.modules.model import Generator
+    from ducosy_gan_b200.postprocess import postprocess_volume
+    from ducosy_gan_b200.synthesis import DualHUSynthesizer
+    nb = 1
+    shapes = orc.generator_param_shapes(1, nb, True)
+    gs, gl = Generator(1, nb), Generator(1, nb)
+    gs.load_state_dict(orc.make_state_dict(shapes, 3))
+    gl.load_state_dict(orc.make_state_dict(shapes, 4))
+    synth = DualHUSynthesizer(gs.cuda().eval(), gl.cuda().eval(), batch_slices=4)
+    vol = orc.phantom_volume(7, H, W, seed=2).astype(np.int16)
+    src = tmp_path / "POST VUE"
+    src.mkdir()
+    for i in range(7):
+        (src / f"IM{i:03d}.dcm").write_bytes(_file(vol[i], explicit=i % 2 == 0, slope="1", intercept="-1024"))
+    merged, slices = dio.synthesize_series(synth, str(src), str(tmp_path / "out"), postprocess=True)
+    want = synth.synthesize_volume(torch.from_numpy(vol), 1.0, -1024.0)
+    want = postprocess_volume(want.cuda()).cpu()
+    assert torch.equal(merged, want)
+    for i in range(7):
+        back = dio.read_dicom(str(tmp_path / "out" / f"{i:04d}.dcm"))
+        assert np.array_equal(back.pixel_array(), want[i].numpy())
+        assert back.series_description == "DuCoSyGAN sCECT v2" and back.transfer_syntax == dio.EXPLICIT_LE

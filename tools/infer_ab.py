@@ -29,6 +29,8 @@ print(json.dumps({"slices_per_s": S * n / (e0.elapsed_time(e1) / 1e3), "checksum
 ''' % ROOT
 
 settings = [dict(), dict(DUCOSY_FUSED_FINALIZE="1"), dict(DUCOSY_FUSED_SPATIAL="0"), dict(DUCOSY_FUSED_FINALIZE="1", DUCOSY_FUSED_SPATIAL="0")]
+if os.environ.get("AB_ONLY_DEFAULT"):
+    settings = settings[:1]
 extra = [s.split("=") for s in sys.argv[1:]]
 res = {}
 for st in settings:
