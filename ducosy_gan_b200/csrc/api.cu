@@ -30,8 +30,13 @@ int check_launch(const char* what) {
   if (e != cudaSuccess) return fail(DUCOSY_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
   return 0;
 }
+// Programmatic dependent launch is OPT-IN (DUCOSY_PDL=1).  Same-box A/B (profiles/r02_pdl_ab.json): the eager batch-1 forward
+// gains 14 % (2.07 -> 1.78 ms per dual-HU slice), a CUDA-graph replay of the same chain gains nothing (1.708 -> 1.703 ms: graph
+// launches already have no gap to hide), and every two-stream path LOSES -- early-resident CTAs spinning at their
+// griddepcontrol.wait hold SM slots the other stream's kernels would have used: train step batch 1 19.07 -> 20.98 ms, batch 8
+// 108.2 -> 111.3 ms, batch-30 synthesis 958 -> 944 slices/s.
 bool pdl_enabled() {
-  static const bool on = []() { const char* e = getenv("DUCOSY_PDL"); return e == nullptr || atoi(e) != 0; }();
+  static const bool on = []() { const char* e = getenv("DUCOSY_PDL"); return e != nullptr && atoi(e) != 0; }();
   return on;
 }
 int num_sms() {
@@ -65,6 +70,11 @@ int check_device_cached() {
 }
 
 size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+bool fused_spatial() {
+  static const bool on = []() { const char* e = getenv("DUCOSY_FUSED_SPATIAL"); return e != nullptr && atoi(e) != 0; }();
+  return on;
+}
 
 void fill_taps_3x3(ConvPlan& p) {
   p.num_phases = 1;
@@ -298,8 +308,12 @@ int generator_forward_impl(const ducosy_gen_config& c, const void* packed, const
     const float* fc2 = c.use_cbam ? reinterpret_cast<const float*>(pk + L.fc2[i]) : nullptr;
     DUCOSY_TRY(run_conv_in(p, scale, shift, fc0, fc2, c.use_cbam ? chmax : nullptr, tickets, H4 * W4, st));
     const int mode = i + 1 < nb ? DUCOSY_PAD_REFLECT : DUCOSY_PAD_ZERO;  // the decoder convs zero-pad
-    static const bool fused_sa = []() { const char* e = getenv("DUCOSY_FUSED_SPATIAL"); return e == nullptr || atoi(e) != 0; }();
-    if (c.use_cbam && !fused_sa) {   // experiment switch: the round-1 path with a separate spatial-attention conv launch
+    // DUCOSY_FUSED_SPATIAL=1 evaluates the 7x7 spatial-attention conv inside the residual pass (one launch less per block).
+    // Same-box A/B, round 2: the separate kernel wins at batch 30 (1003 vs 958 slices/s; the per-row gather of the pooled map
+    // stalls the streaming loop, and a producer-warp variant that overlapped it was slower still, 922) and at batch 1 once the
+    // forward is replayed from a CUDA graph (682 vs 636) -- so the fused form is opt-in.
+    const bool fused_sa = fused_spatial();
+    if (c.use_cbam && !fused_sa) {   // default: channel pooling, the 7x7 attention conv as a kernel of its own, residual pass
       float* sa = reinterpret_cast<float*>(base + w.sa);
       DUCOSY_TRY(ducosy_cbam_pool(P(w.y2b), scale, shift, pooled, B, H4, W4, 256, dt, st));
       DUCOSY_TRY(ducosy_cbam_spatial_conv(pooled, reinterpret_cast<const float*>(pk + L.saw[i]), sa, B, H4, W4, st));
@@ -461,9 +475,9 @@ extern "C" size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg,
 }
 extern "C" int ducosy_generator_num_launches(const ducosy_gen_config* cfg) {
   if (!cfg) return fail(DUCOSY_ERR_ARG, "generator_num_launches: null config");
-  // stem 4 (Cin = 1), 2 x (conv + finalize + apply) down, per block 2 x (conv + finalize) + apply + residual (+ channel MLP + pool;
-  // the spatial-attention conv runs inside the residual pass), 2 x (up conv + finalize) + 1 apply, output conv
-  return 16 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? 2 : 0));
+  // stem 4 (Cin = 1), 2 x (conv + finalize + apply) down, per block 2 x (conv + finalize) + apply + residual (+ channel MLP + pool
+  // + spatial-attention conv, unless that runs inside the residual pass), 2 x (up conv + finalize) + 1 apply, output conv
+  return 16 + cfg->num_residual_blocks * (6 + (cfg->use_cbam ? (fused_spatial() ? 2 : 3) : 0));
 }
 
 extern "C" int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params, int num_params,

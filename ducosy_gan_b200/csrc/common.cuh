@@ -59,8 +59,9 @@ struct PerDeviceOnce {
 // data flow is exactly that of plain stream order; what disappears is the launch gap between dependent kernels -- the
 // batch-1 forward and the one-sample-per-rank training step are chains of 100 / 3000 kernels of a few microseconds each.
 // Kernels that allocate TMEM trigger only AFTER their allocation: a dependent CTA that lands on the same SM first would
-// hold TMEM columns while waiting for this very grid.  DUCOSY_PDL=0 launches without the attribute (then both
-// instructions are no-ops).
+// hold TMEM columns while waiting for this very grid.  Without the launch attribute both instructions are no-ops, and
+// that is the DEFAULT: the attribute is set only with DUCOSY_PDL=1 (measured: it helps eager batch-1 chains and hurts the
+// two-stream paths, see pdl_enabled() in api.cu).
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void pdl_prologue() {

@@ -159,23 +159,36 @@ class DataParallelCycleGANStep(CycleGANStep):
         if self.world > 1 and self._checked_batch != real_A.shape[0] and not torch.cuda.is_current_stream_capturing():
             check_equal_shards(real_A.shape[0], self.group)
             self._checked_batch = real_A.shape[0]
+        # The three exchanges run on NCCL's own stream while the next phase computes: the discriminator losses depend on the
+        # fakes (made before any update) and on the discriminators' own weights only, so moving optimizer_G.step() behind them
+        # changes nothing (DUCOSY_DP_OVERLAP=0 restores the literal order of trainer.py:514-524).
+        import os
+        overlap = os.environ.get("DUCOSY_DP_OVERLAP", "1") != "0" and self.world > 1
         self.bucket_G.zero()
         loss_G, terms, fake_A, fake_B = self.generator_losses(real_A, real_B, masks)
         loss_G.backward()
-        self.bucket_G.all_reduce_mean(self.group)
-        self.optimizer_G.step()
+        work_G = self.bucket_G.all_reduce_mean(self.group, async_op=overlap)
+        if not overlap:
+            self.optimizer_G.step()
 
         self.bucket_D_A.zero()   # also discards what loss_G.backward() left in the discriminators (trainer.py:517)
         loss_D_A = self._disc_loss(self.D_A, real_A, fake_A)
         loss_D_A.backward()
-        self.bucket_D_A.all_reduce_mean(self.group)
-        self.optimizer_D_A.step()
+        work_A = self.bucket_D_A.all_reduce_mean(self.group, async_op=overlap)
+        if not overlap:
+            self.optimizer_D_A.step()
 
         self.bucket_D_B.zero()
         loss_D_B = self._disc_loss(self.D_B, real_B, fake_B)
         loss_D_B.backward()
-        self.bucket_D_B.all_reduce_mean(self.group)
-        self.optimizer_D_B.step()
+        work_B = self.bucket_D_B.all_reduce_mean(self.group, async_op=overlap)
+        if overlap:
+            for work, opt in ((work_G, self.optimizer_G), (work_A, self.optimizer_D_A), (work_B, self.optimizer_D_B)):
+                if work is not None:
+                    work.wait()
+                opt.step()
+        else:
+            self.optimizer_D_B.step()
         if self.world == 1:
             out = {k: v.detach() for k, v in terms.items()}
             out.update(G=loss_G.detach(), D_A=loss_D_A.detach(), D_B=loss_D_B.detach())

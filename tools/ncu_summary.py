@@ -47,5 +47,43 @@ def kernel(path):
             print(f"{k:75s} [{units[i]}]  " + "  ".join(r[i] for r in rows[2:]))
 
 
+def rawcsv(path):
+    """Table of the first launch of every distinct kernel in an exported raw page (ncu -i X.ncu-rep --page raw --csv)."""
+    rows = list(csv.reader(open(path)))
+    hdr, units = rows[0], rows[1]
+    col = lambda k: hdr.index(k) if k in hdr else None
+    ki = col("Kernel Name")
+    want = [("gpu__time_duration.sum", "us"), ("dram__bytes_read.sum", "MB read"), ("dram__bytes_write.sum", "MB written"),
+            ("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "dram %"), ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "L2 %"),
+            ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active", "tensor % active"),
+            ("sm__warps_active.avg.pct_of_peak_sustained_active", "occupancy %"), ("launch__registers_per_thread", "regs"),
+            ("launch__grid_size", "grid")]
+
+    def val(r, k):
+        i = col(k)
+        if i is None or r[i] == "":
+            return float("nan")
+        v = float(r[i].replace(",", ""))
+        u = units[i]
+        if k.startswith("gpu__time"):
+            return v / 1e3 if u.startswith("n") else (v * 1e3 if u.startswith("m") else v)
+        if "bytes" in k:
+            return v * {"byte": 1e-6, "Kbyte": 1e-3, "Mbyte": 1.0, "Gbyte": 1e3}.get(u, 1e-6)
+        return v
+
+    print("# first launch of every distinct (kernel, grid) in " + path.split("/")[-1] + " -- ncu --set full --clock-control none, one 30-slice chunk")
+    print("# " + " | ".join(f"{n:>14s}" for _, n in want) + " | TB/s (read+write) | kernel")
+    seen = set()
+    for r in rows[2:]:
+        name = re.sub(r"\(.*", "", r[ki]).replace("ducosy::<unnamed>::", "").replace("void ", "")
+        key = (name, r[col("launch__grid_size")] if col("launch__grid_size") is not None else "")
+        if key in seen:
+            continue
+        seen.add(key)
+        vals = [val(r, k) for k, _ in want]
+        tbs = (vals[1] + vals[2]) / vals[0] if vals[0] else float("nan")
+        print("  " + " | ".join(f"{v:14.1f}" for v in vals) + f" | {tbs:17.2f} | {name}")
+
+
 if __name__ == "__main__":
-    {"launches": launches, "kernel": kernel}[sys.argv[1]](sys.argv[2])
+    {"launches": launches, "kernel": kernel, "rawcsv": rawcsv}[sys.argv[1]](sys.argv[2])
