@@ -207,6 +207,9 @@ def train_metric(device, rank, world, steps, warmup=2, per_gpu_batch=None):
     ms = float(ms.item())
     skipped = step.optimizer_G.skipped_steps()
     graphed.close()      # the graph holds captured NCCL collectives: it must be gone before the process group is torn down
+    breakdown = None
+    if world > 1 and per_gpu_batch is None:
+        breakdown = guarded_breakdown(step, host, device, ms)
     tflop = (6 * B * 451.11 * 3 + 6 * B * 13.04 * 3) / 1e3      # nominal conv work, backward = 2x forward
     return {"metric": "cyclegan_train_steps_per_s", "value": 1e3 / ms, "unit": "steps/s", "ms_per_step": ms, "steps": steps,
             "samples_per_s": B * 1e3 / ms, "warmup": max(warmup, 2) + 1, "global_batch": B,
@@ -215,9 +218,62 @@ def train_metric(device, rank, world, steps, warmup=2, per_gpu_batch=None):
             "config": "G_A2B/G_B2A (Cin 3, 9 CBAM blocks) + D_A/D_B, 512x512, all 9 loss terms, 3 fused Adam steps; "
                       + (f"batch 8 sharded x{world}" if per_gpu_batch is None else f"{per_gpu_batch} samples per GPU x{world}")
                       + (", NCCL gradient all-reduce" if world > 1 else ""),
-            "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": 4,
+            "h2d_bytes_per_step": sum(t.numel() * 4 for t in host), "d2h_bytes_per_step": 4, "breakdown": breakdown,
             "nominal_tflop_per_step": tflop, "achieved_tflops_nominal": tflop / ms * 1e3 / world,
             "frac_of_sustained_peak_per_gpu": tflop / ms * 1e3 / world / peaks()["tf_sustained"]}
+
+
+def guarded_breakdown(step, host, device, step_ms):
+    """Where a data-parallel step's time goes (outside the timed region, max over ranks): (a) the step's collectives alone,
+    back to back -- three gradient all-reduces on the flat buckets, three all-gathers of the batch-global loss inputs, the
+    11-float logged-loss all-reduce; (b) the SAME local batch through the same kernels with every exchange removed (a second
+    graph capture of the step with the collectives stubbed out).  step - (b) is what the exchange really costs inside the
+    graph (latency, rank skew); (b) against the single-GPU step / N is the efficiency lost to the small per-rank batch."""
+    import torch.distributed as dist
+    from ducosy_gan_b200.data_parallel import GraphedCycleGANStep
+    try:
+        def timed(fn, iters):
+            for _ in range(2):
+                fn()
+            dist.barrier(device_ids=[device.index])
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(iters):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            t = torch.tensor([e0.elapsed_time(e1) / iters], device=device)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return float(t.item())
+
+        b = host[0].shape[0]
+        img = torch.zeros((b, 1, 512, 512), device=device)
+        gathered = torch.empty((b * dist.get_world_size(), 1, 512, 512), device=device)
+        vec = torch.zeros(11, device=device)
+
+        def collectives():
+            for _ in range(3):
+                dist.all_gather_into_tensor(gathered, img)
+            for bk in (step.bucket_G, step.bucket_D_A, step.bucket_D_B):
+                bk.all_reduce_mean(step.group)
+            dist.all_reduce(vec, op=dist.ReduceOp.AVG)
+
+        coll = timed(collectives, 10)
+        world_saved = step.world
+        step.world = 1                                    # batch-global terms on the local batch, plain (unscaled) loss mix
+        for bk in (step.bucket_G, step.bucket_D_A, step.bucket_D_B):
+            bk.all_reduce_mean = lambda *a, **k: None     # instance attribute shadows the method: no exchange
+        local = GraphedCycleGANStep(step, *(t.to(device) for t in host), warmup=2)
+        alone = timed(lambda: local(*host)["G"].item(), 10)
+        local.close()
+        for bk in (step.bucket_G, step.bucket_D_A, step.bucket_D_B):
+            del bk.all_reduce_mean
+        step.world = world_saved
+        return {"step_ms": step_ms, "same_local_batch_without_exchange_ms": alone, "collectives_alone_ms": coll,
+                "gradient_bytes_all_reduced": int(sum(bk.flat.numel() for bk in (step.bucket_G, step.bucket_D_A, step.bucket_D_B)) * 4)}
+    except Exception as e:  # a measurement aid must never take the bench line down
+        return {"error": repr(e)[:300]}
 
 
 def train_checks(device, rank, world):

@@ -5,6 +5,7 @@
 // fp32 parameter / image gradients leave with the true scale.
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 #include "common.cuh"
 #include "input_fn.cuh"
@@ -25,15 +26,20 @@ __device__ __forceinline__ int reflect_sources(int i, int n, int pad, int* u) {
 
 // ------------------------------------------------------------------ output conv backward (modules/model.py:112-113)
 // out = tanh(v), v = conv7x7(reflect_pad3(a)) + bias.  dv = dout * (1 - out^2); db = sum dv.
+// dvh (optional): the same map times the power-of-two gradient scale gs[0], rounded to T -- the A operand of the tensor-core
+// input-gradient kernel below (|dv| <= |dout| and gs[0] * max|dout| is in [1, 2), so nothing overflows or goes subnormal).
+template <typename T>
 __global__ void __launch_bounds__(256)
-out_tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dv,
-                    float* __restrict__ partial, long long n) {
+out_tanh_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ out, float* __restrict__ dv, T* __restrict__ dvh,
+                    const float* __restrict__ gs, float* __restrict__ partial, long long n) {
   pdl_prologue();
   __shared__ float red[8];
   float acc = 0.f;
+  const float sc = dvh != nullptr ? gs[0] : 0.f;
   for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
     const float o = out[i], g = dout[i] * (1.f - o * o);
     dv[i] = g;
+    if (dvh != nullptr) dvh[i] = Cvt<T>::from_f(g * sc);
     acc += g;
   }
 #pragma unroll
@@ -152,6 +158,166 @@ out_conv_dgrad_kernel(const float* __restrict__ dv, const float* __restrict__ w,
   }
 }
 
+// The 4-pixel frame of the image (where ReflectionPad2d(3) folds mirrored positions onto a pixel, or a tap leaves the image)
+// after out_conv_dgrad_mma_kernel wrote the zero-extended sums everywhere: thread = (frame pixel, 8 channels), overwrites da.
+// Frame pixels per sample: rows 0..3 and H-4..H-1 in full (8 W), columns 0..3 and W-4..W-1 of the other rows (8 (H - 8)).
+template <typename T>
+__global__ void __launch_bounds__(256)
+out_conv_dgrad_border_kernel(const float* __restrict__ dv, const float* __restrict__ w, T* __restrict__ da,
+                             const float* __restrict__ gs, int B, int H, int W) {
+  pdl_prologue();
+  __shared__ __align__(16) float ws[49][64];
+  for (int i = threadIdx.x; i < 49 * 64; i += 256) ws[i % 49][i / 49] = w[i];   // w is [c][tap]
+  __syncthreads();
+  const int per_sample = 8 * W + 8 * (H - 8);
+  const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (item >= (long long)B * per_sample * 8) return;
+  const int c8 = int(item & 7);
+  const long long pid = item >> 3;
+  const int b = int(pid / per_sample), idx = int(pid - (long long)b * per_sample);
+  int y, x;
+  if (idx < 4 * W) { y = idx / W; x = idx - y * W; }
+  else if (idx < 8 * W) { const int k = idx - 4 * W; y = H - 4 + k / W; x = k % W; }
+  else { const int k = idx - 8 * W, j = k & 7; y = 4 + (k >> 3); x = j < 4 ? j : W - 8 + j; }
+  const float* dvb = dv + (long long)b * H * W;
+  const float sc = gs[0];
+  int us[3], vs[3];
+  const int nu = reflect_sources(y, H, 3, us), nv = reflect_sources(x, W, 3, vs);
+  float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  for (int iu = 0; iu < nu; ++iu)
+    for (int iv = 0; iv < nv; ++iv) {
+      const int u = us[iu], v = vs[iv];
+      for (int r = 0; r < 7; ++r) {
+        const int yo = u - r;
+        if (yo < 0 || yo >= H) continue;
+        for (int s2 = 0; s2 < 7; ++s2) {
+          const int xo = v - s2;
+          if (xo < 0 || xo >= W) continue;
+          const float gq = __ldg(dvb + (long long)yo * W + xo);
+          const float4 w0 = *reinterpret_cast<const float4*>(&ws[r * 7 + s2][c8 * 8]);
+          const float4 w1 = *reinterpret_cast<const float4*>(&ws[r * 7 + s2][c8 * 8 + 4]);
+          acc[0] += gq * w0.x; acc[1] += gq * w0.y; acc[2] += gq * w0.z; acc[3] += gq * w0.w;
+          acc[4] += gq * w1.x; acc[5] += gq * w1.y; acc[6] += gq * w1.z; acc[7] += gq * w1.w;
+        }
+      }
+    }
+  uint4 o;
+  o.x = Cvt<T>::pack2(acc[0] * sc, acc[1] * sc);
+  o.y = Cvt<T>::pack2(acc[2] * sc, acc[3] * sc);
+  o.z = Cvt<T>::pack2(acc[4] * sc, acc[5] * sc);
+  o.w = Cvt<T>::pack2(acc[6] * sc, acc[7] * sc);
+  *reinterpret_cast<uint4*>(da + (((long long)b * H + y) * W + x) * 64 + c8 * 8) = o;
+}
+
+// ---- the same input gradient on warp-level tensor cores (interior + zero-extended edges; the 4-pixel frame that the reflection
+// touches is then overwritten by out_conv_dgrad_border_kernel above).  GEMM view per image row:
+//     da[x][c] = sum_k A[x][k] * Bw[k][c],   A[x][k = r*7 + s] = dvh[y + 3 - r][x + 3 - s]  (Toeplitz, zero outside the image),
+//     Bw[k][c] = w[c][r][s],  K = 49 padded to 64
+// A warp owns 16 consecutive pixels of a row per step (m16n8k16: 8 channel tiles x 4 k steps = 32 MMAs); its A fragments are 2-byte
+// gathers from a shared-memory tile of dvh (rows y-3..y+3, 70 columns), the 64 B-fragment registers hold the whole filter for
+// the lifetime of the (persistent) CTA; results go through a per-warp staging tile so that every pixel is one 128-byte store.
+template <typename T> struct GMma;
+template <> struct GMma<__half> {
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+template <> struct GMma<__nv_bfloat16> {
+  static __device__ __forceinline__ void mma(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+  }
+};
+
+constexpr int kDgRows = 4, kDgCols = 64;                 // output tile of a 4-warp CTA: warp w <-> row y0 + w, 4 steps of 16 pixels
+constexpr int kDgPitch = kDgCols + 6 + 2;                // staged dvh columns x0-3 .. x0+66, padded to 72
+constexpr int kDgTileRows = kDgRows + 6;
+template <typename T>
+__global__ void __launch_bounds__(128)
+out_conv_dgrad_mma_kernel(const T* __restrict__ dvh, const float* __restrict__ w, T* __restrict__ da, int B, int H, int W) {
+  pdl_prologue();
+  __shared__ __align__(16) unsigned short tile[kDgTileRows * kDgPitch + 8];   // + a zero slot for the padded taps (k >= 49)
+  __shared__ __align__(16) T stage[kDgRows][16][64 + 8];                      // per warp: 16 pixels x 64 channels (+ 16-byte pad)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  constexpr int kZero = kDgTileRows * kDgPitch;
+  // B fragments: b0 = (k = 16ks + 2t, +1; n = 8j + g), b1 = (k + 8, + 9)
+  uint32_t bf[4][8][2];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const int k0 = 16 * ks + 2 * t + 8 * h, c = 8 * j + g;
+        const float v0 = k0 < 49 ? __ldg(w + c * 49 + k0) : 0.f, v1 = k0 + 1 < 49 ? __ldg(w + c * 49 + k0 + 1) : 0.f;
+        bf[ks][j][h] = Cvt<T>::pack2(v0, v1);
+      }
+  // tile offsets of this thread's A columns: k -> (6 - r) * pitch + (6 - s) relative to (row w, pixel m) of the staged tile
+  int off[4][4];
+#pragma unroll
+  for (int ks = 0; ks < 4; ++ks)
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int k = 16 * ks + 2 * t + (q & 1) + 8 * (q >> 1);
+      off[ks][q] = k < 49 ? (6 - k / 7) * kDgPitch + (6 - k % 7) : -1;
+    }
+  if (threadIdx.x < 8) tile[kZero + threadIdx.x] = 0;
+  const int tiles_x = W / kDgCols, tiles_y = H / kDgRows;
+  const int total = B * tiles_y * tiles_x;
+  for (int tl = blockIdx.x; tl < total; tl += gridDim.x) {
+    const int tx = tl % tiles_x, ty = (tl / tiles_x) % tiles_y, b = tl / (tiles_x * tiles_y);
+    const int y0 = ty * kDgRows, x0 = tx * kDgCols;
+    __syncthreads();                                   // the previous tile's readers are done
+    for (int i = threadIdx.x; i < kDgTileRows * kDgPitch; i += 128) {
+      const int rr = i / kDgPitch, cc = i - rr * kDgPitch;
+      const int yy = y0 - 3 + rr, xx = x0 - 3 + cc;
+      unsigned short v = 0;
+      if (yy >= 0 && yy < H && xx >= 0 && xx < W && cc < kDgCols + 6)
+        v = reinterpret_cast<const unsigned short*>(dvh)[((long long)b * H + yy) * W + xx];
+      tile[i] = v;
+    }
+    __syncthreads();
+#pragma unroll 1
+    for (int mt = 0; mt < kDgCols / 16; ++mt) {
+      float acc[8][4];
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[j][q] = 0.f;
+      const int base_a = warp * kDgPitch + mt * 16 + g;   // (row w, pixel g); pixel g + 8 is 8 columns further
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks) {
+        uint32_t a[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {                      // h: k-half (columns 2t.. / 2t+8..)
+          const int o0 = off[ks][2 * h], o1 = off[ks][2 * h + 1];
+          const uint32_t lo_g = tile[o0 >= 0 ? base_a + o0 : kZero], hi_g = tile[o1 >= 0 ? base_a + o1 : kZero];
+          const uint32_t lo_8 = tile[o0 >= 0 ? base_a + 8 + o0 : kZero], hi_8 = tile[o1 >= 0 ? base_a + 8 + o1 : kZero];
+          a[2 * h] = lo_g | (hi_g << 16);                  // a0 / a2: row g
+          a[2 * h + 1] = lo_8 | (hi_8 << 16);              // a1 / a3: row g + 8
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) GMma<T>::mma(acc[j], a[0], a[1], a[2], a[3], bf[ks][j][0], bf[ks][j][1]);
+      }
+      // D fragment: c0,c1 = (pixel g, channels 8j + 2t, +1), c2,c3 = (pixel g + 8, ...)
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        *reinterpret_cast<uint32_t*>(&stage[warp][g][8 * j + 2 * t]) = Cvt<T>::pack2(acc[j][0], acc[j][1]);
+        *reinterpret_cast<uint32_t*>(&stage[warp][g + 8][8 * j + 2 * t]) = Cvt<T>::pack2(acc[j][2], acc[j][3]);
+      }
+      __syncwarp();
+      T* dst = da + (((long long)b * H + y0 + warp) * W + x0 + mt * 16) * 64;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {                        // 16 pixels x 8 chunks of 16 bytes = 128 chunks, 4 per lane
+        const int ch = i * 32 + lane, px = ch >> 3, c8 = ch & 7;
+        *reinterpret_cast<uint4*>(dst + px * 64 + c8 * 8) = *reinterpret_cast<const uint4*>(&stage[warp][px][c8 * 8]);
+      }
+      __syncwarp();
+    }
+  }
+}
+
 // dw[c][r][s] = sum over padded pixels (u,v) of in_pad[u][v][c] * dv[u-r][v-s]   (dv zero outside the image)
 // block = 448 threads = 64 channels x 7 filter rows; one padded row per iteration, the 7 dv rows it meets staged in
 // shared memory with zero borders.  A thread keeps the 7 dv values its filter row needs for the current pixel in a
@@ -195,13 +361,146 @@ out_conv_wgrad_kernel(const T* __restrict__ in_pad, const float* __restrict__ dv
   for (int s = 0; s < 7; ++s) dst[s] = acc[s];
 }
 
-__global__ void out_conv_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw) {
+// ---- the same weight gradient on warp-level tensor cores.  GEMM view per padded row u, 16 padded pixels v0..v0+15 per step:
+//     D[c][n] += sum_k A[c][k] * Bm[k][n],   A[c][k] = in_pad[u][v0 + k][c],   Bm[k][n = r*7 + s] = dvh[u - r][v0 + k - s]
+// (M = 64 channels = 4 m-tiles, N = 49 taps padded to 56 = 7 n-tiles, K = pixels).  in_pad is pixel-major, so the A fragments
+// come out of ldmatrix.trans on a per-warp staging tile filled with cp.async (double-buffered, no CTA barrier in the pixel
+// loop); the Toeplitz B fragments are aligned 32-bit reads from two copies of the 7 staged dvh rows, the second shifted by one
+// element so that the (k, k+1) pair of every tap is word-aligned.  Every warp walks its own pixel steps with all 28
+// accumulator tiles in registers; the four warps' partial sums are added in shared memory and each CTA writes one
+// [64][49] partial, in units of gs[0] (dvh is the scaled 16-bit map), which out_conv_wgrad_reduce_kernel folds back.
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem, bool valid) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  const int bytes = valid ? 16 : 0;   // src-size 0: the 16 bytes are zero-filled
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(s), "l"(gmem), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+__device__ __forceinline__ void ldmatrix_x4_trans(uint32_t (&r)[4], const void* smem) {
+  const uint32_t s = static_cast<uint32_t>(__cvta_generic_to_shared(smem));
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
+}
+
+constexpr int kWgA = 64 + 8;            // elements per staged pixel (16-byte pad: conflict-free ldmatrix rows)
+template <typename T>
+__global__ void __launch_bounds__(128)
+out_conv_wgrad_mma_kernel(const T* __restrict__ in_pad, const T* __restrict__ dvh, float* __restrict__ partial, int B, int H, int W) {
+  pdl_prologue();
+  extern __shared__ __align__(16) unsigned char wg_smem[];
+  const int Wp = W + 6, Hp = H + 6, pitch = ((W + 12 + 16 + 7) / 8) * 8;   // staged dvh row: 6 zeros | W values | zeros (steps run past Wp)
+  unsigned short* rows0 = reinterpret_cast<unsigned short*>(wg_smem);      // [7][pitch]      rows0[r][j] = dvh[u - r][j - 6]
+  unsigned short* rows1 = rows0 + 7 * pitch;                               // [7][pitch]      rows1[r][j] = rows0[r][j + 1]
+  T* abuf = reinterpret_cast<T*>(rows1 + 7 * pitch);                       // [4 warps][2][16][kWgA]
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
+  T* my_a = abuf + warp * 2 * 16 * kWgA;
+  float acc[4][7][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 7; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) acc[i][j][q] = 0.f;
+  // tap of this thread's B column in n-tile j: n = 8j + g -> (r, s); pair (k, k+1) starts at rows[slot(u - r)][v0 + k - s + 6]
+  int tap_r[7], tap_c[7];
+#pragma unroll
+  for (int j = 0; j < 7; ++j) {
+    const int n = 8 * j + g;
+    tap_r[j] = n < 49 ? n / 7 : -1;
+    tap_c[j] = 6 - (n % 7);
+  }
+  const int steps = (Wp + 15) / 16;
+  // a CTA walks a contiguous range of padded rows, so the 7 staged dvh rows form a ring: image row yo lives in slot (yo + 7) % 7
+  // and moving down one padded row replaces exactly one slot
+  const int rows_total = B * Hp, per_cta = (rows_total + gridDim.x - 1) / gridDim.x;
+  const int row_lo = blockIdx.x * per_cta, row_hi = min(rows_total, row_lo + per_cta);
+  int have_b = -1, have_u = -100;
+  for (int row = row_lo; row < row_hi; ++row) {
+    const int b = row / Hp, u = row - b * Hp;
+    const bool slide = b == have_b && u == have_u + 1;
+    have_b = b;
+    have_u = u;
+    __syncthreads();                                     // every warp is done with the previous row's use of the ring
+    for (int i = threadIdx.x; i < (slide ? 1 : 7) * pitch; i += 128) {
+      const int rr = slide ? 0 : i / pitch, j = i - (slide ? 0 : rr * pitch), yo = u - rr;
+      auto at = [&](int jj) -> unsigned short {
+        const int xo = jj - 6;
+        return (yo >= 0 && yo < H && xo >= 0 && xo < W) ? reinterpret_cast<const unsigned short*>(dvh)[((long long)b * H + yo) * W + xo] : (unsigned short)0;
+      };
+      const int slot = (yo + 14) % 7;
+      rows0[slot * pitch + j] = at(j);
+      rows1[slot * pitch + j] = at(j + 1);
+    }
+    __syncthreads();
+    int boff[7];
+#pragma unroll
+    for (int j = 0; j < 7; ++j) boff[j] = tap_r[j] >= 0 ? ((u - tap_r[j] + 14) % 7) * pitch + tap_c[j] : -1;
+    const T* src = in_pad + (long long)row * Wp * 64;
+    auto stage = [&](int st, int buf) {                  // 16 pixels x 128 bytes = 128 chunks of 16 bytes, 4 per lane
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int ch = i * 32 + lane, px = ch >> 3, c8 = ch & 7, v = st * 16 + px;
+        cp_async16(my_a + (buf * 16 + px) * kWgA + c8 * 8, src + (long long)(v < Wp ? v : 0) * 64 + c8 * 8, v < Wp);
+      }
+      cp_async_commit();
+    };
+    int buf = 0;
+    if (warp < steps) stage(warp, 0);
+    for (int st = warp; st < steps; st += 4) {
+      if (st + 4 < steps) { stage(st + 4, buf ^ 1); cp_async_wait<1>(); } else { cp_async_wait<0>(); }
+      __syncwarp();
+      const int v0 = st * 16;
+      uint32_t bfr[7][2];
+#pragma unroll
+      for (int j = 0; j < 7; ++j) {
+        if (boff[j] < 0) { bfr[j][0] = 0; bfr[j][1] = 0; continue; }
+        const int e = boff[j] + v0 + 2 * t;              // element index of (k = 2t) in rows0; word-aligned in rows0 or rows1
+        const unsigned short* base = (e & 1) ? rows1 + (e - 1) : rows0 + e;
+        bfr[j][0] = *reinterpret_cast<const uint32_t*>(base);
+        bfr[j][1] = *reinterpret_cast<const uint32_t*>(base + 8);
+      }
+      const T* a_tile = my_a + buf * 16 * kWgA;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        // matrices: (px 0-7, ch 16i..+7), (px 0-7, ch 16i+8..), (px 8-15, ch 16i..+7), (px 8-15, ch 16i+8..); lane l -> row l%8 of matrix l/8
+        uint32_t a[4];
+        const int mtx = lane >> 3, rr = lane & 7;
+        ldmatrix_x4_trans(a, a_tile + ((mtx >> 1) * 8 + rr) * kWgA + 16 * i + (mtx & 1) * 8);
+#pragma unroll
+        for (int j = 0; j < 7; ++j) GMma<T>::mma(acc[i][j], a[0], a[1], a[2], a[3], bfr[j][0], bfr[j][1]);
+      }
+      __syncwarp();
+      buf ^= 1;
+    }
+  }
+  // add the four warps' partial sums (fixed order) and write this CTA's [64][49] partial
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(wg_smem);        // [64][56] floats = 14 KB, over the dvh tiles
+  for (int wsel = 0; wsel < 4; ++wsel) {
+    if (warp == wsel) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 7; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int c = 16 * i + g + 8 * (q >> 1), n = 8 * j + 2 * t + (q & 1);
+            if (wsel == 0) red[c * 56 + n] = acc[i][j][q]; else red[c * 56 + n] += acc[i][j][q];
+          }
+    }
+    __syncthreads();
+  }
+  float* dst = partial + (long long)blockIdx.x * (64 * 49);
+  for (int i = threadIdx.x; i < 64 * 49; i += 128) dst[i] = red[(i / 49) * 56 + i % 49];
+}
+
+// gs != nullptr: the partials are in units of gs[0] (tensor-core path), gs[1] = 1 / gs[0] (a power of two: exact)
+__global__ void out_conv_wgrad_reduce_kernel(const float* __restrict__ partial, int blocks, float* __restrict__ dw, const float* __restrict__ gs) {
   pdl_prologue();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= 64 * 49) return;
   float s = 0.f;
   for (int k = 0; k < blocks; ++k) s += partial[(long long)k * (64 * 49) + i];
-  dw[i] = s;
+  dw[i] = gs != nullptr ? s * gs[1] : s;
 }
 
 // ------------------------------------------------------------------ stem backward (modules/model.py:90-92)
@@ -627,7 +926,8 @@ constexpr int kOutWgradBlocks = 592;
 }
 
 extern "C" size_t ducosy_out_conv_backward_scratch_bytes(int B, int H, int W) {
-  return (size_t(B) * H * W + kTanhBlocks + size_t(kOutWgradBlocks) * 64 * 49) * sizeof(float);
+  // dv fp32 + partial sums + the scaled 16-bit copy of dv (rounded up to whole floats)
+  return (size_t(B) * H * W + kTanhBlocks + size_t(kOutWgradBlocks) * 64 * 49 + (size_t(B) * H * W + 1) / 2 + 4) * sizeof(float);
 }
 
 extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, const void* in_pad, const float* w, void* da,
@@ -642,18 +942,47 @@ extern "C" int ducosy_out_conv_backward(const float* dout, const float* out, con
   float* dv = scratch;
   float* tpart = dv + n;
   float* wpart = tpart + kTanhBlocks;
-  pdl(out_tanh_bwd_kernel, kTanhBlocks, 256, 0, st)(dout, out, dv, tpart, n);
+  // the tensor-core input gradient needs whole 4 x 64 tiles; other shapes (tests) stay on the CUDA-core kernel
+  static const bool mma_env = []() { const char* e = getenv("DUCOSY_OUTCONV_DGRAD_MMA"); return e == nullptr || atoi(e) != 0; }();
+  const bool use_mma = mma_env && H % kDgRows == 0 && W % kDgCols == 0;
+  void* dvh = wpart + size_t(kOutWgradBlocks) * 64 * 49;
+  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_tanh_bwd_kernel<T>, kTanhBlocks, 256, 0, st)(dout, out, dv, use_mma ? static_cast<T*>(dvh) : nullptr,
+                                                                                       gs, tpart, n)));
   DUCOSY_TRY(check_launch("out_tanh_bwd_kernel"));
   pdl(sum_partials_kernel, 1, 256, 0, st)(tpart, kTanhBlocks, db);
   DUCOSY_TRY(check_launch("sum_partials_kernel"));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_dgrad_kernel<T>, grid_items(n * 2, 256), 256, 0, st)(dv, w, static_cast<T*>(da), gs, B, H, W)));
-  DUCOSY_TRY(check_launch("out_conv_dgrad_kernel"));
+  if (use_mma) {
+    const int tiles = B * (H / kDgRows) * (W / kDgCols), cap = (num_sms() > 0 ? num_sms() : 148) * 3;   // 138 registers: 3 CTAs per SM
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_dgrad_mma_kernel<T>, tiles < cap ? tiles : cap, 128, 0, st)(
+                                        static_cast<const T*>(dvh), w, static_cast<T*>(da), B, H, W)));
+    DUCOSY_TRY(check_launch("out_conv_dgrad_mma_kernel"));
+  }
+  if (use_mma) {
+    const long long items = (long long)B * (8 * W + 8 * (H - 8)) * 8;
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_dgrad_border_kernel<T>, grid_items(items, 256), 256, 0, st)(dv, w, static_cast<T*>(da), gs, B, H, W)));
+    DUCOSY_TRY(check_launch("out_conv_dgrad_border_kernel"));
+  } else {
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_dgrad_kernel<T>, grid_items(n * 2, 256), 256, 0, st)(dv, w, static_cast<T*>(da), gs, B, H, W)));
+    DUCOSY_TRY(check_launch("out_conv_dgrad_kernel"));
+  }
+  static const bool wmma_env = []() { const char* e = getenv("DUCOSY_OUTCONV_WGRAD_MMA"); return e == nullptr || atoi(e) != 0; }();
+  if (use_mma && wmma_env) {
+    const int pitch = ((W + 12 + 16 + 7) / 8) * 8;
+    const size_t smem_mma = size_t(2) * 7 * pitch * 2 + size_t(4) * 2 * 16 * kWgA * 2;
+    DUCOSY_CHECK(smem_mma <= 48 * 1024 && smem_mma >= size_t(64) * 56 * 4, DUCOSY_ERR_SHAPE, "out_conv_backward: W unsupported (%d)", W);
+    const int blocks = min((num_sms() > 0 ? num_sms() : 148) * 3, min(kOutWgradBlocks, B * (H + 6)));
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_wgrad_mma_kernel<T>, blocks, 128, smem_mma, st)(static_cast<const T*>(in_pad), static_cast<const T*>(dvh),
+                                                                                             wpart, B, H, W)));
+    DUCOSY_TRY(check_launch("out_conv_wgrad_mma_kernel"));
+    pdl(out_conv_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st)(wpart, blocks, dw, gs);
+    return check_launch("out_conv_wgrad_reduce_kernel");
+  }
   const int blocks = min(kOutWgradBlocks, B * (H + 6));
   const size_t smem = size_t(7) * (W + 12) * sizeof(float);
   DUCOSY_CHECK(smem <= 48 * 1024, DUCOSY_ERR_SHAPE, "out_conv_backward: W too large (%d)", W);
   DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(out_conv_wgrad_kernel<T>, blocks, kOutWgradThreads, smem, st)(static_cast<const T*>(in_pad), dv, wpart, B, H, W)));
   DUCOSY_TRY(check_launch("out_conv_wgrad_kernel"));
-  pdl(out_conv_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st)(wpart, blocks, dw);
+  pdl(out_conv_wgrad_reduce_kernel, (64 * 49 + 255) / 256, 256, 0, st)(wpart, blocks, dw, static_cast<const float*>(nullptr));
   return check_launch("out_conv_wgrad_reduce_kernel");
 }
 

@@ -28,9 +28,12 @@ def _rel(got, ref):
     return ((got - ref).norm() / ref.norm().clamp_min(1e-30)).item()
 
 
-@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 64, 128)])
+@pytest.mark.parametrize("shape", [(2, 16, 24), (1, 64, 128), (2, 32, 192), (1, 128, 512)])
 def test_out_conv_backward_matches_autograd(ops, shape):
-    """modules/model.py:112-113.  16-bit activations, fp32 everything else: 2e-3 relative (da is rounded to 16 bit)."""
+    """modules/model.py:112-113.  16-bit activations; da is rounded to 16 bit: 2e-3 relative.  Shapes made of whole 4 x 64 pixel
+    tiles run the tensor-core kernels (out_conv_dgrad_mma / out_conv_wgrad_mma, gen_bwd.cu), whose second operand is the
+    16-bit scaled copy of dv -- the same 16-bit gradient maps every other weight gradient of the path is computed from
+    (2e-3 - 4e-3 gates) -- so dw is held to 1e-3 there and to 3e-4 on the all-fp32 CUDA-core path (the 16 x 24 case)."""
     B, H, W = shape
     dtype = torch.float16
     a = F.relu(_rand((B, 64, H, W), 201)).to(dtype)
@@ -47,7 +50,8 @@ def test_out_conv_backward_matches_autograd(ops, shape):
     da, dw, db = ops.out_conv_backward(dout.cuda(), out.detach(), in_pad, w.cuda(), gs)
     got_da = da.float().permute(0, 3, 1, 2) * gs[1]
     assert _rel(got_da, ar.grad) < 2e-3, _rel(got_da, ar.grad)
-    assert _rel(dw, wr.grad) < 3e-4, _rel(dw, wr.grad)
+    print(f"out conv backward {shape}: da rel {_rel(got_da, ar.grad):.2e}  dw rel {_rel(dw, wr.grad):.2e}")
+    assert _rel(dw, wr.grad) < (1e-3 if H % 4 == 0 and W % 64 == 0 else 3e-4), _rel(dw, wr.grad)
     assert abs(db.item() - br.grad.item()) <= 1e-4 * abs(br.grad.item()) + 1e-12
 
 
