@@ -84,6 +84,7 @@ SIGNATURES = {
     "ducosy_conv2d_wgrad_nhwc_oihw": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_in_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ducosy_in_backward_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
+    "ducosy_in_backward_pad_folded": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_dgrad_s2_weight": (_i, [_p, _p, _i, _i, _i, _i, _p]),
     "ducosy_convs2_dgrad_nhwc": (_i, [_p, _p, _p, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_pack_dgrad_s1_weight": (_i, [_p, _p, _i, _i, _i, _p]),

@@ -64,10 +64,40 @@ __global__ void grad_scale_finalize_kernel(float* __restrict__ gs) {
 //   dy = rstd * (g - mean(g) - n * mean(g*n))          (per sample and channel, means over H*W)
 // pass 1: per-block partial sums [B][blocks][2][C];  pass 2 (in_bwd_finalize): fixed-order sum -> [B][2][C];
 // pass 3: dy written 16-bit into a zero-padded buffer.
+// kFold: `da` is not the gradient map itself but the gradient w.r.t. the map padded by ONE pixel, [B][H+2][W+2][C] (what the
+// 3x3 dgrad convolution writes): the padding adjoint of pad_fold_kernel is applied while loading -- the interior value plus, for
+// ReflectionPad2d, the border rows / columns that mirror onto source rows 1, H-2 and columns 1, W-2 (zero padding: the border
+// is dropped) -- so the folded map never makes its own round trip through HBM.  The fold is summed in fp32 in a fixed order;
+// the reduce and the apply pass see the same values.
 template <typename T>
+__device__ __forceinline__ void fold_extras(const uint4* __restrict__ padb /* sample base + c8 */, int y, int x, int H, int W, int cv,
+                                            float (&f)[8]) {
+  const int ry = y == 1 ? 0 : (y == H - 2 ? H + 1 : -1), cx = x == 1 ? 0 : (x == W - 2 ? W + 1 : -1);
+  auto add = [&](int r, int c) {
+    float t[8];
+    const uint4 v = padb[(size_t(r) * (W + 2) + c) * cv];
+    const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float2 q = Cvt<T>::unpack2(w4[k]);
+      t[2 * k] = q.x;
+      t[2 * k + 1] = q.y;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) f[k] += t[k];
+  };
+  if (cx >= 0) add(y + 1, cx);
+  if (ry >= 0) {
+    add(ry, x + 1);
+    if (cx >= 0) add(ry, cx);
+  }
+}
+
+template <typename T, bool kFold>
 __global__ void __launch_bounds__(256)
 in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
-                     const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block) {
+                     const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block,
+                     int H, int W, int fold_mode) {
   pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C] with rows = 256 / (C/8)
   const int cv = C / 8, c8 = threadIdx.x % cv, prow = threadIdx.x / cv, rows = 256 / cv;
@@ -81,24 +111,41 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
-  const uint4* dav = reinterpret_cast<const uint4*>(da) + (size_t(b) * HW) * cv + c8;
+  const uint4* dav = reinterpret_cast<const uint4*>(da) + (kFold ? size_t(b) * (H + 2) * (W + 2) : size_t(b) * HW) * cv + c8;
   const uint4* yv = reinterpret_cast<const uint4*>(y) + (size_t(b) * HW) * cv + c8;
   constexpr int kILP = 4;   // 8 independent 16-byte loads in flight per thread
   for (int pb = p0 + prow; pb < p1; pb += rows * kILP) {
     uint4 a[kILP], v[kILP];
+    int py[kILP], px[kILP];
 #pragma unroll
     for (int u = 0; u < kILP; ++u) {
       const int p = pb + u * rows;
       const bool ok = p < p1;
-      a[u] = ok ? dav[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
+      if (kFold) {
+        py[u] = ok ? p / W : -8;
+        px[u] = p - py[u] * W;
+        a[u] = ok ? dav[(size_t(py[u] + 1) * (W + 2) + px[u] + 1) * cv] : make_uint4(0, 0, 0, 0);
+      } else {
+        a[u] = ok ? dav[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
+      }
       v[u] = ok ? yv[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
     }
 #pragma unroll
     for (int u = 0; u < kILP; ++u) {
       const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+      float fa8[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+        const float2 q = Cvt<T>::unpack2(aw[k]);
+        fa8[2 * k] = q.x;
+        fa8[2 * k + 1] = q.y;
+      }
+      if (kFold && fold_mode == DUCOSY_PAD_REFLECT && py[u] >= 0 &&
+          (py[u] == 1 || py[u] == H - 2 || px[u] == 1 || px[u] == W - 2))
+        fold_extras<T>(dav, py[u], px[u], H, W, cv, fa8);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float2 fa = make_float2(fa8[2 * k], fa8[2 * k + 1]), fy = Cvt<T>::unpack2(vw[k]);
         const float n0 = fmaf(fy.x, sc[2 * k], sh[2 * k]), n1 = fmaf(fy.y, sc[2 * k + 1], sh[2 * k + 1]);
         const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);   // masked-out loads have a = 0: g = 0
         s1[2 * k] += g0;
@@ -146,11 +193,11 @@ in_bwd_finalize_kernel(const float* __restrict__ partial, float* __restrict__ su
 // grid (row CTAs, B): a CTA walks padded rows py = blockIdx.x, += gridDim.x of its sample; thread t handles the 16-byte
 // chunks t, t+256, ... of a row -- 256 is a multiple of C/8, so its 8 channels (and their rstd / shift / means) stay in
 // registers; four chunks are in flight per thread.
-template <typename T>
+template <typename T, bool kFold>
 __global__ void __launch_bounds__(256)
 in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
                         const float* __restrict__ shift, const float* __restrict__ means, T* __restrict__ dy_pad, int B,
-                        int H, int W, int C, int pad, int act) {
+                        int H, int W, int C, int pad, int act, int fold_mode) {
   pdl_prologue();
   const int Hp = H + 2 * pad, Wp = W + 2 * pad, cv = C / 8;
   const int b = blockIdx.y, c8 = threadIdx.x % cv, px0 = threadIdx.x / cv, px_step = 256 / cv;
@@ -171,7 +218,9 @@ in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const
       for (int px = px0; px < Wp; px += px_step) dst_row[size_t(px) * cv] = make_uint4(0, 0, 0, 0);
       continue;
     }
-    const uint4* a_row = reinterpret_cast<const uint4*>(da) + ((size_t(b) * H + sy) * W) * cv + c8;
+    const uint4* a_pad = reinterpret_cast<const uint4*>(da) + (size_t(b) * (H + 2) * (W + 2)) * cv + c8;   // kFold: sample base
+    const uint4* a_row = kFold ? a_pad + (size_t(sy + 1) * (W + 2) + 1) * cv
+                               : reinterpret_cast<const uint4*>(da) + ((size_t(b) * H + sy) * W) * cv + c8;
     const uint4* y_row = reinterpret_cast<const uint4*>(y) + ((size_t(b) * H + sy) * W) * cv + c8;
     for (int pb = px0; pb < Wp; pb += px_step * kILP) {
       uint4 a[kILP], v[kILP];
@@ -191,9 +240,19 @@ in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const
         if (inside[u]) {
           const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
           uint32_t ow[4];
+          float fa8[8];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
+            const float2 q = Cvt<T>::unpack2(aw[k]);
+            fa8[2 * k] = q.x;
+            fa8[2 * k + 1] = q.y;
+          }
+          const int sx = px - pad;
+          if (kFold && fold_mode == DUCOSY_PAD_REFLECT && (sy == 1 || sy == H - 2 || sx == 1 || sx == W - 2))
+            fold_extras<T>(a_pad, sy, sx, H, W, cv, fa8);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const float2 fa = make_float2(fa8[2 * k], fa8[2 * k + 1]), fy = Cvt<T>::unpack2(vw[k]);
             const float n0 = fmaf(fy.x, rs[2 * k], sh[2 * k]), n1 = fmaf(fy.y, rs[2 * k + 1], sh[2 * k + 1]);
             const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);
             ow[k] = Cvt<T>::pack2(rs[2 * k] * (g0 - m1[2 * k] - n0 * m2[2 * k]),
@@ -737,26 +796,54 @@ extern "C" size_t ducosy_in_backward_scratch_bytes(int B, int H, int W, int C) {
   const int blocks = (H * W + 63) / 64;      // upper bound for any pixels-per-CTA choice
   return size_t(B) * (blocks + 1) * 2 * C * 4;
 }
-extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad,
-                                      float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
-                                      ducosy_stream_t stream) {
+namespace {
+int in_backward_impl(const void* da, bool folded, int fold_mode, const void* y, const float* scale, const float* shift, void* dy_pad,
+                     float* scratch, int B, int H, int W, int C, int pad, int act, int dtype, cudaStream_t st) {
   DUCOSY_CHECK(da && y && scale && shift && dy_pad && scratch && B > 0, DUCOSY_ERR_ARG, "in_backward_pad: null pointer");
   DUCOSY_CHECK(C % 8 == 0 && 256 % (C / 8) == 0 && pad >= 0, DUCOSY_ERR_SHAPE, "in_backward_pad: C/8 must divide 256");
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  DUCOSY_CHECK(!folded || (H >= 4 && W >= 4), DUCOSY_ERR_SHAPE, "in_backward_pad_folded: H, W >= 4");
   const int HW = H * W, ppb = in_bwd_pix_per_block(B, HW), blocks = (HW + ppb - 1) / ppb;
   float* partial = scratch;
   float* means = scratch + size_t(B) * blocks * 2 * C;
   const size_t smem = size_t(256 / (C / 8)) * 2 * C * 4;
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T>, dim3(blocks, B), 256, smem, st)(
-                                      static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb)));
+  if (folded)
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T, true>, dim3(blocks, B), 256, smem, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb, H, W, fold_mode)));
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T, false>, dim3(blocks, B), 256, smem, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb, H, W, fold_mode)));
   DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
   pdl(in_bwd_finalize_kernel, dim3((2 * C + 31) / 32, B), 256, 0, st)(partial, means, blocks, C, 1.0f / float(HW));
   DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
   const int row_ctas = std::max(1, std::min(H + 2 * pad, (num_sms() * 4 + B - 1) / B));
-  DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_apply_pad_kernel<T>, dim3(row_ctas, B), 256, 0, st)(
-                                      static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
-                                      static_cast<T*>(dy_pad), B, H, W, C, pad, act)));
+  if (folded)
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_apply_pad_kernel<T, true>, dim3(row_ctas, B), 256, 0, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
+                                        static_cast<T*>(dy_pad), B, H, W, C, pad, act, fold_mode)));
+  else
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_apply_pad_kernel<T, false>, dim3(row_ctas, B), 256, 0, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, means,
+                                        static_cast<T*>(dy_pad), B, H, W, C, pad, act, fold_mode)));
   return check_launch("in_bwd_apply_pad_kernel");
+}
+}  // namespace
+
+extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, const float* shift, void* dy_pad,
+                                      float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
+                                      ducosy_stream_t stream) {
+  return in_backward_impl(da, false, DUCOSY_PAD_ZERO, y, scale, shift, dy_pad, scratch, B, H, W, C, pad, act, dtype,
+                          static_cast<cudaStream_t>(stream));
+}
+
+// The same with the padding adjoint of a pad-1 convolution folded into the loads: da_pad1 [B][H+2][W+2][C] is the gradient
+// w.r.t. the PADDED map (ducosy_conv3x3s1_dgrad_nhwc's output); fold_mode = DUCOSY_PAD_REFLECT | DUCOSY_PAD_ZERO.  Replaces
+// ducosy_pad_fold + ducosy_in_backward_pad (one full read + write of the map less).
+extern "C" int ducosy_in_backward_pad_folded(const void* da_pad1, int fold_mode, const void* y, const float* scale, const float* shift,
+                                             void* dy_pad, float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
+                                             ducosy_stream_t stream) {
+  DUCOSY_CHECK(fold_mode == DUCOSY_PAD_REFLECT || fold_mode == DUCOSY_PAD_ZERO, DUCOSY_ERR_ARG, "in_backward_pad_folded: bad fold mode");
+  return in_backward_impl(da_pad1, true, fold_mode, y, scale, shift, dy_pad, scratch, B, H, W, C, pad, act, dtype,
+                          static_cast<cudaStream_t>(stream));
 }
 
 extern "C" int ducosy_pack_dgrad_s2_weight(const float* w_oihw, void* packed, int Cout, int Cin, int ksize, int dtype,

@@ -423,6 +423,20 @@ def in_backward_pad(da, y, scale, shift, pad, act):
     return out
 
 
+def in_backward_pad_folded(da_pad1, fold_mode, y, scale, shift, pad, act):
+    """``in_backward_pad`` of the map whose gradient w.r.t. its pad-1 form is ``da_pad1`` [B,H+2,W+2,C] (``conv3x3s1_dgrad(...,
+    fold=False)``): the padding adjoint is folded into the loads, the folded map is never written."""
+    B, H, W, Cn = y.shape
+    assert da_pad1.shape == (B, H + 2, W + 2, Cn) and da_pad1.is_contiguous()
+    lib = _lib.load()
+    with _dev(y):
+        scratch = torch.empty(max(lib.ducosy_in_backward_scratch_bytes(B, H, W, Cn) // 4, 4), dtype=torch.float32, device=y.device)
+        out = torch.empty((B, H + 2 * pad, W + 2 * pad, Cn), dtype=y.dtype, device=y.device)
+        call("ducosy_in_backward_pad_folded", ptr(da_pad1), int(fold_mode), ptr(y), ptr(scale), ptr(shift), ptr(out), ptr(scratch), B, H, W,
+             Cn, pad, act, dtype_code(y.dtype), stream_ptr())
+    return out
+
+
 def convs2_dgrad_nhwc(dy_pad, w_oihw):
     """Input gradient of Conv2d(Cin,Cout,k,stride 2,padding 1), k in {3,4}: dy_pad [B,Ho+2,Wo+2,Cout] -> dx [B,2Ho,2Wo,Cin]."""
     Cout, Cin, ksz = w_oihw.shape[:3]
@@ -460,9 +474,10 @@ def apply_windowing(y, hu_lo, hu_hi, window_center, window_width):
     return out
 
 
-def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode, add=None):
+def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode, add=None, fold=True):
     """Input gradient of pad(1) + Conv2d(3x3): dy_pad2 [B,H+4,W+4,Cout] (zero border 2) -> dx [B,H,W,Cin] after folding
-    the padding adjoint (reflect or zero); ``add`` [B,H,W,Cin] is summed in (the skip connection's gradient)."""
+    the padding adjoint (reflect or zero); ``add`` [B,H,W,Cin] is summed in (the skip connection's gradient).
+    ``fold=False`` returns (None, dxpad): the consumer folds while loading (``in_backward_pad_folded``)."""
     Cout, Cin = w_oihw.shape[:2]
     B, Hp, Wp, _ = dy_pad2.shape
     H, W = Hp - 4, Wp - 4
@@ -476,9 +491,22 @@ def conv3x3s1_dgrad(dy_pad2, w_oihw, pad_mode, add=None):
         wd = _cached_pack("dgrad_s1", w_oihw, dy_pad2.dtype, build)
         dxpad = torch.empty((B, H + 2, W + 2, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
         call("ducosy_conv3x3s1_dgrad_nhwc", ptr(dy_pad2), ptr(wd), ptr(dxpad), B, H, W, Cin, Cout, dc, stream_ptr())
+        if not fold:
+            assert add is None
+            return None, dxpad
         dx = torch.empty((B, H, W, Cin), dtype=dy_pad2.dtype, device=dy_pad2.device)
         call("ducosy_pad_fold_add", ptr(dxpad), ptr(add), ptr(dx), B, H, W, Cin, 1, pad_mode, dc, stream_ptr())
     return dx, dxpad
+
+
+def pad_fold(dxpad, pad, pad_mode, add=None):
+    """Adjoint of ReflectionPad2d(pad) / zero padding: dxpad [B,H+2p,W+2p,C] -> dx [B,H,W,C] (+ ``add``)."""
+    B, Hp, Wp, Cn = dxpad.shape
+    H, W = Hp - 2 * pad, Wp - 2 * pad
+    with _dev(dxpad):
+        dx = torch.empty((B, H, W, Cn), dtype=dxpad.dtype, device=dxpad.device)
+        call("ducosy_pad_fold_add", ptr(dxpad), ptr(add), ptr(dx), B, H, W, Cn, pad, pad_mode, dtype_code(dxpad.dtype), stream_ptr())
+    return dx
 
 
 def unpack_wgrad(dwp, Cout, Cin, taps, gs=None):

@@ -87,7 +87,10 @@ def test_workspace_and_shape_validation_without_gpu():
     lib = _lib.load()
     cfg = _lib.GenConfig(1, 9, 1, _lib.F16)
     assert lib.ducosy_generator_num_params(C.byref(cfg)) == 75
-    assert lib.ducosy_generator_num_launches(C.byref(cfg)) == 88
+    assert lib.ducosy_generator_num_launches(C.byref(cfg)) == 97      # 16 + 9 blocks x (6 + pool, spatial conv, channel MLP)
+    cfg_x2 = _lib.GenConfig(1, 9, 1, _lib.F16X2)                          # split-operand arm: packed weights and workspace double
+    assert lib.ducosy_generator_packed_bytes(C.byref(cfg_x2)) > 44_000_000
+    assert lib.ducosy_generator_workspace_bytes(C.byref(cfg_x2), 1, 512, 512) > 380_000_000
     assert lib.ducosy_generator_packed_bytes(C.byref(cfg)) > 22_000_000
     assert lib.ducosy_generator_workspace_bytes(C.byref(cfg), 1, 512, 512) > 200_000_000
     assert lib.ducosy_generator_workspace_bytes(C.byref(cfg), 1, 500, 500) == 0      # unsupported shape

@@ -316,6 +316,33 @@ def test_in_backward_matches_autograd(ops):
         assert err < 4e-3 * max(1.0, ref.abs().max().item()), (act, err, ref.abs().max().item())
 
 
+@pytest.mark.parametrize("mode", ["reflect", "zero"])
+def test_in_backward_folded_matches_autograd_through_the_padding(ops, mode):
+    """ducosy_in_backward_pad_folded: the gradient w.r.t. pad1(act(IN(y))) goes in, the padding adjoint (reference
+    nn.ReflectionPad2d(1) in front of modules/model.py:60-62, or zero padding) is folded while loading.  Against autograd
+    through F.pad + instance_norm + relu, and bit-identical interior / near-identical frame against the two-step form."""
+    dtype = torch.float16
+    B, H, W, Cn = 2, 16, 32, 256
+    y = (_rand((B, H, W, Cn), 191) * 1.5 + 0.8).to(dtype).cuda()
+    dpad = _rand((B, H + 2, W + 2, Cn), 192).to(dtype).cuda()
+    scale, shift = ops.in_finalize(_fake_partials(y), H * W)
+    pm = ops.PAD_REFLECT if mode == "reflect" else ops.PAD_ZERO
+    got = ops.in_backward_pad_folded(dpad, pm, y, scale, shift, 2, ops.ACT_RELU)
+    yr = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
+    a = F.relu(F.instance_norm(yr))
+    ap = F.pad(a, (1, 1, 1, 1), mode="reflect") if mode == "reflect" else F.pad(a, (1, 1, 1, 1))
+    ap.backward(dpad.float().permute(0, 3, 1, 2))
+    ref = F.pad(yr.grad, (2, 2, 2, 2))
+    # relu'(n) is discontinuous at n = 0 and the kernel's statistics (fp32 sums of the 16-bit map) differ from F.instance_norm's in
+    # the last bits: the handful of elements with |n| < 1e-3 may take either branch -- they are left out of the comparison
+    away = F.pad((F.instance_norm(y.float().permute(0, 3, 1, 2)).abs() > 1e-3).float(), (2, 2, 2, 2), value=1.0)
+    assert away.mean().item() > 0.99
+    err = ((got.float().permute(0, 3, 1, 2) - ref).abs() * away).max().item()
+    assert err < 4e-3 * max(1.0, ref.abs().max().item()), (mode, err, ref.abs().max().item())
+    two_step = ops.in_backward_pad(ops.pad_fold(dpad, 1, pm), y, scale, shift, 2, ops.ACT_RELU)
+    assert (got.float() - two_step.float()).abs().max().item() < 4e-3 * max(1.0, ref.abs().max().item())
+
+
 @pytest.mark.parametrize("case", [(2, 16, 16, 256, 512, 4), (1, 32, 64, 64, 128, 4), (2, 32, 32, 128, 256, 3), (1, 16, 64, 64, 128, 3)])
 def test_stride2_dgrad_matches_autograd(ops, case):
     B, Ho, Wo, Cin, Cout, ksz = case
