@@ -187,8 +187,17 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     long long r = i / Cin;
     const int o = int(r % Cout);
     const int tap = int(r / Cout);
-    float acc = 0.f;
-    for (int s = 0; s < splits; ++s) acc += partial[s * per_split + i];
+    // four independent chains (loads of four splits in flight), combined in a fixed order: deterministic
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int s = 0;
+    for (; s + 4 <= splits; s += 4) {
+      a0 += partial[(s + 0) * per_split + i];
+      a1 += partial[(s + 1) * per_split + i];
+      a2 += partial[(s + 2) * per_split + i];
+      a3 += partial[(s + 3) * per_split + i];
+    }
+    for (; s < splits; ++s) a0 += partial[s * per_split + i];
+    const float acc = (a0 + a1) + (a2 + a3);
     if (oihw != 0) dw[((long long)o * Cin + c) * taps + tap] = acc * inv;
     else dw[((long long)o * taps + tap) * Cin + c] = acc;
   }

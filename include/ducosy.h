@@ -315,7 +315,7 @@ typedef struct {
   int input_channels;      /* Generator(input_channels=...) modules/model.py:92 */
   int num_residual_blocks; /* default 9 */
   int use_cbam;            /* default 1 */
-  int dtype;               /* DUCOSY_F16 | DUCOSY_BF16 (16-bit operand type of the tensor-core convs) */
+  int dtype;               /* DUCOSY_F16 | DUCOSY_BF16 (16-bit operand type of the tensor-core convs) | DUCOSY_F16X2 (split-operand arm) */
 } ducosy_gen_config;
 
 /* Number of parameter tensors in state_dict order (modules/model.py:92-113) and packed-cache size in bytes. */
@@ -325,7 +325,12 @@ size_t ducosy_generator_workspace_bytes(const ducosy_gen_config* cfg, int B, int
 /* params_host: host array of DEVICE pointers to the fp32 parameters in state_dict order. */
 int ducosy_generator_pack(const ducosy_gen_config* cfg, const float* const* params_host, int num_params, void* packed,
                           ducosy_stream_t stream);
-/* Generator.forward (modules/model.py:114): x fp32 NCHW [B][Cin][H][W] -> out fp32 [B][1][H][W]. */
+/* Generator.forward (modules/model.py:114): x fp32 NCHW [B][Cin][H][W] -> out fp32 [B][1][H][W].
+ * Shape contract (DUCOSY_ERR_SHAPE otherwise; ducosy_generator_workspace_bytes returns 0): B >= 1, 1 <= Cin <= 16, H a
+ * multiple of 32 and W a multiple of 128, both >= 128, with W/4 in {32, 64, 128 k} and H/4 a multiple of 128 / min(W/4, 128)
+ * (512 x 512 is what generate.py and train.py use).  workspace: 1024-byte aligned, packed: 256-byte aligned.
+ * The TRAINING path built on the per-layer entry points (ducosy_gan_b200/training.py) additionally needs W = 256 or a
+ * multiple of 512 for the generator and H, W multiples of 256 for the discriminator (input_channels == 1 only). */
 int ducosy_generator_forward(const ducosy_gen_config* cfg, const void* packed, const float* x_nchw, float* out, int B,
                              int H, int W, void* workspace, size_t workspace_bytes, ducosy_stream_t stream);
 /* Same with the input taken straight from stored pixel values through the HU window (generate.py:91-96), Cin = 1. */

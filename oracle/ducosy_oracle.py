@@ -19,6 +19,14 @@ Parity status
   vendored, not installed here).  The restatement follows the package's
   published algorithm (gaussian 11/1.5, valid conv, C1/C2 from data_range).
 
+* volume smoothing (``postprocess_volume``), anatomical masks (``mask_*``), the CycleGAN step (``cyclegan_step``) and the
+  image-quality metrics (``metric_mae / psnr / cs / ed / normalize``): PINNED by ``oracle/make_golden_postprocess.py``,
+  ``make_golden_masks.py``, ``make_golden_trainstep.py`` and ``make_golden_metrics.py``, which run the reference's own
+  functions (``modules/postprocess.py``, ``modules/mask_generator.py``, the loop body of ``modules/trainer.py:448-525``,
+  ``calculate.py:232-263,360-381``) on seeded inputs.
+* ``skimage_structural_similarity`` (the core of ``calculate_ssim``): "parity unpinned" -- scikit-image is absent and
+  unpinned; restated with the ``scipy.ndimage.uniform_filter`` it calls.
+
 Every function cites the reference ``file:line`` it follows.
 """
 from __future__ import annotations
