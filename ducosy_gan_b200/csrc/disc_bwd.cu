@@ -65,39 +65,53 @@ __global__ void grad_scale_finalize_kernel(float* __restrict__ gs) {
 // pass 1: per-block partial sums [B][blocks][2][C];  pass 2 (in_bwd_finalize): fixed-order sum -> [B][2][C];
 // pass 3: dy written 16-bit into a zero-padded buffer.
 // kFold: `da` is not the gradient map itself but the gradient w.r.t. the map padded by ONE pixel, [B][H+2][W+2][C] (what the
-// 3x3 dgrad convolution writes): the padding adjoint of pad_fold_kernel is applied while loading -- the interior value plus, for
-// ReflectionPad2d, the border rows / columns that mirror onto source rows 1, H-2 and columns 1, W-2 (zero padding: the border
-// is dropped) -- so the folded map never makes its own round trip through HBM.  The fold is summed in fp32 in a fixed order;
-// the reduce and the apply pass see the same values.
+// 3x3 dgrad convolution writes): the streaming kernels read its interior directly, so the folded map never makes its own round
+// trip through HBM.  For ReflectionPad2d the border rows / columns that mirror onto source rows 1, H-2 and columns 1, W-2 are
+// added into those interior cells beforehand, in place, by pad1_reflect_border_kernel (a few microseconds: 2W + 2(H-2) pixels
+// per sample; reads touch only the outermost ring, writes only cells of the next-but-one ring, so there is no ordering hazard).
+// (A first version added the mirrored terms inside the streaming loops: its temporaries cost them 50 registers and half their
+// occupancy -- ncu: reduce 33 -> 55 us, apply 42 -> 55 us per 134 MB map.)
 template <typename T>
-__device__ __forceinline__ void fold_extras(const uint4* __restrict__ padb /* sample base + c8 */, int y, int x, int H, int W, int cv,
-                                            float (&f)[8]) {
+__global__ void __launch_bounds__(256)
+pad1_reflect_border_kernel(T* __restrict__ dxpad, int B, int H, int W, int C) {
+  pdl_prologue();
+  const int cv = C / 8, per_sample = 2 * W + 2 * (H - 2);
+  const long long item = (long long)blockIdx.x * 256 + threadIdx.x;
+  if (item >= (long long)B * per_sample * cv) return;
+  const int c8 = int(item % cv);
+  const long long pid = item / cv;
+  const int b = int(pid / per_sample), idx = int(pid - (long long)b * per_sample);
+  int y, x;
+  if (idx < W) { y = 1; x = idx; }
+  else if (idx < 2 * W) { y = H - 2; x = idx - W; }
+  else { const int k = idx - 2 * W, j = k >> 1; y = j == 0 ? 0 : (j == H - 3 ? H - 1 : j + 1); x = (k & 1) ? W - 2 : 1; }   // rows 0, 2..H-3, H-1
   const int ry = y == 1 ? 0 : (y == H - 2 ? H + 1 : -1), cx = x == 1 ? 0 : (x == W - 2 ? W + 1 : -1);
+  uint4* base = reinterpret_cast<uint4*>(dxpad) + (size_t(b) * (H + 2) * (W + 2)) * cv + c8;
+  float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
   auto add = [&](int r, int c) {
-    float t[8];
-    const uint4 v = padb[(size_t(r) * (W + 2) + c) * cv];
+    const uint4 v = base[(size_t(r) * (W + 2) + c) * cv];
     const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
     for (int k = 0; k < 4; ++k) {
       const float2 q = Cvt<T>::unpack2(w4[k]);
-      t[2 * k] = q.x;
-      t[2 * k + 1] = q.y;
+      f[2 * k] += q.x;
+      f[2 * k + 1] += q.y;
     }
-#pragma unroll
-    for (int k = 0; k < 8; ++k) f[k] += t[k];
   };
-  if (cx >= 0) add(y + 1, cx);
-  if (ry >= 0) {
-    add(ry, x + 1);
-    if (cx >= 0) add(ry, cx);
+  add(y + 1, x + 1);                      // same summation order as pad_fold_kernel: interior first, then the mirrored cells
+  if (ry >= 0) add(ry, x + 1);
+  if (cx >= 0) {
+    add(y + 1, cx);
+    if (ry >= 0) add(ry, cx);
   }
+  base[(size_t(y + 1) * (W + 2) + x + 1) * cv] =
+      make_uint4(Cvt<T>::pack2(f[0], f[1]), Cvt<T>::pack2(f[2], f[3]), Cvt<T>::pack2(f[4], f[5]), Cvt<T>::pack2(f[6], f[7]));
 }
 
 template <typename T, bool kFold>
-__global__ void __launch_bounds__(256)
-in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
-                     const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block,
-                     int H, int W, int fold_mode) {
+__device__ __forceinline__ void in_bwd_reduce_body(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+                                                   const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act,
+                                                   int pix_per_block, int H /* kFold: log2(W) */, int W) {
   pdl_prologue();
   extern __shared__ float red[];  // [rows][2][C] with rows = 256 / (C/8)
   const int cv = C / 8, c8 = threadIdx.x % cv, prow = threadIdx.x / cv, rows = 256 / cv;
@@ -111,20 +125,19 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
     s1[j] = 0.f;
     s2[j] = 0.f;
   }
-  const uint4* dav = reinterpret_cast<const uint4*>(da) + (kFold ? size_t(b) * (H + 2) * (W + 2) : size_t(b) * HW) * cv + c8;
+  const uint4* dav = reinterpret_cast<const uint4*>(da) + (kFold ? size_t(b) * (HW / W + 2) * (W + 2) : size_t(b) * HW) * cv + c8;
   const uint4* yv = reinterpret_cast<const uint4*>(y) + (size_t(b) * HW) * cv + c8;
   constexpr int kILP = 4;   // 8 independent 16-byte loads in flight per thread
   for (int pb = p0 + prow; pb < p1; pb += rows * kILP) {
     uint4 a[kILP], v[kILP];
-    int py[kILP], px[kILP];
 #pragma unroll
     for (int u = 0; u < kILP; ++u) {
       const int p = pb + u * rows;
       const bool ok = p < p1;
-      if (kFold) {
-        py[u] = ok ? p / W : -8;
-        px[u] = p - py[u] * W;
-        a[u] = ok ? dav[(size_t(py[u] + 1) * (W + 2) + px[u] + 1) * cv] : make_uint4(0, 0, 0, 0);
+      if (kFold) {   // W is a power of two here (checked on the host): H carries log2(W), no division in the streaming loop
+        // padded index of pixel p = (py + 1) * (W + 2) + px + 1 = p + 2 * py + W + 3   (32-bit: one sample's map is < 2^31 chunks)
+        const unsigned ip = unsigned(p + 2 * (p >> H) + W + 3) * unsigned(cv);
+        a[u] = ok ? dav[ip] : make_uint4(0, 0, 0, 0);
       } else {
         a[u] = ok ? dav[size_t(p) * cv] : make_uint4(0, 0, 0, 0);
       }
@@ -133,19 +146,9 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
 #pragma unroll
     for (int u = 0; u < kILP; ++u) {
       const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
-      float fa8[8];
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        const float2 q = Cvt<T>::unpack2(aw[k]);
-        fa8[2 * k] = q.x;
-        fa8[2 * k + 1] = q.y;
-      }
-      if (kFold && fold_mode == DUCOSY_PAD_REFLECT && py[u] >= 0 &&
-          (py[u] == 1 || py[u] == H - 2 || px[u] == 1 || px[u] == W - 2))
-        fold_extras<T>(dav, py[u], px[u], H, W, cv, fa8);
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float2 fa = make_float2(fa8[2 * k], fa8[2 * k + 1]), fy = Cvt<T>::unpack2(vw[k]);
+        const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
         const float n0 = fmaf(fy.x, sc[2 * k], sh[2 * k]), n1 = fmaf(fy.y, sc[2 * k + 1], sh[2 * k + 1]);
         const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);   // masked-out loads have a = 0: g = 0
         s1[2 * k] += g0;
@@ -166,6 +169,21 @@ in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const fl
     for (int r = 0; r < rows; ++r) acc += red[r * 2 * C + i];
     partial[(size_t(b) * gridDim.x + blockIdx.x) * 2 * C + i] = acc;
   }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+in_bwd_reduce_kernel(const T* __restrict__ da, const T* __restrict__ y, const float* __restrict__ scale,
+                     const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block) {
+  in_bwd_reduce_body<T, false>(da, y, scale, shift, partial, HW, C, act, pix_per_block, 0, 1);
+}
+// the padded addressing costs registers: three CTAs per SM are kept by capping them (20 bytes of spill)
+template <typename T>
+__global__ void __launch_bounds__(256, 3)
+in_bwd_reduce_fold_kernel(const T* __restrict__ da_pad1, const T* __restrict__ y, const float* __restrict__ scale,
+                          const float* __restrict__ shift, float* __restrict__ partial, int HW, int C, int act, int pix_per_block,
+                          int log2W, int W) {
+  in_bwd_reduce_body<T, true>(da_pad1, y, scale, shift, partial, HW, C, act, pix_per_block, log2W, W);
 }
 
 // grid (ceil(2C / 32), B), 256 threads = 32 columns x 8 slices of the partial rows; fixed-order double sums (deterministic).
@@ -240,19 +258,9 @@ in_bwd_apply_pad_kernel(const T* __restrict__ da, const T* __restrict__ y, const
         if (inside[u]) {
           const uint32_t aw[4] = {a[u].x, a[u].y, a[u].z, a[u].w}, vw[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
           uint32_t ow[4];
-          float fa8[8];
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            const float2 q = Cvt<T>::unpack2(aw[k]);
-            fa8[2 * k] = q.x;
-            fa8[2 * k + 1] = q.y;
-          }
-          const int sx = px - pad;
-          if (kFold && fold_mode == DUCOSY_PAD_REFLECT && (sy == 1 || sy == H - 2 || sx == 1 || sx == W - 2))
-            fold_extras<T>(a_pad, sy, sx, H, W, cv, fa8);
-#pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const float2 fa = make_float2(fa8[2 * k], fa8[2 * k + 1]), fy = Cvt<T>::unpack2(vw[k]);
+            const float2 fa = Cvt<T>::unpack2(aw[k]), fy = Cvt<T>::unpack2(vw[k]);
             const float n0 = fmaf(fy.x, rs[2 * k], sh[2 * k]), n1 = fmaf(fy.y, rs[2 * k + 1], sh[2 * k + 1]);
             const float g0 = fa.x * act_grad(n0, act), g1 = fa.y * act_grad(n1, act);
             ow[k] = Cvt<T>::pack2(rs[2 * k] * (g0 - m1[2 * k] - n0 * m2[2 * k]),
@@ -801,17 +809,26 @@ int in_backward_impl(const void* da, bool folded, int fold_mode, const void* y, 
                      float* scratch, int B, int H, int W, int C, int pad, int act, int dtype, cudaStream_t st) {
   DUCOSY_CHECK(da && y && scale && shift && dy_pad && scratch && B > 0, DUCOSY_ERR_ARG, "in_backward_pad: null pointer");
   DUCOSY_CHECK(C % 8 == 0 && 256 % (C / 8) == 0 && pad >= 0, DUCOSY_ERR_SHAPE, "in_backward_pad: C/8 must divide 256");
-  DUCOSY_CHECK(!folded || (H >= 4 && W >= 4), DUCOSY_ERR_SHAPE, "in_backward_pad_folded: H, W >= 4");
+  DUCOSY_CHECK(!folded || (H >= 5 && W >= 8 && (W & (W - 1)) == 0), DUCOSY_ERR_SHAPE,
+               "in_backward_pad_folded: H >= 5 and W a power of two >= 8 (got %dx%d)", H, W);
   const int HW = H * W, ppb = in_bwd_pix_per_block(B, HW), blocks = (HW + ppb - 1) / ppb;
   float* partial = scratch;
   float* means = scratch + size_t(B) * blocks * 2 * C;
   const size_t smem = size_t(256 / (C / 8)) * 2 * C * 4;
+  if (folded && fold_mode == DUCOSY_PAD_REFLECT) {
+    // mirrored border rows / columns are added into the interior cells they reflect onto, in place (da_pad1 is consumed here)
+    const long long items = (long long)B * (2 * W + 2 * (H - 2)) * (C / 8);
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(pad1_reflect_border_kernel<T>, int((items + 255) / 256), 256, 0, st)(
+                                        static_cast<T*>(const_cast<void*>(da)), B, H, W, C)));
+    DUCOSY_TRY(check_launch("pad1_reflect_border_kernel"));
+  }
   if (folded)
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T, true>, dim3(blocks, B), 256, smem, st)(
-                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb, H, W, fold_mode)));
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_fold_kernel<T>, dim3(blocks, B), 256, smem, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb,
+                                        __builtin_ctz(unsigned(W)), W)));
   else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T, false>, dim3(blocks, B), 256, smem, st)(
-                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb, H, W, fold_mode)));
+    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_bwd_reduce_kernel<T>, dim3(blocks, B), 256, smem, st)(
+                                        static_cast<const T*>(da), static_cast<const T*>(y), scale, shift, partial, HW, C, act, ppb)));
   DUCOSY_TRY(check_launch("in_bwd_reduce_kernel"));
   pdl(in_bwd_finalize_kernel, dim3((2 * C + 31) / 32, B), 256, 0, st)(partial, means, blocks, C, 1.0f / float(HW));
   DUCOSY_TRY(check_launch("in_bwd_finalize_kernel"));
@@ -837,8 +854,9 @@ extern "C" int ducosy_in_backward_pad(const void* da, const void* y, const float
 
 // The same with the padding adjoint of a pad-1 convolution folded into the loads: da_pad1 [B][H+2][W+2][C] is the gradient
 // w.r.t. the PADDED map (ducosy_conv3x3s1_dgrad_nhwc's output); fold_mode = DUCOSY_PAD_REFLECT | DUCOSY_PAD_ZERO.  Replaces
-// ducosy_pad_fold + ducosy_in_backward_pad (one full read + write of the map less).
-extern "C" int ducosy_in_backward_pad_folded(const void* da_pad1, int fold_mode, const void* y, const float* scale, const float* shift,
+// ducosy_pad_fold + ducosy_in_backward_pad (one full read + write of the map less).  da_pad1 is CONSUMED: with
+// DUCOSY_PAD_REFLECT the mirrored border terms are added into its interior cells in place.
+extern "C" int ducosy_in_backward_pad_folded(void* da_pad1, int fold_mode, const void* y, const float* scale, const float* shift,
                                              void* dy_pad, float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
                                              ducosy_stream_t stream) {
   DUCOSY_CHECK(fold_mode == DUCOSY_PAD_REFLECT || fold_mode == DUCOSY_PAD_ZERO, DUCOSY_ERR_ARG, "in_backward_pad_folded: bad fold mode");

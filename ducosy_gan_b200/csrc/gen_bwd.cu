@@ -631,6 +631,7 @@ cbam_bwd_dz_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const f
   load8f(shift_v + b * kCbamC + c0, hv);
 #pragma unroll
   for (int k = 0; k < 8; ++k) { best[k] = -INFINITY; bidx[k] = 0; }
+#pragma unroll 4   // four pixels' loads in flight per warp (a warp-per-pixel loop with a shuffle reduction is latency bound otherwise)
   for (int i = 0; i < kCbamPix / 8; ++i) {
     const int pix = blk * kCbamPix + warp + i * 8;
     const long long off = ((long long)b * HW + pix) * kCbamC + c0;
@@ -752,6 +753,7 @@ cbam_bwd_dv_kernel(const T* __restrict__ dout, const T* __restrict__ yb, const f
   load8f(ca + b * kCbamC + c0, cav);
 #pragma unroll
   for (int k = 0; k < 8; ++k) accd[k] = 0.f;
+#pragma unroll 4   // four pixels' loads in flight per warp (a warp-per-pixel loop with a shuffle reduction is latency bound otherwise)
   for (int i = 0; i < kCbamPix / 8; ++i) {
     const int pix = blk * kCbamPix + warp + i * 8;
     const long long off = ((long long)b * HW + pix) * kCbamC + c0;

@@ -425,7 +425,8 @@ def in_backward_pad(da, y, scale, shift, pad, act):
 
 def in_backward_pad_folded(da_pad1, fold_mode, y, scale, shift, pad, act):
     """``in_backward_pad`` of the map whose gradient w.r.t. its pad-1 form is ``da_pad1`` [B,H+2,W+2,C] (``conv3x3s1_dgrad(...,
-    fold=False)``): the padding adjoint is folded into the loads, the folded map is never written."""
+    fold=False)``): the streaming kernels read the padded map's interior, the folded map is never written.  ``da_pad1`` is
+    CONSUMED: for reflection padding the mirrored border terms are first added into its interior cells, in place."""
     B, H, W, Cn = y.shape
     assert da_pad1.shape == (B, H + 2, W + 2, Cn) and da_pad1.is_contiguous()
     lib = _lib.load()

@@ -89,9 +89,14 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
             dyb = ops.in_backward_pad(dr, sv["yb"], *sv["nb"], 2, ACT_NONE)
         C = bp[0].shape[0]
         dw_b = ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs)
-        # the reflection adjoint of conv b's input padding is folded into the loads of the InstanceNorm backward
-        _, dpa_pad = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT, fold=False)
-        dya = ops.in_backward_pad_folded(dpa_pad, PAD_REFLECT, sv["ya"], *sv["na"], 2, ACT_RELU)
+        Wb = sv["ya"].shape[2]
+        if Wb >= 8 and Wb & (Wb - 1) == 0:
+            # the reflection adjoint of conv b's input padding is folded into the loads of the InstanceNorm backward
+            _, dpa_pad = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT, fold=False)
+            dya = ops.in_backward_pad_folded(dpa_pad, PAD_REFLECT, sv["ya"], *sv["na"], 2, ACT_RELU)
+        else:
+            dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
+            dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
         dw_a = ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs)
         dr, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT, add=dr)     # conv path + skip connection
         block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)

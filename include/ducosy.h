@@ -414,8 +414,9 @@ int ducosy_in_backward_pad(const void* da, const void* y, const float* scale, co
                            int B, int H, int W, int C, int pad, int act, int dtype, ducosy_stream_t stream);
 /* The same with the padding adjoint of a pad-1 convolution folded into the loads: da_pad1 [B][H+2][W+2][C] is the gradient with
  * respect to the PADDED map (the output of ducosy_conv3x3s1_dgrad_nhwc); fold_mode DUCOSY_PAD_REFLECT | DUCOSY_PAD_ZERO.
- * Replaces ducosy_pad_fold + ducosy_in_backward_pad for a map that has no other consumer. */
-int ducosy_in_backward_pad_folded(const void* da_pad1, int fold_mode, const void* y, const float* scale, const float* shift,
+ * Replaces ducosy_pad_fold + ducosy_in_backward_pad for a map that has no other consumer: da_pad1 is CONSUMED (with
+ * DUCOSY_PAD_REFLECT the mirrored border terms are first added into its interior cells, in place).  H >= 5, W a power of two >= 8. */
+int ducosy_in_backward_pad_folded(void* da_pad1, int fold_mode, const void* y, const float* scale, const float* shift,
                                   void* dy_pad, float* scratch, int B, int H, int W, int C, int pad, int act, int dtype,
                                   ducosy_stream_t stream);
 /* Input gradient of Conv2d(Cin, Cout, k, stride 2, padding 1), k = 4 (PatchGAN) or 3 (generator down convs,

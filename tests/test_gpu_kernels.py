@@ -327,7 +327,7 @@ def test_in_backward_folded_matches_autograd_through_the_padding(ops, mode):
     dpad = _rand((B, H + 2, W + 2, Cn), 192).to(dtype).cuda()
     scale, shift = ops.in_finalize(_fake_partials(y), H * W)
     pm = ops.PAD_REFLECT if mode == "reflect" else ops.PAD_ZERO
-    got = ops.in_backward_pad_folded(dpad, pm, y, scale, shift, 2, ops.ACT_RELU)
+    got = ops.in_backward_pad_folded(dpad.clone(), pm, y, scale, shift, 2, ops.ACT_RELU)   # the padded map is consumed (folded in place)
     yr = y.float().permute(0, 3, 1, 2).clone().requires_grad_(True)
     a = F.relu(F.instance_norm(yr))
     ap = F.pad(a, (1, 1, 1, 1), mode="reflect") if mode == "reflect" else F.pad(a, (1, 1, 1, 1))
