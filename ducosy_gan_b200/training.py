@@ -8,10 +8,50 @@ normalised values are re-derived instead of stored; 16-bit gradient maps carry t
 """
 from __future__ import annotations
 
+import os
+
 import torch
 
 from . import ops
 from .ops import ACT_NONE, ACT_RELU, PAD_REFLECT, PAD_ZERO
+
+
+_WGRAD_STREAMS = {}
+
+
+class _SideWgrad:
+    """Weight gradients on a side stream.  In the backward of a convolution the weight gradient (dy, x -> dW) has no consumer
+    before the optimiser, while the input gradient (dy, W -> dx) is on the critical path of the whole chain; at small per-rank
+    batches neither fills the GPU (128-256 tiles on 148 SMs, and the InstanceNorm / padding kernels between the convolutions
+    use a fraction of it), so the weight gradients of a generator pass CAN run on a second stream next to the chain, joined at
+    the end of the backward.  Inputs are kept alive until the join (no allocator reuse while the side stream may still read
+    them); captured in a CUDA graph this becomes a fork / join like the two generator streams.
+    OPT-IN (DUCOSY_WGRAD_STREAM=1): measured neutral -- 17.84 vs 17.80 ms per step at batch 1, 101.4 vs 101.0 ms at batch 8
+    (tools/gpu_ab_wgrad_stream.sh, profiles/r02_wgrad_stream_ab.json): the two generator streams already fill what the chain
+    leaves idle."""
+
+    def __init__(self):
+        self.cur = torch.cuda.current_stream()
+        self.side = None
+        if os.environ.get("DUCOSY_WGRAD_STREAM", "0") == "1":
+            key = (self.cur.device.index, self.cur.cuda_stream)
+            if key not in _WGRAD_STREAMS:
+                _WGRAD_STREAMS[key] = torch.cuda.Stream(device=self.cur.device)
+            self.side = _WGRAD_STREAMS[key]
+        self.keep = []
+
+    def __call__(self, fn, *inputs):
+        if self.side is None:
+            return fn()
+        self.keep.extend(inputs)
+        self.side.wait_stream(self.cur)          # dy was just produced on the main stream
+        with torch.cuda.stream(self.side):
+            return fn()
+
+    def join(self):
+        if self.side is not None:
+            self.cur.wait_stream(self.side)
+        self.keep.clear()
 
 
 def _split_params(params, num_blocks, use_cbam):
@@ -73,6 +113,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
     gs = ops.grad_scale(dout)
     zero = lambda p: None      # dead bias (in front of a non-affine InstanceNorm): exact zero gradient, materialised by the caller if needed
 
+    side = _SideWgrad()
     da, dw_out, db_out = ops.out_conv_backward(dout, S["out"], S["pout"], outp[0], gs)
     dyu2 = ops.in_backward_pad(da, S["yu2"], *S["nu2"], 2, ACT_RELU)
     dpu1, dw_u2 = ops.upconv2x_backward(S["pu1"], dyu2, u2[0], gs)
@@ -88,7 +129,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
             cbam_grads = []
             dyb = ops.in_backward_pad(dr, sv["yb"], *sv["nb"], 2, ACT_NONE)
         C = bp[0].shape[0]
-        dw_b = ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs)
+        dw_b = side(lambda: ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs), sv["pa"], dyb, gs)
         Wb = sv["ya"].shape[2]
         if Wb >= 8 and Wb & (Wb - 1) == 0:
             # the reflection adjoint of conv b's input padding is folded into the loads of the InstanceNorm backward
@@ -97,19 +138,20 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
         else:
             dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
             dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
-        dw_a = ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs)
+        dw_a = side(lambda: ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs), sv["r"], dya, gs)
         dr, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT, add=dr)     # conv path + skip connection
         block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)
     block_grads.reverse()
 
     dy2 = ops.in_backward_pad(dr, S["y2"], *S["n2"], 1, ACT_RELU)
-    dw_d2 = ops.conv2d_wgrad_oihw(S["p1"], dy2, 3, 3, 2, dy_pad=1, gs=gs)
+    dw_d2 = side(lambda: ops.conv2d_wgrad_oihw(S["p1"], dy2, 3, 3, 2, dy_pad=1, gs=gs), S["p1"], dy2, gs)
     dp1 = ops.convs2_dgrad_nhwc(dy2, d2[0])
     dy1 = ops.in_backward_pad(dp1, S["y1"], *S["n1"], 1, ACT_RELU)
-    dw_d1 = ops.conv2d_wgrad_oihw(S["p0"], dy1, 3, 3, 2, dy_pad=1, gs=gs)
+    dw_d1 = side(lambda: ops.conv2d_wgrad_oihw(S["p0"], dy1, 3, 3, 2, dy_pad=1, gs=gs), S["p0"], dy1, gs)
     dp0 = ops.convs2_dgrad_nhwc(dy1, d1[0])
     dy0 = ops.in_backward_pad(dp0, S["y0"], *S["n0"], 0, ACT_RELU)
     dw_stem, dx = ops.stem_backward(dy0, S["cols"], stem[0], gs, want_dx)
+    side.join()
 
     grads = [dw_stem, zero(stem[1]), dw_d1, zero(d1[1]), dw_d2, zero(d2[1])]
     for g in block_grads:
