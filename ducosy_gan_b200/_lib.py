@@ -109,6 +109,8 @@ SIGNATURES = {
     "ducosy_metrics_slice_stats": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p]),
     "ducosy_metrics_ed": (_i, [_p, _p, _i, _i, _ll, _p, _p, _p, _p]),
     "ducosy_metrics_normalize": (_i, [_p, _i, _p, _ll, _p, _p]),
+    "ducosy_metrics_emd_i16": (_i, [_p, _p, _i, _ll, _i, _i, _p, _p, _p]),
+    "ducosy_metrics_ts": (_i, [_p, _p, _i, _i, _i, _i, _p, _p, _p]),
     "ducosy_metrics_ssim_tiles": (_i, [_i, _i]),
     "ducosy_metrics_ssim": (_i, [_p, _p, _i, _i, _i, _i, C.c_double, _p, _p, _p]),
     "ducosy_postprocess_volume": (_i, [_p, _p, _p, _i, _i, _i, _p, _i, _p, _i, _p, _i, C.c_double, _f, _i, _i, _i, _p]),

@@ -188,6 +188,124 @@ metrics_ssim_kernel(const In* __restrict__ a, const In* __restrict__ b, int H, i
   }
 }
 
+// ---- calculate_emd (calculate.py:320-337) for int16 volumes.  scipy.stats.wasserstein_distance of two equal-weight samples is
+// the integral of |CDF1 - CDF2|; the reference normalises both slices with the same affine map first, so on integer-valued data
+//     d = sum_v |C1(v) - C2(v)| / n / (global_max - global_min + 1e-8),      C = cumulative histogram of the raw values
+// -- integer arithmetic up to the final division (verified to the last bit against scipy).  hist: [S][2][R] zeroed counters.
+__global__ void __launch_bounds__(kThreads)
+metrics_hist_kernel(const int16_t* __restrict__ a, const int16_t* __restrict__ b, long long n, int chunks, int vmin, int R,
+                    unsigned int* __restrict__ hist) {
+  pdl_prologue();
+  const int s = blockIdx.y, c = blockIdx.x;
+  const long long per = (n + chunks - 1) / chunks;
+  const long long lo = c * per, hi = lo + per < n ? lo + per : n;
+  unsigned int* ha = hist + (size_t(s) * 2 + 0) * R;
+  unsigned int* hb = hist + (size_t(s) * 2 + 1) * R;
+  for (long long i = lo + threadIdx.x; i < hi; i += kThreads) {
+    atomicAdd(ha + (int(a[(long long)s * n + i]) - vmin), 1u);   // integer counters: the order of the atomics does not matter
+    atomicAdd(hb + (int(b[(long long)s * n + i]) - vmin), 1u);
+  }
+}
+
+// one CTA per slice: out[s] = sum_v |C1(v) - C2(v)|  (exact in double: < 2^53)
+__global__ void __launch_bounds__(kThreads)
+metrics_emd_scan_kernel(const unsigned int* __restrict__ hist, int R, double* __restrict__ out) {
+  pdl_prologue();
+  __shared__ long long wsum[kThreads / 32];
+  __shared__ long long carry_s;
+  __shared__ double red[kThreads / 32];
+  const int s = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const unsigned int* ha = hist + (size_t(s) * 2 + 0) * R;
+  const unsigned int* hb = hist + (size_t(s) * 2 + 1) * R;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  double acc = 0.0;
+  for (int v0 = 0; v0 < R; v0 += kThreads) {
+    const int v = v0 + threadIdx.x;
+    long long d = v < R ? (long long)ha[v] - (long long)hb[v] : 0;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {          // inclusive scan inside the warp
+      const long long t = __shfl_up_sync(0xffffffffu, d, o);
+      if (lane >= o) d += t;
+    }
+    if (lane == 31) wsum[warp] = d;
+    __syncthreads();
+    long long before = carry_s;
+    for (int w = 0; w < warp; ++w) before += wsum[w];
+    if (v < R) acc += double(llabs(d + before));
+    __syncthreads();
+    if (threadIdx.x == kThreads - 1) carry_s = before + d;
+    __syncthreads();
+  }
+  acc = warp_sum(acc);
+  if (lane == 0) red[warp] = acc;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = red[0];
+    for (int w = 1; w < kThreads / 32; ++w) t += red[w];
+    out[s] = t;
+  }
+}
+
+// ---- calculate_ts (calculate.py:340-358): skimage.filters.sobel of both slices (separable: [1,2,1]/4 smoothing x [1,0,-1]
+// difference, boundary mode 'reflect', magnitude sqrt((gx^2 + gy^2)/2)); per (slice, CTA) partials of sum |g1 - g2|, max g1,
+// max g2.  TS is a ratio of gradient magnitudes, so skimage's int -> float rescaling of the input cancels.  PARITY UNPINNED
+// (scikit-image absent): restated from its published implementation (versions >= 0.18, which no longer zero the border).
+template <typename In>
+__global__ void __launch_bounds__(kThreads)
+metrics_ts_kernel(const In* __restrict__ a, const In* __restrict__ b, int H, int W, int rows_per_cta, double* __restrict__ part) {
+  pdl_prologue();
+  const int s = blockIdx.y;
+  const int y0 = blockIdx.x * rows_per_cta, y1 = min(H, y0 + rows_per_cta);
+  const In* pa = a + (long long)s * H * W;
+  const In* pb = b + (long long)s * H * W;
+  auto rf = [](int i, int n) { return i < 0 ? 0 : (i >= n ? n - 1 : i); };   // scipy 'reflect' at distance 1: (a | a b ... y z | z)
+  double acc = 0.0, m1 = 0.0, m2 = 0.0;
+  for (int i = y0 * W + threadIdx.x; i < y1 * W; i += kThreads) {
+    const int y = i / W, x = i - y * W;
+    const int ym = rf(y - 1, H), yp = rf(y + 1, H), xm = rf(x - 1, W), xp = rf(x + 1, W);
+    auto mag = [&](const In* p) {
+      const double a00 = double(p[ym * W + xm]), a01 = double(p[ym * W + x]), a02 = double(p[ym * W + xp]);
+      const double a10 = double(p[y * W + xm]), a12 = double(p[y * W + xp]);
+      const double a20 = double(p[yp * W + xm]), a21 = double(p[yp * W + x]), a22 = double(p[yp * W + xp]);
+      const double gy = ((a00 + 2.0 * a01 + a02) - (a20 + 2.0 * a21 + a22)) * 0.25;   // edge along axis 0, smoothed along axis 1
+      const double gx = ((a00 + 2.0 * a10 + a20) - (a02 + 2.0 * a12 + a22)) * 0.25;
+      return sqrt((gx * gx + gy * gy) * 0.5);
+    };
+    const double g1 = mag(pa), g2 = mag(pb);
+    acc += fabs(g1 - g2);
+    m1 = fmax(m1, g1);
+    m2 = fmax(m2, g2);
+  }
+  __shared__ double sh[kThreads / 32][3];
+  acc = warp_sum(acc); m1 = warp_max(m1); m2 = warp_max(m2);
+  if ((threadIdx.x & 31) == 0) { sh[threadIdx.x >> 5][0] = acc; sh[threadIdx.x >> 5][1] = m1; sh[threadIdx.x >> 5][2] = m2; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kThreads / 32; ++w) { acc += sh[w][0]; m1 = fmax(m1, sh[w][1]); m2 = fmax(m2, sh[w][2]); }
+    double* dst = part + ((long long)s * gridDim.x + blockIdx.x) * 3;
+    dst[0] = acc;                            // warp 0's sum + the other warps' in index order (fixed order)
+    dst[1] = m1;
+    dst[2] = m2;
+  }
+}
+
+__global__ void metrics_ts_finalize_kernel(const double* __restrict__ part, int S, int ctas, double* __restrict__ out) {
+  pdl_prologue();
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= S) return;
+  double acc = 0.0, m1 = 0.0, m2 = 0.0;
+  for (int c = 0; c < ctas; ++c) {
+    const double* p = part + ((long long)s * ctas + c) * 3;
+    acc += p[0];
+    m1 = fmax(m1, p[1]);
+    m2 = fmax(m2, p[2]);
+  }
+  out[s * 3 + 0] = acc;
+  out[s * 3 + 1] = m1;
+  out[s * 3 + 2] = m2;
+}
+
 int pick_chunks(long long n) {
   long long c = n / 8192;
   if (c < 1) c = 1;
@@ -265,4 +383,33 @@ extern "C" int ducosy_metrics_ssim(const void* a, const void* b, int in_type, in
   DUCOSY_TRY(check_launch("metrics_ssim_kernel"));
   pdl(metrics_finalize_kernel, (S + 255) / 256, 256, 0, st)(scratch, S, gx * gy, 1, ssim_sums);
   return check_launch("metrics_finalize_kernel");
+}
+
+/* calculate_emd for int16 volumes: hist = S*2*R zeroed uint32 counters (R = global max - global min + 1, vmin = global min);
+ * cdf_abs_sums[S] = sum_v |C1(v) - C2(v)| per slice. */
+extern "C" int ducosy_metrics_emd_i16(const int16_t* a, const int16_t* b, int S, long long n, int vmin, int R, unsigned int* hist,
+                                      double* cdf_abs_sums, ducosy_stream_t stream) {
+  DUCOSY_CHECK(a && b && hist && cdf_abs_sums && S > 0 && n > 0 && R > 0 && R <= 65536, DUCOSY_ERR_ARG, "metrics_emd_i16: bad argument");
+  DUCOSY_CHECK(S <= 65535, DUCOSY_ERR_SHAPE, "metrics_emd_i16: at most 65535 slices per call");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int chunks = pick_chunks(n);
+  pdl(metrics_hist_kernel, dim3(chunks, S), kThreads, 0, st)(a, b, n, chunks, vmin, R, hist);
+  DUCOSY_TRY(check_launch("metrics_hist_kernel"));
+  pdl(metrics_emd_scan_kernel, S, kThreads, 0, st)(hist, R, cdf_abs_sums);
+  return check_launch("metrics_emd_scan_kernel");
+}
+
+/* calculate_ts: ts_stats[S][3] = per slice (sum |sobel(a) - sobel(b)|, max sobel(a), max sobel(b)); scratch: S * ceil(H/8) * 3 doubles. */
+extern "C" int ducosy_metrics_ts(const void* a, const void* b, int in_type, int S, int H, int W, double* ts_stats, double* scratch,
+                                 ducosy_stream_t stream) {
+  DUCOSY_CHECK(a && b && ts_stats && scratch && S > 0 && H > 0 && W > 0, DUCOSY_ERR_ARG, "metrics_ts: bad argument");
+  DUCOSY_CHECK(in_type >= DUCOSY_IN_I16 && in_type <= DUCOSY_IN_F64, DUCOSY_ERR_ARG, "metrics_ts: bad input type");
+  DUCOSY_CHECK(S <= 65535 && (long long)H * W < (1LL << 31), DUCOSY_ERR_SHAPE, "metrics_ts: volume too large for one call");
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int rows = 8, ctas = (H + rows - 1) / rows;
+  DUCOSY_DISPATCH_IN(in_type, In, (pdl(metrics_ts_kernel<In>, dim3(ctas, S), kThreads, 0, st)(
+                                      static_cast<const In*>(a), static_cast<const In*>(b), H, W, rows, scratch)));
+  DUCOSY_TRY(check_launch("metrics_ts_kernel"));
+  pdl(metrics_ts_finalize_kernel, (S + 255) / 256, 256, 0, st)(scratch, S, ctas, ts_stats);
+  return check_launch("metrics_ts_finalize_kernel");
 }

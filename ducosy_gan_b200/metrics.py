@@ -7,11 +7,14 @@ with the same names, arguments and return values -- ``(mean, per-slice list)`` -
     calculate_ssim(img1, img2)     calculate.py:265-272  (skimage.metrics.structural_similarity defaults, data_range of img2)
     calculate_cs(img1, img2)       calculate.py:360-367  (sklearn cosine_similarity of the flattened slices)
     calculate_ed(img1, img2)       calculate.py:369-381
+    calculate_emd(img1, img2)      calculate.py:320-337  (scipy wasserstein_distance of the jointly normalised slices; int16
+                                   volumes: cumulative histograms, integer-exact; float volumes: sorted samples)
+    calculate_ts(img1, img2)       calculate.py:340-358  (skimage.filters.sobel magnitudes; parity unpinned, scikit-image absent)
 
 Inputs are [S,H,W] volumes: numpy arrays (copied to the current CUDA device) or CUDA tensors, int16 (the stored pixel arrays
 calculate.py:226-228 saves), float32 or float64.  Arithmetic is float64 like numpy's; int16 volumes reproduce numpy's int16
 wrap-around in ``img1 - img2`` / ``(img1 - img2) ** 2`` (a reference quirk: the raw-HU MAE / PSNR rows are computed that way).
-Not built: EMD (a per-slice sort), TS (skimage sobel), MS-SSIM / LPIPS (third-party networks, absent here).
+Not built: MS-SSIM / LPIPS (third-party networks, absent here).
 ``volume_metrics`` evaluates everything in one pass over the pair.
 """
 from __future__ import annotations
@@ -158,9 +161,48 @@ def calculate_ed(img1, img2):
     return _ed(a, b, _stats(a, b))
 
 
+def calculate_emd(img1, img2):
+    a, b = _pair(img1, img2)
+    S, H, W = a.shape
+    n = H * W
+    st = _stats(a, b).cpu()
+    gmin = min(float(st[:, 7].min()), float(st[:, 9].min()))
+    gmax = max(float(st[:, 8].max()), float(st[:, 10].max()))
+    rng = _wrap16(gmax - gmin, a.dtype) + 1e-8
+    with torch.cuda.device(a.device):
+        if a.dtype == torch.int16:
+            R = int(gmax) - int(gmin) + 1
+            hist = torch.zeros(S * 2 * R, dtype=torch.int32, device=a.device)
+            sums = torch.empty(S, dtype=torch.float64, device=a.device)
+            call("ducosy_metrics_emd_i16", ptr(a), ptr(b), S, n, int(gmin), R, ptr(hist), ptr(sums), stream_ptr())
+            d = sums.cpu() / n / rng
+        else:
+            # float volumes: W1 of two equal-size samples = mean |sorted difference| (the sort is torch's library sort; this
+            # branch is not on any measured path)
+            sa = torch.sort(a.reshape(S, -1).to(torch.float64), dim=1).values
+            sb = torch.sort(b.reshape(S, -1).to(torch.float64), dim=1).values
+            d = ((sa - sb).abs().mean(dim=1) / rng).cpu()
+    v = d / n          # "scale by number of pixels" (calculate.py:334-335)
+    return float(v.mean()), v.tolist()
+
+
+def calculate_ts(img1, img2):
+    a, b = _pair(img1, img2)
+    S, H, W = a.shape
+    with torch.cuda.device(a.device):
+        stats = torch.empty((S, 3), dtype=torch.float64, device=a.device)
+        scratch = torch.empty(S * ((H + 7) // 8) * 3, dtype=torch.float64, device=a.device)
+        call("ducosy_metrics_ts", ptr(a), ptr(b), _IN[a.dtype], S, H, W, ptr(stats), ptr(scratch), stream_ptr())
+    st = stats.cpu()
+    diff = st[:, 0] / (H * W)
+    mx = torch.maximum(st[:, 1], st[:, 2])
+    v = 1.0 - torch.where(mx > 0, diff / torch.where(mx > 0, mx, torch.ones_like(mx)), torch.zeros_like(mx))
+    return float(v.mean()), v.tolist()
+
+
 def volume_metrics(target, pred):
     """What process_single_patient (calculate.py:383-470) computes for one (target, prediction) pair, minus the metrics listed
-    as not built: raw and normalised MAE / PSNR / SSIM plus CS and ED; every entry is ``(mean, per-slice list)``."""
+    as not built: raw and normalised MAE / PSNR / SSIM plus CS, ED, EMD and TS; every entry is ``(mean, per-slice list)``."""
     a, b = _pair(target, pred)
     n = a.shape[1] * a.shape[2]
     out = {}
@@ -168,10 +210,12 @@ def volume_metrics(target, pred):
     st = st_dev.cpu()
     out["mae"], out["psnr"], out["ssim"] = _mae(st, n), _psnr(st, n, a.dtype), _ssim(a, b, st)
     out["cs"], out["ed"] = _cs(st), _ed(a, b, st_dev)
+    out["emd"], out["ts"] = calculate_emd(a, b), calculate_ts(a, b)
     an, bn = normalize(a), normalize(b)
     stn = _stats(an, bn).cpu()
     out["mae_norm"], out["psnr_norm"], out["ssim_norm"] = _mae(stn, n), _psnr(stn, n, an.dtype), _ssim(an, bn, stn)
     return out
 
 
-__all__ = ["normalize", "calculate_mae", "calculate_psnr", "calculate_ssim", "calculate_cs", "calculate_ed", "volume_metrics"]
+__all__ = ["normalize", "calculate_mae", "calculate_psnr", "calculate_ssim", "calculate_cs", "calculate_ed", "calculate_emd",
+           "calculate_ts", "volume_metrics"]

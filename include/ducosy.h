@@ -496,6 +496,15 @@ int ducosy_metrics_ed(const void* a, const void* b, int in_type, int S, long lon
  * minmax: 2 doubles in DEVICE memory. */
 int ducosy_metrics_normalize(const void* in, int in_type, double* out, long long total, const double* minmax,
                              ducosy_stream_t stream);
+/* calculate_emd (calculate.py:320-337) for int16 volumes, integer-exact: cdf_abs_sums[S] = sum_v |C1(v) - C2(v)| over the
+ * R = global max - global min + 1 value bins (vmin = global min of both volumes); hist: S*2*R ZEROED uint32 counters.
+ * The per-slice distance is cdf_abs_sums / n / (range + 1e-8), the reference's scaled value that / n again. */
+int ducosy_metrics_emd_i16(const int16_t* a, const int16_t* b, int S, long long n, int vmin, int R, unsigned int* hist,
+                           double* cdf_abs_sums, ducosy_stream_t stream);
+/* calculate_ts (calculate.py:340-358): ts_stats[S][3] = per slice (sum |sobel(a) - sobel(b)|, max sobel(a), max sobel(b)) with
+ * skimage.filters.sobel's arithmetic (PARITY UNPINNED: scikit-image absent); scratch: S * ceil(H / 8) * 3 doubles. */
+int ducosy_metrics_ts(const void* a, const void* b, int in_type, int S, int H, int W, double* ts_stats, double* scratch,
+                      ducosy_stream_t stream);
 int ducosy_metrics_ssim_tiles(int H, int W);
 /* ssim_sums[S] = sum of the SSIM map over the valid region [3, H-3) x [3, W-3) of each slice pair; mean = / ((H-6)(W-6)). */
 int ducosy_metrics_ssim(const void* a, const void* b, int in_type, int S, int H, int W, double data_range, double* ssim_sums,

@@ -703,3 +703,38 @@ def metric_ed(img1, img2):
         b = (s2 - s2.min()) / (s2.max() - s2.min() + 1e-8)
         out.append(np.linalg.norm(a - b) / np.prod(a.shape))
     return np.mean(out), out
+
+
+def metric_emd(img1, img2):
+    """calculate.py:320-337 (scipy.stats.wasserstein_distance is present here: pinned)."""
+    from scipy.stats import wasserstein_distance
+    gmin, gmax = min(img1.min(), img2.min()), max(img1.max(), img2.max())
+    out = []
+    for s1, s2 in zip(img1, img2):
+        a = (s1 - gmin) / (gmax - gmin + 1e-8)
+        b = (s2 - gmin) / (gmax - gmin + 1e-8)
+        out.append(wasserstein_distance(a.flatten(), b.flatten()) / np.prod(s1.shape))
+    return np.mean(out), out
+
+
+def skimage_sobel(image):
+    """skimage.filters.sobel (>= 0.18, mask=None, mode='reflect') up to the constant factor of its int -> float conversion, which
+    calculate_ts's ratio cancels: separable [1,2,1]/4 smoothing x [1,0,-1] difference per axis, sqrt(mean of squares).
+    PARITY UNPINNED: scikit-image is absent here."""
+    from scipy import ndimage as ndi
+    img = image.astype(np.float64)
+    sm, ed = np.array([1.0, 2.0, 1.0]) / 4.0, np.array([1.0, 0.0, -1.0])
+    g0 = ndi.correlate1d(ndi.correlate1d(img, ed, axis=0, mode="reflect"), sm, axis=1, mode="reflect")
+    g1 = ndi.correlate1d(ndi.correlate1d(img, ed, axis=1, mode="reflect"), sm, axis=0, mode="reflect")
+    return np.sqrt((g0 * g0 + g1 * g1) / 2.0)
+
+
+def metric_ts(img1, img2):
+    """calculate.py:340-358."""
+    out = []
+    for s1, s2 in zip(img1, img2):
+        g1, g2 = skimage_sobel(s1), skimage_sobel(s2)
+        diff = np.mean(np.abs(g1 - g2))
+        mx = np.max([np.abs(g1).max(), np.abs(g2).max()])
+        out.append(1.0 - (diff / mx if mx > 0 else 0))
+    return np.mean(out), out

@@ -1,8 +1,9 @@
 """Golden values for the image-quality metrics: imports the reference's own calculate.py -- unmodified;
 its third-party imports that are absent here (pydicom, skimage, matplotlib, seaborn) are stubbed, and
 skimage.metrics.structural_similarity is stubbed BY THE ORACLE'S RESTATEMENT, so calculate_ssim's own loop / data_range logic
-runs but the SSIM core stays "parity unpinned" -- and runs calculate_mae / calculate_psnr / calculate_ssim / calculate_cs /
-calculate_ed / normalize on seeded int16 volumes and on their normalised float64 forms.  Checks the oracle restatements against
+runs but the SSIM core stays "parity unpinned" (likewise skimage.filters.sobel for calculate_ts) -- and runs calculate_mae /
+calculate_psnr / calculate_ssim / calculate_cs / calculate_ed / calculate_emd / calculate_ts / normalize on seeded int16 volumes
+and (the basic metrics) on their normalised float64 forms.  calculate_emd runs on the real scipy.stats.wasserstein_distance.  Checks the oracle restatements against
 them and stores the values in tests/golden/metrics.npz.
 usage: python oracle/make_golden_metrics.py   (in the container that has /root/reference)      TEST INFRASTRUCTURE ONLY."""
 import importlib.util
@@ -29,7 +30,7 @@ def _stub(name, **attrs):
 _stub("pydicom")
 _stub("skimage")
 _stub("skimage.metrics", structural_similarity=lambda a, b, data_range: orc.skimage_structural_similarity(a, b, data_range))
-_stub("skimage.filters", sobel=None)
+_stub("skimage.filters", sobel=lambda img: orc.skimage_sobel(img))       # TS core: the oracle's restatement (unpinned)
 mpl = _stub("matplotlib", use=lambda *a, **k: None)
 mpl.pyplot = _stub("matplotlib.pyplot")
 _stub("seaborn")
@@ -51,7 +52,7 @@ def main():
         assert np.array_equal(tn, orc.metric_normalize(tgt))
         out[f"shape_{name}"] = np.array([S, H, W, seed])
         for tag, (x, y) in {"raw": (tgt, pred), "norm": (tn, pn)}.items():
-            for metric in ("mae", "psnr", "ssim", "cs", "ed"):
+            for metric in ("mae", "psnr", "ssim", "cs", "ed") + (("emd", "ts") if tag == "raw" else ()):   # advanced pairs: raw only (calculate.py:457-463)
                 m, lst = getattr(ref, f"calculate_{metric}")(x, y)
                 om, olst = getattr(orc, f"metric_{metric}")(x, y)
                 assert np.allclose(np.asarray(lst, dtype=np.float64), np.asarray(olst, dtype=np.float64), rtol=1e-12, atol=0, equal_nan=True), (name, tag, metric)

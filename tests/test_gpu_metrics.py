@@ -31,8 +31,10 @@ def test_metrics_match_reference_golden(golden_dir, name):
     tgt, pred = orc.metrics_test_volumes(S, H, W, seed)
     t, p = torch.from_numpy(tgt).cuda(), torch.from_numpy(pred).cuda()
     for tag, (x, y) in {"raw": (t, p), "norm": (metrics.normalize(t), metrics.normalize(p))}.items():
-        for metric in ("mae", "psnr", "ssim", "cs", "ed"):
+        for metric in ("mae", "psnr", "ssim", "cs", "ed") + (("emd", "ts") if tag == "raw" else ()):
             _check(getattr(metrics, f"calculate_{metric}")(x, y), g[f"{metric}_{tag}_{name}"])
+    # EMD of float volumes (sorted-sample branch) == the histogram branch on the same values
+    _check(metrics.calculate_emd(t.double(), p.double()), g[f"emd_raw_{name}"], rtol=1e-9)
     # int16 MAE is integer arithmetic end to end: bit-exact
     assert metrics.calculate_mae(t, p)[0] == g[f"mae_raw_{name}"][0]
     assert np.array_equal(metrics.normalize(t).cpu().numpy(), orc.metric_normalize(tgt))
@@ -46,7 +48,7 @@ def test_volume_metrics_full_size_vs_oracle():
     out = metrics.volume_metrics(tgt, pred)
     warnings.simplefilter("ignore")
     tn, pn = orc.metric_normalize(tgt), orc.metric_normalize(pred)
-    for key, fn, (x, y) in [("mae", orc.metric_mae, (tgt, pred)), ("psnr", orc.metric_psnr, (tgt, pred)), ("ssim", orc.metric_ssim, (tgt, pred)),
+    for key, fn, (x, y) in [("emd", orc.metric_emd, (tgt, pred)), ("ts", orc.metric_ts, (tgt, pred)), ("mae", orc.metric_mae, (tgt, pred)), ("psnr", orc.metric_psnr, (tgt, pred)), ("ssim", orc.metric_ssim, (tgt, pred)),
                             ("cs", orc.metric_cs, (tgt, pred)), ("ed", orc.metric_ed, (tgt, pred)), ("mae_norm", orc.metric_mae, (tn, pn)),
                             ("psnr_norm", orc.metric_psnr, (tn, pn)), ("ssim_norm", orc.metric_ssim, (tn, pn))]:
         m, lst = fn(x, y)
