@@ -128,6 +128,9 @@ SIGNATURES = {
     "ducosy_binary_fill_holes": (_i, [_p, _p, _i, _i, _i, _p, _sz, _p]),
     "ducosy_detect_lung": (_i, [_p, _p, _i, _i, _i, _f, _f, _i, _i, _p, _sz, _p]),
     "ducosy_detect_lung_vessels": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _sz, _p]),
+    "ducosy_lung_hull": (_i, [_p, _p, _p, _p, _i, _i, _i, _p, _sz, _p]),
+    "ducosy_detect_mediastinum": (_i, [_p, _p, _p, _i, _i, _i, _f, _f, _p, _sz, _p]),
+    "ducosy_detect_bone": (_i, [_p, _p, _p, _i, _i, _i, _f, _i, _p, _sz, _p]),
     "ducosy_adam_multi_step": (_i, [_p, _p, _i, _p, _f, _f, _f, _i, _p]),
     "ducosy_cbam_channel_train": (_i, [_p] * 9 + [_i, _i, _p]),
     "ducosy_cbam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),

@@ -1,11 +1,11 @@
-// Anatomical-mask primitives for training batches (first half): the scipy.ndimage pieces of the reference's
+// Anatomical-mask primitives for training batches: the scipy.ndimage / scipy.spatial / matplotlib.path pieces of the reference's
 // modules/mask_generator.py on the GPU, bit-exact, for batches of 2-D slices:
 //   label4        ndimage.label, default structure (4-connectivity), scipy's numbering      mask_generator.py:32,46,64,85
 //   fill_holes    ndimage.binary_fill_holes, default structure                              mask_generator.py:69,90,242,310
 //   detect_lung   thresholds + border margin + small-component removal                      mask_generator.py:11-52
 //   detect_lung_vessels  component count / area test + (fill_holes - lung) & HU range       mask_generator.py:55-99
-// The convex-hull rasterisation of detect_mediastinum / detect_bone (scipy.spatial.ConvexHull + matplotlib.path edge
-// semantics) is the second half of the row and is not built here.
+//   lung_hull / detect_mediastinum / detect_bone   ConvexHull vertices + Path.contains_points, region growing  mask_generator.py:100-311
+// (the hull part is at the end of this file; matplotlib's rasterisation is restated, parity-unpinned).
 //
 // Connected components: union-find over the pixels of a slice (Komura / Playne-Hawick style).  Every foreground pixel
 // starts as its own root; a pixel is united with its left and upper foreground neighbours by atomicMin on the parent
@@ -223,6 +223,121 @@ __global__ void __launch_bounds__(kT) vessel_kernel(const float* __restrict__ hu
   }
 }
 
+// ---- second half: convex hull of the lung pixels of a slice (mask_generator.py:115-127,204-216) ------------------------------
+// scipy.spatial.ConvexHull(np.argwhere(lung == 1)).vertices are the strictly convex corners of the pixel set in
+// counter-clockwise order (coordinates (row, col)).  Only the leftmost and rightmost lung pixel of every row can be corners, so:
+// per-row extreme columns (shared-memory atomics), then Andrew's monotone chain over those <= 2H candidates by one thread
+// (already sorted by row, then column; collinear points are popped, as qhull reports only true vertices), counter-clockwise,
+// integer cross products.  nverts = 0 marks the reference's fallback branches (fewer than 3 pixels / QhullError on a
+// degenerate set): the callers then use the lung mask itself as "hull".
+__global__ void __launch_bounds__(kT) hull_build_kernel(const uint8_t* __restrict__ lung, int* __restrict__ cand, int* __restrict__ verts,
+                                                        int* __restrict__ nverts, int H, int W, int maxV) {
+  pdl_prologue();
+  extern __shared__ int hull_sm[];      // [H] min column, [H] max column
+  int* minc = hull_sm;
+  int* maxc = hull_sm + H;
+  const int s = blockIdx.x;
+  for (int r = threadIdx.x; r < H; r += kT) { minc[r] = 0x7fffffff; maxc[r] = -1; }
+  __syncthreads();
+  const uint8_t* m = lung + (long long)s * H * W;
+  for (int p = threadIdx.x; p < H * W; p += kT)
+    if (m[p] != 0) {
+      const int y = p / W, x = p - y * W;
+      atomicMin(&minc[y], x);
+      atomicMax(&maxc[y], x);
+    }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
+  int* c = cand + (long long)s * maxV * 2;
+  int* v = verts + (long long)s * maxV * 2;
+  int nc = 0;
+  for (int r = 0; r < H; ++r)
+    if (maxc[r] >= 0) {
+      c[2 * nc] = r; c[2 * nc + 1] = minc[r]; ++nc;
+      if (maxc[r] != minc[r]) { c[2 * nc] = r; c[2 * nc + 1] = maxc[r]; ++nc; }
+    }
+  auto cross = [&](int o, int a, const int* b) {   // (v[a] - v[o]) x (b - v[o])
+    return (long long)(v[2 * a] - v[2 * o]) * (b[1] - v[2 * o + 1]) - (long long)(v[2 * a + 1] - v[2 * o + 1]) * (b[0] - v[2 * o]);
+  };
+  int k = 0;
+  for (int i = 0; i < nc; ++i) {                   // lower chain
+    while (k >= 2 && cross(k - 2, k - 1, c + 2 * i) <= 0) --k;
+    v[2 * k] = c[2 * i]; v[2 * k + 1] = c[2 * i + 1]; ++k;
+  }
+  const int t = k + 1;
+  for (int i = nc - 2; i >= 0; --i) {              // upper chain
+    while (k >= t && cross(k - 2, k - 1, c + 2 * i) <= 0) --k;
+    v[2 * k] = c[2 * i]; v[2 * k + 1] = c[2 * i + 1]; ++k;
+  }
+  const int nv = k - 1;                            // the last point repeats the first
+  nverts[s] = (nc >= 3 && nv >= 3) ? nv : 0;
+}
+
+// hull_mask = matplotlib.path.Path(vertices).contains_points(every pixel) -- the crossings test of matplotlib's
+// point_in_path_impl with its inequality conventions (points exactly on the boundary depend on them; PARITY UNPINNED,
+// matplotlib is absent here; restated in oracle.path_contains_points).  Path coordinates: x = row, y = column.  Integer
+// arithmetic (all products < 2^31).  nverts == 0: hull_mask = lung (the reference's fallback).
+__global__ void __launch_bounds__(kT) hull_raster_kernel(const int* __restrict__ verts, const int* __restrict__ nverts,
+                                                         const uint8_t* __restrict__ lung, uint8_t* __restrict__ hull, int H, int W, int maxV) {
+  pdl_prologue();
+  extern __shared__ int hull_sm[];      // [nv][2]
+  const int s = blockIdx.y, nv = nverts[s];
+  const int* v = verts + (long long)s * maxV * 2;
+  for (int i = threadIdx.x; i < 2 * nv; i += kT) hull_sm[i] = v[i];
+  __syncthreads();
+  for (int p = blockIdx.x * kT + threadIdx.x; p < H * W; p += gridDim.x * kT) {
+    const long long g = (long long)s * H * W + p;
+    if (nv == 0) { hull[g] = lung[g]; continue; }
+    const int tx = p / W, ty = p - tx * W;
+    int inside = 0;
+    int x0 = hull_sm[2 * (nv - 1)], y0 = hull_sm[2 * (nv - 1) + 1];
+    for (int i = 0; i < nv; ++i) {
+      const int x1 = hull_sm[2 * i], y1 = hull_sm[2 * i + 1];
+      const bool f0 = y0 >= ty, f1 = y1 >= ty;
+      if (f0 != f1 && (((y1 - ty) * (x0 - x1) >= (x1 - tx) * (y0 - y1)) == f1)) inside ^= 1;
+      x0 = x1; y0 = y1;
+    }
+    hull[g] = uint8_t(inside);
+  }
+}
+
+// bone candidates (hu >= threshold) & (hu > -1000)   (mask_generator.py:177-179)
+__global__ void __launch_bounds__(kT) bone_candidate_kernel(const float* __restrict__ hu, uint8_t* __restrict__ cand, long long n, float thr) {
+  pdl_prologue();
+  for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
+    const float v = hu[g];
+    cand[g] = (v >= thr && v > -1000.f) ? 1 : 0;
+  }
+}
+// reduced = cand & ~(hull & ~lung & rows above the preserved spine rows) on slices that pass the plausibility test and have a
+// real hull   (mask_generator.py:200-228)
+__global__ void __launch_bounds__(kT) bone_reduce_kernel(const uint8_t* __restrict__ cand, const uint8_t* __restrict__ hull,
+                                                         const uint8_t* __restrict__ lung, const int* __restrict__ num_regions,
+                                                         const int* __restrict__ body_area, const int* __restrict__ lung_area,
+                                                         const int* __restrict__ nverts, uint8_t* __restrict__ reduced, int H, int W,
+                                                         long long n, int spine_start) {
+  pdl_prologue();
+  const int HW = H * W;
+  for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT) {
+    const int s = int(g / HW), y = int(g % HW) / W;
+    const bool ok = num_regions[s] >= 2 && body_area[s] > 0 && (double(lung_area[s]) / double(body_area[s])) >= 0.1 && nverts[s] > 0;
+    const bool region = ok && hull[g] != 0 && lung[g] == 0 && y < spine_start;
+    reduced[g] = (cand[g] != 0 && !region) ? 1 : 0;
+  }
+}
+// region growing (mask_generator.py:230-246): a component of the candidates is kept whole when any of its pixels survived
+__global__ void __launch_bounds__(kT) touch_kernel(const int* __restrict__ L, const uint8_t* __restrict__ reduced, int* __restrict__ flag, long long n) {
+  pdl_prologue();
+  for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT)
+    if (reduced[g] != 0 && L[g] >= 0) flag[L[g]] = 1;     // every writer stores the same value
+}
+__global__ void __launch_bounds__(kT) bone_select_kernel(const uint8_t* __restrict__ cand, const int* __restrict__ L, const int* __restrict__ flag,
+                                                         uint8_t* __restrict__ out, long long n) {
+  pdl_prologue();
+  for (long long g = (long long)blockIdx.x * kT + threadIdx.x; g < n; g += (long long)gridDim.x * kT)
+    out[g] = (cand[g] != 0 && L[g] >= 0 && flag[L[g]] != 0) ? 1 : 0;
+}
+
 int ew_grid(long long n) {
   const long long cap = (long long)(num_sms() > 0 ? num_sms() : 148) * 8;
   const long long b = (n + kT - 1) / kT;
@@ -230,10 +345,11 @@ int ew_grid(long long n) {
 }
 
 struct Scratch {
-  int *L, *aux, *chunk, *num, *area_a, *area_b;
+  int *L, *aux, *chunk, *num, *area_a, *area_b, *hull_cand, *hull_verts, *hull_n;
   uint8_t *u8a, *u8b, *u8c;
   size_t total;
 };
+inline int hull_max_verts(int H) { return 2 * H + 4; }
 Scratch carve(void* base, int B, int H, int W) {
   const size_t n = size_t(B) * H * W;
   const size_t chunks = (size_t(H) * W + kT - 1) / kT;
@@ -254,6 +370,9 @@ Scratch carve(void* base, int B, int H, int W) {
   s.u8a = take(n);
   s.u8b = take(n);
   s.u8c = take(n);
+  s.hull_cand = reinterpret_cast<int*>(take(size_t(B) * hull_max_verts(H) * 2 * 4));
+  s.hull_verts = reinterpret_cast<int*>(take(size_t(B) * hull_max_verts(H) * 2 * 4));
+  s.hull_n = reinterpret_cast<int*>(take(size_t(B) * 4));
   s.total = off;
   return s;
 }
@@ -364,4 +483,83 @@ extern "C" int ducosy_detect_lung_vessels(const float* hu, const uint8_t* lung_m
   pdl(fill_kernel, ew_grid(n), kT, 0, st)(lung_mask, s.L, s.u8a, s.u8c, n);
   pdl(vessel_kernel, ew_grid(n), kT, 0, st)(hu, lung_mask, s.u8c, s.num, s.area_a, s.area_b, vessel_mask, HW, n, vessel_lower, vessel_upper);
   return check_launch("vessel_kernel");
+}
+
+namespace {
+// plausibility inputs of a slice (component count of the lung mask, body / lung areas) and the rasterised hull into s.u8c;
+// s.u8b receives the body mask.  Uses s.L, s.chunk, s.num, s.area_*, s.hull_*.
+int run_hull(const float* hu, const uint8_t* lung_mask, const ducosy::Scratch& s, int B, int H, int W, cudaStream_t st) {
+  const long long n = (long long)B * H * W;
+  const int HW = H * W;
+  DUCOSY_CHECK(size_t(2) * H * sizeof(int) <= 48 * 1024 && size_t(2) * hull_max_verts(H) * sizeof(int) <= 48 * 1024, DUCOSY_ERR_SHAPE,
+               "lung hull: H = %d too large", H);
+  DUCOSY_TRY(run_ccl(lung_mask, 0, s.L, nullptr, nullptr, B, H, W, st));
+  DUCOSY_TRY(run_count(s.L, s.chunk, s.num, nullptr, nullptr, B, H, W, st));
+  pdl(lung_candidate_kernel, ew_grid(n), kT, 0, st)(hu, s.u8c, s.u8b, H, W, n, 0.f, -1.f, 0);   // only the body mask (u8b) is used
+  cudaMemsetAsync(s.area_a, 0, size_t(B) * 4, st);
+  cudaMemsetAsync(s.area_b, 0, size_t(B) * 4, st);
+  pdl(area_kernel, dim3(std::min((HW + kT - 1) / kT, 64), B), kT, 0, st)(s.u8b, lung_mask, s.area_a, s.area_b, HW);
+  DUCOSY_TRY(check_launch("area_kernel"));
+  const int maxV = hull_max_verts(H);
+  pdl(hull_build_kernel, B, kT, size_t(2) * H * sizeof(int), st)(lung_mask, s.hull_cand, s.hull_verts, s.hull_n, H, W, maxV);
+  DUCOSY_TRY(check_launch("hull_build_kernel"));
+  pdl(hull_raster_kernel, dim3(std::min((HW + kT - 1) / kT, 128), B), kT, size_t(2) * maxV * sizeof(int), st)(
+      s.hull_verts, s.hull_n, lung_mask, s.u8c, H, W, maxV);
+  return check_launch("hull_raster_kernel");
+}
+}  // namespace
+
+extern "C" int ducosy_lung_hull(const uint8_t* lung_mask, uint8_t* hull_mask, int32_t* verts, int32_t* nverts, int B, int H, int W,
+                                void* scratch, size_t scratch_bytes, ducosy_stream_t stream) {
+  DUCOSY_CHECK(lung_mask && hull_mask && scratch, DUCOSY_ERR_ARG, "lung_hull: null pointer");
+  DUCOSY_TRY(check_shape("lung_hull", B, H, W));
+  const Scratch s = carve(scratch, B, H, W);
+  DUCOSY_CHECK(scratch_bytes >= s.total, DUCOSY_ERR_WORKSPACE, "lung_hull: scratch %zu < required %zu bytes", scratch_bytes, s.total);
+  DUCOSY_CHECK(size_t(2) * hull_max_verts(H) * sizeof(int) <= 48 * 1024, DUCOSY_ERR_SHAPE, "lung_hull: H = %d too large", H);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const int maxV = hull_max_verts(H), HW = H * W;
+  pdl(hull_build_kernel, B, kT, size_t(2) * H * sizeof(int), st)(lung_mask, s.hull_cand, s.hull_verts, s.hull_n, H, W, maxV);
+  DUCOSY_TRY(check_launch("hull_build_kernel"));
+  pdl(hull_raster_kernel, dim3(std::min((HW + kT - 1) / kT, 128), B), kT, size_t(2) * maxV * sizeof(int), st)(
+      s.hull_verts, s.hull_n, lung_mask, hull_mask, H, W, maxV);
+  DUCOSY_TRY(check_launch("hull_raster_kernel"));
+  if (verts != nullptr) cudaMemcpyAsync(verts, s.hull_verts, size_t(B) * maxV * 2 * 4, cudaMemcpyDeviceToDevice, st);
+  if (nverts != nullptr) cudaMemcpyAsync(nverts, s.hull_n, size_t(B) * 4, cudaMemcpyDeviceToDevice, st);
+  return check_launch("lung_hull");
+}
+
+extern "C" int ducosy_detect_mediastinum(const float* hu, const uint8_t* lung_mask, uint8_t* mediastinum_mask, int B, int H, int W,
+                                         float lower, float upper, void* scratch, size_t scratch_bytes, ducosy_stream_t stream) {
+  DUCOSY_CHECK(hu && lung_mask && mediastinum_mask && scratch, DUCOSY_ERR_ARG, "detect_mediastinum: null pointer");
+  DUCOSY_TRY(check_shape("detect_mediastinum", B, H, W));
+  const Scratch s = carve(scratch, B, H, W);
+  DUCOSY_CHECK(scratch_bytes >= s.total, DUCOSY_ERR_WORKSPACE, "detect_mediastinum: scratch %zu < required %zu bytes", scratch_bytes, s.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * H * W;
+  DUCOSY_TRY(run_hull(hu, lung_mask, s, B, H, W, st));
+  // (hull - lung) & HU range on slices that pass the plausibility test: the vessel kernel with the hull in place of the filled lung
+  pdl(vessel_kernel, ew_grid(n), kT, 0, st)(hu, lung_mask, s.u8c, s.num, s.area_a, s.area_b, mediastinum_mask, H * W, n, lower, upper);
+  return check_launch("vessel_kernel(mediastinum)");
+}
+
+extern "C" int ducosy_detect_bone(const float* hu, const uint8_t* lung_mask, uint8_t* bone_mask, int B, int H, int W, float bone_threshold,
+                                  int spine_start_row, void* scratch, size_t scratch_bytes, ducosy_stream_t stream) {
+  DUCOSY_CHECK(hu && lung_mask && bone_mask && scratch, DUCOSY_ERR_ARG, "detect_bone: null pointer");
+  DUCOSY_TRY(check_shape("detect_bone", B, H, W));
+  const Scratch s = carve(scratch, B, H, W);
+  DUCOSY_CHECK(scratch_bytes >= s.total, DUCOSY_ERR_WORKSPACE, "detect_bone: scratch %zu < required %zu bytes", scratch_bytes, s.total);
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  const long long n = (long long)B * H * W;
+  DUCOSY_TRY(run_hull(hu, lung_mask, s, B, H, W, st));                      // hull in u8c, counts / areas / nverts filled
+  pdl(bone_candidate_kernel, ew_grid(n), kT, 0, st)(hu, s.u8a, n, bone_threshold);
+  pdl(bone_reduce_kernel, ew_grid(n), kT, 0, st)(s.u8a, s.u8c, lung_mask, s.num, s.area_a, s.area_b, s.hull_n, s.u8b, H, W, n, spine_start_row);
+  DUCOSY_TRY(check_launch("bone_reduce_kernel"));
+  DUCOSY_TRY(run_ccl(s.u8a, 0, s.L, nullptr, nullptr, B, H, W, st));        // components of the candidates
+  cudaMemsetAsync(s.aux, 0, size_t(n) * 4, st);
+  pdl(touch_kernel, ew_grid(n), kT, 0, st)(s.L, s.u8b, s.aux, n);
+  pdl(bone_select_kernel, ew_grid(n), kT, 0, st)(s.u8a, s.L, s.aux, s.u8c, n);
+  DUCOSY_TRY(check_launch("bone_select_kernel"));
+  DUCOSY_TRY(run_ccl(s.u8c, 1, s.L, nullptr, s.u8a, B, H, W, st));          // fill holes
+  pdl(fill_kernel, ew_grid(n), kT, 0, st)(s.u8c, s.L, s.u8a, bone_mask, n);
+  return check_launch("fill_kernel(bone)");
 }

@@ -1,4 +1,4 @@
-"""Anatomical masks for training batches on the GPU (first half): the pieces of the reference's
+"""Anatomical masks for training batches on the GPU: the reference's
 ``modules/mask_generator.py`` that are scipy.ndimage work -- connected components, hole filling, the lung mask and the
 lung-vessel mask -- bit-exact with scipy, on batches of HU slices that are already on the device.
 
@@ -7,9 +7,10 @@ The reference computes these per slice on the CPU inside the dataloader workers 
 well below what the GPUs consume.  Same names and argument meaning as the reference's functions; inputs are CUDA tensors
 ``[H,W]`` or ``[B,H,W]`` (every slice is treated on its own, exactly like the reference's 3-D branch), outputs uint8 {0,1}.
 
-Not built yet (second half of the row): the convex-hull rasterisation of ``detect_mediastinum`` / ``detect_bone``
-(``scipy.spatial.ConvexHull`` + ``matplotlib.path.Path.contains_points`` edge semantics; matplotlib is absent here, so parity
-could not be pinned) -- those two raise ``NotImplementedError`` instead of returning something approximately right.
+Second half of the row: ``detect_mediastinum`` / ``detect_bone`` on the rasterised convex hull of the lungs.  The hull
+vertices are scipy's (``scipy.spatial.ConvexHull``: pinned), labelling / hole filling are the bit-exact primitives above; the
+rasterisation follows ``matplotlib.path.Path.contains_points`` restated from matplotlib's crossings test -- matplotlib is absent
+here, so THAT step is parity-unpinned (it decides only pixels exactly on the hull's boundary).
 """
 from __future__ import annotations
 
@@ -87,18 +88,56 @@ def detect_lung_vessels(hu_volume, lung_mask, vessel_lower=-300, vessel_upper=60
     return out[0] if squeeze else out
 
 
+def _pair(hu_volume, lung_mask):
+    hu, squeeze = _as_batch(hu_volume, torch.float32)
+    lm, _ = _as_batch(lung_mask != 0, torch.uint8)
+    if lm.shape != hu.shape:
+        raise RuntimeError(f"lung_mask {tuple(lung_mask.shape)} does not match hu_volume {tuple(hu_volume.shape)}")
+    return hu, lm, squeeze
+
+
+def lung_hull(lung_mask, return_vertices=False):
+    """Rasterised convex hull of every slice's lung pixels, as mask_generator.py:115-127 builds it (ConvexHull vertices ->
+    ``Path.contains_points`` of every pixel).  ``return_vertices``: also (vertices int32 [B,2H+4,2] in scipy's counter-clockwise
+    (row, col) order, count int32 [B]; count 0 = the reference's fallback, hull == lung)."""
+    lm, squeeze = _as_batch(lung_mask != 0, torch.uint8)
+    B, H, W = lm.shape
+    with torch.cuda.device(lm.device):
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=lm.device)
+        verts = torch.zeros((B, 2 * H + 4, 2), dtype=torch.int32, device=lm.device)
+        nv = torch.zeros(B, dtype=torch.int32, device=lm.device)
+        buf, sp, sb = _scratch(B, H, W, lm.device)
+        call("ducosy_lung_hull", ptr(lm), ptr(out), ptr(verts), ptr(nv), B, H, W, sp, sb, stream_ptr())
+    out = out[0] if squeeze else out
+    return (out, verts, nv) if return_vertices else out
+
+
 def detect_mediastinum(hu_volume, lung_mask, mediastinum_lower=-300, mediastinum_upper=450):
-    raise NotImplementedError("detect_mediastinum needs the convex-hull rasterisation (ConvexHull + matplotlib Path.contains_points "
-                              "semantics) -- second half of SURVEY 8f N2, not built; there is deliberately no approximate stand-in")
+    """reference modules/mask_generator.py:100-170."""
+    hu, lm, squeeze = _pair(hu_volume, lung_mask)
+    B, H, W = hu.shape
+    with torch.cuda.device(hu.device):
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=hu.device)
+        buf, sp, sb = _scratch(B, H, W, hu.device)
+        call("ducosy_detect_mediastinum", ptr(hu), ptr(lm), ptr(out), B, H, W, float(mediastinum_lower), float(mediastinum_upper), sp, sb,
+             stream_ptr())
+    return out[0] if squeeze else out
 
 
 def detect_bone(hu_volume, lung_mask, bone_threshold=200, spine_margin_ratio=0.25):
-    raise NotImplementedError("detect_bone needs the convex-hull rasterisation (ConvexHull + matplotlib Path.contains_points "
-                              "semantics) -- second half of SURVEY 8f N2, not built; there is deliberately no approximate stand-in")
+    """reference modules/mask_generator.py:173-311."""
+    hu, lm, squeeze = _pair(hu_volume, lung_mask)
+    B, H, W = hu.shape
+    spine_start = int(H * (1 - spine_margin_ratio))          # mask_generator.py:219 (python float arithmetic)
+    with torch.cuda.device(hu.device):
+        out = torch.empty((B, H, W), dtype=torch.uint8, device=hu.device)
+        buf, sp, sb = _scratch(B, H, W, hu.device)
+        call("ducosy_detect_bone", ptr(hu), ptr(lm), ptr(out), B, H, W, float(bone_threshold), int(spine_start), sp, sb, stream_ptr())
+    return out[0] if squeeze else out
 
 
-def generate_anatomical_masks(hu_image, mask_types=("lung", "lung_vessel")):
-    """reference modules/mask_generator.py:313-347 for the mask types that are built ('lung', 'lung_vessel')."""
+def generate_anatomical_masks(hu_image, mask_types=("lung", "mediastinum", "bone", "lung_vessel")):
+    """reference modules/mask_generator.py:313-347."""
     masks = {}
     lung_mask = detect_lung(hu_image)
     if "lung" in mask_types:

@@ -308,6 +308,23 @@ int ducosy_detect_lung(const float* hu, uint8_t* lung_mask, int B, int H, int W,
  * other slices. */
 int ducosy_detect_lung_vessels(const float* hu, const uint8_t* lung_mask, uint8_t* vessel_mask, int B, int H, int W,
                                float vessel_lower, float vessel_upper, void* scratch, size_t scratch_bytes, ducosy_stream_t stream);
+/* Second half of modules/mask_generator.py: the convex hull of a slice's lung pixels and the two masks built on it.
+ * ducosy_lung_hull: hull_mask = Path(ConvexHull(argwhere(lung == 1)).vertices).contains_points(every pixel)
+ * (mask_generator.py:115-127); the vertices are scipy's (strict corners, counter-clockwise, (row, col)), the rasterisation is
+ * matplotlib's crossings test restated (PARITY UNPINNED: matplotlib absent).  Slices with fewer than 3 lung pixels or a
+ * degenerate (collinear) set get hull_mask = lung_mask and nverts = 0, the reference's fallback.  verts (optional): int32
+ * [B][2H+4][2], nverts (optional): int32 [B].
+ * ducosy_detect_mediastinum (mask_generator.py:100-170): (hull - lung) & (lower <= hu <= upper) on slices with >= 2 lung
+ * components, body area > 0 and lung / body area >= 0.1.
+ * ducosy_detect_bone (mask_generator.py:173-311): (hu >= threshold) & (hu > -1000), minus hull & ~lung above row
+ * spine_start_row (= int(H * (1 - spine_margin_ratio)), computed by the caller in float64), components of the candidates that
+ * still touch the remainder restored whole, holes filled. */
+int ducosy_lung_hull(const uint8_t* lung_mask, uint8_t* hull_mask, int32_t* verts, int32_t* nverts, int B, int H, int W, void* scratch,
+                     size_t scratch_bytes, ducosy_stream_t stream);
+int ducosy_detect_mediastinum(const float* hu, const uint8_t* lung_mask, uint8_t* mediastinum_mask, int B, int H, int W, float lower,
+                              float upper, void* scratch, size_t scratch_bytes, ducosy_stream_t stream);
+int ducosy_detect_bone(const float* hu, const uint8_t* lung_mask, uint8_t* bone_mask, int B, int H, int W, float bone_threshold,
+                       int spine_start_row, void* scratch, size_t scratch_bytes, ducosy_stream_t stream);
 
 /* ---------------------------------------------------------------- whole-generator entry points */
 

@@ -738,3 +738,125 @@ def metric_ts(img1, img2):
         mx = np.max([np.abs(g1).max(), np.abs(g2).max()])
         out.append(1.0 - (diff / mx if mx > 0 else 0))
     return np.mean(out), out
+
+
+# --------------------------------------------------------------------------------------
+# anatomical masks, second half: convex hull of the lungs (mediastinum / bone masks)
+# --------------------------------------------------------------------------------------
+def mask_test_slices_bone(B: int, H: int = 256, W: int = 256, seed: int = 0) -> np.ndarray:
+    """``mask_test_slices`` plus bone-range structures placed to hit every branch of detect_bone: a spine disc inside the
+    preserved bottom quarter, ribs outside the lung hull, a calcification between the lungs (inside the hull: removed), and a
+    bridge that connects an inside-hull piece to a rib (restored by the region growing); soft tissue between the lungs for the
+    mediastinum mask."""
+    rng = np.random.Generator(np.random.PCG64(seed + 977))
+    hu = mask_test_slices(B, H, W, seed).copy()
+    yy, xx = np.mgrid[0:H, 0:W].astype(np.float32)
+    cy, cx = H / 2, W / 2
+    for b in range(B):
+        if b % 5 == 4:
+            continue
+        disc = lambda y, x, r: (yy - y) ** 2 + (xx - x) ** 2 <= r * r
+        hu[b][disc(cy + 0.30 * H, cx, 0.045 * H)] = 500.0                                   # spine (row > 0.75 H)
+        hu[b][disc(cy + 0.30 * H, cx, 0.015 * H)] = 30.0                                    # spinal canal: a hole to fill
+        for sgn in (-1, 1):
+            for k in range(5):                                                              # ribs around the lungs
+                ang = np.deg2rad(-60 + 30 * k)
+                ry, rx = cy + 0.33 * H * np.sin(ang), cx + sgn * 0.41 * W * np.cos(ang)
+                hu[b][disc(ry, rx, 0.012 * H + 1)] = 350.0 + 40 * k
+        hu[b][disc(cy - 0.05 * H, cx, 0.02 * H)] = 420.0                                    # calcification between the lungs
+        hu[b][disc(cy + 0.10 * H, cx + 0.01 * W, 0.015 * H)] = 260.0
+        if b % 2 == 0:                                                                      # bridge: inside-hull bone joined to a rib
+            y0 = int(cy - 0.33 * H * np.sin(np.deg2rad(60)))
+            x0, x1 = int(cx - 0.41 * W * np.cos(np.deg2rad(60))), int(cx - 0.10 * W)
+            hu[b][y0 - 1:y0 + 2, min(x0, x1):max(x0, x1)] = 300.0
+        hu[b] += (rng.standard_normal((H, W)) * 0.0).astype(np.float32)
+    return hu
+
+
+def path_contains_points(verts: np.ndarray, points: np.ndarray) -> np.ndarray:
+    """``matplotlib.path.Path(verts).contains_points(points)`` (radius 0, no codes: the polyline is closed implicitly), restated
+    from matplotlib's ``point_in_path_impl`` (src/_path.h) -- the crossings test with its exact inequality conventions:
+        yflag = (vertex_y >= ty);  for an edge whose end points straddle ty:
+        if ((y1 - ty) * (x0 - x1) >= (x1 - tx) * (y0 - y1)) == yflag1: inside ^= 1
+    PARITY UNPINNED: matplotlib is absent here; only points exactly on the boundary depend on these conventions."""
+    v = np.asarray(verts, dtype=np.float64)
+    tx, ty = np.asarray(points, dtype=np.float64).T
+    inside = np.zeros(len(tx), dtype=bool)
+    n = len(v)
+    for i in range(n):
+        x0, y0 = v[i]
+        x1, y1 = v[(i + 1) % n]
+        f0, f1 = y0 >= ty, y1 >= ty
+        hit = (f0 != f1) & ((((y1 - ty) * (x0 - x1)) >= ((x1 - tx) * (y0 - y1))) == f1)
+        inside ^= hit
+    return inside
+
+
+def mask_convex_hull(lung_slice: np.ndarray):
+    """The hull rasterisation shared by detect_mediastinum / detect_bone (mask_generator.py:115-127,204-216): returns
+    (hull mask uint8, ok) -- ok False where the reference falls into its ``except`` / ``len(lung_coords) < 3`` branches."""
+    from scipy.spatial import ConvexHull
+    coords = np.argwhere(lung_slice == 1)
+    if len(coords) < 3:
+        return lung_slice.copy(), False
+    try:
+        hull = ConvexHull(coords)
+    except Exception:
+        return lung_slice.copy(), False
+    H, W = lung_slice.shape
+    ys, xs = np.mgrid[:H, :W]
+    pts = np.vstack((ys.flatten(), xs.flatten())).T
+    return path_contains_points(coords[hull.vertices], pts).reshape(H, W).astype(np.uint8), True
+
+
+def _hull_slice_ok(lung_slice, body_slice):
+    """the plausibility test in front of every hull use (mask_generator.py:110-114)"""
+    from scipy import ndimage
+    _, num = ndimage.label(lung_slice)
+    body_area, lung_area = body_slice.sum(), lung_slice.sum()
+    return num >= 2 and body_area > 0 and (lung_area / body_area) >= 0.1
+
+
+def mask_detect_mediastinum(hu: np.ndarray, lung_mask: np.ndarray, mediastinum_lower=-300, mediastinum_upper=450) -> np.ndarray:
+    """modules/mask_generator.py:100-170 (3-D branch)."""
+    body = (hu > -1000).astype(np.uint8)
+    out = np.zeros_like(lung_mask, dtype=np.uint8)
+    for z in range(lung_mask.shape[0]):
+        if _hull_slice_ok(lung_mask[z], body[z]):
+            hull, _ = mask_convex_hull(lung_mask[z])
+            cand = hull - lung_mask[z]
+            cond = np.logical_and(hu[z] >= mediastinum_lower, hu[z] <= mediastinum_upper)
+            out[z] = np.logical_and(cand, cond).astype(np.uint8)
+    return out
+
+
+def mask_detect_bone(hu: np.ndarray, lung_mask: np.ndarray, bone_threshold=200, spine_margin_ratio=0.25) -> np.ndarray:
+    """modules/mask_generator.py:173-311 (3-D branch): bone candidates minus the lung hull's interior (outside the lungs, above
+    the preserved spine rows), components of the candidates that still touch the remainder restored, holes filled."""
+    from scipy import ndimage
+    body = (hu > -1000).astype(np.uint8)
+    cand = np.logical_and((hu >= bone_threshold).astype(np.uint8), body).astype(np.uint8)
+    bone = cand.copy()
+    for z in range(lung_mask.shape[0]):
+        if _hull_slice_ok(lung_mask[z], body[z]):
+            hull, ok = mask_convex_hull(lung_mask[z])
+            if ok:
+                height = lung_mask[z].shape[0]
+                spine = np.zeros_like(lung_mask[z], dtype=np.uint8)
+                spine[int(height * (1 - spine_margin_ratio)):, :] = 1
+                region = np.logical_and(np.logical_and(hull, 1 - lung_mask[z]), 1 - spine)
+                bone[z] = np.logical_and(bone[z], 1 - region).astype(np.uint8)
+    for z in range(bone.shape[0]):
+        removed = np.logical_and(cand[z], 1 - bone[z]).astype(np.uint8)
+        if removed.sum() == 0:
+            continue
+        combined = np.logical_or(bone[z], removed).astype(np.uint8)
+        labeled, _ = ndimage.label(combined)
+        keep = set(np.unique(labeled[bone[z] > 0]))
+        keep.discard(0)
+        for lab in keep:
+            bone[z] = np.logical_or(bone[z], np.logical_and(labeled == lab, hu[z] >= bone_threshold)).astype(np.uint8)
+    for z in range(bone.shape[0]):
+        if bone[z].sum() > 0:
+            bone[z] = ndimage.binary_fill_holes(bone[z]).astype(np.uint8)
+    return bone

@@ -14,9 +14,21 @@ OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "..", "tests", "g
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), ".."))
 from oracle import ducosy_oracle as orc  # noqa: E402
 
+class _Path:
+    """Stand-in for matplotlib.path.Path (absent here): contains_points is the ORACLE'S restatement of matplotlib's crossings test
+    (oracle.path_contains_points), so detect_mediastinum / detect_bone run the reference's own control flow, scipy's ConvexHull /
+    label / binary_fill_holes, and an UNPINNED rasterisation of the hull."""
+
+    def __init__(self, vertices):
+        self.vertices = np.asarray(vertices)
+
+    def contains_points(self, points):
+        return orc.path_contains_points(self.vertices, points)
+
+
 stub = types.ModuleType("matplotlib")
 stub_path = types.ModuleType("matplotlib.path")
-stub_path.Path = object
+stub_path.Path = _Path
 stub.path = stub_path
 sys.modules.setdefault("matplotlib", stub)
 sys.modules.setdefault("matplotlib.path", stub_path)
@@ -44,6 +56,25 @@ def main():
         out[f"lung_{name}"] = np.packbits(lung.astype(np.uint8))
         out[f"vessel_{name}"] = np.packbits(vessel.astype(np.uint8))
         print(name, "lung pixels", int(lung.sum()), "vessel pixels", int(vessel.sum()), "per slice", lung.reshape(B, -1).sum(1), vessel.reshape(B, -1).sum(1))
+    # second half of the row: the hull-based masks (bone-range structures added to the phantom)
+    for name, (B, H, W, seed) in {"c": (5, 256, 256, 3), "d": (3, 160, 224, 4)}.items():
+        hu = orc.mask_test_slices_bone(B, H, W, seed)
+        lung = ref.detect_lung(hu.copy())
+        med = ref.detect_mediastinum(hu.copy(), lung.copy())                 # reference, 3-D branch
+        bone = ref.detect_bone(hu.copy(), lung.copy())
+        for z in range(B):                                                   # reference, 2-D branch: same answer per slice
+            assert np.array_equal(ref.detect_mediastinum(hu[z].copy(), lung[z].copy()), med[z]), (name, z)
+            assert np.array_equal(ref.detect_bone(hu[z].copy(), lung[z].copy()), bone[z]), (name, z)
+        assert np.array_equal(med, orc.mask_detect_mediastinum(hu, lung)), name
+        assert np.array_equal(bone, orc.mask_detect_bone(hu, lung)), name
+        cand = (hu >= 200) & (hu > -1000)
+        assert med.sum() > 0 and 0 < bone.sum() and (bone.astype(bool) != cand).any(), "the slices must exercise the hull branches"
+        full = ref.generate_anatomical_masks(hu.copy())
+        assert all(np.array_equal(full[k], v) for k, v in (("lung", lung), ("mediastinum", med), ("bone", bone)))
+        out[f"shape_{name}"] = np.array([B, H, W, seed])
+        out[f"mediastinum_{name}"] = np.packbits(med.astype(np.uint8))
+        out[f"bone_{name}"] = np.packbits(bone.astype(np.uint8))
+        print(name, "mediastinum pixels", med.reshape(B, -1).sum(1), "bone pixels", bone.reshape(B, -1).sum(1), "candidates", cand.reshape(B, -1).sum(1))
     np.savez_compressed(os.path.join(OUT, "masks.npz"), **out)
     print("masks golden ok")
 

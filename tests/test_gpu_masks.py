@@ -91,8 +91,74 @@ def test_detect_lung_and_vessels_match_reference_golden(golden_dir):
         assert np.array_equal(one.cpu().numpy(), unpack(f"lung_{name}")[1])
         masks = mg.generate_anatomical_masks(hu, ("lung", "lung_vessel"))
         assert torch.equal(masks["lung"], lung) and torch.equal(masks["lung_vessel"], vessel)
-    with pytest.raises(NotImplementedError):
-        mg.detect_bone(hu, lung)
+
+
+def test_lung_hull_vertices_match_scipy_convex_hull():
+    """The GPU hull (per-row extremes + monotone chain) against scipy.spatial.ConvexHull on the lung masks of the phantom and on
+    random blobs: same strict corners, same counter-clockwise cyclic order; degenerate sets (empty, < 3 pixels, one row, one
+    diagonal) take the reference's fallback (hull == lung, no vertices)."""
+    from scipy.spatial import ConvexHull
+    from ducosy_gan_b200 import mask_generator as mg
+    rng = np.random.Generator(np.random.PCG64(5))
+    masks = [orc.mask_detect_lung(orc.mask_test_slices_bone(4, 192, 160, 2))]
+    blobs = np.zeros((6, 192, 160), np.uint8)
+    for b in range(4):
+        for _ in range(3 + 4 * b):
+            y, x, r = rng.integers(10, 180), rng.integers(10, 150), rng.integers(1, 12)
+            yy, xx = np.ogrid[:192, :160]
+            blobs[b][(yy - y) ** 2 + (xx - x) ** 2 <= r * r] = 1
+    blobs[4, 50, 20:90] = 1                                   # one row: collinear
+    blobs[5, np.arange(30, 90), np.arange(30, 90)] = 1        # one diagonal: collinear
+    masks.append(blobs)
+    masks.append(np.zeros((2, 192, 160), np.uint8))
+    masks[-1][1, 7, 9] = masks[-1][1, 100, 3] = 1             # two pixels
+    m = np.concatenate(masks)
+    hull, verts, nv = mg.lung_hull(torch.from_numpy(m).cuda(), return_vertices=True)
+    hull, verts, nv = hull.cpu().numpy(), verts.cpu().numpy(), nv.cpu().numpy()
+    seen_real = 0
+    for z in range(m.shape[0]):
+        coords = np.argwhere(m[z] == 1)
+        try:
+            want = coords[ConvexHull(coords).vertices] if len(coords) >= 3 else None
+        except Exception:
+            want = None
+        if want is None:
+            assert nv[z] == 0 and np.array_equal(hull[z], m[z]), z
+            continue
+        seen_real += 1
+        got = verts[z, :nv[z]]
+        assert len(got) == len(want), (z, len(got), len(want))
+        k = int(np.flatnonzero((want == got[0]).all(1))[0])
+        assert np.array_equal(np.roll(want, -k, axis=0), got), z          # same corners, same (counter-clockwise) cyclic order
+        ref_mask, ok = orc.mask_convex_hull(m[z])
+        assert ok and np.array_equal(hull[z], ref_mask), z                # rasterisation == the oracle's crossings test
+    assert seen_real >= 8
+
+
+def test_detect_mediastinum_and_bone_match_reference_golden(golden_dir):
+    """Second half of the row: masks made by the reference's own detect_mediastinum / detect_bone (hull rasterisation through
+    the oracle's restatement of matplotlib's contains_points: that step is parity-unpinned), 3-D and per-slice calls."""
+    from ducosy_gan_b200 import mask_generator as mg
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    for name in "cd":
+        B, H, W, seed = (int(v) for v in g[f"shape_{name}"])
+        hu = torch.from_numpy(orc.mask_test_slices_bone(B, H, W, seed)).cuda()
+        unpack = lambda key: np.unpackbits(g[key])[: B * H * W].reshape(B, H, W)
+        lung = mg.detect_lung(hu)
+        med, bone = mg.detect_mediastinum(hu, lung), mg.detect_bone(hu, lung)
+        assert np.array_equal(med.cpu().numpy(), unpack(f"mediastinum_{name}")), name
+        assert np.array_equal(bone.cpu().numpy(), unpack(f"bone_{name}")), name
+        assert np.array_equal(mg.detect_bone(hu[0], lung[0]).cpu().numpy(), unpack(f"bone_{name}")[0])
+        masks = mg.generate_anatomical_masks(hu)
+        assert list(masks) == ["lung", "mediastinum", "bone", "lung_vessel"]
+        assert torch.equal(masks["mediastinum"], med) and torch.equal(masks["bone"], bone)
+    # other parameters, training size, against the oracle
+    hu = orc.mask_test_slices_bone(4, 512, 512, seed=6)
+    dev = torch.from_numpy(hu).cuda()
+    lung = orc.mask_detect_lung(hu)
+    ldev = torch.from_numpy(lung).cuda()
+    assert np.array_equal(mg.detect_mediastinum(dev, ldev, -200, 300).cpu().numpy(), orc.mask_detect_mediastinum(hu, lung, -200, 300))
+    assert np.array_equal(mg.detect_bone(dev, ldev, 250, 0.4).cpu().numpy(), orc.mask_detect_bone(hu, lung, 250, 0.4))
 
 
 def test_detect_lung_and_vessels_at_training_size_and_other_parameters():

@@ -179,6 +179,24 @@ def test_oracle_masks_match_reference_golden(golden_dir):
         assert np.array_equal(orc.mask_detect_lung_vessels(hu, lung), unpack(f"vessel_{name}"))
 
 
+def test_oracle_hull_masks_match_reference_golden(golden_dir):
+    """SURVEY 8f N2 (second half): the oracle's detect_mediastinum / detect_bone restatements against masks the reference's own
+    functions produced with scipy's ConvexHull / label / binary_fill_holes and the oracle's contains_points (matplotlib absent:
+    that step is parity-unpinned); plus the crossings test itself on a square, where only boundary conventions can differ."""
+    g = np.load(os.path.join(golden_dir, "masks.npz"))
+    for name in "cd":
+        B, H, W, seed = (int(v) for v in g[f"shape_{name}"])
+        hu = orc.mask_test_slices_bone(B, H, W, seed)
+        unpack = lambda key: np.unpackbits(g[key])[: B * H * W].reshape(B, H, W)
+        lung = orc.mask_detect_lung(hu)
+        assert np.array_equal(orc.mask_detect_mediastinum(hu, lung), unpack(f"mediastinum_{name}"))
+        assert np.array_equal(orc.mask_detect_bone(hu, lung), unpack(f"bone_{name}"))
+    sq = np.array([[2, 2], [6, 2], [6, 6], [2, 6]])                     # counter-clockwise square
+    ys, xs = np.mgrid[:9, :9]
+    inside = orc.path_contains_points(sq, np.vstack((ys.ravel(), xs.ravel())).T).reshape(9, 9)
+    assert inside[3:6, 3:6].all() and not inside[:2].any() and not inside[7:].any() and not inside[:, :2].any() and not inside[:, 7:].any()
+
+
 def test_oracle_metrics_match_reference_golden(golden_dir):
     """the oracle's restatements of calculate.py:232-271,360-381 against values the reference's own functions
     produced (oracle/make_golden_metrics.py).  SSIM's core is skimage (absent): parity unpinned, see the oracle docstring."""
