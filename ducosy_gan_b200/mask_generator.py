@@ -1,6 +1,6 @@
-"""Anatomical masks for training batches on the GPU: the reference's
-``modules/mask_generator.py`` that are scipy.ndimage work -- connected components, hole filling, the lung mask and the
-lung-vessel mask -- bit-exact with scipy, on batches of HU slices that are already on the device.
+"""Anatomical masks for training batches on the GPU: the reference's ``modules/mask_generator.py``.
+First the scipy.ndimage work -- connected components, hole filling, the lung mask and the lung-vessel mask -- bit-exact with
+scipy, on batches of HU slices that are already on the device.
 
 The reference computes these per slice on the CPU inside the dataloader workers (``modules/dataset.py:129-158``, about 0.1 s per
 512x512 slice, MASK_GENERATION_GUIDE.md:140-142); at the step rates of the CUDA training path that caps the input pipeline
