@@ -1,6 +1,8 @@
 // Bandwidth-bound kernels around the tensor-core convolutions: weight packing, stem im2col (optionally fused
 // with the HU window), InstanceNorm finalize/apply (+ReLU, + padding writer), CBAM channel MLP, CBAM spatial
 // pooling / 7x7 attention conv, and the residual add.  NHWC 16-bit activations, 128-bit accesses.
+#include <cstdlib>
+
 #include "common.cuh"
 #include "input_fn.cuh"
 
@@ -372,8 +374,8 @@ __device__ __forceinline__ void affine8_split(uint4 rh, uint4 rl, const float* s
 }
 
 // kSplit (DUCOSY_F16X2): a pixel holds 2*C channels, the lo plane C channels behind the hi plane.
-template <typename T, bool kSplit>
-__global__ void __launch_bounds__(256)
+template <typename T, bool kSplit, bool kCap = true>
+__global__ void __launch_bounds__(256, (kSplit || !kCap) ? 1 : 4)   // 64 registers: the 4-CTAs-per-SM grid (row_grid) is ONE resident wave
 in_apply_pad_kernel(const T* __restrict__ y, const float* __restrict__ scale, const float* __restrict__ shift,
                     T* __restrict__ out, int B, int H, int W, int C, int pad, int pad_mode, int act) {
   pdl_prologue();
@@ -726,13 +728,18 @@ extern "C" int ducosy_in_apply_pad(const void* y, const float* scale, const floa
   DUCOSY_CHECK(C % 8 == 0 && pad >= 0 && pad < H && pad < W, DUCOSY_ERR_SHAPE, "in_apply_pad: C %% 8 != 0 or pad too large");
   DUCOSY_CHECK(al16(y) && al16(out_pad) && al16(scale) && al16(shift), DUCOSY_ERR_ALIGN, "in_apply_pad: 16-byte alignment");
   DUCOSY_CHECK(256 % (C / 8) == 0, DUCOSY_ERR_SHAPE, "in_apply_pad: C must be one of 8..2048 with C/8 dividing 256");
+  static const bool cap = []() { const char* e = getenv("DUCOSY_APPLY_CAP"); return e == nullptr || atoi(e) != 0; }();
   if (dtype == DUCOSY_F16X2)
     pdl(in_apply_pad_kernel<__half, true>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
         static_cast<const __half*>(y), scale, shift, static_cast<__half*>(out_pad), B, H, W, C, pad, pad_mode, act);
-  else
-    DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_apply_pad_kernel<T, false>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
-                                        static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
-                                        pad_mode, act)));
+  else if (cap)
+      DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_apply_pad_kernel<T, false, true>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
+                                          static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
+                                          pad_mode, act)));
+    else
+      DUCOSY_DISPATCH_DTYPE(dtype, T, (pdl(in_apply_pad_kernel<T, false, false>, row_grid(B * (H + 2 * pad)), 256, 0, (cudaStream_t)stream)(
+                                          static_cast<const T*>(y), scale, shift, static_cast<T*>(out_pad), B, H, W, C, pad,
+                                          pad_mode, act)));
   return check_launch("in_apply_pad_kernel");
 }
 
