@@ -82,6 +82,7 @@ SIGNATURES = {
     "ducosy_conv2d_wgrad_workspace_bytes": (_sz, [_i, _i, _i, _i, _i, _i, _i]),
     "ducosy_conv2d_wgrad_nhwc": (_i, [_p, _p, _i, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_conv2d_wgrad_nhwc_oihw": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
+    "ducosy_conv2d_wgrad_nhwc_oihw_acc": (_i, [_p, _p, _i, _p, _p, _i, _i, _i, _i, _i, _i, _i, _i, _p, _sz, _i, _p]),
     "ducosy_in_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ducosy_in_backward_pad": (_i, [_p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),
     "ducosy_in_backward_pad_folded": (_i, [_p, _i, _p, _p, _p, _p, _p, _i, _i, _i, _i, _i, _i, _i, _p]),

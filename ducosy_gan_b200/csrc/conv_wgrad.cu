@@ -198,7 +198,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ partial, float* __
     }
     for (; s < splits; ++s) a0 += partial[s * per_split + i];
     const float acc = (a0 + a1) + (a2 + a3);
-    if (oihw != 0) dw[((long long)o * Cin + c) * taps + tap] = acc * inv;
+    if (oihw == 2) dw[((long long)o * Cin + c) * taps + tap] += acc * inv;      // accumulate into an existing gradient (p.grad)
+    else if (oihw != 0) dw[((long long)o * Cin + c) * taps + tap] = acc * inv;
     else dw[((long long)o * taps + tap) * Cin + c] = acc;
   }
 }
@@ -333,6 +334,14 @@ extern "C" int ducosy_conv2d_wgrad_nhwc_oihw(const void* x_pad, const void* dy, 
                                              int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
                                              size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
   return conv2d_wgrad_impl(x_pad, dy, dy_pad, dw_oihw, 1, gs, B, Hp, Wp, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, dtype, stream);
+}
+
+// ... and ACCUMULATED into dw_oihw (dw += gradient * gs[1]): the destination is the parameter's existing .grad (a view of the
+// data-parallel gradient bucket), which saves autograd's own add kernel and the temporary per weight and generator pass.
+extern "C" int ducosy_conv2d_wgrad_nhwc_oihw_acc(const void* x_pad, const void* dy, int dy_pad, float* dw_oihw, const float* gs, int B,
+                                                 int Hp, int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace,
+                                                 size_t workspace_bytes, int dtype, ducosy_stream_t stream) {
+  return conv2d_wgrad_impl(x_pad, dy, dy_pad, dw_oihw, 2, gs, B, Hp, Wp, Cin, Cout, kh, kw, stride, workspace, workspace_bytes, dtype, stream);
 }
 
 // Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) without materialising the

@@ -308,8 +308,13 @@ class _GeneratorFunction(torch.autograd.Function):
         (out,) = ctx.saved_tensors
         saved = ctx.saved
         saved["out"] = out
+        # a leaf parameter that already holds a contiguous fp32 gradient on this device (the views of a data-parallel bucket, an
+        # earlier backward) lets the weight-gradient kernels accumulate into it directly; autograd then gets None for it
+        direct = os.environ.get("DUCOSY_WGRAD_DIRECT", "1") != "0"
+        grad_out = [p.grad if (direct and p.is_leaf and p.grad is not None and p.grad.dtype == torch.float32 and p.grad.is_contiguous()
+                               and p.grad.device == out.device and p.grad.shape == p.shape) else None for p in ctx.param_refs]
         with torch.cuda.device(out.device), ops.pack_cache(ctx.cache):
-            grads, dx = training.generator_backward(ctx.params, ctx.cfg, saved, dout, ctx.needs_input_grad[1])
+            grads, dx = training.generator_backward(ctx.params, ctx.cfg, saved, dout, ctx.needs_input_grad[1], grad_out)
             if dx is not None and ctx.in_shape[1] > 1:
                 full = torch.zeros(ctx.in_shape, dtype=torch.float32, device=out.device)
                 full[:, :1] = dx

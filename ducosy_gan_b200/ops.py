@@ -394,9 +394,10 @@ def conv2d_wgrad_nhwc(x_pad, dy, kh, kw, stride, dy_pad=0):
     return dw
 
 
-def conv2d_wgrad_oihw(x_pad, dy, kh, kw, stride, dy_pad=0, gs=None):
+def conv2d_wgrad_oihw(x_pad, dy, kh, kw, stride, dy_pad=0, gs=None, accumulate_into=None):
     """Weight gradient in the parameter's own layout, fp32 [Cout,Cin,kh,kw], true scale (times gs[1]): conv2d_wgrad_nhwc and
-    unpack_wgrad in one reduction pass."""
+    unpack_wgrad in one reduction pass.  ``accumulate_into``: an existing fp32 gradient of that shape (the parameter's ``.grad``)
+    that receives ``+= dW`` instead of a new tensor being returned (returns None)."""
     B, Hp, Wp, Cin = x_pad.shape
     _, Ho, Wo, Cout = dy.shape
     Ho, Wo = Ho - 2 * dy_pad, Wo - 2 * dy_pad
@@ -405,6 +406,11 @@ def conv2d_wgrad_oihw(x_pad, dy, kh, kw, stride, dy_pad=0, gs=None):
     with _dev(x_pad):
         need = lib.ducosy_conv2d_wgrad_workspace_bytes(B, Ho, Wo, Cin, Cout, kh, kw)
         ws = torch.empty(max(need, 16), dtype=torch.uint8, device=x_pad.device)
+        if accumulate_into is not None:
+            assert accumulate_into.shape == (Cout, Cin, kh, kw) and accumulate_into.dtype == torch.float32 and accumulate_into.is_contiguous()
+            call("ducosy_conv2d_wgrad_nhwc_oihw_acc", ptr(x_pad), ptr(dy), int(dy_pad), ptr(accumulate_into), ptr(gs), B, Hp, Wp, Cin,
+                 Cout, kh, kw, stride, ptr(ws), ws.numel(), dtype_code(x_pad.dtype), stream_ptr())
+            return None
         dw = torch.empty((Cout, Cin, kh, kw), dtype=torch.float32, device=x_pad.device)
         call("ducosy_conv2d_wgrad_nhwc_oihw", ptr(x_pad), ptr(dy), int(dy_pad), ptr(dw), ptr(gs), B, Hp, Wp, Cin, Cout, kh, kw, stride,
              ptr(ws), ws.numel(), dtype_code(x_pad.dtype), stream_ptr())

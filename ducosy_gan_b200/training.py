@@ -104,11 +104,17 @@ def generator_forward_train(params, cfg, x, dtype):
     return out, S
 
 
-def generator_backward(params, cfg, S, dout, want_dx=True):
+def generator_backward(params, cfg, S, dout, want_dx=True, grad_out=None):
     """dout fp32 [B,1,H,W] -> (list of fp32 parameter gradients in named_parameters() order, dx fp32 [B,1,H,W] | None).
-    Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant), returned as None."""
+    Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant), returned as None.
+    ``grad_out``: per parameter an existing gradient tensor (``p.grad``) or None; the 3x3 convolution weights of the residual
+    blocks and the down convolutions accumulate straight into theirs (``+=``, what autograd's AccumulateGrad would do with a
+    returned tensor) and come back as None."""
     _, num_blocks, use_cbam = cfg
     stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
+    if grad_out is None:
+        grad_out = [None] * len(params)
+    _, g_d1, g_d2, g_blocks, _, _, _ = _split_params(grad_out, num_blocks, use_cbam)
     dout = dout.to(torch.float32).contiguous()
     gs = ops.grad_scale(dout)
     zero = lambda p: None      # dead bias (in front of a non-affine InstanceNorm): exact zero gradient, materialised by the caller if needed
@@ -121,7 +127,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
     dr, dw_u1 = ops.upconv2x_backward(S["r_last"], dyu1, u1[0], gs)
 
     block_grads = []
-    for bp, sv in zip(reversed(blocks), reversed(S["blocks"])):
+    for bp, sv, gb in zip(reversed(blocks), reversed(S["blocks"]), reversed(g_blocks)):
         if use_cbam:
             dn, cbam_grads = ops.cbam_backward(sv, dr, bp[4], bp[5], bp[6], gs)
             dyb = ops.in_backward_pad(dn, sv["yb"], *sv["nb"], 2, ACT_NONE)
@@ -129,7 +135,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
             cbam_grads = []
             dyb = ops.in_backward_pad(dr, sv["yb"], *sv["nb"], 2, ACT_NONE)
         C = bp[0].shape[0]
-        dw_b = side(lambda: ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs), sv["pa"], dyb, gs)
+        dw_b = side(lambda: ops.conv2d_wgrad_oihw(sv["pa"], dyb, 3, 3, 1, dy_pad=2, gs=gs, accumulate_into=gb[2]), sv["pa"], dyb, gs)
         Wb = sv["ya"].shape[2]
         if Wb >= 8 and Wb & (Wb - 1) == 0:
             # the reflection adjoint of conv b's input padding is folded into the loads of the InstanceNorm backward
@@ -138,16 +144,16 @@ def generator_backward(params, cfg, S, dout, want_dx=True):
         else:
             dpa, _ = ops.conv3x3s1_dgrad(dyb, bp[2], PAD_REFLECT)
             dya = ops.in_backward_pad(dpa, sv["ya"], *sv["na"], 2, ACT_RELU)
-        dw_a = side(lambda: ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs), sv["r"], dya, gs)
+        dw_a = side(lambda: ops.conv2d_wgrad_oihw(sv["r"], dya, 3, 3, 1, dy_pad=2, gs=gs, accumulate_into=gb[0]), sv["r"], dya, gs)
         dr, _ = ops.conv3x3s1_dgrad(dya, bp[0], PAD_REFLECT, add=dr)     # conv path + skip connection
         block_grads.append([dw_a, zero(bp[1]), dw_b, zero(bp[3])] + cbam_grads)
     block_grads.reverse()
 
     dy2 = ops.in_backward_pad(dr, S["y2"], *S["n2"], 1, ACT_RELU)
-    dw_d2 = side(lambda: ops.conv2d_wgrad_oihw(S["p1"], dy2, 3, 3, 2, dy_pad=1, gs=gs), S["p1"], dy2, gs)
+    dw_d2 = side(lambda: ops.conv2d_wgrad_oihw(S["p1"], dy2, 3, 3, 2, dy_pad=1, gs=gs, accumulate_into=g_d2[0]), S["p1"], dy2, gs)
     dp1 = ops.convs2_dgrad_nhwc(dy2, d2[0])
     dy1 = ops.in_backward_pad(dp1, S["y1"], *S["n1"], 1, ACT_RELU)
-    dw_d1 = side(lambda: ops.conv2d_wgrad_oihw(S["p0"], dy1, 3, 3, 2, dy_pad=1, gs=gs), S["p0"], dy1, gs)
+    dw_d1 = side(lambda: ops.conv2d_wgrad_oihw(S["p0"], dy1, 3, 3, 2, dy_pad=1, gs=gs, accumulate_into=g_d1[0]), S["p0"], dy1, gs)
     dp0 = ops.convs2_dgrad_nhwc(dy1, d1[0])
     dy0 = ops.in_backward_pad(dp0, S["y0"], *S["n0"], 0, ACT_RELU)
     dw_stem, dx = ops.stem_backward(dy0, S["cols"], stem[0], gs, want_dx)

@@ -413,6 +413,11 @@ int ducosy_conv2d_wgrad_nhwc(const void* x_pad, const void* dy, int dy_pad, floa
 int ducosy_conv2d_wgrad_nhwc_oihw(const void* x_pad, const void* dy, int dy_pad, float* dw_oihw, const float* gs, int B, int Hp,
                                   int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes,
                                   int dtype, ducosy_stream_t stream);
+/* The same, ACCUMULATED into dw_oihw (dw += gradient * gs[1]) -- for a destination that already holds a gradient (the
+ * parameter's .grad inside a flat data-parallel bucket): no temporary, no separate add. */
+int ducosy_conv2d_wgrad_nhwc_oihw_acc(const void* x_pad, const void* dy, int dy_pad, float* dw_oihw, const float* gs, int B, int Hp,
+                                      int Wp, int Cin, int Cout, int kh, int kw, int stride, void* workspace, size_t workspace_bytes,
+                                      int dtype, ducosy_stream_t stream);
 
 /* Weight gradient of Upsample(x2 nearest) + Conv3x3(pad 1) (modules/model.py:108-109) on the SOURCE grid: the gradient of
  * the 16 pre-summed (phase, tap) blocks of ducosy_pack_upconv_weight (4/9 of the MACs of a wgrad over the up-sampled map,
