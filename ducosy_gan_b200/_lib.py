@@ -136,6 +136,7 @@ SIGNATURES = {
     "ducosy_cbam_channel_train": (_i, [_p] * 9 + [_i, _i, _p]),
     "ducosy_cbam_backward_scratch_bytes": (_sz, [_i, _i, _i, _i]),
     "ducosy_cbam_backward": (_i, [_p] * 20 + [_i, _i, _i, _i, _i, _p]),
+    "ducosy_cbam_backward_acc": (_i, [_p] * 20 + [_i, _i, _i, _i, _i, _p]),
     "ducosy_unpack_wgrad": (_i, [_p, _p, _i, _i, _i, _p, _p]),
     "ducosy_disc_last_backward_scratch_bytes": (_sz, []),
     "ducosy_disc_last_backward": (_i, [_p, _p, _p, _p, _p, _p, _p, _p, _i, _i, _i, _i, _p]),

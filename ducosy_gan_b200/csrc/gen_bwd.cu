@@ -839,14 +839,25 @@ cbam_channel_bwd_kernel(const float* __restrict__ pdca, int nblk, const float* _
   *cell = Cvt<T>::from_f(Cvt<T>::to_f(*cell) + dmx);
 }
 
-__global__ void cbam_param_reduce_kernel(const float* __restrict__ partial, int parts, int n, float* __restrict__ out,
-                                         const float* __restrict__ gs) {
+// the three CBAM parameter gradients of a block in ONE launch: fixed-order sums of the per-sample / per-CTA partials, true scale
+// (gs[1]); accumulate != 0: added to what the destinations hold (the parameters' existing .grad) instead of overwriting
+__global__ void cbam_param_reduce3_kernel(const float* __restrict__ pfc0, const float* __restrict__ pfc2, int parts_fc, int nfc,
+                                          const float* __restrict__ pdw, int parts_dw, float* __restrict__ dfc0,
+                                          float* __restrict__ dfc2, float* __restrict__ dwsa, const float* __restrict__ gs,
+                                          int accumulate) {
   pdl_prologue();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const float* part;
+  float* out;
+  int parts, n;
+  if (i < nfc) { part = pfc0; out = dfc0; parts = parts_fc; n = nfc; }
+  else if (i < 2 * nfc) { i -= nfc; part = pfc2; out = dfc2; parts = parts_fc; n = nfc; }
+  else if (i < 2 * nfc + 98) { i -= 2 * nfc; part = pdw; out = dwsa; parts = parts_dw; n = 98; }
+  else return;
   float a = 0.f;
-  for (int k = 0; k < parts; ++k) a += partial[(long long)k * n + i];
-  out[i] = a * gs[1];
+  for (int k = 0; k < parts; ++k) a += part[(long long)k * n + i];
+  a *= gs[1];
+  out[i] = accumulate ? out[i] + a : a;
 }
 
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad; modules/trainer.py:360-362): one fused pass over
@@ -1023,11 +1034,12 @@ extern "C" size_t ducosy_cbam_backward_scratch_bytes(int B, int H, int W, int C)
   return words * 4;
 }
 
-extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n, const float* shift_n,
-                                    const float* scale_v, const float* shift_v, const float* ca, const float* hidden,
-                                    const float* chmax, const float* pooled, const float* sa, const float* fc0, const float* fc2,
-                                    const float* wsa, void* dn, float* dfc0, float* dfc2, float* dwsa, float* scratch,
-                                    const float* gs, int B, int H, int W, int C, int dtype, ducosy_stream_t stream) {
+namespace {
+int cbam_backward_impl(const void* dout, const void* yb, const float* scale_n, const float* shift_n,
+                       const float* scale_v, const float* shift_v, const float* ca, const float* hidden,
+                       const float* chmax, const float* pooled, const float* sa, const float* fc0, const float* fc2,
+                       const float* wsa, void* dn, float* dfc0, float* dfc2, float* dwsa, float* scratch,
+                       const float* gs, int B, int H, int W, int C, int dtype, ducosy_stream_t stream, int accumulate) {
   DUCOSY_CHECK(dout && yb && scale_n && shift_n && scale_v && shift_v && ca && hidden && chmax && pooled && sa && fc0 && fc2 &&
                    wsa && dn && dfc0 && dfc2 && dwsa && scratch && gs, DUCOSY_ERR_ARG, "cbam_backward: null pointer");
   DUCOSY_CHECK(C == kCbamC, DUCOSY_ERR_SHAPE, "cbam_backward: built for the %d-channel residual blocks (got %d)", kCbamC, C);
@@ -1060,10 +1072,28 @@ extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const floa
                                                                                   static_cast<T*>(dn), pfc0, pfc2, HW)));
   DUCOSY_TRY(check_launch("cbam_channel_bwd_kernel"));
   const int nfc = C * Hd;
-  pdl(cbam_param_reduce_kernel, (nfc + 255) / 256, 256, 0, st)(pfc0, B, nfc, dfc0, gs);
-  pdl(cbam_param_reduce_kernel, (nfc + 255) / 256, 256, 0, st)(pfc2, B, nfc, dfc2, gs);
-  pdl(cbam_param_reduce_kernel, 1, 128, 0, st)(pdw, sablk, 98, dwsa, gs);
-  return check_launch("cbam_param_reduce_kernel");
+  pdl(cbam_param_reduce3_kernel, (2 * nfc + 98 + 255) / 256, 256, 0, st)(pfc0, pfc2, B, nfc, pdw, sablk, dfc0, dfc2, dwsa, gs, accumulate);
+  return check_launch("cbam_param_reduce3_kernel");
+}
+}  // namespace
+
+extern "C" int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n, const float* shift_n,
+                                    const float* scale_v, const float* shift_v, const float* ca, const float* hidden,
+                                    const float* chmax, const float* pooled, const float* sa, const float* fc0, const float* fc2,
+                                    const float* wsa, void* dn, float* dfc0, float* dfc2, float* dwsa, float* scratch,
+                                    const float* gs, int B, int H, int W, int C, int dtype, ducosy_stream_t stream) {
+  return cbam_backward_impl(dout, yb, scale_n, shift_n, scale_v, shift_v, ca, hidden, chmax, pooled, sa, fc0, fc2, wsa, dn, dfc0, dfc2,
+                            dwsa, scratch, gs, B, H, W, C, dtype, stream, 0);
+}
+// The same with the three parameter gradients ACCUMULATED into dfc0 / dfc2 / dwsa (+=): the destinations are the parameters'
+// existing .grad tensors.
+extern "C" int ducosy_cbam_backward_acc(const void* dout, const void* yb, const float* scale_n, const float* shift_n,
+                                        const float* scale_v, const float* shift_v, const float* ca, const float* hidden,
+                                        const float* chmax, const float* pooled, const float* sa, const float* fc0, const float* fc2,
+                                        const float* wsa, void* dn, float* dfc0, float* dfc2, float* dwsa, float* scratch,
+                                        const float* gs, int B, int H, int W, int C, int dtype, ducosy_stream_t stream) {
+  return cbam_backward_impl(dout, yb, scale_n, shift_n, scale_v, shift_v, ca, hidden, chmax, pooled, sa, fc0, fc2, wsa, dn, dfc0, dfc2,
+                            dwsa, scratch, gs, B, H, W, C, dtype, stream, 1);
 }
 
 extern "C" int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr,

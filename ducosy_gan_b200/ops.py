@@ -635,9 +635,10 @@ def cbam_forward_train(sv, stats, fc0, fc2, wsa, out_mode):
     return residual_apply_pad(yb, scale_v, shift_v, sa, sv["r"], 1, 1, out_mode)
 
 
-def cbam_backward(sv, dout, fc0, fc2, wsa, gs):
+def cbam_backward(sv, dout, fc0, fc2, wsa, gs, accumulate_into=None):
     """CBAM backward: dout [B,H,W,C] 16-bit (gradient of the block output) -> (dn 16-bit gradient w.r.t. InstanceNorm(yb),
-    [d fc.0.weight, d fc.2.weight, d spatial conv weight] fp32 true scale)."""
+    [d fc.0.weight, d fc.2.weight, d spatial conv weight] fp32 true scale).  ``accumulate_into``: the three parameters' existing
+    fp32 gradients (all three or none), which receive ``+=`` -- the list returned is then [None, None, None]."""
     yb = sv["yb"]
     B, H, W, Cn = yb.shape
     dev = yb.device
@@ -645,14 +646,19 @@ def cbam_backward(sv, dout, fc0, fc2, wsa, gs):
     with _dev(yb):
         scratch = torch.empty(lib.ducosy_cbam_backward_scratch_bytes(B, H, W, Cn) // 4, dtype=torch.float32, device=dev)
         dn = torch.empty_like(yb)
-        dfc0 = torch.empty(tuple(fc0.shape), dtype=torch.float32, device=dev)
-        dfc2 = torch.empty(tuple(fc2.shape), dtype=torch.float32, device=dev)
-        dwsa = torch.empty(tuple(wsa.shape), dtype=torch.float32, device=dev)
-        call("ducosy_cbam_backward", ptr(dout), ptr(yb), ptr(sv["nb"][0]), ptr(sv["nb"][1]), ptr(sv["nv"][0]), ptr(sv["nv"][1]),
+        acc = accumulate_into is not None and all(g is not None for g in accumulate_into)
+        if acc:
+            dfc0, dfc2, dwsa = accumulate_into
+            assert dfc0.shape == fc0.shape and dfc2.shape == fc2.shape and dwsa.shape == wsa.shape
+        else:
+            dfc0 = torch.empty(tuple(fc0.shape), dtype=torch.float32, device=dev)
+            dfc2 = torch.empty(tuple(fc2.shape), dtype=torch.float32, device=dev)
+            dwsa = torch.empty(tuple(wsa.shape), dtype=torch.float32, device=dev)
+        call("ducosy_cbam_backward_acc" if acc else "ducosy_cbam_backward", ptr(dout), ptr(yb), ptr(sv["nb"][0]), ptr(sv["nb"][1]), ptr(sv["nv"][0]), ptr(sv["nv"][1]),
              ptr(sv["ca"]), ptr(sv["hidden"]), ptr(sv["chmax"]), ptr(sv["pooled"]), ptr(sv["sa"]), ptr(_f32c(fc0)), ptr(_f32c(fc2)),
              ptr(_f32c(wsa)), ptr(dn), ptr(dfc0), ptr(dfc2), ptr(dwsa), ptr(scratch), ptr(gs), B, H, W, Cn, dtype_code(yb.dtype),
              stream_ptr())
-    return dn, [dfc0, dfc2, dwsa]
+    return dn, ([None, None, None] if acc else [dfc0, dfc2, dwsa])
 
 
 # ------------------------------------------------------------------ stand-alone building blocks (NCHW fp32, reference layout)

@@ -108,7 +108,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True, grad_out=None):
     """dout fp32 [B,1,H,W] -> (list of fp32 parameter gradients in named_parameters() order, dx fp32 [B,1,H,W] | None).
     Biases in front of an InstanceNorm receive an exact zero (the norm removes any per-channel constant), returned as None.
     ``grad_out``: per parameter an existing gradient tensor (``p.grad``) or None; the 3x3 convolution weights of the residual
-    blocks and the down convolutions accumulate straight into theirs (``+=``, what autograd's AccumulateGrad would do with a
+    blocks and the down convolutions and the CBAM parameters accumulate straight into theirs (``+=``, what autograd's AccumulateGrad would do with a
     returned tensor) and come back as None."""
     _, num_blocks, use_cbam = cfg
     stem, d1, d2, blocks, u1, u2, outp = _split_params(params, num_blocks, use_cbam)
@@ -129,7 +129,7 @@ def generator_backward(params, cfg, S, dout, want_dx=True, grad_out=None):
     block_grads = []
     for bp, sv, gb in zip(reversed(blocks), reversed(S["blocks"]), reversed(g_blocks)):
         if use_cbam:
-            dn, cbam_grads = ops.cbam_backward(sv, dr, bp[4], bp[5], bp[6], gs)
+            dn, cbam_grads = ops.cbam_backward(sv, dr, bp[4], bp[5], bp[6], gs, accumulate_into=gb[4:7])
             dyb = ops.in_backward_pad(dn, sv["yb"], *sv["nb"], 2, ACT_NONE)
         else:
             cbam_grads = []

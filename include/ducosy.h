@@ -230,6 +230,12 @@ int ducosy_cbam_backward(const void* dout, const void* yb, const float* scale_n,
                          const float* sa, const float* fc0, const float* fc2, const float* wsa, void* dn, float* dfc0, float* dfc2,
                          float* dwsa, float* scratch, const float* gs, int B, int H, int W, int C, int dtype,
                          ducosy_stream_t stream);
+/* The same with the three parameter gradients ACCUMULATED (+=) into dfc0 / dfc2 / dwsa (the parameters' existing .grad). */
+int ducosy_cbam_backward_acc(const void* dout, const void* yb, const float* scale_n, const float* shift_n, const float* scale_v,
+                             const float* shift_v, const float* ca, const float* hidden, const float* chmax, const float* pooled,
+                             const float* sa, const float* fc0, const float* fc2, const float* wsa, void* dn, float* dfc0, float* dfc2,
+                             float* dwsa, float* scratch, const float* gs, int B, int H, int W, int C, int dtype,
+                             ducosy_stream_t stream);
 /* torch.optim.Adam step (no weight decay, no amsgrad) as constructed at modules/trainer.py:360-362: fp32 param / grad /
  * exp_avg / exp_avg_sq of n elements updated in one pass; step counts from 1. */
 int ducosy_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
