@@ -112,3 +112,45 @@ def test_read_series_orders_by_filename_and_write_series_names(tmp_path):
     dio.write_series(slices, vol + 1, str(out), workers=2)
     assert sorted(os.listdir(out)) == ["0000.dcm", "0001.dcm", "0002.dcm"]                              # generate.py:285
     assert int(dio.read_dicom(str(out / "0002.dcm")).pixel_array()[0, 0]) == 301
+
+
+class _FakeSynth:
+    """Stands in for DualHUSynthesizer on the CPU: records the (slope, intercept) groups it is called with."""
+    device = "cpu"
+
+    def __init__(self):
+        self.calls = []
+
+    def synthesize_volume(self, vol, slope, intercept, postprocess=False):
+        self.calls.append((tuple(vol.shape), slope, intercept))
+        return vol + 7
+
+
+def test_synthesize_series_groups_slices_by_rescale_and_rejects_other_sizes(tmp_path):
+    import torch
+    src = tmp_path / "s"
+    src.mkdir()
+    px = np.zeros((512, 512), np.int16)
+    for i, (sl, ic) in enumerate([("1", "-1024"), ("1", "-1024"), ("1", "-1000"), ("2", "-1000"), ("2", "-1000")]):
+        (src / f"{i:03d}.dcm").write_bytes(_file(px + i, slope=sl, intercept=ic))
+    fake = _FakeSynth()
+    merged, slices = dio.synthesize_series(fake, str(src), str(tmp_path / "o"), postprocess=False, workers=2)
+    assert fake.calls == [((2, 512, 512), 1.0, -1024.0), ((1, 512, 512), 1.0, -1000.0), ((2, 512, 512), 2.0, -1000.0)]
+    assert torch.equal(merged[:, 0, 0], torch.arange(5, dtype=torch.int16) + 7)
+    assert int(dio.read_dicom(str(tmp_path / "o" / "0004.dcm")).pixel_array()[5, 5]) == 11
+    small = tmp_path / "small"
+    small.mkdir()
+    (small / "a.dcm").write_bytes(_file(np.zeros((8, 8), np.int16)))
+    with pytest.raises(dio.DicomError):
+        dio.synthesize_series(fake, str(small), str(tmp_path / "o2"), postprocess=False)
+
+
+def test_read_series_rejects_unsigned_values_beyond_int16(tmp_path):
+    src = tmp_path / "u"
+    src.mkdir()
+    px = np.zeros((8, 8), np.uint16)
+    px[0, 0] = 40000
+    raw = _file(px.view(np.int16), signed=False)
+    (src / "a.dcm").write_bytes(raw)
+    with pytest.raises(dio.DicomError):
+        dio.read_series(str(src))
